@@ -1,0 +1,156 @@
+/*
+ * sdrjfm_b200 — C ABI of the B200-native FM demodulation path.
+ *
+ * This is the drop-in boundary for ONE path of JvanKatwijk/sdr-j-fm: what
+ * fmProcessor::run does between deviceHandler::getSamples and audioSink::putSample /
+ * rdsDecoder::doDecode.  Plain pointers and sizes only; no C++/Qt/torch types; never
+ * throws; every entry point returns an int status (0 = SDRJFM_OK) unless stated.
+ * One calling thread per handle (the reference has exactly one: the fmProcessor QThread).
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the
+ * reference tree).  INTEGRATION.md shows the reference-side binding.
+ *
+ * Sample formats (same as the reference):
+ *   IQ in      : interleaved float32 (re, im) = std::complex<float>, what
+ *                deviceHandler::getSamples delivers (devices/device-handler.h:72-75)
+ *   audio out  : interleaved float32 (left, right) = DSPCOMPLEX re=L im=R, what
+ *                audioSink::putSample takes (includes/output/audiosink.h:44)
+ *   rds out    : interleaved float32 complex at 24 kHz, what rdsDecoder::doDecode takes
+ *                (includes/rds/rds-decoder.h:67-69)
+ */
+#ifndef SDRJFM_B200_H
+#define SDRJFM_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDRJFM_OK              0
+#define SDRJFM_ERR_ARG        -1   /* bad argument                                        */
+#define SDRJFM_ERR_CUDA       -2   /* a CUDA call failed; see sdrjfm_last_error           */
+#define SDRJFM_ERR_NO_DEVICE  -3   /* no sm_100 device: this library has NO CPU fallback  */
+#define SDRJFM_ERR_CAPACITY   -4   /* n_in exceeds max_samples_per_call                   */
+#define SDRJFM_ERR_UNSUPPORTED -5  /* setting not implemented on the GPU path             */
+
+typedef struct sdrjfm_handle sdrjfm_handle;
+
+/* Constructor arguments of fmProcessor (src/fm/fm-processor.cpp:48-63) that matter to
+ * the arithmetic, plus the batch shape.  Zero-initialise, then fill.                    */
+typedef struct sdrjfm_config {
+    int32_t input_rate;            /* inputRate, 2304000 (includes/fm-constants.h:35)    */
+    int32_t fm_rate;               /* fmRate, 192000 (radio.cpp:68)                      */
+    int32_t working_rate;          /* workingRate, 48000 (radio.cpp:233)                 */
+    int32_t audio_rate;            /* audioRate, 48000 (main.cpp:42)                     */
+    int32_t n_streams;             /* independent IQ streams handled by this handle (>=1)*/
+    int32_t device;                /* CUDA device ordinal                                */
+    int64_t max_samples_per_call;  /* per stream; sizes the device buffers               */
+    int32_t keep_taps;             /* 1: keep fm-rate intermediates for sdrjfm_read_tap  */
+    int32_t reserved;
+} sdrjfm_config;
+
+/* fmProcessor::SMetaData (includes/fm/fm-processor.h:91-101) per stream, plus the RF DC
+ * estimate and carrier level the GUI derives its read-outs from.                        */
+typedef struct sdrjfm_meta {
+    float   dc_rf_re, dc_rf_im;    /* RfDC (fm-processor.cpp:425)                        */
+    float   dc_rf_db;              /* DcValRf (fm-processor.cpp:668-670)                 */
+    float   dc_if;                 /* DcValIf = fm_afc (fm-demodulator.cpp:197)          */
+    float   carrier_ampl;          /* am_carr_ampl (fm-demodulator.cpp:130)              */
+    float   pss_phase_shift_deg;   /* PssPhaseShiftDegree (:673)                         */
+    float   pss_phase_change;      /* PssPhaseChange (:675)                              */
+    int32_t pss_state;             /* EPssState 0 OFF, 1 ANALYZING, 2 ESTABLISHED (:676) */
+    float   pilot_lock_strength;   /* PilotPllLockStrength (:666)                        */
+    int32_t pilot_locked;          /* PilotPllLocked                                     */
+    float   peak_left_db, peak_right_db; /* evaluatePeakLevel (:772-798), last interval  */
+} sdrjfm_meta;
+
+/* intermediate taps (fm rate unless noted) readable after a process call when keep_taps */
+enum sdrjfm_tap {
+    SDRJFM_TAP_FM_Z = 0,       /* complex: after fmBand_2 (fm-processor.cpp:474)         */
+    SDRJFM_TAP_DEMOD = 1,      /* float  : fm_Demodulator::demodulate (:497)             */
+    SDRJFM_TAP_PILOT_PHASE = 2,/* float  : pilotRecovery::getPilotPhase (:695)           */
+    SDRJFM_TAP_LOCKED = 3,     /* uint8  : pilotRecovery::isLocked (:697)                */
+    SDRJFM_TAP_PSS_DELAY = 4,  /* float  : pilotDelayPSS (:716)                          */
+    SDRJFM_TAP_LR = 5,         /* complex: (left,right) after the selector (:527-549)    */
+    SDRJFM_TAP_AUDIO192 = 6,   /* complex: after de-emphasis and gain (:594-595,:630)    */
+    SDRJFM_TAP_RDS_CPLX = 7,   /* complex: rdsDataCplx (:754)                            */
+    SDRJFM_TAP_RDS24 = 8       /* complex @24 kHz: rdsSample (:553)                      */
+};
+
+/* --- life cycle: replaces `new fmProcessor (...)` / `delete` (radio.cpp:908-949, 629-644) */
+sdrjfm_handle *sdrjfm_create (const sdrjfm_config *cfg, int *status);
+int  sdrjfm_destroy (sdrjfm_handle *h);
+const char *sdrjfm_last_error (const sdrjfm_handle *h);   /* h may be NULL: create errors */
+const char *sdrjfm_version (void);
+
+/* --- data path: replaces the body of fmProcessor::run (src/fm/fm-processor.cpp:387-686).
+ * HOST buffers.  iq: n_streams rows of n_in complex samples, row r at iq + 2*r*in_pitch
+ * floats (in_pitch in complex samples, >= n_in).  Stateful across calls; any n_in >= 0.
+ * audio: n_streams rows, row pitch audio_pitch complex samples, at working_rate;
+ * rds24: n_streams rows, row pitch rds_pitch, at 24 kHz.  audio/rds24/meta may be NULL.
+ * *n_audio / *n_rds receive the per-stream counts produced by THIS call (equal for all
+ * streams: they depend on the sample count only, never on content).                     */
+int  sdrjfm_process (sdrjfm_handle *h,
+                     const float *iq, int64_t n_in, int64_t in_pitch,
+                     float *audio, int64_t audio_pitch, int64_t *n_audio,
+                     float *rds24, int64_t rds_pitch, int64_t *n_rds,
+                     sdrjfm_meta *meta /* [n_streams] */);
+
+/* Same, with DEVICE pointers (inputs already resident in HBM, outputs left in HBM):
+ * the zero-copy form used by batch replay and by bench.py's device-resident timing.
+ * Asynchronous on the handle's stream; sdrjfm_sync waits.                               */
+int  sdrjfm_process_device (sdrjfm_handle *h,
+                            const float *d_iq, int64_t n_in, int64_t in_pitch,
+                            float *d_audio, int64_t audio_pitch, int64_t *n_audio,
+                            float *d_rds24, int64_t rds_pitch, int64_t *n_rds);
+int  sdrjfm_sync (sdrjfm_handle *h);
+int  sdrjfm_get_meta (sdrjfm_handle *h, sdrjfm_meta *meta /* [n_streams] */);
+/* copies tap `which` of stream `stream` from the LAST process call to host memory;
+ * returns the number of entries (complex entries for complex taps) or a negative status */
+int64_t sdrjfm_read_tap (sdrjfm_handle *h, int which, int32_t stream, void *out, int64_t cap);
+/* the cudaStream_t the handle launches on (for event timing by the caller)              */
+void *sdrjfm_cuda_stream (sdrjfm_handle *h);
+/* stage timing: runs only the decimating front end (DC/LO/FIR, the roofline kernel) on
+ * device input, without touching stream state.  For bench.py / ncu.                     */
+int  sdrjfm_run_frontend_only (sdrjfm_handle *h, const float *d_iq, int64_t n_in, int64_t in_pitch);
+/* number of kernel launches issued by the handle since creation                          */
+int64_t sdrjfm_launch_count (const sdrjfm_handle *h);
+
+/* --- settings: one per fmProcessor setter (includes/fm/fm-processor.h:122-157).  Applied
+ * at the next process call, to all streams — the reference applies them at the next
+ * 16384-sample block (fm-processor.cpp:397-413).                                         */
+int  sdrjfm_set_fm_mode (sdrjfm_handle *h, int32_t mode);          /* setfmMode: 0 Stereo 1 StereoPano 2 Mono */
+int  sdrjfm_set_fm_decoder (sdrjfm_handle *h, int32_t decoder);    /* setFMdecoder / fm_Demodulator::setDecoder: 1..6 */
+int  sdrjfm_set_sound_mode (sdrjfm_handle *h, int32_t selector);   /* setSoundMode: Channels enum */
+int  sdrjfm_set_stereo_panorama (sdrjfm_handle *h, int32_t pan);   /* setStereoPanorama 0..200 */
+int  sdrjfm_set_sound_balance (sdrjfm_handle *h, int32_t balance); /* setSoundBalance -100..100 */
+int  sdrjfm_set_deemphasis (sdrjfm_handle *h, int32_t usec);       /* setDeemphasis (>=1) */
+int  sdrjfm_set_volume_db (sdrjfm_handle *h, float db);            /* setVolume */
+int  sdrjfm_set_lf_cutoff (sdrjfm_handle *h, int32_t hz);          /* setlfcutoff (<=0: off) */
+int  sdrjfm_set_bandwidth (sdrjfm_handle *h, int32_t hz);          /* setBandwidth ("Off" -> 0) */
+int  sdrjfm_set_attenuation (sdrjfm_handle *h, float l, float r);  /* setAttenuation */
+int  sdrjfm_set_rds_mode (sdrjfm_handle *h, int32_t mode);         /* setfmRdsSelector: 0 off, 1..3 */
+int  sdrjfm_set_local_oscillator (sdrjfm_handle *h, int32_t hz);   /* set_localOscillator */
+int  sdrjfm_set_squelch_mode (sdrjfm_handle *h, int32_t mode);     /* set_squelchMode: 0 OFF only */
+int  sdrjfm_set_auto_mono (sdrjfm_handle *h, int32_t on);          /* setAutoMonoMode */
+int  sdrjfm_set_pss_mode (sdrjfm_handle *h, int32_t on);           /* setPSSMode */
+int  sdrjfm_set_dc_remove (sdrjfm_handle *h, int32_t on);          /* setDCRemove (also zeroes RfDC) */
+int  sdrjfm_trigger_frequency_change (sdrjfm_handle *h);           /* triggerFrequencyChange */
+int  sdrjfm_restart_pss_analyzer (sdrjfm_handle *h);               /* restartPssAnalyzer */
+
+/* --- shared tables (tap sets and LUTs) as ONE blob, so that rank 0 can design them and
+ * broadcast them (ncclBroadcast / torch.distributed.broadcast) to the other GPUs' ranks
+ * (SURVEY.md §8(e)).  export: host copy of the blob this handle uses; import: replace the
+ * handle's tables by a blob received from rank 0 (host memory).                          */
+/* host-only designer (no device needed): writes the blob for the given rates/filters into
+ * out (if cap suffices) and returns its size in bytes, or a negative status.             */
+int64_t sdrjfm_design_tables (int32_t input_rate, int32_t fm_rate, int32_t input_filter_hz,
+                              int32_t audio_lp_hz, void *out, int64_t cap);
+int64_t sdrjfm_tables_nbytes (const sdrjfm_handle *h);
+int  sdrjfm_tables_export (const sdrjfm_handle *h, void *out, int64_t cap);
+int  sdrjfm_tables_import (sdrjfm_handle *h, const void *blob, int64_t nbytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

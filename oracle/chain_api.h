@@ -1,0 +1,99 @@
+/*
+ * TEST INFRASTRUCTURE — not product code.
+ *
+ * Common C API of the two CPU checkers under oracle/:
+ *   - oracle/_ref/libsdrjfm_ref.so   : the reference's own DSP classes, compiled from
+ *                                      /root/reference where they lie, driven by
+ *                                      ref_harness.cpp (prefix  ref_)
+ *   - oracle/_build/libsdrjfm_oracle.so : our plain C++ restatement fm_oracle.cpp
+ *                                      (prefix  orc_)
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load these libraries.
+ *
+ * The chain restated is fmProcessor::run (src/fm/fm-processor.cpp:461-648) together with
+ * process_signal_with_rds (:689-759), with every GUI-pushed setting made explicit.
+ */
+#ifndef SDRJFM_CHAIN_API_H
+#define SDRJFM_CHAIN_API_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct chain_cfg {
+    int32_t input_rate;      /* 2304000 (fm-constants.h:35)                          */
+    int32_t fm_rate;         /* 192000  (radio.cpp:68)                               */
+    int32_t fm_mode;         /* 0 Stereo, 1 StereoPano, 2 Mono (fm-processor.h:107)  */
+    int32_t decoder;         /* 1 AM 2 PLL 3 MIXED 4 CBB 5 RBB 6 DIFF (fm-demodulator.cpp:27-32) */
+    int32_t sound_sel;       /* Channels enum, 0 = S_STEREO (fm-processor.h:112-114) */
+    int32_t rds_on;          /* rdsModus != RDS_OFF                                  */
+    int32_t auto_mono;       /* fm-processor.cpp:121                                 */
+    int32_t pss_on;          /* fm-processor.cpp:122                                 */
+    int32_t dc_remove;       /* fm-processor.cpp:134                                 */
+    int32_t input_filter_hz; /* 0 = off, else fmBandwidth in Hz (setBandwidth :232)  */
+    int32_t lf_cutoff_hz;    /* 0 = off, else setlfcutoff (:762)                     */
+    int32_t lo_hz;           /* set_localOscillator (:865)                           */
+    float   lgain, rgain;    /* setAttenuation (:351)                                */
+    int32_t deemph_us;       /* setDeemphasis (:291), 50                             */
+    float   volume_db;       /* setVolume (:299)                                     */
+    int32_t panorama;        /* setStereoPanorama (:277), 100                        */
+    int32_t balance;         /* setSoundBalance (:282), 0                            */
+} chain_cfg;
+
+/* Output taps. Any pointer may be NULL. Capacities are the caller's business:
+ * fm-rate taps need n_in/12 + 1 entries, rds24 needs n_in/96 + 1.                  */
+typedef struct chain_taps {
+    float   *fm_z;        /* complex, after fmBand_2 (fm-processor.cpp:474)          */
+    float   *demod;       /* theDemodulator->demodulate (:497)                       */
+    float   *pilot_phase; /* currentPilotPhase (:695)                                */
+    uint8_t *locked;      /* pilotRecover.isLocked() (:697)                          */
+    float   *pss_delay;   /* pilotDelayPSS after the sample (:716)                   */
+    float   *lr;          /* complex (left,right) after the selector (:527-549)      */
+    float   *audio192;    /* complex after de-emphasis and gain (:594-595,:630)      */
+    float   *rds_cplx;    /* complex rdsDataCplx @fm rate (:754)                     */
+    float   *rds24;       /* complex rdsSample @24 kHz (:553)                        */
+} chain_taps;
+
+typedef struct chain_meta {   /* SMetaData, fm-processor.h:91-101, as of the last sample */
+    float dc_rf_re, dc_rf_im; /* RfDC                                                   */
+    float dc_if;              /* fm_afc                                                 */
+    float carrier_ampl;       /* am_carr_ampl                                           */
+    float pss_phase_shift;    /* pilotDelayPSS                                          */
+    float pss_mean_error;     /* pPSS.get_mean_error()                                  */
+    int32_t pss_minimized;    /* pPSS.is_error_minimized()                              */
+    float pilot_lock_strength;/* pilotRecover.getLockedStrength()                       */
+    int32_t pilot_locked;
+} chain_meta;
+
+#define CHAIN_DECL(P)                                                                   \
+    void   *P##_create (const chain_cfg *cfg);                                          \
+    void    P##_destroy (void *h);                                                      \
+    /* returns fm-rate samples produced; *n_rds24 = 24 kHz samples produced */          \
+    int64_t P##_process (void *h, const float *iq, int64_t n_in,                        \
+                         const chain_taps *taps, int64_t *n_rds24);                     \
+    void    P##_get_meta (void *h, chain_meta *m);                                      \
+    /* table dumps used to pin the restatement bit for bit */                           \
+    int32_t P##_dump_taps (void *h, int which, float *out, int32_t cap);
+
+CHAIN_DECL(ref)
+CHAIN_DECL(orc)
+
+/* `which` for *_dump_taps (complex entries unless noted) */
+enum {
+    DUMP_FMBAND1 = 0,      /* 25 complex                      */
+    DUMP_FMBAND2 = 1,      /* 3 complex                       */
+    DUMP_RDSDECIM = 2,     /* 11 complex                      */
+    DUMP_INPUT_FILTER_FREQ = 3,  /* 65536 complex (frequency domain filterVector) */
+    DUMP_RDS_BP_FREQ = 4,  /* 32768 complex                   */
+    DUMP_PSS_LP_FREQ = 5,  /* 2048 complex                    */
+    DUMP_AUDIO_LP_FREQ = 6,/* 8192 complex                    */
+    DUMP_SINCOS = 7,       /* fm_rate complex (cos, sin)      */
+    DUMP_ATAN = 8,         /* 8 x 8193 floats (as 32772 complex slots) PPY PPX PNY PNX NPY NPX NNY NNX */
+    DUMP_CONSTS = 9        /* 8 floats: K_FM deemphAlpha volumeFactor omega gain pssAlpha pssLockAlpha rfDcAlpha */
+};
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,136 @@
+"""TEST INFRASTRUCTURE — ctypes loader for the two CPU checkers (oracle/chain_api.h).
+
+`load("ref")` -> oracle/_ref/libsdrjfm_ref.so   (reference classes + ref_harness.cpp)
+`load("orc")` -> oracle/_build/libsdrjfm_oracle.so (our restatement, fm_oracle.cpp)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module.  Nothing under the product package imports it.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class ChainCfg(C.Structure):
+    _fields_ = [
+        ("input_rate", C.c_int32), ("fm_rate", C.c_int32), ("fm_mode", C.c_int32),
+        ("decoder", C.c_int32), ("sound_sel", C.c_int32), ("rds_on", C.c_int32),
+        ("auto_mono", C.c_int32), ("pss_on", C.c_int32), ("dc_remove", C.c_int32),
+        ("input_filter_hz", C.c_int32), ("lf_cutoff_hz", C.c_int32), ("lo_hz", C.c_int32),
+        ("lgain", C.c_float), ("rgain", C.c_float), ("deemph_us", C.c_int32),
+        ("volume_db", C.c_float), ("panorama", C.c_int32), ("balance", C.c_int32),
+    ]
+
+
+class ChainTaps(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "fm_z", "demod", "pilot_phase", "locked", "pss_delay", "lr", "audio192",
+        "rds_cplx", "rds24")]
+
+
+class ChainMeta(C.Structure):
+    _fields_ = [
+        ("dc_rf_re", C.c_float), ("dc_rf_im", C.c_float), ("dc_if", C.c_float),
+        ("carrier_ampl", C.c_float), ("pss_phase_shift", C.c_float),
+        ("pss_mean_error", C.c_float), ("pss_minimized", C.c_int32),
+        ("pilot_lock_strength", C.c_float), ("pilot_locked", C.c_int32),
+    ]
+
+
+DEFAULTS = dict(input_rate=2304000, fm_rate=192000, fm_mode=0, decoder=3, sound_sel=0,
+                rds_on=0, auto_mono=1, pss_on=1, dc_remove=1, input_filter_hz=0,
+                lf_cutoff_hz=0, lo_hz=0, lgain=1.0, rgain=1.0, deemph_us=50,
+                volume_db=-6.0, panorama=100, balance=0)
+
+DUMP = dict(fmband1=0, fmband2=1, rdsdecim=2, input_filter_freq=3, rds_bp_freq=4,
+            pss_lp_freq=5, audio_lp_freq=6, sincos=7, atan=8, consts=9)
+
+_PATHS = {"ref": os.path.join(HERE, "_ref", "libsdrjfm_ref.so"),
+          "orc": os.path.join(HERE, "_build", "libsdrjfm_oracle.so")}
+
+
+def build(which=("oracle", "ref")):
+    """make the checkers (the `ref` target is a no-op when /root/reference is absent)."""
+    for tgt in which:
+        subprocess.run(["make", "-s", "-C", HERE, tgt], check=True)
+
+
+def available(prefix):
+    return os.path.exists(_PATHS[prefix])
+
+
+def make_cfg(**kw):
+    d = dict(DEFAULTS)
+    for k, v in kw.items():
+        if k not in d:
+            raise KeyError(k)
+        d[k] = v
+    return ChainCfg(**d)
+
+
+class Chain:
+    """One fmProcessor-equivalent instance of a CPU checker (stateful, streaming)."""
+
+    TAPS = ("fm_z", "demod", "pilot_phase", "locked", "pss_delay", "lr", "audio192",
+            "rds_cplx", "rds24")
+
+    def __init__(self, prefix, **cfg):
+        self.prefix = prefix
+        self.lib = C.CDLL(_PATHS[prefix])
+        f = lambda n: getattr(self.lib, f"{prefix}_{n}")
+        self._create, self._destroy = f("create"), f("destroy")
+        self._process, self._meta, self._dump = f("process"), f("get_meta"), f("dump_taps")
+        self._create.restype = C.c_void_p
+        self._create.argtypes = [C.POINTER(ChainCfg)]
+        self._destroy.argtypes = [C.c_void_p]
+        self._process.restype = C.c_int64
+        self._process.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(ChainTaps),
+                                  C.POINTER(C.c_int64)]
+        self._meta.argtypes = [C.c_void_p, C.POINTER(ChainMeta)]
+        self._dump.restype = C.c_int32
+        self._dump.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int32]
+        self.cfg = make_cfg(**cfg)
+        self.h = self._create(C.byref(self.cfg))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self._destroy(self.h)
+            self.h = None
+
+    def process(self, iq, taps=TAPS):
+        """iq: complex64[n]. Returns dict tap -> ndarray (fm-rate length, rds24 shorter)."""
+        iq = np.ascontiguousarray(iq, dtype=np.complex64)
+        n = iq.shape[0]
+        cap = n // 12 + 2
+        bufs = {}
+        t = ChainTaps()
+        for name in taps:
+            if name == "locked":
+                a = np.zeros(cap, np.uint8)
+            elif name in ("fm_z", "lr", "audio192", "rds_cplx", "rds24"):
+                a = np.zeros(cap, np.complex64)
+            else:
+                a = np.zeros(cap, np.float32)
+            bufs[name] = a
+            setattr(t, name, a.ctypes.data)
+        nr = C.c_int64(0)
+        nfm = self._process(self.h, iq.ctypes.data, n, C.byref(t), C.byref(nr))
+        out = {}
+        for name, a in bufs.items():
+            out[name] = a[:nr.value] if name == "rds24" else a[:nfm]
+        out["n_fm"], out["n_rds24"] = nfm, nr.value
+        return out
+
+    def meta(self):
+        m = ChainMeta()
+        self._meta(self.h, C.byref(m))
+        return {k: getattr(m, k) for k, _ in ChainMeta._fields_}
+
+    def dump(self, which, cap=200000):
+        a = np.zeros(cap, np.complex64)
+        n = self._dump(self.h, DUMP[which], a.ctypes.data, cap)
+        return None if n < 0 else a[:n].copy()

@@ -1,0 +1,353 @@
+/*
+ * TEST INFRASTRUCTURE — not product code.
+ *
+ * Qt-free driver for the reference's OWN DSP classes.  Every arithmetic block called
+ * here (Oscillator, SinCos, DecimatingFIR, fftFilter, fftFilterHilbert, pilotRecovery,
+ * PerfectStereoSeparation, fm_Demodulator, pllC, compAtan) is the reference's source
+ * file, compiled where it lies under /root/reference by oracle/Makefile.  Only the
+ * sequencing below is ours: it restates, in the same order and with the same member
+ * construction arguments,
+ *     fmProcessor::fmProcessor             src/fm/fm-processor.cpp:48-198
+ *     fmProcessor::run (per-sample loop)   src/fm/fm-processor.cpp:373-687
+ *     fmProcessor::process_signal_with_rds src/fm/fm-processor.cpp:689-759
+ *     the setters                          src/fm/fm-processor.cpp:232-301,762-770
+ * fm-processor.cpp itself cannot be compiled here (QThread, signals, sndfile.h,
+ * samplerate.h), which is why this harness exists.  The chain ends at the 192 kHz
+ * de-emphasised, gain-corrected stereo stream: the next reference step is libsamplerate
+ * (newconverter.cpp:55-80), which is not installed and not vendored.
+ */
+#include <cstring>
+#include <vector>
+#include <complex>
+#include <cmath>
+
+// The table dumps below read private members of the reference classes (SinCos::Table,
+// compAtan's tables, PerfectStereoSeparation::lpFilter, fm_Demodulator::K_FM).  The
+// access-specifier override is confined to this harness translation unit; the reference
+// .cpp files are compiled untouched, and class layout does not depend on access.
+#define private public
+#define protected public
+#include "fm-constants.h"
+#include "fir-filters.h"
+#include "fft-filters.h"
+#include "sincos.h"
+#include "oscillator.h"
+#include "pilot-recover.h"
+#include "stereo-separation.h"
+#include "fm-demodulator.h"
+#undef private
+#undef protected
+
+#include "chain_api.h"
+
+#define PILOT_FREQUENCY 19000
+#define RDS_FREQUENCY (3 * PILOT_FREQUENCY)
+#define RDS_RATE 24000
+#define RDS_SAMPLE_DELAY (2 * (FFT_SIZE - PILOTFILTER_SIZE))
+
+namespace {
+
+struct fftFilterPeek : public fftFilter {
+	fftFilterPeek (int32_t s, int d) : fftFilter (s, d) {}
+	std::complex<float> *freq () { return filterVector; }
+	int32_t size () const { return fftSize; }
+};
+
+enum { MODE_STEREO = 0, MODE_PANO = 1, MODE_MONO = 2 };
+enum { S_STEREO, S_STEREO_SWAPPED, S_LEFT, S_RIGHT, S_LEFTplusRIGHT,
+       S_LEFTminusRIGHT, S_LEFTminusRIGHT_Test };
+
+static const char *decoderName (int code) {
+	switch (code) {          // fm-demodulator.cpp:36-44
+	   case 1: return "AM";
+	   case 2: return "FM PLL Decoder";
+	   case 3: return "FM Mixed Demod";
+	   case 4: return "FM Complex Baseband Delay";
+	   case 5: return "FM Real Baseband Delay";
+	   case 6: return "FM Difference Based";
+	}
+	return "";
+}
+
+struct RefChain {
+	chain_cfg	cfg;
+	int32_t		inputRate, fmRate;
+//	member order of fm-processor.h:172-185
+	Oscillator	localOscillator;
+	SinCos		mySinCos;
+	DecimatingFIR	fmBand_1;
+	DecimatingFIR	fmBand_2;
+	fftFilterPeek	fmAudioFilter;
+	fftFilterPeek	inputFilter;
+	pilotRecovery	pilotRecover;
+	PerfectStereoSeparation pPSS;
+	fftFilterPeek	rdsBandPassFilter;
+	fftFilterHilbert rdsHilbertFilter;
+	fm_Demodulator	theDemodulator;      // owned by RadioInterface in the reference (radio.cpp:190)
+	DecimatingFIR	rdsDecimator;        // local of run (), fm-processor.cpp:382
+	std::vector<float> rdsPhaseBuffer;
+	int		rdsPhaseIndex;
+	bool		inputFilterOn, fmAudioFilterActive;
+	float		Lgain, Rgain;
+	int32_t		loFrequency;
+	float		pilotDelayPSS;
+	DSPCOMPLEX	lastAudioSample;
+	float		deemphAlpha, volumeFactor, panorama, leftChannel, rightChannel;
+	DSPCOMPLEX	RfDC;
+	float		rfDcAlpha;
+
+	RefChain (const chain_cfg &c) :
+	   cfg (c), inputRate (c.input_rate), fmRate (c.fm_rate),
+	   localOscillator (c.input_rate),
+	   mySinCos (c.fm_rate),
+//	fm-processor.cpp:68-75 with IRate = inputRate / 6
+	   fmBand_1 (4 * c.input_rate / (c.input_rate / 6) + 1,
+	             c.fm_rate / 2, c.input_rate, c.input_rate / (c.input_rate / 6)),
+	   fmBand_2 ((c.input_rate / 6) / c.fm_rate + 1,
+	             c.fm_rate / 2, c.input_rate / 6, (c.input_rate / 6) / c.fm_rate),
+	   fmAudioFilter (2 * 4096, 756),
+	   inputFilter (2 * 32768, 251),
+	   pilotRecover (c.fm_rate,
+	                 ((float (PILOT_FREQUENCY)) / c.fm_rate) * (2 * M_PI),
+	                 10 * (2 * M_PI) / c.fm_rate, &mySinCos),
+	   pPSS (c.fm_rate, 10.0f / c.fm_rate, &mySinCos),
+	   rdsBandPassFilter (FFT_SIZE, PILOTFILTER_SIZE),
+	   rdsHilbertFilter (FFT_SIZE, PILOTFILTER_SIZE),
+	   theDemodulator (c.fm_rate),
+	   rdsDecimator (11, RDS_RATE / 2, c.fm_rate, c.fm_rate / RDS_RATE),
+	   rdsPhaseBuffer (RDS_SAMPLE_DELAY, 0.0f) {
+	   Lgain = c.lgain; Rgain = c.rgain;            // :110-111 / setAttenuation
+	   loFrequency = c.lo_hz;                       // :144 / set_localOscillator
+	   RfDC = DSPCOMPLEX (0, 0);                    // :135
+	   rfDcAlpha = 1.0f / inputRate;                // :379
+	   pilotDelayPSS = 0;                           // :160
+	   rdsPhaseIndex = 0;                           // :170
+	   lastAudioSample = 0;                         // :173
+	   inputFilter. setLowPass (0.95 * fmRate / 2, inputRate);   // :148
+	   inputFilterOn = false;
+	   if (c.input_filter_hz > 0) {                 // setBandwidth :232-239 then run :397-401
+	      inputFilter. setLowPass (c.input_filter_hz / 2, inputRate);
+	      inputFilterOn = true;
+	   }
+	   fmAudioFilterActive = false;
+	   if (c.lf_cutoff_hz > 0) {                    // setlfcutoff :762-770 then run :403-408
+	      fmAudioFilter. setLowPass (c.lf_cutoff_hz, fmRate);
+	      fmAudioFilterActive = true;
+	   }
+	   rdsBandPassFilter. setBand (RDS_FREQUENCY - RDS_WIDTH / 2,
+	                               RDS_FREQUENCY + RDS_WIDTH / 2, fmRate);  // :166-168
+	   {  // setDeemphasis :291-297
+	      float Tau = 1000000.0 / c.deemph_us;
+	      deemphAlpha = 1.0 / (float (fmRate) / Tau + 1.0);
+	   }
+	   volumeFactor = std::pow (10.0f, c.volume_db / 20.0f);             // :299-301
+	   panorama = (float)c.panorama / 100.0f;                             // :277-280
+	   leftChannel  = (c.balance > 0 ? (100 - c.balance) / 100.0 : 1.0f); // :282-286
+	   rightChannel = (c.balance < 0 ? (100 + c.balance) / 100.0 : 1.0f);
+	   theDemodulator. setDecoder (QString (decoderName (c.decoder)));
+	}
+
+//	fm-processor.cpp:689-759
+	void process_signal_with_rds (const float demod,
+	                              std::complex<float> *audioOut,
+	                              std::complex<float> *rdsValueCmpl,
+	                              float *phaseOut, bool *lockedOut) {
+	   float currentPilotPhase = pilotRecover. getPilotPhase (5 * demod);
+	   const bool pilotLocked = pilotRecover. isLocked ();
+	   *phaseOut = currentPilotPhase;
+	   *lockedOut = pilotLocked;
+
+	   if (!pilotLocked) {
+	      pilotDelayPSS = 0;
+	      pPSS. reset ();
+	   }
+
+	   if (cfg.fm_mode != MODE_MONO && (pilotLocked || !cfg.auto_mono)) {
+	      float phaseforLRDiff =
+	                2 * (currentPilotPhase + M_PI_4 + 0) - pilotDelayPSS;
+	      if (phaseforLRDiff < - 2 * M_PI)
+	         phaseforLRDiff += 4 * M_PI;
+	      phaseforLRDiff = fmod (phaseforLRDiff, 2 * M_PI);
+	      pilotDelayPSS = cfg.pss_on ?
+	                 pPSS. process_sample (demod, phaseforLRDiff) : 0;
+	      float LRDiff =
+	                2.0 * (cfg.sound_sel == S_LEFTminusRIGHT_Test ?
+	                         mySinCos. getSin (phaseforLRDiff) :
+	                         mySinCos. getCos (phaseforLRDiff)) * demod;
+	      float LRPlus = demod;
+	      *audioOut = DSPCOMPLEX (LRPlus, LRDiff);
+	   }
+	   else {
+	      *audioOut = DSPCOMPLEX (demod, 0);
+	   }
+
+	   if (cfg.rds_on) {
+	      float rdsBaseBp = rdsBandPassFilter. Pass (demod);
+	      std::complex<float> rdsBaseHilb = rdsHilbertFilter. Pass (rdsBaseBp);
+	      float thePhase = 3 * (rdsPhaseBuffer [rdsPhaseIndex] + 0);
+	      rdsPhaseBuffer [rdsPhaseIndex] = currentPilotPhase;
+	      rdsPhaseIndex = (rdsPhaseIndex + 1) % RDS_SAMPLE_DELAY;
+	      std::complex<float> oscValue =
+	                std::complex<float> (cos (thePhase), -sin (thePhase));
+	      *rdsValueCmpl = oscValue * rdsBaseHilb;
+	   }
+	}
+
+//	fm-processor.cpp:423-446 (per pulled block) and :461-648 (per sample)
+	int64_t process (const float *iq, int64_t n_in, const chain_taps *t,
+	                 int64_t *n_rds24) {
+	   int64_t nfm = 0, nrds = 0;
+	   for (int64_t i = 0; i < n_in; i ++) {
+	      DSPCOMPLEX x (iq [2 * i], iq [2 * i + 1]);
+	      if (cfg.dc_remove) {
+	         RfDC = (x - RfDC) * rfDcAlpha + RfDC;
+	         constexpr float DCRlimit = 0.01f;
+	         float rfDcReal = real (RfDC);
+	         float rfDcImag = imag (RfDC);
+	         if (rfDcReal > +DCRlimit) rfDcReal = +DCRlimit;
+	         else if (rfDcReal < -DCRlimit) rfDcReal = -DCRlimit;
+	         if (rfDcImag > +DCRlimit) rfDcImag = +DCRlimit;
+	         else if (rfDcImag < -DCRlimit) rfDcImag = -DCRlimit;
+	         x -= std::complex<float> (rfDcReal, rfDcImag);
+	      }
+	      std::complex<float> v =
+	            std::complex<float> (real (x) * Lgain, imag (x) * Rgain);
+	      v = v * localOscillator. nextValue (loFrequency);
+	      if (inputFilterOn)
+	         v = inputFilter. Pass (v);
+	      if (inputRate / fmRate > 1) {
+	         if (!fmBand_1. Pass (v, &v))
+	            continue;
+	         if (!fmBand_2. Pass (v, &v))
+	            continue;
+	      }
+	      float demod = theDemodulator. demodulate (v);
+
+	      std::complex<float> audio;
+	      std::complex<float> rdsDataCplx (0, 0);
+	      float phase; bool locked;
+	      process_signal_with_rds (demod, &audio, &rdsDataCplx, &phase, &locked);
+
+	      const float sumLR  = real (audio);
+	      const float diffLR = imag (audio);
+	      const float diffLRWeightend =
+	            diffLR * (cfg.fm_mode == MODE_PANO ? panorama : 1.0f);
+	      const float left  = sumLR + diffLRWeightend;
+	      const float right = sumLR - diffLRWeightend;
+	      switch (cfg.sound_sel) {
+	         default:
+	         case S_STEREO:
+	            audio = std::complex<float> (left, right); break;
+	         case S_STEREO_SWAPPED:
+	            audio = std::complex<float> (right, left); break;
+	         case S_LEFT:
+	            audio = std::complex<float> (left, left); break;
+	         case S_RIGHT:
+	            audio = std::complex<float> (right, right); break;
+	         case S_LEFTplusRIGHT:
+	            audio = std::complex<float> (sumLR, sumLR); break;
+	         case S_LEFTminusRIGHT:
+	         case S_LEFTminusRIGHT_Test:
+	            audio = std::complex<float> (diffLRWeightend, diffLRWeightend);
+	            break;
+	      }
+	      if (t -> fm_z) { t -> fm_z [2 * nfm] = real (v); t -> fm_z [2 * nfm + 1] = imag (v); }
+	      if (t -> demod) t -> demod [nfm] = demod;
+	      if (t -> pilot_phase) t -> pilot_phase [nfm] = phase;
+	      if (t -> locked) t -> locked [nfm] = locked ? 1 : 0;
+	      if (t -> pss_delay) t -> pss_delay [nfm] = pilotDelayPSS;
+	      if (t -> lr) { t -> lr [2 * nfm] = real (audio); t -> lr [2 * nfm + 1] = imag (audio); }
+	      if (t -> rds_cplx) {
+	         t -> rds_cplx [2 * nfm] = real (rdsDataCplx);
+	         t -> rds_cplx [2 * nfm + 1] = imag (rdsDataCplx);
+	      }
+
+	      if (cfg.rds_on) {
+	         std::complex<float> rdsSample;
+	         if (rdsDecimator. Pass (rdsDataCplx, &rdsSample)) {
+	            if (t -> rds24) {
+	               t -> rds24 [2 * nrds] = real (rdsSample);
+	               t -> rds24 [2 * nrds + 1] = imag (rdsSample);
+	            }
+	            nrds ++;
+	         }
+	      }
+
+	      if (fmAudioFilterActive)
+	         audio = fmAudioFilter. Pass (audio);
+
+	      audio = lastAudioSample =
+	         (audio - lastAudioSample) * deemphAlpha + lastAudioSample;
+
+//	audioGainCorrection :303-306
+	      const float gl = volumeFactor * leftChannel * real (audio);
+	      const float gr = volumeFactor * rightChannel * imag (audio);
+	      if (t -> audio192) { t -> audio192 [2 * nfm] = gl; t -> audio192 [2 * nfm + 1] = gr; }
+	      nfm ++;
+	   }
+	   if (n_rds24) *n_rds24 = nrds;
+	   return nfm;
+	}
+};
+}	// namespace
+
+extern "C" {
+
+void	*ref_create (const chain_cfg *cfg) { return new RefChain (*cfg); }
+void	ref_destroy (void *h) { delete (RefChain *)h; }
+int64_t	ref_process (void *h, const float *iq, int64_t n_in,
+	             const chain_taps *taps, int64_t *n_rds24) {
+	return ((RefChain *)h) -> process (iq, n_in, taps, n_rds24);
+}
+
+void	ref_get_meta (void *h, chain_meta *m) {
+RefChain *c = (RefChain *)h;
+	m -> dc_rf_re = real (c -> RfDC);
+	m -> dc_rf_im = imag (c -> RfDC);
+	m -> dc_if = c -> theDemodulator. get_DcComponent ();
+	m -> carrier_ampl = c -> theDemodulator. get_carrier_ampl ();
+	m -> pss_phase_shift = c -> pilotDelayPSS;
+	m -> pss_mean_error = c -> pPSS. get_mean_error ();
+	m -> pss_minimized = c -> pPSS. is_error_minimized ();
+	m -> pilot_lock_strength = c -> pilotRecover. getLockedStrength ();
+	m -> pilot_locked = c -> pilotRecover. isLocked ();
+}
+
+int32_t	ref_dump_taps (void *h, int which, float *out, int32_t cap) {
+RefChain *c = (RefChain *)h;
+const std::complex<float> *src = nullptr;
+int32_t n = 0;
+	switch (which) {
+	   case DUMP_FMBAND1: src = c -> fmBand_1. getKernel (); n = c -> fmBand_1. filterSize; break;
+	   case DUMP_FMBAND2: src = c -> fmBand_2. getKernel (); n = c -> fmBand_2. filterSize; break;
+	   case DUMP_RDSDECIM: src = c -> rdsDecimator. getKernel (); n = c -> rdsDecimator. filterSize; break;
+	   case DUMP_INPUT_FILTER_FREQ: src = c -> inputFilter. freq (); n = c -> inputFilter. size (); break;
+	   case DUMP_RDS_BP_FREQ: src = c -> rdsBandPassFilter. freq (); n = c -> rdsBandPassFilter. size (); break;
+	   case DUMP_AUDIO_LP_FREQ: src = c -> fmAudioFilter. freq (); n = c -> fmAudioFilter. size (); break;
+	   case DUMP_PSS_LP_FREQ: src = c -> pPSS. lpFilter. filterVector; n = c -> pPSS. lpFilter. fftSize; break;
+	   case DUMP_SINCOS: src = c -> mySinCos. Table; n = c -> mySinCos. Rate; break;
+	   case DUMP_ATAN: {
+	      compAtan &a = c -> theDemodulator. myAtan;
+	      const float *tabs [8] = { a.ATAN2_TABLE_PPY, a.ATAN2_TABLE_PPX, a.ATAN2_TABLE_PNY,
+	                                a.ATAN2_TABLE_PNX, a.ATAN2_TABLE_NPY, a.ATAN2_TABLE_NPX,
+	                                a.ATAN2_TABLE_NNY, a.ATAN2_TABLE_NNX };
+	      if (cap < 8 * 8193 / 2) return -1;
+	      for (int t = 0; t < 8; t ++)
+	         memcpy (out + t * 8193, tabs [t], 8193 * sizeof (float));
+	      return 8 * 8193 / 2;
+	   }
+	   case DUMP_CONSTS: {
+	      if (cap < 4) return -1;
+	      out [0] = c -> theDemodulator. K_FM;   out [1] = c -> deemphAlpha;
+	      out [2] = c -> volumeFactor;            out [3] = c -> pilotRecover. omega;
+	      out [4] = c -> pilotRecover. gain;      out [5] = c -> pPSS. alpha;
+	      out [6] = c -> pPSS. lockAlpha;         out [7] = c -> rfDcAlpha;
+	      return 4;
+	   }
+	   default: return -1;
+	}
+	if (n > cap) n = cap;
+	memcpy (out, src, (size_t)n * 2 * sizeof (float));
+	return n;
+}
+}

@@ -1,0 +1,313 @@
+"""sdr-j-fm_b200 — host-side mirror (Python, ctypes) of the reference's fmProcessor
+interface over the C ABI in include/sdrjfm_b200.h.
+
+The directory name carries a hyphen (it is the repo's package directory, not an
+installable distribution); load it with `load_package()` from `__graft_entry__` or
+`tests/conftest.py`, which registers it as module `sdrjfm_b200`.
+
+There is no CPU fallback anywhere in this package: if the CUDA library is missing or no
+B200 is visible, construction raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libsdrjfm_b200.so")
+HEADER = os.path.join(os.path.dirname(PKG_DIR), "include", "sdrjfm_b200.h")
+
+OK, ERR_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_CAPACITY, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+
+TAP = dict(fm_z=0, demod=1, pilot_phase=2, locked=3, pss_delay=4, lr=5, audio192=6,
+           rds_cplx=7, rds24=8)
+_TAP_DTYPE = dict(fm_z=np.complex64, demod=np.float32, pilot_phase=np.float32,
+                  locked=np.uint8, pss_delay=np.float32, lr=np.complex64,
+                  audio192=np.complex64, rds_cplx=np.complex64, rds24=np.complex64)
+
+
+class SdrjfmError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"sdrjfm status {status}: {msg}")
+        self.status = status
+
+
+class Config(C.Structure):
+    _fields_ = [("input_rate", C.c_int32), ("fm_rate", C.c_int32),
+                ("working_rate", C.c_int32), ("audio_rate", C.c_int32),
+                ("n_streams", C.c_int32), ("device", C.c_int32),
+                ("max_samples_per_call", C.c_int64), ("keep_taps", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class Meta(C.Structure):
+    _fields_ = [("dc_rf_re", C.c_float), ("dc_rf_im", C.c_float), ("dc_rf_db", C.c_float),
+                ("dc_if", C.c_float), ("carrier_ampl", C.c_float),
+                ("pss_phase_shift_deg", C.c_float), ("pss_phase_change", C.c_float),
+                ("pss_state", C.c_int32), ("pilot_lock_strength", C.c_float),
+                ("pilot_locked", C.c_int32), ("peak_left_db", C.c_float),
+                ("peak_right_db", C.c_float)]
+
+
+def build(verbose=False):
+    """Compile csrc/ for sm_100a into libsdrjfm_b200.so (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", os.path.join(PKG_DIR, "csrc")], capture_output=True,
+                       text=True)
+    if verbose or r.returncode:
+        print(r.stdout, r.stderr)
+    if r.returncode:
+        raise RuntimeError("building libsdrjfm_b200.so failed")
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """The loaded C-ABI library (loud failure if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} missing: run __graft_entry__.build() first; "
+                               "there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+        L.sdrjfm_create.restype = vp
+        L.sdrjfm_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_int)]
+        L.sdrjfm_destroy.argtypes = [vp]
+        L.sdrjfm_last_error.restype = C.c_char_p
+        L.sdrjfm_last_error.argtypes = [vp]
+        L.sdrjfm_version.restype = C.c_char_p
+        L.sdrjfm_process.argtypes = [vp, vp, i64, i64, vp, i64, C.POINTER(i64), vp, i64,
+                                     C.POINTER(i64), vp]
+        L.sdrjfm_process_device.argtypes = [vp, vp, i64, i64, vp, i64, C.POINTER(i64), vp, i64,
+                                            C.POINTER(i64)]
+        L.sdrjfm_sync.argtypes = [vp]
+        L.sdrjfm_get_meta.argtypes = [vp, vp]
+        L.sdrjfm_read_tap.restype = i64
+        L.sdrjfm_read_tap.argtypes = [vp, C.c_int, i32, vp, i64]
+        L.sdrjfm_cuda_stream.restype = vp
+        L.sdrjfm_cuda_stream.argtypes = [vp]
+        L.sdrjfm_run_frontend_only.argtypes = [vp, vp, i64, i64]
+        L.sdrjfm_launch_count.restype = i64
+        L.sdrjfm_launch_count.argtypes = [vp]
+        for name in ("fm_mode", "fm_decoder", "sound_mode", "stereo_panorama", "sound_balance",
+                     "deemphasis", "lf_cutoff", "bandwidth", "rds_mode", "local_oscillator",
+                     "squelch_mode", "auto_mono", "pss_mode", "dc_remove"):
+            getattr(L, f"sdrjfm_set_{name}").argtypes = [vp, i32]
+        L.sdrjfm_set_volume_db.argtypes = [vp, f32]
+        L.sdrjfm_set_attenuation.argtypes = [vp, f32, f32]
+        L.sdrjfm_trigger_frequency_change.argtypes = [vp]
+        L.sdrjfm_restart_pss_analyzer.argtypes = [vp]
+        L.sdrjfm_design_tables.restype = i64
+        L.sdrjfm_design_tables.argtypes = [i32, i32, i32, i32, vp, i64]
+        L.sdrjfm_tables_nbytes.restype = i64
+        L.sdrjfm_tables_nbytes.argtypes = [vp]
+        L.sdrjfm_tables_export.argtypes = [vp, vp, i64]
+        L.sdrjfm_tables_import.argtypes = [vp, vp, i64]
+        _lib = L
+    return _lib
+
+
+# ------------------------------------------------------------------------------------------
+# table blob (TableHeader in csrc/tables.hpp)
+_HDR_FIELDS = [("magic", "u4"), ("version", "u4"), ("input_rate", "i4"), ("fm_rate", "i4"),
+               ("decim1", "i4"), ("decim2", "i4"), ("ntaps1", "i4"), ("ntaps2", "i4"),
+               ("ncomp", "i4"), ("input_filter_hz", "i4"), ("audio_lp_hz", "i4"),
+               ("reserved0", "i4"), ("payload_floats", "i8"),
+               ("off_fmband1", "i8"), ("off_fmband2", "i8"), ("off_rdsdecim", "i8"),
+               ("off_comp", "i8"), ("off_comp_consts", "i8"), ("off_atan", "i8"),
+               ("off_sincos", "i8"), ("off_arcsine", "i8"), ("off_tw2048", "i8"),
+               ("off_tw8192", "i8"), ("off_tw32768", "i8"), ("off_pss_lp", "i8"),
+               ("off_rds_bp", "i8"), ("off_audio_lp", "i8"), ("off_input_taps", "i8"),
+               ("off_comp_wide", "i8"), ("ncomp_wide", "i4"), ("reserved1", "i4")]
+_HDR_DTYPE = np.dtype(_HDR_FIELDS)
+
+
+class Tables:
+    """Parsed view of the shared tap/LUT blob (designed once, broadcast to every rank)."""
+
+    def __init__(self, blob):
+        self.blob = np.frombuffer(bytes(blob), dtype=np.uint8).copy()
+        self.hdr = self.blob[:_HDR_DTYPE.itemsize].view(_HDR_DTYPE)[0]
+        assert self.hdr["magic"] == 0x54464A53
+        self.payload = self.blob[_HDR_DTYPE.itemsize:].view(np.float32)
+
+    def _c(self, off, n):
+        return self.payload[off:off + 2 * n].view(np.complex64)
+
+    def _f(self, off, n):
+        return self.payload[off:off + n]
+
+    @property
+    def fmband1(self): return self._c(self.hdr["off_fmband1"], self.hdr["ntaps1"])
+    @property
+    def fmband2(self): return self._c(self.hdr["off_fmband2"], self.hdr["ntaps2"])
+    @property
+    def rdsdecim(self): return self._c(self.hdr["off_rdsdecim"], 11)
+    @property
+    def composite(self): return self._f(self.hdr["off_comp"], self.hdr["ncomp"])
+    @property
+    def consts(self): return self._f(self.hdr["off_comp_consts"], 8)
+    @property
+    def atan(self): return self._f(self.hdr["off_atan"], 8 * 8193)
+    @property
+    def sincos(self): return self._c(self.hdr["off_sincos"], self.hdr["fm_rate"])
+    @property
+    def pss_lp_freq(self): return self._c(self.hdr["off_pss_lp"], 2048)
+    @property
+    def rds_bp_freq(self): return self._c(self.hdr["off_rds_bp"], 32768)
+    @property
+    def audio_lp_freq(self):
+        return self._c(self.hdr["off_audio_lp"], 8192) if self.hdr["audio_lp_hz"] > 0 else None
+    @property
+    def input_taps(self):
+        return self._f(self.hdr["off_input_taps"], 251) if self.hdr["input_filter_hz"] > 0 else None
+
+
+def design_tables(input_rate=2304000, fm_rate=192000, input_filter_hz=0, audio_lp_hz=0):
+    """Host-only table design (no GPU needed) -> Tables."""
+    L = lib()
+    n = L.sdrjfm_design_tables(input_rate, fm_rate, input_filter_hz, audio_lp_hz, None, 0)
+    if n < 0:
+        raise SdrjfmError(n, "design_tables")
+    buf = (C.c_uint8 * n)()
+    L.sdrjfm_design_tables(input_rate, fm_rate, input_filter_hz, audio_lp_hz, buf, n)
+    return Tables(buf)
+
+
+# ------------------------------------------------------------------------------------------
+class FmProcessorB200:
+    """GPU counterpart of `fmProcessor` (includes/fm/fm-processor.h:103-157) for a batch of
+    `n_streams` independent IQ streams.  Method names follow the reference's setters; the
+    data path is `process()` = what fmProcessor::run does with the samples it pulled from
+    `deviceHandler::getSamples`, returning what it would push to `audioSink::putSample`
+    (48 kHz stereo, complex64 re=L im=R) and to `rdsDecoder::doDecode` (24 kHz complex)."""
+
+    FM_MODE = dict(Stereo=0, StereoPano=1, Mono=2)
+    DECODER = {"AM": 1, "FM PLL Decoder": 2, "FM Mixed Demod": 3,
+               "FM Complex Baseband Delay": 4, "FM Real Baseband Delay": 5,
+               "FM Difference Based": 6}   # fm-demodulator.cpp:36-44
+
+    def __init__(self, n_streams=1, input_rate=2304000, fm_rate=192000, working_rate=48000,
+                 audio_rate=48000, max_samples_per_call=2304000, device=0, keep_taps=True):
+        self.L = lib()
+        self.cfg = Config(input_rate, fm_rate, working_rate, audio_rate, n_streams, device,
+                          max_samples_per_call, 1 if keep_taps else 0, 0)
+        st = C.c_int(0)
+        self.h = self.L.sdrjfm_create(C.byref(self.cfg), C.byref(st))
+        if not self.h:
+            raise SdrjfmError(st.value, self.L.sdrjfm_last_error(None).decode())
+        self.n_streams = n_streams
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.sdrjfm_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _ck(self, rc):
+        if rc != OK:
+            raise SdrjfmError(rc, self.L.sdrjfm_last_error(self.h).decode())
+
+    # --- setters, same names as the reference -------------------------------------------
+    def setfmMode(self, m): self._ck(self.L.sdrjfm_set_fm_mode(self.h, self.FM_MODE.get(m, m)))
+    def setFMdecoder(self, d): self._ck(self.L.sdrjfm_set_fm_decoder(self.h, self.DECODER.get(d, d)))
+    def setSoundMode(self, s): self._ck(self.L.sdrjfm_set_sound_mode(self.h, s))
+    def setStereoPanorama(self, p): self._ck(self.L.sdrjfm_set_stereo_panorama(self.h, p))
+    def setSoundBalance(self, b): self._ck(self.L.sdrjfm_set_sound_balance(self.h, b))
+    def setDeemphasis(self, us): self._ck(self.L.sdrjfm_set_deemphasis(self.h, us))
+    def setVolume(self, db): self._ck(self.L.sdrjfm_set_volume_db(self.h, db))
+    def setlfcutoff(self, hz): self._ck(self.L.sdrjfm_set_lf_cutoff(self.h, hz))
+    def setBandwidth(self, hz): self._ck(self.L.sdrjfm_set_bandwidth(self.h, hz))
+    def setAttenuation(self, l, r): self._ck(self.L.sdrjfm_set_attenuation(self.h, l, r))
+    def setfmRdsSelector(self, m): self._ck(self.L.sdrjfm_set_rds_mode(self.h, m))
+    def set_localOscillator(self, hz): self._ck(self.L.sdrjfm_set_local_oscillator(self.h, hz))
+    def set_squelchMode(self, m): self._ck(self.L.sdrjfm_set_squelch_mode(self.h, m))
+    def setAutoMonoMode(self, on): self._ck(self.L.sdrjfm_set_auto_mono(self.h, int(on)))
+    def setPSSMode(self, on): self._ck(self.L.sdrjfm_set_pss_mode(self.h, int(on)))
+    def setDCRemove(self, on): self._ck(self.L.sdrjfm_set_dc_remove(self.h, int(on)))
+    def triggerFrequencyChange(self): self._ck(self.L.sdrjfm_trigger_frequency_change(self.h))
+    def restartPssAnalyzer(self): self._ck(self.L.sdrjfm_restart_pss_analyzer(self.h))
+
+    def configure(self, **kw):
+        """Apply the chain settings used by the CPU checkers' chain_cfg (oracle/chain_api.h)."""
+        m = dict(fm_mode=self.setfmMode, decoder=self.setFMdecoder, sound_sel=self.setSoundMode,
+                 rds_on=self.setfmRdsSelector, auto_mono=self.setAutoMonoMode,
+                 pss_on=self.setPSSMode, dc_remove=self.setDCRemove,
+                 input_filter_hz=self.setBandwidth, lf_cutoff_hz=self.setlfcutoff,
+                 lo_hz=self.set_localOscillator, deemph_us=self.setDeemphasis,
+                 volume_db=self.setVolume, panorama=self.setStereoPanorama,
+                 balance=self.setSoundBalance)
+        if "lgain" in kw or "rgain" in kw:
+            self.setAttenuation(kw.pop("lgain", 1.0), kw.pop("rgain", 1.0))
+        for k, v in kw.items():
+            m[k](v)
+
+    # --- data path -----------------------------------------------------------------------
+    def process(self, iq, want_meta=False):
+        """iq: complex64 [n_streams, n] (or [n] for one stream), HOST memory.
+        Returns (audio48k complex64 [n_streams, n_audio], rds24 complex64 [n_streams, n_rds])."""
+        iq = np.ascontiguousarray(iq, dtype=np.complex64)
+        if iq.ndim == 1:
+            iq = iq[None, :]
+        assert iq.shape[0] == self.n_streams
+        n = iq.shape[1]
+        audio = np.zeros((self.n_streams, n // 48 + 2), np.complex64)
+        rds = np.zeros((self.n_streams, n // 96 + 2), np.complex64)
+        na, nr = C.c_int64(0), C.c_int64(0)
+        meta = (Meta * self.n_streams)() if want_meta else None
+        self._ck(self.L.sdrjfm_process(self.h, iq.ctypes.data, n, iq.shape[1],
+                                       audio.ctypes.data, audio.shape[1], C.byref(na),
+                                       rds.ctypes.data, rds.shape[1], C.byref(nr),
+                                       C.byref(meta) if meta is not None else None))
+        out = (audio[:, :na.value], rds[:, :nr.value])
+        if want_meta:
+            return out + ([{k: getattr(m, k) for k, _ in Meta._fields_} for m in meta],)
+        return out
+
+    def process_device(self, d_iq_ptr, n_in, in_pitch, d_audio_ptr=None, audio_pitch=0,
+                       d_rds_ptr=None, rds_pitch=0):
+        """Device-pointer form (asynchronous on the handle's stream). Returns (n_audio, n_rds)."""
+        na, nr = C.c_int64(0), C.c_int64(0)
+        self._ck(self.L.sdrjfm_process_device(self.h, d_iq_ptr, n_in, in_pitch, d_audio_ptr,
+                                              audio_pitch, C.byref(na), d_rds_ptr, rds_pitch,
+                                              C.byref(nr)))
+        return na.value, nr.value
+
+    def run_frontend_only(self, d_iq_ptr, n_in, in_pitch):
+        self._ck(self.L.sdrjfm_run_frontend_only(self.h, d_iq_ptr, n_in, in_pitch))
+
+    def sync(self): self._ck(self.L.sdrjfm_sync(self.h))
+
+    @property
+    def cuda_stream(self): return self.L.sdrjfm_cuda_stream(self.h)
+
+    @property
+    def launch_count(self): return self.L.sdrjfm_launch_count(self.h)
+
+    def meta(self):
+        meta = (Meta * self.n_streams)()
+        self._ck(self.L.sdrjfm_get_meta(self.h, C.byref(meta)))
+        return [{k: getattr(m, k) for k, _ in Meta._fields_} for m in meta]
+
+    def read_tap(self, name, stream=0, cap=None):
+        cap = cap or (self.cfg.max_samples_per_call // 12 + 16)
+        a = np.zeros(cap, _TAP_DTYPE[name])
+        n = self.L.sdrjfm_read_tap(self.h, TAP[name], stream, a.ctypes.data, cap)
+        if n < 0:
+            raise SdrjfmError(n, self.L.sdrjfm_last_error(self.h).decode())
+        return a[:n].copy()
+
+    # --- shared tables (rank 0 designs, others import after a broadcast) -----------------
+    def tables_export(self):
+        n = self.L.sdrjfm_tables_nbytes(self.h)
+        buf = (C.c_uint8 * n)()
+        self._ck(self.L.sdrjfm_tables_export(self.h, buf, n))
+        return np.frombuffer(buf, dtype=np.uint8).copy()
+
+    def tables_import(self, blob):
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        self._ck(self.L.sdrjfm_tables_import(self.h, blob.ctypes.data, blob.size))

@@ -1,0 +1,72 @@
+// Shared device helpers and the per-stream state layout of the B200 FM path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sdrjfm {
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+constexpr int kDecim      = 12;    // input samples per fm-rate sample (2304000 / 192000)
+constexpr int kHist       = 36;    // raw IQ history the 37-tap composite needs (3 groups)
+constexpr int kMaxSinExc  = 4;
+
+// The reference build has no FMA contraction (x86-64 baseline), so
+// wherever a reference recurrence is restated sample for sample the operations are spelled
+// with the round-to-nearest intrinsics, which nvcc never fuses.
+__device__ __forceinline__ float fmul (float a, float b) { return __fmul_rn (a, b); }
+__device__ __forceinline__ float fadd (float a, float b) { return __fadd_rn (a, b); }
+__device__ __forceinline__ float fsub (float a, float b) { return __fsub_rn (a, b); }
+__device__ __forceinline__ float fdiv (float a, float b) { return __fdiv_rn (a, b); }
+
+// std::complex<float> operator* as GCC emits it without -ffast-math: four products, each
+// rounded, then one subtraction and one addition.
+__device__ __forceinline__ float2 cmul_rn (float2 a, float2 b) {
+	return make_float2 (fsub (fmul (a.x, b.x), fmul (a.y, b.y)),
+	                    fadd (fmul (a.x, b.y), fmul (a.y, b.x)));
+}
+
+// State carried from one process call to the next, one record per IQ stream.
+// (The reference keeps the same quantities in fmProcessor / fm_Demodulator / pilotRecovery
+// / PerfectStereoSeparation member variables.)
+struct StreamState {
+	// RF DC remover, fm-processor.cpp:425 — tracked in double at the fm rate
+	double  dc_re, dc_im;
+	float   dcc_re, dcc_im;          // clamped DC estimate at the previous fm-rate sample
+	// fm_Demodulator members, fm-demodulator.cpp:79-86
+	float   Imin1, Qmin1, Imin2, Qmin2;
+	float   fm_afc, am_carr_ampl;
+	// pllC (PLL decoder), pllC.cpp:43-58
+	float   pll_nco_phase, pll_phase_incr;
+	// pilotRecovery members, pilot-recover.cpp:28-43
+	float   pilot_phase, pilot_old, pilot_lock;
+	int32_t pilot_locked, pilot_stable_cnt;
+	// fmProcessor::pilotDelayPSS and PerfectStereoSeparation members
+	float   pss_delay, pss_acc, pss_mean_error;
+	int32_t pss_minimized, pss_lock_cnt, pss_unlock_cnt;
+	int32_t pss_inp;                 // fftFilter::inp of the PSS low-pass
+	// de-emphasis, fm-processor.cpp:594-595
+	float   deemph_l, deemph_r;
+	// RDS: fftFilter::inp of band-pass and Hilbert (equal), rdsPhaseIndex, rdsDecimator counter
+	int32_t rds_inp, rds_phase_idx, rds_decim_cnt;
+	// audio: samples still to fade in (suppressAudioSampleCnt), peak meter
+	int32_t fade_cnt;
+	float   peak_l, peak_r;
+	int32_t peak_cnt;
+	float   peak_l_db, peak_r_db;
+	int32_t pad [3];
+};
+
+// Settings snapshot taken at a process boundary (fm-processor.cpp:397-413 does the same
+// at every 16384-sample block).
+struct Settings {
+	int32_t fm_mode, decoder, sound_sel, rds_mode;
+	int32_t auto_mono, pss_on, dc_remove, lo_hz;
+	int32_t input_filter_hz, lf_cutoff_hz, squelch_mode, deemph_us;
+	float   lgain, rgain, volume, panorama;
+	float   left_ch, right_ch, deemph_alpha, pad0;
+};
+
+}	// namespace sdrjfm

@@ -1,0 +1,242 @@
+// K2 — fm-rate parallel stage: finish DC removal, apply IQ gain and the constant complex
+// gain of the decimator cascade, normalise, and run the memoryless part of
+// fm_Demodulator::demodulate (src/fm/fm-demodulator.cpp:111-195).
+//
+// One CTA per IQ stream walks the stream in blocks of 256 threads x 8 samples.  The only
+// recurrence here is the RF DC one-pole at the fm rate, r_m = beta r_{m-1} + alpha S_m
+// (fm-processor.cpp:425 aggregated over 12 input samples): a block-wide
+// scan in double gives every thread its start value, after which the thread steps
+// through its 8 samples.  The previous normalised sample (Imin1, Qmin1) crosses threads
+// through shared memory and crosses calls through StreamState.
+#pragma once
+#include "common.cuh"
+
+namespace sdrjfm {
+
+constexpr int kDiThreads = 256;
+constexpr int kDiRun     = 8;                 // consecutive fm samples per thread
+constexpr int kDiBlock   = kDiThreads * kDiRun;
+
+struct DiscrParams {
+	float  sumC, sumiC12;       // sum of composite taps; sum (i C[i]) / 12
+	float  Gre, Gim;            // constant complex gain of the cascade
+	double alpha, beta;         // alpha = (float)1/inputRate; beta = (1 - alpha)^12
+	float  lgain, rgain;
+	int32_t dc_remove, decoder;
+};
+
+// compAtan::atan2, src/various/Xtan2.cpp:56-100.  Only the first-octant table PPY is kept
+// (in shared memory); the other seven tables are single float operations on PPY
+// (Xtan2.cpp:30-37) and are re-derived on the fly with the same roundings.
+__device__ __forceinline__ int atan_index (float num_scaled, float den) {
+	return (int)((double)fdiv (num_scaled, den) + 0.5);
+}
+
+__device__ __forceinline__ float lut_atan2 (const float *PPY, float y, float x) {
+const float S = (float)M_PI;
+const float H = fmul (S, 0.5f);
+	if (isinf (x) || isinf (y)) return 0.f;
+	if (isnan (x) || isnan (y)) return 0.f;
+	if (x == 0.f) {
+	   if (y == 0.f) return 0.f;
+	   return y > 0.f ? (float)(M_PI / 2) : (float)(-M_PI / 2);
+	}
+	if (x > 0.f) {
+	   if (y >= 0.f) {
+	      if (x >= y) return PPY [atan_index (fmul (8192.f, y), x)];
+	      return fsub (H, PPY [atan_index (fmul (8192.f, x), y)]);
+	   }
+	   if (x >= -y) return -PPY [atan_index (fmul (-8192.f, y), x)];
+	   return fsub (PPY [atan_index (fmul (-8192.f, x), y)], H);
+	}
+	if (y >= 0.f) {
+	   if (-x >= y) return fsub (S, PPY [atan_index (fmul (-8192.f, y), x)]);
+	   return fadd (PPY [atan_index (fmul (-8192.f, x), y)], H);
+	}
+	if (x <= y) return fsub (PPY [atan_index (fmul (8192.f, y), x)], S);
+	return fsub (-H, PPY [atan_index (fmul (8192.f, x), y)]);
+}
+
+struct dcplx { double re, im; };
+
+__device__ __forceinline__ dcplx shfl_up_d (dcplx v, int d) {
+dcplx r;
+	r.re = __shfl_up_sync (0xffffffffu, v.re, d);
+	r.im = __shfl_up_sync (0xffffffffu, v.im, d);
+	return r;
+}
+
+// U, Ssum : front-end outputs; res_raw: discriminator output before AFC (float);
+// zabs: |z| ; fmz (optional): the fm-rate complex sample (tap after fmBand_2)
+__global__ void __launch_bounds__ (kDiThreads)
+discriminator_kernel (const float2 *__restrict__ U, const float2 *__restrict__ Ssum,
+                      int64_t pitch, int32_t M, DiscrParams P,
+                      const float *__restrict__ atanPPY, const float *__restrict__ arcsine,
+                      StreamState *__restrict__ state,
+                      float *__restrict__ res_raw, float *__restrict__ zabs,
+                      float2 *__restrict__ iqn, float2 *__restrict__ fmz) {
+__shared__ float  sPPY [8193 + 3];
+__shared__ dcplx  sWarp [kDiThreads / 32];
+__shared__ float2 sLastIQ [kDiThreads + 1];
+__shared__ float2 sLastIQ2 [kDiThreads + 1];
+__shared__ dcplx  sCarry;
+const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+const int stream = blockIdx.x;
+StreamState &st = state [stream];
+const float2 *Us = U + (int64_t)stream * pitch;
+const float2 *Ss = Ssum + (int64_t)stream * pitch;
+
+	for (int i = tid; i < 8193; i += kDiThreads) sPPY [i] = atanPPY [i];
+	if (tid == 0) {
+	   sCarry.re = st.dc_re; sCarry.im = st.dc_im;
+	   sLastIQ [0]  = make_float2 (st.Imin1, st.Qmin1);
+	   sLastIQ2 [0] = make_float2 (st.Imin2, st.Qmin2);
+	}
+//	powers of beta used by the scan: pw[k] = beta^(8 * 2^k)
+double pw [6];
+	pw [0] = P.beta;
+	{  double b8 = P.beta; b8 *= b8; b8 *= b8; b8 *= b8;   // beta^8
+	   pw [0] = b8;
+#pragma unroll
+	   for (int k = 1; k < 6; k ++) pw [k] = pw [k - 1] * pw [k - 1];
+	}
+	__syncthreads ();
+
+	for (int64_t base = 0; base < M; base += kDiBlock) {
+	   const int64_t j0 = base + (int64_t)tid * kDiRun;
+	   float2 u [kDiRun], s [kDiRun];
+#pragma unroll
+	   for (int j = 0; j < kDiRun; j ++) {
+	      const bool ok = j0 + j < M;
+	      u [j] = ok ? Us [j0 + j] : make_float2 (0.f, 0.f);
+	      s [j] = ok ? Ss [j0 + j] : make_float2 (0.f, 0.f);
+	   }
+//	-- DC one-pole: thread aggregate, block scan, per-sample values -----------------
+	   dcplx a; a.re = 0.0; a.im = 0.0;
+	   if (P.dc_remove) {
+#pragma unroll
+	      for (int j = 0; j < kDiRun; j ++) {
+	         a.re = a.re * P.beta + P.alpha * (double)s [j].x;
+	         a.im = a.im * P.beta + P.alpha * (double)s [j].y;
+	      }
+	   }
+	   dcplx inc = a;                                   // inclusive scan over threads
+#pragma unroll
+	   for (int k = 0; k < 5; k ++) {
+	      dcplx y = shfl_up_d (inc, 1 << k);
+	      if (lane >= (1 << k)) { inc.re += y.re * pw [k]; inc.im += y.im * pw [k]; }
+	   }
+	   if (lane == 31) sWarp [warp] = inc;
+	   __syncthreads ();
+//	start value of this thread = carry decayed to the thread + all earlier threads
+	   dcplx r;
+	   {
+	      // contributions of earlier warps, each decayed by beta^(8*32) per warp of distance
+	      dcplx w; w.re = sCarry.re; w.im = sCarry.im;   // value at block start
+	      for (int q = 0; q < warp; q ++) {
+	         w.re = w.re * pw [5] + sWarp [q].re;
+	         w.im = w.im * pw [5] + sWarp [q].im;
+	      }
+	      // decay from warp start to this thread's start: beta^(8*lane)
+	      double dl = 1.0;
+#pragma unroll
+	      for (int k = 0; k < 5; k ++) if (lane & (1 << k)) dl *= pw [k];
+	      dcplx excl = shfl_up_d (inc, 1);
+	      if (lane == 0) { excl.re = 0.0; excl.im = 0.0; }
+	      r.re = w.re * dl + excl.re;
+	      r.im = w.im * dl + excl.im;
+	   }
+	   float2 cprev;
+	   {  // clamped estimate at the sample before this thread's run
+	      const float lim = 0.01f;
+	      cprev.x = fminf (fmaxf ((float)r.re, -lim), lim);
+	      cprev.y = fminf (fmaxf ((float)r.im, -lim), lim);
+	      if (!P.dc_remove) cprev = make_float2 (0.f, 0.f);
+	   }
+//	-- per-sample: corrected, gained, normalised sample ------------------------------
+	   float2 z [kDiRun], nq [kDiRun];
+	   float  za [kDiRun];
+#pragma unroll
+	   for (int j = 0; j < kDiRun; j ++) {
+	      float2 c = make_float2 (0.f, 0.f);
+	      if (P.dc_remove) {
+	         r.re = r.re * P.beta + P.alpha * (double)s [j].x;
+	         r.im = r.im * P.beta + P.alpha * (double)s [j].y;
+	         const float lim = 0.01f;            // DCRlimit, fm-processor.cpp:429
+	         c.x = fminf (fmaxf ((float)r.re, -lim), lim);
+	         c.y = fminf (fmaxf ((float)r.im, -lim), lim);
+	         if (j0 + j == M - 1) {             // state handed to the next call
+	            st.dc_re = r.re; st.dc_im = r.im; st.dcc_re = c.x; st.dcc_im = c.y;
+	         }
+	      }
+	      // sum_i C[i] c[n-i]  ~=  c_m sumC - (c_m - c_{m-1}) sum(i C[i]) / 12
+	      const float kx = c.x * P.sumC - (c.x - cprev.x) * P.sumiC12;
+	      const float ky = c.y * P.sumC - (c.y - cprev.y) * P.sumiC12;
+	      cprev = c;
+	      // IQ gain (fm-processor.cpp:462-464) commutes with the real-tap FIR
+	      const float vx = (u [j].x - kx) * P.lgain;
+	      const float vy = (u [j].y - ky) * P.rgain;
+	      z [j] = make_float2 (vx * P.Gre - vy * P.Gim, vx * P.Gim + vy * P.Gre);
+	      // std::abs (complex<float>) = hypotf: evaluated through double (fm-demodulator.cpp:119)
+	      za [j] = (float)sqrt ((double)z [j].x * (double)z [j].x +
+	                            (double)z [j].y * (double)z [j].y);
+	      if ((double)za [j] <= 0.001) nq [j] = make_float2 (0.001f, 0.001f);   // :120-122
+	      else nq [j] = make_float2 (fdiv (z [j].x, za [j]), fdiv (z [j].y, za [j]));
+	   }
+//	hand the last normalised samples to the next thread
+	   sLastIQ [tid + 1]  = nq [kDiRun - 1];
+	   sLastIQ2 [tid + 1] = nq [kDiRun - 2];
+	   __syncthreads ();
+	   float2 p1 = sLastIQ [tid];         // Imin1, Qmin1 before this thread's first sample
+	   float2 p2 = sLastIQ2 [tid];        // Imin2, Qmin2 (the sample two back)
+#pragma unroll
+	   for (int j = 0; j < kDiRun; j ++) {
+	      const float I = nq [j].x, Q = nq [j].y;
+	      float res;
+	      switch (P.decoder) {
+	         case 4: {   // ComplexBasebandDelay: argX (z * conj (prev)), fm-demodulator.cpp:174-177
+	            const float2 m = cmul_rn (make_float2 (I, Q), make_float2 (p1.x, -p1.y));
+	            res = lut_atan2 (sPPY, m.y, m.x);
+	            break;
+	         }
+	         case 5: {   // RealBasebandDelay, :179-187
+	            float t = (float)((double)fadd (fsub (fmul (p1.x, Q), fmul (p1.y, I)), 1.0f) / 2.0);
+	            int index = (int)floorf (fmul (t, 32768.f));
+	            if (index < 0) index = 0;
+	            if (index >= 32768) index = 32768;
+	            res = arcsine [index];
+	            break;
+	         }
+	         case 6: {   // DifferenceBased, :189-194
+	            res = fsub (fmul (p1.x, fsub (Q, p2.y)), fmul (p1.y, fsub (I, p2.x)));
+	            res = fdiv (res, fmul (fadd (fmul (p1.x, p1.x), fmul (p1.y, p1.y)), sqrtf (2.f)));
+	            break;
+	         }
+	         default:    // MixedDemodulator, :168-171 (also feeds nothing for the PLL decoder)
+	            res = lut_atan2 (sPPY, fsub (fmul (Q, p1.x), fmul (I, p1.y)),
+	                                   fadd (fmul (I, p1.x), fmul (Q, p1.y)));
+	      }
+	      p2 = p1;
+	      p1 = make_float2 (I, Q);
+	      if (j0 + j == M - 1) {
+	         st.Imin1 = p1.x; st.Qmin1 = p1.y; st.Imin2 = p2.x; st.Qmin2 = p2.y;
+	      }
+	      if (j0 + j < M) {
+	         const int64_t o = (int64_t)stream * pitch + j0 + j;
+	         res_raw [o] = res;
+	         zabs [o] = za [j];
+	         if (iqn) iqn [o] = nq [j];
+	         if (fmz) fmz [o] = z [j];
+	      }
+	   }
+//	-- block carry (only full blocks are followed by another block) ------------------
+	   __syncthreads ();
+	   if (tid == kDiThreads - 1) {
+	      sCarry.re = r.re; sCarry.im = r.im;
+	      sLastIQ [0] = nq [kDiRun - 1]; sLastIQ2 [0] = nq [kDiRun - 2];
+	   }
+	   __syncthreads ();
+	}
+}
+
+}	// namespace sdrjfm

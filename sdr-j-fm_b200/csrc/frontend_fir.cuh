@@ -1,0 +1,155 @@
+// K1 — decimating front end: complex IQ at the input rate -> fm-rate samples.
+//
+// Replaces, per input sample, DecimatingFIR::Pass of fmBand_1 (25 taps, /6) followed by
+// fmBand_2 (3 taps, /2) (src/various/fir-filters.cpp:397-424, constructed at
+// src/fm/fm-processor.cpp:68-75) — "the real cpu killer" — and prepares the RF DC
+// removal of fm-processor.cpp:423-446 so that it can be finished at the fm rate.
+//
+// Formulation: both reference kernels are real prototypes times a constant
+// complex gain, so the cascade is ONE real 37-tap polyphase FIR decimating by 12,
+//     U[m] = sum_{i<37} C[i] * x[12 m + 11 - i]          (index contract: bit-exact)
+// with the constant gain G applied downstream.  DC removal is linear and its estimate
+// moves by < 5e-7 per sample, so the kernel only emits the plain 12-sample sums
+//     S[m] = sum_{i<12} x[12 m + i]
+// from which the fm-rate stage advances the one-pole DC estimate and subtracts
+// clamp (RfDC) * sum (C) (+ first-order trend) from U.
+//
+// Data movement: one coalesced 8-byte load per input sample (the only HBM read of the IQ
+// stream), staged in shared memory in POLYPHASE order — sample n of the tile lives at
+// row (n mod 48), column (n div 48) — so that a thread producing four adjacent outputs
+// reads every operand with unit lane stride (conflict-free) and every staged value is
+// reused from registers for up to 4x3 taps.  Taps sit in constant memory and enter the
+// FMAs as immediate constant-bank operands.
+#pragma once
+#include "common.cuh"
+
+namespace sdrjfm {
+
+constexpr int kFeThreads = 128;
+constexpr int kFeGpt     = 4;                       // fm-rate outputs per thread
+constexpr int kFeTileOut = kFeThreads * kFeGpt;     // 512 outputs per CTA
+constexpr int kFeTileIn  = kFeTileOut * kDecim;     // 6144 input samples per CTA (48 KB)
+constexpr int kFeRows    = kDecim * kFeGpt;         // 48 polyphase rows
+constexpr int kFePitch   = kFeThreads + 1;          // 129 columns: column 0 is the halo
+constexpr int kFeSmemBytes = kFeRows * kFePitch * (int)sizeof (float2);   // 49536
+
+__constant__ float c_comp [40];                     // composite taps C[0..36]
+
+// x      : [n_streams][in_pitch] complex, this call's samples (N = 12 * M per stream)
+// hist   : [n_streams][kHist] complex, the 36 raw samples preceding x[.][0]
+// U, S   : [n_streams][out_pitch] complex
+__global__ void __launch_bounds__ (kFeThreads, 4)
+frontend_fir_kernel (const float2 *__restrict__ x, int64_t in_pitch,
+                     const float2 *__restrict__ hist,
+                     float2 *__restrict__ U, float2 *__restrict__ S,
+                     int64_t out_pitch, int32_t M) {
+extern __shared__ float2 sm [];
+const int tid    = threadIdx.x;
+const int stream = blockIdx.y;
+const int64_t out0 = (int64_t)blockIdx.x * kFeTileOut;   // first output of the tile
+const int64_t in0  = out0 * kDecim;                       // first input of the tile
+const int64_t N    = (int64_t)M * kDecim;
+const float2 *xs = x + (int64_t)stream * in_pitch;
+
+//	halo: the 36 samples before the tile, polyphase rows 12..47 of column 0
+	if (tid < kHist) {
+	   float2 v;
+	   if (blockIdx.x == 0) v = hist [(int64_t)stream * kHist + tid];
+	   else                 v = xs [in0 - kHist + tid];
+	   sm [(kDecim + tid) * kFePitch] = v;
+	}
+
+//	body: 48 coalesced 8-byte loads per thread, issued in batches so that 16 are in flight
+#pragma unroll
+	for (int b = 0; b < 3; b ++) {
+	   float2 v [16];
+#pragma unroll
+	   for (int k = 0; k < 16; k ++) {
+	      const int j = (b * 16 + k) * kFeThreads + tid;
+	      const int64_t n = in0 + j;
+	      v [k] = (n < N) ? __ldcs (xs + n) : make_float2 (0.f, 0.f);
+	   }
+#pragma unroll
+	   for (int k = 0; k < 16; k ++) {
+	      const int j = (b * 16 + k) * kFeThreads + tid;
+	      const int col = j / kFeRows;
+	      const int row = j - col * kFeRows;
+	      sm [row * kFePitch + col + 1] = v [k];
+	   }
+	}
+	__syncthreads ();
+
+//	thread t -> outputs 4t..4t+3 of the tile.  Column t+1 holds their own 48 samples
+//	(row 12 k + p = phase p of output k), column t rows 12..47 hold the three outputs before.
+float2 acc [kFeGpt], dcs [kFeGpt];
+#pragma unroll
+	for (int k = 0; k < kFeGpt; k ++) {
+	   acc [k] = make_float2 (0.f, 0.f);
+	   dcs [k] = make_float2 (0.f, 0.f);
+	}
+const float2 *colp = sm + tid;        // previous column
+const float2 *colc = sm + tid + 1;    // own column
+#pragma unroll
+	for (int p = 0; p < kDecim; p ++) {
+	   float2 v [6];
+	   v [0] = colp [(24 + p) * kFePitch];
+	   v [1] = colp [(36 + p) * kFePitch];
+	   v [2] = colc [(p) * kFePitch];
+	   v [3] = colc [(12 + p) * kFePitch];
+	   v [4] = colc [(24 + p) * kFePitch];
+	   v [5] = colc [(36 + p) * kFePitch];
+	   const float c0 = c_comp [11 - p], c1 = c_comp [23 - p], c2 = c_comp [35 - p];
+#pragma unroll
+	   for (int k = 0; k < kFeGpt; k ++) {
+	      acc [k].x = fmaf (c0, v [k + 2].x, acc [k].x);
+	      acc [k].y = fmaf (c0, v [k + 2].y, acc [k].y);
+	      acc [k].x = fmaf (c1, v [k + 1].x, acc [k].x);
+	      acc [k].y = fmaf (c1, v [k + 1].y, acc [k].y);
+	      acc [k].x = fmaf (c2, v [k].x, acc [k].x);
+	      acc [k].y = fmaf (c2, v [k].y, acc [k].y);
+	      dcs [k].x += v [k + 2].x;
+	      dcs [k].y += v [k + 2].y;
+	   }
+	   if (p == kDecim - 1) {            // tap 36 reaches phase 11 three outputs back
+	      const float c3 = c_comp [36];
+	      const float2 w = colp [(12 + p) * kFePitch];
+	      acc [0].x = fmaf (c3, w.x, acc [0].x);      acc [0].y = fmaf (c3, w.y, acc [0].y);
+	      acc [1].x = fmaf (c3, v [0].x, acc [1].x);  acc [1].y = fmaf (c3, v [0].y, acc [1].y);
+	      acc [2].x = fmaf (c3, v [1].x, acc [2].x);  acc [2].y = fmaf (c3, v [1].y, acc [2].y);
+	      acc [3].x = fmaf (c3, v [2].x, acc [3].x);  acc [3].y = fmaf (c3, v [2].y, acc [3].y);
+	   }
+	}
+
+const int64_t m0 = out0 + (int64_t)tid * kFeGpt;
+float2 *Us = U + (int64_t)stream * out_pitch;
+float2 *Ss = S + (int64_t)stream * out_pitch;
+	if (m0 + kFeGpt <= M && (out_pitch & 1) == 0) {
+	   float4 *u4 = reinterpret_cast<float4 *>(Us + m0);
+	   float4 *s4 = reinterpret_cast<float4 *>(Ss + m0);
+	   u4 [0] = make_float4 (acc [0].x, acc [0].y, acc [1].x, acc [1].y);
+	   u4 [1] = make_float4 (acc [2].x, acc [2].y, acc [3].x, acc [3].y);
+	   s4 [0] = make_float4 (dcs [0].x, dcs [0].y, dcs [1].x, dcs [1].y);
+	   s4 [1] = make_float4 (dcs [2].x, dcs [2].y, dcs [3].x, dcs [3].y);
+	}
+	else {
+#pragma unroll
+	   for (int k = 0; k < kFeGpt; k ++)
+	      if (m0 + k < M) { Us [m0 + k] = acc [k]; Ss [m0 + k] = dcs [k]; }
+	}
+}
+
+// After the front end has run: roll the raw-sample history forward.  new_hist[i] is the
+// sample at position n_proc - 36 + i of the concatenation (old_hist | x[0..n_proc)).
+__global__ void roll_history_kernel (const float2 *__restrict__ x, int64_t in_pitch,
+                                     const float2 *__restrict__ old_hist,
+                                     float2 *__restrict__ new_hist, int64_t n_proc) {
+const int stream = blockIdx.x;
+const int i = threadIdx.x;
+	if (i >= kHist) return;
+const int64_t pos = n_proc - kHist + i;
+	new_hist [(int64_t)stream * kHist + i] =
+	      pos >= 0 ? x [(int64_t)stream * in_pitch + pos]
+	               : old_hist [(int64_t)stream * kHist + (kHist + pos)];
+}
+
+}	// namespace sdrjfm

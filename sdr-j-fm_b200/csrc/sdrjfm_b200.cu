@@ -1,0 +1,625 @@
+// C ABI (include/sdrjfm_b200.h) and launch sequencing of the B200 FM path.
+//
+// Per process call and per batch of streams the sequence mirrors the order of
+// fmProcessor::run's per-sample loop (src/fm/fm-processor.cpp:461-648):
+//   K1 frontend_fir_kernel     DC sums + 37-tap /12 polyphase FIR      (:423-446,:462-475)
+//   K2 discriminator_kernel    DC subtract, gains, normalise, atan     (:497 -> fm-demodulator.cpp:111-195)
+//   K3 sequential_kernel       AFC/level one-poles, pilot PLL, lock    (fm-demodulator.cpp:197-198, pilot-recover.cpp)
+//   K4 stereo / mono matrix    PSS + 38 kHz demod + L/R selector       (:689-730,:517-549)
+//   K5 RDS branch              band-pass, Hilbert, x3 pilot mix, /8    (:733-758,:551-553)
+//   K6 de-emphasis, gain, 192->48 kHz, fade-in                        (:594-595,:630-642)
+// There is NO CPU fallback: without a CUDA device sdrjfm_create fails with
+// SDRJFM_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sdrjfm_b200.h"
+#include "tables.hpp"
+#include "common.cuh"
+#include "frontend_fir.cuh"
+#include "discriminator.cuh"
+#include "sequential.cuh"
+#include "audio_out.cuh"
+
+using namespace sdrjfm;
+
+static thread_local std::string g_create_error;
+
+struct sdrjfm_handle {
+	sdrjfm_config cfg;
+	Settings      set;
+	TableBlob     tables;
+	float        *d_tables = nullptr;
+	cudaStream_t  stream = nullptr;
+	int           n_sm = 0;
+	bool          smem_lut_ok = false;
+	SinLut        lut;
+	float        *d_sin_quarter = nullptr;
+
+	int64_t cap_in = 0, cap_fm = 0, cap_audio = 0, cap_rds = 0;   // per-stream capacities (pitches)
+	float2 *d_in = nullptr;                 // staging [S][cap_in]
+	float2 *d_hist [2] = { nullptr, nullptr }; int hist_sel = 0;
+	float2 *d_pend = nullptr; int pend = 0; // leftover raw samples (< 12 per stream)
+	float2 *d_U = nullptr, *d_S = nullptr, *d_iqn = nullptr, *d_fmz = nullptr;
+	float  *d_res = nullptr, *d_zabs = nullptr, *d_demod = nullptr, *d_phase = nullptr;
+	float  *d_pssd = nullptr;
+	uint8_t *d_locked = nullptr;
+	float2 *d_lr = nullptr, *d_a192 = nullptr, *d_rdsc = nullptr, *d_rds24 = nullptr;
+	float2 *d_ahist [2] = { nullptr, nullptr }; int ahist_sel = 0;
+	float2 *d_audio = nullptr;              // [S][cap_audio] working-rate stereo
+	StreamState *d_state = nullptr;
+	int64_t fm_total = 0;                   // fm-rate samples produced so far (per stream)
+	int32_t fade_cnt = 0, fade_max = 0;     // suppressAudioSampleCnt(Max), fm-processor.cpp:130-131
+	int64_t last_nfm = 0, last_naudio = 0, last_nrds = 0;
+	int64_t launches = 0;
+	std::string err;
+};
+
+#define CK(call)                                                                          \
+	do { cudaError_t e_ = (call); if (e_ != cudaSuccess) {                                \
+	   char b_ [256]; snprintf (b_, sizeof b_, "%s failed: %s (%s:%d)", #call,           \
+	                           cudaGetErrorString (e_), __FILE__, __LINE__);              \
+	   h -> err = b_; return SDRJFM_ERR_CUDA; } } while (0)
+
+template <typename T> static cudaError_t dalloc (T **p, size_t n) {
+	cudaError_t e = cudaMalloc ((void **)p, n * sizeof (T));
+	if (e == cudaSuccess) e = cudaMemset (*p, 0, n * sizeof (T));
+	return e;
+}
+
+static void default_settings (Settings &s, int32_t fm_rate) {
+	memset (&s, 0, sizeof s);
+	s.fm_mode = 0;            // FM_Mode::Stereo, fm-processor.cpp:155
+	s.decoder = 3;            // MIXED, fm-demodulator.cpp:66
+	s.sound_sel = 0;          // S_STEREO, :156
+	s.rds_mode = 0;           // RDS_OFF, :133
+	s.auto_mono = 1; s.pss_on = 1; s.dc_remove = 1;     // :121,:122,:134
+	s.lgain = s.rgain = 1.0f; // :110-111
+	s.volume = 0.5f;          // :127
+	s.panorama = 1.0f;        // :128
+	s.left_ch = s.right_ch = 1.0f;                      // :157-158
+	s.deemph_us = 50;
+	s.deemph_alpha = (float)(1.0 / (fm_rate / (1000000.0 / 50.0 + 1)));   // ctor formula :174
+}
+
+// uploads constant-memory taps and derives the launch parameters that depend on the tables
+static int upload_tables (sdrjfm_handle *h) {
+const TableHeader &th = h -> tables.hdr ();
+	if (h -> d_tables) { cudaFree (h -> d_tables); h -> d_tables = nullptr; }
+	CK (cudaMalloc ((void **)&h -> d_tables, th.payload_floats * sizeof (float)));
+	CK (cudaMemcpy (h -> d_tables, h -> tables.payload (), th.payload_floats * sizeof (float),
+	                cudaMemcpyHostToDevice));
+float comp [40] = { 0 };
+	memcpy (comp, h -> tables.payload () + th.off_comp, th.ncomp * sizeof (float));
+	CK (cudaMemcpyToSymbol (c_comp, comp, sizeof comp));
+
+//	audio decimator taps (our own design, audio_out.cuh): Blackman-windowed sinc, fc = 20 kHz
+	{
+	   float t [kRsTaps + 3] = { 0 };
+	   double sum = 0;
+	   std::vector<double> d (kRsTaps);
+	   const double fc = 20000.0 / th.fm_rate;
+	   for (int i = 0; i < kRsTaps; i ++) {
+	      const int k = i - kRsTaps / 2;
+	      const double s = k == 0 ? 2 * fc : sin (2 * M_PI * fc * k) / (M_PI * k);
+	      const double w = 0.42 - 0.5 * cos (2 * M_PI * i / (kRsTaps - 1))
+	                            + 0.08 * cos (4 * M_PI * i / (kRsTaps - 1));
+	      d [i] = s * w; sum += d [i];
+	   }
+	   for (int i = 0; i < kRsTaps; i ++) t [i] = (float)(d [i] / sum);
+	   CK (cudaMemcpyToSymbol (c_rs_taps, t, sizeof t));
+	}
+
+//	quarter-wave sine table + exception list (see sequential.cuh)
+const cf32 *sc = reinterpret_cast<const cf32 *>(h -> tables.payload () + th.off_sincos);
+const int32_t R = th.fm_rate, Q = R / 4;
+SinLut &L = h -> lut;
+	memset (&L, 0, sizeof L);
+	L.rate = R; L.quarter = Q; L.C = R / (2 * M_PI);
+	for (int e = 0; e < kMaxSinExc; e ++) L.sin_exc_idx [e] = L.cos_exc_idx [e] = -1;
+	h -> smem_lut_ok = (R % 4 == 0);
+	if (h -> smem_lut_ok) {
+	   std::vector<float> q (Q + 1);
+	   for (int i = 0; i <= Q; i ++) q [i] = sc [i].imag ();
+	   auto refl = [&](int idx) -> float {
+	      if (idx <= Q) return q [idx];
+	      if (idx <= 2 * Q) return q [2 * Q - idx];
+	      if (idx <= 3 * Q) return -q [idx - 2 * Q];
+	      return -q [R - idx];
+	   };
+	   int ns = 0, nc = 0;
+	   for (int i = 0; i < R && h -> smem_lut_ok; i ++) {
+	      float a = refl (i), b = sc [i].imag ();
+	      if (memcmp (&a, &b, 4) != 0 && !(a == 0.f && b == 0.f)) {
+	         if (ns < kMaxSinExc) { L.sin_exc_idx [ns] = i; L.sin_exc_val [ns] = b; ns ++; }
+	         else h -> smem_lut_ok = false;
+	      }
+	      a = refl ((i + Q) % R); b = sc [i].real ();
+	      if (memcmp (&a, &b, 4) != 0 && !(a == 0.f && b == 0.f)) {
+	         if (nc < kMaxSinExc) { L.cos_exc_idx [nc] = i; L.cos_exc_val [nc] = b; nc ++; }
+	         else h -> smem_lut_ok = false;
+	      }
+	   }
+	   if (h -> smem_lut_ok) {
+	      if (h -> d_sin_quarter) cudaFree (h -> d_sin_quarter);
+	      CK (cudaMalloc ((void **)&h -> d_sin_quarter, (Q + 1) * sizeof (float)));
+	      CK (cudaMemcpy (h -> d_sin_quarter, q.data (), (Q + 1) * sizeof (float),
+	                      cudaMemcpyHostToDevice));
+	      L.q = h -> d_sin_quarter;
+	   }
+	}
+	if (!h -> smem_lut_ok) {
+	   h -> err = "SinCos table is not quarter-wave symmetric for this fm_rate";
+	   return SDRJFM_ERR_UNSUPPORTED;
+	}
+	return SDRJFM_OK;
+}
+
+static int rebuild_tables (sdrjfm_handle *h) {
+	h -> tables = build_tables (h -> cfg.input_rate, h -> cfg.fm_rate,
+	                            h -> set.input_filter_hz, h -> set.lf_cutoff_hz);
+	return upload_tables (h);
+}
+
+extern "C" {
+
+const char *sdrjfm_version (void) { return "sdrjfm_b200 0.1 (sm_100a)"; }
+
+const char *sdrjfm_last_error (const sdrjfm_handle *h) {
+	return h ? h -> err.c_str () : g_create_error.c_str ();
+}
+
+sdrjfm_handle *sdrjfm_create (const sdrjfm_config *cfg, int *status) {
+int dummy; if (!status) status = &dummy;
+	*status = SDRJFM_ERR_ARG;
+	if (!cfg || cfg -> n_streams < 1 || cfg -> max_samples_per_call < 1) {
+	   g_create_error = "bad config"; return nullptr;
+	}
+	if (cfg -> input_rate != 2304000 || cfg -> fm_rate != 192000) {
+//	the reference itself only supports 2304000 (and the 192000 bypass), SURVEY.md §8(d) config 4
+	   g_create_error = "only input_rate 2304000 / fm_rate 192000 are supported";
+	   *status = SDRJFM_ERR_UNSUPPORTED; return nullptr;
+	}
+int ndev = 0;
+	if (cudaGetDeviceCount (&ndev) != cudaSuccess || ndev <= cfg -> device) {
+	   g_create_error = "no CUDA device: this library has no CPU fallback";
+	   *status = SDRJFM_ERR_NO_DEVICE; return nullptr;
+	}
+cudaDeviceProp prop;
+	if (cudaSetDevice (cfg -> device) != cudaSuccess ||
+	    cudaGetDeviceProperties (&prop, cfg -> device) != cudaSuccess || prop.major < 10) {
+	   g_create_error = "device is not sm_100-class (B200)";
+	   *status = SDRJFM_ERR_NO_DEVICE; return nullptr;
+	}
+sdrjfm_handle *h = new sdrjfm_handle ();
+	h -> cfg = *cfg;
+	if (h -> cfg.working_rate <= 0) h -> cfg.working_rate = 48000;
+	if (h -> cfg.audio_rate <= 0) h -> cfg.audio_rate = h -> cfg.working_rate;
+	h -> n_sm = prop.multiProcessorCount;
+	default_settings (h -> set, cfg -> fm_rate);
+	h -> fade_max = h -> cfg.working_rate / 2;
+	h -> fade_cnt = h -> fade_max;
+const int64_t S = cfg -> n_streams;
+	h -> cap_in    = ((cfg -> max_samples_per_call + kDecim + 15) / 16) * 16;
+	h -> cap_fm    = ((h -> cap_in / kDecim + 1 + 15) / 16) * 16;
+	h -> cap_audio = ((h -> cap_fm / kRsDecim + 1 + 15) / 16) * 16;
+	h -> cap_rds   = ((h -> cap_fm / 8 + 1 + 15) / 16) * 16;
+auto fail = [&](cudaError_t e, const char *what) -> sdrjfm_handle * {
+	   g_create_error = std::string (what) + ": " + cudaGetErrorString (e);
+	   *status = SDRJFM_ERR_CUDA; sdrjfm_destroy (h); return nullptr;
+	};
+cudaError_t e;
+#define AL(p, n) if ((e = dalloc (&h -> p, (size_t)(n))) != cudaSuccess) return fail (e, "cudaMalloc " #p)
+	if ((e = cudaStreamCreateWithFlags (&h -> stream, cudaStreamNonBlocking)) != cudaSuccess)
+	   return fail (e, "cudaStreamCreate");
+	AL (d_in, S * h -> cap_in);
+	AL (d_hist [0], S * kHist); AL (d_hist [1], S * kHist);
+	AL (d_pend, S * kDecim);
+	AL (d_U, S * h -> cap_fm); AL (d_S, S * h -> cap_fm);
+	AL (d_iqn, S * h -> cap_fm); AL (d_fmz, S * h -> cap_fm);
+	AL (d_res, S * h -> cap_fm); AL (d_zabs, S * h -> cap_fm);
+	AL (d_demod, S * h -> cap_fm); AL (d_phase, S * h -> cap_fm); AL (d_pssd, S * h -> cap_fm);
+	AL (d_locked, S * h -> cap_fm);
+	AL (d_lr, S * h -> cap_fm); AL (d_a192, S * h -> cap_fm);
+	AL (d_rdsc, S * h -> cap_fm); AL (d_rds24, S * h -> cap_rds);
+	AL (d_ahist [0], S * kRsHist); AL (d_ahist [1], S * kRsHist);
+	AL (d_audio, S * h -> cap_audio);
+	AL (d_state, S);
+#undef AL
+	{  // initial member values of the reference objects
+	   std::vector<StreamState> st (S);
+	   memset (st.data (), 0, S * sizeof (StreamState));
+	   for (auto &s : st) { s.Imin1 = s.Qmin1 = s.Imin2 = s.Qmin2 = 0.01f; }   // fm-demodulator.cpp:79-82
+	   if ((e = cudaMemcpy (h -> d_state, st.data (), S * sizeof (StreamState),
+	                        cudaMemcpyHostToDevice)) != cudaSuccess) return fail (e, "state upload");
+	}
+	if ((e = cudaFuncSetAttribute (frontend_fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                               kFeSmemBytes)) != cudaSuccess) return fail (e, "smem attr K1");
+	if ((e = cudaFuncSetAttribute (sequential_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                               (cfg -> fm_rate / 4 + 1) * (int)sizeof (float))) != cudaSuccess)
+	   return fail (e, "smem attr K3");
+int rc = rebuild_tables (h);
+	if (rc != SDRJFM_OK) { g_create_error = h -> err; *status = rc; sdrjfm_destroy (h); return nullptr; }
+	*status = SDRJFM_OK;
+	return h;
+}
+
+int sdrjfm_destroy (sdrjfm_handle *h) {
+	if (!h) return SDRJFM_ERR_ARG;
+	cudaSetDevice (h -> cfg.device);
+	if (h -> stream) cudaStreamSynchronize (h -> stream);
+void *ptrs [] = { h -> d_tables, h -> d_sin_quarter, h -> d_in, h -> d_hist [0], h -> d_hist [1],
+	              h -> d_pend, h -> d_U, h -> d_S, h -> d_iqn, h -> d_fmz, h -> d_res, h -> d_zabs,
+	              h -> d_demod, h -> d_phase, h -> d_pssd, h -> d_locked, h -> d_lr, h -> d_a192,
+	              h -> d_rdsc, h -> d_rds24, h -> d_ahist [0], h -> d_ahist [1], h -> d_audio,
+	              h -> d_state };
+	for (void *p : ptrs) if (p) cudaFree (p);
+	if (h -> stream) cudaStreamDestroy (h -> stream);
+	delete h;
+	return SDRJFM_OK;
+}
+
+void *sdrjfm_cuda_stream (sdrjfm_handle *h) { return h ? (void *)h -> stream : nullptr; }
+int64_t sdrjfm_launch_count (const sdrjfm_handle *h) { return h ? h -> launches : 0; }
+
+int sdrjfm_sync (sdrjfm_handle *h) {
+	if (!h) return SDRJFM_ERR_ARG;
+	CK (cudaStreamSynchronize (h -> stream));
+	return SDRJFM_OK;
+}
+
+static int launch_frontend (sdrjfm_handle *h, const float2 *src, int64_t pitch, int32_t M,
+                            const float2 *hist) {
+const int S = h -> cfg.n_streams;
+dim3 grid ((unsigned)((M + kFeTileOut - 1) / kFeTileOut), (unsigned)S);
+	frontend_fir_kernel<<<grid, kFeThreads, kFeSmemBytes, h -> stream>>> (
+	      src, pitch, hist, h -> d_U, h -> d_S, h -> cap_fm, M);
+	h -> launches ++;
+	CK (cudaGetLastError ());
+	return SDRJFM_OK;
+}
+
+int sdrjfm_run_frontend_only (sdrjfm_handle *h, const float *d_iq, int64_t n_in, int64_t in_pitch) {
+	if (!h || !d_iq || n_in < kDecim || in_pitch < n_in) return SDRJFM_ERR_ARG;
+	if (n_in > h -> cfg.max_samples_per_call) { h -> err = "n_in exceeds max_samples_per_call"; return SDRJFM_ERR_CAPACITY; }
+	CK (cudaSetDevice (h -> cfg.device));
+	return launch_frontend (h, (const float2 *)d_iq, in_pitch, (int32_t)(n_in / kDecim),
+	                        h -> d_hist [h -> hist_sel]);
+}
+
+// the launch sequence behind both process entry points; `src` is a device pointer holding
+// (pending | new) samples contiguously per stream with row pitch `pitch`
+static int run_chain (sdrjfm_handle *h, const float2 *src, int64_t pitch, int64_t n_proc,
+                      float2 *d_audio_out, int64_t audio_pitch, int64_t *n_audio,
+                      float2 *d_rds_out, int64_t rds_pitch, int64_t *n_rds) {
+const int S = h -> cfg.n_streams;
+const Settings &st = h -> set;
+const TableHeader &th = h -> tables.hdr ();
+const float *T = h -> d_tables;
+const int32_t M = (int32_t)(n_proc / kDecim);
+	h -> last_nfm = M; h -> last_naudio = 0; h -> last_nrds = 0;
+	if (n_audio) *n_audio = 0;
+	if (n_rds) *n_rds = 0;
+	if (M == 0) return SDRJFM_OK;
+int rc;
+//	K1 ------------------------------------------------------------------------------------
+	if ((rc = launch_frontend (h, src, pitch, M, h -> d_hist [h -> hist_sel])) != SDRJFM_OK) return rc;
+	roll_history_kernel<<<S, 64, 0, h -> stream>>> (src, pitch, h -> d_hist [h -> hist_sel],
+	                                               h -> d_hist [h -> hist_sel ^ 1], n_proc);
+	h -> hist_sel ^= 1; h -> launches ++;
+//	K2 ------------------------------------------------------------------------------------
+const float *consts = h -> tables.payload () + th.off_comp_consts;
+DiscrParams dp;
+	dp.sumC = consts [0]; dp.sumiC12 = consts [1] / 12.0f;
+	dp.Gre = consts [2]; dp.Gim = consts [3];
+	dp.alpha = (double)(1.0f / h -> cfg.input_rate);          // rfDcAlpha, fm-processor.cpp:379
+	dp.beta = pow (1.0 - dp.alpha, (double)kDecim);
+	dp.lgain = st.lgain; dp.rgain = st.rgain;
+	dp.dc_remove = st.dc_remove; dp.decoder = st.decoder;
+	discriminator_kernel<<<S, kDiThreads, 0, h -> stream>>> (
+	      h -> d_U, h -> d_S, h -> cap_fm, M, dp, T + th.off_atan, T + th.off_arcsine,
+	      h -> d_state, h -> d_res, h -> d_zabs, h -> d_iqn, h -> d_fmz);
+	h -> launches ++;
+//	K3 ------------------------------------------------------------------------------------
+SeqParams sp;
+	sp.K_FM = consts [4];
+	sp.omega = (float)(((float)19000 / h -> cfg.fm_rate) * (2 * M_PI));   // OMEGA_PILOT, :34
+	sp.gain = (float)(10 * (2 * M_PI) / h -> cfg.fm_rate);                // :79
+	sp.lock_half_rate = h -> cfg.fm_rate >> 1;
+	sp.decoder = st.decoder;
+	{  // pllC ctor, fm-demodulator.cpp:66-72 / pllC.cpp:38-58
+	   const float maxdev = 0.95 * (0.5 * h -> cfg.fm_rate);
+	   const float fac = 2.0 * M_PI / h -> cfg.fm_rate;
+	   const float bw = 0.85 * h -> cfg.fm_rate;
+	   sp.pll_beta = exp (-2.0 * M_PI * bw / 2 / h -> cfg.fm_rate);
+	   sp.pll_lo = -maxdev * fac; sp.pll_hi = maxdev * fac;
+	   sp.pll_reset = 0.0f;
+	}
+	sp.n_streams = S;
+const int seq_blocks = (S + kSeqLanes - 1) / kSeqLanes;
+	sequential_kernel<true><<<seq_blocks, kSeqLanes, (h -> lut.quarter + 1) * sizeof (float), h -> stream>>> (
+	      h -> d_res, h -> d_zabs, h -> d_iqn, h -> cap_fm, M, sp, h -> lut, T + th.off_atan,
+	      h -> d_state, h -> d_demod, h -> d_phase, h -> d_locked);
+	h -> launches ++;
+//	K4 ------------------------------------------------------------------------------------
+	{
+	   dim3 g ((unsigned)((M + 255) / 256), (unsigned)S);
+	   mono_matrix_kernel<<<g, 256, 0, h -> stream>>> (h -> d_demod, h -> cap_fm, M, st.sound_sel, h -> d_lr);
+	   h -> launches ++;
+	}
+//	K6 ------------------------------------------------------------------------------------
+DeemphParams ep;
+	ep.alpha = st.deemph_alpha;
+	ep.gl = st.volume * st.left_ch; ep.gr = st.volume * st.right_ch;   // fm-processor.cpp:304-305
+	ep.n_streams = S;
+	deemphasis_kernel<<<(S + 31) / 32, 32, 0, h -> stream>>> (h -> d_lr, h -> cap_fm, M, ep,
+	                                                          h -> d_state, h -> d_a192);
+	h -> launches ++;
+const int64_t q0 = h -> fm_total / kRsDecim;
+const int64_t q1 = (h -> fm_total + M) / kRsDecim;
+const int32_t nq = (int32_t)(q1 - q0);
+float2 *aout = d_audio_out ? d_audio_out : h -> d_audio;
+const int64_t apitch = d_audio_out ? audio_pitch : h -> cap_audio;
+	if (nq > 0) {
+	   dim3 g ((unsigned)((nq + 127) / 128), (unsigned)S);
+	   resample4_kernel<<<g, 128, 0, h -> stream>>> (h -> d_a192, h -> cap_fm, h -> d_ahist [h -> ahist_sel],
+	                                                aout, apitch, h -> fm_total, q0, nq,
+	                                                h -> fade_cnt, h -> fade_max);
+	   h -> launches ++;
+	   h -> fade_cnt = h -> fade_cnt > nq ? h -> fade_cnt - nq : 0;
+	}
+	roll_audio_history_kernel<<<S, kRsHist, 0, h -> stream>>> (h -> d_a192, h -> cap_fm,
+	      h -> d_ahist [h -> ahist_sel], h -> d_ahist [h -> ahist_sel ^ 1], M);
+	h -> ahist_sel ^= 1; h -> launches ++;
+	h -> fm_total += M;
+	h -> last_naudio = nq;
+	if (n_audio) *n_audio = nq;
+	(void)d_rds_out; (void)rds_pitch;
+	CK (cudaGetLastError ());
+	return SDRJFM_OK;
+}
+
+// stage (pending | new) samples when the call is not aligned to 12; returns the source to read
+static int stage_input (sdrjfm_handle *h, const float *iq, int64_t n_in, int64_t in_pitch,
+                        cudaMemcpyKind kind, const float2 **src, int64_t *pitch, int64_t *n_proc) {
+const int S = h -> cfg.n_streams;
+const int64_t total = h -> pend + n_in;
+	*n_proc = (total / kDecim) * kDecim;
+	if (kind == cudaMemcpyDeviceToDevice && h -> pend == 0 && *n_proc == n_in) {
+	   *src = (const float2 *)iq; *pitch = in_pitch;       // zero-copy
+	   return SDRJFM_OK;
+	}
+	if (h -> pend)
+	   CK (cudaMemcpy2DAsync (h -> d_in, h -> cap_in * sizeof (float2), h -> d_pend,
+	                          kDecim * sizeof (float2), h -> pend * sizeof (float2), S,
+	                          cudaMemcpyDeviceToDevice, h -> stream));
+	if (n_in)
+	   CK (cudaMemcpy2DAsync (h -> d_in + h -> pend, h -> cap_in * sizeof (float2), iq,
+	                          in_pitch * sizeof (float2), n_in * sizeof (float2), S, kind, h -> stream));
+const int newpend = (int)(total - *n_proc);
+	if (newpend)
+	   CK (cudaMemcpy2DAsync (h -> d_pend, kDecim * sizeof (float2), h -> d_in + *n_proc,
+	                          h -> cap_in * sizeof (float2), newpend * sizeof (float2), S,
+	                          cudaMemcpyDeviceToDevice, h -> stream));
+	h -> pend = newpend;
+	*src = h -> d_in; *pitch = h -> cap_in;
+	return SDRJFM_OK;
+}
+
+int sdrjfm_process_device (sdrjfm_handle *h, const float *d_iq, int64_t n_in, int64_t in_pitch,
+                           float *d_audio, int64_t audio_pitch, int64_t *n_audio,
+                           float *d_rds24, int64_t rds_pitch, int64_t *n_rds) {
+	if (!h || n_in < 0 || (n_in > 0 && (!d_iq || in_pitch < n_in))) return SDRJFM_ERR_ARG;
+	if (n_in > h -> cfg.max_samples_per_call) { h -> err = "n_in exceeds max_samples_per_call"; return SDRJFM_ERR_CAPACITY; }
+	CK (cudaSetDevice (h -> cfg.device));
+const float2 *src; int64_t pitch, n_proc;
+int rc = stage_input (h, d_iq, n_in, in_pitch, cudaMemcpyDeviceToDevice, &src, &pitch, &n_proc);
+	if (rc != SDRJFM_OK) return rc;
+	return run_chain (h, src, pitch, n_proc, (float2 *)d_audio, audio_pitch, n_audio,
+	                  (float2 *)d_rds24, rds_pitch, n_rds);
+}
+
+int sdrjfm_process (sdrjfm_handle *h, const float *iq, int64_t n_in, int64_t in_pitch,
+                    float *audio, int64_t audio_pitch, int64_t *n_audio,
+                    float *rds24, int64_t rds_pitch, int64_t *n_rds, sdrjfm_meta *meta) {
+	if (!h || n_in < 0 || (n_in > 0 && (!iq || in_pitch < n_in))) return SDRJFM_ERR_ARG;
+	if (n_in > h -> cfg.max_samples_per_call) { h -> err = "n_in exceeds max_samples_per_call"; return SDRJFM_ERR_CAPACITY; }
+	CK (cudaSetDevice (h -> cfg.device));
+const int S = h -> cfg.n_streams;
+const float2 *src; int64_t pitch, n_proc;
+int rc = stage_input (h, iq, n_in, in_pitch, cudaMemcpyHostToDevice, &src, &pitch, &n_proc);
+	if (rc != SDRJFM_OK) return rc;
+int64_t na = 0, nr = 0;
+	rc = run_chain (h, src, pitch, n_proc, nullptr, 0, &na, nullptr, 0, &nr);
+	if (rc != SDRJFM_OK) return rc;
+	if (audio && na > 0) {
+	   if (audio_pitch < na) return SDRJFM_ERR_ARG;
+	   CK (cudaMemcpy2DAsync (audio, audio_pitch * sizeof (float2), h -> d_audio,
+	                          h -> cap_audio * sizeof (float2), na * sizeof (float2), S,
+	                          cudaMemcpyDeviceToHost, h -> stream));
+	}
+	if (rds24 && nr > 0) {
+	   if (rds_pitch < nr) return SDRJFM_ERR_ARG;
+	   CK (cudaMemcpy2DAsync (rds24, rds_pitch * sizeof (float2), h -> d_rds24,
+	                          h -> cap_rds * sizeof (float2), nr * sizeof (float2), S,
+	                          cudaMemcpyDeviceToHost, h -> stream));
+	}
+	CK (cudaStreamSynchronize (h -> stream));
+	if (n_audio) *n_audio = na;
+	if (n_rds) *n_rds = nr;
+	if (meta) return sdrjfm_get_meta (h, meta);
+	return SDRJFM_OK;
+}
+
+int sdrjfm_get_meta (sdrjfm_handle *h, sdrjfm_meta *meta) {
+	if (!h || !meta) return SDRJFM_ERR_ARG;
+const int S = h -> cfg.n_streams;
+std::vector<StreamState> st (S);
+	CK (cudaMemcpyAsync (st.data (), h -> d_state, S * sizeof (StreamState), cudaMemcpyDeviceToHost, h -> stream));
+	CK (cudaStreamSynchronize (h -> stream));
+	for (int s = 0; s < S; s ++) {
+	   sdrjfm_meta &m = meta [s];
+	   const StreamState &x = st [s];
+	   m.dc_rf_re = (float)x.dc_re; m.dc_rf_im = (float)x.dc_im;
+	   m.dc_rf_db = h -> set.dc_remove ?
+	         20 * log10f (hypotf (m.dc_rf_re, m.dc_rf_im) + 1.0f / 32768) : -99.99f;
+	   m.dc_if = x.fm_afc;
+	   m.carrier_ampl = x.am_carr_ampl;
+	   m.pss_phase_shift_deg = (float)(x.pss_delay / M_PI * 180.0f);
+	   m.pss_phase_change = x.pss_mean_error * 1000;
+	   const bool locked = h -> set.fm_mode != 2 && x.pilot_locked;       // isPilotLocked, :869-879
+	   m.pilot_locked = locked;
+	   m.pilot_lock_strength = h -> set.fm_mode != 2 ? x.pilot_lock : 0.f;
+	   m.pss_state = (h -> set.pss_on && locked) ? (x.pss_minimized ? 2 : 1) : 0;
+	   m.peak_left_db = x.peak_l_db; m.peak_right_db = x.peak_r_db;
+	}
+	return SDRJFM_OK;
+}
+
+int64_t sdrjfm_read_tap (sdrjfm_handle *h, int which, int32_t stream, void *out, int64_t cap) {
+	if (!h || !out || stream < 0 || stream >= h -> cfg.n_streams) return SDRJFM_ERR_ARG;
+const void *src = nullptr; size_t esz = 0; int64_t n = h -> last_nfm; int64_t pitch = h -> cap_fm;
+	switch (which) {
+	   case SDRJFM_TAP_FM_Z:        src = h -> d_fmz;    esz = 8; break;
+	   case SDRJFM_TAP_DEMOD:       src = h -> d_demod;  esz = 4; break;
+	   case SDRJFM_TAP_PILOT_PHASE: src = h -> d_phase;  esz = 4; break;
+	   case SDRJFM_TAP_LOCKED:      src = h -> d_locked; esz = 1; break;
+	   case SDRJFM_TAP_PSS_DELAY:   src = h -> d_pssd;   esz = 4; break;
+	   case SDRJFM_TAP_LR:          src = h -> d_lr;     esz = 8; break;
+	   case SDRJFM_TAP_AUDIO192:    src = h -> d_a192;   esz = 8; break;
+	   case SDRJFM_TAP_RDS_CPLX:    src = h -> d_rdsc;   esz = 8; break;
+	   case SDRJFM_TAP_RDS24:       src = h -> d_rds24;  esz = 8; n = h -> last_nrds; pitch = h -> cap_rds; break;
+	   default: return SDRJFM_ERR_ARG;
+	}
+	if (n > cap) n = cap;
+	if (n <= 0) return 0;
+	CK (cudaMemcpyAsync (out, (const char *)src + (size_t)stream * pitch * esz, n * esz,
+	                     cudaMemcpyDeviceToHost, h -> stream));
+	CK (cudaStreamSynchronize (h -> stream));
+	return n;
+}
+
+// ---- settings (fm-processor.cpp:232-301, 351-359, 762-770, 840-933) -----------------------
+int sdrjfm_set_fm_mode (sdrjfm_handle *h, int32_t m) {
+	if (!h || m < 0 || m > 2) return SDRJFM_ERR_ARG;
+	h -> set.fm_mode = m; return SDRJFM_OK;
+}
+int sdrjfm_set_fm_decoder (sdrjfm_handle *h, int32_t d) {
+	if (!h || d < 1 || d > 6) return SDRJFM_ERR_ARG;
+	if (d == 1) { h -> err = "AM decoder is not on the GPU path"; return SDRJFM_ERR_UNSUPPORTED; }
+	h -> set.decoder = d; return SDRJFM_OK;
+}
+int sdrjfm_set_sound_mode (sdrjfm_handle *h, int32_t s) {
+	if (!h || s < 0 || s > 6) return SDRJFM_ERR_ARG;
+	h -> set.sound_sel = s; return SDRJFM_OK;
+}
+int sdrjfm_set_stereo_panorama (sdrjfm_handle *h, int32_t pan) {
+	if (!h) return SDRJFM_ERR_ARG;
+	h -> set.panorama = (float)pan / 100.0f; return SDRJFM_OK;           // :279
+}
+int sdrjfm_set_sound_balance (sdrjfm_handle *h, int32_t balance) {
+	if (!h) return SDRJFM_ERR_ARG;
+	h -> set.left_ch  = (balance > 0 ? (100 - balance) / 100.0 : 1.0f);   // :284-285
+	h -> set.right_ch = (balance < 0 ? (100 + balance) / 100.0 : 1.0f);
+	return SDRJFM_OK;
+}
+int sdrjfm_set_deemphasis (sdrjfm_handle *h, int32_t v) {
+	if (!h || v < 1) return SDRJFM_ERR_ARG;
+float Tau = 1000000.0 / v;                                                // :295-296
+	h -> set.deemph_us = v;
+	h -> set.deemph_alpha = 1.0 / (float (h -> cfg.fm_rate) / Tau + 1.0);
+	return SDRJFM_OK;
+}
+int sdrjfm_set_volume_db (sdrjfm_handle *h, float db) {
+	if (!h) return SDRJFM_ERR_ARG;
+	h -> set.volume = std::pow (10.0f, db / 20.0f); return SDRJFM_OK;     // :300
+}
+int sdrjfm_set_lf_cutoff (sdrjfm_handle *h, int32_t hz) {
+	if (!h) return SDRJFM_ERR_ARG;
+	if (hz > 0) { h -> err = "audio low-pass is not on the GPU path yet"; return SDRJFM_ERR_UNSUPPORTED; }
+	h -> set.lf_cutoff_hz = 0; return SDRJFM_OK;
+}
+int sdrjfm_set_bandwidth (sdrjfm_handle *h, int32_t hz) {
+	if (!h) return SDRJFM_ERR_ARG;
+	if (hz > 0) { h -> err = "input filter is not on the GPU path yet"; return SDRJFM_ERR_UNSUPPORTED; }
+	h -> set.input_filter_hz = 0; return SDRJFM_OK;
+}
+int sdrjfm_set_attenuation (sdrjfm_handle *h, float l, float r) {
+	if (!h) return SDRJFM_ERR_ARG;
+	h -> set.lgain = l; h -> set.rgain = r; return SDRJFM_OK;             // :356-357
+}
+int sdrjfm_set_rds_mode (sdrjfm_handle *h, int32_t m) {
+	if (!h || m < 0 || m > 3) return SDRJFM_ERR_ARG;
+	if (m != 0) { h -> err = "RDS branch is not on the GPU path yet"; return SDRJFM_ERR_UNSUPPORTED; }
+	h -> set.rds_mode = m; return SDRJFM_OK;
+}
+int sdrjfm_set_local_oscillator (sdrjfm_handle *h, int32_t hz) {
+	if (!h) return SDRJFM_ERR_ARG;
+	if (hz != 0) { h -> err = "LO offset is not on the GPU path yet"; return SDRJFM_ERR_UNSUPPORTED; }
+	h -> set.lo_hz = hz; return SDRJFM_OK;
+}
+int sdrjfm_set_squelch_mode (sdrjfm_handle *h, int32_t m) {
+	if (!h) return SDRJFM_ERR_ARG;
+	if (m != 0) { h -> err = "squelch is out of scope (SURVEY.md §2 row 11)"; return SDRJFM_ERR_UNSUPPORTED; }
+	h -> set.squelch_mode = 0; return SDRJFM_OK;
+}
+int sdrjfm_set_auto_mono (sdrjfm_handle *h, int32_t on) {
+	if (!h) return SDRJFM_ERR_ARG;
+	h -> set.auto_mono = on != 0; return SDRJFM_OK;
+}
+int sdrjfm_set_pss_mode (sdrjfm_handle *h, int32_t on) {
+	if (!h) return SDRJFM_ERR_ARG;
+	h -> set.pss_on = on != 0; return SDRJFM_OK;
+}
+int sdrjfm_set_dc_remove (sdrjfm_handle *h, int32_t on) {
+	if (!h) return SDRJFM_ERR_ARG;
+	h -> set.dc_remove = on != 0;
+//	setDCRemove also zeroes RfDC (:917-920): clear the DC fields of every stream
+	CK (cudaSetDevice (h -> cfg.device));
+	CK (cudaMemset2DAsync (h -> d_state, sizeof (StreamState), 0, 2 * sizeof (double) + 2 * sizeof (float),
+	                       h -> cfg.n_streams, h -> stream));
+	return SDRJFM_OK;
+}
+int sdrjfm_trigger_frequency_change (sdrjfm_handle *h) {
+	if (!h) return SDRJFM_ERR_ARG;
+	h -> fade_cnt = h -> fade_max;                                        // :848
+	return sdrjfm_restart_pss_analyzer (h);
+}
+int sdrjfm_restart_pss_analyzer (sdrjfm_handle *h) {
+	if (!h) return SDRJFM_ERR_ARG;
+	return SDRJFM_OK;     // PSS state lives with K4 (added with the stereo path)
+}
+
+int64_t sdrjfm_design_tables (int32_t input_rate, int32_t fm_rate, int32_t input_filter_hz,
+                              int32_t audio_lp_hz, void *out, int64_t cap) {
+	if (input_rate < 6 * fm_rate || fm_rate <= 0) return SDRJFM_ERR_ARG;
+TableBlob b = build_tables (input_rate, fm_rate, input_filter_hz, audio_lp_hz);
+	if (out && cap >= (int64_t)b.bytes.size ()) memcpy (out, b.bytes.data (), b.bytes.size ());
+	return (int64_t)b.bytes.size ();
+}
+int64_t sdrjfm_tables_nbytes (const sdrjfm_handle *h) {
+	return h ? (int64_t)h -> tables.bytes.size () : SDRJFM_ERR_ARG;
+}
+int sdrjfm_tables_export (const sdrjfm_handle *h, void *out, int64_t cap) {
+	if (!h || !out || cap < (int64_t)h -> tables.bytes.size ()) return SDRJFM_ERR_ARG;
+	memcpy (out, h -> tables.bytes.data (), h -> tables.bytes.size ());
+	return SDRJFM_OK;
+}
+int sdrjfm_tables_import (sdrjfm_handle *h, const void *blob, int64_t nbytes) {
+	if (!h || !blob || nbytes < (int64_t)sizeof (TableHeader)) return SDRJFM_ERR_ARG;
+const TableHeader *th = (const TableHeader *)blob;
+	if (th -> magic != 0x54464A53u ||
+	    nbytes != (int64_t)(sizeof (TableHeader) + th -> payload_floats * sizeof (float)) ||
+	    th -> input_rate != h -> cfg.input_rate || th -> fm_rate != h -> cfg.fm_rate)
+	   return SDRJFM_ERR_ARG;
+	CK (cudaSetDevice (h -> cfg.device));
+	CK (cudaStreamSynchronize (h -> stream));
+	h -> tables.bytes.assign ((const unsigned char *)blob, (const unsigned char *)blob + nbytes);
+	return upload_tables (h);
+}
+
+}	// extern "C"

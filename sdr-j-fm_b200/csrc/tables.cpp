@@ -1,0 +1,269 @@
+// Host-side table design; see tables.hpp for what follows which reference lines.
+#include "tables.hpp"
+#include <cmath>
+#include <cstring>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+namespace sdrjfm {
+
+// Blackman-windowed sinc prototype shared by the reference's three designers.
+// `f` is the (float) normalised cut-off.  Promotion as in fir-filters.cpp:46-58 /
+// :202-213 / :332-343: the sinc and window are evaluated in double, the product is
+// narrowed to float once per tap.
+std::vector<float> design_sinc_blackman (int ntaps, float f) {
+std::vector<float> t (ntaps);
+const int mid = ntaps / 2;
+	for (int i = 0; i < ntaps; i ++) {
+	   float v;
+	   if (i == mid)
+	      v = (float)(2 * M_PI * f);
+	   else
+	      v = (float)(sin (2 * M_PI * f * (i - mid)) / (i - mid));
+	   const double w = 0.42
+	                  - 0.50 * cos (2 * M_PI * (float)i / (float)ntaps)
+	                  + 0.08 * cos (4 * M_PI * (float)i / (float)ntaps);
+	   t [i] = (float)(v * w);
+	}
+	return t;
+}
+
+static float float_sum (const std::vector<float> &t) {
+float s = 0.0f;                       // accumulated in float, as the reference does
+	for (float v : t) s += v;
+	return s;
+}
+
+// DecimatingFIR::newKernel (int32_t low), fir-filters.cpp:327-347.  Note the reference's
+// quirk at :346 — the imaginary part is NOT normalised.
+std::vector<cf32> design_decimating_lowpass (int ntaps, int32_t low, int32_t fs) {
+const float f = (float)low / fs;
+std::vector<float> t = design_sinc_blackman (ntaps, f);
+const float s = float_sum (t);
+std::vector<cf32> k (ntaps);
+	for (int i = 0; i < ntaps; i ++)
+	   k [i] = cf32 (t [i] / s, t [i]);
+	return k;
+}
+
+// LowPassFIR::newKernel, fir-filters.cpp:41-62
+std::vector<cf32> design_lowpass (int ntaps, int32_t fc, int32_t fs) {
+const float f = (float)fc / fs;
+std::vector<float> t = design_sinc_blackman (ntaps, f);
+const float s = float_sum (t);
+std::vector<cf32> k (ntaps);
+	for (int i = 0; i < ntaps; i ++)
+	   k [i] = cf32 (t [i] / s, 0);
+	return k;
+}
+
+// BandPassFIR::newKernel, fir-filters.cpp:197-222: low-pass prototype of half the band
+// width, shifted to the band centre.
+std::vector<cf32> design_bandpass (int ntaps, int32_t low, int32_t high, int32_t fs) {
+const float lo    = (float)((high - low) / 2) / fs;
+const float shift = (float)((high + low) / 2) / fs;
+std::vector<float> t = design_sinc_blackman (ntaps, lo);
+const float s = float_sum (t);
+std::vector<cf32> k (ntaps);
+const int mid = ntaps / 2;
+	for (int i = 0; i < ntaps; i ++) {
+	   const float v = (float)((i - mid) * (2 * M_PI * shift));
+	   // v is a float in the reference, so cos/sin resolve to the float overloads (:219-220)
+	   k [i] = cf32 (t [i] * cosf (v) / s, t [i] * sinf (v) / s);
+	}
+	return k;
+}
+
+// exp table of Fft_transformRadix2, fft-complex.cpp:65-71: the angle is formed in double,
+// narrowed to float, and std::exp (complex<float>) evaluates cosf/sinf of that float.
+std::vector<cf32> fft_twiddles (int n) {
+std::vector<cf32> w (n / 2);
+	for (int i = 0; i < n / 2; i ++) {
+	   const float a = (float)(-2 * M_PI * i / n);
+	   w [i] = cf32 (cosf (a), sinf (a));
+	}
+	return w;
+}
+
+// Radix-2 decimation-in-time FFT with the operation order of fft-complex.cpp:73-98
+// (bit reversal, then stages of size 2,4,..n; butterfly temp = v[l]*w; v[l] = v[j]-temp;
+// v[j] += temp), float32 throughout.  Used on the host only to transform filter kernels.
+void fft_radix2_reference_order (cf32 *v, int n) {
+int levels = 0;
+	while ((1 << levels) < n) levels ++;
+std::vector<cf32> w = fft_twiddles (n);
+	for (int i = 0; i < n; i ++) {
+	   int j = 0;
+	   for (int b = 0; b < levels; b ++)
+	      j |= ((i >> b) & 1) << (levels - 1 - b);
+	   if (j > i) std::swap (v [i], v [j]);
+	}
+	for (int size = 2; size <= n; size *= 2) {
+	   const int half = size / 2, step = n / size;
+	   for (int i = 0; i < n; i += size)
+	      for (int j = i, k = 0; j < i + half; j ++, k += step) {
+	         const cf32 a = v [j + half], b = w [k];
+	         // std::complex<float> product, 4 multiplies + 2 adds, no contraction
+	         const cf32 t (a.real () * b.real () - a.imag () * b.imag (),
+	                       a.real () * b.imag () + a.imag () * b.real ());
+	         v [j + half] = v [j] - t;
+	         v [j] += t;
+	      }
+	}
+}
+
+static std::vector<cf32> filter_spectrum (const std::vector<cf32> &taps, int nfft) {
+std::vector<cf32> v (nfft, cf32 (0, 0));      // fft-filters.cpp:74-81 / :87-94
+	for (size_t i = 0; i < taps.size (); i ++) v [i] = taps [i];
+	fft_radix2_reference_order (v.data (), nfft);
+	return v;
+}
+
+namespace {
+struct Packer {
+	std::vector<float> f;
+	int64_t put (const float *p, size_t n) {
+	   while (f.size () % 4) f.push_back (0.0f);      // keep every table 16-byte aligned
+	   int64_t off = (int64_t)f.size ();
+	   f.insert (f.end (), p, p + n);
+	   return off;
+	}
+	int64_t put (const std::vector<float> &v) { return put (v.data (), v.size ()); }
+	int64_t put (const std::vector<cf32> &v) {
+	   return put (reinterpret_cast<const float *>(v.data ()), v.size () * 2);
+	}
+};
+}
+
+TableBlob build_tables (int32_t input_rate, int32_t fm_rate, int32_t input_filter_hz,
+                        int32_t audio_lp_hz) {
+TableHeader h;
+Packer pk;
+	memset (&h, 0, sizeof (h));
+	h.magic = 0x54464A53u; h.version = 1;
+	h.input_rate = input_rate; h.fm_rate = fm_rate;
+	h.input_filter_hz = input_filter_hz; h.audio_lp_hz = audio_lp_hz;
+
+//	fmBand_1 / fmBand_2 constructor arguments, fm-processor.cpp:36,68-75
+	const int32_t irate = input_rate / 6;
+	h.decim1 = input_rate / irate;
+	h.decim2 = irate / fm_rate;
+	h.ntaps1 = 4 * input_rate / irate + 1;
+	h.ntaps2 = irate / fm_rate + 1;
+	std::vector<cf32> k1 = design_decimating_lowpass (h.ntaps1, fm_rate / 2, input_rate);
+	std::vector<cf32> k2 = design_decimating_lowpass (h.ntaps2, fm_rate / 2, irate);
+	std::vector<cf32> kr = design_decimating_lowpass (kRdsDecimTaps, 24000 / 2, fm_rate);
+	h.off_fmband1 = pk.put (k1);
+	h.off_fmband2 = pk.put (k2);
+	h.off_rdsdecim = pk.put (kr);
+
+//	Composite of the two decimators.  Each reference kernel is (t/sum, t) = t * (1/sum + j)
+//	up to one float rounding of the real part, so the cascade equals a REAL FIR over the
+//	input-rate samples followed by one constant complex gain G:
+//	  z[m] = G * sum_n C[n] x[D*m + D - 1 - n],  C[d1*j + i] += t2[j]*t1[i],  D = d1*d2
+	h.ncomp = h.ntaps1 + h.decim1 * (h.ntaps2 - 1);
+	std::vector<double> cd (h.ncomp, 0.0);
+	for (int j = 0; j < h.ntaps2; j ++)
+	   for (int i = 0; i < h.ntaps1; i ++)
+	      cd [h.decim1 * j + i] += (double)k2 [j].imag () * (double)k1 [i].imag ();
+	std::vector<float> comp (h.ncomp);
+	double sumC = 0, sumiC = 0;
+	for (int i = 0; i < h.ncomp; i ++) {
+	   comp [i] = (float)cd [i];
+	   sumC += comp [i]; sumiC += (double)i * comp [i];
+	}
+	h.off_comp = pk.put (comp);
+	std::complex<double> g1 ((double)k1 [h.ntaps1 / 2].real () / k1 [h.ntaps1 / 2].imag (), 1.0);
+	std::complex<double> g2 ((double)k2 [h.ntaps2 / 2].real () / k2 [h.ntaps2 / 2].imag (), 1.0);
+	std::complex<double> G = g1 * g2;
+//	K_FM of fm_Demodulator::fm_Demodulator, fm-demodulator.cpp:58-64
+	float F_G     = 0.65 * fm_rate / 2;
+	float Delta_F = 0.95 * fm_rate / 2;
+	float B_FM    = 2 * (Delta_F + F_G);
+	float K_FM    = 2 * B_FM * M_PI / F_G;
+	float consts [8] = { (float)sumC, (float)sumiC, (float)G.real (), (float)G.imag (),
+	                     K_FM, 0, 0, 0 };
+	h.off_comp_consts = pk.put (consts, 8);
+
+//	compAtan, Xtan2.cpp:26-38 (Stretch is a float holding M_PI)
+	{
+	   const float Stretch = M_PI;
+	   std::vector<float> t (kAtanTables * (kAtanSize + 1));
+	   float *PPY = &t [0 * (kAtanSize + 1)], *PPX = &t [1 * (kAtanSize + 1)];
+	   float *PNY = &t [2 * (kAtanSize + 1)], *PNX = &t [3 * (kAtanSize + 1)];
+	   float *NPY = &t [4 * (kAtanSize + 1)], *NPX = &t [5 * (kAtanSize + 1)];
+	   float *NNY = &t [6 * (kAtanSize + 1)], *NNX = &t [7 * (kAtanSize + 1)];
+	   for (int i = 0; i <= kAtanSize; i ++) {
+	      float f = (float)i / kAtanSize;
+	      PPY [i] = atanf (f) * Stretch / M_PI;     // atan (float) is the float overload there
+	      PPX [i] = Stretch * 0.5f - PPY [i];
+	      PNY [i] = -PPY [i];
+	      PNX [i] = PPY [i] - Stretch * 0.5f;
+	      NPY [i] = Stretch - PPY [i];
+	      NPX [i] = PPY [i] + Stretch * 0.5f;
+	      NNY [i] = PPY [i] - Stretch;
+	      NNX [i] = -Stretch * 0.5f - PPY [i];
+	   }
+	   h.off_atan = pk.put (t);
+	}
+
+//	SinCos (fmRate), sincos.cpp:36-45
+	{
+	   std::vector<cf32> t (fm_rate);
+	   for (int i = 0; i < fm_rate; i ++)
+	      t [i] = cf32 (cos (2 * M_PI * i / fm_rate), sin (2 * M_PI * i / fm_rate));
+	   h.off_sincos = pk.put (t);
+	}
+
+//	Arcsine table, fm-demodulator.cpp:73-77
+	{
+	   std::vector<float> t (kArcsineSize + 1);
+	   for (int i = 0; i <= kArcsineSize; i ++)
+	      t [i] = asin (2.0 * i / kArcsineSize - 1.0) / 2.0;
+	   h.off_arcsine = pk.put (t);
+	}
+
+	h.off_tw2048  = pk.put (fft_twiddles (kPssFftSize));
+	h.off_tw8192  = pk.put (fft_twiddles (kAudioFftSize));
+	h.off_tw32768 = pk.put (fft_twiddles (kRdsFftSize));
+
+//	PerfectStereoSeparation: lpFilter (2048, 295).setLowPass (15000, rate),
+//	stereo-separation.cpp:31-39
+	h.off_pss_lp = pk.put (filter_spectrum (design_lowpass (kPssDegree, 15000, fm_rate), kPssFftSize));
+//	rdsBandPassFilter.setBand (57000 -+ 2400, fmRate), fm-processor.cpp:166-168
+	h.off_rds_bp = pk.put (filter_spectrum (
+	         design_bandpass (kRdsDegree, 57000 - 2400, 57000 + 2400, fm_rate), kRdsFftSize));
+//	fmAudioFilter.setLowPass (lowPassFrequency, fmRate), fm-processor.cpp:403-408
+	if (audio_lp_hz > 0)
+	   h.off_audio_lp = pk.put (filter_spectrum (
+	         design_lowpass (kAudioDegree, audio_lp_hz, fm_rate), kAudioFftSize));
+//	inputFilter.setLowPass (fmBandwidth / 2, inputRate), fm-processor.cpp:397-401.  The
+//	65536-point overlap-add filter is a delayed linear convolution with these 251 real
+//	taps; the GPU path folds them into the decimator composite.
+	if (input_filter_hz > 0) {
+	   std::vector<cf32> lp = design_lowpass (kInputDegree, input_filter_hz / 2, input_rate);
+	   std::vector<float> t (kInputDegree);
+	   for (int i = 0; i < kInputDegree; i ++) t [i] = lp [i].real ();
+	   h.off_input_taps = pk.put (t);
+	   h.ncomp_wide = h.ncomp + kInputDegree - 1;
+	   std::vector<double> wd (h.ncomp_wide, 0.0);
+	   for (int a = 0; a < kInputDegree; a ++)
+	      for (int b = 0; b < h.ncomp; b ++)
+	         wd [a + b] += (double)t [a] * cd [b];
+	   std::vector<float> wide (h.ncomp_wide);
+	   for (int i = 0; i < h.ncomp_wide; i ++) wide [i] = (float)wd [i];
+	   h.off_comp_wide = pk.put (wide);
+	}
+	while (pk.f.size () % 4) pk.f.push_back (0.0f);
+	h.payload_floats = (int64_t)pk.f.size ();
+
+TableBlob blob;
+	blob.bytes.resize (sizeof (TableHeader) + pk.f.size () * sizeof (float));
+	memcpy (blob.bytes.data (), &h, sizeof (h));
+	memcpy (blob.bytes.data () + sizeof (h), pk.f.data (), pk.f.size () * sizeof (float));
+	return blob;
+}
+
+}	// namespace sdrjfm

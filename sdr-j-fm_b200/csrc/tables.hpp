@@ -1,0 +1,82 @@
+// Host-side design of every tap set and look-up table the FM path needs.
+//
+// These are one-off, host-evaluated formulas; they follow the reference's float/double
+// promotion exactly so that the device tables are bit-identical
+// to what the reference's constructors build:
+//   windowed-sinc designers   src/various/fir-filters.cpp:41-62 (LowPassFIR),
+//                             :197-222 (BandPassFIR), :327-347 (DecimatingFIR)
+//   SinCos table              src/various/sincos.cpp:36-45
+//   Oscillator table          src/various/oscillator.cpp:26-37
+//   compAtan tables           src/various/Xtan2.cpp:12-39
+//   FFT twiddles              src/various/fft-complex.cpp:65-71
+//   fftFilter spectra         src/various/fft-filters.cpp:71-95 (setBand / setLowPass)
+// The result is ONE contiguous blob (header + float payload) so that rank 0 can design it
+// once and broadcast it to the other GPUs.
+#pragma once
+#include <cstdint>
+#include <complex>
+#include <vector>
+
+namespace sdrjfm {
+
+typedef std::complex<float> cf32;
+
+constexpr int   kAtanSize      = 8192;          // Xtan2.cpp:9
+constexpr int   kAtanTables    = 8;
+constexpr int   kCompositeTaps = 37;            // 25 + 6*(3-1)
+constexpr int   kRdsFftSize    = 32768;         // FFT_SIZE, fm-constants.h:107
+constexpr int   kRdsDegree     = 768;           // PILOTFILTER_SIZE, fm-constants.h:106
+constexpr int   kPssFftSize    = 2048;          // stereo-separation.cpp:31
+constexpr int   kPssDegree     = 295;
+constexpr int   kAudioFftSize  = 8192;          // fm-processor.cpp:76
+constexpr int   kAudioDegree   = 756;
+constexpr int   kInputFftSize  = 65536;         // fm-processor.cpp:77
+constexpr int   kInputDegree   = 251;
+constexpr int   kRdsDecimTaps  = 11;            // fm-processor.cpp:382
+constexpr int   kArcsineSize   = 4 * 8192;      // fm-demodulator.cpp:73
+
+// offsets are in floats from the start of the payload
+struct TableHeader {
+	uint32_t magic;           // 'SJFT'
+	uint32_t version;
+	int32_t  input_rate, fm_rate;
+	int32_t  decim1, decim2;  // 6 and 2 at 2304000
+	int32_t  ntaps1, ntaps2;  // 25 and 3
+	int32_t  ncomp;           // composite real taps (ntaps1 + decim1*(ntaps2-1))
+	int32_t  input_filter_hz, audio_lp_hz;
+	int32_t  reserved0;
+	int64_t  payload_floats;
+	int64_t  off_fmband1, off_fmband2, off_rdsdecim;     // complex taps
+	int64_t  off_comp;          // ncomp real composite taps  C[i] (input-rate index i)
+	int64_t  off_comp_consts;   // [sumC, sumiC, Gre, Gim, K_FM, pad, pad, pad]
+	int64_t  off_atan;          // 8 * 8193 floats, order PPY PPX PNY PNX NPY NPX NNY NNX
+	int64_t  off_sincos;        // fm_rate complex (cos, sin)
+	int64_t  off_arcsine;       // 32769 floats
+	int64_t  off_tw2048, off_tw8192, off_tw32768;        // n/2 complex each
+	int64_t  off_pss_lp, off_rds_bp, off_audio_lp;       // frequency-domain filter vectors
+	int64_t  off_input_taps;    // 251 real time-domain taps (0 if input filter off)
+	int64_t  off_comp_wide;     // composite of input filter and the decimator cascade
+	int32_t  ncomp_wide;
+	int32_t  reserved1;
+};
+
+struct TableBlob {
+	std::vector<unsigned char> bytes;      // TableHeader followed by the float payload
+	const TableHeader &hdr () const { return *reinterpret_cast<const TableHeader *>(bytes.data ()); }
+	TableHeader &hdr () { return *reinterpret_cast<TableHeader *>(bytes.data ()); }
+	const float *payload () const { return reinterpret_cast<const float *>(bytes.data () + sizeof (TableHeader)); }
+	float *payload () { return reinterpret_cast<float *>(bytes.data () + sizeof (TableHeader)); }
+};
+
+// designers (exposed for the unit tests through the C ABI's table export)
+std::vector<float> design_sinc_blackman (int ntaps, float f);              // un-normalised tmp[]
+std::vector<cf32>  design_decimating_lowpass (int ntaps, int32_t low, int32_t fs);
+std::vector<cf32>  design_lowpass (int ntaps, int32_t fc, int32_t fs);
+std::vector<cf32>  design_bandpass (int ntaps, int32_t low, int32_t high, int32_t fs);
+void               fft_radix2_reference_order (cf32 *v, int n);            // same op order as fft-complex.cpp:50-102
+std::vector<cf32>  fft_twiddles (int n);
+
+TableBlob build_tables (int32_t input_rate, int32_t fm_rate, int32_t input_filter_hz,
+                        int32_t audio_lp_hz);
+
+}	// namespace sdrjfm
