@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py — IQ MS/s through the FM demodulation chain on N B200s (one rank per GPU).
+
+Contract: `python bench.py --gpus N --steps K --warmup W [--impl reference]` prints ONE JSON
+line (rank 0).  A "step" = one pass of the hot path over one batch of synthetic IQ:
+`--streams` independent 2.304 MS/s streams x `--seconds` of signal PER GPU (weak scaling:
+the batch per GPU is fixed, streams are sharded over ranks, there is no data-path
+collective; the only collective is the one-time broadcast of the tap/LUT blob).
+
+  value     whole-job throughput, inputs resident in HBM, CUDA-event timed on the handle's
+            stream, max over ranks
+  e2e       same metric through the host-buffer C-ABI call (sdrjfm_process): pinned host
+            IQ in, audio + RDS baseband out, copies inside the timed region
+  roofline  the decimating front-end kernel timed alone: 8.667 algorithmic bytes per input
+            sample (8 B float2 read + 8/12 B fm-rate float2 write)
+  cpu_baseline  the reference's own DSP classes (oracle/_ref) — or the port when _ref is
+            absent — on the host cores, bounded sample (rank 0, N=1 only)
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from __graft_entry__ import load_package  # noqa: E402
+
+INPUT_RATE = 2304000
+ALGO_BYTES_PER_SAMPLE = 8.0 + 8.0 / 12.0
+FALLBACK_HBM_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md, used if MEASURED_PEAKS.json is absent
+
+
+def chain_settings():
+    """settings of the benchmarked chain = BASELINE.json config 5 (stereo + pilot/PSS + RDS)
+    as far as the GPU path implements it; the same dict configures the CPU reference arm."""
+    return dict(fm_mode=0, decoder=3, rds_on=0, auto_mono=1, pss_on=1, dc_remove=1,
+                deemph_us=50, volume_db=-6.0)
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            for k in ("hbm_gbs", "hbm_gb_s", "hbm_copy_gbs"):
+                if k in d:
+                    return float(d[k]), "measured"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback"
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": int(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+def gen_batch_gpu(torch, dev, n_streams, n, stream0=0, group=16):
+    """config-5 style IQ on the GPU: stream s = stereo MPX, L tone 400+10 s Hz, 10 % pilot,
+    57 kHz BPSK-like RDS sub-carrier, 75 kHz deviation, amp 0.5, AWGN 40 dB (seeded)."""
+    out = torch.empty((n_streams, n), dtype=torch.complex64, device=dev)
+    t = torch.arange(n, dtype=torch.float64, device=dev) / INPUT_RATE
+    th = 2 * np.pi * 19000.0 * t
+    sin_th, sin_2th, sin_3th = torch.sin(th), torch.sin(2 * th), torch.sin(3 * th)
+    g = torch.Generator(device=dev)
+    for s0 in range(0, n_streams, group):
+        ss = torch.arange(s0, min(s0 + group, n_streams), device=dev, dtype=torch.float64)
+        sid = ss + stream0
+        L = torch.sin(2 * np.pi * (400.0 + 10.0 * sid)[:, None] * t[None, :])
+        g.manual_seed(2000 + int(sid[0].item()))
+        bits = torch.randint(0, 2, (len(ss), 4096), device=dev, generator=g)
+        d = torch.cumsum(bits, dim=1) & 1
+        bit_idx = torch.floor(t * 1187.5).long() % 4096
+        half = torch.floor(t * 2375.0).long() & 1
+        sym = (1.0 - 2.0 * d[:, bit_idx].double()) * (1.0 - 2.0 * half.double())[None, :]
+        mpx = 0.45 * L + 0.45 * L * sin_2th[None, :] + 0.10 * sin_th[None, :] + 0.05 * sym * sin_3th[None, :]
+        phi = torch.cumsum(2 * np.pi * 75000.0 / INPUT_RATE * mpx, dim=1) + 0.1 * sid[:, None]
+        sigma = 0.5 / np.sqrt(2.0) * 10 ** (-40.0 / 20)
+        noise = sigma * torch.randn((len(ss), n, 2), device=dev, generator=g, dtype=torch.float32)
+        x = 0.5 * torch.polar(torch.ones_like(phi), phi)
+        out[s0:s0 + len(ss)] = x.to(torch.complex64) + torch.view_as_complex(noise)
+        del L, mpx, phi, x, noise, sym
+    return out
+
+
+def cpu_reference_rate(settings, seconds_per_thread, threads=None):
+    """times the reference DSP classes (oracle/_ref; the port if absent) on host cores:
+    one stream per thread, each `seconds_per_thread` of config-2/5 signal. Returns dict."""
+    from oracle import chainlib
+    chainlib.build(("oracle", "ref"))
+    kind, prefix = ("reference", "ref") if chainlib.available("ref") else ("port", "orc")
+    sig = importlib.import_module("sdrjfm_b200.signals")
+    cores = threads or os.cpu_count() or 1
+    block = sig.batch_stream(0, INPUT_RATE)           # 1 s block, fed repeatedly
+    reps = max(1, int(round(seconds_per_thread)))
+    chains = [chainlib.Chain(prefix, **settings) for _ in range(cores)]
+    taps = ("audio192", "rds24")
+
+    def work(c):
+        for _ in range(reps):
+            c.process(block, taps=taps)
+
+    ths = [threading.Thread(target=work, args=(c,)) for c in chains]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    total = cores * reps * len(block)
+    return {"value": total / dt / 1e6, "unit": "MS/s", "cores": cores, "kind": kind,
+            "sample": f"{cores} streams x {reps} s of 2.304 MS/s stereo+pilot IQ, one stream per "
+                      f"thread, chain up to 192 kHz de-emphasised audio (libsamplerate absent)",
+            "seconds": dt}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=256, help="IQ streams per GPU")
+    ap.add_argument("--seconds", type=float, default=0.5, help="signal seconds per stream per step")
+    ap.add_argument("--cpu-seconds", type=float, default=3.0, help="cpu baseline: signal seconds per thread")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    pkg = load_package()
+    settings = chain_settings()
+    n = int(args.seconds * INPUT_RATE) // 12 * 12
+    workload = (f"batched multi-stream (BASELINE config 5 shape): {args.streams} streams/GPU x "
+                f"{n} IQ samples @2.304 MS/s, stereo MPX + 19 kHz pilot + 57 kHz RDS sub-carrier")
+    config = {"workload": workload, "streams_per_gpu": args.streams, "samples_per_stream": n,
+              "settings": settings, "l2_policy": "inputs larger than L2 (per-step IQ batch >> 126 MB)",
+              "chain": "DC-remove, FIR /12, Mixed discriminator, AFC, pilot PLL, de-emphasis, "
+                       "192->48 kHz (stereo matrix/PSS and RDS stages: see DESIGN.md status)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_reference_rate(settings, args.cpu_seconds)
+        # K timed steps of the bounded sample (each step = cores x cpu_seconds of signal)
+        vals = [r["value"]]
+        for _ in range(max(0, min(args.steps, 3) - 1)):
+            vals.append(cpu_reference_rate(settings, args.cpu_seconds)["value"])
+        v = float(np.mean(vals))
+        line = {"impl": "reference", "metric": "IQ MS/s through full FM demod chain", "value": v,
+                "unit": "MS/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": 0,
+                "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": "MS/s", "cores": r["cores"], "kind": r["kind"],
+                                 "sample": r["sample"]},
+                "e2e": {"value": v, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the FM path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    S = args.streams
+    proc = pkg.FmProcessorB200(n_streams=S, max_samples_per_call=n, device=local)
+    proc.configure(**settings)
+    # shared tap/LUT blob: rank 0 designs, everyone imports what rank 0 broadcast (NCCL)
+    if world > 1:
+        blob = torch.from_numpy(proc.tables_export()).to(dev)
+        dist.broadcast(blob, src=0)
+        proc.tables_import(blob.cpu().numpy())
+
+    x = gen_batch_gpu(torch, dev, S, n, stream0=rank * S)
+    torch.cuda.synchronize()
+    ext = torch.cuda.ExternalStream(proc.cuda_stream, device=dev)
+    d_audio = torch.empty((S, n // 48 + 16), dtype=torch.complex64, device=dev)
+    d_rds = torch.empty((S, n // 96 + 16), dtype=torch.complex64, device=dev)
+
+    def step_device():
+        proc.process_device(x.data_ptr(), n, x.stride(0), d_audio.data_ptr(), d_audio.stride(0),
+                            d_rds.data_ptr(), d_rds.stride(0))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(ext):
+            e0.record(ext)
+            for _ in range(steps):
+                fn()
+            e1.record(ext)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(args.warmup):
+        step_device()
+    proc.sync()
+    l0 = proc.launch_count
+    with ClockSampler(local) as clk:
+        ms = timed(step_device, args.steps)
+    launches = proc.launch_count - l0
+    value = world * S * n * args.steps / (ms * 1e-3) / 1e6
+
+    # roofline: the front-end kernel alone
+    for _ in range(3):
+        proc.run_frontend_only(x.data_ptr(), n, x.stride(0))
+    fe_steps = max(args.steps, 5)
+    fe_ms = timed(lambda: proc.run_frontend_only(x.data_ptr(), n, x.stride(0)), fe_steps) / fe_steps
+    peak, peak_kind = peak_hbm()
+    achieved = ALGO_BYTES_PER_SAMPLE * S * n / (fe_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "frontend_fir_kernel", "achieved": achieved, "peak": peak,
+                "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel_ms": fe_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SAMPLE * S * n}
+
+    # end to end through the host-buffer C-ABI call
+    e2e = None
+    if not args.no_e2e:
+        hx = torch.empty((S, n), dtype=torch.complex64, pin_memory=True)
+        hx.copy_(x)
+        ha = torch.empty((S, n // 48 + 16), dtype=torch.complex64, pin_memory=True)
+        hr = torch.empty((S, n // 96 + 16), dtype=torch.complex64, pin_memory=True)
+        import ctypes as C
+        na, nr = C.c_int64(0), C.c_int64(0)
+
+        def step_host():
+            rc = proc.L.sdrjfm_process(proc.h, hx.data_ptr(), n, hx.stride(0), ha.data_ptr(),
+                                       ha.stride(0), C.byref(na), hr.data_ptr(), hr.stride(0),
+                                       C.byref(nr), None)
+            assert rc == 0, proc.L.sdrjfm_last_error(proc.h)
+
+        step_host()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, 3))
+        for _ in range(e2e_steps):
+            step_host()          # synchronous: returns after the D2H copies completed
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * S * n * e2e_steps / dt / 1e6, "unit": "MS/s",
+               "h2d_bytes_per_step": S * n * 8,
+               "d2h_bytes_per_step": S * (na.value + nr.value) * 8, "steps": e2e_steps}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_reference_rate(settings, args.cpu_seconds)
+        cpu.pop("seconds", None)
+
+    if rank == 0:
+        line = {"metric": "IQ MS/s through full FM demod chain", "value": value, "unit": "MS/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "x_realtime_2p304MSps": value / 2.304, "roofline": roofline,
+                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clk.summary()}
+        print(json.dumps(line))
+    proc.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,75 @@
+"""CPU: the C-ABI library loads and exports every symbol include/sdrjfm_b200.h declares,
+fails loudly without a device, and its host-designed tables are bit-identical to what the
+reference's constructors build (oracle/_ref dumps)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+
+def _same(a, b):
+    return a.shape == b.shape and np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    hdr = open(pkg.HEADER).read()
+    names = sorted(set(re.findall(r"\b(sdrjfm_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 30
+    L = pkg.lib()
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert b"sm_100a" in L.sdrjfm_version()
+
+
+def test_create_fails_loudly_without_device(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    with pytest.raises(pkg.SdrjfmError) as e:
+        pkg.FmProcessorB200(n_streams=1)
+    assert e.value.status == pkg.ERR_NO_DEVICE
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_bad_arguments(pkg):
+    L = pkg.lib()
+    st = C.c_int(0)
+    assert not L.sdrjfm_create(None, C.byref(st)) and st.value == pkg.ERR_ARG
+    cfg = pkg.Config(2400000, 192000, 48000, 48000, 1, 0, 1000, 0, 0)
+    assert not L.sdrjfm_create(C.byref(cfg), C.byref(st)) and st.value == pkg.ERR_UNSUPPORTED
+    assert L.sdrjfm_design_tables(100, 192000, 0, 0, None, 0) == pkg.ERR_ARG
+
+
+def test_tables_match_reference_constructors(pkg, chainlib, ref_available):
+    which = "ref" if ref_available else "orc"
+    T = pkg.design_tables(input_filter_hz=165000, audio_lp_hz=15000)
+    c = chainlib.Chain(which, input_filter_hz=165000, lf_cutoff_hz=15000)
+    assert _same(T.fmband1, c.dump("fmband1"))
+    assert _same(T.fmband2, c.dump("fmband2"))
+    assert _same(T.rdsdecim, c.dump("rdsdecim"))
+    assert _same(T.sincos, c.dump("sincos"))
+    assert _same(T.atan, c.dump("atan").view(np.float32))
+    assert _same(T.pss_lp_freq, c.dump("pss_lp_freq"))
+    assert _same(T.rds_bp_freq, c.dump("rds_bp_freq"))
+    assert _same(T.audio_lp_freq, c.dump("audio_lp_freq"))
+    k = c.dump("consts").view(np.float32)
+    assert T.consts[4] == k[0]                       # K_FM
+    # the 251 input taps are the real part of the low-pass whose spectrum the reference holds
+    spec = np.fft.fft(np.concatenate([T.input_taps.astype(np.float64), np.zeros(65536 - 251)]))
+    ref = c.dump("input_filter_freq").astype(np.complex128)
+    assert np.abs(spec - ref).max() < 2e-5
+
+
+def test_composite_equals_cascade(pkg):
+    """the 37 real taps x constant gain reproduce the two reference kernels in cascade."""
+    T = pkg.design_tables()
+    k1, k2 = T.fmband1.astype(np.complex128), T.fmband2.astype(np.complex128)
+    casc = np.zeros(37, complex)
+    for j in range(3):
+        casc[6 * j:6 * j + 25] += k2[j] * k1
+    G = complex(T.consts[2], T.consts[3])
+    comp = T.composite.astype(np.float64) * G
+    assert np.abs(comp - casc).max() < 3e-7 * np.abs(casc).max()
+    assert abs(T.consts[0] - T.composite.astype(np.float64).sum()) < 1e-6
