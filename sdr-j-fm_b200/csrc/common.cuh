@@ -34,7 +34,7 @@ __device__ __forceinline__ float2 cmul_rn (float2 a, float2 b) {
 struct StreamState {
 	// RF DC remover, fm-processor.cpp:425 — tracked in double at the fm rate
 	double  dc_re, dc_im;
-	float   dcc_re, dcc_im;          // clamped DC estimate at the previous fm-rate sample
+	float   sprev [4];               // 12-sample block sums S[m-1], S[m-2] (re, im each)
 	// fm_Demodulator members, fm-demodulator.cpp:79-86
 	float   Imin1, Qmin1, Imin2, Qmin2;
 	float   fm_afc, am_carr_ampl;
@@ -56,7 +56,7 @@ struct StreamState {
 	float   peak_l, peak_r;
 	int32_t peak_cnt;
 	float   peak_l_db, peak_r_db;
-	int32_t pad [3];
+	int32_t pad [1];
 };
 
 // Settings snapshot taken at a process boundary (fm-processor.cpp:397-413 does the same

@@ -18,7 +18,8 @@ constexpr int kDiRun     = 8;                 // consecutive fm samples per thre
 constexpr int kDiBlock   = kDiThreads * kDiRun;
 
 struct DiscrParams {
-	float  sumC, sumiC12;       // sum of composite taps; sum (i C[i]) / 12
+	float  sumC, sumCm;         // sum of the plain composite taps C; of the DC-folded taps C'
+	float  gb0, gb1, gb2;       // alpha * block means of the tail sums g (tables.cpp)
 	float  Gre, Gim;            // constant complex gain of the cascade
 	double alpha, beta;         // alpha = (float)1/inputRate; beta = (1 - alpha)^12
 	float  lgain, rgain;
@@ -86,6 +87,9 @@ StreamState &st = state [stream];
 const float2 *Us = U + (int64_t)stream * pitch;
 const float2 *Ss = Ssum + (int64_t)stream * pitch;
 
+//	read before anything of this call can overwrite it
+const float2 sp1 = make_float2 (st.sprev [0], st.sprev [1]);
+const float2 sp2 = make_float2 (st.sprev [2], st.sprev [3]);
 	for (int i = tid; i < 8193; i += kDiThreads) sPPY [i] = atanPPY [i];
 	if (tid == 0) {
 	   sCarry.re = st.dc_re; sCarry.im = st.dc_im;
@@ -146,13 +150,10 @@ double pw [6];
 	      r.re = w.re * dl + excl.re;
 	      r.im = w.im * dl + excl.im;
 	   }
-	   float2 cprev;
-	   {  // clamped estimate at the sample before this thread's run
-	      const float lim = 0.01f;
-	      cprev.x = fminf (fmaxf ((float)r.re, -lim), lim);
-	      cprev.y = fminf (fmaxf ((float)r.im, -lim), lim);
-	      if (!P.dc_remove) cprev = make_float2 (0.f, 0.f);
-	   }
+	   // block sums of the two fm-rate samples before this thread's run (for the clamped case)
+	   float2 sm1, sm2;
+	   sm1 = (j0 >= 1 && j0 - 1 < M) ? Ss [j0 - 1] : sp1;
+	   sm2 = (j0 >= 2 && j0 - 2 < M) ? Ss [j0 - 2] : (j0 == 1 ? sp1 : sp2);
 //	-- per-sample: corrected, gained, normalised sample ------------------------------
 	   float2 z [kDiRun], nq [kDiRun];
 	   float  za [kDiRun];
@@ -166,13 +167,22 @@ double pw [6];
 	         c.x = fminf (fmaxf ((float)r.re, -lim), lim);
 	         c.y = fminf (fmaxf ((float)r.im, -lim), lim);
 	         if (j0 + j == M - 1) {             // state handed to the next call
-	            st.dc_re = r.re; st.dc_im = r.im; st.dcc_re = c.x; st.dcc_im = c.y;
+	            st.dc_re = r.re; st.dc_im = r.im;
 	         }
 	      }
-	      // sum_i C[i] c[n-i]  ~=  c_m sumC - (c_m - c_{m-1}) sum(i C[i]) / 12
-	      const float kx = c.x * P.sumC - (c.x - cprev.x) * P.sumiC12;
-	      const float ky = c.y * P.sumC - (c.y - cprev.y) * P.sumiC12;
-	      cprev = c;
+	      // K1 ran the DC-folded taps C' = C + alpha g.  Free-running component: subtract
+	      // r sum(C').  Component on the clamp (or DC removal off): the subtracted value is the
+	      // constant c, so take alpha sum_i g[i] x[n-i] back out via the 12-sample block sums.
+	      const float wx = P.gb0 * s [j].x + P.gb1 * sm1.x + P.gb2 * sm2.x;
+	      const float wy = P.gb0 * s [j].y + P.gb1 * sm1.y + P.gb2 * sm2.y;
+	      const bool freex = P.dc_remove && c.x == (float)r.re;
+	      const bool freey = P.dc_remove && c.y == (float)r.im;
+	      const float kx = freex ? c.x * P.sumCm : c.x * P.sumC + wx;
+	      const float ky = freey ? c.y * P.sumCm : c.y * P.sumC + wy;
+	      sm2 = sm1; sm1 = s [j];
+	      if (j0 + j == M - 1) {
+	         st.sprev [0] = sm1.x; st.sprev [1] = sm1.y; st.sprev [2] = sm2.x; st.sprev [3] = sm2.y;
+	      }
 	      // IQ gain (fm-processor.cpp:462-464) commutes with the real-tap FIR
 	      const float vx = (u [j].x - kx) * P.lgain;
 	      const float vy = (u [j].y - ky) * P.rgain;

@@ -83,7 +83,11 @@ static void default_settings (Settings &s, int32_t fm_rate) {
 	s.panorama = 1.0f;        // :128
 	s.left_ch = s.right_ch = 1.0f;                      // :157-158
 	s.deemph_us = 50;
-	s.deemph_alpha = (float)(1.0 / (fm_rate / (1000000.0 / 50.0 + 1)));   // ctor formula :174
+	{  // the constructor's own formula (:174) is always overwritten by setDeemphasis through
+	   // make_newProcessor (radio.cpp:940, default 50 us radio.cpp:2129); start from the latter
+	   float Tau = 1000000.0 / 50;
+	   s.deemph_alpha = 1.0 / (float (fm_rate) / Tau + 1.0);
+	}
 }
 
 // uploads constant-memory taps and derives the launch parameters that depend on the tables
@@ -240,6 +244,8 @@ cudaError_t e;
 	if ((e = cudaFuncSetAttribute (frontend_fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                               kFeSmemBytes)) != cudaSuccess) return fail (e, "smem attr K1");
 	if ((e = cudaFuncSetAttribute (sequential_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                               (cfg -> fm_rate / 4 + 1) * (int)sizeof (float))) != cudaSuccess ||
+	    (e = cudaFuncSetAttribute (sequential_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                               (cfg -> fm_rate / 4 + 1) * (int)sizeof (float))) != cudaSuccess)
 	   return fail (e, "smem attr K3");
 int rc = rebuild_tables (h);
@@ -314,7 +320,8 @@ int rc;
 //	K2 ------------------------------------------------------------------------------------
 const float *consts = h -> tables.payload () + th.off_comp_consts;
 DiscrParams dp;
-	dp.sumC = consts [0]; dp.sumiC12 = consts [1] / 12.0f;
+	dp.sumC = consts [0]; dp.sumCm = consts [1];
+	dp.gb0 = consts [5]; dp.gb1 = consts [6]; dp.gb2 = consts [7];
 	dp.Gre = consts [2]; dp.Gim = consts [3];
 	dp.alpha = (double)(1.0f / h -> cfg.input_rate);          // rfDcAlpha, fm-processor.cpp:379
 	dp.beta = pow (1.0 - dp.alpha, (double)kDecim);
@@ -341,9 +348,15 @@ SeqParams sp;
 	}
 	sp.n_streams = S;
 const int seq_blocks = (S + kSeqLanes - 1) / kSeqLanes;
-	sequential_kernel<true><<<seq_blocks, kSeqLanes, (h -> lut.quarter + 1) * sizeof (float), h -> stream>>> (
-	      h -> d_res, h -> d_zabs, h -> d_iqn, h -> cap_fm, M, sp, h -> lut, T + th.off_atan,
-	      h -> d_state, h -> d_demod, h -> d_phase, h -> d_locked);
+const size_t seq_smem = (h -> lut.quarter + 1) * sizeof (float);
+	if (st.decoder == 2)
+	   sequential_kernel<true><<<seq_blocks, kSeqLanes, seq_smem, h -> stream>>> (
+	         h -> d_res, h -> d_zabs, h -> d_iqn, h -> cap_fm, M, sp, h -> lut, T + th.off_atan,
+	         h -> d_state, h -> d_demod, h -> d_phase, h -> d_locked);
+	else
+	   sequential_kernel<false><<<seq_blocks, kSeqLanes, seq_smem, h -> stream>>> (
+	         h -> d_res, h -> d_zabs, h -> d_iqn, h -> cap_fm, M, sp, h -> lut, T + th.off_atan,
+	         h -> d_state, h -> d_demod, h -> d_phase, h -> d_locked);
 	h -> launches ++;
 //	K4 ------------------------------------------------------------------------------------
 	{
@@ -580,7 +593,7 @@ int sdrjfm_set_dc_remove (sdrjfm_handle *h, int32_t on) {
 	h -> set.dc_remove = on != 0;
 //	setDCRemove also zeroes RfDC (:917-920): clear the DC fields of every stream
 	CK (cudaSetDevice (h -> cfg.device));
-	CK (cudaMemset2DAsync (h -> d_state, sizeof (StreamState), 0, 2 * sizeof (double) + 2 * sizeof (float),
+	CK (cudaMemset2DAsync (h -> d_state, sizeof (StreamState), 0, 2 * sizeof (double),
 	                       h -> cfg.n_streams, h -> stream));
 	return SDRJFM_OK;
 }

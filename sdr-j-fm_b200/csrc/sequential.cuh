@@ -17,35 +17,44 @@
 namespace sdrjfm {
 
 struct SinLut {
-	const float *q;          // quarter wave, Rate/4 + 1 entries (shared or global memory)
+	const float *q;          // quarter wave, Rate/4 + 1 entries (global copy)
 	int32_t rate, quarter;
 	int32_t sin_exc_idx [kMaxSinExc]; float sin_exc_val [kMaxSinExc];
 	int32_t cos_exc_idx [kMaxSinExc]; float cos_exc_val [kMaxSinExc];
 	double  C;               // Rate / (2 pi), sincos.cpp:45
 };
 
-__device__ __forceinline__ float lut_sin_idx (const SinLut &L, int32_t idx) {
+// Table value sin (2 pi idx / Rate) for 0 <= idx < Rate from the quarter wave `q`.
+// Every exception sits where the reflected index is 0 (the zero crossings), so the
+// exception list is only consulted there.
+__device__ __forceinline__ float lut_sin_idx (const SinLut &L, const float *q, int32_t idx) {
+const int32_t Q = L.quarter, H = 2 * Q;
+int32_t k = idx >= H ? idx - H : idx;          // [0, H)
+	k = k > Q ? H - k : k;                         // [0, Q]
+float v = q [k];
+	v = idx >= H ? -v : v;
+	if (k == 0 && idx != 0) {
 #pragma unroll
-	for (int e = 0; e < kMaxSinExc; e ++)
-	   if (idx == L.sin_exc_idx [e]) return L.sin_exc_val [e];
-const int32_t Q = L.quarter;
-	if (idx <= Q) return L.q [idx];
-	if (idx <= 2 * Q) return L.q [2 * Q - idx];
-	if (idx <= 3 * Q) return -L.q [idx - 2 * Q];
-	return -L.q [L.rate - idx];
+	   for (int e = 0; e < kMaxSinExc; e ++)
+	      if (idx == L.sin_exc_idx [e]) v = L.sin_exc_val [e];
+	}
+	return v;
 }
 
-__device__ __forceinline__ float lut_cos_idx (const SinLut &L, int32_t idx) {
-#pragma unroll
-	for (int e = 0; e < kMaxSinExc; e ++)
-	   if (idx == L.cos_exc_idx [e]) return L.cos_exc_val [e];
-int32_t s = idx + L.quarter;
+__device__ __forceinline__ float lut_cos_idx (const SinLut &L, const float *q, int32_t idx) {
+const int32_t Q = L.quarter, H = 2 * Q;
+int32_t s = idx + Q;
 	if (s >= L.rate) s -= L.rate;
-const int32_t Q = L.quarter;
-	if (s <= Q) return L.q [s];
-	if (s <= 2 * Q) return L.q [2 * Q - s];
-	if (s <= 3 * Q) return -L.q [s - 2 * Q];
-	return -L.q [L.rate - s];
+int32_t k = s >= H ? s - H : s;
+	k = k > Q ? H - k : k;
+float v = q [k];
+	v = s >= H ? -v : v;
+	if (k == 0) {
+#pragma unroll
+	   for (int e = 0; e < kMaxSinExc; e ++)
+	      if (idx == L.cos_exc_idx [e]) v = L.cos_exc_val [e];
+	}
+	return v;
 }
 
 // SinCos::fromPhasetoIndex for Phase >= 0 (sincos.cpp:54-56): int32 (Phase * C) % Rate
@@ -56,9 +65,9 @@ int32_t i = (int32_t)((double)phase * L.C);
 }
 
 // SinCos::getSin, sincos.cpp:75-79
-__device__ __forceinline__ float lut_getSin (const SinLut &L, float phase) {
-	if (phase < 0.f) return -lut_sin_idx (L, phase_index (L, -phase));
-	return lut_sin_idx (L, phase_index (L, phase));
+__device__ __forceinline__ float lut_getSin (const SinLut &L, const float *q, float phase) {
+	if (phase < 0.f) return -lut_sin_idx (L, q, phase_index (L, -phase));
+	return lut_sin_idx (L, q, phase_index (L, phase));
 }
 
 // the phase normalisation shared by SinCos::getCos / getComplex, sincos.cpp:81-91
@@ -68,12 +77,19 @@ __device__ __forceinline__ int32_t cos_phase_index (const SinLut &L, float phase
 	return phase_index (L, phase);
 }
 
-// PI_Constrain, includes/fm-constants.h:148-158 (all comparisons and fmod in double)
+// PI_Constrain, includes/fm-constants.h:148-158.  The reference compares the float against
+// the DOUBLE 2*M_PI; kTwoPiF is the float just above that double and there is no float in
+// between, so the float comparisons below select exactly the same branch.  fmod (v, 2 pi)
+// for 2 pi <= v < 4 pi is the exact difference v - 2 pi (Sterbenz), the common wrap.
 __device__ __forceinline__ float pi_constrain (float val) {
+const float kTwoPiF = 6.2831855f;
+	if (val >= 0.f && val < kTwoPiF) return val;
 const double v = (double)val;
-	if (0 <= v && v < 2 * M_PI) return val;
-	if (v >= 2 * M_PI) return (float)fmod (v, 2 * M_PI);
-	if (v > -2 * M_PI) return (float)(v + 2 * M_PI);
+	if (val >= kTwoPiF) {
+	   if (val < 12.566370f) return (float)(v - 2 * M_PI);
+	   return (float)fmod (v, 2 * M_PI);
+	}
+	if (val > -kTwoPiF) return (float)(v + 2 * M_PI);
 	return (float)(2 * M_PI - fmod (-v, 2 * M_PI));
 }
 
@@ -89,87 +105,111 @@ struct SeqParams {
 
 constexpr int kSeqLanes = 32;
 
-// res_raw, zabs, iqn : K2 outputs.  demod / pilot_phase / locked : fm-rate outputs.
-template <bool SMEM_LUT>
-__global__ void __launch_bounds__ (kSeqLanes)
-sequential_kernel (const float *__restrict__ res_raw, const float *__restrict__ zabs,
-                   const float2 *__restrict__ iqn, int64_t pitch, int32_t M,
-                   SeqParams P, SinLut L, const float *__restrict__ atanPPY,
-                   StreamState *__restrict__ state,
-                   float *__restrict__ demod_out, float *__restrict__ phase_out,
-                   uint8_t *__restrict__ locked_out) {
-extern __shared__ float sq [];
-	if (SMEM_LUT) {
-	   for (int i = threadIdx.x; i <= L.quarter; i += blockDim.x) sq [i] = L.q [i];
-	   __syncthreads ();
-	   L.q = sq;
-	}
-const int stream = blockIdx.x * blockDim.x + threadIdx.x;
-	if (stream >= P.n_streams) return;
-StreamState &st = state [stream];
-const float *rr = res_raw + (int64_t)stream * pitch;
-const float *za = zabs + (int64_t)stream * pitch;
-const float2 *nq = iqn ? iqn + (int64_t)stream * pitch : nullptr;
-float *dm = demod_out + (int64_t)stream * pitch;
-float *ph = phase_out + (int64_t)stream * pitch;
-uint8_t *lk = locked_out + (int64_t)stream * pitch;
+struct SeqCarry {      // loop-carried registers of one stream
+	float fm_afc, am, phase, oldv, plock, nco, incr;
+	int   locked, stable;
+};
 
-float fm_afc = st.fm_afc, am = st.am_carr_ampl;
-float phase = st.pilot_phase, oldv = st.pilot_old, plock = st.pilot_lock;
-int   locked = st.pilot_locked, stable = st.pilot_stable_cnt;
-float nco = st.pll_nco_phase, incr = st.pll_phase_incr;
-
+template <bool PLL_DECODER>
+__device__ __forceinline__ void seq_step (const SeqParams &P, const SinLut &L, const float *q,
+                                          const float *atanPPY, SeqCarry &c, float res, float zAbs,
+                                          float2 nqv, float &demod_o, float &phase_o, uint8_t &lock_o) {
 const float carrierAlpha = 0.0010f, fmDcAlpha = 0.0001f;          // fm-demodulator.cpp:115-117
 const float oneMinusCarrier = fsub (1.0f, carrierAlpha);
 const float oneMinusDc = fsub (1.0f, fmDcAlpha);
 const float lockAlpha = 1.0f / 3000.0f;                           // pilot-recover.cpp:57
 const double oneMinusLock = 1.0 - (double)lockAlpha;
-
-	for (int32_t m = 0; m < M; m ++) {
-	   float res = rr [m];
-	   const float zAbs = za [m];
-	   am = fadd (fmul (oneMinusCarrier, am), fmul (carrierAlpha, zAbs));
-	   if (P.decoder == 2 || P.decoder == 1) {
+	c.am = fadd (fmul (oneMinusCarrier, c.am), fmul (carrierAlpha, zAbs));
+	if (PLL_DECODER) {
 //	pllC::do_pll on the normalised sample, pllC.cpp:67-90
-	      const float2 s = nq [m];
-	      const int32_t ci = cos_phase_index (L, nco);
-	      const float2 osc = make_float2 (lut_cos_idx (L, ci), lut_sin_idx (L, ci));
-	      const float2 d = cmul_rn (make_float2 (osc.x, -osc.y), s);
-	      const float perr = lut_atan2 (atanPPY, d.y, d.x);
-	      incr = fadd (fmul (fsub (1.0f, P.pll_beta), perr), fmul (P.pll_beta, incr));
-	      if (incr < P.pll_lo || incr > P.pll_hi) incr = P.pll_reset;
-	      nco = fadd (nco, incr);
-	      if ((double)nco >= 2 * M_PI) nco = (float)fmod ((double)nco, 2 * M_PI);
-	      else while (nco < 0.f) nco = (float)((double)nco + 2 * M_PI);
-	      res = incr;
-	   }
-	   fm_afc = fadd (fmul (oneMinusDc, fm_afc), fmul (fmDcAlpha, res));
-	   const float demod = fdiv (fmul (fmul (20.0f, fsub (res, fm_afc)), 1.0f), P.K_FM);
-
-//	pilotRecovery::getPilotPhase (5 * demod), pilot-recover.cpp:54-83
-	   const float pilot = fmul (5.0f, demod);
-	   const float osc = lut_getSin (L, phase);
-	   const float perr = fmul (pilot, osc);
-	   phase = fadd (phase, fmul (perr, P.gain));
-	   const float cur = pi_constrain (phase);
-	   phase = pi_constrain (fadd (phase, P.omega));
-	   const float quad = fdiv (fsub (osc, oldv), P.omega);
-	   oldv = osc;
-	   plock = (float)((double)fmul (lockAlpha, fmul (-quad, pilot)) +
-	                   (double)plock * oneMinusLock);
-	   if (plock > 0.07f) {
-	      if (locked || ++stable > P.lock_half_rate) locked = 1;
-	   }
-	   else { locked = 0; stable = 0; }
-
-	   dm [m] = demod;
-	   ph [m] = cur;
-	   lk [m] = (uint8_t)locked;
+	   const int32_t ci = cos_phase_index (L, c.nco);
+	   const float2 osc = make_float2 (lut_cos_idx (L, q, ci), lut_sin_idx (L, q, ci));
+	   const float2 d = cmul_rn (make_float2 (osc.x, -osc.y), nqv);
+	   const float perr = lut_atan2 (atanPPY, d.y, d.x);
+	   c.incr = fadd (fmul (fsub (1.0f, P.pll_beta), perr), fmul (P.pll_beta, c.incr));
+	   if (c.incr < P.pll_lo || c.incr > P.pll_hi) c.incr = P.pll_reset;
+	   c.nco = fadd (c.nco, c.incr);
+	   if ((double)c.nco >= 2 * M_PI) c.nco = (float)fmod ((double)c.nco, 2 * M_PI);
+	   else while (c.nco < 0.f) c.nco = (float)((double)c.nco + 2 * M_PI);
+	   res = c.incr;
 	}
-	st.fm_afc = fm_afc; st.am_carr_ampl = am;
-	st.pilot_phase = phase; st.pilot_old = oldv; st.pilot_lock = plock;
-	st.pilot_locked = locked; st.pilot_stable_cnt = stable;
-	st.pll_nco_phase = nco; st.pll_phase_incr = incr;
+	c.fm_afc = fadd (fmul (oneMinusDc, c.fm_afc), fmul (fmDcAlpha, res));
+const float demod = fdiv (fmul (fmul (20.0f, fsub (res, c.fm_afc)), 1.0f), P.K_FM);
+//	pilotRecovery::getPilotPhase (5 * demod), pilot-recover.cpp:54-83
+const float pilot = fmul (5.0f, demod);
+const float osc = lut_getSin (L, q, c.phase);
+const float perr = fmul (pilot, osc);
+	c.phase = fadd (c.phase, fmul (perr, P.gain));
+const float cur = pi_constrain (c.phase);
+	c.phase = pi_constrain (fadd (c.phase, P.omega));
+const float quad = fdiv (fsub (osc, c.oldv), P.omega);
+	c.oldv = osc;
+	c.plock = (float)((double)fmul (lockAlpha, fmul (-quad, pilot)) + (double)c.plock * oneMinusLock);
+	if (c.plock > 0.07f) {
+	   if (c.locked || ++c.stable > P.lock_half_rate) c.locked = 1;
+	}
+	else { c.locked = 0; c.stable = 0; }
+	demod_o = demod; phase_o = cur; lock_o = (uint8_t)c.locked;
+}
+
+// res_raw, zabs, iqn : K2 outputs.  demod / pilot_phase / locked : fm-rate outputs.
+// One lane per stream; the quarter-wave sine table lives in shared memory.
+template <bool PLL_DECODER>
+__global__ void __launch_bounds__ (kSeqLanes)
+sequential_kernel (const float *__restrict__ res_raw, const float *__restrict__ zabs,
+                   const float2 *__restrict__ iqn, int64_t pitch, int32_t M,
+                   const SeqParams P, const SinLut L, const float *__restrict__ atanPPY,
+                   StreamState *__restrict__ state,
+                   float *__restrict__ demod_out, float *__restrict__ phase_out,
+                   uint8_t *__restrict__ locked_out) {
+extern __shared__ float sq [];
+	for (int i = threadIdx.x; i <= L.quarter; i += blockDim.x) sq [i] = L.q [i];
+	__syncthreads ();
+const int stream = blockIdx.x * blockDim.x + threadIdx.x;
+	if (stream >= P.n_streams) return;
+StreamState &st = state [stream];
+const float *rr = res_raw + (int64_t)stream * pitch;
+const float *za = zabs + (int64_t)stream * pitch;
+const float2 *nq = iqn + (int64_t)stream * pitch;
+float *dm = demod_out + (int64_t)stream * pitch;
+float *ph = phase_out + (int64_t)stream * pitch;
+uint8_t *lk = locked_out + (int64_t)stream * pitch;
+
+SeqCarry c;
+	c.fm_afc = st.fm_afc; c.am = st.am_carr_ampl;
+	c.phase = st.pilot_phase; c.oldv = st.pilot_old; c.plock = st.pilot_lock;
+	c.locked = st.pilot_locked; c.stable = st.pilot_stable_cnt;
+	c.nco = st.pll_nco_phase; c.incr = st.pll_phase_incr;
+
+int32_t m = 0;
+	for (; m + 4 <= M; m += 4) {
+	   const float4 r4 = *reinterpret_cast<const float4 *>(rr + m);
+	   const float4 z4 = *reinterpret_cast<const float4 *>(za + m);
+	   float2 n4 [4];
+	   if (PLL_DECODER) {
+#pragma unroll
+	      for (int k = 0; k < 4; k ++) n4 [k] = nq [m + k];
+	   }
+	   const float rv [4] = { r4.x, r4.y, r4.z, r4.w }, zv [4] = { z4.x, z4.y, z4.z, z4.w };
+	   float d4 [4], p4 [4]; uint8_t l4 [4];
+#pragma unroll
+	   for (int k = 0; k < 4; k ++)
+	      seq_step<PLL_DECODER> (P, L, sq, atanPPY, c, rv [k], zv [k],
+	                             PLL_DECODER ? n4 [k] : make_float2 (0.f, 0.f), d4 [k], p4 [k], l4 [k]);
+	   *reinterpret_cast<float4 *>(dm + m) = make_float4 (d4 [0], d4 [1], d4 [2], d4 [3]);
+	   *reinterpret_cast<float4 *>(ph + m) = make_float4 (p4 [0], p4 [1], p4 [2], p4 [3]);
+	   *reinterpret_cast<uchar4 *>(lk + m) = make_uchar4 (l4 [0], l4 [1], l4 [2], l4 [3]);
+	}
+	for (; m < M; m ++) {
+	   float d, p; uint8_t l;
+	   seq_step<PLL_DECODER> (P, L, sq, atanPPY, c, rr [m], za [m],
+	                          PLL_DECODER ? nq [m] : make_float2 (0.f, 0.f), d, p, l);
+	   dm [m] = d; ph [m] = p; lk [m] = l;
+	}
+	st.fm_afc = c.fm_afc; st.am_carr_ampl = c.am;
+	st.pilot_phase = c.phase; st.pilot_old = c.oldv; st.pilot_lock = c.plock;
+	st.pilot_locked = c.locked; st.pilot_stable_cnt = c.stable;
+	st.pll_nco_phase = c.nco; st.pll_phase_incr = c.incr;
 }
 
 // K6a — de-emphasis one-pole and gain, fm-processor.cpp:594-595 and :303-306, one lane per

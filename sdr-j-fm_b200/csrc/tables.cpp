@@ -168,11 +168,25 @@ Packer pk;
 	for (int j = 0; j < h.ntaps2; j ++)
 	   for (int i = 0; i < h.ntaps1; i ++)
 	      cd [h.decim1 * j + i] += (double)k2 [j].imag () * (double)k1 [i].imag ();
+//	RF DC removal folded into the taps.  The reference subtracts the one-pole
+//	estimate r[n] (fm-processor.cpp:425,444) BEFORE the FIR; inside the 37-sample window
+//	r[n-i] = r[n] - alpha * sum_{j=n-i+1..n} (x[j] - r[j-1]), hence
+//	  sum_i C[i] (x[n-i] - r[n-i]) = sum_i (C[i] + alpha g[i]) x[n-i] - r[n] (sumC + alpha sum g) + O(alpha^2)
+//	with the tail sums g[i] = sum_{k>i} C[k].  The kernel therefore runs the taps
+//	C'[i] = C[i] + alpha g[i]; while a component of r sits on the +-0.01 clamp the subtracted
+//	value is constant instead, and the fm-rate stage takes alpha*sum g x back out using the
+//	12-sample block sums (block means gbar[0..2] of g).
+	const double alpha = (double)(1.0f / input_rate);      // rfDcAlpha, fm-processor.cpp:379
+	std::vector<double> gt (h.ncomp, 0.0);
+	for (int i = 0; i < h.ncomp; i ++)
+	   for (int k = i + 1; k < h.ncomp; k ++) gt [i] += (double)(float)cd [k];
 	std::vector<float> comp (h.ncomp);
-	double sumC = 0, sumiC = 0;
+	double sumC = 0, sumCm = 0, gbar [3] = { 0, 0, 0 };
 	for (int i = 0; i < h.ncomp; i ++) {
-	   comp [i] = (float)cd [i];
-	   sumC += comp [i]; sumiC += (double)i * comp [i];
+	   const double c = (double)(float)cd [i];
+	   comp [i] = (float)(c + alpha * gt [i]);
+	   sumC += c; sumCm += comp [i];
+	   if (i < 36) gbar [i / 12] += gt [i] / 12.0;
 	}
 	h.off_comp = pk.put (comp);
 	std::complex<double> g1 ((double)k1 [h.ntaps1 / 2].real () / k1 [h.ntaps1 / 2].imag (), 1.0);
@@ -183,8 +197,9 @@ Packer pk;
 	float Delta_F = 0.95 * fm_rate / 2;
 	float B_FM    = 2 * (Delta_F + F_G);
 	float K_FM    = 2 * B_FM * M_PI / F_G;
-	float consts [8] = { (float)sumC, (float)sumiC, (float)G.real (), (float)G.imag (),
-	                     K_FM, 0, 0, 0 };
+	float consts [8] = { (float)sumC, (float)sumCm, (float)G.real (), (float)G.imag (),
+	                     K_FM, (float)(alpha * gbar [0]), (float)(alpha * gbar [1]),
+	                     (float)(alpha * gbar [2]) };
 	h.off_comp_consts = pk.put (consts, 8);
 
 //	compAtan, Xtan2.cpp:26-38 (Stretch is a float holding M_PI)

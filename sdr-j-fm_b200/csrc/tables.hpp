@@ -47,8 +47,8 @@ struct TableHeader {
 	int32_t  reserved0;
 	int64_t  payload_floats;
 	int64_t  off_fmband1, off_fmband2, off_rdsdecim;     // complex taps
-	int64_t  off_comp;          // ncomp real composite taps  C[i] (input-rate index i)
-	int64_t  off_comp_consts;   // [sumC, sumiC, Gre, Gim, K_FM, pad, pad, pad]
+	int64_t  off_comp;          // ncomp real composite taps C'[i] = C[i] + alpha g[i] (DC removal folded in)
+	int64_t  off_comp_consts;   // [sumC, sumC', Gre, Gim, K_FM, alpha*gbar0, alpha*gbar1, alpha*gbar2]
 	int64_t  off_atan;          // 8 * 8193 floats, order PPY PPX PNY PNX NPY NPX NNY NNX
 	int64_t  off_sincos;        // fm_rate complex (cos, sin)
 	int64_t  off_arcsine;       // 32769 floats

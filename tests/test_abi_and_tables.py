@@ -70,6 +70,11 @@ def test_composite_equals_cascade(pkg):
     for j in range(3):
         casc[6 * j:6 * j + 25] += k2[j] * k1
     G = complex(T.consts[2], T.consts[3])
-    comp = T.composite.astype(np.float64) * G
+    # the stored taps are C' = C + alpha*g (RF DC removal folded in, g = tail sums of C)
+    alpha = float(np.float32(1.0) / np.float32(2304000))
+    C = (casc / G).real
+    g = np.array([C[i + 1:].sum() for i in range(37)])
+    comp = (T.composite.astype(np.float64) - alpha * g) * G
     assert np.abs(comp - casc).max() < 3e-7 * np.abs(casc).max()
-    assert abs(T.consts[0] - T.composite.astype(np.float64).sum()) < 1e-6
+    assert abs(T.consts[0] - C.sum()) < 1e-6
+    assert abs(T.consts[1] - T.composite.astype(np.float64).sum()) < 1e-6
