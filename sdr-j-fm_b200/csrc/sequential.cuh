@@ -27,8 +27,13 @@ struct SinLut {
 // Table value sin (2 pi idx / Rate) for 0 <= idx < Rate from the quarter wave `q`.
 // Every exception sits where the reflected index is 0 (the zero crossings), so the
 // exception list is only consulted there.
+// (the fm rate is a compile-time constant of the device code: 192000 is the only rate the
+// reference really supports; the host refuses anything else)
+constexpr int32_t kFmRate = 192000;
+__device__ int32_t phase_index_rare (float phase);
+
 __device__ __forceinline__ float lut_sin_idx (const SinLut &L, const float *q, int32_t idx) {
-const int32_t Q = L.quarter, H = 2 * Q;
+constexpr int32_t Q = kFmRate / 4, H = 2 * Q;
 int32_t k = idx >= H ? idx - H : idx;          // [0, H)
 	k = k > Q ? H - k : k;                         // [0, Q]
 float v = q [k];
@@ -42,9 +47,9 @@ float v = q [k];
 }
 
 __device__ __forceinline__ float lut_cos_idx (const SinLut &L, const float *q, int32_t idx) {
-const int32_t Q = L.quarter, H = 2 * Q;
+constexpr int32_t Q = kFmRate / 4, H = 2 * Q;
 int32_t s = idx + Q;
-	if (s >= L.rate) s -= L.rate;
+	if (s >= kFmRate) s -= kFmRate;
 int32_t k = s >= H ? s - H : s;
 	k = k > Q ? H - k : k;
 float v = q [k];
@@ -59,8 +64,9 @@ float v = q [k];
 
 // SinCos::fromPhasetoIndex for Phase >= 0 (sincos.cpp:54-56): int32 (Phase * C) % Rate
 __device__ __forceinline__ int32_t phase_index (const SinLut &L, float phase) {
-int32_t i = (int32_t)((double)phase * L.C);
-	if (i >= L.rate) i %= L.rate;
+int32_t i = (int32_t)((double)phase * (kFmRate / (2 * M_PI)));
+	if (i >= kFmRate) i -= kFmRate;                // phases here are < 4 pi ...
+	if (i >= kFmRate || i < 0) i = phase_index_rare (phase);   // ... anything else: exact slow path
 	return i;
 }
 
@@ -81,16 +87,25 @@ __device__ __forceinline__ int32_t cos_phase_index (const SinLut &L, float phase
 // the DOUBLE 2*M_PI; kTwoPiF is the float just above that double and there is no float in
 // between, so the float comparisons below select exactly the same branch.  fmod (v, 2 pi)
 // for 2 pi <= v < 4 pi is the exact difference v - 2 pi (Sterbenz), the common wrap.
+__device__ __noinline__ float pi_constrain_rare (float val) {
+const float kTwoPiF = 6.2831855f;
+const double v = (double)val;
+	if (val >= kTwoPiF) return (float)fmod (v, 2 * M_PI);
+	if (val > -kTwoPiF) return (float)(v + 2 * M_PI);
+	return (float)(2 * M_PI - fmod (-v, 2 * M_PI));
+}
+
 __device__ __forceinline__ float pi_constrain (float val) {
 const float kTwoPiF = 6.2831855f;
 	if (val >= 0.f && val < kTwoPiF) return val;
-const double v = (double)val;
-	if (val >= kTwoPiF) {
-	   if (val < 12.566370f) return (float)(v - 2 * M_PI);
-	   return (float)fmod (v, 2 * M_PI);
-	}
-	if (val > -kTwoPiF) return (float)(v + 2 * M_PI);
-	return (float)(2 * M_PI - fmod (-v, 2 * M_PI));
+	if (val >= kTwoPiF && val < 12.566370f) return (float)((double)val - 2 * M_PI);
+	return pi_constrain_rare (val);
+}
+
+// rare paths of SinCos index arithmetic, kept out of line so the hot loop stays small
+__device__ __noinline__ int32_t phase_index_rare (float phase) {
+int32_t i = (int32_t)((double)phase * (kFmRate / (2 * M_PI)));
+	return i % kFmRate;
 }
 
 struct SeqParams {
