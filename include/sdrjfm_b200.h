@@ -115,6 +115,10 @@ void *sdrjfm_cuda_stream (sdrjfm_handle *h);
 int  sdrjfm_run_frontend_only (sdrjfm_handle *h, const float *d_iq, int64_t n_in, int64_t in_pitch);
 /* number of kernel launches issued by the handle since creation                          */
 int64_t sdrjfm_launch_count (const sdrjfm_handle *h);
+/* diagnostics of the parallel-in-time pilot PLL solver for the last process call, per stream:
+ * [sum of iterations over windows, max iterations of a window, windows that fell back to the
+ * one-lane walk, number of windows]                                                      */
+int  sdrjfm_pilot_stats (sdrjfm_handle *h, int32_t *out /* [n_streams][4] */);
 
 /* --- settings: one per fmProcessor setter (includes/fm/fm-processor.h:122-157).  Applied
  * at the next process call, to all streams — the reference applies them at the next

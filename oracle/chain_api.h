@@ -72,6 +72,11 @@ typedef struct chain_meta {   /* SMetaData, fm-processor.h:91-101, as of the las
     /* returns fm-rate samples produced; *n_rds24 = 24 kHz samples produced */          \
     int64_t P##_process (void *h, const float *iq, int64_t n_in,                        \
                          const chain_taps *taps, int64_t *n_rds24);                     \
+    /* same chain entered AFTER the discriminator: feeds n_fm given demod values (e.g. the   \
+       GPU's own demod tap) through process_signal_with_rds .. gain, so that the stages      \
+       behind the discriminator can be compared on bit-identical inputs */                  \
+    int64_t P##_process_demod (void *h, const float *demod, int64_t n_fm,                   \
+                               const chain_taps *taps, int64_t *n_rds24);                   \
     void    P##_get_meta (void *h, chain_meta *m);                                      \
     /* table dumps used to pin the restatement bit for bit */                           \
     int32_t P##_dump_taps (void *h, int which, float *out, int32_t cap);

@@ -84,6 +84,10 @@ class Chain:
         f = lambda n: getattr(self.lib, f"{prefix}_{n}")
         self._create, self._destroy = f("create"), f("destroy")
         self._process, self._meta, self._dump = f("process"), f("get_meta"), f("dump_taps")
+        self._process_demod = f("process_demod")
+        self._process_demod.restype = C.c_int64
+        self._process_demod.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(ChainTaps),
+                                        C.POINTER(C.c_int64)]
         self._create.restype = C.c_void_p
         self._create.argtypes = [C.POINTER(ChainCfg)]
         self._destroy.argtypes = [C.c_void_p]
@@ -101,11 +105,18 @@ class Chain:
             self._destroy(self.h)
             self.h = None
 
+    def process_demod(self, demod, taps=TAPS):
+        """enter the chain AFTER the discriminator with given float32 demod values."""
+        demod = np.ascontiguousarray(demod, dtype=np.float32)
+        return self._run(self._process_demod, demod, demod.shape[0], demod.shape[0] + 2, taps)
+
     def process(self, iq, taps=TAPS):
         """iq: complex64[n]. Returns dict tap -> ndarray (fm-rate length, rds24 shorter)."""
         iq = np.ascontiguousarray(iq, dtype=np.complex64)
         n = iq.shape[0]
-        cap = n // 12 + 2
+        return self._run(self._process, iq, n, n // 12 + 2, taps)
+
+    def _run(self, fn, iq, n, cap, taps):
         bufs = {}
         t = ChainTaps()
         for name in taps:
@@ -118,7 +129,7 @@ class Chain:
             bufs[name] = a
             setattr(t, name, a.ctypes.data)
         nr = C.c_int64(0)
-        nfm = self._process(self.h, iq.ctypes.data, n, C.byref(t), C.byref(nr))
+        nfm = fn(self.h, iq.ctypes.data, n, C.byref(t), C.byref(nr))
         out = {}
         for name, a in bufs.items():
             out[name] = a[:nr.value] if name == "rds24" else a[:nfm]

@@ -410,6 +410,64 @@ struct Oracle {
 	   return res;
 	}
 
+//	one fm-rate sample after the discriminator (:515-648); also entered by orc_process_demod
+	void after_demod (float demod, cf v, const chain_taps *t, int64_t &nfm, int64_t &nrds) {
+	   // process_signal_with_rds, :689-759
+	   float curPhase = pilot_phase (5 * demod);
+	   const bool locked = pLocked;
+	   if (!locked) { pilotDelayPSS = 0; pss_reset (); }
+	   cf audio, rdsC (0, 0);
+	   if (cfg.fm_mode != 2 && (locked || !cfg.auto_mono)) {
+	      float ph = 2 * (curPhase + M_PI_4 + 0) - pilotDelayPSS;
+	      if (ph < -2 * M_PI) ph += 4 * M_PI;
+	      ph = fmod (ph, 2 * M_PI);
+	      pilotDelayPSS = cfg.pss_on ? pss_sample (demod, ph) : 0;
+	      float diff = 2.0 * (cfg.sound_sel == 6 ? sc. get_sin (ph) : real (sc. get_complex (ph))) * demod;
+	      audio = cf (demod, diff);
+	   }
+	   else audio = cf (demod, 0);
+	   if (cfg.rds_on) {
+	      float bp = rdsBp. pass_real (demod);
+	      cf hil = rdsHil. pass_cplx (cf (bp, 0));
+	      float thePhase = 3 * (rdsPhaseBuf [rdsPhaseIdx] + 0);
+	      rdsPhaseBuf [rdsPhaseIdx] = curPhase;
+	      rdsPhaseIdx = (rdsPhaseIdx + 1) % (int)rdsPhaseBuf. size ();
+	      cf osc (cosf (thePhase), -sinf (thePhase));
+	      rdsC = osc * hil;
+	   }
+	   // matrix and selector, :517-549
+	   const float sumLR = real (audio), diffLR = imag (audio);
+	   const float dw = diffLR * (cfg.fm_mode == 1 ? pan : 1.0f);
+	   const float left = sumLR + dw, right = sumLR - dw;
+	   switch (cfg.sound_sel) {
+	      default:
+	      case 0: audio = cf (left, right); break;
+	      case 1: audio = cf (right, left); break;
+	      case 2: audio = cf (left, left); break;
+	      case 3: audio = cf (right, right); break;
+	      case 4: audio = cf (sumLR, sumLR); break;
+	      case 5: case 6: audio = cf (dw, dw); break;
+	   }
+	   if (t -> fm_z) { t -> fm_z [2 * nfm] = real (v); t -> fm_z [2 * nfm + 1] = imag (v); }
+	   if (t -> demod) t -> demod [nfm] = demod;
+	   if (t -> pilot_phase) t -> pilot_phase [nfm] = curPhase;
+	   if (t -> locked) t -> locked [nfm] = locked ? 1 : 0;
+	   if (t -> pss_delay) t -> pss_delay [nfm] = pilotDelayPSS;
+	   if (t -> lr) { t -> lr [2 * nfm] = real (audio); t -> lr [2 * nfm + 1] = imag (audio); }
+	   if (t -> rds_cplx) { t -> rds_cplx [2 * nfm] = real (rdsC); t -> rds_cplx [2 * nfm + 1] = imag (rdsC); }
+	   if (cfg.rds_on) {
+	      cf r24;
+	      if (rdsDecim. pass (rdsC, &r24)) {                             // :553
+	         if (t -> rds24) { t -> rds24 [2 * nrds] = real (r24); t -> rds24 [2 * nrds + 1] = imag (r24); }
+	         nrds ++;
+	      }
+	   }
+	   if (audioOn) audio = audioLp. pass_cplx (audio);                  // :589-591
+	   audio = lastAudio = (audio - lastAudio) * deAlpha + lastAudio;    // :594-595
+	   const float gl = vol * lch * real (audio), gr = vol * rch * imag (audio);   // :304-305
+	   if (t -> audio192) { t -> audio192 [2 * nfm] = gl; t -> audio192 [2 * nfm + 1] = gr; }
+	}
+
 	int64_t process (const float *iq, int64_t n_in, const chain_taps *t, int64_t *n_rds24) {
 	   int64_t nfm = 0, nrds = 0;
 	   for (int64_t i = 0; i < n_in; i ++) {
@@ -429,61 +487,7 @@ struct Oracle {
 	      if (!band1. pass (v, &v)) continue;                               // :472-475
 	      if (!band2. pass (v, &v)) continue;
 	      float demod = demodulate (v);                                     // :497
-
-	      // process_signal_with_rds, :689-759
-	      float curPhase = pilot_phase (5 * demod);
-	      const bool locked = pLocked;
-	      if (!locked) { pilotDelayPSS = 0; pss_reset (); }
-	      cf audio, rdsC (0, 0);
-	      if (cfg.fm_mode != 2 && (locked || !cfg.auto_mono)) {
-	         float ph = 2 * (curPhase + M_PI_4 + 0) - pilotDelayPSS;
-	         if (ph < -2 * M_PI) ph += 4 * M_PI;
-	         ph = fmod (ph, 2 * M_PI);
-	         pilotDelayPSS = cfg.pss_on ? pss_sample (demod, ph) : 0;
-	         float diff = 2.0 * (cfg.sound_sel == 6 ? sc. get_sin (ph) : real (sc. get_complex (ph))) * demod;
-	         audio = cf (demod, diff);
-	      }
-	      else audio = cf (demod, 0);
-	      if (cfg.rds_on) {
-	         float bp = rdsBp. pass_real (demod);
-	         cf hil = rdsHil. pass_cplx (cf (bp, 0));
-	         float thePhase = 3 * (rdsPhaseBuf [rdsPhaseIdx] + 0);
-	         rdsPhaseBuf [rdsPhaseIdx] = curPhase;
-	         rdsPhaseIdx = (rdsPhaseIdx + 1) % (int)rdsPhaseBuf. size ();
-	         cf osc (cosf (thePhase), -sinf (thePhase));
-	         rdsC = osc * hil;
-	      }
-	      // matrix and selector, :517-549
-	      const float sumLR = real (audio), diffLR = imag (audio);
-	      const float dw = diffLR * (cfg.fm_mode == 1 ? pan : 1.0f);
-	      const float left = sumLR + dw, right = sumLR - dw;
-	      switch (cfg.sound_sel) {
-	         default:
-	         case 0: audio = cf (left, right); break;
-	         case 1: audio = cf (right, left); break;
-	         case 2: audio = cf (left, left); break;
-	         case 3: audio = cf (right, right); break;
-	         case 4: audio = cf (sumLR, sumLR); break;
-	         case 5: case 6: audio = cf (dw, dw); break;
-	      }
-	      if (t -> fm_z) { t -> fm_z [2 * nfm] = real (v); t -> fm_z [2 * nfm + 1] = imag (v); }
-	      if (t -> demod) t -> demod [nfm] = demod;
-	      if (t -> pilot_phase) t -> pilot_phase [nfm] = curPhase;
-	      if (t -> locked) t -> locked [nfm] = locked ? 1 : 0;
-	      if (t -> pss_delay) t -> pss_delay [nfm] = pilotDelayPSS;
-	      if (t -> lr) { t -> lr [2 * nfm] = real (audio); t -> lr [2 * nfm + 1] = imag (audio); }
-	      if (t -> rds_cplx) { t -> rds_cplx [2 * nfm] = real (rdsC); t -> rds_cplx [2 * nfm + 1] = imag (rdsC); }
-	      if (cfg.rds_on) {
-	         cf r24;
-	         if (rdsDecim. pass (rdsC, &r24)) {                             // :553
-	            if (t -> rds24) { t -> rds24 [2 * nrds] = real (r24); t -> rds24 [2 * nrds + 1] = imag (r24); }
-	            nrds ++;
-	         }
-	      }
-	      if (audioOn) audio = audioLp. pass_cplx (audio);                  // :589-591
-	      audio = lastAudio = (audio - lastAudio) * deAlpha + lastAudio;    // :594-595
-	      const float gl = vol * lch * real (audio), gr = vol * rch * imag (audio);   // :304-305
-	      if (t -> audio192) { t -> audio192 [2 * nfm] = gl; t -> audio192 [2 * nfm + 1] = gr; }
+	      after_demod (demod, v, t, nfm, nrds);
 	      nfm ++;
 	   }
 	   if (n_rds24) *n_rds24 = nrds;
@@ -498,6 +502,15 @@ void	orc_destroy (void *h) { delete (Oracle *)h; }
 int64_t	orc_process (void *h, const float *iq, int64_t n_in, const chain_taps *taps, int64_t *n_rds24) {
 	return ((Oracle *)h) -> process (iq, n_in, taps, n_rds24);
 }
+int64_t	orc_process_demod (void *h, const float *demod, int64_t n_fm, const chain_taps *taps,
+	                   int64_t *n_rds24) {
+Oracle *c = (Oracle *)h;
+int64_t nfm = 0, nrds = 0;
+	for (int64_t i = 0; i < n_fm; i ++) { c -> after_demod (demod [i], cf (0, 0), taps, nfm, nrds); nfm ++; }
+	if (n_rds24) *n_rds24 = nrds;
+	return nfm;
+}
+
 void	orc_get_meta (void *h, chain_meta *m) {
 Oracle *c = (Oracle *)h;
 	m -> dc_rf_re = real (c -> RfDC); m -> dc_rf_im = imag (c -> RfDC);

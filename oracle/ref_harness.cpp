@@ -193,6 +193,72 @@ struct RefChain {
 	   }
 	}
 
+//	everything fmProcessor::run does with one fm-rate sample after the discriminator
+//	(:515-648); also entered directly by ref_process_demod
+	void after_demod (float demod, std::complex<float> v, const chain_taps *t,
+	                  int64_t &nfm, int64_t &nrds) {
+	   std::complex<float> audio;
+	   std::complex<float> rdsDataCplx (0, 0);
+	   float phase; bool locked;
+	   process_signal_with_rds (demod, &audio, &rdsDataCplx, &phase, &locked);
+
+	   const float sumLR  = real (audio);
+	   const float diffLR = imag (audio);
+	   const float diffLRWeightend =
+	         diffLR * (cfg.fm_mode == MODE_PANO ? panorama : 1.0f);
+	   const float left  = sumLR + diffLRWeightend;
+	   const float right = sumLR - diffLRWeightend;
+	   switch (cfg.sound_sel) {
+	      default:
+	      case S_STEREO:
+	         audio = std::complex<float> (left, right); break;
+	      case S_STEREO_SWAPPED:
+	         audio = std::complex<float> (right, left); break;
+	      case S_LEFT:
+	         audio = std::complex<float> (left, left); break;
+	      case S_RIGHT:
+	         audio = std::complex<float> (right, right); break;
+	      case S_LEFTplusRIGHT:
+	         audio = std::complex<float> (sumLR, sumLR); break;
+	      case S_LEFTminusRIGHT:
+	      case S_LEFTminusRIGHT_Test:
+	         audio = std::complex<float> (diffLRWeightend, diffLRWeightend);
+	         break;
+	   }
+	   if (t -> fm_z) { t -> fm_z [2 * nfm] = real (v); t -> fm_z [2 * nfm + 1] = imag (v); }
+	   if (t -> demod) t -> demod [nfm] = demod;
+	   if (t -> pilot_phase) t -> pilot_phase [nfm] = phase;
+	   if (t -> locked) t -> locked [nfm] = locked ? 1 : 0;
+	   if (t -> pss_delay) t -> pss_delay [nfm] = pilotDelayPSS;
+	   if (t -> lr) { t -> lr [2 * nfm] = real (audio); t -> lr [2 * nfm + 1] = imag (audio); }
+	   if (t -> rds_cplx) {
+	      t -> rds_cplx [2 * nfm] = real (rdsDataCplx);
+	      t -> rds_cplx [2 * nfm + 1] = imag (rdsDataCplx);
+	   }
+
+	   if (cfg.rds_on) {
+	      std::complex<float> rdsSample;
+	      if (rdsDecimator. Pass (rdsDataCplx, &rdsSample)) {
+	         if (t -> rds24) {
+	            t -> rds24 [2 * nrds] = real (rdsSample);
+	            t -> rds24 [2 * nrds + 1] = imag (rdsSample);
+	         }
+	         nrds ++;
+	      }
+	   }
+
+	   if (fmAudioFilterActive)
+	      audio = fmAudioFilter. Pass (audio);
+
+	   audio = lastAudioSample =
+	      (audio - lastAudioSample) * deemphAlpha + lastAudioSample;
+
+//	audioGainCorrection :303-306
+	   const float gl = volumeFactor * leftChannel * real (audio);
+	   const float gr = volumeFactor * rightChannel * imag (audio);
+	   if (t -> audio192) { t -> audio192 [2 * nfm] = gl; t -> audio192 [2 * nfm + 1] = gr; }
+	}
+
 //	fm-processor.cpp:423-446 (per pulled block) and :461-648 (per sample)
 	int64_t process (const float *iq, int64_t n_in, const chain_taps *t,
 	                 int64_t *n_rds24) {
@@ -222,67 +288,7 @@ struct RefChain {
 	            continue;
 	      }
 	      float demod = theDemodulator. demodulate (v);
-
-	      std::complex<float> audio;
-	      std::complex<float> rdsDataCplx (0, 0);
-	      float phase; bool locked;
-	      process_signal_with_rds (demod, &audio, &rdsDataCplx, &phase, &locked);
-
-	      const float sumLR  = real (audio);
-	      const float diffLR = imag (audio);
-	      const float diffLRWeightend =
-	            diffLR * (cfg.fm_mode == MODE_PANO ? panorama : 1.0f);
-	      const float left  = sumLR + diffLRWeightend;
-	      const float right = sumLR - diffLRWeightend;
-	      switch (cfg.sound_sel) {
-	         default:
-	         case S_STEREO:
-	            audio = std::complex<float> (left, right); break;
-	         case S_STEREO_SWAPPED:
-	            audio = std::complex<float> (right, left); break;
-	         case S_LEFT:
-	            audio = std::complex<float> (left, left); break;
-	         case S_RIGHT:
-	            audio = std::complex<float> (right, right); break;
-	         case S_LEFTplusRIGHT:
-	            audio = std::complex<float> (sumLR, sumLR); break;
-	         case S_LEFTminusRIGHT:
-	         case S_LEFTminusRIGHT_Test:
-	            audio = std::complex<float> (diffLRWeightend, diffLRWeightend);
-	            break;
-	      }
-	      if (t -> fm_z) { t -> fm_z [2 * nfm] = real (v); t -> fm_z [2 * nfm + 1] = imag (v); }
-	      if (t -> demod) t -> demod [nfm] = demod;
-	      if (t -> pilot_phase) t -> pilot_phase [nfm] = phase;
-	      if (t -> locked) t -> locked [nfm] = locked ? 1 : 0;
-	      if (t -> pss_delay) t -> pss_delay [nfm] = pilotDelayPSS;
-	      if (t -> lr) { t -> lr [2 * nfm] = real (audio); t -> lr [2 * nfm + 1] = imag (audio); }
-	      if (t -> rds_cplx) {
-	         t -> rds_cplx [2 * nfm] = real (rdsDataCplx);
-	         t -> rds_cplx [2 * nfm + 1] = imag (rdsDataCplx);
-	      }
-
-	      if (cfg.rds_on) {
-	         std::complex<float> rdsSample;
-	         if (rdsDecimator. Pass (rdsDataCplx, &rdsSample)) {
-	            if (t -> rds24) {
-	               t -> rds24 [2 * nrds] = real (rdsSample);
-	               t -> rds24 [2 * nrds + 1] = imag (rdsSample);
-	            }
-	            nrds ++;
-	         }
-	      }
-
-	      if (fmAudioFilterActive)
-	         audio = fmAudioFilter. Pass (audio);
-
-	      audio = lastAudioSample =
-	         (audio - lastAudioSample) * deemphAlpha + lastAudioSample;
-
-//	audioGainCorrection :303-306
-	      const float gl = volumeFactor * leftChannel * real (audio);
-	      const float gr = volumeFactor * rightChannel * imag (audio);
-	      if (t -> audio192) { t -> audio192 [2 * nfm] = gl; t -> audio192 [2 * nfm + 1] = gr; }
+	      after_demod (demod, v, t, nfm, nrds);
 	      nfm ++;
 	   }
 	   if (n_rds24) *n_rds24 = nrds;
@@ -298,6 +304,18 @@ void	ref_destroy (void *h) { delete (RefChain *)h; }
 int64_t	ref_process (void *h, const float *iq, int64_t n_in,
 	             const chain_taps *taps, int64_t *n_rds24) {
 	return ((RefChain *)h) -> process (iq, n_in, taps, n_rds24);
+}
+
+int64_t	ref_process_demod (void *h, const float *demod, int64_t n_fm,
+	                   const chain_taps *taps, int64_t *n_rds24) {
+RefChain *c = (RefChain *)h;
+int64_t nfm = 0, nrds = 0;
+	for (int64_t i = 0; i < n_fm; i ++) {
+	   c -> after_demod (demod [i], std::complex<float> (0, 0), taps, nfm, nrds);
+	   nfm ++;
+	}
+	if (n_rds24) *n_rds24 = nrds;
+	return nfm;
 }
 
 void	ref_get_meta (void *h, chain_meta *m) {

@@ -92,6 +92,7 @@ def lib():
         L.sdrjfm_run_frontend_only.argtypes = [vp, vp, i64, i64]
         L.sdrjfm_launch_count.restype = i64
         L.sdrjfm_launch_count.argtypes = [vp]
+        L.sdrjfm_pilot_stats.argtypes = [vp, vp]
         for name in ("fm_mode", "fm_decoder", "sound_mode", "stereo_panorama", "sound_balance",
                      "deemphasis", "lf_cutoff", "bandwidth", "rds_mode", "local_oscillator",
                      "squelch_mode", "auto_mono", "pss_mode", "dc_remove"):
@@ -287,6 +288,13 @@ class FmProcessorB200:
 
     @property
     def launch_count(self): return self.L.sdrjfm_launch_count(self.h)
+
+    def pilot_stats(self):
+        """per stream [iterations summed over windows, max per window, fall-back windows, windows]
+        of the parallel-in-time pilot PLL solver for the last process call."""
+        a = np.zeros((self.n_streams, 4), np.int32)
+        self._ck(self.L.sdrjfm_pilot_stats(self.h, a.ctypes.data))
+        return a
 
     def meta(self):
         meta = (Meta * self.n_streams)()

@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -23,6 +24,7 @@
 #include "frontend_fir.cuh"
 #include "discriminator.cuh"
 #include "sequential.cuh"
+#include "pilot.cuh"
 #include "audio_out.cuh"
 
 using namespace sdrjfm;
@@ -52,6 +54,8 @@ struct sdrjfm_handle {
 	float2 *d_ahist [2] = { nullptr, nullptr }; int ahist_sel = 0;
 	float2 *d_audio = nullptr;              // [S][cap_audio] working-rate stereo
 	StreamState *d_state = nullptr;
+	int32_t *d_iter_stats = nullptr;        // pilot_kernel diagnostics: [S][4]
+	bool    sequential_pll = false;         // SDRJFM_SEQUENTIAL_PLL=1: lane-per-stream K3 (cross-check)
 	int64_t fm_total = 0;                   // fm-rate samples produced so far (per stream)
 	int32_t fade_cnt = 0, fade_max = 0;     // suppressAudioSampleCnt(Max), fm-processor.cpp:130-131
 	int64_t last_nfm = 0, last_naudio = 0, last_nrds = 0;
@@ -233,6 +237,7 @@ cudaError_t e;
 	AL (d_ahist [0], S * kRsHist); AL (d_ahist [1], S * kRsHist);
 	AL (d_audio, S * h -> cap_audio);
 	AL (d_state, S);
+	AL (d_iter_stats, S * 4);
 #undef AL
 	{  // initial member values of the reference objects
 	   std::vector<StreamState> st (S);
@@ -248,6 +253,9 @@ cudaError_t e;
 	    (e = cudaFuncSetAttribute (sequential_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                               (cfg -> fm_rate / 4 + 1) * (int)sizeof (float))) != cudaSuccess)
 	   return fail (e, "smem attr K3");
+	if ((e = cudaFuncSetAttribute (pilot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                               (int)kPiSmemBytes)) != cudaSuccess) return fail (e, "smem attr pilot");
+	{ const char *env = getenv ("SDRJFM_SEQUENTIAL_PLL"); h -> sequential_pll = env && env [0] == '1'; }
 int rc = rebuild_tables (h);
 	if (rc != SDRJFM_OK) { g_create_error = h -> err; *status = rc; sdrjfm_destroy (h); return nullptr; }
 	*status = SDRJFM_OK;
@@ -262,7 +270,7 @@ void *ptrs [] = { h -> d_tables, h -> d_sin_quarter, h -> d_in, h -> d_hist [0],
 	              h -> d_pend, h -> d_U, h -> d_S, h -> d_iqn, h -> d_fmz, h -> d_res, h -> d_zabs,
 	              h -> d_demod, h -> d_phase, h -> d_pssd, h -> d_locked, h -> d_lr, h -> d_a192,
 	              h -> d_rdsc, h -> d_rds24, h -> d_ahist [0], h -> d_ahist [1], h -> d_audio,
-	              h -> d_state };
+	              h -> d_state, h -> d_iter_stats };
 	for (void *p : ptrs) if (p) cudaFree (p);
 	if (h -> stream) cudaStreamDestroy (h -> stream);
 	delete h;
@@ -271,6 +279,14 @@ void *ptrs [] = { h -> d_tables, h -> d_sin_quarter, h -> d_in, h -> d_hist [0],
 
 void *sdrjfm_cuda_stream (sdrjfm_handle *h) { return h ? (void *)h -> stream : nullptr; }
 int64_t sdrjfm_launch_count (const sdrjfm_handle *h) { return h ? h -> launches : 0; }
+
+int sdrjfm_pilot_stats (sdrjfm_handle *h, int32_t *out /* [n_streams][4] */) {
+	if (!h || !out) return SDRJFM_ERR_ARG;
+	CK (cudaMemcpyAsync (out, h -> d_iter_stats, (size_t)h -> cfg.n_streams * 4 * sizeof (int32_t),
+	                     cudaMemcpyDeviceToHost, h -> stream));
+	CK (cudaStreamSynchronize (h -> stream));
+	return SDRJFM_OK;
+}
 
 int sdrjfm_sync (sdrjfm_handle *h) {
 	if (!h) return SDRJFM_ERR_ARG;
@@ -353,10 +369,18 @@ const size_t seq_smem = (h -> lut.quarter + 1) * sizeof (float);
 	   sequential_kernel<true><<<seq_blocks, kSeqLanes, seq_smem, h -> stream>>> (
 	         h -> d_res, h -> d_zabs, h -> d_iqn, h -> cap_fm, M, sp, h -> lut, T + th.off_atan,
 	         h -> d_state, h -> d_demod, h -> d_phase, h -> d_locked);
-	else
+	else if (h -> sequential_pll)
 	   sequential_kernel<false><<<seq_blocks, kSeqLanes, seq_smem, h -> stream>>> (
 	         h -> d_res, h -> d_zabs, h -> d_iqn, h -> cap_fm, M, sp, h -> lut, T + th.off_atan,
 	         h -> d_state, h -> d_demod, h -> d_phase, h -> d_locked);
+	else {
+	   PilotParams pp;
+	   pp.K_FM = sp.K_FM; pp.omega = sp.omega; pp.gain = sp.gain;
+	   pp.lock_half_rate = sp.lock_half_rate; pp.n_streams = S;
+	   pilot_kernel<<<S, kPiThreads, kPiSmemBytes, h -> stream>>> (
+	         h -> d_res, h -> d_zabs, h -> cap_fm, M, pp, h -> lut, h -> d_state,
+	         h -> d_demod, h -> d_phase, h -> d_locked, h -> d_iter_stats);
+	}
 	h -> launches ++;
 //	K4 ------------------------------------------------------------------------------------
 	{

@@ -131,3 +131,44 @@ def test_full_size_properties(pkg, signals):
     assert abs(f - 1000.0) < 1.0
     # 75 kHz deviation -> 2 pi 75000/192000 * 20/K_FM = 1.587 peak
     assert abs(np.max(np.abs(d)) - 1.587) < 0.02
+
+
+@pytest.mark.parametrize("sig_name", ["stereo", "stereo_clean", "mono", "batch3"])
+def test_parallel_pilot_pll_is_bit_exact(pkg, signals, chainlib, ref_available, sig_name):
+    """K3 solves the pilot PLL in parallel in time (pilot.cuh).  Fed with the GPU's OWN demod
+    tap, the reference's pilotRecovery (entered through *_process_demod) must give the same
+    pilot phase BIT FOR BIT and the same lock flags; the solver must not have needed its
+    sequential fall-back."""
+    n = N1 * 3 // 2
+    x = dict(stereo=lambda: signals.stereo_pilot(n),
+             stereo_clean=lambda: signals.stereo_pilot(n, snr_db=None),
+             mono=lambda: signals.mono_tone(n),
+             batch3=lambda: signals.batch_stream(3, n))[sig_name]()
+    cfg = dict(fm_mode=0, volume_db=0.0)
+    p = pkg.FmProcessorB200(n_streams=1, max_samples_per_call=n)
+    p.configure(**cfg)
+    chunks = [N1 // 2, 16384, N1 - 16384 - N1 // 2 + 12 * 7, n]
+    demod, phase, locked, stats = [], [], [], np.zeros(4, np.int64)
+    pos = 0
+    for c in chunks:
+        c = min(c, n - pos)
+        if c <= 0:
+            break
+        p.process(x[pos:pos + c])
+        demod.append(p.read_tap("demod")); phase.append(p.read_tap("pilot_phase"))
+        locked.append(p.read_tap("locked"))
+        stats += p.pilot_stats()[0]
+        pos += c
+    meta = p.meta()[0]
+    p.close()
+    demod, phase, locked = map(np.concatenate, (demod, phase, locked))
+    which = "ref" if ref_available else "orc"
+    c = chainlib.Chain(which, **cfg)
+    ref = c.process_demod(demod, taps=("pilot_phase", "locked"))
+    assert np.array_equal(phase.view(np.uint32), ref["pilot_phase"].view(np.uint32)), \
+        f"first mismatch at {np.argmax(phase != ref['pilot_phase'])}"
+    assert np.array_equal(locked, ref["locked"])
+    assert abs(meta["pilot_lock_strength"] - c.meta()["pilot_lock_strength"]) < 1e-5
+    assert stats[2] == 0, f"sequential fall-back used in {stats[2]} of {stats[3]} windows"
+    assert stats[0] / stats[3] < 8, f"mean iterations per window {stats[0] / stats[3]}"
+    print(f"{sig_name}: {stats[0] / stats[3]:.2f} iterations per window, max {stats[1]}")
