@@ -1,65 +1,166 @@
-// K6b — fm-rate audio to working rate (192 kHz -> 48 kHz) and the start-up fade-in.
+// K6 — audio back end at the fm rate, one launch, parallel over tiles AND streams:
+//   de-emphasis one-pole      src/fm/fm-processor.cpp:594-595   (alpha from setDeemphasis :291-297)
+//   audioGainCorrection       src/fm/fm-processor.cpp:303-306
+//   192 kHz -> working rate   src/fm/fm-processor.cpp:633-634   (newConverter = libsamplerate)
+//   fade-in after (re)tune    src/fm/fm-processor.cpp:638-642
 //
-// The reference does this step with libsamplerate (newConverter, SRC_SINC_MEDIUM_QUALITY,
-// src/various/newconverter.cpp:26-80, called at src/fm/fm-processor.cpp:633-634).  That
-// library is neither vendored in the reference tree nor installed here, so its
-// coefficient table cannot be restated: PARITY UNPINNED for this stage.
-// What is built instead is a documented polyphase windowed-sinc decimator of our own:
+// De-emphasis is the linear recurrence y[n] = y[n-1] + alpha (x[n] - y[n-1]).  With
+// alpha = 0.094 (50 us) a state error decays by (1 - alpha)^384 < 1e-16, so every tile
+// simply starts kAuWarm samples early from a zero state and is exact to float rounding;
+// the tile that contains the first sample of the call starts from the carried state instead.
+// Inside a tile the recurrence is a block scan of affine maps.
+//
+// The reference does the 192 -> 48 kHz step with libsamplerate (SRC_SINC_MEDIUM_QUALITY,
+// src/various/newconverter.cpp:26-80).  That library is neither vendored in the reference
+// tree nor installed here, so its coefficient table cannot be restated: PARITY UNPINNED for
+// this stage.  What is built instead is a documented polyphase windowed-sinc
+// decimator of our own,
 //     y[q] = sum_{i<129} h[i] a[4 q + 3 - i],   h = Blackman-windowed sinc, fc = 20 kHz
-// validated against a float64 model of the same taps.  The fade-in restates
-// fm-processor.cpp:638-642 exactly.
+// validated against a float64 model of the same taps.
 #pragma once
 #include "common.cuh"
 
 namespace sdrjfm {
 
-constexpr int kRsTaps = 129;
-constexpr int kRsHist = 128;
+constexpr int kRsTaps  = 129;
+constexpr int kRsHist  = 128;
 constexpr int kRsDecim = 4;
+
+constexpr int kAuThreads = 256;
+constexpr int kAuRun     = 10;                          // consecutive fm samples per thread
+constexpr int kAuSpan    = kAuThreads * kAuRun;         // 2560 samples staged per CTA
+constexpr int kAuTile    = 2048;                        // fm samples owned by a CTA
+constexpr int kAuLead    = kAuSpan - kAuTile;           // 512 = 384 warm-up + 128 filter history
+constexpr int kAuWarm    = kAuLead - kRsHist;
 
 __constant__ float c_rs_taps [kRsTaps + 3];
 
-// a      : [S][pitch] fm-rate stereo of this call (M samples); hist: [S][128] previous ones
-// out    : [S][out_pitch] working-rate stereo
-// g0     : global fm index of a[.][0];  q0: global output index of out[.][0];  nq: outputs
-__global__ void resample4_kernel (const float2 *__restrict__ a, int64_t pitch,
-                                  const float2 *__restrict__ hist,
-                                  float2 *__restrict__ out, int64_t out_pitch,
-                                  int64_t g0, int64_t q0, int32_t nq,
-                                  int32_t fade_cnt, int32_t fade_max) {
-const int stream = blockIdx.y;
-const int q = blockIdx.x * blockDim.x + threadIdx.x;
-	if (q >= nq) return;
-const float2 *as = a + (int64_t)stream * pitch;
-const float2 *hs = hist + (int64_t)stream * kRsHist;
-const int64_t top = (q0 + q) * kRsDecim + (kRsDecim - 1) - g0;   // local index of newest sample
-float2 acc = make_float2 (0.f, 0.f);
-	for (int i = 0; i < kRsTaps; i ++) {
-	   const int64_t j = top - i;
-	   const float2 v = j >= 0 ? as [j] : hs [kRsHist + j];
-	   acc.x = fmaf (c_rs_taps [i], v.x, acc.x);
-	   acc.y = fmaf (c_rs_taps [i], v.y, acc.y);
-	}
-//	fade-in: pcmSample *= (max - cnt) / max while cnt > 0; cnt decrements per output sample
-const int32_t cnt = fade_cnt - q;
-	if (cnt > 0) {
-	   const float f = fdiv (fsub ((float)fade_max, (float)cnt), (float)fade_max);
-	   acc.x = fmul (acc.x, f); acc.y = fmul (acc.y, f);
-	}
-	out [(int64_t)stream * out_pitch + q] = acc;
-}
+struct AudioParams {
+	float   alpha, gl, gr;
+	int32_t M;                 // fm samples of this call
+	int64_t g0;                // global fm index of local sample 0 (decimation phase)
+	int64_t q0;                // global output index of the first output of this call
+	int32_t nq;                // outputs of this call
+	int32_t fade_cnt, fade_max;
+	int32_t write_tap;         // keep the 192 kHz stream (SDRJFM_TAP_AUDIO192)
+	int32_t sel;               // which de-emphasis state buffer holds the carried state
+};
 
-// new_hist[i] = sample at local index M - 128 + i of (old_hist | a[0..M))
-__global__ void roll_audio_history_kernel (const float2 *__restrict__ a, int64_t pitch,
-                                           const float2 *__restrict__ old_hist,
-                                           float2 *__restrict__ new_hist, int32_t M) {
-const int stream = blockIdx.x;
-const int i = threadIdx.x;
-	if (i >= kRsHist) return;
-const int64_t pos = (int64_t)M - kRsHist + i;
-	new_hist [(int64_t)stream * kRsHist + i] =
-	      pos >= 0 ? a [(int64_t)stream * pitch + pos]
-	               : old_hist [(int64_t)stream * kRsHist + (kRsHist + pos)];
+// lr    : [S][pitch] fm-rate (left, right) of this call
+// hist  : [S][128] de-emphasised, gain-corrected samples preceding this call; new_hist: same, rolled
+// a192  : [S][pitch] tap (optional);  out: [S][out_pitch] working-rate stereo
+__global__ void __launch_bounds__ (kAuThreads)
+audio_kernel (const float2 *__restrict__ lr, int64_t pitch, AudioParams P,
+              const float2 *__restrict__ hist, float2 *__restrict__ new_hist,
+              StreamState *__restrict__ state, float2 *__restrict__ a192,
+              float2 *__restrict__ out, int64_t out_pitch) {
+// phase-major staging: sample with global index g sits at [(g - G0) & 3][(g - G0) >> 2]
+__shared__ float2 sA [4][kAuSpan / 4 + 2];
+__shared__ float  sWl [kAuThreads / 32], sWr [kAuThreads / 32], sWa [kAuThreads / 32];
+const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+const int stream = blockIdx.y;
+const int t0 = blockIdx.x * kAuTile;                    // first owned local sample
+const int s0 = t0 - kAuLead;                            // first staged local sample
+const float2 *in = lr + (int64_t)stream * pitch;
+const int64_t G0 = (P.g0 + s0) & ~(int64_t)3;           // staging origin, multiple of 4 (may be < 0)
+const int shift = (int)((P.g0 + s0) - G0);
+
+//	-- de-emphasis: thread-local zero-state response, block scan, second pass ---------------
+const int n0 = s0 + tid * kAuRun;
+float2 x [kAuRun];
+const float oma = fsub (1.0f, P.alpha);
+float A = 1.0f, Bl = 0.f, Br = 0.f;
+#pragma unroll
+	for (int j = 0; j < kAuRun; j ++) {
+	   const int n = n0 + j;
+	   const bool ok = n >= 0 && n < P.M;
+	   x [j] = ok ? in [n] : make_float2 (0.f, 0.f);
+	   if (ok) {
+	      Bl = fadd (fmul (fsub (x [j].x, Bl), P.alpha), Bl);
+	      Br = fadd (fmul (fsub (x [j].y, Br), P.alpha), Br);
+	      A *= oma;
+	   }
+	}
+float iA = A, iBl = Bl, iBr = Br;                       // inclusive scan of (A, B) over lanes
+#pragma unroll
+	for (int k = 1; k < 32; k <<= 1) {
+	   const float yA = __shfl_up_sync (0xffffffffu, iA, k);
+	   const float yl = __shfl_up_sync (0xffffffffu, iBl, k);
+	   const float yr = __shfl_up_sync (0xffffffffu, iBr, k);
+	   if (lane >= k) { iBl = fmaf (iA, yl, iBl); iBr = fmaf (iA, yr, iBr); iA *= yA; }
+	}
+	if (lane == 31) { sWa [warp] = iA; sWl [warp] = iBl; sWr [warp] = iBr; }
+	__syncthreads ();
+//	state entering the staged span: the carried state if the span starts at (or before) the
+//	first sample of the call, else zero (the warm-up forgets it)
+float yl = 0.f, yr = 0.f;
+	if (s0 <= 0) { yl = state [stream].deemph [P.sel][0]; yr = state [stream].deemph [P.sel][1]; }
+	for (int q = 0; q < warp; q ++) { yl = fmaf (sWa [q], yl, sWl [q]); yr = fmaf (sWa [q], yr, sWr [q]); }
+	{
+	   float eA = __shfl_up_sync (0xffffffffu, iA, 1);
+	   float el = __shfl_up_sync (0xffffffffu, iBl, 1);
+	   float er = __shfl_up_sync (0xffffffffu, iBr, 1);
+	   if (lane == 0) { eA = 1.f; el = 0.f; er = 0.f; }
+	   yl = fmaf (eA, yl, el); yr = fmaf (eA, yr, er);
+	}
+float2 *tap = a192 ? a192 + (int64_t)stream * pitch : nullptr;
+#pragma unroll
+	for (int j = 0; j < kAuRun; j ++) {
+	   const int n = n0 + j;
+	   float2 v;
+	   if (n >= 0 && n < P.M) {
+	      yl = fadd (fmul (fsub (x [j].x, yl), P.alpha), yl);       // :594-595
+	      yr = fadd (fmul (fsub (x [j].y, yr), P.alpha), yr);
+	      v = make_float2 (fmul (P.gl, yl), fmul (P.gr, yr));       // :304-305
+	      if (tap && n >= t0 && P.write_tap) tap [n] = v;
+	      if (n == P.M - 1) { state [stream].deemph [P.sel ^ 1][0] = yl; state [stream].deemph [P.sel ^ 1][1] = yr; }
+	   }
+	   else if (n < 0 && n >= -kRsHist) v = hist [(int64_t)stream * kRsHist + kRsHist + n];
+	   else v = make_float2 (0.f, 0.f);
+	   const int r = n - s0 + shift;
+	   sA [r & 3][r >> 2] = v;
+	}
+	__syncthreads ();
+
+//	-- history for the next call: the last 128 samples of (old history | this call) ----------
+	if (t0 + kAuTile >= P.M && t0 < P.M && tid < kRsHist) {        // the CTA owning the last sample
+	   const int n = P.M - kRsHist + tid;
+	   float2 v;
+	   if (n >= s0 && n >= -kRsHist) { const int r = n - s0 + shift; v = sA [r & 3][r >> 2]; }
+	   else v = hist [(int64_t)stream * kRsHist + kRsHist + n];    // n < -128 + ... only when M < 128
+	   if (n < -kRsHist) v = make_float2 (0.f, 0.f);
+	   new_hist [(int64_t)stream * kRsHist + tid] = v;
+	}
+
+//	-- 129-tap polyphase decimator: outputs at global fm index g = 3 mod 4 -------------------
+	for (int o = tid; o < kAuTile / kRsDecim + 1; o += kAuThreads) {
+	   // o-th candidate output of the tile: the first g >= g(t0) with g = 3 mod 4
+	   const int64_t gt0 = P.g0 + t0;
+	   const int64_t g = ((gt0 + 0) | 3) + 4 * (int64_t)o;          // (gt0 | 3) is the first such g
+	   const int n = (int)(g - P.g0);                                // local index of the newest sample
+	   if (n >= t0 + kAuTile || n >= P.M) break;
+	   const int r = n - s0 + shift;                                 // r & 3 == 3 by construction
+	   const int k = r >> 2;
+	   float2 acc = make_float2 (0.f, 0.f);
+#pragma unroll
+	   for (int ph = 0; ph < 4; ph ++) {                             // taps i = 4 j + ph hit phase 3 - ph
+	      const float2 *col = sA [3 - ph];
+#pragma unroll 8
+	      for (int j = 0; 4 * j + ph < kRsTaps; j ++) {
+	         const float2 v = col [k - j];
+	         const float c = c_rs_taps [4 * j + ph];
+	         acc.x = fmaf (c, v.x, acc.x);
+	         acc.y = fmaf (c, v.y, acc.y);
+	      }
+	   }
+	   const int64_t q = g >> 2;                                     // global output index
+	   const int32_t cnt = P.fade_cnt - (int32_t)(q - P.q0);         // :638-642
+	   if (cnt > 0) {
+	      const float f = fdiv (fsub ((float)P.fade_max, (float)cnt), (float)P.fade_max);
+	      acc.x = fmul (acc.x, f); acc.y = fmul (acc.y, f);
+	   }
+	   out [(int64_t)stream * out_pitch + (q - P.q0)] = acc;
+	}
 }
 
 // mono / unlocked path of process_signal_with_rds + the L/R matrix, fm-processor.cpp:728-730

@@ -48,7 +48,7 @@ struct StreamState {
 	int32_t pss_minimized, pss_lock_cnt, pss_unlock_cnt;
 	int32_t pss_inp;                 // fftFilter::inp of the PSS low-pass
 	// de-emphasis, fm-processor.cpp:594-595
-	float   deemph_l, deemph_r;
+	float   deemph [2][2];           // [buffer][left,right]: read from one, written to the other (K6)
 	// RDS: fftFilter::inp of band-pass and Hilbert (equal), rdsPhaseIndex, rdsDecimator counter
 	int32_t rds_inp, rds_phase_idx, rds_decim_cnt;
 	// audio: samples still to fade in (suppressAudioSampleCnt), peak meter

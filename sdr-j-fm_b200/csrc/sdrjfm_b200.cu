@@ -389,29 +389,27 @@ const size_t seq_smem = (h -> lut.quarter + 1) * sizeof (float);
 	   h -> launches ++;
 	}
 //	K6 ------------------------------------------------------------------------------------
-DeemphParams ep;
-	ep.alpha = st.deemph_alpha;
-	ep.gl = st.volume * st.left_ch; ep.gr = st.volume * st.right_ch;   // fm-processor.cpp:304-305
-	ep.n_streams = S;
-	deemphasis_kernel<<<(S + 31) / 32, 32, 0, h -> stream>>> (h -> d_lr, h -> cap_fm, M, ep,
-	                                                          h -> d_state, h -> d_a192);
-	h -> launches ++;
 const int64_t q0 = h -> fm_total / kRsDecim;
 const int64_t q1 = (h -> fm_total + M) / kRsDecim;
 const int32_t nq = (int32_t)(q1 - q0);
 float2 *aout = d_audio_out ? d_audio_out : h -> d_audio;
 const int64_t apitch = d_audio_out ? audio_pitch : h -> cap_audio;
-	if (nq > 0) {
-	   dim3 g ((unsigned)((nq + 127) / 128), (unsigned)S);
-	   resample4_kernel<<<g, 128, 0, h -> stream>>> (h -> d_a192, h -> cap_fm, h -> d_ahist [h -> ahist_sel],
-	                                                aout, apitch, h -> fm_total, q0, nq,
-	                                                h -> fade_cnt, h -> fade_max);
+	{
+	   AudioParams ap;
+	   ap.alpha = st.deemph_alpha;
+	   ap.gl = st.volume * st.left_ch; ap.gr = st.volume * st.right_ch;   // fm-processor.cpp:304-305
+	   ap.M = M; ap.g0 = h -> fm_total; ap.q0 = q0; ap.nq = nq;
+	   ap.fade_cnt = h -> fade_cnt; ap.fade_max = h -> fade_max;
+	   ap.write_tap = h -> cfg.keep_taps;
+	   ap.sel = h -> ahist_sel;
+	   dim3 g ((unsigned)((M + kAuTile - 1) / kAuTile), (unsigned)S);
+	   audio_kernel<<<g, kAuThreads, 0, h -> stream>>> (
+	         h -> d_lr, h -> cap_fm, ap, h -> d_ahist [h -> ahist_sel], h -> d_ahist [h -> ahist_sel ^ 1],
+	         h -> d_state, h -> d_a192, aout, apitch);
 	   h -> launches ++;
+	   h -> ahist_sel ^= 1;
 	   h -> fade_cnt = h -> fade_cnt > nq ? h -> fade_cnt - nq : 0;
 	}
-	roll_audio_history_kernel<<<S, kRsHist, 0, h -> stream>>> (h -> d_a192, h -> cap_fm,
-	      h -> d_ahist [h -> ahist_sel], h -> d_ahist [h -> ahist_sel ^ 1], M);
-	h -> ahist_sel ^= 1; h -> launches ++;
 	h -> fm_total += M;
 	h -> last_naudio = nq;
 	if (n_audio) *n_audio = nq;

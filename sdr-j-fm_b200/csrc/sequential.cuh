@@ -227,38 +227,4 @@ int32_t m = 0;
 	st.pll_nco_phase = c.nco; st.pll_phase_incr = c.incr;
 }
 
-// K6a — de-emphasis one-pole and gain, fm-processor.cpp:594-595 and :303-306, one lane per
-// stream (two independent float chains, left and right), bit-exact.
-struct DeemphParams { float alpha, gl, gr; int32_t n_streams; };
-
-__global__ void deemphasis_kernel (const float2 *__restrict__ lr, int64_t pitch, int32_t M,
-                                   DeemphParams P, StreamState *__restrict__ state,
-                                   float2 *__restrict__ out) {
-const int stream = blockIdx.x * blockDim.x + threadIdx.x;
-	if (stream >= P.n_streams) return;
-StreamState &st = state [stream];
-const float2 *in = lr + (int64_t)stream * pitch;
-float2 *o = out + (int64_t)stream * pitch;
-float l = st.deemph_l, r = st.deemph_r;
-int32_t m = 0;
-	for (; m + 4 <= M; m += 4) {
-	   float2 v [4];
-#pragma unroll
-	   for (int k = 0; k < 4; k ++) v [k] = in [m + k];
-#pragma unroll
-	   for (int k = 0; k < 4; k ++) {
-	      l = fadd (fmul (fsub (v [k].x, l), P.alpha), l);
-	      r = fadd (fmul (fsub (v [k].y, r), P.alpha), r);
-	      o [m + k] = make_float2 (fmul (P.gl, l), fmul (P.gr, r));
-	   }
-	}
-	for (; m < M; m ++) {
-	   const float2 v = in [m];
-	   l = fadd (fmul (fsub (v.x, l), P.alpha), l);
-	   r = fadd (fmul (fsub (v.y, r), P.alpha), r);
-	   o [m] = make_float2 (fmul (P.gl, l), fmul (P.gr, r));
-	}
-	st.deemph_l = l; st.deemph_r = r;
-}
-
 }	// namespace sdrjfm
