@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <cstddef>
 #include <string>
 #include <vector>
 
@@ -25,6 +26,7 @@
 #include "discriminator.cuh"
 #include "sequential.cuh"
 #include "pilot.cuh"
+#include "stereo.cuh"
 #include "audio_out.cuh"
 
 using namespace sdrjfm;
@@ -54,6 +56,7 @@ struct sdrjfm_handle {
 	float2 *d_ahist [2] = { nullptr, nullptr }; int ahist_sel = 0;
 	float2 *d_audio = nullptr;              // [S][cap_audio] working-rate stereo
 	StreamState *d_state = nullptr;
+	float2  *d_pss_ring = nullptr;          // [S][2048] PSS filter input ring (state)
 	int32_t *d_iter_stats = nullptr;        // pilot_kernel diagnostics: [S][4]
 	bool    sequential_pll = false;         // SDRJFM_SEQUENTIAL_PLL=1: lane-per-stream K3 (cross-check)
 	int64_t fm_total = 0;                   // fm-rate samples produced so far (per stream)
@@ -120,6 +123,14 @@ float comp [40] = { 0 };
 	   }
 	   for (int i = 0; i < kRsTaps; i ++) t [i] = (float)(d [i] / sum);
 	   CK (cudaMemcpyToSymbol (c_rs_taps, t, sizeof t));
+	}
+
+//	PSS low-pass taps: lpFilter (2048, 295).setLowPass (15000, rate), stereo-separation.cpp:31-39
+	{
+	   std::vector<cf32> lp = design_lowpass (kPssTaps, 15000, th.fm_rate);
+	   float t [kPssTaps + 1] = { 0 };
+	   for (int i = 0; i < kPssTaps; i ++) t [i] = lp [i].real ();
+	   CK (cudaMemcpyToSymbol (c_pss_taps, t, sizeof t));
 	}
 
 //	quarter-wave sine table + exception list (see sequential.cuh)
@@ -238,6 +249,7 @@ cudaError_t e;
 	AL (d_audio, S * h -> cap_audio);
 	AL (d_state, S);
 	AL (d_iter_stats, S * 4);
+	AL (d_pss_ring, S * kPssRing);
 #undef AL
 	{  // initial member values of the reference objects
 	   std::vector<StreamState> st (S);
@@ -270,7 +282,7 @@ void *ptrs [] = { h -> d_tables, h -> d_sin_quarter, h -> d_in, h -> d_hist [0],
 	              h -> d_pend, h -> d_U, h -> d_S, h -> d_iqn, h -> d_fmz, h -> d_res, h -> d_zabs,
 	              h -> d_demod, h -> d_phase, h -> d_pssd, h -> d_locked, h -> d_lr, h -> d_a192,
 	              h -> d_rdsc, h -> d_rds24, h -> d_ahist [0], h -> d_ahist [1], h -> d_audio,
-	              h -> d_state, h -> d_iter_stats };
+	              h -> d_state, h -> d_iter_stats, h -> d_pss_ring };
 	for (void *p : ptrs) if (p) cudaFree (p);
 	if (h -> stream) cudaStreamDestroy (h -> stream);
 	delete h;
@@ -384,8 +396,17 @@ const size_t seq_smem = (h -> lut.quarter + 1) * sizeof (float);
 	h -> launches ++;
 //	K4 ------------------------------------------------------------------------------------
 	{
-	   dim3 g ((unsigned)((M + 255) / 256), (unsigned)S);
-	   mono_matrix_kernel<<<g, 256, 0, h -> stream>>> (h -> d_demod, h -> cap_fm, M, st.sound_sel, h -> d_lr);
+	   StereoParams q;
+	   q.fm_mode = st.fm_mode; q.auto_mono = st.auto_mono; q.pss_on = st.pss_on;
+	   q.sound_sel = st.sound_sel; q.panorama = st.panorama;
+	   q.pss_alpha = 10.0f / h -> cfg.fm_rate;                 // fm-processor.cpp:81-82
+	   q.pss_lock_alpha = 1.0f / h -> cfg.fm_rate;             // stereo-separation.cpp:32
+	   q.rate3 = 3 * h -> cfg.fm_rate;
+	   q.write_pss_tap = h -> cfg.keep_taps;
+	   stereo_kernel<<<S, kStThreads, 0, h -> stream>>> (
+	         h -> d_demod, h -> d_phase, h -> d_locked, h -> cap_fm, M, q,
+	         reinterpret_cast<const float2 *>(T + th.off_sincos), h -> d_state, h -> d_pss_ring,
+	         h -> d_lr, h -> d_pssd);
 	   h -> launches ++;
 	}
 //	K6 ------------------------------------------------------------------------------------
@@ -626,7 +647,12 @@ int sdrjfm_trigger_frequency_change (sdrjfm_handle *h) {
 }
 int sdrjfm_restart_pss_analyzer (sdrjfm_handle *h) {
 	if (!h) return SDRJFM_ERR_ARG;
-	return SDRJFM_OK;     // PSS state lives with K4 (added with the stereo path)
+//	pilotDelayPSS = 0; pPSS.reset () (:857-860): zero the six PSS fields of every stream
+	CK (cudaSetDevice (h -> cfg.device));
+	CK (cudaMemset2DAsync ((char *)h -> d_state + offsetof (StreamState, pss_delay), sizeof (StreamState), 0,
+	                       offsetof (StreamState, pss_inp) - offsetof (StreamState, pss_delay),
+	                       h -> cfg.n_streams, h -> stream));
+	return SDRJFM_OK;
 }
 
 int64_t sdrjfm_design_tables (int32_t input_rate, int32_t fm_rate, int32_t input_filter_hz,
