@@ -16,6 +16,8 @@
 #include <cstring>
 #include <cstdlib>
 #include <cstddef>
+#include <algorithm>
+#include <complex>
 #include <string>
 #include <vector>
 
@@ -27,6 +29,7 @@
 #include "sequential.cuh"
 #include "pilot.cuh"
 #include "stereo.cuh"
+#include "rds.cuh"
 #include "audio_out.cuh"
 
 using namespace sdrjfm;
@@ -56,6 +59,12 @@ struct sdrjfm_handle {
 	float2 *d_ahist [2] = { nullptr, nullptr }; int ahist_sel = 0;
 	float2 *d_audio = nullptr;              // [S][cap_audio] working-rate stereo
 	StreamState *d_state = nullptr;
+	// RDS branch (allocated when RDS is first switched on)
+	float   *d_rds_dring = nullptr, *d_rds_pring = nullptr;     // [S][131072] demod / pilot phase by rds index
+	float   *d_rds_bp = nullptr, *d_rds_hi = nullptr;           // [S][2][32000] / [S][2][32768]
+	float2  *d_rds_R = nullptr, *d_rds_tw = nullptr, *d_rds_dtaps = nullptr;
+	float2  *d_rds_hist [2] = { nullptr, nullptr }; int rds_hist_sel = 0;
+	int64_t  rds_total = 0, rds_last_block = -1;
 	float2  *d_pss_ring = nullptr;          // [S][2048] PSS filter input ring (state)
 	int32_t *d_iter_stats = nullptr;        // pilot_kernel diagnostics: [S][4]
 	bool    sequential_pll = false;         // SDRJFM_SEQUENTIAL_PLL=1: lane-per-stream K3 (cross-check)
@@ -184,6 +193,50 @@ static int rebuild_tables (sdrjfm_handle *h) {
 	return upload_tables (h);
 }
 
+// allocates and zeroes the RDS state, uploads the band-pass spectrum, twiddles and decimator taps
+static int rds_setup (sdrjfm_handle *h) {
+const int64_t S = h -> cfg.n_streams;
+const TableHeader &th = h -> tables.hdr ();
+	if (!h -> d_rds_dring) {
+	   CK (dalloc (&h -> d_rds_dring, (size_t)S * kRdsRing));
+	   CK (dalloc (&h -> d_rds_pring, (size_t)S * kRdsRing));
+	   CK (dalloc (&h -> d_rds_bp, (size_t)S * 2 * kRdsBlock));
+	   CK (dalloc (&h -> d_rds_hi, (size_t)S * 2 * kRdsN));
+	   CK (dalloc (&h -> d_rds_hist [0], (size_t)S * (kRdsDecTaps - 1)));
+	   CK (dalloc (&h -> d_rds_hist [1], (size_t)S * (kRdsDecTaps - 1)));
+	   CK (dalloc (&h -> d_rds_R, (size_t)kRdsNh + 1));
+	   CK (dalloc (&h -> d_rds_tw, (size_t)kRdsNh));
+	   CK (dalloc (&h -> d_rds_dtaps, (size_t)kRdsDecTaps));
+	   CK (cudaFuncSetAttribute (rds_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRdsFftSmem));
+//	rdsBandPassFilter.setBand (RDS_FREQUENCY -+ RDS_WIDTH / 2, fmRate), fm-processor.cpp:166-168; Pass (float)
+//	returns 3 * Re (conv): real taps 3 Re k[j].  R[k] = (1/Nh) sum_j 3 r[j] exp (-2 pi i j k / N), k = 0..Nh
+	   std::vector<cf32> bp = design_bandpass (kRdsTaps, 57000 - 2400, 57000 + 2400, th.fm_rate);
+	   std::vector<std::complex<double>> w (kRdsN);
+	   for (int t = 0; t < kRdsN; t ++) w [t] = std::polar (1.0, -2 * M_PI * t / kRdsN);
+	   std::vector<float2> R (kRdsNh + 1), tw (kRdsNh);
+	   for (int k = 0; k <= kRdsNh; k ++) {
+	      std::complex<double> a (0, 0);
+	      for (int j = 0; j < kRdsTaps; j ++)
+	         a += 3.0 * (double)bp [j].real () * w [(int)(((int64_t)j * k) & (kRdsN - 1))];
+	      a /= (double)kRdsNh;
+	      R [k] = make_float2 ((float)a.real (), (float)a.imag ());
+	   }
+	   for (int k = 0; k < kRdsNh; k ++) tw [k] = make_float2 ((float)w [k].real (), (float)w [k].imag ());
+	   CK (cudaMemcpy (h -> d_rds_R, R.data (), R.size () * sizeof (float2), cudaMemcpyHostToDevice));
+	   CK (cudaMemcpy (h -> d_rds_tw, tw.data (), tw.size () * sizeof (float2), cudaMemcpyHostToDevice));
+	   CK (cudaMemcpy (h -> d_rds_dtaps, h -> tables.payload () + th.off_rdsdecim,
+	                   kRdsDecTaps * sizeof (float2), cudaMemcpyHostToDevice));
+	}
+	else {
+	   CK (cudaMemsetAsync (h -> d_rds_dring, 0, (size_t)S * kRdsRing * sizeof (float), h -> stream));
+	   CK (cudaMemsetAsync (h -> d_rds_pring, 0, (size_t)S * kRdsRing * sizeof (float), h -> stream));
+	   CK (cudaMemsetAsync (h -> d_rds_hist [0], 0, (size_t)S * (kRdsDecTaps - 1) * sizeof (float2), h -> stream));
+	   CK (cudaMemsetAsync (h -> d_rds_hist [1], 0, (size_t)S * (kRdsDecTaps - 1) * sizeof (float2), h -> stream));
+	}
+	h -> rds_total = 0; h -> rds_last_block = -1;
+	return SDRJFM_OK;
+}
+
 extern "C" {
 
 const char *sdrjfm_version (void) { return "sdrjfm_b200 0.1 (sm_100a)"; }
@@ -282,7 +335,9 @@ void *ptrs [] = { h -> d_tables, h -> d_sin_quarter, h -> d_in, h -> d_hist [0],
 	              h -> d_pend, h -> d_U, h -> d_S, h -> d_iqn, h -> d_fmz, h -> d_res, h -> d_zabs,
 	              h -> d_demod, h -> d_phase, h -> d_pssd, h -> d_locked, h -> d_lr, h -> d_a192,
 	              h -> d_rdsc, h -> d_rds24, h -> d_ahist [0], h -> d_ahist [1], h -> d_audio,
-	              h -> d_state, h -> d_iter_stats, h -> d_pss_ring };
+	              h -> d_state, h -> d_iter_stats, h -> d_pss_ring,
+	              h -> d_rds_dring, h -> d_rds_pring, h -> d_rds_bp, h -> d_rds_hi, h -> d_rds_R, h -> d_rds_tw,
+	              h -> d_rds_dtaps, h -> d_rds_hist [0], h -> d_rds_hist [1] };
 	for (void *p : ptrs) if (p) cudaFree (p);
 	if (h -> stream) cudaStreamDestroy (h -> stream);
 	delete h;
@@ -409,6 +464,39 @@ const size_t seq_smem = (h -> lut.quarter + 1) * sizeof (float);
 	         h -> d_lr, h -> d_pssd);
 	   h -> launches ++;
 	}
+//	K5 ------------------------------------------------------------------------------------
+	if (st.rds_mode != 0) {
+	   const int64_t n0 = h -> rds_total;
+	   for (int32_t m = 0; m < M; ) {
+	      const int64_t K = (n0 + m) / kRdsBlock;
+	      const int32_t mEnd = (int32_t)std::min<int64_t> (M, (K + 1) * kRdsBlock - n0);
+	      dim3 g ((unsigned)((mEnd - m + 255) / 256), (unsigned)S);
+	      rds_append_kernel<<<g, 256, 0, h -> stream>>> (h -> d_demod, h -> d_phase, h -> cap_fm, m, mEnd, n0,
+	                                                    h -> d_rds_dring, h -> d_rds_pring);
+	      h -> launches ++;
+	      if (K >= 1 && h -> rds_last_block < K - 1) {
+	         rds_block_kernel<<<S, kRdsThreads, kRdsFftSmem, h -> stream>>> (
+	               h -> d_rds_dring, K - 1, h -> d_rds_tw, h -> d_rds_R, h -> d_rds_bp, h -> d_rds_hi);
+	         h -> launches ++;
+	         h -> rds_last_block = K - 1;
+	      }
+	      rds_mix_kernel<<<g, 256, 0, h -> stream>>> (h -> d_rds_pring, h -> d_rds_bp, h -> d_rds_hi,
+	                                                 h -> cap_fm, m, mEnd, n0, h -> d_rdsc);
+	      h -> launches ++;
+	      m = mEnd;
+	   }
+	   const int32_t nout = (int32_t)((n0 + M) / kRdsDecim - n0 / kRdsDecim);
+	   float2 *rout = d_rds_out ? d_rds_out : h -> d_rds24;
+	   const int64_t rpitch = d_rds_out ? rds_pitch : h -> cap_rds;
+	   dim3 g ((unsigned)((std::max (nout, 1) + 127) / 128), (unsigned)S);
+	   rds_decim_kernel<<<g, 128, 0, h -> stream>>> (h -> d_rdsc, h -> cap_fm, M, n0, h -> d_rds_dtaps,
+	         h -> d_rds_hist [h -> rds_hist_sel], h -> d_rds_hist [h -> rds_hist_sel ^ 1], rout, rpitch, nout);
+	   h -> launches ++;
+	   h -> rds_hist_sel ^= 1;
+	   h -> rds_total += M;
+	   h -> last_nrds = nout;
+	   if (n_rds) *n_rds = nout;
+	}
 //	K6 ------------------------------------------------------------------------------------
 const int64_t q0 = h -> fm_total / kRsDecim;
 const int64_t q1 = (h -> fm_total + M) / kRsDecim;
@@ -434,7 +522,6 @@ const int64_t apitch = d_audio_out ? audio_pitch : h -> cap_audio;
 	h -> fm_total += M;
 	h -> last_naudio = nq;
 	if (n_audio) *n_audio = nq;
-	(void)d_rds_out; (void)rds_pitch;
 	CK (cudaGetLastError ());
 	return SDRJFM_OK;
 }
@@ -610,7 +697,14 @@ int sdrjfm_set_attenuation (sdrjfm_handle *h, float l, float r) {
 }
 int sdrjfm_set_rds_mode (sdrjfm_handle *h, int32_t m) {
 	if (!h || m < 0 || m > 3) return SDRJFM_ERR_ARG;
-	if (m != 0) { h -> err = "RDS branch is not on the GPU path yet"; return SDRJFM_ERR_UNSUPPORTED; }
+//	all three RDS demodulator variants (rds-decoder.cpp) consume the same 24 kHz baseband; the
+//	selector only matters to the (host-side, untouched) rdsDecoder.  Switching RDS on starts
+//	the branch from cleared filters (the reference would resume with stale block contents).
+	if (m != 0 && h -> set.rds_mode == 0) {
+	   CK (cudaSetDevice (h -> cfg.device));
+	   int rc = rds_setup (h);
+	   if (rc != SDRJFM_OK) return rc;
+	}
 	h -> set.rds_mode = m; return SDRJFM_OK;
 }
 int sdrjfm_set_local_oscillator (sdrjfm_handle *h, int32_t hz) {

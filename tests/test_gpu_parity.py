@@ -30,7 +30,7 @@ def run_gpu(pkg, x, chunks=None, **cfg):
     S, n = x.shape
     p = pkg.FmProcessorB200(n_streams=S, max_samples_per_call=max(chunks) if chunks else n)
     p.configure(**cfg)
-    taps = {k: [[] for _ in range(S)] for k in ("fm_z", "demod", "pilot_phase", "locked", "pss_delay", "lr", "audio192")}
+    taps = {k: [[] for _ in range(S)] for k in ("fm_z", "demod", "pilot_phase", "locked", "pss_delay", "lr", "audio192", "rds_cplx")}
     audio, rds = [], []
     pos = 0
     for c in (chunks or [n]):
@@ -229,3 +229,25 @@ def test_stereo_separation_figure(pkg, signals, checker):
     ref = sep(checker(**cfg).process(x, taps=("audio192",))["audio192"])
     print("separation dB: gpu", got, "reference", ref)
     assert abs(got - ref) < 0.05 and got > 20
+
+
+@pytest.mark.parametrize("chunks", [None, [16384] * 282, [N1 // 3 + 12, 5, 70000 * 12, N1 * 2]])
+def test_rds_branch_matches_reference(pkg, signals, checker, chunks):
+    """config 5 signal (57 kHz BPSK sub-carrier): band-pass, block-aligned Hilbert transform,
+    x3 pilot mix with the 64000-sample phase delay, 11-tap /8 decimator -> 24 kHz baseband.
+    Output counts are an index contract (8q+7); values within 1e-5 RMS."""
+    n = N1 * 2
+    x = signals.batch_stream(5, n)
+    cfg = dict(fm_mode=0, rds_on=1, volume_db=-6.0)
+    ref = checker(**cfg).process(x)
+    got = run_gpu(pkg, x, chunks=chunks, **cfg)
+    assert got["rds24"].shape[1] == ref["n_rds24"] == (n // 12) // 8
+    assert rms(ref["rds24"]) > 1e-2                       # there is an RDS signal to compare
+    e_c, e_24 = rms(got["rds_cplx"][0] - ref["rds_cplx"]), rms(got["rds24"][0] - ref["rds24"])
+    print("rds_cplx rms err", e_c, "rds24 rms err", e_24, "signal rms", rms(ref["rds24"]))
+    assert e_c < 1e-5 and e_24 < 1e-5
+    assert rms(got["audio192"][0] - ref["audio192"]) < 1e-5
+    ref2 = checker(**cfg).process_demod(got["demod"][0])
+    e2 = rms(got["rds24"][0] - ref2["rds24"])
+    print("rds24 rms err vs reference on GPU demod", e2)
+    assert e2 < 3e-6
