@@ -39,7 +39,7 @@ FALLBACK_HBM_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md, used if M
 def chain_settings():
     """settings of the benchmarked chain = BASELINE.json config 5 (stereo + pilot/PSS + RDS)
     as far as the GPU path implements it; the same dict configures the CPU reference arm."""
-    return dict(fm_mode=0, decoder=3, rds_on=0, auto_mono=1, pss_on=1, dc_remove=1,
+    return dict(fm_mode=0, decoder=3, rds_on=1, auto_mono=1, pss_on=1, dc_remove=1,
                 deemph_us=50, volume_db=-6.0)
 
 
@@ -183,8 +183,8 @@ def main():
                 f"{n} IQ samples @2.304 MS/s, stereo MPX + 19 kHz pilot + 57 kHz RDS sub-carrier")
     config = {"workload": workload, "streams_per_gpu": args.streams, "samples_per_stream": n,
               "settings": settings, "l2_policy": "inputs larger than L2 (per-step IQ batch >> 126 MB)",
-              "chain": "DC-remove, FIR /12, Mixed discriminator, AFC, pilot PLL, de-emphasis, "
-                       "192->48 kHz (stereo matrix/PSS and RDS stages: see DESIGN.md status)"}
+              "chain": "DC-remove, FIR /12, Mixed discriminator, AFC, pilot PLL + lock, PSS, 38 kHz L-R "
+                       "matrix, RDS band-pass/Hilbert/x3 mix//8, de-emphasis, gain, 192->48 kHz"}
 
     if args.impl == "reference":
         if rank != 0:
