@@ -142,14 +142,126 @@ float2 *Ss = S + (int64_t)stream * out_pitch;
 // sample at position n_proc - 36 + i of the concatenation (old_hist | x[0..n_proc)).
 __global__ void roll_history_kernel (const float2 *__restrict__ x, int64_t in_pitch,
                                      const float2 *__restrict__ old_hist,
-                                     float2 *__restrict__ new_hist, int64_t n_proc) {
+                                     float2 *__restrict__ new_hist, int64_t n_proc, int hist_len) {
 const int stream = blockIdx.x;
 const int i = threadIdx.x;
-	if (i >= kHist) return;
-const int64_t pos = n_proc - kHist + i;
-	new_hist [(int64_t)stream * kHist + i] =
+	if (i >= hist_len) return;
+const int64_t pos = n_proc - hist_len + i;
+	new_hist [(int64_t)stream * hist_len + i] =
 	      pos >= 0 ? x [(int64_t)stream * in_pitch + pos]
-	               : old_hist [(int64_t)stream * kHist + (kHist + pos)];
+	               : old_hist [(int64_t)stream * hist_len + (hist_len + pos)];
+}
+
+// ---- input filter ON ------------------------------------------------------------------------
+// inputFilter = fftFilter (65536, 251) (fm-processor.cpp:77,397-401,469-470) is a linear
+// convolution with 251 real low-pass taps delayed by NumofSamples = 65285 input samples
+// (SURVEY.md §8(a) a4).  Cascaded with the decimators it is ONE real FIR of 251 + 37 - 1 = 287
+// taps Cw decimating by 12:   z[m] = G sum_t Cw[t] x[12 m + 11 - 65285 - t].
+// 65285 = 12 * 5440 + 5, so with taps shifted by 5 (Cws[t'] = Cw[t' - 5], 292 taps)
+//     F[m] = sum_{t'<292} Cws[t'] x[12 m + 11 - t'],      z[m] = G F[m - 5440]:
+// the same polyphase form as the narrow kernel with 25 tap groups instead of 3, followed by
+// a pure fm-rate delay of 5440 samples (fm_delay_kernel).  ~600 FMA per output: this variant
+// is FP32-bound, not HBM-bound.
+constexpr int kFwGroups  = 25;                      // 12 * 25 = 300 >= 292 taps
+constexpr int kFwHist    = 12 * kFwGroups;          // 300 raw samples of history kept per stream
+constexpr int kFwHalo    = 6;                       // halo columns: 24 outputs = 288 samples
+constexpr int kFwPitch   = kFeThreads + kFwHalo + 1;
+constexpr int kFwSmemBytes = kFeRows * kFwPitch * (int)sizeof (float2);
+constexpr int kFwDelay   = 5440;                    // fm-rate samples
+
+__constant__ float c_wide [kDecim][kFwGroups + 3];  // c_wide[p][g] = C'ws[12 g + 11 - p]
+
+__global__ void __launch_bounds__ (kFeThreads, 3)
+frontend_wide_kernel (const float2 *__restrict__ x, int64_t in_pitch,
+                      const float2 *__restrict__ hist,
+                      float2 *__restrict__ U, float2 *__restrict__ S,
+                      int64_t out_pitch, int32_t M) {
+extern __shared__ float2 sm [];
+const int tid    = threadIdx.x;
+const int stream = blockIdx.y;
+const int64_t out0 = (int64_t)blockIdx.x * kFeTileOut;
+const int64_t in0  = out0 * kDecim;
+const int64_t N    = (int64_t)M * kDecim;
+const float2 *xs = x + (int64_t)stream * in_pitch;
+constexpr int kHaloIn = kFwHalo * kFeRows;           // 288 samples before the tile
+
+//	halo: columns 0..5 (sample in0 - 288 + i sits at row i % 48, column i / 48)
+	for (int i = tid; i < kHaloIn; i += kFeThreads) {
+	   float2 v;
+	   if (blockIdx.x == 0) v = hist [(int64_t)stream * kFwHist + (kFwHist - kHaloIn) + i];
+	   else                 v = xs [in0 - kHaloIn + i];
+	   sm [(i % kFeRows) * kFwPitch + i / kFeRows] = v;
+	}
+#pragma unroll
+	for (int b = 0; b < 3; b ++) {
+	   float2 v [16];
+#pragma unroll
+	   for (int k = 0; k < 16; k ++) {
+	      const int j = (b * 16 + k) * kFeThreads + tid;
+	      const int64_t n = in0 + j;
+	      v [k] = (n < N) ? __ldcs (xs + n) : make_float2 (0.f, 0.f);
+	   }
+#pragma unroll
+	   for (int k = 0; k < 16; k ++) {
+	      const int j = (b * 16 + k) * kFeThreads + tid;
+	      const int col = j / kFeRows;
+	      const int row = j - col * kFeRows;
+	      sm [row * kFwPitch + col + kFwHalo] = v [k];
+	   }
+	}
+	__syncthreads ();
+
+//	thread t -> outputs 4t..4t+3; output index 4t + q (q may be negative) sits in column
+//	t + kFwHalo + floor (q / 4), rows 12 * (q mod 4) + p
+float2 acc [kFeGpt], dcs [kFeGpt];
+#pragma unroll
+	for (int k = 0; k < kFeGpt; k ++) { acc [k] = make_float2 (0.f, 0.f); dcs [k] = make_float2 (0.f, 0.f); }
+const float2 *col0 = sm + tid + kFwHalo;
+#pragma unroll 1
+	for (int p = 0; p < kDecim; p ++) {
+	   float2 w3 = col0 [(36 + p) * kFwPitch];       // q = 3
+	   float2 w2 = col0 [(24 + p) * kFwPitch];       // q = 2
+	   float2 w1 = col0 [(12 + p) * kFwPitch];       // q = 1
+	   float2 w0 = col0 [(p) * kFwPitch];            // q = 0
+	   dcs [3].x += w3.x; dcs [3].y += w3.y; dcs [2].x += w2.x; dcs [2].y += w2.y;
+	   dcs [1].x += w1.x; dcs [1].y += w1.y; dcs [0].x += w0.x; dcs [0].y += w0.y;
+#pragma unroll
+	   for (int g = 0; g < kFwGroups; g ++) {
+	      const float c = c_wide [p][g];
+	      acc [3].x = fmaf (c, w3.x, acc [3].x); acc [3].y = fmaf (c, w3.y, acc [3].y);
+	      acc [2].x = fmaf (c, w2.x, acc [2].x); acc [2].y = fmaf (c, w2.y, acc [2].y);
+	      acc [1].x = fmaf (c, w1.x, acc [1].x); acc [1].y = fmaf (c, w1.y, acc [1].y);
+	      acc [0].x = fmaf (c, w0.x, acc [0].x); acc [0].y = fmaf (c, w0.y, acc [0].y);
+	      w3 = w2; w2 = w1; w1 = w0;
+	      if (g + 1 < kFwGroups) {
+	         const int q = -1 - g;                        // next older output index relative to 4t
+	         const int cq = (q - 3) / 4;                  // floor (q / 4) for negative q
+	         const int rq = q - 4 * cq;                   // q mod 4 in 0..3
+	         w0 = col0 [cq + (12 * rq + p) * kFwPitch];
+	      }
+	   }
+	}
+const int64_t m0 = out0 + (int64_t)tid * kFeGpt;
+float2 *Us = U + (int64_t)stream * out_pitch;
+float2 *Ss = S + (int64_t)stream * out_pitch;
+#pragma unroll
+	for (int k = 0; k < kFeGpt; k ++)
+	   if (m0 + k < M) { Us [m0 + k] = acc [k]; Ss [m0 + k] = dcs [k]; }
+}
+
+// fm-rate delay line: out[m] = (hist | in)[m], new_hist = the last D entries of (hist | in)
+__global__ void fm_delay_kernel (const float2 *__restrict__ in, int64_t pitch, int32_t M, int D,
+                                 const float2 *__restrict__ hist, float2 *__restrict__ new_hist,
+                                 float2 *__restrict__ out) {
+const int stream = blockIdx.y;
+const int i = blockIdx.x * blockDim.x + threadIdx.x;
+const float2 *is = in + (int64_t)stream * pitch;
+const float2 *hs = hist + (int64_t)stream * D;
+	if (i < M) out [(int64_t)stream * pitch + i] = i < D ? hs [i] : is [i - D];
+	if (i < D) {
+	   const int j = M + i;                              // index into (hist | in)
+	   new_hist [(int64_t)stream * D + i] = j < D ? hs [j] : is [j - D];
+	}
 }
 
 }	// namespace sdrjfm

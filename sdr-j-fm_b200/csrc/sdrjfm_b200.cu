@@ -59,6 +59,11 @@ struct sdrjfm_handle {
 	float2 *d_ahist [2] = { nullptr, nullptr }; int ahist_sel = 0;
 	float2 *d_audio = nullptr;              // [S][cap_audio] working-rate stereo
 	StreamState *d_state = nullptr;
+	// input filter ON (allocated when first switched on): wide front end + fm-rate delay lines
+	float2 *d_histw [2] = { nullptr, nullptr }; int histw_sel = 0;
+	float2 *d_Uw = nullptr, *d_Sw = nullptr;
+	float2 *d_udel [2] = { nullptr, nullptr }, *d_sdel [2] = { nullptr, nullptr }; int del_sel = 0;
+	float   wide_sumC = 0, wide_sumCm = 0;
 	// RDS branch (allocated when RDS is first switched on)
 	float   *d_rds_dring = nullptr, *d_rds_pring = nullptr;     // [S][131072] demod / pilot phase by rds index
 	float   *d_rds_bp = nullptr, *d_rds_hi = nullptr;           // [S][2][32000] / [S][2][32768]
@@ -132,6 +137,27 @@ float comp [40] = { 0 };
 	   }
 	   for (int i = 0; i < kRsTaps; i ++) t [i] = (float)(d [i] / sum);
 	   CK (cudaMemcpyToSymbol (c_rs_taps, t, sizeof t));
+	}
+
+//	input filter ON: composite of the 251-tap low-pass and the decimator cascade, shifted by 5
+//	samples (frontend_fir.cuh), RF DC removal folded in exactly like the narrow taps (tables.cpp)
+	if (th.ncomp_wide > 0) {
+	   const float *wide = h -> tables.payload () + th.off_comp_wide;
+	   std::vector<double> cw (kFwHist, 0.0), g (kFwHist, 0.0);
+	   for (int t = 0; t < th.ncomp_wide && t + 5 < kFwHist; t ++) cw [t + 5] = (double)wide [t];
+	   for (int i = 0; i < kFwHist; i ++)
+	      for (int k = i + 1; k < kFwHist; k ++) g [i] += cw [k];
+	   const double alpha = (double)(1.0f / th.input_rate);
+	   float cwide [kDecim][kFwGroups + 3];
+	   memset (cwide, 0, sizeof cwide);
+	   double sC = 0, sCm = 0;
+	   for (int i = 0; i < kFwHist; i ++) {
+	      const float f = (float)(cw [i] + alpha * g [i]);
+	      sC += cw [i]; sCm += f;
+	      cwide [11 - i % kDecim][i / kDecim] = f;
+	   }
+	   h -> wide_sumC = (float)sC; h -> wide_sumCm = (float)sCm;
+	   CK (cudaMemcpyToSymbol (c_wide, cwide, sizeof cwide));
 	}
 
 //	PSS low-pass taps: lpFilter (2048, 295).setLowPass (15000, rate), stereo-separation.cpp:31-39
@@ -337,7 +363,9 @@ void *ptrs [] = { h -> d_tables, h -> d_sin_quarter, h -> d_in, h -> d_hist [0],
 	              h -> d_rdsc, h -> d_rds24, h -> d_ahist [0], h -> d_ahist [1], h -> d_audio,
 	              h -> d_state, h -> d_iter_stats, h -> d_pss_ring,
 	              h -> d_rds_dring, h -> d_rds_pring, h -> d_rds_bp, h -> d_rds_hi, h -> d_rds_R, h -> d_rds_tw,
-	              h -> d_rds_dtaps, h -> d_rds_hist [0], h -> d_rds_hist [1] };
+	              h -> d_rds_dtaps, h -> d_rds_hist [0], h -> d_rds_hist [1],
+	              h -> d_histw [0], h -> d_histw [1], h -> d_Uw, h -> d_Sw, h -> d_udel [0], h -> d_udel [1],
+	              h -> d_sdel [0], h -> d_sdel [1] };
 	for (void *p : ptrs) if (p) cudaFree (p);
 	if (h -> stream) cudaStreamDestroy (h -> stream);
 	delete h;
@@ -365,10 +393,35 @@ static int launch_frontend (sdrjfm_handle *h, const float2 *src, int64_t pitch, 
                             const float2 *hist) {
 const int S = h -> cfg.n_streams;
 dim3 grid ((unsigned)((M + kFeTileOut - 1) / kFeTileOut), (unsigned)S);
-	frontend_fir_kernel<<<grid, kFeThreads, kFeSmemBytes, h -> stream>>> (
-	      src, pitch, hist, h -> d_U, h -> d_S, h -> cap_fm, M);
+	if (h -> set.input_filter_hz > 0)
+	   frontend_wide_kernel<<<grid, kFeThreads, kFwSmemBytes, h -> stream>>> (
+	         src, pitch, h -> d_histw [h -> histw_sel], h -> d_Uw, h -> d_Sw, h -> cap_fm, M);
+	else
+	   frontend_fir_kernel<<<grid, kFeThreads, kFeSmemBytes, h -> stream>>> (
+	         src, pitch, hist, h -> d_U, h -> d_S, h -> cap_fm, M);
 	h -> launches ++;
 	CK (cudaGetLastError ());
+	return SDRJFM_OK;
+}
+
+// buffers of the wide (input filter ON) front end; cleared start
+static int wide_setup (sdrjfm_handle *h) {
+const int64_t S = h -> cfg.n_streams;
+	if (!h -> d_Uw) {
+	   CK (dalloc (&h -> d_histw [0], (size_t)S * kFwHist)); CK (dalloc (&h -> d_histw [1], (size_t)S * kFwHist));
+	   CK (dalloc (&h -> d_Uw, (size_t)S * h -> cap_fm)); CK (dalloc (&h -> d_Sw, (size_t)S * h -> cap_fm));
+	   for (int i = 0; i < 2; i ++) {
+	      CK (dalloc (&h -> d_udel [i], (size_t)S * kFwDelay)); CK (dalloc (&h -> d_sdel [i], (size_t)S * kFwDelay));
+	   }
+	   CK (cudaFuncSetAttribute (frontend_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwSmemBytes));
+	}
+	else {
+	   for (int i = 0; i < 2; i ++) {
+	      CK (cudaMemsetAsync (h -> d_histw [i], 0, (size_t)S * kFwHist * sizeof (float2), h -> stream));
+	      CK (cudaMemsetAsync (h -> d_udel [i], 0, (size_t)S * kFwDelay * sizeof (float2), h -> stream));
+	      CK (cudaMemsetAsync (h -> d_sdel [i], 0, (size_t)S * kFwDelay * sizeof (float2), h -> stream));
+	   }
+	}
 	return SDRJFM_OK;
 }
 
@@ -396,15 +449,31 @@ const int32_t M = (int32_t)(n_proc / kDecim);
 	if (M == 0) return SDRJFM_OK;
 int rc;
 //	K1 ------------------------------------------------------------------------------------
+const bool wide = st.input_filter_hz > 0;
 	if ((rc = launch_frontend (h, src, pitch, M, h -> d_hist [h -> hist_sel])) != SDRJFM_OK) return rc;
-	roll_history_kernel<<<S, 64, 0, h -> stream>>> (src, pitch, h -> d_hist [h -> hist_sel],
-	                                               h -> d_hist [h -> hist_sel ^ 1], n_proc);
-	h -> hist_sel ^= 1; h -> launches ++;
+	if (wide) {
+	   roll_history_kernel<<<S, 320, 0, h -> stream>>> (src, pitch, h -> d_histw [h -> histw_sel],
+	                                                   h -> d_histw [h -> histw_sel ^ 1], n_proc, kFwHist);
+	   h -> histw_sel ^= 1;
+	   dim3 g ((unsigned)((std::max (M, kFwDelay) + 255) / 256), (unsigned)S);
+	   fm_delay_kernel<<<g, 256, 0, h -> stream>>> (h -> d_Uw, h -> cap_fm, M, kFwDelay, h -> d_udel [h -> del_sel],
+	                                                h -> d_udel [h -> del_sel ^ 1], h -> d_U);
+	   fm_delay_kernel<<<g, 256, 0, h -> stream>>> (h -> d_Sw, h -> cap_fm, M, kFwDelay, h -> d_sdel [h -> del_sel],
+	                                                h -> d_sdel [h -> del_sel ^ 1], h -> d_S);
+	   h -> del_sel ^= 1;
+	   h -> launches += 3;
+	}
+	else {
+	   roll_history_kernel<<<S, 64, 0, h -> stream>>> (src, pitch, h -> d_hist [h -> hist_sel],
+	                                                  h -> d_hist [h -> hist_sel ^ 1], n_proc, kHist);
+	   h -> hist_sel ^= 1; h -> launches ++;
+	}
 //	K2 ------------------------------------------------------------------------------------
 const float *consts = h -> tables.payload () + th.off_comp_consts;
 DiscrParams dp;
 	dp.sumC = consts [0]; dp.sumCm = consts [1];
 	dp.gb0 = consts [5]; dp.gb1 = consts [6]; dp.gb2 = consts [7];
+	if (wide) { dp.sumC = h -> wide_sumC; dp.sumCm = h -> wide_sumCm; dp.gb0 = dp.gb1 = dp.gb2 = 0.f; }
 	dp.Gre = consts [2]; dp.Gim = consts [3];
 	dp.alpha = (double)(1.0f / h -> cfg.input_rate);          // rfDcAlpha, fm-processor.cpp:379
 	dp.beta = pow (1.0 - dp.alpha, (double)kDecim);
@@ -688,8 +757,16 @@ int sdrjfm_set_lf_cutoff (sdrjfm_handle *h, int32_t hz) {
 }
 int sdrjfm_set_bandwidth (sdrjfm_handle *h, int32_t hz) {
 	if (!h) return SDRJFM_ERR_ARG;
-	if (hz > 0) { h -> err = "input filter is not on the GPU path yet"; return SDRJFM_ERR_UNSUPPORTED; }
-	h -> set.input_filter_hz = 0; return SDRJFM_OK;
+//	setBandwidth (:232-239): "Off" -> 0; else fmBandwidth in Hz, the low-pass corner is hz / 2 (:398).
+//	Switching the filter on (or changing it) starts it from a cleared state.
+	CK (cudaSetDevice (h -> cfg.device));
+	const int32_t v = hz > 0 ? hz : 0;
+	if (v == h -> set.input_filter_hz) return SDRJFM_OK;
+	h -> set.input_filter_hz = v;
+	int rc = rebuild_tables (h);
+	if (rc != SDRJFM_OK) return rc;
+	if (v > 0) return wide_setup (h);
+	return SDRJFM_OK;
 }
 int sdrjfm_set_attenuation (sdrjfm_handle *h, float l, float r) {
 	if (!h) return SDRJFM_ERR_ARG;

@@ -251,3 +251,25 @@ def test_rds_branch_matches_reference(pkg, signals, checker, chunks):
     e2 = rms(got["rds24"][0] - ref2["rds24"])
     print("rds24 rms err vs reference on GPU demod", e2)
     assert e2 < 3e-6
+
+
+@pytest.mark.parametrize("chunks", [None, [16384] * 141])
+def test_input_filter_config3_matches_reference(pkg, signals, checker, chunks):
+    """config 3: stereo signal + adjacent FM carrier at +200 kHz, +20 dB; setBandwidth (165 kHz)
+    => 251-tap low-pass at 82.5 kHz in front of the decimators, delay 65285 input samples."""
+    n = N1
+    x = signals.adjacent_interferer(n)
+    cfg = dict(fm_mode=0, input_filter_hz=165000, volume_db=0.0)
+    ref = checker(**cfg).process(x)
+    got = run_gpu(pkg, x, chunks=chunks, **cfg)
+    assert len(got["demod"][0]) == ref["n_fm"]
+    assert np.all(np.abs(ref["fm_z"][:5440]) < 1e-12) and np.all(np.abs(got["fm_z"][0][:5440]) < 1e-12)
+    e = rms(got["fm_z"][0] - ref["fm_z"]) / rms(ref["fm_z"])
+    print("fm_z rel rms", e, "demod", rms(got["demod"][0] - ref["demod"]),
+          "audio192", rms(got["audio192"][0] - ref["audio192"]))
+    assert e < 3e-6
+    assert rms(got["demod"][0] - ref["demod"]) < 1e-5
+    assert rms(got["audio192"][0] - ref["audio192"]) < 1e-5
+    # the filter does its job: without it the interferer wrecks the demodulated signal
+    off = checker(fm_mode=0, volume_db=0.0).process(x)
+    assert rms(off["demod"][5440:] - ref["demod"][5440:]) > 1e-2
