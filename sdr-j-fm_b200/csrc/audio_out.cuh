@@ -163,6 +163,68 @@ float2 *tap = a192 ? a192 + (int64_t)stream * pitch : nullptr;
 	}
 }
 
+// ---- optional audio low-pass -------------------------------------------------------------------
+// fmAudioFilter = fftFilter (8192, 756).setLowPass (lowPassFrequency, fmRate), applied to the
+// (left, right) pair after the selector and before de-emphasis (fm-processor.cpp:76,403-408,
+// 589-591).  The taps are real, so it is the same 756-tap FIR on each channel, delayed by
+// NumofSamples = 8192 - 756 = 7436 samples:  y[n] = sum_j h[j] q[n - 7436 - j].
+constexpr int kAlpTaps    = 756;
+constexpr int kAlpDelay   = 8192 - kAlpTaps;          // 7436
+constexpr int kAlpHist    = 8192;                     // >= 7436 + 755 samples of (left,right) history
+constexpr int kAlpThreads = 256;
+constexpr int kAlpPer     = 4;
+constexpr int kAlpTile    = kAlpThreads * kAlpPer;    // 1024 outputs per CTA
+constexpr int kAlpSpan    = kAlpTile + kAlpTaps;      // staged inputs (1780 >= 1024 + 755)
+
+__constant__ float c_alp_taps [kAlpTaps];
+
+// q: [S][pitch] this call's (left,right); hist: [S][8192] the samples before it (oldest first)
+__global__ void __launch_bounds__ (kAlpThreads)
+audio_lp_kernel (const float2 *__restrict__ q, int64_t pitch, int32_t M,
+                 const float2 *__restrict__ hist, float2 *__restrict__ out) {
+// phase-major staging: staged element e sits at [e & 3][e >> 2] (conflict-free sliding windows)
+__shared__ float2 sQ [4][kAlpSpan / 4 + 2];
+const int tid = threadIdx.x;
+const int stream = blockIdx.y;
+const int t0 = blockIdx.x * kAlpTile;
+const int lo = t0 - kAlpDelay - (kAlpTaps - 1);       // local index of staged element 0
+const float2 *qs = q + (int64_t)stream * pitch;
+const float2 *hs = hist + (int64_t)stream * kAlpHist;
+	for (int e = tid; e < kAlpSpan; e += kAlpThreads) {
+	   const int n = lo + e;
+	   float2 v = make_float2 (0.f, 0.f);
+	   if (n >= 0) { if (n < M) v = qs [n]; }
+	   else if (n >= -kAlpHist) v = hs [kAlpHist + n];
+	   sQ [e & 3][e >> 2] = v;
+	}
+	__syncthreads ();
+//	output t0 + 4 tid + k, tap j reads staged element 4 tid + k + 755 - j
+float2 acc [kAlpPer];
+#pragma unroll
+	for (int k = 0; k < kAlpPer; k ++) acc [k] = make_float2 (0.f, 0.f);
+float2 w [kAlpPer];
+#pragma unroll
+	for (int k = 0; k < kAlpPer; k ++) { const int e = 4 * tid + k + kAlpTaps - 1; w [k] = sQ [e & 3][e >> 2]; }
+#pragma unroll 4
+	for (int j = 0; j < kAlpTaps; j ++) {
+	   const float c = c_alp_taps [j];
+#pragma unroll
+	   for (int k = 0; k < kAlpPer; k ++) {
+	      acc [k].x = fmaf (c, w [k].x, acc [k].x);
+	      acc [k].y = fmaf (c, w [k].y, acc [k].y);
+	   }
+#pragma unroll
+	   for (int k = kAlpPer - 1; k > 0; k --) w [k] = w [k - 1];
+	   const int e = 4 * tid + kAlpTaps - 2 - j;          // element for k = 0 at tap j + 1
+	   w [0] = e >= 0 ? sQ [e & 3][e >> 2] : make_float2 (0.f, 0.f);
+	}
+#pragma unroll
+	for (int k = 0; k < kAlpPer; k ++) {
+	   const int n = t0 + 4 * tid + k;
+	   if (n < M) out [(int64_t)stream * pitch + n] = acc [k];
+	}
+}
+
 // mono / unlocked path of process_signal_with_rds + the L/R matrix, fm-processor.cpp:728-730
 // and :517-549 with diffLR = 0: left = right = sumLR = demod for every selector except
 // S_LEFTminusRIGHT(_Test), which yields 0.

@@ -143,8 +143,8 @@ float2 *Ss = S + (int64_t)stream * out_pitch;
 __global__ void roll_history_kernel (const float2 *__restrict__ x, int64_t in_pitch,
                                      const float2 *__restrict__ old_hist,
                                      float2 *__restrict__ new_hist, int64_t n_proc, int hist_len) {
-const int stream = blockIdx.x;
-const int i = threadIdx.x;
+const int stream = blockIdx.y;
+const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= hist_len) return;
 const int64_t pos = n_proc - hist_len + i;
 	new_hist [(int64_t)stream * hist_len + i] =

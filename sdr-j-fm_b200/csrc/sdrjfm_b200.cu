@@ -64,6 +64,9 @@ struct sdrjfm_handle {
 	float2 *d_Uw = nullptr, *d_Sw = nullptr;
 	float2 *d_udel [2] = { nullptr, nullptr }, *d_sdel [2] = { nullptr, nullptr }; int del_sel = 0;
 	float   wide_sumC = 0, wide_sumCm = 0;
+	// audio low-pass (allocated when first switched on)
+	float2 *d_alp_hist [2] = { nullptr, nullptr }; int alp_sel = 0;
+	float2 *d_lrf = nullptr;
 	// RDS branch (allocated when RDS is first switched on)
 	float   *d_rds_dring = nullptr, *d_rds_pring = nullptr;     // [S][131072] demod / pilot phase by rds index
 	float   *d_rds_bp = nullptr, *d_rds_hi = nullptr;           // [S][2][32000] / [S][2][32768]
@@ -365,7 +368,7 @@ void *ptrs [] = { h -> d_tables, h -> d_sin_quarter, h -> d_in, h -> d_hist [0],
 	              h -> d_rds_dring, h -> d_rds_pring, h -> d_rds_bp, h -> d_rds_hi, h -> d_rds_R, h -> d_rds_tw,
 	              h -> d_rds_dtaps, h -> d_rds_hist [0], h -> d_rds_hist [1],
 	              h -> d_histw [0], h -> d_histw [1], h -> d_Uw, h -> d_Sw, h -> d_udel [0], h -> d_udel [1],
-	              h -> d_sdel [0], h -> d_sdel [1] };
+	              h -> d_sdel [0], h -> d_sdel [1], h -> d_alp_hist [0], h -> d_alp_hist [1], h -> d_lrf };
 	for (void *p : ptrs) if (p) cudaFree (p);
 	if (h -> stream) cudaStreamDestroy (h -> stream);
 	delete h;
@@ -452,7 +455,7 @@ int rc;
 const bool wide = st.input_filter_hz > 0;
 	if ((rc = launch_frontend (h, src, pitch, M, h -> d_hist [h -> hist_sel])) != SDRJFM_OK) return rc;
 	if (wide) {
-	   roll_history_kernel<<<S, 320, 0, h -> stream>>> (src, pitch, h -> d_histw [h -> histw_sel],
+	   roll_history_kernel<<<dim3 (2, S), 160, 0, h -> stream>>> (src, pitch, h -> d_histw [h -> histw_sel],
 	                                                   h -> d_histw [h -> histw_sel ^ 1], n_proc, kFwHist);
 	   h -> histw_sel ^= 1;
 	   dim3 g ((unsigned)((std::max (M, kFwDelay) + 255) / 256), (unsigned)S);
@@ -464,7 +467,7 @@ const bool wide = st.input_filter_hz > 0;
 	   h -> launches += 3;
 	}
 	else {
-	   roll_history_kernel<<<S, 64, 0, h -> stream>>> (src, pitch, h -> d_hist [h -> hist_sel],
+	   roll_history_kernel<<<dim3 (1, S), 64, 0, h -> stream>>> (src, pitch, h -> d_hist [h -> hist_sel],
 	                                                  h -> d_hist [h -> hist_sel ^ 1], n_proc, kHist);
 	   h -> hist_sel ^= 1; h -> launches ++;
 	}
@@ -567,6 +570,16 @@ const size_t seq_smem = (h -> lut.quarter + 1) * sizeof (float);
 	   if (n_rds) *n_rds = nout;
 	}
 //	K6 ------------------------------------------------------------------------------------
+const float2 *lr_in = h -> d_lr;
+	if (st.lf_cutoff_hz > 0) {
+	   dim3 g ((unsigned)((M + kAlpTile - 1) / kAlpTile), (unsigned)S);
+	   audio_lp_kernel<<<g, kAlpThreads, 0, h -> stream>>> (h -> d_lr, h -> cap_fm, M,
+	                                                        h -> d_alp_hist [h -> alp_sel], h -> d_lrf);
+	   roll_history_kernel<<<dim3 (kAlpHist / 256, S), 256, 0, h -> stream>>> (
+	         h -> d_lr, h -> cap_fm, h -> d_alp_hist [h -> alp_sel], h -> d_alp_hist [h -> alp_sel ^ 1], M, kAlpHist);
+	   h -> alp_sel ^= 1; h -> launches += 2;
+	   lr_in = h -> d_lrf;
+	}
 const int64_t q0 = h -> fm_total / kRsDecim;
 const int64_t q1 = (h -> fm_total + M) / kRsDecim;
 const int32_t nq = (int32_t)(q1 - q0);
@@ -582,7 +595,7 @@ const int64_t apitch = d_audio_out ? audio_pitch : h -> cap_audio;
 	   ap.sel = h -> ahist_sel;
 	   dim3 g ((unsigned)((M + kAuTile - 1) / kAuTile), (unsigned)S);
 	   audio_kernel<<<g, kAuThreads, 0, h -> stream>>> (
-	         h -> d_lr, h -> cap_fm, ap, h -> d_ahist [h -> ahist_sel], h -> d_ahist [h -> ahist_sel ^ 1],
+	         lr_in, h -> cap_fm, ap, h -> d_ahist [h -> ahist_sel], h -> d_ahist [h -> ahist_sel ^ 1],
 	         h -> d_state, h -> d_a192, aout, apitch);
 	   h -> launches ++;
 	   h -> ahist_sel ^= 1;
@@ -752,8 +765,26 @@ int sdrjfm_set_volume_db (sdrjfm_handle *h, float db) {
 }
 int sdrjfm_set_lf_cutoff (sdrjfm_handle *h, int32_t hz) {
 	if (!h) return SDRJFM_ERR_ARG;
-	if (hz > 0) { h -> err = "audio low-pass is not on the GPU path yet"; return SDRJFM_ERR_UNSUPPORTED; }
-	h -> set.lf_cutoff_hz = 0; return SDRJFM_OK;
+//	setlfcutoff (:762-770): <= 0 switches fmAudioFilter off; else it is re-designed and starts cleared
+	CK (cudaSetDevice (h -> cfg.device));
+	const int32_t v = hz > 0 ? hz : 0;
+	if (v == h -> set.lf_cutoff_hz) return SDRJFM_OK;
+	h -> set.lf_cutoff_hz = v;
+	if (v > 0) {
+	   const int64_t S = h -> cfg.n_streams;
+	   if (!h -> d_lrf) {
+	      CK (dalloc (&h -> d_alp_hist [0], (size_t)S * kAlpHist)); CK (dalloc (&h -> d_alp_hist [1], (size_t)S * kAlpHist));
+	      CK (dalloc (&h -> d_lrf, (size_t)S * h -> cap_fm));
+	   }
+	   else for (int i = 0; i < 2; i ++)
+	      CK (cudaMemsetAsync (h -> d_alp_hist [i], 0, (size_t)S * kAlpHist * sizeof (float2), h -> stream));
+	   std::vector<cf32> lp = design_lowpass (kAlpTaps, v, h -> cfg.fm_rate);
+	   float t [kAlpTaps];
+	   for (int i = 0; i < kAlpTaps; i ++) t [i] = lp [i].real ();
+	   CK (cudaMemcpyToSymbolAsync (c_alp_taps, t, sizeof t, 0, cudaMemcpyHostToDevice, h -> stream));
+	   CK (cudaStreamSynchronize (h -> stream));
+	}
+	return SDRJFM_OK;
 }
 int sdrjfm_set_bandwidth (sdrjfm_handle *h, int32_t hz) {
 	if (!h) return SDRJFM_ERR_ARG;

@@ -273,3 +273,17 @@ def test_input_filter_config3_matches_reference(pkg, signals, checker, chunks):
     # the filter does its job: without it the interferer wrecks the demodulated signal
     off = checker(fm_mode=0, volume_db=0.0).process(x)
     assert rms(off["demod"][5440:] - ref["demod"][5440:]) > 1e-2
+
+
+@pytest.mark.parametrize("chunks", [None, [16384] * 141])
+def test_audio_lowpass_matches_reference(pkg, signals, checker, chunks):
+    """fmAudioFilter (8192-FFT, 756 taps, 15 kHz) on the (left, right) pair: delay 7436 samples."""
+    n = N1
+    x = signals.stereo_pilot(n, left_hz=1000.0, right_hz=3000.0)
+    cfg = dict(fm_mode=0, lf_cutoff_hz=15000, volume_db=0.0)
+    ref = checker(**cfg).process(x)
+    got = run_gpu(pkg, x, chunks=chunks, **cfg)
+    e = rms(got["audio192"][0] - ref["audio192"])
+    print("audio192 rms err with audio low-pass", e)
+    assert e < 1e-5
+    assert np.all(np.abs(got["audio192"][0][:7436]) < 1e-12)
