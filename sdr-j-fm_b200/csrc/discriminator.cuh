@@ -24,6 +24,13 @@ struct DiscrParams {
 	double alpha, beta;         // alpha = (float)1/inputRate; beta = (1 - alpha)^12
 	float  lgain, rgain;
 	int32_t dc_remove, decoder;
+	// local oscillator on: gains and rotation were applied per input sample by K1; the DC value
+	// the reference subtracted BEFORE the rotation comes back out as clamp (r) * gains *
+	// Table[LOPhase at 12 (m + lo_moff) + 11] * H,  H = sum_t C[t] exp (+2 pi i lo t / inputRate)
+	const float2 *lo_tab;
+	int32_t lo_rate, lo_hz, lo_moff;
+	int64_t lo_phase;
+	float  Hre, Him;
 };
 
 // compAtan::atan2, src/various/Xtan2.cpp:56-100.  Only the first-octant table PPY is kept
@@ -184,8 +191,17 @@ double pw [6];
 	         st.sprev [0] = sm1.x; st.sprev [1] = sm1.y; st.sprev [2] = sm2.x; st.sprev [3] = sm2.y;
 	      }
 	      // IQ gain (fm-processor.cpp:462-464) commutes with the real-tap FIR
-	      const float vx = (u [j].x - kx) * P.lgain;
-	      const float vy = (u [j].y - ky) * P.rgain;
+	      float vx = (u [j].x - kx) * P.lgain;
+	      float vy = (u [j].y - ky) * P.rgain;
+	      if (P.lo_tab) {
+	         int64_t t = (P.lo_phase - (int64_t)P.lo_hz * (12 * (j0 + j + (int64_t)P.lo_moff) + 12)) % P.lo_rate;
+	         if (t < 0) t += P.lo_rate;
+	         const float2 o = P.lo_tab [t];
+	         const float2 a = make_float2 (c.x * P.lgain, c.y * P.rgain);
+	         const float2 b = make_float2 (a.x * o.x - a.y * o.y, a.x * o.y + a.y * o.x);
+	         vx = u [j].x - (b.x * P.Hre - b.y * P.Him);
+	         vy = u [j].y - (b.x * P.Him + b.y * P.Hre);
+	      }
 	      z [j] = make_float2 (vx * P.Gre - vy * P.Gim, vx * P.Gim + vy * P.Gre);
 	      // std::abs (complex<float>) = hypotf: evaluated through double (fm-demodulator.cpp:119)
 	      za [j] = (float)sqrt ((double)z [j].x * (double)z [j].x +

@@ -35,15 +35,38 @@ constexpr int kFeSmemBytes = kFeRows * kFePitch * (int)sizeof (float2);   // 495
 
 __constant__ float c_comp [40];                     // composite taps C[0..36]
 
+// Local oscillator (fm-processor.cpp:462-466, oscillator.cpp:26-58): before the filters every
+// sample is scaled per component (IQ gain) and multiplied by Table[LOPhase], LOPhase stepping
+// by -lo per sample modulo inputRate.  tab = the reference's inputRate-entry table.
+struct LoParams {
+	const float2 *tab;         // nullptr: LO off (lo = 0 multiplies by (1,0): identity)
+	int32_t rate;              // inputRate
+	int32_t lo;                // loFrequency (Hz = table steps per sample)
+	int32_t step128;           // (128 * lo) mod rate, in [0, rate)
+	int64_t phase;             // LOPhase after the sample before src[0]
+	float   lgain, rgain;
+};
+
+__device__ __forceinline__ int32_t lo_index (const LoParams &L, int64_t n) {     // sample src[n]
+int64_t t = (L.phase - (int64_t)L.lo * (n + 1)) % L.rate;
+	return (int32_t)(t < 0 ? t + L.rate : t);
+}
+__device__ __forceinline__ float2 lo_apply (const LoParams &L, float2 v, int32_t idx) {
+	return cmul_rn (make_float2 (fmul (v.x, L.lgain), fmul (v.y, L.rgain)), L.tab [idx]);
+}
+
 // x      : [n_streams][in_pitch] complex, this call's samples (N = 12 * M per stream)
 // hist   : [n_streams][kHist] complex, the 36 raw samples preceding x[.][0]
 // U, S   : [n_streams][out_pitch] complex
+template <bool LO>
 __global__ void __launch_bounds__ (kFeThreads, 4)
 frontend_fir_kernel (const float2 *__restrict__ x, int64_t in_pitch,
                      const float2 *__restrict__ hist,
                      float2 *__restrict__ U, float2 *__restrict__ S,
-                     int64_t out_pitch, int32_t M) {
+                     int64_t out_pitch, int32_t M, const LoParams lop) {
 extern __shared__ float2 sm [];
+__shared__ float2 sRaw [LO ? kFeTileOut : 1];
+	if (LO) { for (int i = threadIdx.x; i < kFeTileOut; i += kFeThreads) sRaw [i] = make_float2 (0.f, 0.f); __syncthreads (); }
 const int tid    = threadIdx.x;
 const int stream = blockIdx.y;
 const int64_t out0 = (int64_t)blockIdx.x * kFeTileOut;   // first output of the tile
@@ -56,8 +79,10 @@ const float2 *xs = x + (int64_t)stream * in_pitch;
 	   float2 v;
 	   if (blockIdx.x == 0) v = hist [(int64_t)stream * kHist + tid];
 	   else                 v = xs [in0 - kHist + tid];
+	   if (LO) v = lo_apply (lop, v, lo_index (lop, in0 - kHist + tid));
 	   sm [(kDecim + tid) * kFePitch] = v;
 	}
+int32_t loIdx = LO ? lo_index (lop, in0 + tid) : 0;
 
 //	body: 48 coalesced 8-byte loads per thread, issued in batches so that 16 are in flight
 #pragma unroll
@@ -68,6 +93,12 @@ const float2 *xs = x + (int64_t)stream * in_pitch;
 	      const int j = (b * 16 + k) * kFeThreads + tid;
 	      const int64_t n = in0 + j;
 	      v [k] = (n < N) ? __ldcs (xs + n) : make_float2 (0.f, 0.f);
+	      if (LO) {
+	         // the RF DC estimate follows the RAW samples: block sums before gain and rotation
+	         atomicAdd (&sRaw [j / kDecim].x, v [k].x); atomicAdd (&sRaw [j / kDecim].y, v [k].y);
+	         v [k] = lo_apply (lop, v [k], loIdx);
+	         loIdx -= lop.step128; if (loIdx < 0) loIdx += lop.rate;
+	      }
 	   }
 #pragma unroll
 	   for (int k = 0; k < 16; k ++) {
@@ -123,6 +154,10 @@ const float2 *colc = sm + tid + 1;    // own column
 const int64_t m0 = out0 + (int64_t)tid * kFeGpt;
 float2 *Us = U + (int64_t)stream * out_pitch;
 float2 *Ss = S + (int64_t)stream * out_pitch;
+	if (LO) {
+#pragma unroll
+	   for (int k = 0; k < kFeGpt; k ++) dcs [k] = sRaw [tid * kFeGpt + k];
+	}
 	if (m0 + kFeGpt <= M && (out_pitch & 1) == 0) {
 	   float4 *u4 = reinterpret_cast<float4 *>(Us + m0);
 	   float4 *s4 = reinterpret_cast<float4 *>(Ss + m0);
@@ -171,12 +206,15 @@ constexpr int kFwDelay   = 5440;                    // fm-rate samples
 
 __constant__ float c_wide [kDecim][kFwGroups + 3];  // c_wide[p][g] = C'ws[12 g + 11 - p]
 
+template <bool LO>
 __global__ void __launch_bounds__ (kFeThreads, 3)
 frontend_wide_kernel (const float2 *__restrict__ x, int64_t in_pitch,
                       const float2 *__restrict__ hist,
                       float2 *__restrict__ U, float2 *__restrict__ S,
-                      int64_t out_pitch, int32_t M) {
+                      int64_t out_pitch, int32_t M, const LoParams lop) {
 extern __shared__ float2 sm [];
+__shared__ float2 sRaw [LO ? kFeTileOut : 1];
+	if (LO) { for (int i = threadIdx.x; i < kFeTileOut; i += kFeThreads) sRaw [i] = make_float2 (0.f, 0.f); __syncthreads (); }
 const int tid    = threadIdx.x;
 const int stream = blockIdx.y;
 const int64_t out0 = (int64_t)blockIdx.x * kFeTileOut;
@@ -190,8 +228,10 @@ constexpr int kHaloIn = kFwHalo * kFeRows;           // 288 samples before the t
 	   float2 v;
 	   if (blockIdx.x == 0) v = hist [(int64_t)stream * kFwHist + (kFwHist - kHaloIn) + i];
 	   else                 v = xs [in0 - kHaloIn + i];
+	   if (LO) v = lo_apply (lop, v, lo_index (lop, in0 - kHaloIn + i));
 	   sm [(i % kFeRows) * kFwPitch + i / kFeRows] = v;
 	}
+int32_t loIdx = LO ? lo_index (lop, in0 + tid) : 0;
 #pragma unroll
 	for (int b = 0; b < 3; b ++) {
 	   float2 v [16];
@@ -200,6 +240,12 @@ constexpr int kHaloIn = kFwHalo * kFeRows;           // 288 samples before the t
 	      const int j = (b * 16 + k) * kFeThreads + tid;
 	      const int64_t n = in0 + j;
 	      v [k] = (n < N) ? __ldcs (xs + n) : make_float2 (0.f, 0.f);
+	      if (LO) {
+	         // the RF DC estimate follows the RAW samples: block sums before gain and rotation
+	         atomicAdd (&sRaw [j / kDecim].x, v [k].x); atomicAdd (&sRaw [j / kDecim].y, v [k].y);
+	         v [k] = lo_apply (lop, v [k], loIdx);
+	         loIdx -= lop.step128; if (loIdx < 0) loIdx += lop.rate;
+	      }
 	   }
 #pragma unroll
 	   for (int k = 0; k < 16; k ++) {
@@ -246,7 +292,7 @@ float2 *Us = U + (int64_t)stream * out_pitch;
 float2 *Ss = S + (int64_t)stream * out_pitch;
 #pragma unroll
 	for (int k = 0; k < kFeGpt; k ++)
-	   if (m0 + k < M) { Us [m0 + k] = acc [k]; Ss [m0 + k] = dcs [k]; }
+	   if (m0 + k < M) { Us [m0 + k] = acc [k]; Ss [m0 + k] = LO ? sRaw [tid * kFeGpt + k] : dcs [k]; }
 }
 
 // fm-rate delay line: out[m] = (hist | in)[m], new_hist = the last D entries of (hist | in)

@@ -64,6 +64,10 @@ struct sdrjfm_handle {
 	float2 *d_Uw = nullptr, *d_Sw = nullptr;
 	float2 *d_udel [2] = { nullptr, nullptr }, *d_sdel [2] = { nullptr, nullptr }; int del_sel = 0;
 	float   wide_sumC = 0, wide_sumCm = 0;
+	// local oscillator (table built when lo first becomes non-zero)
+	float2 *d_lo_tab = nullptr;
+	int64_t lo_phase = 0;                   // Oscillator::LOPhase after the last processed sample
+	float   lo_Hre = 1.f, lo_Him = 0.f;     // H (lo) of the active composite taps
 	// audio low-pass (allocated when first switched on)
 	float2 *d_alp_hist [2] = { nullptr, nullptr }; int alp_sel = 0;
 	float2 *d_lrf = nullptr;
@@ -123,6 +127,25 @@ const TableHeader &th = h -> tables.hdr ();
 	                cudaMemcpyHostToDevice));
 float comp [40] = { 0 };
 	memcpy (comp, h -> tables.payload () + th.off_comp, th.ncomp * sizeof (float));
+const int32_t lo_hz = h -> set.lo_hz;
+	h -> lo_Hre = 1.f; h -> lo_Him = 0.f;
+	if (lo_hz != 0) {
+//	With the oscillator on, the DC folding of tables.cpp does not apply (the subtracted DC is rotated
+//	sample by sample): run the plain composite C[d1 j + i] = t2[j] t1[i] and take the DC term out at the
+//	fm rate through H (lo) = sum_t C[t] exp (+2 pi i lo t / inputRate)  (discriminator.cuh).
+	   const cf32 *k1 = reinterpret_cast<const cf32 *>(h -> tables.payload () + th.off_fmband1);
+	   const cf32 *k2 = reinterpret_cast<const cf32 *>(h -> tables.payload () + th.off_fmband2);
+	   std::vector<double> cd (th.ncomp, 0.0);
+	   for (int j = 0; j < th.ntaps2; j ++)
+	      for (int i = 0; i < th.ntaps1; i ++)
+	         cd [th.decim1 * j + i] += (double)k2 [j].imag () * (double)k1 [i].imag ();
+	   std::complex<double> H (0, 0);
+	   for (int t = 0; t < th.ncomp; t ++) {
+	      comp [t] = (float)cd [t];
+	      H += (double)comp [t] * std::polar (1.0, 2 * M_PI * (double)lo_hz * t / th.input_rate);
+	   }
+	   h -> lo_Hre = (float)H.real (); h -> lo_Him = (float)H.imag ();
+	}
 	CK (cudaMemcpyToSymbol (c_comp, comp, sizeof comp));
 
 //	audio decimator taps (our own design, audio_out.cuh): Blackman-windowed sinc, fc = 20 kHz
@@ -150,7 +173,7 @@ float comp [40] = { 0 };
 	   for (int t = 0; t < th.ncomp_wide && t + 5 < kFwHist; t ++) cw [t + 5] = (double)wide [t];
 	   for (int i = 0; i < kFwHist; i ++)
 	      for (int k = i + 1; k < kFwHist; k ++) g [i] += cw [k];
-	   const double alpha = (double)(1.0f / th.input_rate);
+	   const double alpha = lo_hz != 0 ? 0.0 : (double)(1.0f / th.input_rate);
 	   float cwide [kDecim][kFwGroups + 3];
 	   memset (cwide, 0, sizeof cwide);
 	   double sC = 0, sCm = 0;
@@ -160,6 +183,12 @@ float comp [40] = { 0 };
 	      cwide [11 - i % kDecim][i / kDecim] = f;
 	   }
 	   h -> wide_sumC = (float)sC; h -> wide_sumCm = (float)sCm;
+	   if (lo_hz != 0) {
+	      std::complex<double> H (0, 0);
+	      for (int t = 0; t < kFwHist; t ++)
+	         H += (double)(float)cw [t] * std::polar (1.0, 2 * M_PI * (double)lo_hz * t / th.input_rate);
+	      h -> lo_Hre = (float)H.real (); h -> lo_Him = (float)H.imag ();
+	   }
 	   CK (cudaMemcpyToSymbol (c_wide, cwide, sizeof cwide));
 	}
 
@@ -340,7 +369,9 @@ cudaError_t e;
 	   if ((e = cudaMemcpy (h -> d_state, st.data (), S * sizeof (StreamState),
 	                        cudaMemcpyHostToDevice)) != cudaSuccess) return fail (e, "state upload");
 	}
-	if ((e = cudaFuncSetAttribute (frontend_fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	if ((e = cudaFuncSetAttribute (frontend_fir_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                               kFeSmemBytes)) != cudaSuccess ||
+	    (e = cudaFuncSetAttribute (frontend_fir_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                               kFeSmemBytes)) != cudaSuccess) return fail (e, "smem attr K1");
 	if ((e = cudaFuncSetAttribute (sequential_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                               (cfg -> fm_rate / 4 + 1) * (int)sizeof (float))) != cudaSuccess ||
@@ -368,7 +399,7 @@ void *ptrs [] = { h -> d_tables, h -> d_sin_quarter, h -> d_in, h -> d_hist [0],
 	              h -> d_rds_dring, h -> d_rds_pring, h -> d_rds_bp, h -> d_rds_hi, h -> d_rds_R, h -> d_rds_tw,
 	              h -> d_rds_dtaps, h -> d_rds_hist [0], h -> d_rds_hist [1],
 	              h -> d_histw [0], h -> d_histw [1], h -> d_Uw, h -> d_Sw, h -> d_udel [0], h -> d_udel [1],
-	              h -> d_sdel [0], h -> d_sdel [1], h -> d_alp_hist [0], h -> d_alp_hist [1], h -> d_lrf };
+	              h -> d_sdel [0], h -> d_sdel [1], h -> d_alp_hist [0], h -> d_alp_hist [1], h -> d_lrf, h -> d_lo_tab };
 	for (void *p : ptrs) if (p) cudaFree (p);
 	if (h -> stream) cudaStreamDestroy (h -> stream);
 	delete h;
@@ -396,12 +427,27 @@ static int launch_frontend (sdrjfm_handle *h, const float2 *src, int64_t pitch, 
                             const float2 *hist) {
 const int S = h -> cfg.n_streams;
 dim3 grid ((unsigned)((M + kFeTileOut - 1) / kFeTileOut), (unsigned)S);
-	if (h -> set.input_filter_hz > 0)
-	   frontend_wide_kernel<<<grid, kFeThreads, kFwSmemBytes, h -> stream>>> (
-	         src, pitch, h -> d_histw [h -> histw_sel], h -> d_Uw, h -> d_Sw, h -> cap_fm, M);
-	else
-	   frontend_fir_kernel<<<grid, kFeThreads, kFeSmemBytes, h -> stream>>> (
-	         src, pitch, hist, h -> d_U, h -> d_S, h -> cap_fm, M);
+LoParams lp;
+	memset (&lp, 0, sizeof lp);
+const bool lo = h -> set.lo_hz != 0;
+	if (lo) {
+	   lp.tab = h -> d_lo_tab; lp.rate = h -> cfg.input_rate; lp.lo = h -> set.lo_hz;
+	   int64_t s128 = (128 * (int64_t)h -> set.lo_hz) % lp.rate; if (s128 < 0) s128 += lp.rate;
+	   lp.step128 = (int32_t)s128; lp.phase = h -> lo_phase;
+	   lp.lgain = h -> set.lgain; lp.rgain = h -> set.rgain;
+	}
+	if (h -> set.input_filter_hz > 0) {
+	   if (lo) frontend_wide_kernel<true><<<grid, kFeThreads, kFwSmemBytes, h -> stream>>> (
+	         src, pitch, h -> d_histw [h -> histw_sel], h -> d_Uw, h -> d_Sw, h -> cap_fm, M, lp);
+	   else    frontend_wide_kernel<false><<<grid, kFeThreads, kFwSmemBytes, h -> stream>>> (
+	         src, pitch, h -> d_histw [h -> histw_sel], h -> d_Uw, h -> d_Sw, h -> cap_fm, M, lp);
+	}
+	else {
+	   if (lo) frontend_fir_kernel<true><<<grid, kFeThreads, kFeSmemBytes, h -> stream>>> (
+	         src, pitch, hist, h -> d_U, h -> d_S, h -> cap_fm, M, lp);
+	   else    frontend_fir_kernel<false><<<grid, kFeThreads, kFeSmemBytes, h -> stream>>> (
+	         src, pitch, hist, h -> d_U, h -> d_S, h -> cap_fm, M, lp);
+	}
 	h -> launches ++;
 	CK (cudaGetLastError ());
 	return SDRJFM_OK;
@@ -416,7 +462,8 @@ const int64_t S = h -> cfg.n_streams;
 	   for (int i = 0; i < 2; i ++) {
 	      CK (dalloc (&h -> d_udel [i], (size_t)S * kFwDelay)); CK (dalloc (&h -> d_sdel [i], (size_t)S * kFwDelay));
 	   }
-	   CK (cudaFuncSetAttribute (frontend_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwSmemBytes));
+	   CK (cudaFuncSetAttribute (frontend_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwSmemBytes));
+	   CK (cudaFuncSetAttribute (frontend_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwSmemBytes));
 	}
 	else {
 	   for (int i = 0; i < 2; i ++) {
@@ -477,6 +524,13 @@ DiscrParams dp;
 	dp.sumC = consts [0]; dp.sumCm = consts [1];
 	dp.gb0 = consts [5]; dp.gb1 = consts [6]; dp.gb2 = consts [7];
 	if (wide) { dp.sumC = h -> wide_sumC; dp.sumCm = h -> wide_sumCm; dp.gb0 = dp.gb1 = dp.gb2 = 0.f; }
+	dp.lo_tab = nullptr; dp.lo_rate = h -> cfg.input_rate; dp.lo_hz = st.lo_hz; dp.lo_moff = wide ? -kFwDelay : 0;
+	dp.lo_phase = h -> lo_phase; dp.Hre = h -> lo_Hre; dp.Him = h -> lo_Him;
+	if (st.lo_hz != 0) {
+	   dp.lo_tab = h -> d_lo_tab;
+	   int64_t np = (h -> lo_phase - (int64_t)st.lo_hz * n_proc) % h -> cfg.input_rate;
+	   h -> lo_phase = np < 0 ? np + h -> cfg.input_rate : np;       // LOPhase after this call's samples
+	}
 	dp.Gre = consts [2]; dp.Gim = consts [3];
 	dp.alpha = (double)(1.0f / h -> cfg.input_rate);          // rfDcAlpha, fm-processor.cpp:379
 	dp.beta = pow (1.0 - dp.alpha, (double)kDecim);
@@ -817,8 +871,22 @@ int sdrjfm_set_rds_mode (sdrjfm_handle *h, int32_t m) {
 }
 int sdrjfm_set_local_oscillator (sdrjfm_handle *h, int32_t hz) {
 	if (!h) return SDRJFM_ERR_ARG;
-	if (hz != 0) { h -> err = "LO offset is not on the GPU path yet"; return SDRJFM_ERR_UNSUPPORTED; }
-	h -> set.lo_hz = hz; return SDRJFM_OK;
+//	set_localOscillator (:865-867).  The oscillator table (inputRate complex entries, oscillator.cpp:26-37)
+//	is built the first time lo is non-zero.
+	if (hz <= -h -> cfg.input_rate || hz >= h -> cfg.input_rate) return SDRJFM_ERR_ARG;
+	CK (cudaSetDevice (h -> cfg.device));
+	if (hz != 0 && !h -> d_lo_tab) {
+	   const int32_t R = h -> cfg.input_rate;
+	   std::vector<float2> t (R);
+	   for (int32_t i = 0; i < R; i ++)
+	      t [i] = make_float2 ((float)cos (2.0 * M_PI * i / R), (float)sin (2.0 * M_PI * i / R));
+	   CK (cudaMalloc ((void **)&h -> d_lo_tab, (size_t)R * sizeof (float2)));
+	   CK (cudaMemcpy (h -> d_lo_tab, t.data (), (size_t)R * sizeof (float2), cudaMemcpyHostToDevice));
+	}
+	if (hz == h -> set.lo_hz) return SDRJFM_OK;
+	h -> set.lo_hz = hz;
+	CK (cudaStreamSynchronize (h -> stream));
+	return upload_tables (h);        // taps with / without the DC folding, H (lo)
 }
 int sdrjfm_set_squelch_mode (sdrjfm_handle *h, int32_t m) {
 	if (!h) return SDRJFM_ERR_ARG;

@@ -287,3 +287,30 @@ def test_audio_lowpass_matches_reference(pkg, signals, checker, chunks):
     print("audio192 rms err with audio low-pass", e)
     assert e < 1e-5
     assert np.all(np.abs(got["audio192"][0][:7436]) < 1e-12)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(fm_mode=0, lo_hz=30000, volume_db=0.0),
+    dict(fm_mode=0, lo_hz=-47000, lgain=0.9, rgain=1.05, volume_db=0.0),
+    dict(fm_mode=0, lo_hz=30000, input_filter_hz=165000, volume_db=0.0),
+    dict(fm_mode=0, lo_hz=30000, dc_remove=0, volume_db=0.0),
+])
+def test_local_oscillator_and_iq_gain_match_reference(pkg, signals, checker, cfg):
+    """set_localOscillator / setAttenuation: per-sample IQ gain and LO mix in front of the
+    filters (fm-processor.cpp:462-466), with the RF DC remover ahead of them."""
+    n = N1
+    t = np.arange(n) / 2304000.0
+    x = signals.stereo_pilot(n) * np.exp(2j * np.pi * cfg["lo_hz"] * t)     # station offset by +lo
+    x = signals.dc_offset(x.astype(np.complex64))
+    ref = checker(**cfg).process(x)
+    got = run_gpu(pkg, x, chunks=[N1 // 3 + 7, 16384, n], **cfg)
+    e = rms(got["fm_z"][0] - ref["fm_z"]) / rms(ref["fm_z"])
+    print(cfg, "fm_z rel", e, "demod", rms(got["demod"][0] - ref["demod"]),
+          "audio192", rms(got["audio192"][0] - ref["audio192"]))
+    # With the oscillator on, the DC folding of the narrow path does not apply (DESIGN.md §3): the
+    # first-order drift of the DC estimate inside the tap window shows at the IF / demod taps
+    # (exact to 1e-7 with dc_remove=0).  The audio contract (1e-5 RMS) holds regardless.
+    tol = 2e-7 if not cfg.get("dc_remove", 1) else 2e-5
+    assert e < tol
+    assert rms(got["demod"][0] - ref["demod"]) < 2e-5
+    assert rms(got["audio192"][0] - ref["audio192"]) < 1e-5
