@@ -216,7 +216,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     S = args.streams
-    proc = pkg.FmProcessorB200(n_streams=S, max_samples_per_call=n, device=local)
+    proc = pkg.FmProcessorB200(n_streams=S, max_samples_per_call=n, device=local, keep_taps=False)
     proc.configure(**settings)
     # shared tap/LUT blob: rank 0 designs, everyone imports what rank 0 broadcast (NCCL)
     if world > 1:

@@ -42,6 +42,9 @@ struct sdrjfm_handle {
 	TableBlob     tables;
 	float        *d_tables = nullptr;
 	cudaStream_t  stream = nullptr;
+	cudaStream_t  copy_stream = nullptr;    // H2D of the next time slice while the current one computes
+	cudaEvent_t   ev_h2d [2] = { nullptr, nullptr }, ev_done [2] = { nullptr, nullptr };
+	float2 *d_in2 = nullptr;                // second staging buffer (allocated on first pipelined call)
 	int           n_sm = 0;
 	bool          smem_lut_ok = false;
 	SinLut        lut;
@@ -401,6 +404,9 @@ void *ptrs [] = { h -> d_tables, h -> d_sin_quarter, h -> d_in, h -> d_hist [0],
 	              h -> d_histw [0], h -> d_histw [1], h -> d_Uw, h -> d_Sw, h -> d_udel [0], h -> d_udel [1],
 	              h -> d_sdel [0], h -> d_sdel [1], h -> d_alp_hist [0], h -> d_alp_hist [1], h -> d_lrf, h -> d_lo_tab };
 	for (void *p : ptrs) if (p) cudaFree (p);
+	if (h -> d_in2) cudaFree (h -> d_in2);
+	for (int i = 0; i < 2; i ++) { if (h -> ev_h2d [i]) cudaEventDestroy (h -> ev_h2d [i]); if (h -> ev_done [i]) cudaEventDestroy (h -> ev_done [i]); }
+	if (h -> copy_stream) cudaStreamDestroy (h -> copy_stream);
 	if (h -> stream) cudaStreamDestroy (h -> stream);
 	delete h;
 	return SDRJFM_OK;
@@ -709,12 +715,58 @@ int sdrjfm_process (sdrjfm_handle *h, const float *iq, int64_t n_in, int64_t in_
 	if (n_in > h -> cfg.max_samples_per_call) { h -> err = "n_in exceeds max_samples_per_call"; return SDRJFM_ERR_CAPACITY; }
 	CK (cudaSetDevice (h -> cfg.device));
 const int S = h -> cfg.n_streams;
-const float2 *src; int64_t pitch, n_proc;
-int rc = stage_input (h, iq, n_in, in_pitch, cudaMemcpyHostToDevice, &src, &pitch, &n_proc);
-	if (rc != SDRJFM_OK) return rc;
+int rc;
 int64_t na = 0, nr = 0;
-	rc = run_chain (h, src, pitch, n_proc, nullptr, 0, &na, nullptr, 0, &nr);
-	if (rc != SDRJFM_OK) return rc;
+//	Large offline calls (no tap read-back wanted): the call is cut into time slices and the
+//	host->device copy of slice c+1 runs on a second stream while slice c computes.  The chain is
+//	stateful, so this is exactly the sequence of smaller calls the GUI cadence would make.
+const int64_t kSlices = 8;
+const int64_t slice = ((n_in / kSlices) / 3072) * 3072;          // multiple of 12 * 256
+	if (!h -> cfg.keep_taps && h -> pend == 0 && slice >= (1 << 16)) {
+	   if (!h -> copy_stream) {
+	      CK (cudaStreamCreateWithFlags (&h -> copy_stream, cudaStreamNonBlocking));
+	      for (int i = 0; i < 2; i ++) {
+	         CK (cudaEventCreateWithFlags (&h -> ev_h2d [i], cudaEventDisableTiming));
+	         CK (cudaEventCreateWithFlags (&h -> ev_done [i], cudaEventDisableTiming));
+	      }
+	      CK (cudaMalloc ((void **)&h -> d_in2, (size_t)S * h -> cap_in * sizeof (float2)));
+	   }
+	   float2 *buf [2] = { h -> d_in, h -> d_in2 };
+	   int64_t pos = 0; int c = 0;
+	   while (pos < n_in) {
+	      const int64_t rest = n_in - pos;
+	      const bool last = rest < 2 * slice;                      // the last slice takes the ragged tail
+	      const int64_t len = last ? rest : slice;
+	      const int b = c & 1;
+	      if (c >= 2) CK (cudaStreamWaitEvent (h -> copy_stream, h -> ev_done [b], 0));
+	      CK (cudaMemcpy2DAsync (buf [b], h -> cap_in * sizeof (float2), (const float2 *)iq + pos,
+	                             in_pitch * sizeof (float2), len * sizeof (float2), S,
+	                             cudaMemcpyHostToDevice, h -> copy_stream));
+	      CK (cudaEventRecord (h -> ev_h2d [b], h -> copy_stream));
+	      CK (cudaStreamWaitEvent (h -> stream, h -> ev_h2d [b], 0));
+	      const int64_t n_proc = (len / kDecim) * kDecim;
+	      const int newpend = (int)(len - n_proc);                 // only possible in the last slice
+	      if (newpend)
+	         CK (cudaMemcpy2DAsync (h -> d_pend, kDecim * sizeof (float2), buf [b] + n_proc,
+	                                h -> cap_in * sizeof (float2), newpend * sizeof (float2), S,
+	                                cudaMemcpyDeviceToDevice, h -> stream));
+	      h -> pend = newpend;
+	      int64_t a1 = 0, r1 = 0;
+	      rc = run_chain (h, buf [b], h -> cap_in, n_proc, h -> d_audio + na, h -> cap_audio, &a1,
+	                      h -> d_rds24 + nr, h -> cap_rds, &r1);
+	      if (rc != SDRJFM_OK) return rc;
+	      CK (cudaEventRecord (h -> ev_done [b], h -> stream));
+	      na += a1; nr += r1; pos += len; c ++;
+	   }
+	   h -> last_naudio = na; h -> last_nrds = nr;
+	}
+	else {
+	   const float2 *src; int64_t pitch, n_proc;
+	   rc = stage_input (h, iq, n_in, in_pitch, cudaMemcpyHostToDevice, &src, &pitch, &n_proc);
+	   if (rc != SDRJFM_OK) return rc;
+	   rc = run_chain (h, src, pitch, n_proc, nullptr, 0, &na, nullptr, 0, &nr);
+	   if (rc != SDRJFM_OK) return rc;
+	}
 	if (audio && na > 0) {
 	   if (audio_pitch < na) return SDRJFM_ERR_ARG;
 	   CK (cudaMemcpy2DAsync (audio, audio_pitch * sizeof (float2), h -> d_audio,
