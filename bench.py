@@ -220,9 +220,8 @@ def main():
     proc.configure(**settings)
     # shared tap/LUT blob: rank 0 designs, everyone imports what rank 0 broadcast (NCCL)
     if world > 1:
-        blob = torch.from_numpy(proc.tables_export()).to(dev)
-        dist.broadcast(blob, src=0)
-        proc.tables_import(blob.cpu().numpy())
+        sh = importlib.import_module("sdrjfm_b200.sharding")
+        proc.tables_import(sh.broadcast_tables(proc.tables_export() if rank == 0 else None, dist, device=dev))
 
     x = gen_batch_gpu(torch, dev, S, n, stream0=rank * S)
     torch.cuda.synchronize()
@@ -271,8 +270,15 @@ def main():
     fe_ms = timed(lambda: proc.run_frontend_only(x.data_ptr(), n, x.stride(0)), fe_steps) / fe_steps
     peak, peak_kind = peak_hbm()
     achieved = ALGO_BYTES_PER_SAMPLE * S * n / (fe_ms * 1e-3) / 1e9
+    traffic = None      # dram bytes per launch from the committed ncu --set full capture of this workload
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_frontend_traffic.json")))
+        if tr["streams"] == S and tr["samples_per_stream"] == n:
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "frontend_fir_kernel", "achieved": achieved, "peak": peak,
-                "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel_ms": fe_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SAMPLE * S * n}
 
     # end to end through the host-buffer C-ABI call
