@@ -117,18 +117,21 @@ float f = (float)v;
 	return f < 0.f ? 0.f : f;
 }
 
-__global__ void __launch_bounds__ (kPiThreads, 1)
+template <bool LUT_SMEM>
+__global__ void __launch_bounds__ (kPiThreads, LUT_SMEM ? 1 : 2)
 pilot_kernel (const float *__restrict__ res_raw, const float *__restrict__ zabs,
               int64_t pitch, int32_t M, const PilotParams P, const SinLut L,
               StreamState *__restrict__ state,
               float *__restrict__ demod_out, float *__restrict__ phase_out,
               uint8_t *__restrict__ locked_out, int32_t *__restrict__ iter_stats) {
 extern __shared__ __align__ (16) unsigned char smem_raw [];
-float *sq = reinterpret_cast<float *>(smem_raw);
-PilotSmem &S = *reinterpret_cast<PilotSmem *>(smem_raw + kPiLutBytes);
+// LUT_SMEM: the quarter-wave sine table is staged in shared memory (one CTA per SM).  Otherwise it is
+// read through L1 (192 KB, read-only path), which leaves room for two CTAs per SM.
+const float *sq = LUT_SMEM ? reinterpret_cast<const float *>(smem_raw) : L.q;
+PilotSmem &S = *reinterpret_cast<PilotSmem *>(smem_raw + (LUT_SMEM ? kPiLutBytes : 0));
 const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 const int stream = blockIdx.x;
-	for (int i = tid; i <= kFmRate / 4; i += kPiThreads) sq [i] = L.q [i];
+	if (LUT_SMEM) { float *w = reinterpret_cast<float *>(smem_raw); for (int i = tid; i <= kFmRate / 4; i += kPiThreads) w [i] = L.q [i]; }
 StreamState &st = state [stream];
 const float *rr = res_raw + (int64_t)stream * pitch;
 const float *za = zabs + (int64_t)stream * pitch;

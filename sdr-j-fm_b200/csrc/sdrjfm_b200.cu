@@ -82,6 +82,7 @@ struct sdrjfm_handle {
 	int64_t  rds_total = 0, rds_last_block = -1;
 	float2  *d_pss_ring = nullptr;          // [S][2048] PSS filter input ring (state)
 	int32_t *d_iter_stats = nullptr;        // pilot_kernel diagnostics: [S][4]
+	bool    pilot_lut_smem = false;         // SDRJFM_PILOT_LUT_SMEM=1: sine table in shared memory, 1 CTA/SM
 	bool    sequential_pll = false;         // SDRJFM_SEQUENTIAL_PLL=1: lane-per-stream K3 (cross-check)
 	int64_t fm_total = 0;                   // fm-rate samples produced so far (per stream)
 	int32_t fade_cnt = 0, fade_max = 0;     // suppressAudioSampleCnt(Max), fm-processor.cpp:130-131
@@ -381,8 +382,13 @@ cudaError_t e;
 	    (e = cudaFuncSetAttribute (sequential_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                               (cfg -> fm_rate / 4 + 1) * (int)sizeof (float))) != cudaSuccess)
 	   return fail (e, "smem attr K3");
-	if ((e = cudaFuncSetAttribute (pilot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                               (int)kPiSmemBytes)) != cudaSuccess) return fail (e, "smem attr pilot");
+	if ((e = cudaFuncSetAttribute (pilot_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                               (int)kPiSmemBytes)) != cudaSuccess ||
+	    (e = cudaFuncSetAttribute (pilot_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                               (int)sizeof (PilotSmem))) != cudaSuccess ||
+	    (e = cudaFuncSetAttribute (pilot_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+	                               25)) != cudaSuccess) return fail (e, "smem attr pilot");
+	{ const char *env = getenv ("SDRJFM_PILOT_LUT_SMEM"); h -> pilot_lut_smem = env && env [0] == '1'; }
 	{ const char *env = getenv ("SDRJFM_SEQUENTIAL_PLL"); h -> sequential_pll = env && env [0] == '1'; }
 int rc = rebuild_tables (h);
 	if (rc != SDRJFM_OK) { g_create_error = h -> err; *status = rc; sdrjfm_destroy (h); return nullptr; }
@@ -576,9 +582,14 @@ const size_t seq_smem = (h -> lut.quarter + 1) * sizeof (float);
 	   PilotParams pp;
 	   pp.K_FM = sp.K_FM; pp.omega = sp.omega; pp.gain = sp.gain;
 	   pp.lock_half_rate = sp.lock_half_rate; pp.n_streams = S;
-	   pilot_kernel<<<S, kPiThreads, kPiSmemBytes, h -> stream>>> (
-	         h -> d_res, h -> d_zabs, h -> cap_fm, M, pp, h -> lut, h -> d_state,
-	         h -> d_demod, h -> d_phase, h -> d_locked, h -> d_iter_stats);
+	   if (h -> pilot_lut_smem)
+	      pilot_kernel<true><<<S, kPiThreads, kPiSmemBytes, h -> stream>>> (
+	            h -> d_res, h -> d_zabs, h -> cap_fm, M, pp, h -> lut, h -> d_state,
+	            h -> d_demod, h -> d_phase, h -> d_locked, h -> d_iter_stats);
+	   else
+	      pilot_kernel<false><<<S, kPiThreads, sizeof (PilotSmem), h -> stream>>> (
+	            h -> d_res, h -> d_zabs, h -> cap_fm, M, pp, h -> lut, h -> d_state,
+	            h -> d_demod, h -> d_phase, h -> d_locked, h -> d_iter_stats);
 	}
 	h -> launches ++;
 //	K4 ------------------------------------------------------------------------------------

@@ -199,20 +199,39 @@ float2 *ring = ring_g + (int64_t)stream * kPssRing;
 #pragma unroll
 	      for (int k = 0; k < kStPer; k ++) acc [k] = make_float2 (0.f, 0.f);
 	      if (m0 < len) {
-	         const int base = pos + m0 - kPssDelay + 2 * kPssRing;      // slot of u[.] for k = 0, j = 0
-	         float2 w [kStPer];
+//	      element i of the window = u[block start + m0 + i - 1753]; at tap j output k reads element k - j.
+//	      Elements live in register slot (i mod 6), so with the tap loop unrolled by 6 every slot is static.
+	         const int base = pos + m0 - kPssDelay + 2 * kPssRing;      // ring slot of element 0
+	         float2 v [kStPer];
 #pragma unroll
-	         for (int k = 0; k < kStPer; k ++) w [k] = sRing [(base + k) & (kPssRing - 1)];
-	         for (int j = 0; j < kPssTaps; j ++) {
-	            const float c = c_pss_taps [j];
+	         for (int k = 0; k < kStPer; k ++) v [k] = sRing [(base + k) & (kPssRing - 1)];
+	         int nxt = base - 1;                                          // ring slot of element -j-1
+#pragma unroll 1
+	         for (int j0 = 0; j0 + kStPer <= kPssTaps; j0 += kStPer) {
+#pragma unroll
+	            for (int u = 0; u < kStPer; u ++) {
+	               const float c = c_pss_taps [j0 + u];
+#pragma unroll
+	               for (int k = 0; k < kStPer; k ++) {
+	                  const float2 w = v [(k - u + kStPer) % kStPer];
+	                  acc [k].x = fmaf (c, w.x, acc [k].x);
+	                  acc [k].y = fmaf (c, w.y, acc [k].y);
+	               }
+	               v [(kStPer - 1 - u) % kStPer] = sRing [nxt & (kPssRing - 1)];
+	               nxt --;
+	            }
+	         }
+#pragma unroll
+	         for (int u = 0; u < kPssTaps % kStPer; u ++) {               // remaining taps (295 = 49 * 6 + 1)
+	            const float c = c_pss_taps [(kPssTaps / kStPer) * kStPer + u];
 #pragma unroll
 	            for (int k = 0; k < kStPer; k ++) {
-	               acc [k].x = fmaf (c, w [k].x, acc [k].x);
-	               acc [k].y = fmaf (c, w [k].y, acc [k].y);
+	               const float2 w = v [(k - u + kStPer) % kStPer];
+	               acc [k].x = fmaf (c, w.x, acc [k].x);
+	               acc [k].y = fmaf (c, w.y, acc [k].y);
 	            }
-#pragma unroll
-	            for (int k = kStPer - 1; k > 0; k --) w [k] = w [k - 1];
-	            w [0] = sRing [(base - j - 1) & (kPssRing - 1)];
+	            v [(kStPer - 1 - u) % kStPer] = sRing [nxt & (kPssRing - 1)];
+	            nxt --;
 	         }
 	      }
 #pragma unroll
