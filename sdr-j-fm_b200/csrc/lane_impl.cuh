@@ -1,0 +1,932 @@
+// Launch sequencing of the B200 FM path for one lane of streams (included by sdrjfm_b200.cu).
+//
+// Per process call and per batch of streams the sequence mirrors the order of
+// fmProcessor::run's per-sample loop (src/fm/fm-processor.cpp:461-648):
+//   K1 frontend_fir_kernel     DC sums + 37-tap /12 polyphase FIR      (:423-446,:462-475)
+//   K2 discriminator_kernel    DC subtract, gains, normalise, atan     (:497 -> fm-demodulator.cpp:111-195)
+//   K3 sequential_kernel       AFC/level one-poles, pilot PLL, lock    (fm-demodulator.cpp:197-198, pilot-recover.cpp)
+//   K4 stereo / mono matrix    PSS + 38 kHz demod + L/R selector       (:689-730,:517-549)
+//   K5 RDS branch              band-pass, Hilbert, x3 pilot mix, /8    (:733-758,:551-553)
+//   K6 de-emphasis, gain, 192->48 kHz, fade-in                        (:594-595,:630-642)
+// There is NO CPU fallback: without a CUDA device sdrjfm_create fails with
+// SDRJFM_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <cstdlib>
+#include <cstddef>
+#include <algorithm>
+#include <complex>
+#include <string>
+#include <vector>
+
+#include "../../include/sdrjfm_b200.h"
+#include "tables.hpp"
+#include "common.cuh"
+#include "frontend_fir.cuh"
+#include "discriminator.cuh"
+#include "sequential.cuh"
+#include "pilot.cuh"
+#include "stereo.cuh"
+#include "rds.cuh"
+#include "audio_out.cuh"
+
+// One LANE = the complete launch sequence and state for a group of IQ streams on its own CUDA
+// stream.  The C ABI (sdrjfm_b200.cu) splits a handle's streams over a few lanes so that the
+// latency-bound per-stream kernels of one lane overlap the kernels of the others.
+#pragma once
+using namespace sdrjfm;
+
+static thread_local std::string g_create_error;
+struct Lane;
+static int lane_destroy (Lane *h);
+static int lane_restart_pss_analyzer (Lane *h);
+static int lane_get_meta (Lane *h, sdrjfm_meta *meta);
+
+
+struct Lane {
+	sdrjfm_config cfg;
+	Settings      set;
+	TableBlob     tables;
+	float        *d_tables = nullptr;
+	cudaStream_t  stream = nullptr;
+	int           n_sm = 0;
+	bool          smem_lut_ok = false;
+	SinLut        lut;
+	float        *d_sin_quarter = nullptr;
+
+	int64_t cap_in = 0, cap_fm = 0, cap_audio = 0, cap_rds = 0;   // per-stream capacities (pitches)
+	float2 *d_in = nullptr;                 // staging [S][cap_in]
+	float2 *d_hist [2] = { nullptr, nullptr }; int hist_sel = 0;
+	float2 *d_pend = nullptr; int pend = 0; // leftover raw samples (< 12 per stream)
+	float2 *d_U = nullptr, *d_S = nullptr, *d_iqn = nullptr, *d_fmz = nullptr;
+	float  *d_res = nullptr, *d_zabs = nullptr, *d_demod = nullptr, *d_phase = nullptr;
+	float  *d_pssd = nullptr;
+	uint8_t *d_locked = nullptr;
+	float2 *d_lr = nullptr, *d_a192 = nullptr, *d_rdsc = nullptr, *d_rds24 = nullptr;
+	float2 *d_ahist [2] = { nullptr, nullptr }; int ahist_sel = 0;
+	float2 *d_audio = nullptr;              // [S][cap_audio] working-rate stereo
+	StreamState *d_state = nullptr;
+	// input filter ON (allocated when first switched on): wide front end + fm-rate delay lines
+	float2 *d_histw [2] = { nullptr, nullptr }; int histw_sel = 0;
+	float2 *d_Uw = nullptr, *d_Sw = nullptr;
+	float2 *d_udel [2] = { nullptr, nullptr }, *d_sdel [2] = { nullptr, nullptr }; int del_sel = 0;
+	float   wide_sumC = 0, wide_sumCm = 0;
+	// local oscillator (table built when lo first becomes non-zero)
+	float2 *d_lo_tab = nullptr;
+	int64_t lo_phase = 0;                   // Oscillator::LOPhase after the last processed sample
+	float   lo_Hre = 1.f, lo_Him = 0.f;     // H (lo) of the active composite taps
+	// audio low-pass (allocated when first switched on)
+	float2 *d_alp_hist [2] = { nullptr, nullptr }; int alp_sel = 0;
+	float2 *d_lrf = nullptr;
+	// RDS branch (allocated when RDS is first switched on)
+	float   *d_rds_dring = nullptr, *d_rds_pring = nullptr;     // [S][131072] demod / pilot phase by rds index
+	float   *d_rds_bp = nullptr, *d_rds_hi = nullptr;           // [S][2][32000] / [S][2][32768]
+	float2  *d_rds_R = nullptr, *d_rds_tw = nullptr, *d_rds_dtaps = nullptr;
+	float2  *d_rds_hist [2] = { nullptr, nullptr }; int rds_hist_sel = 0;
+	int64_t  rds_total = 0, rds_last_block = -1;
+	float2  *d_pss_ring = nullptr;          // [S][2048] PSS filter input ring (state)
+	int32_t *d_iter_stats = nullptr;        // pilot_kernel diagnostics: [S][4]
+	bool    pilot_lut_smem = false;         // SDRJFM_PILOT_LUT_SMEM=1: sine table in shared memory, 1 CTA/SM
+	bool    sequential_pll = false;         // SDRJFM_SEQUENTIAL_PLL=1: lane-per-stream K3 (cross-check)
+	int64_t fm_total = 0;                   // fm-rate samples produced so far (per stream)
+	int32_t fade_cnt = 0, fade_max = 0;     // suppressAudioSampleCnt(Max), fm-processor.cpp:130-131
+	int64_t last_nfm = 0, last_naudio = 0, last_nrds = 0;
+	int64_t launches = 0;
+	std::string err;
+};
+
+#define CK(call)                                                                          \
+	do { cudaError_t e_ = (call); if (e_ != cudaSuccess) {                                \
+	   char b_ [256]; snprintf (b_, sizeof b_, "%s failed: %s (%s:%d)", #call,           \
+	                           cudaGetErrorString (e_), __FILE__, __LINE__);              \
+	   h -> err = b_; return SDRJFM_ERR_CUDA; } } while (0)
+
+template <typename T> static cudaError_t dalloc (T **p, size_t n) {
+	cudaError_t e = cudaMalloc ((void **)p, n * sizeof (T));
+	if (e == cudaSuccess) e = cudaMemset (*p, 0, n * sizeof (T));
+	return e;
+}
+
+static void default_settings (Settings &s, int32_t fm_rate) {
+	memset (&s, 0, sizeof s);
+	s.fm_mode = 0;            // FM_Mode::Stereo, fm-processor.cpp:155
+	s.decoder = 3;            // MIXED, fm-demodulator.cpp:66
+	s.sound_sel = 0;          // S_STEREO, :156
+	s.rds_mode = 0;           // RDS_OFF, :133
+	s.auto_mono = 1; s.pss_on = 1; s.dc_remove = 1;     // :121,:122,:134
+	s.lgain = s.rgain = 1.0f; // :110-111
+	s.volume = 0.5f;          // :127
+	s.panorama = 1.0f;        // :128
+	s.left_ch = s.right_ch = 1.0f;                      // :157-158
+	s.deemph_us = 50;
+	{  // the constructor's own formula (:174) is always overwritten by setDeemphasis through
+	   // make_newProcessor (radio.cpp:940, default 50 us radio.cpp:2129); start from the latter
+	   float Tau = 1000000.0 / 50;
+	   s.deemph_alpha = 1.0 / (float (fm_rate) / Tau + 1.0);
+	}
+}
+
+// uploads constant-memory taps and derives the launch parameters that depend on the tables
+static int upload_tables (Lane *h) {
+const TableHeader &th = h -> tables.hdr ();
+	if (h -> d_tables) { cudaFree (h -> d_tables); h -> d_tables = nullptr; }
+	CK (cudaMalloc ((void **)&h -> d_tables, th.payload_floats * sizeof (float)));
+	CK (cudaMemcpy (h -> d_tables, h -> tables.payload (), th.payload_floats * sizeof (float),
+	                cudaMemcpyHostToDevice));
+float comp [40] = { 0 };
+	memcpy (comp, h -> tables.payload () + th.off_comp, th.ncomp * sizeof (float));
+const int32_t lo_hz = h -> set.lo_hz;
+	h -> lo_Hre = 1.f; h -> lo_Him = 0.f;
+	if (lo_hz != 0) {
+//	With the oscillator on, the DC folding of tables.cpp does not apply (the subtracted DC is rotated
+//	sample by sample): run the plain composite C[d1 j + i] = t2[j] t1[i] and take the DC term out at the
+//	fm rate through H (lo) = sum_t C[t] exp (+2 pi i lo t / inputRate)  (discriminator.cuh).
+	   const cf32 *k1 = reinterpret_cast<const cf32 *>(h -> tables.payload () + th.off_fmband1);
+	   const cf32 *k2 = reinterpret_cast<const cf32 *>(h -> tables.payload () + th.off_fmband2);
+	   std::vector<double> cd (th.ncomp, 0.0);
+	   for (int j = 0; j < th.ntaps2; j ++)
+	      for (int i = 0; i < th.ntaps1; i ++)
+	         cd [th.decim1 * j + i] += (double)k2 [j].imag () * (double)k1 [i].imag ();
+	   std::complex<double> H (0, 0);
+	   for (int t = 0; t < th.ncomp; t ++) {
+	      comp [t] = (float)cd [t];
+	      H += (double)comp [t] * std::polar (1.0, 2 * M_PI * (double)lo_hz * t / th.input_rate);
+	   }
+	   h -> lo_Hre = (float)H.real (); h -> lo_Him = (float)H.imag ();
+	}
+	CK (cudaMemcpyToSymbol (c_comp, comp, sizeof comp));
+
+//	audio decimator taps (our own design, audio_out.cuh): Blackman-windowed sinc, fc = 20 kHz
+	{
+	   float t [kRsTaps + 3] = { 0 };
+	   double sum = 0;
+	   std::vector<double> d (kRsTaps);
+	   const double fc = 20000.0 / th.fm_rate;
+	   for (int i = 0; i < kRsTaps; i ++) {
+	      const int k = i - kRsTaps / 2;
+	      const double s = k == 0 ? 2 * fc : sin (2 * M_PI * fc * k) / (M_PI * k);
+	      const double w = 0.42 - 0.5 * cos (2 * M_PI * i / (kRsTaps - 1))
+	                            + 0.08 * cos (4 * M_PI * i / (kRsTaps - 1));
+	      d [i] = s * w; sum += d [i];
+	   }
+	   for (int i = 0; i < kRsTaps; i ++) t [i] = (float)(d [i] / sum);
+	   CK (cudaMemcpyToSymbol (c_rs_taps, t, sizeof t));
+	}
+
+//	input filter ON: composite of the 251-tap low-pass and the decimator cascade, shifted by 5
+//	samples (frontend_fir.cuh), RF DC removal folded in exactly like the narrow taps (tables.cpp)
+	if (th.ncomp_wide > 0) {
+	   const float *wide = h -> tables.payload () + th.off_comp_wide;
+	   std::vector<double> cw (kFwHist, 0.0), g (kFwHist, 0.0);
+	   for (int t = 0; t < th.ncomp_wide && t + 5 < kFwHist; t ++) cw [t + 5] = (double)wide [t];
+	   for (int i = 0; i < kFwHist; i ++)
+	      for (int k = i + 1; k < kFwHist; k ++) g [i] += cw [k];
+	   const double alpha = lo_hz != 0 ? 0.0 : (double)(1.0f / th.input_rate);
+	   float cwide [kDecim][kFwGroups + 3];
+	   memset (cwide, 0, sizeof cwide);
+	   double sC = 0, sCm = 0;
+	   for (int i = 0; i < kFwHist; i ++) {
+	      const float f = (float)(cw [i] + alpha * g [i]);
+	      sC += cw [i]; sCm += f;
+	      cwide [11 - i % kDecim][i / kDecim] = f;
+	   }
+	   h -> wide_sumC = (float)sC; h -> wide_sumCm = (float)sCm;
+	   if (lo_hz != 0) {
+	      std::complex<double> H (0, 0);
+	      for (int t = 0; t < kFwHist; t ++)
+	         H += (double)(float)cw [t] * std::polar (1.0, 2 * M_PI * (double)lo_hz * t / th.input_rate);
+	      h -> lo_Hre = (float)H.real (); h -> lo_Him = (float)H.imag ();
+	   }
+	   CK (cudaMemcpyToSymbol (c_wide, cwide, sizeof cwide));
+	}
+
+//	PSS low-pass taps: lpFilter (2048, 295).setLowPass (15000, rate), stereo-separation.cpp:31-39
+	{
+	   std::vector<cf32> lp = design_lowpass (kPssTaps, 15000, th.fm_rate);
+	   float t [kPssTaps + 1] = { 0 };
+	   for (int i = 0; i < kPssTaps; i ++) t [i] = lp [i].real ();
+	   CK (cudaMemcpyToSymbol (c_pss_taps, t, sizeof t));
+	}
+
+//	quarter-wave sine table + exception list (see sequential.cuh)
+const cf32 *sc = reinterpret_cast<const cf32 *>(h -> tables.payload () + th.off_sincos);
+const int32_t R = th.fm_rate, Q = R / 4;
+SinLut &L = h -> lut;
+	memset (&L, 0, sizeof L);
+	L.rate = R; L.quarter = Q; L.C = R / (2 * M_PI);
+	for (int e = 0; e < kMaxSinExc; e ++) L.sin_exc_idx [e] = L.cos_exc_idx [e] = -1;
+	h -> smem_lut_ok = (R % 4 == 0);
+	if (h -> smem_lut_ok) {
+	   std::vector<float> q (Q + 1);
+	   for (int i = 0; i <= Q; i ++) q [i] = sc [i].imag ();
+	   auto refl = [&](int idx) -> float {
+	      if (idx <= Q) return q [idx];
+	      if (idx <= 2 * Q) return q [2 * Q - idx];
+	      if (idx <= 3 * Q) return -q [idx - 2 * Q];
+	      return -q [R - idx];
+	   };
+	   int ns = 0, nc = 0;
+	   for (int i = 0; i < R && h -> smem_lut_ok; i ++) {
+	      float a = refl (i), b = sc [i].imag ();
+	      if (memcmp (&a, &b, 4) != 0 && !(a == 0.f && b == 0.f)) {
+	         if (ns < kMaxSinExc) { L.sin_exc_idx [ns] = i; L.sin_exc_val [ns] = b; ns ++; }
+	         else h -> smem_lut_ok = false;
+	      }
+	      a = refl ((i + Q) % R); b = sc [i].real ();
+	      if (memcmp (&a, &b, 4) != 0 && !(a == 0.f && b == 0.f)) {
+	         if (nc < kMaxSinExc) { L.cos_exc_idx [nc] = i; L.cos_exc_val [nc] = b; nc ++; }
+	         else h -> smem_lut_ok = false;
+	      }
+	   }
+	   if (h -> smem_lut_ok) {
+	      if (h -> d_sin_quarter) cudaFree (h -> d_sin_quarter);
+	      CK (cudaMalloc ((void **)&h -> d_sin_quarter, (Q + 1) * sizeof (float)));
+	      CK (cudaMemcpy (h -> d_sin_quarter, q.data (), (Q + 1) * sizeof (float),
+	                      cudaMemcpyHostToDevice));
+	      L.q = h -> d_sin_quarter;
+	   }
+	}
+	if (!h -> smem_lut_ok) {
+	   h -> err = "SinCos table is not quarter-wave symmetric for this fm_rate";
+	   return SDRJFM_ERR_UNSUPPORTED;
+	}
+	return SDRJFM_OK;
+}
+
+static int rebuild_tables (Lane *h) {
+	h -> tables = build_tables (h -> cfg.input_rate, h -> cfg.fm_rate,
+	                            h -> set.input_filter_hz, h -> set.lf_cutoff_hz);
+	return upload_tables (h);
+}
+
+// allocates and zeroes the RDS state, uploads the band-pass spectrum, twiddles and decimator taps
+static int rds_setup (Lane *h) {
+const int64_t S = h -> cfg.n_streams;
+const TableHeader &th = h -> tables.hdr ();
+	if (!h -> d_rds_dring) {
+	   CK (dalloc (&h -> d_rds_dring, (size_t)S * kRdsRing));
+	   CK (dalloc (&h -> d_rds_pring, (size_t)S * kRdsRing));
+	   CK (dalloc (&h -> d_rds_bp, (size_t)S * 2 * kRdsBlock));
+	   CK (dalloc (&h -> d_rds_hi, (size_t)S * 2 * kRdsN));
+	   CK (dalloc (&h -> d_rds_hist [0], (size_t)S * (kRdsDecTaps - 1)));
+	   CK (dalloc (&h -> d_rds_hist [1], (size_t)S * (kRdsDecTaps - 1)));
+	   CK (dalloc (&h -> d_rds_R, (size_t)kRdsNh + 1));
+	   CK (dalloc (&h -> d_rds_tw, (size_t)kRdsNh));
+	   CK (dalloc (&h -> d_rds_dtaps, (size_t)kRdsDecTaps));
+	   CK (cudaFuncSetAttribute (rds_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRdsFftSmem));
+//	rdsBandPassFilter.setBand (RDS_FREQUENCY -+ RDS_WIDTH / 2, fmRate), fm-processor.cpp:166-168; Pass (float)
+//	returns 3 * Re (conv): real taps 3 Re k[j].  R[k] = (1/Nh) sum_j 3 r[j] exp (-2 pi i j k / N), k = 0..Nh
+	   std::vector<cf32> bp = design_bandpass (kRdsTaps, 57000 - 2400, 57000 + 2400, th.fm_rate);
+	   std::vector<std::complex<double>> w (kRdsN);
+	   for (int t = 0; t < kRdsN; t ++) w [t] = std::polar (1.0, -2 * M_PI * t / kRdsN);
+	   std::vector<float2> R (kRdsNh + 1), tw (kRdsNh);
+	   for (int k = 0; k <= kRdsNh; k ++) {
+	      std::complex<double> a (0, 0);
+	      for (int j = 0; j < kRdsTaps; j ++)
+	         a += 3.0 * (double)bp [j].real () * w [(int)(((int64_t)j * k) & (kRdsN - 1))];
+	      a /= (double)kRdsNh;
+	      R [k] = make_float2 ((float)a.real (), (float)a.imag ());
+	   }
+	   for (int k = 0; k < kRdsNh; k ++) tw [k] = make_float2 ((float)w [k].real (), (float)w [k].imag ());
+	   CK (cudaMemcpy (h -> d_rds_R, R.data (), R.size () * sizeof (float2), cudaMemcpyHostToDevice));
+	   CK (cudaMemcpy (h -> d_rds_tw, tw.data (), tw.size () * sizeof (float2), cudaMemcpyHostToDevice));
+	   CK (cudaMemcpy (h -> d_rds_dtaps, h -> tables.payload () + th.off_rdsdecim,
+	                   kRdsDecTaps * sizeof (float2), cudaMemcpyHostToDevice));
+	}
+	else {
+	   CK (cudaMemsetAsync (h -> d_rds_dring, 0, (size_t)S * kRdsRing * sizeof (float), h -> stream));
+	   CK (cudaMemsetAsync (h -> d_rds_pring, 0, (size_t)S * kRdsRing * sizeof (float), h -> stream));
+	   CK (cudaMemsetAsync (h -> d_rds_hist [0], 0, (size_t)S * (kRdsDecTaps - 1) * sizeof (float2), h -> stream));
+	   CK (cudaMemsetAsync (h -> d_rds_hist [1], 0, (size_t)S * (kRdsDecTaps - 1) * sizeof (float2), h -> stream));
+	}
+	h -> rds_total = 0; h -> rds_last_block = -1;
+	return SDRJFM_OK;
+}
+
+static const char *lane_last_error (const Lane *h) {
+	return h ? h -> err.c_str () : g_create_error.c_str ();
+}
+
+static Lane *lane_create (const sdrjfm_config *cfg, int *status) {
+int dummy; if (!status) status = &dummy;
+	*status = SDRJFM_ERR_ARG;
+	if (!cfg || cfg -> n_streams < 1 || cfg -> max_samples_per_call < 1) {
+	   g_create_error = "bad config"; return nullptr;
+	}
+	if (cfg -> input_rate != 2304000 || cfg -> fm_rate != 192000) {
+//	the reference itself only supports 2304000 (and the 192000 bypass), SURVEY.md §8(d) config 4
+	   g_create_error = "only input_rate 2304000 / fm_rate 192000 are supported";
+	   *status = SDRJFM_ERR_UNSUPPORTED; return nullptr;
+	}
+int ndev = 0;
+	if (cudaGetDeviceCount (&ndev) != cudaSuccess || ndev <= cfg -> device) {
+	   g_create_error = "no CUDA device: this library has no CPU fallback";
+	   *status = SDRJFM_ERR_NO_DEVICE; return nullptr;
+	}
+cudaDeviceProp prop;
+	if (cudaSetDevice (cfg -> device) != cudaSuccess ||
+	    cudaGetDeviceProperties (&prop, cfg -> device) != cudaSuccess || prop.major < 10) {
+	   g_create_error = "device is not sm_100-class (B200)";
+	   *status = SDRJFM_ERR_NO_DEVICE; return nullptr;
+	}
+Lane *h = new Lane ();
+	h -> cfg = *cfg;
+	if (h -> cfg.working_rate <= 0) h -> cfg.working_rate = 48000;
+	if (h -> cfg.audio_rate <= 0) h -> cfg.audio_rate = h -> cfg.working_rate;
+	h -> n_sm = prop.multiProcessorCount;
+	default_settings (h -> set, cfg -> fm_rate);
+	h -> fade_max = h -> cfg.working_rate / 2;
+	h -> fade_cnt = h -> fade_max;
+const int64_t S = cfg -> n_streams;
+	h -> cap_in    = ((cfg -> max_samples_per_call + kDecim + 15) / 16) * 16;
+	h -> cap_fm    = ((h -> cap_in / kDecim + 1 + 15) / 16) * 16;
+	h -> cap_audio = ((h -> cap_fm / kRsDecim + 1 + 15) / 16) * 16;
+	h -> cap_rds   = ((h -> cap_fm / 8 + 1 + 15) / 16) * 16;
+auto fail = [&](cudaError_t e, const char *what) -> Lane * {
+	   g_create_error = std::string (what) + ": " + cudaGetErrorString (e);
+	   *status = SDRJFM_ERR_CUDA; lane_destroy (h); return nullptr;
+	};
+cudaError_t e;
+#define AL(p, n) if ((e = dalloc (&h -> p, (size_t)(n))) != cudaSuccess) return fail (e, "cudaMalloc " #p)
+	if ((e = cudaStreamCreateWithFlags (&h -> stream, cudaStreamNonBlocking)) != cudaSuccess)
+	   return fail (e, "cudaStreamCreate");
+	AL (d_in, S * h -> cap_in);
+	AL (d_hist [0], S * kHist); AL (d_hist [1], S * kHist);
+	AL (d_pend, S * kDecim);
+	AL (d_U, S * h -> cap_fm); AL (d_S, S * h -> cap_fm);
+	AL (d_iqn, S * h -> cap_fm); AL (d_fmz, S * h -> cap_fm);
+	AL (d_res, S * h -> cap_fm); AL (d_zabs, S * h -> cap_fm);
+	AL (d_demod, S * h -> cap_fm); AL (d_phase, S * h -> cap_fm); AL (d_pssd, S * h -> cap_fm);
+	AL (d_locked, S * h -> cap_fm);
+	AL (d_lr, S * h -> cap_fm); AL (d_a192, S * h -> cap_fm);
+	AL (d_rdsc, S * h -> cap_fm); AL (d_rds24, S * h -> cap_rds);
+	AL (d_ahist [0], S * kRsHist); AL (d_ahist [1], S * kRsHist);
+	AL (d_audio, S * h -> cap_audio);
+	AL (d_state, S);
+	AL (d_iter_stats, S * 4);
+	AL (d_pss_ring, S * kPssRing);
+#undef AL
+	{  // initial member values of the reference objects
+	   std::vector<StreamState> st (S);
+	   memset (st.data (), 0, S * sizeof (StreamState));
+	   for (auto &s : st) { s.Imin1 = s.Qmin1 = s.Imin2 = s.Qmin2 = 0.01f; }   // fm-demodulator.cpp:79-82
+	   if ((e = cudaMemcpy (h -> d_state, st.data (), S * sizeof (StreamState),
+	                        cudaMemcpyHostToDevice)) != cudaSuccess) return fail (e, "state upload");
+	}
+	if ((e = cudaFuncSetAttribute (frontend_fir_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                               kFeSmemBytes)) != cudaSuccess ||
+	    (e = cudaFuncSetAttribute (frontend_fir_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                               kFeSmemBytes)) != cudaSuccess) return fail (e, "smem attr K1");
+	if ((e = cudaFuncSetAttribute (sequential_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                               (cfg -> fm_rate / 4 + 1) * (int)sizeof (float))) != cudaSuccess ||
+	    (e = cudaFuncSetAttribute (sequential_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                               (cfg -> fm_rate / 4 + 1) * (int)sizeof (float))) != cudaSuccess)
+	   return fail (e, "smem attr K3");
+	if ((e = cudaFuncSetAttribute (pilot_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                               (int)kPiSmemBytes)) != cudaSuccess ||
+	    (e = cudaFuncSetAttribute (pilot_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                               (int)sizeof (PilotSmem))) != cudaSuccess ||
+	    (e = cudaFuncSetAttribute (pilot_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+	                               25)) != cudaSuccess) return fail (e, "smem attr pilot");
+	{ const char *env = getenv ("SDRJFM_PILOT_LUT_SMEM"); h -> pilot_lut_smem = env && env [0] == '1'; }
+	{ const char *env = getenv ("SDRJFM_SEQUENTIAL_PLL"); h -> sequential_pll = env && env [0] == '1'; }
+int rc = rebuild_tables (h);
+	if (rc != SDRJFM_OK) { g_create_error = h -> err; *status = rc; lane_destroy (h); return nullptr; }
+	*status = SDRJFM_OK;
+	return h;
+}
+
+static int lane_destroy (Lane *h) {
+	if (!h) return SDRJFM_ERR_ARG;
+	cudaSetDevice (h -> cfg.device);
+	if (h -> stream) cudaStreamSynchronize (h -> stream);
+void *ptrs [] = { h -> d_tables, h -> d_sin_quarter, h -> d_in, h -> d_hist [0], h -> d_hist [1],
+	              h -> d_pend, h -> d_U, h -> d_S, h -> d_iqn, h -> d_fmz, h -> d_res, h -> d_zabs,
+	              h -> d_demod, h -> d_phase, h -> d_pssd, h -> d_locked, h -> d_lr, h -> d_a192,
+	              h -> d_rdsc, h -> d_rds24, h -> d_ahist [0], h -> d_ahist [1], h -> d_audio,
+	              h -> d_state, h -> d_iter_stats, h -> d_pss_ring,
+	              h -> d_rds_dring, h -> d_rds_pring, h -> d_rds_bp, h -> d_rds_hi, h -> d_rds_R, h -> d_rds_tw,
+	              h -> d_rds_dtaps, h -> d_rds_hist [0], h -> d_rds_hist [1],
+	              h -> d_histw [0], h -> d_histw [1], h -> d_Uw, h -> d_Sw, h -> d_udel [0], h -> d_udel [1],
+	              h -> d_sdel [0], h -> d_sdel [1], h -> d_alp_hist [0], h -> d_alp_hist [1], h -> d_lrf, h -> d_lo_tab };
+	for (void *p : ptrs) if (p) cudaFree (p);
+	if (h -> stream) cudaStreamDestroy (h -> stream);
+	delete h;
+	return SDRJFM_OK;
+}
+
+static void *lane_cuda_stream (Lane *h) { return h ? (void *)h -> stream : nullptr; }
+static int64_t lane_launch_count (const Lane *h) { return h ? h -> launches : 0; }
+
+static int lane_pilot_stats (Lane *h, int32_t *out /* [n_streams][4] */) {
+	if (!h || !out) return SDRJFM_ERR_ARG;
+	CK (cudaMemcpyAsync (out, h -> d_iter_stats, (size_t)h -> cfg.n_streams * 4 * sizeof (int32_t),
+	                     cudaMemcpyDeviceToHost, h -> stream));
+	CK (cudaStreamSynchronize (h -> stream));
+	return SDRJFM_OK;
+}
+
+static int lane_sync (Lane *h) {
+	if (!h) return SDRJFM_ERR_ARG;
+	CK (cudaStreamSynchronize (h -> stream));
+	return SDRJFM_OK;
+}
+
+static int launch_frontend (Lane *h, const float2 *src, int64_t pitch, int32_t M,
+                            const float2 *hist) {
+const int S = h -> cfg.n_streams;
+dim3 grid ((unsigned)((M + kFeTileOut - 1) / kFeTileOut), (unsigned)S);
+LoParams lp;
+	memset (&lp, 0, sizeof lp);
+const bool lo = h -> set.lo_hz != 0;
+	if (lo) {
+	   lp.tab = h -> d_lo_tab; lp.rate = h -> cfg.input_rate; lp.lo = h -> set.lo_hz;
+	   int64_t s128 = (128 * (int64_t)h -> set.lo_hz) % lp.rate; if (s128 < 0) s128 += lp.rate;
+	   lp.step128 = (int32_t)s128; lp.phase = h -> lo_phase;
+	   lp.lgain = h -> set.lgain; lp.rgain = h -> set.rgain;
+	}
+	if (h -> set.input_filter_hz > 0) {
+	   if (lo) frontend_wide_kernel<true><<<grid, kFeThreads, kFwSmemBytes, h -> stream>>> (
+	         src, pitch, h -> d_histw [h -> histw_sel], h -> d_Uw, h -> d_Sw, h -> cap_fm, M, lp);
+	   else    frontend_wide_kernel<false><<<grid, kFeThreads, kFwSmemBytes, h -> stream>>> (
+	         src, pitch, h -> d_histw [h -> histw_sel], h -> d_Uw, h -> d_Sw, h -> cap_fm, M, lp);
+	}
+	else {
+	   if (lo) frontend_fir_kernel<true><<<grid, kFeThreads, kFeSmemBytes, h -> stream>>> (
+	         src, pitch, hist, h -> d_U, h -> d_S, h -> cap_fm, M, lp);
+	   else    frontend_fir_kernel<false><<<grid, kFeThreads, kFeSmemBytes, h -> stream>>> (
+	         src, pitch, hist, h -> d_U, h -> d_S, h -> cap_fm, M, lp);
+	}
+	h -> launches ++;
+	CK (cudaGetLastError ());
+	return SDRJFM_OK;
+}
+
+// buffers of the wide (input filter ON) front end; cleared start
+static int wide_setup (Lane *h) {
+const int64_t S = h -> cfg.n_streams;
+	if (!h -> d_Uw) {
+	   CK (dalloc (&h -> d_histw [0], (size_t)S * kFwHist)); CK (dalloc (&h -> d_histw [1], (size_t)S * kFwHist));
+	   CK (dalloc (&h -> d_Uw, (size_t)S * h -> cap_fm)); CK (dalloc (&h -> d_Sw, (size_t)S * h -> cap_fm));
+	   for (int i = 0; i < 2; i ++) {
+	      CK (dalloc (&h -> d_udel [i], (size_t)S * kFwDelay)); CK (dalloc (&h -> d_sdel [i], (size_t)S * kFwDelay));
+	   }
+	   CK (cudaFuncSetAttribute (frontend_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwSmemBytes));
+	   CK (cudaFuncSetAttribute (frontend_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwSmemBytes));
+	}
+	else {
+	   for (int i = 0; i < 2; i ++) {
+	      CK (cudaMemsetAsync (h -> d_histw [i], 0, (size_t)S * kFwHist * sizeof (float2), h -> stream));
+	      CK (cudaMemsetAsync (h -> d_udel [i], 0, (size_t)S * kFwDelay * sizeof (float2), h -> stream));
+	      CK (cudaMemsetAsync (h -> d_sdel [i], 0, (size_t)S * kFwDelay * sizeof (float2), h -> stream));
+	   }
+	}
+	return SDRJFM_OK;
+}
+
+static int lane_run_frontend_only (Lane *h, const float *d_iq, int64_t n_in, int64_t in_pitch) {
+	if (!h || !d_iq || n_in < kDecim || in_pitch < n_in) return SDRJFM_ERR_ARG;
+	if (n_in > h -> cfg.max_samples_per_call) { h -> err = "n_in exceeds max_samples_per_call"; return SDRJFM_ERR_CAPACITY; }
+	CK (cudaSetDevice (h -> cfg.device));
+	return launch_frontend (h, (const float2 *)d_iq, in_pitch, (int32_t)(n_in / kDecim),
+	                        h -> d_hist [h -> hist_sel]);
+}
+
+// the launch sequence behind both process entry points; `src` is a device pointer holding
+// (pending | new) samples contiguously per stream with row pitch `pitch`
+static int run_chain (Lane *h, const float2 *src, int64_t pitch, int64_t n_proc,
+                      float2 *d_audio_out, int64_t audio_pitch, int64_t *n_audio,
+                      float2 *d_rds_out, int64_t rds_pitch, int64_t *n_rds) {
+const int S = h -> cfg.n_streams;
+const Settings &st = h -> set;
+const TableHeader &th = h -> tables.hdr ();
+const float *T = h -> d_tables;
+const int32_t M = (int32_t)(n_proc / kDecim);
+	h -> last_nfm = M; h -> last_naudio = 0; h -> last_nrds = 0;
+	if (n_audio) *n_audio = 0;
+	if (n_rds) *n_rds = 0;
+	if (M == 0) return SDRJFM_OK;
+int rc;
+//	K1 ------------------------------------------------------------------------------------
+const bool wide = st.input_filter_hz > 0;
+	if ((rc = launch_frontend (h, src, pitch, M, h -> d_hist [h -> hist_sel])) != SDRJFM_OK) return rc;
+	if (wide) {
+	   roll_history_kernel<<<dim3 (2, S), 160, 0, h -> stream>>> (src, pitch, h -> d_histw [h -> histw_sel],
+	                                                   h -> d_histw [h -> histw_sel ^ 1], n_proc, kFwHist);
+	   h -> histw_sel ^= 1;
+	   dim3 g ((unsigned)((std::max (M, kFwDelay) + 255) / 256), (unsigned)S);
+	   fm_delay_kernel<<<g, 256, 0, h -> stream>>> (h -> d_Uw, h -> cap_fm, M, kFwDelay, h -> d_udel [h -> del_sel],
+	                                                h -> d_udel [h -> del_sel ^ 1], h -> d_U);
+	   fm_delay_kernel<<<g, 256, 0, h -> stream>>> (h -> d_Sw, h -> cap_fm, M, kFwDelay, h -> d_sdel [h -> del_sel],
+	                                                h -> d_sdel [h -> del_sel ^ 1], h -> d_S);
+	   h -> del_sel ^= 1;
+	   h -> launches += 3;
+	}
+	else {
+	   roll_history_kernel<<<dim3 (1, S), 64, 0, h -> stream>>> (src, pitch, h -> d_hist [h -> hist_sel],
+	                                                  h -> d_hist [h -> hist_sel ^ 1], n_proc, kHist);
+	   h -> hist_sel ^= 1; h -> launches ++;
+	}
+//	K2 ------------------------------------------------------------------------------------
+const float *consts = h -> tables.payload () + th.off_comp_consts;
+DiscrParams dp;
+	dp.sumC = consts [0]; dp.sumCm = consts [1];
+	dp.gb0 = consts [5]; dp.gb1 = consts [6]; dp.gb2 = consts [7];
+	if (wide) { dp.sumC = h -> wide_sumC; dp.sumCm = h -> wide_sumCm; dp.gb0 = dp.gb1 = dp.gb2 = 0.f; }
+	dp.lo_tab = nullptr; dp.lo_rate = h -> cfg.input_rate; dp.lo_hz = st.lo_hz; dp.lo_moff = wide ? -kFwDelay : 0;
+	dp.lo_phase = h -> lo_phase; dp.Hre = h -> lo_Hre; dp.Him = h -> lo_Him;
+	if (st.lo_hz != 0) {
+	   dp.lo_tab = h -> d_lo_tab;
+	   int64_t np = (h -> lo_phase - (int64_t)st.lo_hz * n_proc) % h -> cfg.input_rate;
+	   h -> lo_phase = np < 0 ? np + h -> cfg.input_rate : np;       // LOPhase after this call's samples
+	}
+	dp.Gre = consts [2]; dp.Gim = consts [3];
+	dp.alpha = (double)(1.0f / h -> cfg.input_rate);          // rfDcAlpha, fm-processor.cpp:379
+	dp.beta = pow (1.0 - dp.alpha, (double)kDecim);
+	dp.lgain = st.lgain; dp.rgain = st.rgain;
+	dp.dc_remove = st.dc_remove; dp.decoder = st.decoder;
+	discriminator_kernel<<<S, kDiThreads, 0, h -> stream>>> (
+	      h -> d_U, h -> d_S, h -> cap_fm, M, dp, T + th.off_atan, T + th.off_arcsine,
+	      h -> d_state, h -> d_res, h -> d_zabs, h -> d_iqn, h -> d_fmz);
+	h -> launches ++;
+//	K3 ------------------------------------------------------------------------------------
+SeqParams sp;
+	sp.K_FM = consts [4];
+	sp.omega = (float)(((float)19000 / h -> cfg.fm_rate) * (2 * M_PI));   // OMEGA_PILOT, :34
+	sp.gain = (float)(10 * (2 * M_PI) / h -> cfg.fm_rate);                // :79
+	sp.lock_half_rate = h -> cfg.fm_rate >> 1;
+	sp.decoder = st.decoder;
+	{  // pllC ctor, fm-demodulator.cpp:66-72 / pllC.cpp:38-58
+	   const float maxdev = 0.95 * (0.5 * h -> cfg.fm_rate);
+	   const float fac = 2.0 * M_PI / h -> cfg.fm_rate;
+	   const float bw = 0.85 * h -> cfg.fm_rate;
+	   sp.pll_beta = exp (-2.0 * M_PI * bw / 2 / h -> cfg.fm_rate);
+	   sp.pll_lo = -maxdev * fac; sp.pll_hi = maxdev * fac;
+	   sp.pll_reset = 0.0f;
+	}
+	sp.n_streams = S;
+const int seq_blocks = (S + kSeqLanes - 1) / kSeqLanes;
+const size_t seq_smem = (h -> lut.quarter + 1) * sizeof (float);
+	if (st.decoder == 2)
+	   sequential_kernel<true><<<seq_blocks, kSeqLanes, seq_smem, h -> stream>>> (
+	         h -> d_res, h -> d_zabs, h -> d_iqn, h -> cap_fm, M, sp, h -> lut, T + th.off_atan,
+	         h -> d_state, h -> d_demod, h -> d_phase, h -> d_locked);
+	else if (h -> sequential_pll)
+	   sequential_kernel<false><<<seq_blocks, kSeqLanes, seq_smem, h -> stream>>> (
+	         h -> d_res, h -> d_zabs, h -> d_iqn, h -> cap_fm, M, sp, h -> lut, T + th.off_atan,
+	         h -> d_state, h -> d_demod, h -> d_phase, h -> d_locked);
+	else {
+	   PilotParams pp;
+	   pp.K_FM = sp.K_FM; pp.omega = sp.omega; pp.gain = sp.gain;
+	   pp.lock_half_rate = sp.lock_half_rate; pp.n_streams = S;
+	   if (h -> pilot_lut_smem)
+	      pilot_kernel<true><<<S, kPiThreads, kPiSmemBytes, h -> stream>>> (
+	            h -> d_res, h -> d_zabs, h -> cap_fm, M, pp, h -> lut, h -> d_state,
+	            h -> d_demod, h -> d_phase, h -> d_locked, h -> d_iter_stats);
+	   else
+	      pilot_kernel<false><<<S, kPiThreads, sizeof (PilotSmem), h -> stream>>> (
+	            h -> d_res, h -> d_zabs, h -> cap_fm, M, pp, h -> lut, h -> d_state,
+	            h -> d_demod, h -> d_phase, h -> d_locked, h -> d_iter_stats);
+	}
+	h -> launches ++;
+//	K4 ------------------------------------------------------------------------------------
+	{
+	   StereoParams q;
+	   q.fm_mode = st.fm_mode; q.auto_mono = st.auto_mono; q.pss_on = st.pss_on;
+	   q.sound_sel = st.sound_sel; q.panorama = st.panorama;
+	   q.pss_alpha = 10.0f / h -> cfg.fm_rate;                 // fm-processor.cpp:81-82
+	   q.pss_lock_alpha = 1.0f / h -> cfg.fm_rate;             // stereo-separation.cpp:32
+	   q.rate3 = 3 * h -> cfg.fm_rate;
+	   q.write_pss_tap = h -> cfg.keep_taps;
+	   stereo_kernel<<<S, kStThreads, 0, h -> stream>>> (
+	         h -> d_demod, h -> d_phase, h -> d_locked, h -> cap_fm, M, q,
+	         reinterpret_cast<const float2 *>(T + th.off_sincos), h -> d_state, h -> d_pss_ring,
+	         h -> d_lr, h -> d_pssd);
+	   h -> launches ++;
+	}
+//	K5 ------------------------------------------------------------------------------------
+	if (st.rds_mode != 0) {
+	   const int64_t n0 = h -> rds_total;
+	   for (int32_t m = 0; m < M; ) {
+	      const int64_t K = (n0 + m) / kRdsBlock;
+	      const int32_t mEnd = (int32_t)std::min<int64_t> (M, (K + 1) * kRdsBlock - n0);
+	      dim3 g ((unsigned)((mEnd - m + 255) / 256), (unsigned)S);
+	      rds_append_kernel<<<g, 256, 0, h -> stream>>> (h -> d_demod, h -> d_phase, h -> cap_fm, m, mEnd, n0,
+	                                                    h -> d_rds_dring, h -> d_rds_pring);
+	      h -> launches ++;
+	      if (K >= 1 && h -> rds_last_block < K - 1) {
+	         rds_block_kernel<<<S, kRdsThreads, kRdsFftSmem, h -> stream>>> (
+	               h -> d_rds_dring, K - 1, h -> d_rds_tw, h -> d_rds_R, h -> d_rds_bp, h -> d_rds_hi);
+	         h -> launches ++;
+	         h -> rds_last_block = K - 1;
+	      }
+	      rds_mix_kernel<<<g, 256, 0, h -> stream>>> (h -> d_rds_pring, h -> d_rds_bp, h -> d_rds_hi,
+	                                                 h -> cap_fm, m, mEnd, n0, h -> d_rdsc);
+	      h -> launches ++;
+	      m = mEnd;
+	   }
+	   const int32_t nout = (int32_t)((n0 + M) / kRdsDecim - n0 / kRdsDecim);
+	   float2 *rout = d_rds_out ? d_rds_out : h -> d_rds24;
+	   const int64_t rpitch = d_rds_out ? rds_pitch : h -> cap_rds;
+	   dim3 g ((unsigned)((std::max (nout, 1) + 127) / 128), (unsigned)S);
+	   rds_decim_kernel<<<g, 128, 0, h -> stream>>> (h -> d_rdsc, h -> cap_fm, M, n0, h -> d_rds_dtaps,
+	         h -> d_rds_hist [h -> rds_hist_sel], h -> d_rds_hist [h -> rds_hist_sel ^ 1], rout, rpitch, nout);
+	   h -> launches ++;
+	   h -> rds_hist_sel ^= 1;
+	   h -> rds_total += M;
+	   h -> last_nrds = nout;
+	   if (n_rds) *n_rds = nout;
+	}
+//	K6 ------------------------------------------------------------------------------------
+const float2 *lr_in = h -> d_lr;
+	if (st.lf_cutoff_hz > 0) {
+	   dim3 g ((unsigned)((M + kAlpTile - 1) / kAlpTile), (unsigned)S);
+	   audio_lp_kernel<<<g, kAlpThreads, 0, h -> stream>>> (h -> d_lr, h -> cap_fm, M,
+	                                                        h -> d_alp_hist [h -> alp_sel], h -> d_lrf);
+	   roll_history_kernel<<<dim3 (kAlpHist / 256, S), 256, 0, h -> stream>>> (
+	         h -> d_lr, h -> cap_fm, h -> d_alp_hist [h -> alp_sel], h -> d_alp_hist [h -> alp_sel ^ 1], M, kAlpHist);
+	   h -> alp_sel ^= 1; h -> launches += 2;
+	   lr_in = h -> d_lrf;
+	}
+const int64_t q0 = h -> fm_total / kRsDecim;
+const int64_t q1 = (h -> fm_total + M) / kRsDecim;
+const int32_t nq = (int32_t)(q1 - q0);
+float2 *aout = d_audio_out ? d_audio_out : h -> d_audio;
+const int64_t apitch = d_audio_out ? audio_pitch : h -> cap_audio;
+	{
+	   AudioParams ap;
+	   ap.alpha = st.deemph_alpha;
+	   ap.gl = st.volume * st.left_ch; ap.gr = st.volume * st.right_ch;   // fm-processor.cpp:304-305
+	   ap.M = M; ap.g0 = h -> fm_total; ap.q0 = q0; ap.nq = nq;
+	   ap.fade_cnt = h -> fade_cnt; ap.fade_max = h -> fade_max;
+	   ap.write_tap = h -> cfg.keep_taps;
+	   ap.sel = h -> ahist_sel;
+	   dim3 g ((unsigned)((M + kAuTile - 1) / kAuTile), (unsigned)S);
+	   audio_kernel<<<g, kAuThreads, 0, h -> stream>>> (
+	         lr_in, h -> cap_fm, ap, h -> d_ahist [h -> ahist_sel], h -> d_ahist [h -> ahist_sel ^ 1],
+	         h -> d_state, h -> d_a192, aout, apitch);
+	   h -> launches ++;
+	   h -> ahist_sel ^= 1;
+	   h -> fade_cnt = h -> fade_cnt > nq ? h -> fade_cnt - nq : 0;
+	}
+	h -> fm_total += M;
+	h -> last_naudio = nq;
+	if (n_audio) *n_audio = nq;
+	CK (cudaGetLastError ());
+	return SDRJFM_OK;
+}
+
+// stage (pending | new) samples when the call is not aligned to 12; returns the source to read
+static int stage_input (Lane *h, const float *iq, int64_t n_in, int64_t in_pitch,
+                        cudaMemcpyKind kind, const float2 **src, int64_t *pitch, int64_t *n_proc) {
+const int S = h -> cfg.n_streams;
+const int64_t total = h -> pend + n_in;
+	*n_proc = (total / kDecim) * kDecim;
+	if (kind == cudaMemcpyDeviceToDevice && h -> pend == 0 && *n_proc == n_in) {
+	   *src = (const float2 *)iq; *pitch = in_pitch;       // zero-copy
+	   return SDRJFM_OK;
+	}
+	if (h -> pend)
+	   CK (cudaMemcpy2DAsync (h -> d_in, h -> cap_in * sizeof (float2), h -> d_pend,
+	                          kDecim * sizeof (float2), h -> pend * sizeof (float2), S,
+	                          cudaMemcpyDeviceToDevice, h -> stream));
+	if (n_in)
+	   CK (cudaMemcpy2DAsync (h -> d_in + h -> pend, h -> cap_in * sizeof (float2), iq,
+	                          in_pitch * sizeof (float2), n_in * sizeof (float2), S, kind, h -> stream));
+const int newpend = (int)(total - *n_proc);
+	if (newpend)
+	   CK (cudaMemcpy2DAsync (h -> d_pend, kDecim * sizeof (float2), h -> d_in + *n_proc,
+	                          h -> cap_in * sizeof (float2), newpend * sizeof (float2), S,
+	                          cudaMemcpyDeviceToDevice, h -> stream));
+	h -> pend = newpend;
+	*src = h -> d_in; *pitch = h -> cap_in;
+	return SDRJFM_OK;
+}
+
+static int lane_process_device (Lane *h, const float *d_iq, int64_t n_in, int64_t in_pitch,
+                           float *d_audio, int64_t audio_pitch, int64_t *n_audio,
+                           float *d_rds24, int64_t rds_pitch, int64_t *n_rds) {
+	if (!h || n_in < 0 || (n_in > 0 && (!d_iq || in_pitch < n_in))) return SDRJFM_ERR_ARG;
+	if (n_in > h -> cfg.max_samples_per_call) { h -> err = "n_in exceeds max_samples_per_call"; return SDRJFM_ERR_CAPACITY; }
+	CK (cudaSetDevice (h -> cfg.device));
+const float2 *src; int64_t pitch, n_proc;
+int rc = stage_input (h, d_iq, n_in, in_pitch, cudaMemcpyDeviceToDevice, &src, &pitch, &n_proc);
+	if (rc != SDRJFM_OK) return rc;
+	return run_chain (h, src, pitch, n_proc, (float2 *)d_audio, audio_pitch, n_audio,
+	                  (float2 *)d_rds24, rds_pitch, n_rds);
+}
+
+static int lane_get_meta (Lane *h, sdrjfm_meta *meta) {
+	if (!h || !meta) return SDRJFM_ERR_ARG;
+const int S = h -> cfg.n_streams;
+std::vector<StreamState> st (S);
+	CK (cudaMemcpyAsync (st.data (), h -> d_state, S * sizeof (StreamState), cudaMemcpyDeviceToHost, h -> stream));
+	CK (cudaStreamSynchronize (h -> stream));
+	for (int s = 0; s < S; s ++) {
+	   sdrjfm_meta &m = meta [s];
+	   const StreamState &x = st [s];
+	   m.dc_rf_re = (float)x.dc_re; m.dc_rf_im = (float)x.dc_im;
+	   m.dc_rf_db = h -> set.dc_remove ?
+	         20 * log10f (hypotf (m.dc_rf_re, m.dc_rf_im) + 1.0f / 32768) : -99.99f;
+	   m.dc_if = x.fm_afc;
+	   m.carrier_ampl = x.am_carr_ampl;
+	   m.pss_phase_shift_deg = (float)(x.pss_delay / M_PI * 180.0f);
+	   m.pss_phase_change = x.pss_mean_error * 1000;
+	   const bool locked = h -> set.fm_mode != 2 && x.pilot_locked;       // isPilotLocked, :869-879
+	   m.pilot_locked = locked;
+	   m.pilot_lock_strength = h -> set.fm_mode != 2 ? x.pilot_lock : 0.f;
+	   m.pss_state = (h -> set.pss_on && locked) ? (x.pss_minimized ? 2 : 1) : 0;
+	   m.peak_left_db = x.peak_l_db; m.peak_right_db = x.peak_r_db;
+	}
+	return SDRJFM_OK;
+}
+
+static int64_t lane_read_tap (Lane *h, int which, int32_t stream, void *out, int64_t cap) {
+	if (!h || !out || stream < 0 || stream >= h -> cfg.n_streams) return SDRJFM_ERR_ARG;
+const void *src = nullptr; size_t esz = 0; int64_t n = h -> last_nfm; int64_t pitch = h -> cap_fm;
+	switch (which) {
+	   case SDRJFM_TAP_FM_Z:        src = h -> d_fmz;    esz = 8; break;
+	   case SDRJFM_TAP_DEMOD:       src = h -> d_demod;  esz = 4; break;
+	   case SDRJFM_TAP_PILOT_PHASE: src = h -> d_phase;  esz = 4; break;
+	   case SDRJFM_TAP_LOCKED:      src = h -> d_locked; esz = 1; break;
+	   case SDRJFM_TAP_PSS_DELAY:   src = h -> d_pssd;   esz = 4; break;
+	   case SDRJFM_TAP_LR:          src = h -> d_lr;     esz = 8; break;
+	   case SDRJFM_TAP_AUDIO192:    src = h -> d_a192;   esz = 8; break;
+	   case SDRJFM_TAP_RDS_CPLX:    src = h -> d_rdsc;   esz = 8; break;
+	   case SDRJFM_TAP_RDS24:       src = h -> d_rds24;  esz = 8; n = h -> last_nrds; pitch = h -> cap_rds; break;
+	   default: return SDRJFM_ERR_ARG;
+	}
+	if (n > cap) n = cap;
+	if (n <= 0) return 0;
+	CK (cudaMemcpyAsync (out, (const char *)src + (size_t)stream * pitch * esz, n * esz,
+	                     cudaMemcpyDeviceToHost, h -> stream));
+	CK (cudaStreamSynchronize (h -> stream));
+	return n;
+}
+
+// ---- settings (fm-processor.cpp:232-301, 351-359, 762-770, 840-933) -----------------------
+static int lane_set_fm_mode (Lane *h, int32_t m) {
+	if (!h || m < 0 || m > 2) return SDRJFM_ERR_ARG;
+	h -> set.fm_mode = m; return SDRJFM_OK;
+}
+static int lane_set_fm_decoder (Lane *h, int32_t d) {
+	if (!h || d < 1 || d > 6) return SDRJFM_ERR_ARG;
+	if (d == 1) { h -> err = "AM decoder is not on the GPU path"; return SDRJFM_ERR_UNSUPPORTED; }
+	h -> set.decoder = d; return SDRJFM_OK;
+}
+static int lane_set_sound_mode (Lane *h, int32_t s) {
+	if (!h || s < 0 || s > 6) return SDRJFM_ERR_ARG;
+	h -> set.sound_sel = s; return SDRJFM_OK;
+}
+static int lane_set_stereo_panorama (Lane *h, int32_t pan) {
+	if (!h) return SDRJFM_ERR_ARG;
+	h -> set.panorama = (float)pan / 100.0f; return SDRJFM_OK;           // :279
+}
+static int lane_set_sound_balance (Lane *h, int32_t balance) {
+	if (!h) return SDRJFM_ERR_ARG;
+	h -> set.left_ch  = (balance > 0 ? (100 - balance) / 100.0 : 1.0f);   // :284-285
+	h -> set.right_ch = (balance < 0 ? (100 + balance) / 100.0 : 1.0f);
+	return SDRJFM_OK;
+}
+static int lane_set_deemphasis (Lane *h, int32_t v) {
+	if (!h || v < 1) return SDRJFM_ERR_ARG;
+float Tau = 1000000.0 / v;                                                // :295-296
+	h -> set.deemph_us = v;
+	h -> set.deemph_alpha = 1.0 / (float (h -> cfg.fm_rate) / Tau + 1.0);
+	return SDRJFM_OK;
+}
+static int lane_set_volume_db (Lane *h, float db) {
+	if (!h) return SDRJFM_ERR_ARG;
+	h -> set.volume = std::pow (10.0f, db / 20.0f); return SDRJFM_OK;     // :300
+}
+static int lane_set_lf_cutoff (Lane *h, int32_t hz) {
+	if (!h) return SDRJFM_ERR_ARG;
+//	setlfcutoff (:762-770): <= 0 switches fmAudioFilter off; else it is re-designed and starts cleared
+	CK (cudaSetDevice (h -> cfg.device));
+	const int32_t v = hz > 0 ? hz : 0;
+	if (v == h -> set.lf_cutoff_hz) return SDRJFM_OK;
+	h -> set.lf_cutoff_hz = v;
+	if (v > 0) {
+	   const int64_t S = h -> cfg.n_streams;
+	   if (!h -> d_lrf) {
+	      CK (dalloc (&h -> d_alp_hist [0], (size_t)S * kAlpHist)); CK (dalloc (&h -> d_alp_hist [1], (size_t)S * kAlpHist));
+	      CK (dalloc (&h -> d_lrf, (size_t)S * h -> cap_fm));
+	   }
+	   else for (int i = 0; i < 2; i ++)
+	      CK (cudaMemsetAsync (h -> d_alp_hist [i], 0, (size_t)S * kAlpHist * sizeof (float2), h -> stream));
+	   std::vector<cf32> lp = design_lowpass (kAlpTaps, v, h -> cfg.fm_rate);
+	   float t [kAlpTaps];
+	   for (int i = 0; i < kAlpTaps; i ++) t [i] = lp [i].real ();
+	   CK (cudaMemcpyToSymbolAsync (c_alp_taps, t, sizeof t, 0, cudaMemcpyHostToDevice, h -> stream));
+	   CK (cudaStreamSynchronize (h -> stream));
+	}
+	return SDRJFM_OK;
+}
+static int lane_set_bandwidth (Lane *h, int32_t hz) {
+	if (!h) return SDRJFM_ERR_ARG;
+//	setBandwidth (:232-239): "Off" -> 0; else fmBandwidth in Hz, the low-pass corner is hz / 2 (:398).
+//	Switching the filter on (or changing it) starts it from a cleared state.
+	CK (cudaSetDevice (h -> cfg.device));
+	const int32_t v = hz > 0 ? hz : 0;
+	if (v == h -> set.input_filter_hz) return SDRJFM_OK;
+	h -> set.input_filter_hz = v;
+	int rc = rebuild_tables (h);
+	if (rc != SDRJFM_OK) return rc;
+	if (v > 0) return wide_setup (h);
+	return SDRJFM_OK;
+}
+static int lane_set_attenuation (Lane *h, float l, float r) {
+	if (!h) return SDRJFM_ERR_ARG;
+	h -> set.lgain = l; h -> set.rgain = r; return SDRJFM_OK;             // :356-357
+}
+static int lane_set_rds_mode (Lane *h, int32_t m) {
+	if (!h || m < 0 || m > 3) return SDRJFM_ERR_ARG;
+//	all three RDS demodulator variants (rds-decoder.cpp) consume the same 24 kHz baseband; the
+//	selector only matters to the (host-side, untouched) rdsDecoder.  Switching RDS on starts
+//	the branch from cleared filters (the reference would resume with stale block contents).
+	if (m != 0 && h -> set.rds_mode == 0) {
+	   CK (cudaSetDevice (h -> cfg.device));
+	   int rc = rds_setup (h);
+	   if (rc != SDRJFM_OK) return rc;
+	}
+	h -> set.rds_mode = m; return SDRJFM_OK;
+}
+static int lane_set_local_oscillator (Lane *h, int32_t hz) {
+	if (!h) return SDRJFM_ERR_ARG;
+//	set_localOscillator (:865-867).  The oscillator table (inputRate complex entries, oscillator.cpp:26-37)
+//	is built the first time lo is non-zero.
+	if (hz <= -h -> cfg.input_rate || hz >= h -> cfg.input_rate) return SDRJFM_ERR_ARG;
+	CK (cudaSetDevice (h -> cfg.device));
+	if (hz != 0 && !h -> d_lo_tab) {
+	   const int32_t R = h -> cfg.input_rate;
+	   std::vector<float2> t (R);
+	   for (int32_t i = 0; i < R; i ++)
+	      t [i] = make_float2 ((float)cos (2.0 * M_PI * i / R), (float)sin (2.0 * M_PI * i / R));
+	   CK (cudaMalloc ((void **)&h -> d_lo_tab, (size_t)R * sizeof (float2)));
+	   CK (cudaMemcpy (h -> d_lo_tab, t.data (), (size_t)R * sizeof (float2), cudaMemcpyHostToDevice));
+	}
+	if (hz == h -> set.lo_hz) return SDRJFM_OK;
+	h -> set.lo_hz = hz;
+	CK (cudaStreamSynchronize (h -> stream));
+	return upload_tables (h);        // taps with / without the DC folding, H (lo)
+}
+static int lane_set_squelch_mode (Lane *h, int32_t m) {
+	if (!h) return SDRJFM_ERR_ARG;
+	if (m != 0) { h -> err = "squelch is out of scope (SURVEY.md §2 row 11)"; return SDRJFM_ERR_UNSUPPORTED; }
+	h -> set.squelch_mode = 0; return SDRJFM_OK;
+}
+static int lane_set_auto_mono (Lane *h, int32_t on) {
+	if (!h) return SDRJFM_ERR_ARG;
+	h -> set.auto_mono = on != 0; return SDRJFM_OK;
+}
+static int lane_set_pss_mode (Lane *h, int32_t on) {
+	if (!h) return SDRJFM_ERR_ARG;
+	h -> set.pss_on = on != 0; return SDRJFM_OK;
+}
+static int lane_set_dc_remove (Lane *h, int32_t on) {
+	if (!h) return SDRJFM_ERR_ARG;
+	h -> set.dc_remove = on != 0;
+//	setDCRemove also zeroes RfDC (:917-920): clear the DC fields of every stream
+	CK (cudaSetDevice (h -> cfg.device));
+	CK (cudaMemset2DAsync (h -> d_state, sizeof (StreamState), 0, 2 * sizeof (double),
+	                       h -> cfg.n_streams, h -> stream));
+	return SDRJFM_OK;
+}
+static int lane_trigger_frequency_change (Lane *h) {
+	if (!h) return SDRJFM_ERR_ARG;
+	h -> fade_cnt = h -> fade_max;                                        // :848
+	return lane_restart_pss_analyzer (h);
+}
+static int lane_restart_pss_analyzer (Lane *h) {
+	if (!h) return SDRJFM_ERR_ARG;
+//	pilotDelayPSS = 0; pPSS.reset () (:857-860): zero the six PSS fields of every stream
+	CK (cudaSetDevice (h -> cfg.device));
+	CK (cudaMemset2DAsync ((char *)h -> d_state + offsetof (StreamState, pss_delay), sizeof (StreamState), 0,
+	                       offsetof (StreamState, pss_inp) - offsetof (StreamState, pss_delay),
+	                       h -> cfg.n_streams, h -> stream));
+	return SDRJFM_OK;
+}
+
+static int64_t lane_tables_nbytes (const Lane *h) {
+	return h ? (int64_t)h -> tables.bytes.size () : SDRJFM_ERR_ARG;
+}
+static int lane_tables_export (const Lane *h, void *out, int64_t cap) {
+	if (!h || !out || cap < (int64_t)h -> tables.bytes.size ()) return SDRJFM_ERR_ARG;
+	memcpy (out, h -> tables.bytes.data (), h -> tables.bytes.size ());
+	return SDRJFM_OK;
+}
+static int lane_tables_import (Lane *h, const void *blob, int64_t nbytes) {
+	if (!h || !blob || nbytes < (int64_t)sizeof (TableHeader)) return SDRJFM_ERR_ARG;
+const TableHeader *th = (const TableHeader *)blob;
+	if (th -> magic != 0x54464A53u ||
+	    nbytes != (int64_t)(sizeof (TableHeader) + th -> payload_floats * sizeof (float)) ||
+	    th -> input_rate != h -> cfg.input_rate || th -> fm_rate != h -> cfg.fm_rate)
+	   return SDRJFM_ERR_ARG;
+	CK (cudaSetDevice (h -> cfg.device));
+	CK (cudaStreamSynchronize (h -> stream));
+	h -> tables.bytes.assign ((const unsigned char *)blob, (const unsigned char *)blob + nbytes);
+	return upload_tables (h);
+}
+
