@@ -28,6 +28,36 @@ __device__ __forceinline__ float2 cmul_rn (float2 a, float2 b) {
 	                    fadd (fmul (a.x, b.y), fmul (a.y, b.x)));
 }
 
+// generic inclusive scan of affine maps x -> A x + B over the CTA (thread order); returns
+// the value entering this thread given `carry` entering thread 0, and the value leaving the
+// last thread through *total.
+__device__ __forceinline__ double block_affine_start (double A, double B, double carry,
+                                                       double *sA, double *sB, double *total) {
+const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+double iA = A, iB = B;
+#pragma unroll
+	for (int k = 1; k < 32; k <<= 1) {
+	   const double yA = __shfl_up_sync (0xffffffffu, iA, k);
+	   const double yB = __shfl_up_sync (0xffffffffu, iB, k);
+	   if (lane >= k) { iB = iA * yB + iB; iA = iA * yA; }
+	}
+	if (lane == 31) { sA [warp] = iA; sB [warp] = iB; }
+	__syncthreads ();
+double w = carry;
+	for (int q = 0; q < warp; q ++) w = sA [q] * w + sB [q];
+double eA = __shfl_up_sync (0xffffffffu, iA, 1);
+double eB = __shfl_up_sync (0xffffffffu, iB, 1);
+	if (lane == 0) { eA = 1.0; eB = 0.0; }
+const double start = eA * w + eB;
+	if (total) {
+	   double t = carry;
+	   for (int q = 0; q < (int)(blockDim.x >> 5); q ++) t = sA [q] * t + sB [q];
+	   *total = t;
+	}
+	__syncthreads ();
+	return start;
+}
+
 // State carried from one process call to the next, one record per IQ stream.
 // (The reference keeps the same quantities in fmProcessor / fm_Demodulator / pilotRecovery
 // / PerfectStereoSeparation member variables.)

@@ -74,13 +74,108 @@ dcplx r;
 	return r;
 }
 
+// What K2 carries from one call to the next, snapshotted by the pre-pass so that the tiles
+// of a call (which all read it) never race with the tile that writes the new values.
+struct DiscrSnap {
+	double dc_re, dc_im;
+	float2 sp1, sp2;           // block sums S[-1], S[-2]
+	float2 p1, p2;             // normalised samples -1 and -2 (Imin1/Qmin1, Imin2/Qmin2)
+};
+
+// pre-pass, grid (tiles, streams): zero-state response of the RF DC one-pole over each FULL tile
+// (tileB), and the snapshot of the carried state.
+__global__ void __launch_bounds__ (kDiThreads)
+dc_tile_kernel (const float2 *__restrict__ Ssum, int64_t pitch, int32_t M, DiscrParams P,
+                const StreamState *__restrict__ state, dcplx *__restrict__ tileB, int32_t ntiles,
+                DiscrSnap *__restrict__ snap) {
+__shared__ dcplx sWarp [kDiThreads / 32];
+const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+const int stream = blockIdx.y, tile = blockIdx.x;
+	if (tile == 0 && tid == 0) {
+	   const StreamState &st = state [stream];
+	   DiscrSnap q;
+	   q.dc_re = st.dc_re; q.dc_im = st.dc_im;
+	   q.sp1 = make_float2 (st.sprev [0], st.sprev [1]); q.sp2 = make_float2 (st.sprev [2], st.sprev [3]);
+	   q.p1 = make_float2 (st.Imin1, st.Qmin1); q.p2 = make_float2 (st.Imin2, st.Qmin2);
+	   snap [stream] = q;
+	}
+	if (!P.dc_remove || (int64_t)(tile + 1) * kDiBlock > M) return;      // only full tiles are predecessors
+const float2 *Ss = Ssum + (int64_t)stream * pitch + (int64_t)tile * kDiBlock + tid * kDiRun;
+double pw [5];
+	{  double b8 = P.beta; b8 *= b8; b8 *= b8; b8 *= b8; pw [0] = b8;
+#pragma unroll
+	   for (int k = 1; k < 5; k ++) pw [k] = pw [k - 1] * pw [k - 1]; }
+dcplx a; a.re = 0.0; a.im = 0.0;
+#pragma unroll
+	for (int j = 0; j < kDiRun; j ++) {
+	   const float2 s = Ss [j];
+	   a.re = a.re * P.beta + P.alpha * (double)s.x;
+	   a.im = a.im * P.beta + P.alpha * (double)s.y;
+	}
+#pragma unroll
+	for (int k = 0; k < 5; k ++) {
+	   dcplx y = shfl_up_d (a, 1 << k);
+	   if (lane >= (1 << k)) { a.re += y.re * pw [k]; a.im += y.im * pw [k]; }
+	}
+	if (lane == 31) sWarp [warp] = a;
+	__syncthreads ();
+	if (tid == 0) {
+	   const double pwarp = pw [4] * pw [4];              // beta^(8*32)
+	   dcplx w; w.re = 0.0; w.im = 0.0;
+	   for (int q = 0; q < kDiThreads / 32; q ++) { w.re = w.re * pwarp + sWarp [q].re; w.im = w.im * pwarp + sWarp [q].im; }
+	   tileB [(int64_t)stream * ntiles + tile] = w;
+	}
+}
+
+// one fm-rate sample: DC subtraction (free-running or clamped), gains / LO correction, constant
+// complex gain, magnitude, normalisation (fm-processor.cpp:423-446,462-466; fm-demodulator.cpp:119-126)
+__device__ __forceinline__ void disc_sample (const DiscrParams &P, float2 u, float2 s, float2 sm1, float2 sm2,
+                                             double rre, double rim, int64_t j,
+                                             float2 &z, float &za, float2 &nq) {
+float2 c = make_float2 (0.f, 0.f);
+	if (P.dc_remove) {
+	   const float lim = 0.01f;            // DCRlimit, fm-processor.cpp:429
+	   c.x = fminf (fmaxf ((float)rre, -lim), lim);
+	   c.y = fminf (fmaxf ((float)rim, -lim), lim);
+	}
+//	K1 ran the DC-folded taps C' = C + alpha g.  Free-running component: subtract r sum(C').
+//	Component on the clamp (or DC removal off): the subtracted value is the constant c, so take
+//	alpha sum_i g[i] x[n-i] back out via the 12-sample block sums.
+const float wx = P.gb0 * s.x + P.gb1 * sm1.x + P.gb2 * sm2.x;
+const float wy = P.gb0 * s.y + P.gb1 * sm1.y + P.gb2 * sm2.y;
+const bool freex = P.dc_remove && c.x == (float)rre;
+const bool freey = P.dc_remove && c.y == (float)rim;
+const float kx = freex ? c.x * P.sumCm : c.x * P.sumC + wx;
+const float ky = freey ? c.y * P.sumCm : c.y * P.sumC + wy;
+//	IQ gain (fm-processor.cpp:462-464) commutes with the real-tap FIR
+float vx = (u.x - kx) * P.lgain;
+float vy = (u.y - ky) * P.rgain;
+	if (P.lo_tab) {
+	   int64_t t = (P.lo_phase - (int64_t)P.lo_hz * (12 * (j + (int64_t)P.lo_moff) + 12)) % P.lo_rate;
+	   if (t < 0) t += P.lo_rate;
+	   const float2 o = P.lo_tab [t];
+	   const float2 a = make_float2 (c.x * P.lgain, c.y * P.rgain);
+	   const float2 b = make_float2 (a.x * o.x - a.y * o.y, a.x * o.y + a.y * o.x);
+	   vx = u.x - (b.x * P.Hre - b.y * P.Him);
+	   vy = u.y - (b.x * P.Him + b.y * P.Hre);
+	}
+	z = make_float2 (vx * P.Gre - vy * P.Gim, vx * P.Gim + vy * P.Gre);
+//	std::abs (complex<float>) = hypotf: evaluated through double (fm-demodulator.cpp:119)
+	za = (float)sqrt ((double)z.x * (double)z.x + (double)z.y * (double)z.y);
+	if ((double)za <= 0.001) nq = make_float2 (0.001f, 0.001f);   // :120-122
+	else nq = make_float2 (fdiv (z.x, za), fdiv (z.y, za));
+}
+
 // U, Ssum : front-end outputs; res_raw: discriminator output before AFC (float);
-// zabs: |z| ; fmz (optional): the fm-rate complex sample (tap after fmBand_2)
+// zabs: |z| ; fmz (optional): the fm-rate complex sample (tap after fmBand_2).
+// grid (tiles of kDiBlock samples, streams): every tile is independent given the snapshot and
+// the tile aggregates of the DC one-pole.
 __global__ void __launch_bounds__ (kDiThreads)
 discriminator_kernel (const float2 *__restrict__ U, const float2 *__restrict__ Ssum,
                       int64_t pitch, int32_t M, DiscrParams P,
                       const float *__restrict__ atanPPY, const float *__restrict__ arcsine,
-                      StreamState *__restrict__ state,
+                      StreamState *__restrict__ state, const dcplx *__restrict__ tileB, int32_t ntiles,
+                      const DiscrSnap *__restrict__ snap,
                       float *__restrict__ res_raw, float *__restrict__ zabs,
                       float2 *__restrict__ iqn, float2 *__restrict__ fmz) {
 __shared__ float  sPPY [8193 + 3];
@@ -89,31 +184,49 @@ __shared__ float2 sLastIQ [kDiThreads + 1];
 __shared__ float2 sLastIQ2 [kDiThreads + 1];
 __shared__ dcplx  sCarry;
 const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-const int stream = blockIdx.x;
+const int stream = blockIdx.y, tile = blockIdx.x;
 StreamState &st = state [stream];
 const float2 *Us = U + (int64_t)stream * pitch;
 const float2 *Ss = Ssum + (int64_t)stream * pitch;
+const DiscrSnap sn = snap [stream];
+const int64_t base = (int64_t)tile * kDiBlock;
 
-//	read before anything of this call can overwrite it
-const float2 sp1 = make_float2 (st.sprev [0], st.sprev [1]);
-const float2 sp2 = make_float2 (st.sprev [2], st.sprev [3]);
 	for (int i = tid; i < 8193; i += kDiThreads) sPPY [i] = atanPPY [i];
-	if (tid == 0) {
-	   sCarry.re = st.dc_re; sCarry.im = st.dc_im;
-	   sLastIQ [0]  = make_float2 (st.Imin1, st.Qmin1);
-	   sLastIQ2 [0] = make_float2 (st.Imin2, st.Qmin2);
-	}
 //	powers of beta used by the scan: pw[k] = beta^(8 * 2^k)
 double pw [6];
-	pw [0] = P.beta;
 	{  double b8 = P.beta; b8 *= b8; b8 *= b8; b8 *= b8;   // beta^8
 	   pw [0] = b8;
 #pragma unroll
 	   for (int k = 1; k < 6; k ++) pw [k] = pw [k - 1] * pw [k - 1];
 	}
+	if (tid == 0) {
+//	   DC estimate entering the tile: carried state pushed through the earlier (full) tiles
+	   dcplx r; r.re = sn.dc_re; r.im = sn.dc_im;
+	   if (P.dc_remove && tile > 0) {
+	      double pt = pw [5]; pt *= pt; pt *= pt; pt *= pt;           // beta^(8*32*8) = beta^2048
+	      for (int q = 0; q < tile; q ++) {
+	         const dcplx b = tileB [(int64_t)stream * ntiles + q];
+	         r.re = r.re * pt + b.re; r.im = r.im * pt + b.im;
+	      }
+	   }
+	   sCarry = r;
+//	   the two normalised samples before the tile
+	   if (tile == 0) { sLastIQ [0] = sn.p1; sLastIQ2 [0] = sn.p2; }
+	   else {
+	      const float2 s1 = Ss [base - 1], s2 = Ss [base - 2], s3 = Ss [base - 3];
+	      const float2 s4 = base >= 4 ? Ss [base - 4] : sn.sp1;
+	      // r after sample base-1 is the carry; one step back for sample base-2
+	      const double r2re = P.dc_remove ? (r.re - P.alpha * (double)s1.x) / P.beta : 0.0;
+	      const double r2im = P.dc_remove ? (r.im - P.alpha * (double)s1.y) / P.beta : 0.0;
+	      float2 z, n1, n2; float za;
+	      disc_sample (P, Us [base - 1], s1, s2, s3, r.re, r.im, base - 1, z, za, n1);
+	      disc_sample (P, Us [base - 2], s2, s3, s4, r2re, r2im, base - 2, z, za, n2);
+	      sLastIQ [0] = n1; sLastIQ2 [0] = n2;
+	   }
+	}
 	__syncthreads ();
 
-	for (int64_t base = 0; base < M; base += kDiBlock) {
+	{
 	   const int64_t j0 = base + (int64_t)tid * kDiRun;
 	   float2 u [kDiRun], s [kDiRun];
 #pragma unroll
@@ -142,13 +255,11 @@ double pw [6];
 //	start value of this thread = carry decayed to the thread + all earlier threads
 	   dcplx r;
 	   {
-	      // contributions of earlier warps, each decayed by beta^(8*32) per warp of distance
-	      dcplx w; w.re = sCarry.re; w.im = sCarry.im;   // value at block start
+	      dcplx w; w.re = sCarry.re; w.im = sCarry.im;   // value at tile start
 	      for (int q = 0; q < warp; q ++) {
 	         w.re = w.re * pw [5] + sWarp [q].re;
 	         w.im = w.im * pw [5] + sWarp [q].im;
 	      }
-	      // decay from warp start to this thread's start: beta^(8*lane)
 	      double dl = 1.0;
 #pragma unroll
 	      for (int k = 0; k < 5; k ++) if (lane & (1 << k)) dl *= pw [k];
@@ -159,55 +270,23 @@ double pw [6];
 	   }
 	   // block sums of the two fm-rate samples before this thread's run (for the clamped case)
 	   float2 sm1, sm2;
-	   sm1 = (j0 >= 1 && j0 - 1 < M) ? Ss [j0 - 1] : sp1;
-	   sm2 = (j0 >= 2 && j0 - 2 < M) ? Ss [j0 - 2] : (j0 == 1 ? sp1 : sp2);
+	   sm1 = (j0 >= 1 && j0 - 1 < M) ? Ss [j0 - 1] : sn.sp1;
+	   sm2 = (j0 >= 2 && j0 - 2 < M) ? Ss [j0 - 2] : (j0 == 1 ? sn.sp1 : sn.sp2);
 //	-- per-sample: corrected, gained, normalised sample ------------------------------
 	   float2 z [kDiRun], nq [kDiRun];
 	   float  za [kDiRun];
 #pragma unroll
 	   for (int j = 0; j < kDiRun; j ++) {
-	      float2 c = make_float2 (0.f, 0.f);
 	      if (P.dc_remove) {
 	         r.re = r.re * P.beta + P.alpha * (double)s [j].x;
 	         r.im = r.im * P.beta + P.alpha * (double)s [j].y;
-	         const float lim = 0.01f;            // DCRlimit, fm-processor.cpp:429
-	         c.x = fminf (fmaxf ((float)r.re, -lim), lim);
-	         c.y = fminf (fmaxf ((float)r.im, -lim), lim);
-	         if (j0 + j == M - 1) {             // state handed to the next call
-	            st.dc_re = r.re; st.dc_im = r.im;
-	         }
+	         if (j0 + j == M - 1) { st.dc_re = r.re; st.dc_im = r.im; }    // state handed to the next call
 	      }
-	      // K1 ran the DC-folded taps C' = C + alpha g.  Free-running component: subtract
-	      // r sum(C').  Component on the clamp (or DC removal off): the subtracted value is the
-	      // constant c, so take alpha sum_i g[i] x[n-i] back out via the 12-sample block sums.
-	      const float wx = P.gb0 * s [j].x + P.gb1 * sm1.x + P.gb2 * sm2.x;
-	      const float wy = P.gb0 * s [j].y + P.gb1 * sm1.y + P.gb2 * sm2.y;
-	      const bool freex = P.dc_remove && c.x == (float)r.re;
-	      const bool freey = P.dc_remove && c.y == (float)r.im;
-	      const float kx = freex ? c.x * P.sumCm : c.x * P.sumC + wx;
-	      const float ky = freey ? c.y * P.sumCm : c.y * P.sumC + wy;
+	      disc_sample (P, u [j], s [j], sm1, sm2, r.re, r.im, j0 + j, z [j], za [j], nq [j]);
 	      sm2 = sm1; sm1 = s [j];
 	      if (j0 + j == M - 1) {
 	         st.sprev [0] = sm1.x; st.sprev [1] = sm1.y; st.sprev [2] = sm2.x; st.sprev [3] = sm2.y;
 	      }
-	      // IQ gain (fm-processor.cpp:462-464) commutes with the real-tap FIR
-	      float vx = (u [j].x - kx) * P.lgain;
-	      float vy = (u [j].y - ky) * P.rgain;
-	      if (P.lo_tab) {
-	         int64_t t = (P.lo_phase - (int64_t)P.lo_hz * (12 * (j0 + j + (int64_t)P.lo_moff) + 12)) % P.lo_rate;
-	         if (t < 0) t += P.lo_rate;
-	         const float2 o = P.lo_tab [t];
-	         const float2 a = make_float2 (c.x * P.lgain, c.y * P.rgain);
-	         const float2 b = make_float2 (a.x * o.x - a.y * o.y, a.x * o.y + a.y * o.x);
-	         vx = u [j].x - (b.x * P.Hre - b.y * P.Him);
-	         vy = u [j].y - (b.x * P.Him + b.y * P.Hre);
-	      }
-	      z [j] = make_float2 (vx * P.Gre - vy * P.Gim, vx * P.Gim + vy * P.Gre);
-	      // std::abs (complex<float>) = hypotf: evaluated through double (fm-demodulator.cpp:119)
-	      za [j] = (float)sqrt ((double)z [j].x * (double)z [j].x +
-	                            (double)z [j].y * (double)z [j].y);
-	      if ((double)za [j] <= 0.001) nq [j] = make_float2 (0.001f, 0.001f);   // :120-122
-	      else nq [j] = make_float2 (fdiv (z [j].x, za [j]), fdiv (z [j].y, za [j]));
 	   }
 //	hand the last normalised samples to the next thread
 	   sLastIQ [tid + 1]  = nq [kDiRun - 1];
@@ -255,13 +334,6 @@ double pw [6];
 	         if (fmz) fmz [o] = z [j];
 	      }
 	   }
-//	-- block carry (only full blocks are followed by another block) ------------------
-	   __syncthreads ();
-	   if (tid == kDiThreads - 1) {
-	      sCarry.re = r.re; sCarry.im = r.im;
-	      sLastIQ [0] = nq [kDiRun - 1]; sLastIQ2 [0] = nq [kDiRun - 2];
-	   }
-	   __syncthreads ();
 	}
 }
 

@@ -83,9 +83,10 @@ struct Lane {
 	// RDS branch (allocated when RDS is first switched on)
 	float   *d_rds_dring = nullptr, *d_rds_pring = nullptr;     // [S][131072] demod / pilot phase by rds index
 	float   *d_rds_bp = nullptr, *d_rds_hi = nullptr;           // [S][2][32000] / [S][2][32768]
-	float2  *d_rds_R = nullptr, *d_rds_tw = nullptr, *d_rds_dtaps = nullptr;
+	float2  *d_rds_R = nullptr, *d_rds_tw = nullptr, *d_rds_tws = nullptr, *d_rds_dtaps = nullptr;
 	float2  *d_rds_hist [2] = { nullptr, nullptr }; int rds_hist_sel = 0;
 	int64_t  rds_total = 0, rds_last_block = -1;
+	dcplx   *d_tileB = nullptr; DiscrSnap *d_snap = nullptr; int32_t ntiles_cap = 0;   // K2 pre-pass
 	float2  *d_pss_ring = nullptr;          // [S][2048] PSS filter input ring (state)
 	int32_t *d_iter_stats = nullptr;        // pilot_kernel diagnostics: [S][4]
 	bool    pilot_lut_smem = false;         // SDRJFM_PILOT_LUT_SMEM=1: sine table in shared memory, 1 CTA/SM
@@ -274,6 +275,7 @@ const TableHeader &th = h -> tables.hdr ();
 	   CK (dalloc (&h -> d_rds_hist [1], (size_t)S * (kRdsDecTaps - 1)));
 	   CK (dalloc (&h -> d_rds_R, (size_t)kRdsNh + 1));
 	   CK (dalloc (&h -> d_rds_tw, (size_t)kRdsNh));
+	   CK (dalloc (&h -> d_rds_tws, (size_t)kRdsNh));
 	   CK (dalloc (&h -> d_rds_dtaps, (size_t)kRdsDecTaps));
 	   CK (cudaFuncSetAttribute (rds_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRdsFftSmem));
 //	rdsBandPassFilter.setBand (RDS_FREQUENCY -+ RDS_WIDTH / 2, fmRate), fm-processor.cpp:166-168; Pass (float)
@@ -292,6 +294,13 @@ const TableHeader &th = h -> tables.hdr ();
 	   for (int k = 0; k < kRdsNh; k ++) tw [k] = make_float2 ((float)w [k].real (), (float)w [k].imag ());
 	   CK (cudaMemcpy (h -> d_rds_R, R.data (), R.size () * sizeof (float2), cudaMemcpyHostToDevice));
 	   CK (cudaMemcpy (h -> d_rds_tw, tw.data (), tw.size () * sizeof (float2), cudaMemcpyHostToDevice));
+	   std::vector<float2> tws (kRdsNh, make_float2 (1.f, 0.f));      // tws[half + pos] = exp (-2 pi i pos / (2 half))
+	   for (int half = 1; half <= kRdsNh / 2; half <<= 1)
+	      for (int pos = 0; pos < half; pos ++) {
+	         const std::complex<double> v = w [(int)((int64_t)pos * (kRdsN / 2) / half) & (kRdsN - 1)];   // exp(-2 pi i pos/(2 half))
+	         tws [half + pos] = make_float2 ((float)v.real (), (float)v.imag ());
+	      }
+	   CK (cudaMemcpy (h -> d_rds_tws, tws.data (), tws.size () * sizeof (float2), cudaMemcpyHostToDevice));
 	   CK (cudaMemcpy (h -> d_rds_dtaps, h -> tables.payload () + th.off_rdsdecim,
 	                   kRdsDecTaps * sizeof (float2), cudaMemcpyHostToDevice));
 	}
@@ -366,6 +375,8 @@ cudaError_t e;
 	AL (d_audio, S * h -> cap_audio);
 	AL (d_state, S);
 	AL (d_iter_stats, S * 4);
+	h -> ntiles_cap = (int32_t)((h -> cap_fm + kDiBlock - 1) / kDiBlock);
+	AL (d_tileB, S * h -> ntiles_cap); AL (d_snap, S);
 	AL (d_pss_ring, S * kPssRing);
 #undef AL
 	{  // initial member values of the reference objects
@@ -406,9 +417,9 @@ void *ptrs [] = { h -> d_tables, h -> d_sin_quarter, h -> d_in, h -> d_hist [0],
 	              h -> d_pend, h -> d_U, h -> d_S, h -> d_iqn, h -> d_fmz, h -> d_res, h -> d_zabs,
 	              h -> d_demod, h -> d_phase, h -> d_pssd, h -> d_locked, h -> d_lr, h -> d_a192,
 	              h -> d_rdsc, h -> d_rds24, h -> d_ahist [0], h -> d_ahist [1], h -> d_audio,
-	              h -> d_state, h -> d_iter_stats, h -> d_pss_ring,
+	              h -> d_state, h -> d_iter_stats, h -> d_pss_ring, h -> d_tileB, h -> d_snap,
 	              h -> d_rds_dring, h -> d_rds_pring, h -> d_rds_bp, h -> d_rds_hi, h -> d_rds_R, h -> d_rds_tw,
-	              h -> d_rds_dtaps, h -> d_rds_hist [0], h -> d_rds_hist [1],
+	              h -> d_rds_dtaps, h -> d_rds_tws, h -> d_rds_hist [0], h -> d_rds_hist [1],
 	              h -> d_histw [0], h -> d_histw [1], h -> d_Uw, h -> d_Sw, h -> d_udel [0], h -> d_udel [1],
 	              h -> d_sdel [0], h -> d_sdel [1], h -> d_alp_hist [0], h -> d_alp_hist [1], h -> d_lrf, h -> d_lo_tab };
 	for (void *p : ptrs) if (p) cudaFree (p);
@@ -547,10 +558,17 @@ DiscrParams dp;
 	dp.beta = pow (1.0 - dp.alpha, (double)kDecim);
 	dp.lgain = st.lgain; dp.rgain = st.rgain;
 	dp.dc_remove = st.dc_remove; dp.decoder = st.decoder;
-	discriminator_kernel<<<S, kDiThreads, 0, h -> stream>>> (
-	      h -> d_U, h -> d_S, h -> cap_fm, M, dp, T + th.off_atan, T + th.off_arcsine,
-	      h -> d_state, h -> d_res, h -> d_zabs, h -> d_iqn, h -> d_fmz);
-	h -> launches ++;
+const int32_t ntiles = (M + kDiBlock - 1) / kDiBlock;
+	{
+	   dim3 g ((unsigned)ntiles, (unsigned)S);
+	   dc_tile_kernel<<<g, kDiThreads, 0, h -> stream>>> (h -> d_S, h -> cap_fm, M, dp, h -> d_state,
+	                                                       h -> d_tileB, ntiles, h -> d_snap);
+	   discriminator_kernel<<<g, kDiThreads, 0, h -> stream>>> (
+	         h -> d_U, h -> d_S, h -> cap_fm, M, dp, T + th.off_atan, T + th.off_arcsine,
+	         h -> d_state, h -> d_tileB, ntiles, h -> d_snap, h -> d_res, h -> d_zabs,
+	         st.decoder == 2 ? h -> d_iqn : nullptr, h -> cfg.keep_taps ? h -> d_fmz : nullptr);
+	   h -> launches += 2;
+	}
 //	K3 ------------------------------------------------------------------------------------
 SeqParams sp;
 	sp.K_FM = consts [4];
@@ -618,7 +636,7 @@ const size_t seq_smem = (h -> lut.quarter + 1) * sizeof (float);
 	      h -> launches ++;
 	      if (K >= 1 && h -> rds_last_block < K - 1) {
 	         rds_block_kernel<<<S, kRdsThreads, kRdsFftSmem, h -> stream>>> (
-	               h -> d_rds_dring, K - 1, h -> d_rds_tw, h -> d_rds_R, h -> d_rds_bp, h -> d_rds_hi);
+	               h -> d_rds_dring, K - 1, h -> d_rds_tw, h -> d_rds_tws, h -> d_rds_R, h -> d_rds_bp, h -> d_rds_hi);
 	         h -> launches ++;
 	         h -> rds_last_block = K - 1;
 	      }

@@ -111,6 +111,31 @@ const float p1 = fadd (phi, fmul (fmul (pilot, osc), gain));
 	return pi_constrain (fadd (p1, omega));
 }
 
+// The same step for the segment walk: phi is known to lie in [0, 2 pi] (it is a pi_constrain or
+// wrap_2pi result), only the next phase is wanted, and the derivative is accumulated to first
+// order (sum of x cos phi).  Bit-identical to pilot_step for such phi.
+__device__ __forceinline__ float pilot_walk_step (const SinLut &L, const float *q, float phi, float pilot,
+                                                  float gain, float omega, float &dsum) {
+constexpr int32_t Q = kFmRate / 4, H = 2 * Q;
+const float kTwoPiF = 6.2831855f;
+int32_t i = (int32_t)((double)phi * (kFmRate / (2 * M_PI)));     // SinCos::fromPhasetoIndex, Phase >= 0
+	if (i >= kFmRate) i -= kFmRate;
+const bool neg = i >= H;
+int32_t k = neg ? i - H : i;
+	k = k > Q ? H - k : k;
+float v = q [k];
+	v = neg ? -v : v;
+	if (k == 0 && i != 0) {                      // the zero crossings: patched from the exception list
+#pragma unroll
+	   for (int e = 0; e < kMaxSinExc; e ++) if (i == L.sin_exc_idx [e]) v = L.sin_exc_val [e];
+	}
+	dsum = fmaf (pilot, __cosf (phi), dsum);
+float p2 = fadd (fadd (phi, fmul (fmul (pilot, v), gain)), omega);
+	if (p2 >= kTwoPiF) p2 = (float)((double)p2 - 2 * M_PI);     // PI_Constrain: fmod (v, 2 pi), v < 4 pi
+	else if (p2 < 0.f) p2 = pi_constrain (p2);                  // cannot happen for |pilot| < 1000
+	return p2;
+}
+
 __device__ __forceinline__ float wrap_2pi (double v) {          // any double -> float in [0, 2 pi]
 	v -= 2 * M_PI * floor (v * (1.0 / (2 * M_PI)));
 float f = (float)v;
@@ -206,94 +231,80 @@ int    itTotal = 0, itMax = 0, nFallback = 0;
 	   int it = 0;
 	   bool converged = false;
 	   for (; it < kPiMaxIter; it ++) {
-//	   anchors: sample 0, and the first sample of every run of est inside [4.6, 5.3)
-	      unsigned flags = 0;
-	      {
-	         bool prevIn = false;
-	         if (n0 > 0 && n0 - 1 < Tw) { const float e = S.est [n0 - 1]; prevIn = e >= 4.6f && e < 5.3f; }
+//	   anchors: sample 0, and the first sample of every run of est inside [4.6, 5.3).  They only
+//	   depend on the estimate to ~0.05 rad, so they are refreshed at iterations 0, 4, 8 and 16.
+	      if (it == 0 || it == 4 || it == 8 || it == 16) {
+	         unsigned flags = 0;
+	         {
+	            bool prevIn = false;
+	            if (n0 > 0 && n0 - 1 < Tw) { const float e = S.est [n0 - 1]; prevIn = e >= 4.6f && e < 5.3f; }
 #pragma unroll
-	         for (int j = 0; j < kPiPer; j ++) {
-	            bool in = false;
-	            if (n0 + j < Tw) { const float e = S.est [n0 + j]; in = e >= 4.6f && e < 5.3f; }
-	            if ((in && !prevIn && n0 + j > 0) || (n0 + j == 0)) flags |= 1u << j;
-	            prevIn = in;
+	            for (int j = 0; j < kPiPer; j ++) {
+	               bool in = false;
+	               if (n0 + j < Tw) { const float e = S.est [n0 + j]; in = e >= 4.6f && e < 5.3f; }
+	               if ((in && !prevIn && n0 + j > 0) || (n0 + j == 0)) flags |= 1u << j;
+	               prevIn = in;
+	            }
 	         }
-	      }
-	      int cnt = __popc (flags);
-	      int inc = cnt;
+	         int cnt = __popc (flags);
+	         int inc = cnt;
 #pragma unroll
-	      for (int k = 1; k < 32; k <<= 1) {
-	         const int y = __shfl_up_sync (0xffffffffu, inc, k);
-	         if (lane >= k) inc += y;
-	      }
-	      if (lane == 31) S.warpI [warp] = inc;
-	      __syncthreads ();
-	      int off = inc - cnt;
-	      for (int q = 0; q < warp; q ++) off += S.warpI [q];
-	      if (tid == kPiThreads - 1) {
-	         S.nseg = off + cnt;
-	         S.overflow = (off + cnt > kPiMaxSeg);
-	      }
+	         for (int k = 1; k < 32; k <<= 1) {
+	            const int y = __shfl_up_sync (0xffffffffu, inc, k);
+	            if (lane >= k) inc += y;
+	         }
+	         if (lane == 31) S.warpI [warp] = inc;
+	         __syncthreads ();
+	         int off = inc - cnt;
+	         for (int q = 0; q < warp; q ++) off += S.warpI [q];
+	         if (tid == kPiThreads - 1) {
+	            S.nseg = off + cnt;
+	            S.overflow = (off + cnt > kPiMaxSeg);
+	         }
 #pragma unroll
-	      for (int j = 0; j < kPiPer; j ++)
-	         if ((flags >> j) & 1u) { if (off < kPiMaxSeg) S.anc [off] = (int16_t)(n0 + j); off ++; }
-	      __syncthreads ();
-	      if (S.overflow) break;
+	         for (int j = 0; j < kPiPer; j ++)
+	            if ((flags >> j) & 1u) { if (off < kPiMaxSeg) S.anc [off] = (int16_t)(n0 + j); off ++; }
+	         __syncthreads ();
+	         if (S.overflow) break;
+	      }
 	      const int nseg = S.nseg;
-//	   advance every segment with the exact reference arithmetic
+//	   advance every segment with the exact reference arithmetic; a segment is consistent when it
+//	   ends bit-exactly on the value the next segment starts from
 	      int bad = 0;
 	      for (int c = tid; c < nseg; c += kPiThreads) {
 	         const int a0 = S.anc [c];
 	         const int a1 = (c + 1 < nseg) ? (int)S.anc [c + 1] : Tw;
 	         float p = S.est [a0];
-	         float d = 1.0f;
+	         float dsum = 0.0f;
 	         for (int n = a0; n < a1; n ++) {
-	            const float xv = S.x [n];
 	            if (n > a0) S.est [n] = p;
-	            float osc, cur;
-	            const float pn = pilot_step (L, sq, p, xv, P.gain, P.omega, osc, cur);
-	            d *= 1.0f + P.gain * xv * __cosf (p);
-	            p = pn;
+	            p = pilot_walk_step (L, sq, p, S.x [n], P.gain, P.omega, dsum);
 	         }
-	         S.G [c] = p; S.der [c] = d;
-	      }
-	      __syncthreads ();
-	      for (int c = tid; c < nseg; c += kPiThreads) {
+	         S.G [c] = p;
+	         S.der [c] = fmaf (P.gain, dsum, 1.0f);      // d(end)/d(start) to first order
 	         double rs = 0.0;
 	         if (c + 1 < nseg) {
-	            const float nextP = S.est [S.anc [c + 1]];
-	            if (nextP != S.G [c]) { bad = 1; rs = (double)S.G [c] - (double)nextP; }
+	            const float nextP = S.est [a1];          // only its owner's walk reads it; nobody writes it here
+	            if (nextP != p) { bad = 1; rs = (double)p - (double)nextP; }
 	         }
 	         S.resid [c] = rs;
 	      }
 	      const int nbad = __syncthreads_count (bad);
 	      if (nbad == 0) { converged = true; break; }
-//	   Newton correction of the anchors: delta[c+1] = resid[c] + der[c] delta[c], delta[0] = 0
-	      if (warp == 0) {
-	         const int per = (nseg + 31) / 32;                // segments per lane
-	         const int c0 = lane * per;
-	         double A = 1.0, B = 0.0;                         // lane's composite map
-	         for (int c = c0; c < min (c0 + per, nseg); c ++) { B = S.resid [c] + (double)S.der [c] * B; A *= (double)S.der [c]; }
-#pragma unroll
-	         for (int k = 1; k < 32; k <<= 1) {
-	            const double Ay = __shfl_up_sync (0xffffffffu, A, k);
-	            const double By = __shfl_up_sync (0xffffffffu, B, k);
-	            if (lane >= k) { B = B + A * By; A = A * Ay; }
-	         }
-	         double dIn = __shfl_up_sync (0xffffffffu, B, 1);  // delta entering this lane's first segment
-	         if (lane == 0) dIn = 0.0;
-	         for (int c = c0; c < min (c0 + per, nseg); c ++) {
-	            S.delta [c] = dIn;
+//	   Newton correction of the anchors: delta[c+1] = resid[c] + der[c] delta[c], delta[0] = 0,
+//	   as a block-wide scan of affine maps (thread t owns segments per*t .. per*t + per - 1)
+	      {
+	         const int per = (nseg + kPiThreads - 1) / kPiThreads;
+	         const int c0 = tid * per, c1 = min (c0 + per, nseg);
+	         double A = 1.0, B = 0.0;
+	         for (int c = c0; c < c1; c ++) { B = S.resid [c] + (double)S.der [c] * B; A *= (double)S.der [c]; }
+	         double dIn = block_affine_start (A, B, 0.0, S.warpA, S.warpB, nullptr);
+	         for (int c = c0; c < c1; c ++) {
+	            if (c > 0 && dIn != 0.0) {
+	               const int a0 = S.anc [c];
+	               S.est [a0] = wrap_2pi ((double)S.est [a0] + dIn);
+	            }
 	            dIn = S.resid [c] + (double)S.der [c] * dIn;
-	         }
-	      }
-	      __syncthreads ();
-	      for (int c = tid; c < nseg; c += kPiThreads) {
-	         const double dl = S.delta [c];
-	         if (dl != 0.0 && c > 0) {
-	            const int a0 = S.anc [c];
-	            const int a1 = (c + 1 < nseg) ? (int)S.anc [c + 1] : Tw;
-	            for (int n = a0; n < a1; n ++) S.est [n] = wrap_2pi ((double)S.est [n] + dl);
 	         }
 	      }
 	      __syncthreads ();

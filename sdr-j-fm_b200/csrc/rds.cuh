@@ -41,32 +41,51 @@ __device__ __forceinline__ float2 cmulf (float2 a, float2 b) {
 __device__ __forceinline__ float2 cconj (float2 a) { return make_float2 (a.x, -a.y); }
 __device__ __forceinline__ int brev14 (int k) { return (int)(__brev ((unsigned)k) >> 18); }
 
-// in-place radix-2 FFTs of length kRdsNh in shared memory; tw[k] = exp (-2 pi i k / kRdsN), k < kRdsNh
+// in-place radix-2 FFTs of length kRdsNh in shared memory.  tws = per-stage twiddle table:
+// tws[half + pos] = exp (-2 pi i pos / (2 half)), pos < half  (kRdsNh entries, coalesced per stage).
+// Every thread first loads the operands and twiddles of all its butterflies of a stage, then
+// computes, then stores, so the shared/global load latencies overlap instead of serialising.
+constexpr int kRdsBpt = kRdsNh / 2 / kRdsThreads;       // butterflies per thread per stage (8)
+
 // forward: decimation in frequency, natural order in -> bit-reversed order out
-__device__ void fft_dif (float2 *a, const float2 *__restrict__ tw) {
+__device__ void fft_dif (float2 *a, const float2 *__restrict__ tws) {
 	for (int half = kRdsNh / 2; half >= 1; half >>= 1) {
-	   const int tstep = kRdsNh / half;                 // table index step: W_Nh^(pos Nh/(2 half)) = W_N^(pos Nh/half)
-	   for (int b = threadIdx.x; b < kRdsNh / 2; b += kRdsThreads) {
+	   float2 u [kRdsBpt], v [kRdsBpt], w [kRdsBpt];
+	   int idx [kRdsBpt];
+#pragma unroll
+	   for (int q = 0; q < kRdsBpt; q ++) {
+	      const int b = threadIdx.x + q * kRdsThreads;
 	      const int pos = b & (half - 1);
-	      const int i = ((b - pos) << 1) + pos, j = i + half;
-	      const float2 u = a [i], v = a [j];
-	      a [i] = make_float2 (u.x + v.x, u.y + v.y);
-	      a [j] = cmulf (make_float2 (u.x - v.x, u.y - v.y), tw [pos * tstep]);
+	      idx [q] = ((b - pos) << 1) + pos;
+	      u [q] = a [idx [q]]; v [q] = a [idx [q] + half];
+	      w [q] = __ldg (tws + half + pos);
+	   }
+#pragma unroll
+	   for (int q = 0; q < kRdsBpt; q ++) {
+	      a [idx [q]] = make_float2 (u [q].x + v [q].x, u [q].y + v [q].y);
+	      a [idx [q] + half] = cmulf (make_float2 (u [q].x - v [q].x, u [q].y - v [q].y), w [q]);
 	   }
 	   __syncthreads ();
 	}
 }
 // inverse: decimation in time with conjugate twiddles, bit-reversed order in -> natural order out
-__device__ void ifft_dit (float2 *a, const float2 *__restrict__ tw) {
+__device__ void ifft_dit (float2 *a, const float2 *__restrict__ tws) {
 	for (int half = 1; half <= kRdsNh / 2; half <<= 1) {
-	   const int tstep = kRdsNh / half;
-	   for (int b = threadIdx.x; b < kRdsNh / 2; b += kRdsThreads) {
+	   float2 u [kRdsBpt], v [kRdsBpt], w [kRdsBpt];
+	   int idx [kRdsBpt];
+#pragma unroll
+	   for (int q = 0; q < kRdsBpt; q ++) {
+	      const int b = threadIdx.x + q * kRdsThreads;
 	      const int pos = b & (half - 1);
-	      const int i = ((b - pos) << 1) + pos, j = i + half;
-	      const float2 t = cmulf (a [j], cconj (tw [pos * tstep]));
-	      const float2 u = a [i];
-	      a [i] = make_float2 (u.x + t.x, u.y + t.y);
-	      a [j] = make_float2 (u.x - t.x, u.y - t.y);
+	      idx [q] = ((b - pos) << 1) + pos;
+	      u [q] = a [idx [q]]; v [q] = a [idx [q] + half];
+	      w [q] = __ldg (tws + half + pos);
+	   }
+#pragma unroll
+	   for (int q = 0; q < kRdsBpt; q ++) {
+	      const float2 t = cmulf (v [q], cconj (w [q]));
+	      a [idx [q]] = make_float2 (u [q].x + t.x, u [q].y + t.y);
+	      a [idx [q] + half] = make_float2 (u [q].x - t.x, u [q].y - t.y);
 	   }
 	   __syncthreads ();
 	}
@@ -119,10 +138,11 @@ __device__ void spectrum_pass (float2 *a, const float2 *__restrict__ tw, const f
 
 // dring : [S][kRdsRing] demod by rds sample index (ring);  blk: Hilbert block index k >= 0
 // bpb   : [S][2][32000] band-pass block (slot k & 1);  hib : [S][2][32768] its Hilbert transform
-// R     : kRdsNh + 1 complex, spectrum of 3 r[j] scaled by 1/Nh;  tw: kRdsNh twiddles
+// R     : kRdsNh + 1 complex, spectrum of 3 r[j] scaled by 1/Nh;  tw: exp (-2 pi i k / N), k < Nh (spectrum
+//         pass);  tws: per-stage twiddles of the Nh-point transforms
 __global__ void __launch_bounds__ (kRdsThreads, 1)
 rds_block_kernel (const float *__restrict__ dring, int64_t blk,
-                  const float2 *__restrict__ tw, const float2 *__restrict__ R,
+                  const float2 *__restrict__ tw, const float2 *__restrict__ tws, const float2 *__restrict__ R,
                   float *__restrict__ bpb, float *__restrict__ hib) {
 extern __shared__ __align__ (16) float2 fa [];
 const int tid = threadIdx.x;
@@ -139,9 +159,9 @@ const int64_t base = (blk - 1) * (int64_t)kRdsBlock - (kRdsTaps - 1);   // rds i
 	   fa [m] = make_float2 (v0, v1);
 	}
 	__syncthreads ();
-	fft_dif (fa, tw);
+	fft_dif (fa, tws);
 	spectrum_pass<false> (fa, tw, R);
-	ifft_dit (fa, tw);
+	ifft_dit (fa, tws);
 //	valid outputs c[767 + i], i < 32000 -> bp block; re-pack zero-padded for the Hilbert pass
 float2 z [kRdsNh / kRdsThreads];
 #pragma unroll
@@ -159,9 +179,9 @@ float2 z [kRdsNh / kRdsThreads];
 	   if (2 * m < kRdsBlock) reinterpret_cast<float2 *>(bpo) [m] = z [q];
 	}
 	__syncthreads ();
-	fft_dif (fa, tw);
+	fft_dif (fa, tws);
 	spectrum_pass<true> (fa, tw, R);
-	ifft_dit (fa, tw);
+	ifft_dit (fa, tws);
 	for (int m = tid; m < kRdsNh; m += kRdsThreads) reinterpret_cast<float2 *>(hio) [m] = fa [m];
 }
 
