@@ -149,8 +149,7 @@ float2 *tap = a192 ? a192 + (int64_t)stream * pitch : nullptr;
 	      for (int j = 0; 4 * j + ph < kRsTaps; j ++) {
 	         const float2 v = col [k - j];
 	         const float c = c_rs_taps [4 * j + ph];
-	         acc.x = fmaf (c, v.x, acc.x);
-	         acc.y = fmaf (c, v.y, acc.y);
+	         acc = ffma2 (c, v, acc);
 	      }
 	   }
 	   const int64_t q = g >> 2;                                     // global output index
@@ -210,8 +209,7 @@ float2 w [kAlpPer];
 	   const float c = c_alp_taps [j];
 #pragma unroll
 	   for (int k = 0; k < kAlpPer; k ++) {
-	      acc [k].x = fmaf (c, w [k].x, acc [k].x);
-	      acc [k].y = fmaf (c, w [k].y, acc [k].y);
+	      acc [k] = ffma2 (c, w [k], acc [k]);
 	   }
 #pragma unroll
 	   for (int k = kAlpPer - 1; k > 0; k --) w [k] = w [k - 1];

@@ -21,6 +21,19 @@ __device__ __forceinline__ float fadd (float a, float b) { return __fadd_rn (a, 
 __device__ __forceinline__ float fsub (float a, float b) { return __fsub_rn (a, b); }
 __device__ __forceinline__ float fdiv (float a, float b) { return __fdiv_rn (a, b); }
 
+// Blackwell packed FP32: one FFMA2 instruction does acc.{x,y} = c * w.{x,y} + acc.{x,y} (two fma.rn,
+// the scalar tap is broadcast).  Real taps times complex samples is the shape of every FIR here.
+__device__ __forceinline__ float2 ffma2 (float c, float2 w, float2 acc) {
+unsigned long long a, b, d, r;
+	asm ("mov.b64 %0, {%1,%2};" : "=l"(a) : "f"(c), "f"(c));
+	asm ("mov.b64 %0, {%1,%2};" : "=l"(b) : "f"(w.x), "f"(w.y));
+	asm ("mov.b64 %0, {%1,%2};" : "=l"(d) : "f"(acc.x), "f"(acc.y));
+	asm ("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(d));
+float2 o;
+	asm ("mov.b64 {%0,%1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(r));
+	return o;
+}
+
 // std::complex<float> operator* as GCC emits it without -ffast-math: four products, each
 // rounded, then one subtraction and one addition.
 __device__ __forceinline__ float2 cmul_rn (float2 a, float2 b) {

@@ -132,22 +132,17 @@ const float2 *colc = sm + tid + 1;    // own column
 	   const float c0 = c_comp [11 - p], c1 = c_comp [23 - p], c2 = c_comp [35 - p];
 #pragma unroll
 	   for (int k = 0; k < kFeGpt; k ++) {
-	      acc [k].x = fmaf (c0, v [k + 2].x, acc [k].x);
-	      acc [k].y = fmaf (c0, v [k + 2].y, acc [k].y);
-	      acc [k].x = fmaf (c1, v [k + 1].x, acc [k].x);
-	      acc [k].y = fmaf (c1, v [k + 1].y, acc [k].y);
-	      acc [k].x = fmaf (c2, v [k].x, acc [k].x);
-	      acc [k].y = fmaf (c2, v [k].y, acc [k].y);
+	      acc [k] = ffma2 (c0, v [k + 2], acc [k]);
+	      acc [k] = ffma2 (c1, v [k + 1], acc [k]);
+	      acc [k] = ffma2 (c2, v [k], acc [k]);
 	      dcs [k].x += v [k + 2].x;
 	      dcs [k].y += v [k + 2].y;
 	   }
 	   if (p == kDecim - 1) {            // tap 36 reaches phase 11 three outputs back
 	      const float c3 = c_comp [36];
 	      const float2 w = colp [(12 + p) * kFePitch];
-	      acc [0].x = fmaf (c3, w.x, acc [0].x);      acc [0].y = fmaf (c3, w.y, acc [0].y);
-	      acc [1].x = fmaf (c3, v [0].x, acc [1].x);  acc [1].y = fmaf (c3, v [0].y, acc [1].y);
-	      acc [2].x = fmaf (c3, v [1].x, acc [2].x);  acc [2].y = fmaf (c3, v [1].y, acc [2].y);
-	      acc [3].x = fmaf (c3, v [2].x, acc [3].x);  acc [3].y = fmaf (c3, v [2].y, acc [3].y);
+	      acc [0] = ffma2 (c3, w, acc [0]);      acc [1] = ffma2 (c3, v [0], acc [1]);
+	      acc [2] = ffma2 (c3, v [1], acc [2]);  acc [3] = ffma2 (c3, v [2], acc [3]);
 	   }
 	}
 
@@ -274,10 +269,8 @@ const float2 *col0 = sm + tid + kFwHalo;
 #pragma unroll
 	   for (int g = 0; g < kFwGroups; g ++) {
 	      const float c = c_wide [p][g];
-	      acc [3].x = fmaf (c, w3.x, acc [3].x); acc [3].y = fmaf (c, w3.y, acc [3].y);
-	      acc [2].x = fmaf (c, w2.x, acc [2].x); acc [2].y = fmaf (c, w2.y, acc [2].y);
-	      acc [1].x = fmaf (c, w1.x, acc [1].x); acc [1].y = fmaf (c, w1.y, acc [1].y);
-	      acc [0].x = fmaf (c, w0.x, acc [0].x); acc [0].y = fmaf (c, w0.y, acc [0].y);
+	      acc [3] = ffma2 (c, w3, acc [3]); acc [2] = ffma2 (c, w2, acc [2]);
+	      acc [1] = ffma2 (c, w1, acc [1]); acc [0] = ffma2 (c, w0, acc [0]);
 	      w3 = w2; w2 = w1; w1 = w0;
 	      if (g + 1 < kFwGroups) {
 	         const int q = -1 - g;                        // next older output index relative to 4t

@@ -395,13 +395,13 @@ cudaError_t e;
 	    (e = cudaFuncSetAttribute (sequential_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                               (cfg -> fm_rate / 4 + 1) * (int)sizeof (float))) != cudaSuccess)
 	   return fail (e, "smem attr K3");
-	if ((e = cudaFuncSetAttribute (pilot_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                               (int)kPiSmemBytes)) != cudaSuccess ||
-	    (e = cudaFuncSetAttribute (pilot_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                               (int)sizeof (PilotSmem))) != cudaSuccess ||
-	    (e = cudaFuncSetAttribute (pilot_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
-	                               25)) != cudaSuccess) return fail (e, "smem attr pilot");
-	{ const char *env = getenv ("SDRJFM_PILOT_LUT_SMEM"); h -> pilot_lut_smem = env && env [0] == '1'; }
+	if ((e = cudaFuncSetAttribute (pilot_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                               (int)sizeof (PilotSmem))) != cudaSuccess) return fail (e, "smem attr pilot");
+//	the variant with the sine table staged in shared memory only fits with small windows
+	{ const char *env = getenv ("SDRJFM_PILOT_LUT_SMEM");
+	  h -> pilot_lut_smem = env && env [0] == '1' && kPiSmemBytes <= 227 * 1024 &&
+	        cudaFuncSetAttribute (pilot_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                              (int)kPiSmemBytes) == cudaSuccess; }
 	{ const char *env = getenv ("SDRJFM_SEQUENTIAL_PLL"); h -> sequential_pll = env && env [0] == '1'; }
 int rc = rebuild_tables (h);
 	if (rc != SDRJFM_OK) { g_create_error = h -> err; *status = rc; lane_destroy (h); return nullptr; }

@@ -32,6 +32,7 @@ constexpr int kStBlock   = kStThreads * kStPer;   // 1536 <= 1753
 constexpr int kPssDelay  = 1753;                  // fftSize - filterDegree
 constexpr int kPssTaps   = 295;
 constexpr int kPssRing   = 2048;
+constexpr int kStMaxTrans = 32;
 
 __constant__ float c_pss_taps [kPssTaps + 1];     // LowPassFIR (295, 15000, fmRate) real taps
 
@@ -110,7 +111,8 @@ __shared__ float  sErr [kStBlock];              // raw re*im per sample of the b
 __shared__ float  sDel [kStBlock + 1];          // pilotDelayPSS BEFORE sample m (entry 0 = carry)
 __shared__ double sSa [kStThreads / 32], sSb [kStThreads / 32];
 __shared__ PssState sS;
-__shared__ int sLen, sPos;
+__shared__ int sLen, sPos, sNTrans;
+__shared__ int sTrans [kStMaxTrans];
 const int tid = threadIdx.x;
 const int stream = blockIdx.x;
 StreamState &st = state [stream];
@@ -129,19 +131,39 @@ float2 *ring = ring_g + (int64_t)stream * kPssRing;
 	}
 	__syncthreads ();
 
+//	positions where the lock flag changes (rare: typically one per station), found once for the
+//	whole call so that the block loop never waits on global memory for them
+	if (tid == 0) sNTrans = 0;
+	__syncthreads ();
+	for (int32_t m = tid + 1; m < M; m += kStThreads)
+	   if ((lk [m] != 0) != (lk [m - 1] != 0)) {
+	      const int slot = atomicAdd (&sNTrans, 1);
+	      if (slot < kStMaxTrans) sTrans [slot] = m;
+	   }
+	__syncthreads ();
+const int nTrans = sNTrans;                       // > kStMaxTrans: fall back to scanning per block
+bool curLock = M > 0 ? lk [0] != 0 : false;
+
 	for (int32_t p = 0; p < M; ) {
 //	-- category of the block: 0 not stereo-decoded, 1 locked stereo, 2 unlocked stereo -------
-	   const bool lock0 = lk [p] != 0;
+	   const bool lock0 = curLock;
 	   const int cat = (P.fm_mode != 2 && (lock0 || !P.auto_mono)) ? (lock0 ? 1 : 2) : 0;
 	   const int want = min (kStBlock, M - p);
-	   int firstDiff = want;
-	   for (int m = tid; m < want; m += kStThreads)
-	      if ((lk [p + m] != 0) != lock0) { firstDiff = m; break; }
-	   if (tid == 0) sLen = want;
-	   __syncthreads ();
-	   if (firstDiff < want) atomicMin (&sLen, firstDiff);
-	   __syncthreads ();
-	   const int len = sLen;
+	   int len = want;
+	   if (nTrans <= kStMaxTrans) {
+	      for (int i = 0; i < nTrans; i ++) { const int t = sTrans [i]; if (t > p && t - p < len) len = t - p; }
+	   }
+	   else {
+	      int firstDiff = want;
+	      for (int m = tid; m < want; m += kStThreads)
+	         if ((lk [p + m] != 0) != lock0) { firstDiff = m; break; }
+	      if (tid == 0) sLen = want;
+	      __syncthreads ();
+	      if (firstDiff < want) atomicMin (&sLen, firstDiff);
+	      __syncthreads ();
+	      len = sLen;
+	   }
+	   if (p + len < M) curLock = lk [p + len] != 0;    // (consumed one block later: latency hidden)
 	   const int m0 = tid * kStPer;
 	   const int pos = sPos;
 
@@ -184,8 +206,7 @@ float2 *ring = ring_g + (int64_t)stream * kPssRing;
 #pragma unroll
 	               for (int k = 0; k < kStPer; k ++) {
 	                  const float2 w = v [(k - u + kStPer) % kStPer];
-	                  acc [k].x = fmaf (c, w.x, acc [k].x);
-	                  acc [k].y = fmaf (c, w.y, acc [k].y);
+	                  acc [k] = ffma2 (c, w, acc [k]);
 	               }
 	               v [(kStPer - 1 - u) % kStPer] = sRing [nxt & (kPssRing - 1)];
 	               nxt --;
@@ -197,8 +218,7 @@ float2 *ring = ring_g + (int64_t)stream * kPssRing;
 #pragma unroll
 	            for (int k = 0; k < kStPer; k ++) {
 	               const float2 w = v [(k - u + kStPer) % kStPer];
-	               acc [k].x = fmaf (c, w.x, acc [k].x);
-	               acc [k].y = fmaf (c, w.y, acc [k].y);
+	               acc [k] = ffma2 (c, w, acc [k]);
 	            }
 	            v [(kStPer - 1 - u) % kStPer] = sRing [nxt & (kPssRing - 1)];
 	            nxt --;
