@@ -38,7 +38,10 @@ typedef struct sdrjfm_handle sdrjfm_handle;
 /* Constructor arguments of fmProcessor (src/fm/fm-processor.cpp:48-63) that matter to
  * the arithmetic, plus the batch shape.  Zero-initialise, then fill.                    */
 typedef struct sdrjfm_config {
-    int32_t input_rate;            /* inputRate, 2304000 (includes/fm-constants.h:35)    */
+    int32_t input_rate;            /* inputRate, 2304000 (includes/fm-constants.h:35); also
+                                      2400000 / 6000000 / 10000000 with the reference's own
+                                      integer-decimation arithmetic (fm-processor.cpp:36,68-75):
+                                      stage 1 /6, stage 2 /(inputRate/6/fmRate) = /12, /30, /48  */
     int32_t fm_rate;               /* fmRate, 192000 (radio.cpp:68)                      */
     int32_t working_rate;          /* workingRate, 48000 (radio.cpp:233)                 */
     int32_t audio_rate;            /* audioRate, 48000 (main.cpp:42)                     */
@@ -46,7 +49,10 @@ typedef struct sdrjfm_config {
     int32_t device;                /* CUDA device ordinal                                */
     int64_t max_samples_per_call;  /* per stream; sizes the device buffers               */
     int32_t keep_taps;             /* 1: keep fm-rate intermediates for sdrjfm_read_tap  */
-    int32_t reserved;
+    int32_t front_end_mode;        /* 0: the reference's integer decimation (12m+11 index contract);
+                                      1: rational polyphase resampler to exactly fm_rate (new block,
+                                         BASELINE config 4): /5 low-pass, then L/M = 5 fm_rate / input_rate
+                                         (2/5, 4/25, 12/125 at 2.4, 6, 10 MS/s); csrc/resample.cuh        */
 } sdrjfm_config;
 
 /* fmProcessor::SMetaData (includes/fm/fm-processor.h:91-101) per stream, plus the RF DC
@@ -103,6 +109,30 @@ int  sdrjfm_process_device (sdrjfm_handle *h,
                             const float *d_iq, int64_t n_in, int64_t in_pitch,
                             float *d_audio, int64_t audio_pitch, int64_t *n_audio,
                             float *d_rds24, int64_t rds_pitch, int64_t *n_rds);
+
+/* Device-native sample formats.  The reference's device handlers convert to complex float on
+ * the CPU before the ring buffer; here the conversion is fused into the front-end kernel's only
+ * read of the samples, so 2 or 4 bytes per IQ sample cross PCIe / HBM instead of 8.  The floats
+ * entering the filters are bit-identical to the handler's (all divisors are powers of two). */
+enum sdrjfm_iq_format {
+    SDRJFM_IQ_CF32 = 0,   /* interleaved float32: what getSamples delivers                          */
+    SDRJFM_IQ_U8   = 1,   /* rtlsdr: (b - 127) / 128        devices/rtlsdr-handler/rtlsdr-handler.cpp:286-293 */
+    SDRJFM_IQ_S8   = 2,   /* hackrf: b / 128                devices/hackrf-handler/hackrf-handler.cpp:355-368 */
+    SDRJFM_IQ_S16  = 3    /* v / denominator: sdrplay 2048|8192 (sdrplay-handler.cpp:266-270,481-488),
+                             sdrplay v3 2048|4096 (sdrplay-handler-v3.cpp:254-263,293), pluto 2048
+                             (pluto-handler.cpp:574-583), lime 2048, airspy 2048                     */
+};
+/* sdrjfm_process / sdrjfm_process_device for samples in a device format; in_pitch in IQ samples.
+ * denominator: the int16 divisor (power of two); ignored for the 8-bit formats.               */
+int  sdrjfm_process_raw (sdrjfm_handle *h, const void *iq, int32_t format, int32_t denominator,
+                         int64_t n_in, int64_t in_pitch,
+                         float *audio, int64_t audio_pitch, int64_t *n_audio,
+                         float *rds24, int64_t rds_pitch, int64_t *n_rds,
+                         sdrjfm_meta *meta /* [n_streams] */);
+int  sdrjfm_process_raw_device (sdrjfm_handle *h, const void *d_iq, int32_t format, int32_t denominator,
+                                int64_t n_in, int64_t in_pitch,
+                                float *d_audio, int64_t audio_pitch, int64_t *n_audio,
+                                float *d_rds24, int64_t rds_pitch, int64_t *n_rds);
 int  sdrjfm_sync (sdrjfm_handle *h);
 int  sdrjfm_get_meta (sdrjfm_handle *h, sdrjfm_meta *meta /* [n_streams] */);
 /* copies tap `which` of stream `stream` from the LAST process call to host memory;
@@ -113,6 +143,8 @@ void *sdrjfm_cuda_stream (sdrjfm_handle *h);
 /* stage timing: runs only the decimating front end (DC/LO/FIR, the roofline kernel) on
  * device input, without touching stream state.  For bench.py / ncu.                     */
 int  sdrjfm_run_frontend_only (sdrjfm_handle *h, const float *d_iq, int64_t n_in, int64_t in_pitch);
+int  sdrjfm_run_frontend_only_raw (sdrjfm_handle *h, const void *d_iq, int32_t format, int32_t denominator,
+                                   int64_t n_in, int64_t in_pitch);
 /* number of kernel launches issued by the handle since creation                          */
 int64_t sdrjfm_launch_count (const sdrjfm_handle *h);
 /* diagnostics of the parallel-in-time pilot PLL solver for the last process call, per stream:

@@ -116,6 +116,13 @@ class Chain:
         n = iq.shape[0]
         return self._run(self._process, iq, n, n // 12 + 2, taps)
 
+    def process_fm(self, z, taps=TAPS):
+        """for a chain created with input_rate == fm_rate (the reference's decimator bypass,
+        fm-processor.cpp:471): z = complex64 samples already at the fm rate."""
+        assert self.cfg.input_rate == self.cfg.fm_rate
+        z = np.ascontiguousarray(z, dtype=np.complex64)
+        return self._run(self._process, z, z.shape[0], z.shape[0] + 2, taps)
+
     def _run(self, fn, iq, n, cap, taps):
         bufs = {}
         t = ChainTaps()

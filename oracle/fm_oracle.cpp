@@ -484,8 +484,10 @@ struct Oracle {
 	      if (loPhase < 0) loPhase += inRate; else if (loPhase >= inRate) loPhase -= inRate;
 	      v = v * loTab [loPhase];
 	      if (inputOn) v = inputLp. pass_cplx (v);                          // :469-470
-	      if (!band1. pass (v, &v)) continue;                               // :472-475
-	      if (!band2. pass (v, &v)) continue;
+	      if (inRate / fmRate > 1) {                                        // :471 (192000: bypass)
+	         if (!band1. pass (v, &v)) continue;                            // :472-475
+	         if (!band2. pass (v, &v)) continue;
+	      }
 	      float demod = demodulate (v);                                     // :497
 	      after_demod (demod, v, t, nfm, nrds);
 	      nfm ++;

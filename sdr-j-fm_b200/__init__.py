@@ -27,6 +27,18 @@ _TAP_DTYPE = dict(fm_z=np.complex64, demod=np.float32, pilot_phase=np.float32,
                   audio192=np.complex64, rds_cplx=np.complex64, rds24=np.complex64)
 
 
+# device sample formats (enum sdrjfm_iq_format): dtype of one I or Q component
+IQ_FORMAT = dict(cf32=0, u8=1, s8=2, s16=3)
+_IQ_DTYPE = {0: np.float32, 1: np.uint8, 2: np.int8, 3: np.int16}
+
+
+def front_end_decimation(input_rate, fm_rate=192000):
+    """input samples per fm-rate sample, from the reference's constructor arithmetic
+    (fm-processor.cpp:36,68-75): IRate = inputRate/6; stage 1 /6; stage 2 /(IRate/fmRate)."""
+    irate = input_rate // 6
+    return (input_rate // irate) * (irate // fm_rate)
+
+
 class SdrjfmError(RuntimeError):
     def __init__(self, status, msg):
         super().__init__(f"sdrjfm status {status}: {msg}")
@@ -38,7 +50,7 @@ class Config(C.Structure):
                 ("working_rate", C.c_int32), ("audio_rate", C.c_int32),
                 ("n_streams", C.c_int32), ("device", C.c_int32),
                 ("max_samples_per_call", C.c_int64), ("keep_taps", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("front_end_mode", C.c_int32)]
 
 
 class Meta(C.Structure):
@@ -83,6 +95,11 @@ def lib():
                                      C.POINTER(i64), vp]
         L.sdrjfm_process_device.argtypes = [vp, vp, i64, i64, vp, i64, C.POINTER(i64), vp, i64,
                                             C.POINTER(i64)]
+        L.sdrjfm_process_raw.argtypes = [vp, vp, i32, i32, i64, i64, vp, i64, C.POINTER(i64), vp, i64,
+                                         C.POINTER(i64), vp]
+        L.sdrjfm_process_raw_device.argtypes = [vp, vp, i32, i32, i64, i64, vp, i64, C.POINTER(i64),
+                                                vp, i64, C.POINTER(i64)]
+        L.sdrjfm_run_frontend_only_raw.argtypes = [vp, vp, i32, i32, i64, i64]
         L.sdrjfm_sync.argtypes = [vp]
         L.sdrjfm_get_meta.argtypes = [vp, vp]
         L.sdrjfm_read_tap.restype = i64
@@ -122,7 +139,9 @@ _HDR_FIELDS = [("magic", "u4"), ("version", "u4"), ("input_rate", "i4"), ("fm_ra
                ("off_sincos", "i8"), ("off_arcsine", "i8"), ("off_tw2048", "i8"),
                ("off_tw8192", "i8"), ("off_tw32768", "i8"), ("off_pss_lp", "i8"),
                ("off_rds_bp", "i8"), ("off_audio_lp", "i8"), ("off_input_taps", "i8"),
-               ("off_comp_wide", "i8"), ("ncomp_wide", "i4"), ("reserved1", "i4")]
+               ("off_comp_wide", "i8"), ("ncomp_wide", "i4"), ("reserved1", "i4"),
+               ("rs_L", "i4"), ("rs_M", "i4"), ("rs_P", "i4"), ("rs_ntapsA", "i4"),
+               ("off_rsA", "i8"), ("off_rsB", "i8")]
 _HDR_DTYPE = np.dtype(_HDR_FIELDS)
 
 
@@ -163,6 +182,15 @@ class Tables:
     def audio_lp_freq(self):
         return self._c(self.hdr["off_audio_lp"], 8192) if self.hdr["audio_lp_hz"] > 0 else None
     @property
+    def resampler(self):
+        """(L, M, P, stage-A taps [49], stage-B taps [L, P]) of the rational polyphase resampler, or None."""
+        L, M, P = int(self.hdr["rs_L"]), int(self.hdr["rs_M"]), int(self.hdr["rs_P"])
+        if L == 0:
+            return None
+        return (L, M, P, self._f(self.hdr["off_rsA"], self.hdr["rs_ntapsA"]),
+                self._f(self.hdr["off_rsB"], L * P).reshape(L, P))
+
+    @property
     def input_taps(self):
         return self._f(self.hdr["off_input_taps"], 251) if self.hdr["input_filter_hz"] > 0 else None
 
@@ -192,15 +220,18 @@ class FmProcessorB200:
                "FM Difference Based": 6}   # fm-demodulator.cpp:36-44
 
     def __init__(self, n_streams=1, input_rate=2304000, fm_rate=192000, working_rate=48000,
-                 audio_rate=48000, max_samples_per_call=2304000, device=0, keep_taps=True):
+                 audio_rate=48000, max_samples_per_call=2304000, device=0, keep_taps=True,
+                 front_end_mode=0):
         self.L = lib()
         self.cfg = Config(input_rate, fm_rate, working_rate, audio_rate, n_streams, device,
-                          max_samples_per_call, 1 if keep_taps else 0, 0)
+                          max_samples_per_call, 1 if keep_taps else 0, front_end_mode)
         st = C.c_int(0)
         self.h = self.L.sdrjfm_create(C.byref(self.cfg), C.byref(st))
         if not self.h:
             raise SdrjfmError(st.value, self.L.sdrjfm_last_error(None).decode())
         self.n_streams = n_streams
+        # input samples per fm-rate sample (a lower bound in the resampler mode: sizes the outputs)
+        self.decim = (input_rate // fm_rate) if front_end_mode == 1 else front_end_decimation(input_rate, fm_rate)
 
     def close(self):
         if getattr(self, "h", None):
@@ -256,8 +287,8 @@ class FmProcessorB200:
             iq = iq[None, :]
         assert iq.shape[0] == self.n_streams
         n = iq.shape[1]
-        audio = np.zeros((self.n_streams, n // 48 + 2), np.complex64)
-        rds = np.zeros((self.n_streams, n // 96 + 2), np.complex64)
+        audio = np.zeros((self.n_streams, n // (4 * self.decim) + 2), np.complex64)
+        rds = np.zeros((self.n_streams, n // (8 * self.decim) + 2), np.complex64)
         na, nr = C.c_int64(0), C.c_int64(0)
         meta = (Meta * self.n_streams)() if want_meta else None
         self._ck(self.L.sdrjfm_process(self.h, iq.ctypes.data, n, iq.shape[1],
@@ -268,6 +299,36 @@ class FmProcessorB200:
         if want_meta:
             return out + ([{k: getattr(m, k) for k, _ in Meta._fields_} for m in meta],)
         return out
+
+    def process_raw(self, iq, fmt, denominator=2048):
+        """iq: [n_streams, n, 2] (or [n, 2]) array of uint8 / int8 / int16 components in HOST memory,
+        the bytes a device delivers; fmt in IQ_FORMAT.  Same results as process() on the floats the
+        reference's handler would have made of them."""
+        f = IQ_FORMAT.get(fmt, fmt)
+        iq = np.ascontiguousarray(iq, dtype=_IQ_DTYPE[f])
+        if iq.ndim == 2:
+            iq = iq[None]
+        assert iq.shape[0] == self.n_streams and iq.shape[2] == 2
+        n = iq.shape[1]
+        audio = np.zeros((self.n_streams, n // (4 * self.decim) + 2), np.complex64)
+        rds = np.zeros((self.n_streams, n // (8 * self.decim) + 2), np.complex64)
+        na, nr = C.c_int64(0), C.c_int64(0)
+        self._ck(self.L.sdrjfm_process_raw(self.h, iq.ctypes.data, f, denominator, n, n,
+                                           audio.ctypes.data, audio.shape[1], C.byref(na),
+                                           rds.ctypes.data, rds.shape[1], C.byref(nr), None))
+        return audio[:, :na.value], rds[:, :nr.value]
+
+    def process_raw_device(self, d_iq_ptr, fmt, denominator, n_in, in_pitch, d_audio_ptr=None,
+                           audio_pitch=0, d_rds_ptr=None, rds_pitch=0):
+        na, nr = C.c_int64(0), C.c_int64(0)
+        self._ck(self.L.sdrjfm_process_raw_device(self.h, d_iq_ptr, IQ_FORMAT.get(fmt, fmt), denominator,
+                                                  n_in, in_pitch, d_audio_ptr, audio_pitch, C.byref(na),
+                                                  d_rds_ptr, rds_pitch, C.byref(nr)))
+        return na.value, nr.value
+
+    def run_frontend_only_raw(self, d_iq_ptr, fmt, denominator, n_in, in_pitch):
+        self._ck(self.L.sdrjfm_run_frontend_only_raw(self.h, d_iq_ptr, IQ_FORMAT.get(fmt, fmt), denominator,
+                                                     n_in, in_pitch))
 
     def process_device(self, d_iq_ptr, n_in, in_pitch, d_audio_ptr=None, audio_pitch=0,
                        d_rds_ptr=None, rds_pitch=0):
@@ -302,7 +363,7 @@ class FmProcessorB200:
         return [{k: getattr(m, k) for k, _ in Meta._fields_} for m in meta]
 
     def read_tap(self, name, stream=0, cap=None):
-        cap = cap or (self.cfg.max_samples_per_call // 12 + 16)
+        cap = cap or (self.cfg.max_samples_per_call // self.decim + 16)
         a = np.zeros(cap, _TAP_DTYPE[name])
         n = self.L.sdrjfm_read_tap(self.h, TAP[name], stream, a.ctypes.data, cap)
         if n < 0:

@@ -21,14 +21,14 @@ struct DiscrParams {
 	float  sumC, sumCm;         // sum of the plain composite taps C; of the DC-folded taps C'
 	float  gb0, gb1, gb2;       // alpha * block means of the tail sums g (tables.cpp)
 	float  Gre, Gim;            // constant complex gain of the cascade
-	double alpha, beta;         // alpha = (float)1/inputRate; beta = (1 - alpha)^12
+	double alpha, beta;         // alpha = (float)1/inputRate; beta = (1 - alpha)^decim
 	float  lgain, rgain;
 	int32_t dc_remove, decoder;
 	// local oscillator on: gains and rotation were applied per input sample by K1; the DC value
 	// the reference subtracted BEFORE the rotation comes back out as clamp (r) * gains *
-	// Table[LOPhase at 12 (m + lo_moff) + 11] * H,  H = sum_t C[t] exp (+2 pi i lo t / inputRate)
+	// Table[LOPhase at decim (m + lo_moff) + decim - 1] * H,  H = sum_t C[t] exp (+2 pi i lo t / inputRate)
 	const float2 *lo_tab;
-	int32_t lo_rate, lo_hz, lo_moff;
+	int32_t lo_rate, lo_hz, lo_moff, decim;      // decim: input samples per fm-rate sample
 	int64_t lo_phase;
 	float  Hre, Him;
 };
@@ -151,7 +151,7 @@ const float ky = freey ? c.y * P.sumCm : c.y * P.sumC + wy;
 float vx = (u.x - kx) * P.lgain;
 float vy = (u.y - ky) * P.rgain;
 	if (P.lo_tab) {
-	   int64_t t = (P.lo_phase - (int64_t)P.lo_hz * (12 * (j + (int64_t)P.lo_moff) + 12)) % P.lo_rate;
+	   int64_t t = (P.lo_phase - (int64_t)P.lo_hz * ((int64_t)P.decim * (j + (int64_t)P.lo_moff) + P.decim)) % P.lo_rate;
 	   if (t < 0) t += P.lo_rate;
 	   const float2 o = P.lo_tab [t];
 	   const float2 a = make_float2 (c.x * P.lgain, c.y * P.rgain);

@@ -56,12 +56,12 @@ __device__ __forceinline__ float2 lo_apply (const LoParams &L, float2 v, int32_t
 }
 
 // x      : [n_streams][in_pitch] complex, this call's samples (N = 12 * M per stream)
-// hist   : [n_streams][kHist] complex, the 36 raw samples preceding x[.][0]
+// hist   : [n_streams][hist_len] complex, the raw samples preceding x[.][0] (the last 36 are used)
 // U, S   : [n_streams][out_pitch] complex
 template <bool LO>
 __global__ void __launch_bounds__ (kFeThreads, 4)
 frontend_fir_kernel (const float2 *__restrict__ x, int64_t in_pitch,
-                     const float2 *__restrict__ hist,
+                     const float2 *__restrict__ hist, int hist_len,
                      float2 *__restrict__ U, float2 *__restrict__ S,
                      int64_t out_pitch, int32_t M, const LoParams lop) {
 extern __shared__ float2 sm [];
@@ -77,7 +77,7 @@ const float2 *xs = x + (int64_t)stream * in_pitch;
 //	halo: the 36 samples before the tile, polyphase rows 12..47 of column 0
 	if (tid < kHist) {
 	   float2 v;
-	   if (blockIdx.x == 0) v = hist [(int64_t)stream * kHist + tid];
+	   if (blockIdx.x == 0) v = hist [(int64_t)stream * hist_len + (hist_len - kHist) + tid];
 	   else                 v = xs [in0 - kHist + tid];
 	   if (LO) v = lo_apply (lop, v, lo_index (lop, in0 - kHist + tid));
 	   sm [(kDecim + tid) * kFePitch] = v;
@@ -204,7 +204,7 @@ __constant__ float c_wide [kDecim][kFwGroups + 3];  // c_wide[p][g] = C'ws[12 g 
 template <bool LO>
 __global__ void __launch_bounds__ (kFeThreads, 3)
 frontend_wide_kernel (const float2 *__restrict__ x, int64_t in_pitch,
-                      const float2 *__restrict__ hist,
+                      const float2 *__restrict__ hist, int hist_len,
                       float2 *__restrict__ U, float2 *__restrict__ S,
                       int64_t out_pitch, int32_t M, const LoParams lop) {
 extern __shared__ float2 sm [];
@@ -221,7 +221,7 @@ constexpr int kHaloIn = kFwHalo * kFeRows;           // 288 samples before the t
 //	halo: columns 0..5 (sample in0 - 288 + i sits at row i % 48, column i / 48)
 	for (int i = tid; i < kHaloIn; i += kFeThreads) {
 	   float2 v;
-	   if (blockIdx.x == 0) v = hist [(int64_t)stream * kFwHist + (kFwHist - kHaloIn) + i];
+	   if (blockIdx.x == 0) v = hist [(int64_t)stream * hist_len + (hist_len - kHaloIn) + i];
 	   else                 v = xs [in0 - kHaloIn + i];
 	   if (LO) v = lo_apply (lop, v, lo_index (lop, in0 - kHaloIn + i));
 	   sm [(i % kFeRows) * kFwPitch + i / kFeRows] = v;

@@ -25,6 +25,8 @@
 #include "tables.hpp"
 #include "common.cuh"
 #include "frontend_fir.cuh"
+#include "frontend_poly.cuh"
+#include "resample.cuh"
 #include "discriminator.cuh"
 #include "sequential.cuh"
 #include "pilot.cuh"
@@ -43,7 +45,15 @@ struct Lane;
 static int lane_destroy (Lane *h);
 static int lane_restart_pss_analyzer (Lane *h);
 static int lane_get_meta (Lane *h, sdrjfm_meta *meta);
+static cudaError_t poly_set_attr (int shape);
 
+
+// front-end shapes: decimation, outputs per thread, tap groups narrow / with inputFilter
+struct FeShape { int D, gpt, ng, ngw; };
+static const FeShape kFeShapes [] = { { 12, 4, 4, 25 }, { 30, 2, 2, 11 }, { 48, 1, 2, 7 },
+                                      { kRsStageADecim, 8, 10, 0 } };     // last: stage A of the rational resampler
+constexpr int kShapeResample = 3;
+constexpr int kInputFilterDelay = kInputFftSize - kInputDegree;       // 65285 input samples
 
 struct Lane {
 	sdrjfm_config cfg;
@@ -57,9 +67,22 @@ struct Lane {
 	float        *d_sin_quarter = nullptr;
 
 	int64_t cap_in = 0, cap_fm = 0, cap_audio = 0, cap_rds = 0;   // per-stream capacities (pitches)
-	float2 *d_in = nullptr;                 // staging [S][cap_in]
+	// front-end shape: decimation D = 6 * (inputRate / 6 / fmRate) and the kernel instantiation for it
+	int           decim = 12, shape = 0;    // shape indexes kFeShapes
+	int           hist_len = 0, hist_len_w = 0;   // raw-sample history kept per stream (narrow / input filter on)
+	int           fw_delay = 0, fw_shift = 0;     // inputFilter latency 65285 = decim * fw_delay + fw_shift
+	int           ngw = 0;                        // tap groups of the wide composite
+	bool          force_generic = false;    // SDRJFM_GENERIC_FE=1: K1g also where the tuned D = 12 kernels apply
+	float2 *d_in = nullptr;                 // staging [S][cap_in] (8 bytes per sample: any format fits)
 	float2 *d_hist [2] = { nullptr, nullptr }; int hist_sel = 0;
-	float2 *d_pend = nullptr; int pend = 0; // leftover raw samples (< 12 per stream)
+	float2 *d_pend = nullptr; int pend = 0; // leftover raw samples (< decim per stream), in format pend_fmt
+	int     pend_fmt = 0;
+	// rational polyphase resampler (front_end_mode 1): stage-A output and the stage-B state
+	bool    resample = false;
+	int     rsL = 0, rsM = 0, rsP = 0, rsHB = 0;
+	int64_t cap_a = 0, a_total = 0;         // stage-A samples per call (pitch) / produced so far
+	float2 *d_A = nullptr, *d_SA = nullptr;
+	float2 *d_bha [2] = { nullptr, nullptr }, *d_bhs [2] = { nullptr, nullptr }; int bh_sel = 0;
 	float2 *d_U = nullptr, *d_S = nullptr, *d_iqn = nullptr, *d_fmz = nullptr;
 	float  *d_res = nullptr, *d_zabs = nullptr, *d_demod = nullptr, *d_phase = nullptr;
 	float  *d_pssd = nullptr;
@@ -136,7 +159,7 @@ const TableHeader &th = h -> tables.hdr ();
 	CK (cudaMalloc ((void **)&h -> d_tables, th.payload_floats * sizeof (float)));
 	CK (cudaMemcpy (h -> d_tables, h -> tables.payload (), th.payload_floats * sizeof (float),
 	                cudaMemcpyHostToDevice));
-float comp [40] = { 0 };
+float comp [96] = { 0 };
 	memcpy (comp, h -> tables.payload () + th.off_comp, th.ncomp * sizeof (float));
 const int32_t lo_hz = h -> set.lo_hz;
 	h -> lo_Hre = 1.f; h -> lo_Him = 0.f;
@@ -157,7 +180,7 @@ const int32_t lo_hz = h -> set.lo_hz;
 	   }
 	   h -> lo_Hre = (float)H.real (); h -> lo_Him = (float)H.imag ();
 	}
-	CK (cudaMemcpyToSymbol (c_comp, comp, sizeof comp));
+	CK (cudaMemcpyToSymbol (c_comp, comp, 40 * sizeof (float)));
 
 //	audio decimator taps (our own design, audio_out.cuh): Blackman-windowed sinc, fc = 20 kHz
 	{
@@ -176,32 +199,56 @@ const int32_t lo_hz = h -> set.lo_hz;
 	   CK (cudaMemcpyToSymbol (c_rs_taps, t, sizeof t));
 	}
 
-//	input filter ON: composite of the 251-tap low-pass and the decimator cascade, shifted by 5
-//	samples (frontend_fir.cuh), RF DC removal folded in exactly like the narrow taps (tables.cpp)
+//	K1g taps, narrow: c_poly[p][g] = C'[D g + D - 1 - p]
+const int D = h -> decim;
+const FeShape &fs = kFeShapes [h -> shape];
+float cpoly [kPolyMaxTaps];
+	memset (cpoly, 0, sizeof cpoly);
+	if (h -> resample) {      // stage A of the rational resampler: its own 49 taps, no DC folding
+	   if (th.rs_L != h -> rsL || th.rs_M != h -> rsM || th.rs_P != h -> rsP || th.rs_ntapsA > D * fs.ng) {
+	      h -> err = "table blob carries no (or another) resampler design"; return SDRJFM_ERR_ARG;
+	   }
+	   memset (comp, 0, sizeof comp);
+	   memcpy (comp, h -> tables.payload () + th.off_rsA, th.rs_ntapsA * sizeof (float));
+	}
+const int ncomp = h -> resample ? th.rs_ntapsA : th.ncomp;
+	for (int g = 0; g < fs.ng; g ++)
+	   for (int p = 0; p < D; p ++) {
+	      const int i = D * g + D - 1 - p;
+	      cpoly [p * fs.ng + g] = i < ncomp ? comp [i] : 0.f;
+	   }
+
+//	input filter ON: composite of the 251-tap low-pass and the decimator cascade, shifted by
+//	fw_shift samples (frontend_fir.cuh), RF DC removal folded in exactly like the narrow taps (tables.cpp)
 	if (th.ncomp_wide > 0) {
 	   const float *wide = h -> tables.payload () + th.off_comp_wide;
-	   std::vector<double> cw (kFwHist, 0.0), g (kFwHist, 0.0);
-	   for (int t = 0; t < th.ncomp_wide && t + 5 < kFwHist; t ++) cw [t + 5] = (double)wide [t];
-	   for (int i = 0; i < kFwHist; i ++)
-	      for (int k = i + 1; k < kFwHist; k ++) g [i] += cw [k];
+	   const int len = fs.ngw * D;
+	   if (th.ncomp_wide + h -> fw_shift > len) { h -> err = "wide composite does not fit its tap groups"; return SDRJFM_ERR_UNSUPPORTED; }
+	   std::vector<double> cw (len, 0.0), g (len, 0.0);
+	   for (int t = 0; t < th.ncomp_wide; t ++) cw [t + h -> fw_shift] = (double)wide [t];
+	   for (int i = 0; i < len; i ++)
+	      for (int k = i + 1; k < len; k ++) g [i] += cw [k];
 	   const double alpha = lo_hz != 0 ? 0.0 : (double)(1.0f / th.input_rate);
 	   float cwide [kDecim][kFwGroups + 3];
 	   memset (cwide, 0, sizeof cwide);
+	   memset (cpoly, 0, sizeof cpoly);
 	   double sC = 0, sCm = 0;
-	   for (int i = 0; i < kFwHist; i ++) {
+	   for (int i = 0; i < len; i ++) {
 	      const float f = (float)(cw [i] + alpha * g [i]);
 	      sC += cw [i]; sCm += f;
-	      cwide [11 - i % kDecim][i / kDecim] = f;
+	      if (D == kDecim) cwide [11 - i % kDecim][i / kDecim] = f;
+	      cpoly [(D - 1 - i % D) * fs.ngw + i / D] = f;
 	   }
 	   h -> wide_sumC = (float)sC; h -> wide_sumCm = (float)sCm;
 	   if (lo_hz != 0) {
 	      std::complex<double> H (0, 0);
-	      for (int t = 0; t < kFwHist; t ++)
+	      for (int t = 0; t < len; t ++)
 	         H += (double)(float)cw [t] * std::polar (1.0, 2 * M_PI * (double)lo_hz * t / th.input_rate);
 	      h -> lo_Hre = (float)H.real (); h -> lo_Him = (float)H.imag ();
 	   }
-	   CK (cudaMemcpyToSymbol (c_wide, cwide, sizeof cwide));
+	   if (D == kDecim) CK (cudaMemcpyToSymbol (c_wide, cwide, sizeof cwide));
 	}
+	CK (cudaMemcpyToSymbol (c_poly, cpoly, sizeof cpoly));
 
 //	PSS low-pass taps: lpFilter (2048, 295).setLowPass (15000, rate), stereo-separation.cpp:31-39
 	{
@@ -324,9 +371,27 @@ int dummy; if (!status) status = &dummy;
 	if (!cfg || cfg -> n_streams < 1 || cfg -> max_samples_per_call < 1) {
 	   g_create_error = "bad config"; return nullptr;
 	}
-	if (cfg -> input_rate != 2304000 || cfg -> fm_rate != 192000) {
-//	the reference itself only supports 2304000 (and the 192000 bypass), SURVEY.md §8(d) config 4
-	   g_create_error = "only input_rate 2304000 / fm_rate 192000 are supported";
+//	the decimation follows from the rates exactly as in the reference's constructor
+//	(fm-processor.cpp:36,68-75): IRate = inputRate / 6, stage 1 /6, stage 2 / (IRate / fmRate)
+int decim = 0, shape = -1;
+int rsL = 0, rsM = 0, rsP = 0;
+	if (cfg -> front_end_mode == 1) {
+	   std::vector<float> ha, hb;
+	   if (cfg -> fm_rate == 192000 && design_resampler (cfg -> input_rate, cfg -> fm_rate, rsL, rsM, rsP, ha, hb)) {
+	      decim = kRsStageADecim; shape = kShapeResample;
+	   }
+	}
+	else if (cfg -> front_end_mode != 0) { g_create_error = "front_end_mode must be 0 or 1"; return nullptr; }
+	else if (cfg -> fm_rate == 192000 && cfg -> input_rate >= 12 * cfg -> fm_rate) {
+	   const int32_t irate = cfg -> input_rate / 6;
+	   decim = (cfg -> input_rate / irate) * (irate / cfg -> fm_rate);
+	   for (int i = 0; i < (int)(sizeof kFeShapes / sizeof kFeShapes [0]); i ++)
+	      if (kFeShapes [i].D == decim) shape = i;
+	}
+	if (shape < 0) {
+	   g_create_error = "unsupported rates: fm_rate must be 192000 and input_rate must give a front-end "
+	                    "decimation of 12, 30 or 48 (2304000, 2400000, 6000000, 10000000, ...); the resampler "
+	                    "mode needs 5 * 192000 / input_rate = L / M with L <= 16";
 	   *status = SDRJFM_ERR_UNSUPPORTED; return nullptr;
 	}
 int ndev = 0;
@@ -342,6 +407,16 @@ cudaDeviceProp prop;
 	}
 Lane *h = new Lane ();
 	h -> cfg = *cfg;
+	h -> decim = decim; h -> shape = shape;
+	h -> resample = shape == kShapeResample;
+	h -> rsL = rsL; h -> rsM = rsM; h -> rsP = rsP; h -> rsHB = rsP - 1 + kRsHistPad;
+	h -> ngw = kFeShapes [shape].ngw;
+	h -> fw_delay = kInputFilterDelay / decim; h -> fw_shift = kInputFilterDelay % decim;
+	{  const FeShape &fs = kFeShapes [shape];
+	   const int rows = fs.D * fs.gpt;
+	   h -> hist_len   = ((fs.ng - 1 + fs.gpt - 1) / fs.gpt) * rows;      // Poly<>::HaloIn
+	   h -> hist_len_w = std::max (((fs.ngw - 1 + fs.gpt - 1) / fs.gpt) * rows, fs.ngw * fs.D);
+	   const char *env = getenv ("SDRJFM_GENERIC_FE"); h -> force_generic = env && env [0] == '1'; }
 	if (h -> cfg.working_rate <= 0) h -> cfg.working_rate = 48000;
 	if (h -> cfg.audio_rate <= 0) h -> cfg.audio_rate = h -> cfg.working_rate;
 	h -> n_sm = prop.multiProcessorCount;
@@ -349,8 +424,12 @@ Lane *h = new Lane ();
 	h -> fade_max = h -> cfg.working_rate / 2;
 	h -> fade_cnt = h -> fade_max;
 const int64_t S = cfg -> n_streams;
-	h -> cap_in    = ((cfg -> max_samples_per_call + kDecim + 15) / 16) * 16;
-	h -> cap_fm    = ((h -> cap_in / kDecim + 1 + 15) / 16) * 16;
+	h -> cap_in    = ((cfg -> max_samples_per_call + decim + 15) / 16) * 16;
+	h -> cap_fm    = ((h -> cap_in / decim + 1 + 15) / 16) * 16;
+	if (h -> resample) {
+	   h -> cap_a  = h -> cap_fm;
+	   h -> cap_fm = ((h -> cap_a * rsL / rsM + 2 + 15) / 16) * 16;
+	}
 	h -> cap_audio = ((h -> cap_fm / kRsDecim + 1 + 15) / 16) * 16;
 	h -> cap_rds   = ((h -> cap_fm / 8 + 1 + 15) / 16) * 16;
 auto fail = [&](cudaError_t e, const char *what) -> Lane * {
@@ -362,8 +441,12 @@ cudaError_t e;
 	if ((e = cudaStreamCreateWithFlags (&h -> stream, cudaStreamNonBlocking)) != cudaSuccess)
 	   return fail (e, "cudaStreamCreate");
 	AL (d_in, S * h -> cap_in);
-	AL (d_hist [0], S * kHist); AL (d_hist [1], S * kHist);
-	AL (d_pend, S * kDecim);
+	AL (d_hist [0], S * h -> hist_len); AL (d_hist [1], S * h -> hist_len);
+	AL (d_pend, S * decim);
+	if (h -> resample) {
+	   AL (d_A, S * h -> cap_a); AL (d_SA, S * h -> cap_a);
+	   for (int i = 0; i < 2; i ++) { AL (d_bha [i], S * h -> rsHB); AL (d_bhs [i], S * h -> rsHB); }
+	}
 	AL (d_U, S * h -> cap_fm); AL (d_S, S * h -> cap_fm);
 	AL (d_iqn, S * h -> cap_fm); AL (d_fmz, S * h -> cap_fm);
 	AL (d_res, S * h -> cap_fm); AL (d_zabs, S * h -> cap_fm);
@@ -390,6 +473,7 @@ cudaError_t e;
 	                               kFeSmemBytes)) != cudaSuccess ||
 	    (e = cudaFuncSetAttribute (frontend_fir_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                               kFeSmemBytes)) != cudaSuccess) return fail (e, "smem attr K1");
+	if ((e = poly_set_attr (shape)) != cudaSuccess) return fail (e, "smem attr K1g");
 	if ((e = cudaFuncSetAttribute (sequential_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                               (cfg -> fm_rate / 4 + 1) * (int)sizeof (float))) != cudaSuccess ||
 	    (e = cudaFuncSetAttribute (sequential_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -421,7 +505,8 @@ void *ptrs [] = { h -> d_tables, h -> d_sin_quarter, h -> d_in, h -> d_hist [0],
 	              h -> d_rds_dring, h -> d_rds_pring, h -> d_rds_bp, h -> d_rds_hi, h -> d_rds_R, h -> d_rds_tw,
 	              h -> d_rds_dtaps, h -> d_rds_tws, h -> d_rds_hist [0], h -> d_rds_hist [1],
 	              h -> d_histw [0], h -> d_histw [1], h -> d_Uw, h -> d_Sw, h -> d_udel [0], h -> d_udel [1],
-	              h -> d_sdel [0], h -> d_sdel [1], h -> d_alp_hist [0], h -> d_alp_hist [1], h -> d_lrf, h -> d_lo_tab };
+	              h -> d_sdel [0], h -> d_sdel [1], h -> d_alp_hist [0], h -> d_alp_hist [1], h -> d_lrf, h -> d_lo_tab,
+	              h -> d_A, h -> d_SA, h -> d_bha [0], h -> d_bha [1], h -> d_bhs [0], h -> d_bhs [1] };
 	for (void *p : ptrs) if (p) cudaFree (p);
 	if (h -> stream) cudaStreamDestroy (h -> stream);
 	delete h;
@@ -445,10 +530,32 @@ static int lane_sync (Lane *h) {
 	return SDRJFM_OK;
 }
 
-static int launch_frontend (Lane *h, const float2 *src, int64_t pitch, int32_t M,
-                            const float2 *hist) {
+// ---- K1g dispatch over the instantiated shapes ---------------------------------------------
+template <int D, int GPT, int NG> static cudaError_t poly_attr_one () {
+	return cudaFuncSetAttribute (frontend_poly_kernel<D, GPT, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                             Poly<D, GPT, NG>::SmemBytes);
+}
+static cudaError_t poly_set_attr (int shape) {
+cudaError_t e;
+	switch (shape) {
+	   case 0:  e = poly_attr_one<12, 4, 4> (); if (e == cudaSuccess) e = poly_attr_one<12, 4, 25> (); break;
+	   case 1:  e = poly_attr_one<30, 2, 2> (); if (e == cudaSuccess) e = poly_attr_one<30, 2, 11> (); break;
+	   case 2:  e = poly_attr_one<48, 1, 2> (); if (e == cudaSuccess) e = poly_attr_one<48, 1, 7> (); break;
+	   default: e = poly_attr_one<kRsStageADecim, 8, 10> (); break;
+	}
+	return e;
+}
+template <int D, int GPT, int NG>
+static void poly_launch (Lane *h, const void *src, int64_t pitch, RawFmt rf, const float2 *hist, int hist_len,
+                         float2 *U, float2 *Sb, int32_t M, const LoParams &lp) {
+typedef Poly<D, GPT, NG> P;
+dim3 grid ((unsigned)((M + P::TileOut - 1) / P::TileOut), (unsigned)h -> cfg.n_streams);
+	frontend_poly_kernel<D, GPT, NG><<<grid, kFeThreads, P::SmemBytes, h -> stream>>> (
+	      src, pitch, rf, hist, hist_len, U, Sb, h -> resample ? h -> cap_a : h -> cap_fm, M, lp);
+}
+
+static int launch_frontend (Lane *h, const void *src, RawFmt rf, int64_t pitch, int32_t M) {
 const int S = h -> cfg.n_streams;
-dim3 grid ((unsigned)((M + kFeTileOut - 1) / kFeTileOut), (unsigned)S);
 LoParams lp;
 	memset (&lp, 0, sizeof lp);
 const bool lo = h -> set.lo_hz != 0;
@@ -458,17 +565,36 @@ const bool lo = h -> set.lo_hz != 0;
 	   lp.step128 = (int32_t)s128; lp.phase = h -> lo_phase;
 	   lp.lgain = h -> set.lgain; lp.rgain = h -> set.rgain;
 	}
-	if (h -> set.input_filter_hz > 0) {
-	   if (lo) frontend_wide_kernel<true><<<grid, kFeThreads, kFwSmemBytes, h -> stream>>> (
-	         src, pitch, h -> d_histw [h -> histw_sel], h -> d_Uw, h -> d_Sw, h -> cap_fm, M, lp);
-	   else    frontend_wide_kernel<false><<<grid, kFeThreads, kFwSmemBytes, h -> stream>>> (
-	         src, pitch, h -> d_histw [h -> histw_sel], h -> d_Uw, h -> d_Sw, h -> cap_fm, M, lp);
+const bool wide = h -> set.input_filter_hz > 0;
+const float2 *hist = wide ? h -> d_histw [h -> histw_sel] : h -> d_hist [h -> hist_sel];
+const int hlen = wide ? h -> hist_len_w : h -> hist_len;
+float2 *U = wide ? h -> d_Uw : h -> d_U, *Sb = wide ? h -> d_Sw : h -> d_S;
+	if (h -> resample) { U = h -> d_A; Sb = h -> d_SA; }
+	if (h -> decim == kDecim && rf.fmt == kFmtCF32 && !h -> force_generic) {
+//	   the tuned kernels of the reference's own rate and sample format
+	   const float2 *x = (const float2 *)src;
+	   dim3 grid ((unsigned)((M + kFeTileOut - 1) / kFeTileOut), (unsigned)S);
+	   if (wide) {
+	      if (lo) frontend_wide_kernel<true><<<grid, kFeThreads, kFwSmemBytes, h -> stream>>> (
+	            x, pitch, hist, hlen, U, Sb, h -> cap_fm, M, lp);
+	      else    frontend_wide_kernel<false><<<grid, kFeThreads, kFwSmemBytes, h -> stream>>> (
+	            x, pitch, hist, hlen, U, Sb, h -> cap_fm, M, lp);
+	   }
+	   else {
+	      if (lo) frontend_fir_kernel<true><<<grid, kFeThreads, kFeSmemBytes, h -> stream>>> (
+	            x, pitch, hist, hlen, U, Sb, h -> cap_fm, M, lp);
+	      else    frontend_fir_kernel<false><<<grid, kFeThreads, kFeSmemBytes, h -> stream>>> (
+	            x, pitch, hist, hlen, U, Sb, h -> cap_fm, M, lp);
+	   }
 	}
-	else {
-	   if (lo) frontend_fir_kernel<true><<<grid, kFeThreads, kFeSmemBytes, h -> stream>>> (
-	         src, pitch, hist, h -> d_U, h -> d_S, h -> cap_fm, M, lp);
-	   else    frontend_fir_kernel<false><<<grid, kFeThreads, kFeSmemBytes, h -> stream>>> (
-	         src, pitch, hist, h -> d_U, h -> d_S, h -> cap_fm, M, lp);
+	else switch (h -> shape * 2 + (wide ? 1 : 0)) {
+	   case 0: poly_launch<12, 4, 4>  (h, src, pitch, rf, hist, hlen, U, Sb, M, lp); break;
+	   case 1: poly_launch<12, 4, 25> (h, src, pitch, rf, hist, hlen, U, Sb, M, lp); break;
+	   case 2: poly_launch<30, 2, 2>  (h, src, pitch, rf, hist, hlen, U, Sb, M, lp); break;
+	   case 3: poly_launch<30, 2, 11> (h, src, pitch, rf, hist, hlen, U, Sb, M, lp); break;
+	   case 4: poly_launch<48, 1, 2>  (h, src, pitch, rf, hist, hlen, U, Sb, M, lp); break;
+	   case 5: poly_launch<48, 1, 7> (h, src, pitch, rf, hist, hlen, U, Sb, M, lp); break;
+	   default: poly_launch<kRsStageADecim, 8, 10> (h, src, pitch, rf, hist, hlen, U, Sb, M, lp); break;
 	}
 	h -> launches ++;
 	CK (cudaGetLastError ());
@@ -478,67 +604,95 @@ const bool lo = h -> set.lo_hz != 0;
 // buffers of the wide (input filter ON) front end; cleared start
 static int wide_setup (Lane *h) {
 const int64_t S = h -> cfg.n_streams;
+const size_t HL = (size_t)h -> hist_len_w, DL = (size_t)h -> fw_delay;
 	if (!h -> d_Uw) {
-	   CK (dalloc (&h -> d_histw [0], (size_t)S * kFwHist)); CK (dalloc (&h -> d_histw [1], (size_t)S * kFwHist));
+	   CK (dalloc (&h -> d_histw [0], S * HL)); CK (dalloc (&h -> d_histw [1], S * HL));
 	   CK (dalloc (&h -> d_Uw, (size_t)S * h -> cap_fm)); CK (dalloc (&h -> d_Sw, (size_t)S * h -> cap_fm));
 	   for (int i = 0; i < 2; i ++) {
-	      CK (dalloc (&h -> d_udel [i], (size_t)S * kFwDelay)); CK (dalloc (&h -> d_sdel [i], (size_t)S * kFwDelay));
+	      CK (dalloc (&h -> d_udel [i], S * DL)); CK (dalloc (&h -> d_sdel [i], S * DL));
 	   }
 	   CK (cudaFuncSetAttribute (frontend_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwSmemBytes));
 	   CK (cudaFuncSetAttribute (frontend_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwSmemBytes));
 	}
 	else {
 	   for (int i = 0; i < 2; i ++) {
-	      CK (cudaMemsetAsync (h -> d_histw [i], 0, (size_t)S * kFwHist * sizeof (float2), h -> stream));
-	      CK (cudaMemsetAsync (h -> d_udel [i], 0, (size_t)S * kFwDelay * sizeof (float2), h -> stream));
-	      CK (cudaMemsetAsync (h -> d_sdel [i], 0, (size_t)S * kFwDelay * sizeof (float2), h -> stream));
+	      CK (cudaMemsetAsync (h -> d_histw [i], 0, S * HL * sizeof (float2), h -> stream));
+	      CK (cudaMemsetAsync (h -> d_udel [i], 0, S * DL * sizeof (float2), h -> stream));
+	      CK (cudaMemsetAsync (h -> d_sdel [i], 0, S * DL * sizeof (float2), h -> stream));
 	   }
 	}
 	return SDRJFM_OK;
 }
 
-static int lane_run_frontend_only (Lane *h, const float *d_iq, int64_t n_in, int64_t in_pitch) {
-	if (!h || !d_iq || n_in < kDecim || in_pitch < n_in) return SDRJFM_ERR_ARG;
+static int lane_run_frontend_only (Lane *h, const void *d_iq, int32_t fmt, float scale, int64_t n_in, int64_t in_pitch) {
+	if (!h || !d_iq || n_in < h -> decim || in_pitch < n_in) return SDRJFM_ERR_ARG;
 	if (n_in > h -> cfg.max_samples_per_call) { h -> err = "n_in exceeds max_samples_per_call"; return SDRJFM_ERR_CAPACITY; }
 	CK (cudaSetDevice (h -> cfg.device));
-	return launch_frontend (h, (const float2 *)d_iq, in_pitch, (int32_t)(n_in / kDecim),
-	                        h -> d_hist [h -> hist_sel]);
+RawFmt rf; rf.fmt = fmt; rf.scale = scale;
+	return launch_frontend (h, d_iq, rf, in_pitch, (int32_t)(n_in / h -> decim));
 }
 
 // the launch sequence behind both process entry points; `src` is a device pointer holding
 // (pending | new) samples contiguously per stream with row pitch `pitch`
-static int run_chain (Lane *h, const float2 *src, int64_t pitch, int64_t n_proc,
+static int run_chain (Lane *h, const void *src, RawFmt rf, int64_t pitch, int64_t n_proc,
                       float2 *d_audio_out, int64_t audio_pitch, int64_t *n_audio,
                       float2 *d_rds_out, int64_t rds_pitch, int64_t *n_rds) {
 const int S = h -> cfg.n_streams;
 const Settings &st = h -> set;
 const TableHeader &th = h -> tables.hdr ();
 const float *T = h -> d_tables;
-const int32_t M = (int32_t)(n_proc / kDecim);
+const int32_t M1 = (int32_t)(n_proc / h -> decim);      // front-end (stage A) outputs of this call
+int32_t M = M1;
+	if (h -> resample)      // fm samples that exist once stage-A sample a_total + M1 - 1 does (resample.cuh)
+	   M = (int32_t)(((h -> a_total + M1) * h -> rsL + h -> rsM - 1) / h -> rsM - h -> fm_total);
 	h -> last_nfm = M; h -> last_naudio = 0; h -> last_nrds = 0;
 	if (n_audio) *n_audio = 0;
 	if (n_rds) *n_rds = 0;
-	if (M == 0) return SDRJFM_OK;
+	if (M1 == 0) return SDRJFM_OK;
 int rc;
 //	K1 ------------------------------------------------------------------------------------
 const bool wide = st.input_filter_hz > 0;
-	if ((rc = launch_frontend (h, src, pitch, M, h -> d_hist [h -> hist_sel])) != SDRJFM_OK) return rc;
+	if ((rc = launch_frontend (h, src, rf, pitch, M1)) != SDRJFM_OK) return rc;
 	if (wide) {
-	   roll_history_kernel<<<dim3 (2, S), 160, 0, h -> stream>>> (src, pitch, h -> d_histw [h -> histw_sel],
-	                                                   h -> d_histw [h -> histw_sel ^ 1], n_proc, kFwHist);
+	   roll_history_raw_kernel<<<dim3 ((h -> hist_len_w + 159) / 160, S), 160, 0, h -> stream>>> (
+	         src, pitch, rf, h -> d_histw [h -> histw_sel], h -> d_histw [h -> histw_sel ^ 1], n_proc, h -> hist_len_w);
 	   h -> histw_sel ^= 1;
-	   dim3 g ((unsigned)((std::max (M, kFwDelay) + 255) / 256), (unsigned)S);
-	   fm_delay_kernel<<<g, 256, 0, h -> stream>>> (h -> d_Uw, h -> cap_fm, M, kFwDelay, h -> d_udel [h -> del_sel],
+	   const int DL = h -> fw_delay;
+	   dim3 g ((unsigned)((std::max (M, DL) + 255) / 256), (unsigned)S);
+	   fm_delay_kernel<<<g, 256, 0, h -> stream>>> (h -> d_Uw, h -> cap_fm, M, DL, h -> d_udel [h -> del_sel],
 	                                                h -> d_udel [h -> del_sel ^ 1], h -> d_U);
-	   fm_delay_kernel<<<g, 256, 0, h -> stream>>> (h -> d_Sw, h -> cap_fm, M, kFwDelay, h -> d_sdel [h -> del_sel],
+	   fm_delay_kernel<<<g, 256, 0, h -> stream>>> (h -> d_Sw, h -> cap_fm, M, DL, h -> d_sdel [h -> del_sel],
 	                                                h -> d_sdel [h -> del_sel ^ 1], h -> d_S);
 	   h -> del_sel ^= 1;
 	   h -> launches += 3;
 	}
 	else {
-	   roll_history_kernel<<<dim3 (1, S), 64, 0, h -> stream>>> (src, pitch, h -> d_hist [h -> hist_sel],
-	                                                  h -> d_hist [h -> hist_sel ^ 1], n_proc, kHist);
+	   roll_history_raw_kernel<<<dim3 ((h -> hist_len + 63) / 64, S), 64, 0, h -> stream>>> (
+	         src, pitch, rf, h -> d_hist [h -> hist_sel], h -> d_hist [h -> hist_sel ^ 1], n_proc, h -> hist_len);
 	   h -> hist_sel ^= 1; h -> launches ++;
+	}
+	if (h -> resample) {
+//	   stage B: rational L / M from the stage-A rate to the fm rate
+	   if (M > 0) {
+	      ResampleParams q;
+	      q.L = h -> rsL; q.MB = h -> rsM; q.P = h -> rsP; q.HB = h -> rsHB;
+	      q.a0 = h -> a_total; q.m0 = h -> fm_total; q.M = M;
+//	      group delay of the two symmetric filters in stage-A samples (24 input samples + the prototype's
+//	      centre): the DC estimate subtracted from fm sample m is the one at the CENTRE of its window
+	      q.dA = (int32_t)lround ((kRsStageATaps - 1) / 2.0 / kRsStageADecim + (h -> rsL * h -> rsP - 1) / 2.0 / h -> rsL);
+	      dim3 g ((unsigned)((M + 255) / 256), (unsigned)S);
+	      resample_b_kernel<<<g, 256, 0, h -> stream>>> (h -> d_A, h -> d_SA, h -> cap_a, h -> d_bha [h -> bh_sel],
+	            h -> d_bhs [h -> bh_sel], T + th.off_rsB, q, h -> d_U, h -> d_S, h -> cap_fm);
+	      h -> launches ++;
+	   }
+	   dim3 gr ((unsigned)((h -> rsHB + 63) / 64), (unsigned)S);
+	   roll_history_kernel<<<gr, 64, 0, h -> stream>>> (h -> d_A, h -> cap_a, h -> d_bha [h -> bh_sel],
+	                                                   h -> d_bha [h -> bh_sel ^ 1], M1, h -> rsHB);
+	   roll_history_kernel<<<gr, 64, 0, h -> stream>>> (h -> d_SA, h -> cap_a, h -> d_bhs [h -> bh_sel],
+	                                                   h -> d_bhs [h -> bh_sel ^ 1], M1, h -> rsHB);
+	   h -> bh_sel ^= 1; h -> launches += 2;
+	   h -> a_total += M1;
+	   if (M == 0) { CK (cudaGetLastError ()); return SDRJFM_OK; }
 	}
 //	K2 ------------------------------------------------------------------------------------
 const float *consts = h -> tables.payload () + th.off_comp_consts;
@@ -546,7 +700,8 @@ DiscrParams dp;
 	dp.sumC = consts [0]; dp.sumCm = consts [1];
 	dp.gb0 = consts [5]; dp.gb1 = consts [6]; dp.gb2 = consts [7];
 	if (wide) { dp.sumC = h -> wide_sumC; dp.sumCm = h -> wide_sumCm; dp.gb0 = dp.gb1 = dp.gb2 = 0.f; }
-	dp.lo_tab = nullptr; dp.lo_rate = h -> cfg.input_rate; dp.lo_hz = st.lo_hz; dp.lo_moff = wide ? -kFwDelay : 0;
+	dp.lo_tab = nullptr; dp.lo_rate = h -> cfg.input_rate; dp.lo_hz = st.lo_hz; dp.lo_moff = wide ? -h -> fw_delay : 0;
+	dp.decim = h -> decim;
 	dp.lo_phase = h -> lo_phase; dp.Hre = h -> lo_Hre; dp.Him = h -> lo_Him;
 	if (st.lo_hz != 0) {
 	   dp.lo_tab = h -> d_lo_tab;
@@ -555,7 +710,13 @@ DiscrParams dp;
 	}
 	dp.Gre = consts [2]; dp.Gim = consts [3];
 	dp.alpha = (double)(1.0f / h -> cfg.input_rate);          // rfDcAlpha, fm-processor.cpp:379
-	dp.beta = pow (1.0 - dp.alpha, (double)kDecim);
+	dp.beta = pow (1.0 - dp.alpha, (double)h -> decim);
+	if (h -> resample) {
+//	   unit-gain real cascade (every polyphase branch normalised), no DC folding; the estimate advances
+//	   by inputRate / fmRate input samples per fm sample on average
+	   dp.sumC = dp.sumCm = 1.f; dp.gb0 = dp.gb1 = dp.gb2 = 0.f; dp.Gre = 1.f; dp.Gim = 0.f;
+	   dp.beta = pow (1.0 - dp.alpha, (double)h -> cfg.input_rate / (double)h -> cfg.fm_rate);
+	}
 	dp.lgain = st.lgain; dp.rgain = st.rgain;
 	dp.dc_remove = st.dc_remove; dp.decoder = st.decoder;
 const int32_t ntiles = (M + kDiBlock - 1) / kDiBlock;
@@ -696,43 +857,48 @@ const int64_t apitch = d_audio_out ? audio_pitch : h -> cap_audio;
 	return SDRJFM_OK;
 }
 
-// stage (pending | new) samples when the call is not aligned to 12; returns the source to read
-static int stage_input (Lane *h, const float *iq, int64_t n_in, int64_t in_pitch,
-                        cudaMemcpyKind kind, const float2 **src, int64_t *pitch, int64_t *n_proc) {
+// stage (pending | new) samples when the call is not aligned to the decimation; returns the source to
+// read.  Samples are moved as bytes (bps = bytes per IQ sample of the call's format).
+static int stage_input (Lane *h, const void *iq, int fmt, int64_t n_in, int64_t in_pitch,
+                        cudaMemcpyKind kind, const void **src, int64_t *pitch, int64_t *n_proc) {
 const int S = h -> cfg.n_streams;
+const int D = h -> decim;
+const size_t bps = (size_t)fmt_bytes (fmt);
+	if (h -> pend && fmt != h -> pend_fmt) { h -> err = "sample format changed while samples were pending"; return SDRJFM_ERR_ARG; }
 const int64_t total = h -> pend + n_in;
-	*n_proc = (total / kDecim) * kDecim;
-	if (kind == cudaMemcpyDeviceToDevice && h -> pend == 0 && *n_proc == n_in) {
-	   *src = (const float2 *)iq; *pitch = in_pitch;       // zero-copy
+	*n_proc = (total / D) * D;
+//	zero-copy needs rows the kernel can address as whole samples
+	if (kind == cudaMemcpyDeviceToDevice && h -> pend == 0 && *n_proc == n_in && ((uintptr_t)iq % bps) == 0) {
+	   *src = iq; *pitch = in_pitch;
 	   return SDRJFM_OK;
 	}
+char *din = (char *)h -> d_in; char *dp = (char *)h -> d_pend;
+const size_t rowb = (size_t)h -> cap_in * bps;
 	if (h -> pend)
-	   CK (cudaMemcpy2DAsync (h -> d_in, h -> cap_in * sizeof (float2), h -> d_pend,
-	                          kDecim * sizeof (float2), h -> pend * sizeof (float2), S,
-	                          cudaMemcpyDeviceToDevice, h -> stream));
+	   CK (cudaMemcpy2DAsync (din, rowb, dp, D * bps, h -> pend * bps, S, cudaMemcpyDeviceToDevice, h -> stream));
 	if (n_in)
-	   CK (cudaMemcpy2DAsync (h -> d_in + h -> pend, h -> cap_in * sizeof (float2), iq,
-	                          in_pitch * sizeof (float2), n_in * sizeof (float2), S, kind, h -> stream));
+	   CK (cudaMemcpy2DAsync (din + h -> pend * bps, rowb, iq, in_pitch * bps, n_in * bps, S, kind, h -> stream));
 const int newpend = (int)(total - *n_proc);
 	if (newpend)
-	   CK (cudaMemcpy2DAsync (h -> d_pend, kDecim * sizeof (float2), h -> d_in + *n_proc,
-	                          h -> cap_in * sizeof (float2), newpend * sizeof (float2), S,
+	   CK (cudaMemcpy2DAsync (dp, D * bps, din + *n_proc * bps, rowb, newpend * bps, S,
 	                          cudaMemcpyDeviceToDevice, h -> stream));
-	h -> pend = newpend;
+	h -> pend = newpend; h -> pend_fmt = fmt;
 	*src = h -> d_in; *pitch = h -> cap_in;
 	return SDRJFM_OK;
 }
 
-static int lane_process_device (Lane *h, const float *d_iq, int64_t n_in, int64_t in_pitch,
+static int lane_process_device (Lane *h, const void *d_iq, int32_t fmt, float scale, int64_t n_in, int64_t in_pitch,
                            float *d_audio, int64_t audio_pitch, int64_t *n_audio,
                            float *d_rds24, int64_t rds_pitch, int64_t *n_rds) {
 	if (!h || n_in < 0 || (n_in > 0 && (!d_iq || in_pitch < n_in))) return SDRJFM_ERR_ARG;
+	if (fmt < kFmtCF32 || fmt > kFmtS16) return SDRJFM_ERR_ARG;
 	if (n_in > h -> cfg.max_samples_per_call) { h -> err = "n_in exceeds max_samples_per_call"; return SDRJFM_ERR_CAPACITY; }
 	CK (cudaSetDevice (h -> cfg.device));
-const float2 *src; int64_t pitch, n_proc;
-int rc = stage_input (h, d_iq, n_in, in_pitch, cudaMemcpyDeviceToDevice, &src, &pitch, &n_proc);
+const void *src; int64_t pitch, n_proc;
+int rc = stage_input (h, d_iq, fmt, n_in, in_pitch, cudaMemcpyDeviceToDevice, &src, &pitch, &n_proc);
 	if (rc != SDRJFM_OK) return rc;
-	return run_chain (h, src, pitch, n_proc, (float2 *)d_audio, audio_pitch, n_audio,
+RawFmt rf; rf.fmt = fmt; rf.scale = scale;
+	return run_chain (h, src, rf, pitch, n_proc, (float2 *)d_audio, audio_pitch, n_audio,
 	                  (float2 *)d_rds24, rds_pitch, n_rds);
 }
 
@@ -848,6 +1014,7 @@ static int lane_set_bandwidth (Lane *h, int32_t hz) {
 //	Switching the filter on (or changing it) starts it from a cleared state.
 	CK (cudaSetDevice (h -> cfg.device));
 	const int32_t v = hz > 0 ? hz : 0;
+	if (v > 0 && h -> resample) { h -> err = "inputFilter is not available in the resampler mode"; return SDRJFM_ERR_UNSUPPORTED; }
 	if (v == h -> set.input_filter_hz) return SDRJFM_OK;
 	h -> set.input_filter_hz = v;
 	int rc = rebuild_tables (h);
@@ -876,6 +1043,7 @@ static int lane_set_local_oscillator (Lane *h, int32_t hz) {
 //	set_localOscillator (:865-867).  The oscillator table (inputRate complex entries, oscillator.cpp:26-37)
 //	is built the first time lo is non-zero.
 	if (hz <= -h -> cfg.input_rate || hz >= h -> cfg.input_rate) return SDRJFM_ERR_ARG;
+	if (hz != 0 && h -> resample) { h -> err = "the local oscillator is not available in the resampler mode"; return SDRJFM_ERR_UNSUPPORTED; }
 	CK (cudaSetDevice (h -> cfg.device));
 	if (hz != 0 && !h -> d_lo_tab) {
 	   const int32_t R = h -> cfg.input_rate;

@@ -151,15 +151,31 @@ int sdrjfm_sync (sdrjfm_handle *h) {
 	return for_lanes (h, [](Lane *l) { return lane_sync (l); });
 }
 
-int sdrjfm_process_device (sdrjfm_handle *h, const float *d_iq, int64_t n_in, int64_t in_pitch,
-                           float *d_audio, int64_t audio_pitch, int64_t *n_audio,
-                           float *d_rds24, int64_t rds_pitch, int64_t *n_rds) {
+// scale of a device sample format: what the reference's handler divides by (power of two: exact)
+static int raw_scale (sdrjfm_handle *h, int32_t format, int32_t denominator, float *scale) {
+	switch (format) {
+	   case SDRJFM_IQ_CF32: *scale = 1.0f; return SDRJFM_OK;
+	   case SDRJFM_IQ_U8: case SDRJFM_IQ_S8: *scale = 1.0f / 128.0f; return SDRJFM_OK;
+	   case SDRJFM_IQ_S16:
+	      if (denominator <= 0 || (denominator & (denominator - 1)) != 0) {
+	         h -> err = "int16 denominator must be a power of two (2048, 4096, 8192 in the reference's handlers)";
+	         return SDRJFM_ERR_ARG;
+	      }
+	      *scale = 1.0f / (float)denominator; return SDRJFM_OK;
+	   default: h -> err = "unknown sample format"; return SDRJFM_ERR_ARG;
+	}
+}
+
+static int process_dev (sdrjfm_handle *h, const void *d_iq, int32_t fmt, float scale, int64_t n_in, int64_t in_pitch,
+                        float *d_audio, int64_t audio_pitch, int64_t *n_audio,
+                        float *d_rds24, int64_t rds_pitch, int64_t *n_rds) {
 	if (!h || n_in < 0 || (n_in > 0 && (!d_iq || in_pitch < n_in))) return SDRJFM_ERR_ARG;
 	if (n_in > h -> cfg.max_samples_per_call) { h -> err = "n_in exceeds max_samples_per_call"; return SDRJFM_ERR_CAPACITY; }
 	HK (cudaSetDevice (h -> cfg.device));
 int64_t na = 0, nr = 0;
+const int64_t bps = fmt_bytes (fmt);
 const int rc = fork_join (h, [&](Lane *l, int32_t s0) {
-	   return lane_process_device (l, d_iq + 2 * (int64_t)s0 * in_pitch, n_in, in_pitch,
+	   return lane_process_device (l, (const char *)d_iq + bps * (int64_t)s0 * in_pitch, fmt, scale, n_in, in_pitch,
 	                               d_audio ? d_audio + 2 * (int64_t)s0 * audio_pitch : nullptr, audio_pitch, &na,
 	                               d_rds24 ? d_rds24 + 2 * (int64_t)s0 * rds_pitch : nullptr, rds_pitch, &nr);
 	});
@@ -168,28 +184,59 @@ const int rc = fork_join (h, [&](Lane *l, int32_t s0) {
 	return rc;
 }
 
+int sdrjfm_process_device (sdrjfm_handle *h, const float *d_iq, int64_t n_in, int64_t in_pitch,
+                           float *d_audio, int64_t audio_pitch, int64_t *n_audio,
+                           float *d_rds24, int64_t rds_pitch, int64_t *n_rds) {
+	return process_dev (h, d_iq, SDRJFM_IQ_CF32, 1.0f, n_in, in_pitch, d_audio, audio_pitch, n_audio,
+	                    d_rds24, rds_pitch, n_rds);
+}
+
+int sdrjfm_process_raw_device (sdrjfm_handle *h, const void *d_iq, int32_t format, int32_t denominator,
+                               int64_t n_in, int64_t in_pitch,
+                               float *d_audio, int64_t audio_pitch, int64_t *n_audio,
+                               float *d_rds24, int64_t rds_pitch, int64_t *n_rds) {
+	if (!h) return SDRJFM_ERR_ARG;
+float scale;
+int rc = raw_scale (h, format, denominator, &scale);
+	if (rc != SDRJFM_OK) return rc;
+	return process_dev (h, d_iq, format, scale, n_in, in_pitch, d_audio, audio_pitch, n_audio,
+	                    d_rds24, rds_pitch, n_rds);
+}
+
 int sdrjfm_run_frontend_only (sdrjfm_handle *h, const float *d_iq, int64_t n_in, int64_t in_pitch) {
+	return sdrjfm_run_frontend_only_raw (h, d_iq, SDRJFM_IQ_CF32, 1, n_in, in_pitch);
+}
+
+int sdrjfm_run_frontend_only_raw (sdrjfm_handle *h, const void *d_iq, int32_t format, int32_t denominator,
+                                  int64_t n_in, int64_t in_pitch) {
 	if (!h || !d_iq) return SDRJFM_ERR_ARG;
+float scale;
+int rc = raw_scale (h, format, denominator, &scale);
+	if (rc != SDRJFM_OK) return rc;
 	HK (cudaSetDevice (h -> cfg.device));
+const int64_t bps = fmt_bytes (format);
 	return fork_join (h, [&](Lane *l, int32_t s0) {
-	   return lane_run_frontend_only (l, d_iq + 2 * (int64_t)s0 * in_pitch, n_in, in_pitch);
+	   return lane_run_frontend_only (l, (const char *)d_iq + bps * (int64_t)s0 * in_pitch, format, scale, n_in, in_pitch);
 	});
 }
 
-int sdrjfm_process (sdrjfm_handle *h, const float *iq, int64_t n_in, int64_t in_pitch,
-                    float *audio, int64_t audio_pitch, int64_t *n_audio,
-                    float *rds24, int64_t rds_pitch, int64_t *n_rds, sdrjfm_meta *meta) {
+static int process_host (sdrjfm_handle *h, const void *iq, int32_t fmt, float scale, int64_t n_in, int64_t in_pitch,
+                         float *audio, int64_t audio_pitch, int64_t *n_audio,
+                         float *rds24, int64_t rds_pitch, int64_t *n_rds, sdrjfm_meta *meta) {
 	if (!h || n_in < 0 || (n_in > 0 && (!iq || in_pitch < n_in))) return SDRJFM_ERR_ARG;
 	if (n_in > h -> cfg.max_samples_per_call) { h -> err = "n_in exceeds max_samples_per_call"; return SDRJFM_ERR_CAPACITY; }
 	HK (cudaSetDevice (h -> cfg.device));
 const int S = h -> cfg.n_streams;
+const size_t bps = (size_t)fmt_bytes (fmt);
+const size_t rowb = (size_t)h -> cap_in * bps;                 // staging row pitch in bytes
 int rc;
 int64_t na = 0, nr = 0;
 //	Large offline calls (no tap read-back wanted): the call is cut into time slices and the
 //	host->device copy of slice c+1 runs on a second stream while slice c computes.  The chain is
 //	stateful, so this is exactly the sequence of smaller calls the GUI cadence would make.
 const int64_t kSlices = 8;
-const int64_t slice = ((n_in / kSlices) / 3072) * 3072;          // multiple of 12 * 256
+const int64_t unit = 256 * (int64_t)h -> lanes [0] -> decim;
+const int64_t slice = ((n_in / kSlices) / unit) * unit;          // multiple of the decimation
 	if (!h -> cfg.keep_taps && slice >= (1 << 16)) {
 	   if (!h -> copy_stream) {
 	      HK (cudaStreamCreateWithFlags (&h -> copy_stream, cudaStreamNonBlocking));
@@ -205,15 +252,14 @@ const int64_t slice = ((n_in / kSlices) / 3072) * 3072;          // multiple of 
 	      const int64_t len = rest < 2 * slice ? rest : slice;     // the last slice takes the ragged tail
 	      const int b = c & 1;
 	      if (c >= 2) HK (cudaStreamWaitEvent (h -> copy_stream, h -> ev_done [b], 0));
-	      HK (cudaMemcpy2DAsync (h -> d_in [b], h -> cap_in * sizeof (float2), (const float2 *)iq + pos,
-	                             in_pitch * sizeof (float2), len * sizeof (float2), S,
-	                             cudaMemcpyHostToDevice, h -> copy_stream));
+	      HK (cudaMemcpy2DAsync (h -> d_in [b], rowb, (const char *)iq + pos * bps,
+	                             in_pitch * bps, len * bps, S, cudaMemcpyHostToDevice, h -> copy_stream));
 	      HK (cudaEventRecord (h -> ev_h2d [b], h -> copy_stream));
 	      HK (cudaStreamWaitEvent (h -> stream, h -> ev_h2d [b], 0));
 	      int64_t a1 = 0, r1 = 0;
-	      rc = sdrjfm_process_device (h, (const float *)h -> d_in [b], len, h -> cap_in,
-	                                  (float *)(h -> d_audio + na), h -> cap_audio, &a1,
-	                                  (float *)(h -> d_rds24 + nr), h -> cap_rds, &r1);
+	      rc = process_dev (h, h -> d_in [b], fmt, scale, len, h -> cap_in,
+	                        (float *)(h -> d_audio + na), h -> cap_audio, &a1,
+	                        (float *)(h -> d_rds24 + nr), h -> cap_rds, &r1);
 	      if (rc != SDRJFM_OK) return rc;
 	      HK (cudaEventRecord (h -> ev_done [b], h -> stream));
 	      na += a1; nr += r1; pos += len; c ++;
@@ -221,10 +267,10 @@ const int64_t slice = ((n_in / kSlices) / 3072) * 3072;          // multiple of 
 	}
 	else {
 	   if (n_in)
-	      HK (cudaMemcpy2DAsync (h -> d_in [0], h -> cap_in * sizeof (float2), iq, in_pitch * sizeof (float2),
-	                             n_in * sizeof (float2), S, cudaMemcpyHostToDevice, h -> stream));
-	   rc = sdrjfm_process_device (h, (const float *)h -> d_in [0], n_in, h -> cap_in, (float *)h -> d_audio,
-	                               h -> cap_audio, &na, (float *)h -> d_rds24, h -> cap_rds, &nr);
+	      HK (cudaMemcpy2DAsync (h -> d_in [0], rowb, iq, in_pitch * bps, n_in * bps, S,
+	                             cudaMemcpyHostToDevice, h -> stream));
+	   rc = process_dev (h, h -> d_in [0], fmt, scale, n_in, h -> cap_in, (float *)h -> d_audio,
+	                     h -> cap_audio, &na, (float *)h -> d_rds24, h -> cap_rds, &nr);
 	   if (rc != SDRJFM_OK) return rc;
 	}
 	if (audio && na > 0) {
@@ -244,6 +290,25 @@ const int64_t slice = ((n_in / kSlices) / 3072) * 3072;          // multiple of 
 	if (n_rds) *n_rds = nr;
 	if (meta) return sdrjfm_get_meta (h, meta);
 	return SDRJFM_OK;
+}
+
+int sdrjfm_process (sdrjfm_handle *h, const float *iq, int64_t n_in, int64_t in_pitch,
+                    float *audio, int64_t audio_pitch, int64_t *n_audio,
+                    float *rds24, int64_t rds_pitch, int64_t *n_rds, sdrjfm_meta *meta) {
+	return process_host (h, iq, SDRJFM_IQ_CF32, 1.0f, n_in, in_pitch, audio, audio_pitch, n_audio,
+	                     rds24, rds_pitch, n_rds, meta);
+}
+
+int sdrjfm_process_raw (sdrjfm_handle *h, const void *iq, int32_t format, int32_t denominator,
+                        int64_t n_in, int64_t in_pitch,
+                        float *audio, int64_t audio_pitch, int64_t *n_audio,
+                        float *rds24, int64_t rds_pitch, int64_t *n_rds, sdrjfm_meta *meta) {
+	if (!h) return SDRJFM_ERR_ARG;
+float scale;
+int rc = raw_scale (h, format, denominator, &scale);
+	if (rc != SDRJFM_OK) return rc;
+	return process_host (h, iq, format, scale, n_in, in_pitch, audio, audio_pitch, n_audio,
+	                     rds24, rds_pitch, n_rds, meta);
 }
 
 int sdrjfm_get_meta (sdrjfm_handle *h, sdrjfm_meta *meta) {

@@ -121,6 +121,45 @@ std::vector<cf32> v (nfft, cf32 (0, 0));      // fft-filters.cpp:74-81 / :87-94
 	return v;
 }
 
+// Rational polyphase resampler input_rate -> fm_rate in two stages (resample.cuh):
+//   A: 49-tap Blackman-windowed sinc, cut-off 0.1 fs, /5
+//   B: L / M = 5 fm_rate / input_rate (reduced), prototype = Blackman-windowed sinc at rate L fa with
+//      cut-off fm_rate / 2, L * P taps, P = ceil (8 M / L); phase phi holds h[phi + L j], unit DC gain
+// Designed in double, stored as float.
+static double blackman (int i, int n) {
+	return 0.42 - 0.5 * cos (2 * M_PI * i / (n - 1)) + 0.08 * cos (4 * M_PI * i / (n - 1));
+}
+static double sinc_lp (double fc, double t) {       // ideal low-pass, cut-off fc (cycles / sample), at time t
+	return t == 0.0 ? 2 * fc : sin (2 * M_PI * fc * t) / (M_PI * t);
+}
+bool design_resampler (int32_t input_rate, int32_t fm_rate, int &L, int &M, int &P,
+                       std::vector<float> &hA, std::vector<float> &hB) {
+const int DA = 5;
+	if (input_rate % DA != 0) return false;
+int64_t a = (int64_t)DA * fm_rate, b = input_rate;
+	while (b) { int64_t t = a % b; a = b; b = t; }
+	L = (int)((int64_t)DA * fm_rate / a); M = (int)(input_rate / a);
+	P = (8 * M + L - 1) / L;
+	if (L < 1 || L > 16 || P > 128 || M < L) return false;
+const int NA = 49;
+	{  std::vector<double> d (NA); double sum = 0;
+	   for (int i = 0; i < NA; i ++) { d [i] = sinc_lp (0.1, i - (NA - 1) / 2.0) * blackman (i, NA); sum += d [i]; }
+	   hA.resize (NA);
+	   for (int i = 0; i < NA; i ++) hA [i] = (float)(d [i] / sum); }
+const int NB = L * P;
+const double fc = 0.5 * (double)fm_rate / ((double)input_rate / DA * L);
+	hB.assign ((size_t)NB, 0.f);
+	for (int phi = 0; phi < L; phi ++) {
+	   std::vector<double> d (P); double sum = 0;
+	   for (int j = 0; j < P; j ++) {
+	      const int k = phi + L * j;
+	      d [j] = sinc_lp (fc, k - (NB - 1) / 2.0) * blackman (k, NB); sum += d [j];
+	   }
+	   for (int j = 0; j < P; j ++) hB [(size_t)phi * P + j] = (float)(d [j] / sum);
+	}
+	return true;
+}
+
 namespace {
 struct Packer {
 	std::vector<float> f;
@@ -181,12 +220,13 @@ Packer pk;
 	for (int i = 0; i < h.ncomp; i ++)
 	   for (int k = i + 1; k < h.ncomp; k ++) gt [i] += (double)(float)cd [k];
 	std::vector<float> comp (h.ncomp);
+	const int D = h.decim1 * h.decim2;
 	double sumC = 0, sumCm = 0, gbar [3] = { 0, 0, 0 };
 	for (int i = 0; i < h.ncomp; i ++) {
 	   const double c = (double)(float)cd [i];
 	   comp [i] = (float)(c + alpha * gt [i]);
 	   sumC += c; sumCm += comp [i];
-	   if (i < 36) gbar [i / 12] += gt [i] / 12.0;
+	   if (i / D < 3) gbar [i / D] += gt [i] / (double)D;      // means over the D-sample blocks S[m], S[m-1], S[m-2]
 	}
 	h.off_comp = pk.put (comp);
 	std::complex<double> g1 ((double)k1 [h.ntaps1 / 2].real () / k1 [h.ntaps1 / 2].imag (), 1.0);
@@ -270,6 +310,15 @@ Packer pk;
 	   std::vector<float> wide (h.ncomp_wide);
 	   for (int i = 0; i < h.ncomp_wide; i ++) wide [i] = (float)wd [i];
 	   h.off_comp_wide = pk.put (wide);
+	}
+//	rational polyphase resampler (new block, resample.cuh)
+	{
+	   int L, M, P; std::vector<float> hA, hB;
+	   if (design_resampler (input_rate, fm_rate, L, M, P, hA, hB)) {
+	      h.rs_L = L; h.rs_M = M; h.rs_P = P; h.rs_ntapsA = (int32_t)hA.size ();
+	      h.off_rsA = pk.put (hA);
+	      h.off_rsB = pk.put (hB);
+	   }
 	}
 	while (pk.f.size () % 4) pk.f.push_back (0.0f);
 	h.payload_floats = (int64_t)pk.f.size ();

@@ -58,6 +58,10 @@ struct TableHeader {
 	int64_t  off_comp_wide;     // composite of input filter and the decimator cascade
 	int32_t  ncomp_wide;
 	int32_t  reserved1;
+	// rational polyphase resampler (front_end_mode 1, resample.cuh); rs_L = 0 when the rates admit none
+	int32_t  rs_L, rs_M, rs_P, rs_ntapsA;   // stage B: up L, down M, P taps per phase; stage A taps (49)
+	int64_t  off_rsA;                        // rs_ntapsA real taps, unit DC gain
+	int64_t  off_rsB;                        // [rs_L][rs_P] real taps, every phase unit DC gain
 };
 
 struct TableBlob {
@@ -75,6 +79,11 @@ std::vector<cf32>  design_lowpass (int ntaps, int32_t fc, int32_t fs);
 std::vector<cf32>  design_bandpass (int ntaps, int32_t low, int32_t high, int32_t fs);
 void               fft_radix2_reference_order (cf32 *v, int n);            // same op order as fft-complex.cpp:50-102
 std::vector<cf32>  fft_twiddles (int n);
+
+// rational resampler design (resample.cuh): false when 5 * fm_rate / input_rate does not reduce to
+// L / M with L <= 16 and P <= 128
+bool design_resampler (int32_t input_rate, int32_t fm_rate, int &L, int &M, int &P,
+                       std::vector<float> &hA, std::vector<float> &hB);
 
 TableBlob build_tables (int32_t input_rate, int32_t fm_rate, int32_t input_filter_hz,
                         int32_t audio_lp_hz);

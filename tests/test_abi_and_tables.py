@@ -37,7 +37,7 @@ def test_bad_arguments(pkg):
     L = pkg.lib()
     st = C.c_int(0)
     assert not L.sdrjfm_create(None, C.byref(st)) and st.value == pkg.ERR_ARG
-    cfg = pkg.Config(2400000, 192000, 48000, 48000, 1, 0, 1000, 0, 0)
+    cfg = pkg.Config(1920000, 192000, 48000, 48000, 1, 0, 1000, 0, 0)   # colibri's rate: stage 2 would decimate by 1
     assert not L.sdrjfm_create(C.byref(cfg), C.byref(st)) and st.value == pkg.ERR_UNSUPPORTED
     assert L.sdrjfm_design_tables(100, 192000, 0, 0, None, 0) == pkg.ERR_ARG
 
@@ -78,3 +78,17 @@ def test_composite_equals_cascade(pkg):
     assert np.abs(comp - casc).max() < 3e-7 * np.abs(casc).max()
     assert abs(T.consts[0] - C.sum()) < 1e-6
     assert abs(T.consts[1] - T.composite.astype(np.float64).sum()) < 1e-6
+
+
+@pytest.mark.parametrize("fs", [2400000, 6000000, 10000000])
+def test_tables_at_device_rates_match_reference_constructors(pkg, chainlib, ref_available, fs):
+    """BASELINE config 4: at 2.4 / 6 / 10 MS/s the reference's constructor arithmetic gives stage 2
+    = IRate/192000 + 1 taps, /(IRate/192000); the host designer must build the same kernels."""
+    which = "ref" if ref_available else "orc"
+    T = pkg.design_tables(input_rate=fs)
+    c = chainlib.Chain(which, input_rate=fs)
+    assert _same(T.fmband1, c.dump("fmband1"))
+    assert _same(T.fmband2, c.dump("fmband2"))
+    d = pkg.front_end_decimation(fs)
+    assert d == int(T.hdr["decim1"]) * int(T.hdr["decim2"]) == {2400000: 12, 6000000: 30, 10000000: 48}[fs]
+    assert int(T.hdr["ncomp"]) == 25 + 6 * (d // 6)
