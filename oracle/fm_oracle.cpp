@@ -11,7 +11,7 @@
  *   radix-2 FFT                                src/various/fft-complex.cpp:50-102
  *   tap designers                              src/various/fir-filters.cpp:41-62,197-222,327-347
  *   DecimatingFIR::Pass                        src/various/fir-filters.cpp:397-424
- *   fm_Demodulator (decoders 2..6)             src/fm/fm-demodulator.cpp:51-205
+ *   fm_Demodulator (decoders 1..6)             src/fm/fm-demodulator.cpp:51-241
  *   pllC                                       src/various/pllC.cpp:38-90
  *   compAtan                                   src/various/Xtan2.cpp:12-100
  *   SinCos                                     src/various/sincos.cpp:36-91
@@ -383,6 +383,17 @@ struct Oracle {
 	   if (zAbs <= 0.001) I = Q = 0.001;
 	   else { I = real (z) / zAbs; Q = imag (z) / zAbs; }
 	   am_carr = (1.0f - carrierAlpha) * am_carr + carrierAlpha * zAbs;
+	   if (cfg.decoder == 1) {                                              // decodeAM, :215-241
+	      do_pll (z);                                                       // on the RAW sample: AFC read-out only
+	      res = pllIncr;
+	      fm_afc = (1 - fmDcAlpha) * fm_afc + fmDcAlpha * res;
+	      float gainLimit = 0.01f;
+	      res = (std::abs (z) - am_carr) / (am_carr < gainLimit ? gainLimit : am_carr);
+	      float audioLimit = 1.0f;
+	      if (res > audioLimit) res = audioLimit;
+	      else if (res < -audioLimit) res = -audioLimit;
+	      return res;
+	   }
 	   z = cf (I, Q);
 	   int index = 0;
 	   float Scaler = sqrt (2);

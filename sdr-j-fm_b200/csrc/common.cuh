@@ -34,6 +34,19 @@ float2 o;
 	return o;
 }
 
+// the same with the tap already duplicated into a register pair (taps stored as float2 {c, c} in
+// constant memory: one 64-bit constant load feeds the instruction directly, no packing moves)
+__device__ __forceinline__ float2 ffma2p (float2 cc, float2 w, float2 acc) {
+unsigned long long a, b, d, r;
+	asm ("mov.b64 %0, {%1,%2};" : "=l"(a) : "f"(cc.x), "f"(cc.y));
+	asm ("mov.b64 %0, {%1,%2};" : "=l"(b) : "f"(w.x), "f"(w.y));
+	asm ("mov.b64 %0, {%1,%2};" : "=l"(d) : "f"(acc.x), "f"(acc.y));
+	asm ("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(d));
+float2 o;
+	asm ("mov.b64 {%0,%1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(r));
+	return o;
+}
+
 // std::complex<float> operator* as GCC emits it without -ffast-math: four products, each
 // rounded, then one subtraction and one addition.
 __device__ __forceinline__ float2 cmul_rn (float2 a, float2 b) {

@@ -330,7 +330,7 @@ double pw [6];
 	         const int64_t o = (int64_t)stream * pitch + j0 + j;
 	         res_raw [o] = res;
 	         zabs [o] = za [j];
-	         if (iqn) iqn [o] = nq [j];
+	         if (iqn) iqn [o] = P.decoder == 1 ? z [j] : nq [j];       // AM: pllC runs on the raw sample
 	         if (fmz) fmz [o] = z [j];
 	      }
 	   }

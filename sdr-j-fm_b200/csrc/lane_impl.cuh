@@ -253,8 +253,9 @@ const int ncomp = h -> resample ? th.rs_ntapsA : th.ncomp;
 //	PSS low-pass taps: lpFilter (2048, 295).setLowPass (15000, rate), stereo-separation.cpp:31-39
 	{
 	   std::vector<cf32> lp = design_lowpass (kPssTaps, 15000, th.fm_rate);
-	   float t [kPssTaps + 1] = { 0 };
-	   for (int i = 0; i < kPssTaps; i ++) t [i] = lp [i].real ();
+	   float2 t [kPssTaps + 1];
+	   memset (t, 0, sizeof t);
+	   for (int i = 0; i < kPssTaps; i ++) t [i] = make_float2 (lp [i].real (), lp [i].real ());
 	   CK (cudaMemcpyToSymbol (c_pss_taps, t, sizeof t));
 	}
 
@@ -288,6 +289,8 @@ SinLut &L = h -> lut;
 	         else h -> smem_lut_ok = false;
 	      }
 	   }
+	   L.sin_at_half = sc [R / 2].imag ();
+	   for (int e = 0; e < ns; e ++) if (L.sin_exc_idx [e] != R / 2) h -> smem_lut_ok = false;
 	   if (h -> smem_lut_ok) {
 	      if (h -> d_sin_quarter) cudaFree (h -> d_sin_quarter);
 	      CK (cudaMalloc ((void **)&h -> d_sin_quarter, (Q + 1) * sizeof (float)));
@@ -474,9 +477,11 @@ cudaError_t e;
 	    (e = cudaFuncSetAttribute (frontend_fir_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                               kFeSmemBytes)) != cudaSuccess) return fail (e, "smem attr K1");
 	if ((e = poly_set_attr (shape)) != cudaSuccess) return fail (e, "smem attr K1g");
-	if ((e = cudaFuncSetAttribute (sequential_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	if ((e = cudaFuncSetAttribute (sequential_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                               (cfg -> fm_rate / 4 + 1) * (int)sizeof (float))) != cudaSuccess ||
-	    (e = cudaFuncSetAttribute (sequential_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    (e = cudaFuncSetAttribute (sequential_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                               (cfg -> fm_rate / 4 + 1) * (int)sizeof (float))) != cudaSuccess ||
+	    (e = cudaFuncSetAttribute (sequential_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                               (cfg -> fm_rate / 4 + 1) * (int)sizeof (float))) != cudaSuccess)
 	   return fail (e, "smem attr K3");
 	if ((e = cudaFuncSetAttribute (pilot_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -727,7 +732,7 @@ const int32_t ntiles = (M + kDiBlock - 1) / kDiBlock;
 	   discriminator_kernel<<<g, kDiThreads, 0, h -> stream>>> (
 	         h -> d_U, h -> d_S, h -> cap_fm, M, dp, T + th.off_atan, T + th.off_arcsine,
 	         h -> d_state, h -> d_tileB, ntiles, h -> d_snap, h -> d_res, h -> d_zabs,
-	         st.decoder == 2 ? h -> d_iqn : nullptr, h -> cfg.keep_taps ? h -> d_fmz : nullptr);
+	         (st.decoder == 2 || st.decoder == 1) ? h -> d_iqn : nullptr, h -> cfg.keep_taps ? h -> d_fmz : nullptr);
 	   h -> launches += 2;
 	}
 //	K3 ------------------------------------------------------------------------------------
@@ -749,11 +754,15 @@ SeqParams sp;
 const int seq_blocks = (S + kSeqLanes - 1) / kSeqLanes;
 const size_t seq_smem = (h -> lut.quarter + 1) * sizeof (float);
 	if (st.decoder == 2)
-	   sequential_kernel<true><<<seq_blocks, kSeqLanes, seq_smem, h -> stream>>> (
+	   sequential_kernel<1><<<seq_blocks, kSeqLanes, seq_smem, h -> stream>>> (
+	         h -> d_res, h -> d_zabs, h -> d_iqn, h -> cap_fm, M, sp, h -> lut, T + th.off_atan,
+	         h -> d_state, h -> d_demod, h -> d_phase, h -> d_locked);
+	else if (st.decoder == 1)
+	   sequential_kernel<2><<<seq_blocks, kSeqLanes, seq_smem, h -> stream>>> (
 	         h -> d_res, h -> d_zabs, h -> d_iqn, h -> cap_fm, M, sp, h -> lut, T + th.off_atan,
 	         h -> d_state, h -> d_demod, h -> d_phase, h -> d_locked);
 	else if (h -> sequential_pll)
-	   sequential_kernel<false><<<seq_blocks, kSeqLanes, seq_smem, h -> stream>>> (
+	   sequential_kernel<0><<<seq_blocks, kSeqLanes, seq_smem, h -> stream>>> (
 	         h -> d_res, h -> d_zabs, h -> d_iqn, h -> cap_fm, M, sp, h -> lut, T + th.off_atan,
 	         h -> d_state, h -> d_demod, h -> d_phase, h -> d_locked);
 	else {
@@ -957,7 +966,6 @@ static int lane_set_fm_mode (Lane *h, int32_t m) {
 }
 static int lane_set_fm_decoder (Lane *h, int32_t d) {
 	if (!h || d < 1 || d > 6) return SDRJFM_ERR_ARG;
-	if (d == 1) { h -> err = "AM decoder is not on the GPU path"; return SDRJFM_ERR_UNSUPPORTED; }
 	h -> set.decoder = d; return SDRJFM_OK;
 }
 static int lane_set_sound_mode (Lane *h, int32_t s) {

@@ -34,10 +34,13 @@
 
 namespace sdrjfm {
 
-constexpr int kPiThreads = 256;
+// 512 threads x 8 samples: a 4096-sample window has about 410 segments, so most lanes walk one
+// segment per iteration; at 64 registers two CTAs share an SM (32 warps: the walk is a dependent
+// chain of ~9-cycle instructions, only thread-level parallelism hides it).
+constexpr int kPiThreads = 512;
 constexpr int kPiPer     = 8;                        // consecutive samples per thread
-constexpr int kPiWin     = kPiThreads * kPiPer;      // 2048 fm samples per window
-constexpr int kPiMaxSeg  = 448;                      // anchors per window (about 205 in practice)
+constexpr int kPiWin     = kPiThreads * kPiPer;      // 4096 fm samples per window
+constexpr int kPiMaxSeg  = 896;                      // anchors per window (about 410 in practice)
 constexpr int kPiMaxIter = 24;
 constexpr int kPiWarps   = kPiThreads / 32;
 
@@ -125,10 +128,7 @@ int32_t k = neg ? i - H : i;
 	k = k > Q ? H - k : k;
 float v = q [k];
 	v = neg ? -v : v;
-	if (k == 0 && i != 0) {                      // the zero crossings: patched from the exception list
-#pragma unroll
-	   for (int e = 0; e < kMaxSinExc; e ++) if (i == L.sin_exc_idx [e]) v = L.sin_exc_val [e];
-	}
+	if (i == H) v = L.sin_at_half;               // the zero crossing at pi: the table holds sin (pi) as computed, not -0
 	dsum = fmaf (pilot, __cosf (phi), dsum);
 float p2 = fadd (fadd (phi, fmul (fmul (pilot, v), gain)), omega);
 	if (p2 >= kTwoPiF) p2 = (float)((double)p2 - 2 * M_PI);     // PI_Constrain: fmod (v, 2 pi), v < 4 pi

@@ -22,6 +22,7 @@ struct SinLut {
 	int32_t sin_exc_idx [kMaxSinExc]; float sin_exc_val [kMaxSinExc];
 	int32_t cos_exc_idx [kMaxSinExc]; float cos_exc_val [kMaxSinExc];
 	double  C;               // Rate / (2 pi), sincos.cpp:45
+	float   sin_at_half;     // table value at idx = Rate / 2: the only sine entry the reflection can miss
 };
 
 // Table value sin (2 pi idx / Rate) for 0 <= idx < Rate from the quarter wave `q`.
@@ -125,7 +126,10 @@ struct SeqCarry {      // loop-carried registers of one stream
 	int   locked, stable;
 };
 
-template <bool PLL_DECODER>
+// DEC: 0 = discriminator output computed by K2 (Mixed, complex/real baseband delay, difference),
+//      1 = PLL decoder (pllC on the normalised sample), 2 = AM decoder (pllC on the raw sample for
+//      the AFC read-out, audio from the envelope: fm_Demodulator::decodeAM, fm-demodulator.cpp:215-241)
+template <int DEC>
 __device__ __forceinline__ void seq_step (const SeqParams &P, const SinLut &L, const float *q,
                                           const float *atanPPY, SeqCarry &c, float res, float zAbs,
                                           float2 nqv, float &demod_o, float &phase_o, uint8_t &lock_o) {
@@ -135,8 +139,8 @@ const float oneMinusDc = fsub (1.0f, fmDcAlpha);
 const float lockAlpha = 1.0f / 3000.0f;                           // pilot-recover.cpp:57
 const double oneMinusLock = 1.0 - (double)lockAlpha;
 	c.am = fadd (fmul (oneMinusCarrier, c.am), fmul (carrierAlpha, zAbs));
-	if (PLL_DECODER) {
-//	pllC::do_pll on the normalised sample, pllC.cpp:67-90
+	if (DEC != 0) {
+//	pllC::do_pll on the normalised (AM: the raw) sample, pllC.cpp:67-90
 	   const int32_t ci = cos_phase_index (L, c.nco);
 	   const float2 osc = make_float2 (lut_cos_idx (L, q, ci), lut_sin_idx (L, q, ci));
 	   const float2 d = cmul_rn (make_float2 (osc.x, -osc.y), nqv);
@@ -149,7 +153,13 @@ const double oneMinusLock = 1.0 - (double)lockAlpha;
 	   res = c.incr;
 	}
 	c.fm_afc = fadd (fmul (oneMinusDc, c.fm_afc), fmul (fmDcAlpha, res));
-const float demod = fdiv (fmul (fmul (20.0f, fsub (res, c.fm_afc)), 1.0f), P.K_FM);
+float demod = fdiv (fmul (fmul (20.0f, fsub (res, c.fm_afc)), 1.0f), P.K_FM);
+	if (DEC == 2) {
+//	envelope minus carrier level, normalised to the carrier level, limited to +-1 (:230-241)
+	   const float gainLimit = 0.01f;
+	   demod = fdiv (fsub (zAbs, c.am), c.am < gainLimit ? gainLimit : c.am);
+	   demod = demod > 1.0f ? 1.0f : (demod < -1.0f ? -1.0f : demod);
+	}
 //	pilotRecovery::getPilotPhase (5 * demod), pilot-recover.cpp:54-83
 const float pilot = fmul (5.0f, demod);
 const float osc = lut_getSin (L, q, c.phase);
@@ -169,7 +179,7 @@ const float quad = fdiv (fsub (osc, c.oldv), P.omega);
 
 // res_raw, zabs, iqn : K2 outputs.  demod / pilot_phase / locked : fm-rate outputs.
 // One lane per stream; the quarter-wave sine table lives in shared memory.
-template <bool PLL_DECODER>
+template <int DEC>
 __global__ void __launch_bounds__ (kSeqLanes)
 sequential_kernel (const float *__restrict__ res_raw, const float *__restrict__ zabs,
                    const float2 *__restrict__ iqn, int64_t pitch, int32_t M,
@@ -201,7 +211,7 @@ int32_t m = 0;
 	   const float4 r4 = *reinterpret_cast<const float4 *>(rr + m);
 	   const float4 z4 = *reinterpret_cast<const float4 *>(za + m);
 	   float2 n4 [4];
-	   if (PLL_DECODER) {
+	   if (DEC != 0) {
 #pragma unroll
 	      for (int k = 0; k < 4; k ++) n4 [k] = nq [m + k];
 	   }
@@ -209,16 +219,16 @@ int32_t m = 0;
 	   float d4 [4], p4 [4]; uint8_t l4 [4];
 #pragma unroll
 	   for (int k = 0; k < 4; k ++)
-	      seq_step<PLL_DECODER> (P, L, sq, atanPPY, c, rv [k], zv [k],
-	                             PLL_DECODER ? n4 [k] : make_float2 (0.f, 0.f), d4 [k], p4 [k], l4 [k]);
+	      seq_step<DEC> (P, L, sq, atanPPY, c, rv [k], zv [k],
+	                     DEC != 0 ? n4 [k] : make_float2 (0.f, 0.f), d4 [k], p4 [k], l4 [k]);
 	   *reinterpret_cast<float4 *>(dm + m) = make_float4 (d4 [0], d4 [1], d4 [2], d4 [3]);
 	   *reinterpret_cast<float4 *>(ph + m) = make_float4 (p4 [0], p4 [1], p4 [2], p4 [3]);
 	   *reinterpret_cast<uchar4 *>(lk + m) = make_uchar4 (l4 [0], l4 [1], l4 [2], l4 [3]);
 	}
 	for (; m < M; m ++) {
 	   float d, p; uint8_t l;
-	   seq_step<PLL_DECODER> (P, L, sq, atanPPY, c, rr [m], za [m],
-	                          PLL_DECODER ? nq [m] : make_float2 (0.f, 0.f), d, p, l);
+	   seq_step<DEC> (P, L, sq, atanPPY, c, rr [m], za [m],
+	                  DEC != 0 ? nq [m] : make_float2 (0.f, 0.f), d, p, l);
 	   dm [m] = d; ph [m] = p; lk [m] = l;
 	}
 	st.fm_afc = c.fm_afc; st.am_carr_ampl = c.am;

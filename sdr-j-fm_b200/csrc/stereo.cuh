@@ -34,7 +34,7 @@ constexpr int kPssTaps   = 295;
 constexpr int kPssRing   = 2048;
 constexpr int kStMaxTrans = 32;
 
-__constant__ float c_pss_taps [kPssTaps + 1];     // LowPassFIR (295, 15000, fmRate) real taps
+__constant__ float2 c_pss_taps [kPssTaps + 1];    // LowPassFIR (295, 15000, fmRate) real taps, each as {c, c}
 
 struct StereoParams {
 	int32_t fm_mode, auto_mono, pss_on, sound_sel;
@@ -50,19 +50,32 @@ struct PssState {              // PerfectStereoSeparation members + fmProcessor:
 	int32_t minimized, lockCnt, unlockCnt;
 };
 
+// fmod (v, 2 pi) for a float v, through double as the reference evaluates it.  fmod is exact, and for
+// 2 pi <= v < 6 pi the exact result is the plain double difference v - 2 pi n (Sterbenz: operands
+// within a factor two), so the common cases cost one DADD.  The comparisons use the floats just above
+// the doubles 2 pi and 4 pi (no float lies in between), which select the same branch as the reference.
+__device__ __noinline__ float fmod_2pi_rare (float v) { return (float)fmod ((double)v, 2 * M_PI); }
+__device__ __forceinline__ float fmod_2pi (float v) {
+const float kTwoPiF = 6.2831855f, kFourPiF = 12.566371f, kSixPiF = 18.849556f;
+	if (v >= 0.f && v < kTwoPiF) return v;
+	if (v >= kTwoPiF && v < kFourPiF) return (float)((double)v - 2 * M_PI);
+	if (v >= kFourPiF && v < kSixPiF) return (float)((double)v - 4 * M_PI);
+	return fmod_2pi_rare (v);
+}
+
 // SinCos::getComplex / getCos index, sincos.cpp:81-91
 __device__ __forceinline__ int32_t sincos_index (float phase) {
 	while (phase < 0.f) phase = (float)((double)phase + 2 * M_PI);
-	phase = (float)fmod ((double)phase, 2 * M_PI);
+	phase = fmod_2pi (phase);
 int32_t i = (int32_t)((double)phase * (kFmRate / (2 * M_PI)));
-	return i % kFmRate;
+	return i >= kFmRate ? i % kFmRate : i;
 }
 
 // phaseforLRDiff, fm-processor.cpp:707-714
 __device__ __forceinline__ float phase_for_lr (float cur, float pssDelay) {
 float ph = (float)(2 * ((double)cur + M_PI_4 + 0) - (double)pssDelay);
-	if ((double)ph < -2 * M_PI) ph = (float)((double)ph + 4 * M_PI);
-	return (float)fmod ((double)ph, 2 * M_PI);
+	if (ph < -6.283185f) ph = (float)((double)ph + 4 * M_PI);      // (double)ph < -2 pi: -6.283185f is the float just above -2 pi
+	return fmod_2pi (ph);
 }
 
 // matrix and selector, fm-processor.cpp:517-549
@@ -202,11 +215,11 @@ bool curLock = M > 0 ? lk [0] != 0 : false;
 	         for (int j0 = 0; j0 + kStPer <= kPssTaps; j0 += kStPer) {
 #pragma unroll
 	            for (int u = 0; u < kStPer; u ++) {
-	               const float c = c_pss_taps [j0 + u];
+	               const float2 c = c_pss_taps [j0 + u];
 #pragma unroll
 	               for (int k = 0; k < kStPer; k ++) {
 	                  const float2 w = v [(k - u + kStPer) % kStPer];
-	                  acc [k] = ffma2 (c, w, acc [k]);
+	                  acc [k] = ffma2p (c, w, acc [k]);
 	               }
 	               v [(kStPer - 1 - u) % kStPer] = sRing [nxt & (kPssRing - 1)];
 	               nxt --;
@@ -214,11 +227,11 @@ bool curLock = M > 0 ? lk [0] != 0 : false;
 	         }
 #pragma unroll
 	         for (int u = 0; u < kPssTaps % kStPer; u ++) {               // remaining taps (295 = 49 * 6 + 1)
-	            const float c = c_pss_taps [(kPssTaps / kStPer) * kStPer + u];
+	            const float2 c = c_pss_taps [(kPssTaps / kStPer) * kStPer + u];
 #pragma unroll
 	            for (int k = 0; k < kStPer; k ++) {
 	               const float2 w = v [(k - u + kStPer) % kStPer];
-	               acc [k] = ffma2 (c, w, acc [k]);
+	               acc [k] = ffma2p (c, w, acc [k]);
 	            }
 	            v [(kStPer - 1 - u) % kStPer] = sRing [nxt & (kPssRing - 1)];
 	            nxt --;
@@ -343,7 +356,9 @@ bool curLock = M > 0 ? lk [0] != 0 : false;
 	            osc = phLR < 0.f ? -sincos [((int32_t)((double)(-phLR) * (kFmRate / (2 * M_PI)))) % kFmRate].y
 	                             :  sincos [((int32_t)((double)phLR * (kFmRate / (2 * M_PI)))) % kFmRate].y;
 	         }
-	         const float diff = (float)(2.0 * (double)osc * (double)d);
+	         // (float)(2.0 * osc * d) evaluated in double: the double product of two floats is exact and
+	         // doubling is exact, so this is the single float rounding of osc * d, doubled
+	         const float diff = fmul (2.0f, fmul (osc, d));
 	         out [p + m] = lr_matrix (d, diff, P);
 	         if (tapd && P.write_pss_tap) {
 	            // pilotDelayPSS after the sample = the value entering the next one

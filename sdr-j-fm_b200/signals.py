@@ -85,3 +85,11 @@ def batch_stream(s, n, fs=INPUT_RATE, amp=0.5, snr_db=40.0, with_rds=True):
 def dc_offset(x, dc=0.004 + 0.003j):
     """adds a front-end DC offset (exercises the RF DC remover, fm-processor.cpp:423-446)."""
     return (x + np.complex64(dc)).astype(np.complex64)
+
+
+def am_tone(n, fs=INPUT_RATE, tone_hz=1000.0, depth=0.5, amp=0.4, f_offset=3000.0, snr_db=40.0, seed=1237):
+    """AM carrier (for the AM decoder, fm-demodulator.cpp:215-241): amp (1 + depth sin) at a small offset."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n, dtype=np.float64) / fs
+    x = amp * (1.0 + depth * np.sin(2 * np.pi * tone_hz * t)) * np.exp(2j * np.pi * f_offset * t)
+    return (x + _awgn(rng, n, amp, snr_db)).astype(np.complex64)

@@ -338,3 +338,22 @@ def test_pipelined_host_call_equals_streaming(pkg, signals):
     assert au_a.shape == au_b.shape == (3, n // 12 // 4) and rd_a.shape == rd_b.shape
     assert rms(au_a - au_b) < 1e-6 and rms(rd_a - rd_b) < 1e-6
     assert rms(au_a) > 1e-3
+
+
+@pytest.mark.parametrize("chunks", [None, [16384] * 40])
+def test_am_decoder_matches_reference(pkg, signals, checker, chunks):
+    """decoder 1 = AM (fm_Demodulator::decodeAM): envelope minus the carrier-level one-pole, normalised
+    and limited; pllC runs on the raw sample for the AFC read-out only."""
+    n = N1 // 4
+    x = signals.am_tone(n)
+    cfg = dict(decoder=1, fm_mode=2, volume_db=0.0)
+    c = checker(**cfg)
+    ref = c.process(x)
+    got = run_gpu(pkg, x, chunks=chunks, **cfg)
+    e = rms(got["demod"][0] - ref["demod"])
+    print("AM demod rms err", e, "audio192", rms(got["audio192"][0] - ref["audio192"]), "signal rms", rms(ref["demod"]))
+    assert rms(ref["demod"][20000:]) > 0.1
+    assert e < 1e-5 and rms(got["audio192"][0] - ref["audio192"]) < 1e-5
+    m, rm = got["meta"][0], c.meta()
+    assert abs(m["carrier_ampl"] - rm["carrier_ampl"]) < 1e-5 * max(1.0, rm["carrier_ampl"])
+    assert abs(m["dc_if"] - rm["dc_if"]) < 1e-4

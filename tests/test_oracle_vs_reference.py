@@ -24,6 +24,10 @@ CASES = [
     ("lo_gain_pano", dict(lo_hz=25000, lgain=0.9, rgain=1.1, fm_mode=1, panorama=150,
                           balance=-30, sound_sel=1, deemph_us=75), "stereo_pilot", N1 // 3),
     ("no_dc_no_automono", dict(dc_remove=0, auto_mono=0, pss_on=0), "stereo_pilot", N1 // 4),
+    ("am_decoder", dict(decoder=1, fm_mode=2), "am_tone", N1 // 4),
+    ("rate_6M", dict(input_rate=6000000, rds_on=1), "stereo_pilot", N1 // 2),
+    ("rate_10M_filter", dict(input_rate=10000000, input_filter_hz=165000), "stereo_pilot", N1 // 2),
+    ("rate_2p4M_lo", dict(input_rate=2400000, lo_hz=-30000), "stereo_pilot", N1 // 4),
 ]
 
 
