@@ -159,7 +159,20 @@ def cpu_reference_rate(settings, seconds_per_thread, threads=None):
             "seconds": dt}
 
 
+def emit(line):
+    """the ONE JSON line goes to the real stdout; everything else a library prints to fd 1 during the
+    run (e.g. NCCL's version banner) has been routed to stderr by main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -203,7 +216,7 @@ def main():
                                  "sample": r["sample"]},
                 "e2e": {"value": v, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -238,14 +251,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, st=None):
+        st = st or ext
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(ext):
-            e0.record(ext)
+        with torch.cuda.stream(st):
+            e0.record(st)
             for _ in range(steps):
                 fn()
-            e1.record(ext)
+            e1.record(st)
         barrier()
         ms = e0.elapsed_time(e1)
         if world > 1:
@@ -266,23 +280,40 @@ def main():
     launches = proc.launch_count - l0
     value = world * S * n * args.steps / (ms * 1e-3) / 1e6
 
-    # roofline: the front-end kernel alone
+    # roofline: the front-end kernel alone, as ONE launch over all streams of this GPU (a handle whose
+    # streams are not split into lanes; the lanes of `proc` would issue one launch per lane concurrently)
+    saved = os.environ.get("SDRJFM_LANES")
+    os.environ["SDRJFM_LANES"] = "1"
+    proc1 = pkg.FmProcessorB200(n_streams=S, max_samples_per_call=n, device=local, keep_taps=False)
+    if saved is None:
+        del os.environ["SDRJFM_LANES"]
+    else:
+        os.environ["SDRJFM_LANES"] = saved
+    proc1.configure(**settings)
+    ext1 = torch.cuda.ExternalStream(proc1.cuda_stream, device=dev)
     for _ in range(3):
-        proc.run_frontend_only(x.data_ptr(), n, x.stride(0))
+        proc1.run_frontend_only(x.data_ptr(), n, x.stride(0))
+    proc1.sync()
     fe_steps = max(args.steps, 5)
-    fe_ms = timed(lambda: proc.run_frontend_only(x.data_ptr(), n, x.stride(0)), fe_steps) / fe_steps
+    fe_l0 = proc1.launch_count
+    fe_ms = timed(lambda: proc1.run_frontend_only(x.data_ptr(), n, x.stride(0)), fe_steps, ext1) / fe_steps
+    fe_launches = (proc1.launch_count - fe_l0) / fe_steps
+    proc1.close()
     peak, peak_kind = peak_hbm()
     achieved = ALGO_BYTES_PER_SAMPLE * S * n / (fe_ms * 1e-3) / 1e9
     traffic = None      # dram bytes per launch from the committed ncu --set full capture of this workload
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r1_frontend_traffic.json")))
-        if tr["streams"] == S and tr["samples_per_stream"] == n:
+        if tr["streams"] == S and tr["samples_per_stream"] == n and tr["kernel"] == "frontend_tma_kernel":
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "frontend_fir_kernel", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "frontend_tma_kernel", "achieved": achieved, "peak": peak,
                 "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel_ms": fe_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SAMPLE * S * n}
+                "kernel_ms": fe_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SAMPLE * S * n,
+                "launches_timed": fe_launches,
+                "note": "one cp.async.bulk.tensor-fed launch over all streams (+ one small launch for the "
+                        "ragged last tile of each stream when n/12 is not a multiple of 512)"}
 
     # end to end through the host-buffer C-ABI call
     e2e = None
@@ -367,7 +398,7 @@ def main():
                 "x_realtime_2p304MSps": value / 2.304, "roofline": roofline,
                 "cpu_baseline": cpu, "e2e": e2e, "device_format_u8": raw, "gpu_launches": int(launches),
                 "clocks": clk.summary()}
-        print(json.dumps(line))
+        emit(line)
     proc.close()
     if world > 1:
         dist.destroy_process_group()

@@ -63,13 +63,14 @@ __global__ void __launch_bounds__ (kFeThreads, 4)
 frontend_fir_kernel (const float2 *__restrict__ x, int64_t in_pitch,
                      const float2 *__restrict__ hist, int hist_len,
                      float2 *__restrict__ U, float2 *__restrict__ S,
-                     int64_t out_pitch, int32_t M, const LoParams lop) {
+                     int64_t out_pitch, int32_t M, const LoParams lop, int32_t tile0) {
 extern __shared__ float2 sm [];
 __shared__ float2 sRaw [LO ? kFeTileOut : 1];
 	if (LO) { for (int i = threadIdx.x; i < kFeTileOut; i += kFeThreads) sRaw [i] = make_float2 (0.f, 0.f); __syncthreads (); }
 const int tid    = threadIdx.x;
 const int stream = blockIdx.y;
-const int64_t out0 = (int64_t)blockIdx.x * kFeTileOut;   // first output of the tile
+const int tile = blockIdx.x + tile0;                     // tile0: the tiles before it were done by K1t
+const int64_t out0 = (int64_t)tile * kFeTileOut;         // first output of the tile
 const int64_t in0  = out0 * kDecim;                       // first input of the tile
 const int64_t N    = (int64_t)M * kDecim;
 const float2 *xs = x + (int64_t)stream * in_pitch;
@@ -77,7 +78,7 @@ const float2 *xs = x + (int64_t)stream * in_pitch;
 //	halo: the 36 samples before the tile, polyphase rows 12..47 of column 0
 	if (tid < kHist) {
 	   float2 v;
-	   if (blockIdx.x == 0) v = hist [(int64_t)stream * hist_len + (hist_len - kHist) + tid];
+	   if (tile == 0) v = hist [(int64_t)stream * hist_len + (hist_len - kHist) + tid];
 	   else                 v = xs [in0 - kHist + tid];
 	   if (LO) v = lo_apply (lop, v, lo_index (lop, in0 - kHist + tid));
 	   sm [(kDecim + tid) * kFePitch] = v;

@@ -26,6 +26,7 @@
 #include "common.cuh"
 #include "frontend_fir.cuh"
 #include "frontend_poly.cuh"
+#include "frontend_tma.cuh"
 #include "resample.cuh"
 #include "discriminator.cuh"
 #include "sequential.cuh"
@@ -72,6 +73,8 @@ struct Lane {
 	int           hist_len = 0, hist_len_w = 0;   // raw-sample history kept per stream (narrow / input filter on)
 	int           fw_delay = 0, fw_shift = 0;     // inputFilter latency 65285 = decim * fw_delay + fw_shift
 	int           ngw = 0;                        // tap groups of the wide composite
+	bool          use_tma = true;           // SDRJFM_NO_TMA=1: the register-staged K1 instead of K1t
+	int           tma_ctas = 0;             // persistent CTAs of K1t per launch (SDRJFM_TMA_CTAS overrides)
 	bool          force_generic = false;    // SDRJFM_GENERIC_FE=1: K1g also where the tuned D = 12 kernels apply
 	float2 *d_in = nullptr;                 // staging [S][cap_in] (8 bytes per sample: any format fits)
 	float2 *d_hist [2] = { nullptr, nullptr }; int hist_sel = 0;
@@ -419,10 +422,13 @@ Lane *h = new Lane ();
 	   const int rows = fs.D * fs.gpt;
 	   h -> hist_len   = ((fs.ng - 1 + fs.gpt - 1) / fs.gpt) * rows;      // Poly<>::HaloIn
 	   h -> hist_len_w = std::max (((fs.ngw - 1 + fs.gpt - 1) / fs.gpt) * rows, fs.ngw * fs.D);
-	   const char *env = getenv ("SDRJFM_GENERIC_FE"); h -> force_generic = env && env [0] == '1'; }
+	   const char *env = getenv ("SDRJFM_GENERIC_FE"); h -> force_generic = env && env [0] == '1';
+	   env = getenv ("SDRJFM_NO_TMA"); h -> use_tma = !(env && env [0] == '1');
+	   env = getenv ("SDRJFM_TMA_CTAS"); h -> tma_ctas = env && atoi (env) > 0 ? atoi (env) : 0; }
 	if (h -> cfg.working_rate <= 0) h -> cfg.working_rate = 48000;
 	if (h -> cfg.audio_rate <= 0) h -> cfg.audio_rate = h -> cfg.working_rate;
 	h -> n_sm = prop.multiProcessorCount;
+	if (h -> tma_ctas == 0) h -> tma_ctas = h -> n_sm;       // one persistent CTA per SM saturates HBM (measured)
 	default_settings (h -> set, cfg -> fm_rate);
 	h -> fade_max = h -> cfg.working_rate / 2;
 	h -> fade_cnt = h -> fade_max;
@@ -475,7 +481,9 @@ cudaError_t e;
 	if ((e = cudaFuncSetAttribute (frontend_fir_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                               kFeSmemBytes)) != cudaSuccess ||
 	    (e = cudaFuncSetAttribute (frontend_fir_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                               kFeSmemBytes)) != cudaSuccess) return fail (e, "smem attr K1");
+	                               kFeSmemBytes)) != cudaSuccess ||
+	    (e = cudaFuncSetAttribute (frontend_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                               kFtSmemBytes)) != cudaSuccess) return fail (e, "smem attr K1");
 	if ((e = poly_set_attr (shape)) != cudaSuccess) return fail (e, "smem attr K1g");
 	if ((e = cudaFuncSetAttribute (sequential_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                               (cfg -> fm_rate / 4 + 1) * (int)sizeof (float))) != cudaSuccess ||
@@ -535,6 +543,21 @@ static int lane_sync (Lane *h) {
 	return SDRJFM_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*TmaEncodeFn) (CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TmaEncodeFn tma_encoder () {
+static TmaEncodeFn fn = [] () -> TmaEncodeFn {
+	   void *p = nullptr;
+	   cudaDriverEntryPointQueryResult q;
+	   if (cudaGetDriverEntryPoint ("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+	       q != cudaDriverEntryPointSuccess) return nullptr;
+	   return (TmaEncodeFn)p;
+	} ();
+	return fn;
+}
+
 // ---- K1g dispatch over the instantiated shapes ---------------------------------------------
 template <int D, int GPT, int NG> static cudaError_t poly_attr_one () {
 	return cudaFuncSetAttribute (frontend_poly_kernel<D, GPT, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -585,11 +608,36 @@ float2 *U = wide ? h -> d_Uw : h -> d_U, *Sb = wide ? h -> d_Sw : h -> d_S;
 	      else    frontend_wide_kernel<false><<<grid, kFeThreads, kFwSmemBytes, h -> stream>>> (
 	            x, pitch, hist, hlen, U, Sb, h -> cap_fm, M, lp);
 	   }
+	   else if (lo)
+	      frontend_fir_kernel<true><<<grid, kFeThreads, kFeSmemBytes, h -> stream>>> (
+	            x, pitch, hist, hlen, U, Sb, h -> cap_fm, M, lp, 0);
 	   else {
-	      if (lo) frontend_fir_kernel<true><<<grid, kFeThreads, kFeSmemBytes, h -> stream>>> (
-	            x, pitch, hist, hlen, U, Sb, h -> cap_fm, M, lp);
-	      else    frontend_fir_kernel<false><<<grid, kFeThreads, kFeSmemBytes, h -> stream>>> (
-	            x, pitch, hist, hlen, U, Sb, h -> cap_fm, M, lp);
+//	      whole 512-output tiles through TMA (K1t), the ragged last tile through the plain kernel
+	      int32_t tiles = 0;
+	      CUtensorMap map;
+	      if (h -> use_tma && M >= kFeTileOut && ((uintptr_t)x & 15) == 0 && (pitch & 1) == 0 && tma_encoder ()) {
+	         tiles = M / kFeTileOut;
+	         const cuuint64_t gdim [4] = { 32, 3, (cuuint64_t)tiles * kFtRows, (cuuint64_t)S };
+	         const cuuint64_t gstr [3] = { 128, 384, (cuuint64_t)pitch * sizeof (float2) };
+	         const cuuint32_t box [4] = { 32, 3, kFtBoxRows, 1 };
+	         const cuuint32_t estr [4] = { 1, 1, 1, 1 };
+	         const CUresult r = tma_encoder () (&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)x, gdim, gstr, box, estr,
+	               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+	               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	         if (r != CUDA_SUCCESS) tiles = 0;
+	      }
+	      if (tiles > 0) {
+	         const int64_t total = (int64_t)tiles * S;
+	         const unsigned g = (unsigned)std::min<int64_t> (total, (int64_t)h -> tma_ctas);
+	         frontend_tma_kernel<<<g, kFeThreads, kFtSmemBytes, h -> stream>>> (map, hist, hlen, U, Sb, h -> cap_fm, tiles, S);
+	         if (M % kFeTileOut) {
+	            frontend_fir_kernel<false><<<dim3 (1, S), kFeThreads, kFeSmemBytes, h -> stream>>> (
+	                  x, pitch, hist, hlen, U, Sb, h -> cap_fm, M, lp, tiles);
+	            h -> launches ++;
+	         }
+	      }
+	      else frontend_fir_kernel<false><<<grid, kFeThreads, kFeSmemBytes, h -> stream>>> (
+	            x, pitch, hist, hlen, U, Sb, h -> cap_fm, M, lp, 0);
 	   }
 	}
 	else switch (h -> shape * 2 + (wide ? 1 : 0)) {

@@ -96,6 +96,10 @@ sdrjfm_handle *h = new sdrjfm_handle ();
 	   h -> first.push_back (lo);
 	}
 	h -> first.push_back (cfg -> n_streams);
+//	K1t is persistent: the lanes share the SMs (one CTA per SM in total keeps HBM saturated and leaves
+//	the rest of each SM to the latency-bound kernels of the other lanes)
+	if (!getenv ("SDRJFM_TMA_CTAS"))
+	   for (Lane *l : h -> lanes) l -> tma_ctas = std::max (1, (l -> n_sm + nl - 1) / nl);
 	h -> cfg = h -> lanes [0] -> cfg; h -> cfg.n_streams = cfg -> n_streams;
 	h -> cap_in = h -> lanes [0] -> cap_in; h -> cap_audio = h -> lanes [0] -> cap_audio;
 	h -> cap_rds = h -> lanes [0] -> cap_rds;

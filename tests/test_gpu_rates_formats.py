@@ -141,8 +141,9 @@ def test_device_sample_formats_equal_handler_conversion(pkg, signals, checker, f
     b = run_gpu(pkg, xf, fs, chunks=chunks, **cfg)
     for k in ("fm_z", "demod", "audio192"):
         if fs == 2304000:
-            # float path = the tuned kernel, raw path = K1g: same taps, different summation order
-            assert rms(a[k] - b[k]) < 1e-6, k
+            # float path = K1t (TMA), raw path = K1g: same taps, different summation order; behind the
+            # discriminator a last-bit difference can flip an atan-table index (7.9e-5 per flip)
+            assert rms(a[k] - b[k]) < (1e-6 if k == "fm_z" else 5e-6), k
         else:
             assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), k
     ref = checker(input_rate=fs, **cfg).process(xf)
