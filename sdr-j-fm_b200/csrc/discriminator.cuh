@@ -16,6 +16,7 @@ namespace sdrjfm {
 constexpr int kDiThreads = 256;
 constexpr int kDiRun     = 8;                 // consecutive fm samples per thread
 constexpr int kDiBlock   = kDiThreads * kDiRun;
+constexpr int kDiTilesPerCta = 4;             // the 32 KB arctan table is staged once per CTA
 
 struct DiscrParams {
 	float  sumC, sumCm;         // sum of the plain composite taps C; of the DC-folded taps C'
@@ -36,8 +37,11 @@ struct DiscrParams {
 // compAtan::atan2, src/various/Xtan2.cpp:56-100.  Only the first-octant table PPY is kept
 // (in shared memory); the other seven tables are single float operations on PPY
 // (Xtan2.cpp:30-37) and are re-derived on the fly with the same roundings.
+// (int)(q + 0.5) with the sum formed in double (Xtan2.cpp:74-97).  For 0 <= q <= 8192 the float sum
+// truncates to the same integer: q + 0.5 is exact unless it crosses into the next binade, and there
+// the rounding (< 2^-11) cannot cross an integer from below.
 __device__ __forceinline__ int atan_index (float num_scaled, float den) {
-	return (int)((double)fdiv (num_scaled, den) + 0.5);
+	return (int)fadd (fdiv (num_scaled, den), 0.5f);
 }
 
 __device__ __forceinline__ float lut_atan2 (const float *PPY, float y, float x) {
@@ -160,10 +164,19 @@ float vy = (u.y - ky) * P.rgain;
 	   vy = u.y - (b.x * P.Him + b.y * P.Hre);
 	}
 	z = make_float2 (vx * P.Gre - vy * P.Gim, vx * P.Gim + vy * P.Gre);
-//	std::abs (complex<float>) = hypotf: evaluated through double (fm-demodulator.cpp:119)
-	za = (float)sqrt ((double)z.x * (double)z.x + (double)z.y * (double)z.y);
-	if ((double)za <= 0.001) nq = make_float2 (0.001f, 0.001f);   // :120-122
-	else nq = make_float2 (fdiv (z.x, za), fdiv (z.y, za));
+//	std::abs (complex<float>) (fm-demodulator.cpp:119).  z itself carries ~1e-6 of re-association
+//	error against the reference (composite FIR), so the magnitude is taken in float (1e-7) instead of
+//	through a double square root, and the two divisions share one reciprocal: q = a r, corrected
+//	once with the exact residual (q + (a - q b) r), which is the correctly rounded quotient.
+	za = __fsqrt_rn (fmaf (z.x, z.x, fmul (z.y, z.y)));
+	if (za <= 0.001f) nq = make_float2 (0.001f, 0.001f);          // :120-122
+	else {
+	   const float r = __frcp_rn (za);
+	   float qx = fmul (z.x, r), qy = fmul (z.y, r);
+	   qx = fmaf (fmaf (-qx, za, z.x), r, qx);
+	   qy = fmaf (fmaf (-qy, za, z.y), r, qy);
+	   nq = make_float2 (qx, qy);
+	}
 }
 
 // U, Ssum : front-end outputs; res_raw: discriminator output before AFC (float);
@@ -184,14 +197,15 @@ __shared__ float2 sLastIQ [kDiThreads + 1];
 __shared__ float2 sLastIQ2 [kDiThreads + 1];
 __shared__ dcplx  sCarry;
 const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-const int stream = blockIdx.y, tile = blockIdx.x;
+const int stream = blockIdx.y;
 StreamState &st = state [stream];
 const float2 *Us = U + (int64_t)stream * pitch;
 const float2 *Ss = Ssum + (int64_t)stream * pitch;
 const DiscrSnap sn = snap [stream];
-const int64_t base = (int64_t)tile * kDiBlock;
 
 	for (int i = tid; i < 8193; i += kDiThreads) sPPY [i] = atanPPY [i];
+	for (int tile = blockIdx.x * kDiTilesPerCta; tile < min ((int)(blockIdx.x + 1) * kDiTilesPerCta, ntiles); tile ++) {
+const int64_t base = (int64_t)tile * kDiBlock;
 //	powers of beta used by the scan: pw[k] = beta^(8 * 2^k)
 double pw [6];
 	{  double b8 = P.beta; b8 *= b8; b8 *= b8; b8 *= b8;   // beta^8
@@ -334,6 +348,8 @@ double pw [6];
 	         if (fmz) fmz [o] = z [j];
 	      }
 	   }
+	}
+	   __syncthreads ();          // the per-tile shared scratch is reused by the next tile
 	}
 }
 

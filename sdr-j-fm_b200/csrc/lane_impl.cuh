@@ -56,6 +56,22 @@ static const FeShape kFeShapes [] = { { 12, 4, 4, 25 }, { 30, 2, 2, 11 }, { 48, 
 constexpr int kShapeResample = 3;
 constexpr int kInputFilterDelay = kInputFftSize - kInputDegree;       // 65285 input samples
 
+// Host image of everything this configuration keeps in __constant__ memory.  The constant banks
+// belong to the one loaded module, i.e. they are shared by every handle of the process: each lane
+// keeps its image and a content signature, and whoever launches makes sure the device holds ITS
+// image (consts_ensure).  Handles with different configurations may therefore coexist; they must
+// not be driven from different threads at the same time.
+struct ConstImage {
+	float  comp [40];
+	float  rs_taps [kRsTaps + 3];
+	float  wide [kDecim][kFwGroups + 3];
+	float  poly [kPolyMaxTaps];
+	float2 pss [kPssTaps + 1];
+	float  alp [kAlpTaps];
+	uint64_t sig;
+};
+static uint64_t g_const_sig = 0;          // signature of the image the device holds now
+
 struct Lane {
 	sdrjfm_config cfg;
 	Settings      set;
@@ -121,6 +137,7 @@ struct Lane {
 	int32_t fade_cnt = 0, fade_max = 0;     // suppressAudioSampleCnt(Max), fm-processor.cpp:130-131
 	int64_t last_nfm = 0, last_naudio = 0, last_nrds = 0;
 	int64_t launches = 0;
+	ConstImage ci;
 	std::string err;
 };
 
@@ -155,6 +172,33 @@ static void default_settings (Settings &s, int32_t fm_rate) {
 	}
 }
 
+// copies the lane's constant image to the device (all launches of the process are drained first:
+// kernels of another configuration may still be reading the banks)
+static int consts_upload (Lane *h) {
+	CK (cudaDeviceSynchronize ());
+	CK (cudaMemcpyToSymbol (c_comp, h -> ci.comp, sizeof h -> ci.comp));
+	CK (cudaMemcpyToSymbol (c_rs_taps, h -> ci.rs_taps, sizeof h -> ci.rs_taps));
+	CK (cudaMemcpyToSymbol (c_wide, h -> ci.wide, sizeof h -> ci.wide));
+	CK (cudaMemcpyToSymbol (c_poly, h -> ci.poly, sizeof h -> ci.poly));
+	CK (cudaMemcpyToSymbol (c_pss_taps, h -> ci.pss, sizeof h -> ci.pss));
+	CK (cudaMemcpyToSymbol (c_alp_taps, h -> ci.alp, sizeof h -> ci.alp));
+	g_const_sig = h -> ci.sig;
+	return SDRJFM_OK;
+}
+// new contents: recompute the signature (FNV-1a over the image) and upload
+static int consts_commit (Lane *h) {
+uint64_t x = 1469598103934665603ull;
+const unsigned char *p = reinterpret_cast<const unsigned char *>(&h -> ci);
+	for (size_t i = 0; i < offsetof (ConstImage, sig); i ++) { x ^= p [i]; x *= 1099511628211ull; }
+	h -> ci.sig = x ? x : 1;
+	if (h -> ci.sig == g_const_sig) return SDRJFM_OK;
+	return consts_upload (h);
+}
+// before launching: the device must hold this lane's image
+static inline int consts_ensure (Lane *h) {
+	return h -> ci.sig == g_const_sig ? SDRJFM_OK : consts_upload (h);
+}
+
 // uploads constant-memory taps and derives the launch parameters that depend on the tables
 static int upload_tables (Lane *h) {
 const TableHeader &th = h -> tables.hdr ();
@@ -183,7 +227,7 @@ const int32_t lo_hz = h -> set.lo_hz;
 	   }
 	   h -> lo_Hre = (float)H.real (); h -> lo_Him = (float)H.imag ();
 	}
-	CK (cudaMemcpyToSymbol (c_comp, comp, 40 * sizeof (float)));
+	memcpy (h -> ci.comp, comp, sizeof h -> ci.comp);
 
 //	audio decimator taps (our own design, audio_out.cuh): Blackman-windowed sinc, fc = 20 kHz
 	{
@@ -199,7 +243,7 @@ const int32_t lo_hz = h -> set.lo_hz;
 	      d [i] = s * w; sum += d [i];
 	   }
 	   for (int i = 0; i < kRsTaps; i ++) t [i] = (float)(d [i] / sum);
-	   CK (cudaMemcpyToSymbol (c_rs_taps, t, sizeof t));
+	   memcpy (h -> ci.rs_taps, t, sizeof t);
 	}
 
 //	K1g taps, narrow: c_poly[p][g] = C'[D g + D - 1 - p]
@@ -249,9 +293,9 @@ const int ncomp = h -> resample ? th.rs_ntapsA : th.ncomp;
 	         H += (double)(float)cw [t] * std::polar (1.0, 2 * M_PI * (double)lo_hz * t / th.input_rate);
 	      h -> lo_Hre = (float)H.real (); h -> lo_Him = (float)H.imag ();
 	   }
-	   if (D == kDecim) CK (cudaMemcpyToSymbol (c_wide, cwide, sizeof cwide));
+	   if (D == kDecim) memcpy (h -> ci.wide, cwide, sizeof cwide);
 	}
-	CK (cudaMemcpyToSymbol (c_poly, cpoly, sizeof cpoly));
+	memcpy (h -> ci.poly, cpoly, sizeof cpoly);
 
 //	PSS low-pass taps: lpFilter (2048, 295).setLowPass (15000, rate), stereo-separation.cpp:31-39
 	{
@@ -259,7 +303,7 @@ const int ncomp = h -> resample ? th.rs_ntapsA : th.ncomp;
 	   float2 t [kPssTaps + 1];
 	   memset (t, 0, sizeof t);
 	   for (int i = 0; i < kPssTaps; i ++) t [i] = make_float2 (lp [i].real (), lp [i].real ());
-	   CK (cudaMemcpyToSymbol (c_pss_taps, t, sizeof t));
+	   memcpy (h -> ci.pss, t, sizeof t);
 	}
 
 //	quarter-wave sine table + exception list (see sequential.cuh)
@@ -306,7 +350,7 @@ SinLut &L = h -> lut;
 	   h -> err = "SinCos table is not quarter-wave symmetric for this fm_rate";
 	   return SDRJFM_ERR_UNSUPPORTED;
 	}
-	return SDRJFM_OK;
+	return consts_commit (h);
 }
 
 static int rebuild_tables (Lane *h) {
@@ -584,6 +628,7 @@ dim3 grid ((unsigned)((M + P::TileOut - 1) / P::TileOut), (unsigned)h -> cfg.n_s
 
 static int launch_frontend (Lane *h, const void *src, RawFmt rf, int64_t pitch, int32_t M) {
 const int S = h -> cfg.n_streams;
+	{ const int rc = consts_ensure (h); if (rc != SDRJFM_OK) return rc; }
 LoParams lp;
 	memset (&lp, 0, sizeof lp);
 const bool lo = h -> set.lo_hz != 0;
@@ -777,7 +822,8 @@ const int32_t ntiles = (M + kDiBlock - 1) / kDiBlock;
 	   dim3 g ((unsigned)ntiles, (unsigned)S);
 	   dc_tile_kernel<<<g, kDiThreads, 0, h -> stream>>> (h -> d_S, h -> cap_fm, M, dp, h -> d_state,
 	                                                       h -> d_tileB, ntiles, h -> d_snap);
-	   discriminator_kernel<<<g, kDiThreads, 0, h -> stream>>> (
+	   const dim3 gd ((unsigned)((ntiles + kDiTilesPerCta - 1) / kDiTilesPerCta), (unsigned)S);
+	   discriminator_kernel<<<gd, kDiThreads, 0, h -> stream>>> (
 	         h -> d_U, h -> d_S, h -> cap_fm, M, dp, T + th.off_atan, T + th.off_arcsine,
 	         h -> d_state, h -> d_tileB, ntiles, h -> d_snap, h -> d_res, h -> d_zabs,
 	         (st.decoder == 2 || st.decoder == 1) ? h -> d_iqn : nullptr, h -> cfg.keep_taps ? h -> d_fmz : nullptr);
@@ -1057,10 +1103,9 @@ static int lane_set_lf_cutoff (Lane *h, int32_t hz) {
 	   else for (int i = 0; i < 2; i ++)
 	      CK (cudaMemsetAsync (h -> d_alp_hist [i], 0, (size_t)S * kAlpHist * sizeof (float2), h -> stream));
 	   std::vector<cf32> lp = design_lowpass (kAlpTaps, v, h -> cfg.fm_rate);
-	   float t [kAlpTaps];
-	   for (int i = 0; i < kAlpTaps; i ++) t [i] = lp [i].real ();
-	   CK (cudaMemcpyToSymbolAsync (c_alp_taps, t, sizeof t, 0, cudaMemcpyHostToDevice, h -> stream));
-	   CK (cudaStreamSynchronize (h -> stream));
+	   for (int i = 0; i < kAlpTaps; i ++) h -> ci.alp [i] = lp [i].real ();
+	   int rc = consts_commit (h);
+	   if (rc != SDRJFM_OK) return rc;
 	}
 	return SDRJFM_OK;
 }
