@@ -78,6 +78,8 @@ struct Lane {
 	TableBlob     tables;
 	float        *d_tables = nullptr;
 	cudaStream_t  stream = nullptr;
+	cudaStream_t  stream_rds = nullptr;     // the RDS branch runs beside the stereo decoder (both only read K3's outputs)
+	cudaEvent_t   ev_k3 = nullptr, ev_rds = nullptr;
 	int           n_sm = 0;
 	bool          smem_lut_ok = false;
 	SinLut        lut;
@@ -491,7 +493,10 @@ auto fail = [&](cudaError_t e, const char *what) -> Lane * {
 	};
 cudaError_t e;
 #define AL(p, n) if ((e = dalloc (&h -> p, (size_t)(n))) != cudaSuccess) return fail (e, "cudaMalloc " #p)
-	if ((e = cudaStreamCreateWithFlags (&h -> stream, cudaStreamNonBlocking)) != cudaSuccess)
+	if ((e = cudaStreamCreateWithFlags (&h -> stream, cudaStreamNonBlocking)) != cudaSuccess ||
+	    (e = cudaStreamCreateWithFlags (&h -> stream_rds, cudaStreamNonBlocking)) != cudaSuccess ||
+	    (e = cudaEventCreateWithFlags (&h -> ev_k3, cudaEventDisableTiming)) != cudaSuccess ||
+	    (e = cudaEventCreateWithFlags (&h -> ev_rds, cudaEventDisableTiming)) != cudaSuccess)
 	   return fail (e, "cudaStreamCreate");
 	AL (d_in, S * h -> cap_in);
 	AL (d_hist [0], S * h -> hist_len); AL (d_hist [1], S * h -> hist_len);
@@ -565,6 +570,9 @@ void *ptrs [] = { h -> d_tables, h -> d_sin_quarter, h -> d_in, h -> d_hist [0],
 	              h -> d_sdel [0], h -> d_sdel [1], h -> d_alp_hist [0], h -> d_alp_hist [1], h -> d_lrf, h -> d_lo_tab,
 	              h -> d_A, h -> d_SA, h -> d_bha [0], h -> d_bha [1], h -> d_bhs [0], h -> d_bhs [1] };
 	for (void *p : ptrs) if (p) cudaFree (p);
+	if (h -> stream_rds) { cudaStreamSynchronize (h -> stream_rds); cudaStreamDestroy (h -> stream_rds); }
+	if (h -> ev_k3) cudaEventDestroy (h -> ev_k3);
+	if (h -> ev_rds) cudaEventDestroy (h -> ev_rds);
 	if (h -> stream) cudaStreamDestroy (h -> stream);
 	delete h;
 	return SDRJFM_OK;
@@ -873,6 +881,7 @@ const size_t seq_smem = (h -> lut.quarter + 1) * sizeof (float);
 	            h -> d_demod, h -> d_phase, h -> d_locked, h -> d_iter_stats);
 	}
 	h -> launches ++;
+	if (st.rds_mode != 0) CK (cudaEventRecord (h -> ev_k3, h -> stream));
 //	K4 ------------------------------------------------------------------------------------
 	{
 	   StereoParams q;
@@ -890,21 +899,24 @@ const size_t seq_smem = (h -> lut.quarter + 1) * sizeof (float);
 	}
 //	K5 ------------------------------------------------------------------------------------
 	if (st.rds_mode != 0) {
+//	   fork: the RDS branch on its own stream, ordered after K3 (it reads demod and the pilot phase)
+	   cudaStream_t rs = h -> stream_rds;
+	   CK (cudaStreamWaitEvent (rs, h -> ev_k3, 0));
 	   const int64_t n0 = h -> rds_total;
 	   for (int32_t m = 0; m < M; ) {
 	      const int64_t K = (n0 + m) / kRdsBlock;
 	      const int32_t mEnd = (int32_t)std::min<int64_t> (M, (K + 1) * kRdsBlock - n0);
 	      dim3 g ((unsigned)((mEnd - m + 255) / 256), (unsigned)S);
-	      rds_append_kernel<<<g, 256, 0, h -> stream>>> (h -> d_demod, h -> d_phase, h -> cap_fm, m, mEnd, n0,
+	      rds_append_kernel<<<g, 256, 0, rs>>> (h -> d_demod, h -> d_phase, h -> cap_fm, m, mEnd, n0,
 	                                                    h -> d_rds_dring, h -> d_rds_pring);
 	      h -> launches ++;
 	      if (K >= 1 && h -> rds_last_block < K - 1) {
-	         rds_block_kernel<<<S, kRdsThreads, kRdsFftSmem, h -> stream>>> (
+	         rds_block_kernel<<<S, kRdsThreads, kRdsFftSmem, rs>>> (
 	               h -> d_rds_dring, K - 1, h -> d_rds_tw, h -> d_rds_tws, h -> d_rds_R, h -> d_rds_bp, h -> d_rds_hi);
 	         h -> launches ++;
 	         h -> rds_last_block = K - 1;
 	      }
-	      rds_mix_kernel<<<g, 256, 0, h -> stream>>> (h -> d_rds_pring, h -> d_rds_bp, h -> d_rds_hi,
+	      rds_mix_kernel<<<g, 256, 0, rs>>> (h -> d_rds_pring, h -> d_rds_bp, h -> d_rds_hi,
 	                                                 h -> cap_fm, m, mEnd, n0, h -> d_rdsc);
 	      h -> launches ++;
 	      m = mEnd;
@@ -913,13 +925,14 @@ const size_t seq_smem = (h -> lut.quarter + 1) * sizeof (float);
 	   float2 *rout = d_rds_out ? d_rds_out : h -> d_rds24;
 	   const int64_t rpitch = d_rds_out ? rds_pitch : h -> cap_rds;
 	   dim3 g ((unsigned)((std::max (nout, 1) + 127) / 128), (unsigned)S);
-	   rds_decim_kernel<<<g, 128, 0, h -> stream>>> (h -> d_rdsc, h -> cap_fm, M, n0, h -> d_rds_dtaps,
+	   rds_decim_kernel<<<g, 128, 0, rs>>> (h -> d_rdsc, h -> cap_fm, M, n0, h -> d_rds_dtaps,
 	         h -> d_rds_hist [h -> rds_hist_sel], h -> d_rds_hist [h -> rds_hist_sel ^ 1], rout, rpitch, nout);
 	   h -> launches ++;
 	   h -> rds_hist_sel ^= 1;
 	   h -> rds_total += M;
 	   h -> last_nrds = nout;
 	   if (n_rds) *n_rds = nout;
+	   CK (cudaEventRecord (h -> ev_rds, rs));
 	}
 //	K6 ------------------------------------------------------------------------------------
 const float2 *lr_in = h -> d_lr;
@@ -956,6 +969,7 @@ const int64_t apitch = d_audio_out ? audio_pitch : h -> cap_audio;
 	h -> fm_total += M;
 	h -> last_naudio = nq;
 	if (n_audio) *n_audio = nq;
+	if (st.rds_mode != 0) CK (cudaStreamWaitEvent (h -> stream, h -> ev_rds, 0));     // join
 	CK (cudaGetLastError ());
 	return SDRJFM_OK;
 }
