@@ -168,6 +168,51 @@ def emit(line):
 _REAL_STDOUT = 1
 
 
+def front_end_sweep(pkg, torch, dev, local, S, peak):
+    """the decimating front end alone (one launch over S streams, no lanes) for every rate / format:
+    algorithmic bytes = bytes of one IQ sample in that format + 8 bytes per fm-rate output."""
+    os.environ["SDRJFM_LANES"] = "1"
+    out = []
+    seconds = 0.25
+    fmts = {"cf32": (torch.float32, 8), "s16": (torch.int16, 4), "u8": (torch.uint8, 2)}
+    cases = [(2304000, 0, "cf32"), (2304000, 0, "s16"), (2304000, 0, "u8"), (2400000, 0, "u8"),
+             (6000000, 0, "cf32"), (6000000, 0, "s16"), (10000000, 0, "cf32"), (10000000, 0, "s16"),
+             (2400000, 1, "cf32"), (6000000, 1, "s16"), (10000000, 1, "s16")]
+    try:
+        for rate, mode, fmt in cases:
+            dec = 5 if mode == 1 else pkg.front_end_decimation(rate)
+            n = int(seconds * rate) // (dec * 512) * (dec * 512)
+            p = pkg.FmProcessorB200(n_streams=S, input_rate=rate, max_samples_per_call=n, device=local,
+                                    keep_taps=False, front_end_mode=mode)
+            dt, bps = fmts[fmt]
+            if fmt == "cf32":
+                buf = torch.randn((S, n, 2), device=dev, dtype=torch.float32) * 0.3
+            else:
+                buf = torch.randint(0, 200, (S, n, 2), device=dev, dtype=dt)
+            st = torch.cuda.ExternalStream(p.cuda_stream, device=dev)
+            for _ in range(3):
+                p.run_frontend_only_raw(buf.data_ptr(), fmt, 2048, n, n)
+            p.sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            with torch.cuda.stream(st):
+                e0.record(st)
+                for _ in range(reps):
+                    p.run_frontend_only_raw(buf.data_ptr(), fmt, 2048, n, n)
+                e1.record(st)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            algo = S * n * (bps + 8.0 / dec)
+            out.append({"input_rate": rate, "front_end_mode": mode, "format": fmt, "decimation": dec,
+                        "kernel_ms": ms, "GS_per_s": S * n / ms / 1e6, "achieved_GBps": algo / ms / 1e6,
+                        "frac_of_hbm_peak": algo / ms / 1e6 / peak})
+            p.close()
+            del buf
+    finally:
+        del os.environ["SDRJFM_LANES"]
+    return out
+
+
 def main():
     global _REAL_STDOUT
     sys.stdout.flush()
@@ -183,6 +228,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=3.0, help="cpu baseline: signal seconds per thread")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--front-end-sweep", action="store_true",
+                    help="also time the front-end kernel alone for every device rate / sample format "
+                         "(BASELINE config 4 and SURVEY.md §8(f) rank 1); adds `front_end_sweep` to the line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -384,6 +432,9 @@ def main():
                        "h2d_bytes_per_step": S * n * 2,
                        "d2h_bytes_per_step": S * (na.value + nr.value) * 8, "steps": e2e_steps}}
 
+    sweep = None
+    if args.front_end_sweep and rank == 0:
+        sweep = front_end_sweep(pkg, torch, dev, local, S, peak)
     clk.__exit__()
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -396,7 +447,8 @@ def main():
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "x_realtime_2p304MSps": value / 2.304, "roofline": roofline,
-                "cpu_baseline": cpu, "e2e": e2e, "device_format_u8": raw, "gpu_launches": int(launches),
+                "cpu_baseline": cpu, "e2e": e2e, "device_format_u8": raw, "front_end_sweep": sweep,
+                "gpu_launches": int(launches),
                 "clocks": clk.summary()}
         emit(line)
     proc.close()
