@@ -47,45 +47,67 @@ __device__ __forceinline__ int brev14 (int k) { return (int)(__brev ((unsigned)k
 // computes, then stores, so the shared/global load latencies overlap instead of serialising.
 constexpr int kRdsBpt = kRdsNh / 2 / kRdsThreads;       // butterflies per thread per stage (8)
 
+// Two radix-2 stages are merged into one pass over shared memory (a radix-4 butterfly written as the
+// two radix-2 layers it consists of, outputs left where the radix-2 stages would have put them, so the
+// overall permutation is still plain bit reversal): 7 passes and barriers instead of 14.
+constexpr int kRdsQpt = kRdsNh / 4 / kRdsThreads;       // quads per thread per pass (4)
+static_assert ((kRdsNh & (kRdsNh - 1)) == 0 && (31 - __builtin_clz (kRdsNh)) % 2 == 0, "an even number of radix-2 stages");
+
 // forward: decimation in frequency, natural order in -> bit-reversed order out
 __device__ void fft_dif (float2 *a, const float2 *__restrict__ tws) {
-	for (int half = kRdsNh / 2; half >= 1; half >>= 1) {
-	   float2 u [kRdsBpt], v [kRdsBpt], w [kRdsBpt];
-	   int idx [kRdsBpt];
+	for (int h = kRdsNh / 2; h >= 2; h >>= 2) {           // stages `half = h` and `half = h / 2`
+	   const int hh = h >> 1;
+	   float2 x0 [kRdsQpt], x1 [kRdsQpt], x2 [kRdsQpt], x3 [kRdsQpt], w [kRdsQpt], w2 [kRdsQpt];
+	   int idx [kRdsQpt];
 #pragma unroll
-	   for (int q = 0; q < kRdsBpt; q ++) {
+	   for (int q = 0; q < kRdsQpt; q ++) {
 	      const int b = threadIdx.x + q * kRdsThreads;
-	      const int pos = b & (half - 1);
-	      idx [q] = ((b - pos) << 1) + pos;
-	      u [q] = a [idx [q]]; v [q] = a [idx [q] + half];
-	      w [q] = __ldg (tws + half + pos);
+	      const int pos = b & (hh - 1);
+	      idx [q] = ((b - pos) << 2) + pos;
+	      x0 [q] = a [idx [q]]; x1 [q] = a [idx [q] + hh]; x2 [q] = a [idx [q] + h]; x3 [q] = a [idx [q] + h + hh];
+	      w [q] = __ldg (tws + h + pos);                 // exp (-2 pi i pos / (2 h))
+	      w2 [q] = __ldg (tws + hh + pos);               // exp (-2 pi i pos / h)
 	   }
 #pragma unroll
-	   for (int q = 0; q < kRdsBpt; q ++) {
-	      a [idx [q]] = make_float2 (u [q].x + v [q].x, u [q].y + v [q].y);
-	      a [idx [q] + half] = cmulf (make_float2 (u [q].x - v [q].x, u [q].y - v [q].y), w [q]);
+	   for (int q = 0; q < kRdsQpt; q ++) {
+	      const float2 A = make_float2 (x0 [q].x + x2 [q].x, x0 [q].y + x2 [q].y);
+	      const float2 B = make_float2 (x1 [q].x + x3 [q].x, x1 [q].y + x3 [q].y);
+	      const float2 C = cmulf (make_float2 (x0 [q].x - x2 [q].x, x0 [q].y - x2 [q].y), w [q]);
+	      const float2 T = cmulf (make_float2 (x1 [q].x - x3 [q].x, x1 [q].y - x3 [q].y), w [q]);
+	      const float2 D = make_float2 (T.y, -T.x);     // twiddle of pos + h/2 is -i times that of pos
+	      a [idx [q]]          = make_float2 (A.x + B.x, A.y + B.y);
+	      a [idx [q] + hh]     = cmulf (make_float2 (A.x - B.x, A.y - B.y), w2 [q]);
+	      a [idx [q] + h]      = make_float2 (C.x + D.x, C.y + D.y);
+	      a [idx [q] + h + hh] = cmulf (make_float2 (C.x - D.x, C.y - D.y), w2 [q]);
 	   }
 	   __syncthreads ();
 	}
 }
 // inverse: decimation in time with conjugate twiddles, bit-reversed order in -> natural order out
 __device__ void ifft_dit (float2 *a, const float2 *__restrict__ tws) {
-	for (int half = 1; half <= kRdsNh / 2; half <<= 1) {
-	   float2 u [kRdsBpt], v [kRdsBpt], w [kRdsBpt];
-	   int idx [kRdsBpt];
+	for (int h = 1; h <= kRdsNh / 4; h <<= 2) {           // stages `half = h` and `half = 2 h`
+	   float2 x0 [kRdsQpt], x1 [kRdsQpt], x2 [kRdsQpt], x3 [kRdsQpt], w [kRdsQpt], w2 [kRdsQpt];
+	   int idx [kRdsQpt];
 #pragma unroll
-	   for (int q = 0; q < kRdsBpt; q ++) {
+	   for (int q = 0; q < kRdsQpt; q ++) {
 	      const int b = threadIdx.x + q * kRdsThreads;
-	      const int pos = b & (half - 1);
-	      idx [q] = ((b - pos) << 1) + pos;
-	      u [q] = a [idx [q]]; v [q] = a [idx [q] + half];
-	      w [q] = __ldg (tws + half + pos);
+	      const int pos = b & (h - 1);
+	      idx [q] = ((b - pos) << 2) + pos;
+	      x0 [q] = a [idx [q]]; x1 [q] = a [idx [q] + h]; x2 [q] = a [idx [q] + 2 * h]; x3 [q] = a [idx [q] + 3 * h];
+	      w [q] = cconj (__ldg (tws + h + pos));
+	      w2 [q] = cconj (__ldg (tws + 2 * h + pos));
 	   }
 #pragma unroll
-	   for (int q = 0; q < kRdsBpt; q ++) {
-	      const float2 t = cmulf (v [q], cconj (w [q]));
-	      a [idx [q]] = make_float2 (u [q].x + t.x, u [q].y + t.y);
-	      a [idx [q] + half] = make_float2 (u [q].x - t.x, u [q].y - t.y);
+	   for (int q = 0; q < kRdsQpt; q ++) {
+	      const float2 t1 = cmulf (x1 [q], w [q]), t2 = cmulf (x3 [q], w [q]);
+	      const float2 y0 = make_float2 (x0 [q].x + t1.x, x0 [q].y + t1.y), y1 = make_float2 (x0 [q].x - t1.x, x0 [q].y - t1.y);
+	      const float2 y2 = make_float2 (x2 [q].x + t2.x, x2 [q].y + t2.y), y3 = make_float2 (x2 [q].x - t2.x, x2 [q].y - t2.y);
+	      const float2 t = cmulf (y2, w2 [q]), u = cmulf (y3, w2 [q]);
+	      const float2 tp = make_float2 (-u.y, u.x);    // conjugate twiddle of pos + h is +i times that of pos
+	      a [idx [q]]         = make_float2 (y0.x + t.x, y0.y + t.y);
+	      a [idx [q] + h]     = make_float2 (y1.x + tp.x, y1.y + tp.y);
+	      a [idx [q] + 2 * h] = make_float2 (y0.x - t.x, y0.y - t.y);
+	      a [idx [q] + 3 * h] = make_float2 (y1.x - tp.x, y1.y - tp.y);
 	   }
 	   __syncthreads ();
 	}
