@@ -67,7 +67,9 @@ typedef struct sdrjfm_meta {
     int32_t pss_state;             /* EPssState 0 OFF, 1 ANALYZING, 2 ESTABLISHED (:676) */
     float   pilot_lock_strength;   /* PilotPllLockStrength (:666)                        */
     int32_t pilot_locked;          /* PilotPllLocked                                     */
-    float   peak_left_db, peak_right_db; /* evaluatePeakLevel (:772-798), last interval  */
+    float   peak_left_db, peak_right_db; /* reserved (0): evaluatePeakLevel (:772-798) and insertTestTone work on
+                                            the 48 kHz PCM the caller already holds; see INTEGRATION.md      */
+    int32_t squelch_active;        /* getSquelchState (:217-219)                          */
 } sdrjfm_meta;
 
 /* intermediate taps (fm rate unless noted) readable after a process call when keep_taps */
@@ -167,7 +169,8 @@ int  sdrjfm_set_bandwidth (sdrjfm_handle *h, int32_t hz);          /* setBandwid
 int  sdrjfm_set_attenuation (sdrjfm_handle *h, float l, float r);  /* setAttenuation */
 int  sdrjfm_set_rds_mode (sdrjfm_handle *h, int32_t mode);         /* setfmRdsSelector: 0 off, 1..3 */
 int  sdrjfm_set_local_oscillator (sdrjfm_handle *h, int32_t hz);   /* set_localOscillator */
-int  sdrjfm_set_squelch_mode (sdrjfm_handle *h, int32_t mode);     /* set_squelchMode: 0 OFF only */
+int  sdrjfm_set_squelch_mode (sdrjfm_handle *h, int32_t mode);     /* set_squelchMode: 0 OFF, 1 NSQ (noise), 2 LSQ (level) */
+int  sdrjfm_set_squelch_value (sdrjfm_handle *h, int32_t value);   /* set_squelchValue: 0..100 */
 int  sdrjfm_set_auto_mono (sdrjfm_handle *h, int32_t on);          /* setAutoMonoMode */
 int  sdrjfm_set_pss_mode (sdrjfm_handle *h, int32_t on);           /* setPSSMode */
 int  sdrjfm_set_dc_remove (sdrjfm_handle *h, int32_t on);          /* setDCRemove (also zeroes RfDC) */

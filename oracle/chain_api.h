@@ -39,6 +39,8 @@ typedef struct chain_cfg {
     float   volume_db;       /* setVolume (:299)                                     */
     int32_t panorama;        /* setStereoPanorama (:277), 100                        */
     int32_t balance;         /* setSoundBalance (:282), 0                            */
+    int32_t squelch_mode;    /* set_squelchMode (:882): 0 OFF, 1 NSQ, 2 LSQ (fm-processor.h:87); ref_ only */
+    int32_t squelch_value;   /* set_squelchValue (:213), 0..100                      */
 } chain_cfg;
 
 /* Output taps. Any pointer may be NULL. Capacities are the caller's business:
@@ -64,6 +66,7 @@ typedef struct chain_meta {   /* SMetaData, fm-processor.h:91-101, as of the las
     int32_t pss_minimized;    /* pPSS.is_error_minimized()                              */
     float pilot_lock_strength;/* pilotRecover.getLockedStrength()                       */
     int32_t pilot_locked;
+    int32_t squelch_active;   /* mySquelch.getSquelchActive () (ref_ only)                */
 } chain_meta;
 
 #define CHAIN_DECL(P)                                                                   \
@@ -95,7 +98,9 @@ enum {
     DUMP_AUDIO_LP_FREQ = 6,/* 8192 complex                    */
     DUMP_SINCOS = 7,       /* fm_rate complex (cos, sin)      */
     DUMP_ATAN = 8,         /* 8 x 8193 floats (as 32772 complex slots) PPY PPX PNY PNX NPY NPX NNY NNX */
-    DUMP_CONSTS = 9        /* 8 floats: K_FM deemphAlpha volumeFactor omega gain pssAlpha pssLockAlpha rfDcAlpha */
+    DUMP_CONSTS = 9,       /* 8 floats: K_FM deemphAlpha volumeFactor omega gain pssAlpha pssLockAlpha rfDcAlpha */
+    DUMP_SQUELCH_IIR = 10  /* ref_ only: squelch filters (squelchClass.cpp:12-21) as floats: high-pass gain, 10 x
+                              (A1 A2 B1 B2), low-pass gain, 10 x (A1 A2 B1 B2)  = 82 floats (41 complex slots) */
 };
 
 #ifdef __cplusplus

@@ -23,6 +23,7 @@ class ChainCfg(C.Structure):
         ("input_filter_hz", C.c_int32), ("lf_cutoff_hz", C.c_int32), ("lo_hz", C.c_int32),
         ("lgain", C.c_float), ("rgain", C.c_float), ("deemph_us", C.c_int32),
         ("volume_db", C.c_float), ("panorama", C.c_int32), ("balance", C.c_int32),
+        ("squelch_mode", C.c_int32), ("squelch_value", C.c_int32),
     ]
 
 
@@ -38,16 +39,17 @@ class ChainMeta(C.Structure):
         ("carrier_ampl", C.c_float), ("pss_phase_shift", C.c_float),
         ("pss_mean_error", C.c_float), ("pss_minimized", C.c_int32),
         ("pilot_lock_strength", C.c_float), ("pilot_locked", C.c_int32),
+        ("squelch_active", C.c_int32),
     ]
 
 
 DEFAULTS = dict(input_rate=2304000, fm_rate=192000, fm_mode=0, decoder=3, sound_sel=0,
                 rds_on=0, auto_mono=1, pss_on=1, dc_remove=1, input_filter_hz=0,
                 lf_cutoff_hz=0, lo_hz=0, lgain=1.0, rgain=1.0, deemph_us=50,
-                volume_db=-6.0, panorama=100, balance=0)
+                volume_db=-6.0, panorama=100, balance=0, squelch_mode=0, squelch_value=0)
 
 DUMP = dict(fmband1=0, fmband2=1, rdsdecim=2, input_filter_freq=3, rds_bp_freq=4,
-            pss_lp_freq=5, audio_lp_freq=6, sincos=7, atan=8, consts=9)
+            pss_lp_freq=5, audio_lp_freq=6, sincos=7, atan=8, consts=9, squelch_iir=10)
 
 _PATHS = {"ref": os.path.join(HERE, "_ref", "libsdrjfm_ref.so"),
           "orc": os.path.join(HERE, "_build", "libsdrjfm_oracle.so")}

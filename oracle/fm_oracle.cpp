@@ -531,6 +531,7 @@ Oracle *c = (Oracle *)h;
 	m -> pss_phase_shift = c -> pilotDelayPSS; m -> pss_mean_error = c -> psMean;
 	m -> pss_minimized = c -> psMin; m -> pilot_lock_strength = c -> pLock;
 	m -> pilot_locked = c -> pLocked;
+	m -> squelch_active = 0;          // the port has no squelch (ref_ only; chain_api.h)
 }
 int32_t	orc_dump_taps (void *h, int which, float *out, int32_t cap) {
 Oracle *c = (Oracle *)h;

@@ -35,10 +35,16 @@
 #include "pilot-recover.h"
 #include "stereo-separation.h"
 #include "fm-demodulator.h"
+#include "squelchClass.h"
 #undef private
 #undef protected
 
 #include "chain_api.h"
+
+// the signal body moc would generate for `signals: void setSquelchIsActive (bool)` (squelchClass.h):
+// the GUI indicator is not part of the arithmetic
+void	squelch::setSquelchIsActive (bool) {}
+
 
 #define PILOT_FREQUENCY 19000
 #define RDS_FREQUENCY (3 * PILOT_FREQUENCY)
@@ -84,6 +90,7 @@ struct RefChain {
 	fftFilterPeek	rdsBandPassFilter;
 	fftFilterHilbert rdsHilbertFilter;
 	fm_Demodulator	theDemodulator;      // owned by RadioInterface in the reference (radio.cpp:190)
+	squelch		mySquelch;           // fm-processor.cpp:87-88
 	DecimatingFIR	rdsDecimator;        // local of run (), fm-processor.cpp:382
 	std::vector<float> rdsPhaseBuffer;
 	int		rdsPhaseIndex;
@@ -114,6 +121,7 @@ struct RefChain {
 	   rdsBandPassFilter (FFT_SIZE, PILOTFILTER_SIZE),
 	   rdsHilbertFilter (FFT_SIZE, PILOTFILTER_SIZE),
 	   theDemodulator (c.fm_rate),
+	   mySquelch (1, 70000, c.fm_rate / 20, c.fm_rate),
 	   rdsDecimator (11, RDS_RATE / 2, c.fm_rate, c.fm_rate / RDS_RATE),
 	   rdsPhaseBuffer (RDS_SAMPLE_DELAY, 0.0f) {
 	   Lgain = c.lgain; Rgain = c.rgain;            // :110-111 / setAttenuation
@@ -145,6 +153,7 @@ struct RefChain {
 	   leftChannel  = (c.balance > 0 ? (100 - c.balance) / 100.0 : 1.0f); // :282-286
 	   rightChannel = (c.balance < 0 ? (100 + c.balance) / 100.0 : 1.0f);
 	   theDemodulator. setDecoder (QString (decoderName (c.decoder)));
+	   mySquelch. setSquelchLevel (c.squelch_value);                    // :410-413 (squelchValue != oldSquelchValue)
 	}
 
 //	fm-processor.cpp:689-759
@@ -288,6 +297,11 @@ struct RefChain {
 	            continue;
 	      }
 	      float demod = theDemodulator. demodulate (v);
+	      switch (cfg.squelch_mode) {                                   // :499-510
+	         case 1: demod = mySquelch. do_noise_squelch (demod); break;
+	         case 2: demod = mySquelch. do_level_squelch (demod, theDemodulator. get_carrier_ampl ()); break;
+	         default:;
+	      }
 	      after_demod (demod, v, t, nfm, nrds);
 	      nfm ++;
 	   }
@@ -311,7 +325,9 @@ int64_t	ref_process_demod (void *h, const float *demod, int64_t n_fm,
 RefChain *c = (RefChain *)h;
 int64_t nfm = 0, nrds = 0;
 	for (int64_t i = 0; i < n_fm; i ++) {
-	   c -> after_demod (demod [i], std::complex<float> (0, 0), taps, nfm, nrds);
+	   float d = demod [i];
+	   if (c -> cfg.squelch_mode == 1) d = c -> mySquelch. do_noise_squelch (d);   // (the level squelch needs the carrier level)
+	   c -> after_demod (d, std::complex<float> (0, 0), taps, nfm, nrds);
 	   nfm ++;
 	}
 	if (n_rds24) *n_rds24 = nrds;
@@ -329,6 +345,7 @@ RefChain *c = (RefChain *)h;
 	m -> pss_minimized = c -> pPSS. is_error_minimized ();
 	m -> pilot_lock_strength = c -> pilotRecover. getLockedStrength ();
 	m -> pilot_locked = c -> pilotRecover. isLocked ();
+	m -> squelch_active = c -> mySquelch. getSquelchActive ();
 }
 
 int32_t	ref_dump_taps (void *h, int which, float *out, int32_t cap) {
@@ -361,6 +378,23 @@ int32_t n = 0;
 	      out [4] = c -> pilotRecover. gain;      out [5] = c -> pPSS. alpha;
 	      out [6] = c -> pPSS. lockAlpha;         out [7] = c -> rfDcAlpha;
 	      return 4;
+	   }
+	   case DUMP_SQUELCH_IIR: {
+//	      the two filters mySquelch builds (squelchClass.cpp:12-21), constructed again here because
+//	      the members are private: HighPassIIR (20, 70000 - 100, fs, S_CHEBYSHEV), LowPassIIR (20, 70000, ..)
+	      if (cap < 41) return -1;
+	      HighPassIIR hp (20, 70000 - 100, c -> fmRate, S_CHEBYSHEV);
+	      LowPassIIR lp (20, 70000, c -> fmRate, S_CHEBYSHEV);
+	      int k = 0;
+	      Basic_IIR *f [2] = { &hp, &lp };
+	      for (int w = 0; w < 2; w ++) {
+	         out [k ++] = f [w] -> gain;
+	         for (int i = 0; i < f [w] -> numofQuads; i ++) {
+	            out [k ++] = f [w] -> Quads [i]. A1; out [k ++] = f [w] -> Quads [i]. A2;
+	            out [k ++] = f [w] -> Quads [i]. B1; out [k ++] = f [w] -> Quads [i]. B2;
+	         }
+	      }
+	      return 41;
 	   }
 	   default: return -1;
 	}

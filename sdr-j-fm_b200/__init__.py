@@ -59,7 +59,7 @@ class Meta(C.Structure):
                 ("pss_phase_shift_deg", C.c_float), ("pss_phase_change", C.c_float),
                 ("pss_state", C.c_int32), ("pilot_lock_strength", C.c_float),
                 ("pilot_locked", C.c_int32), ("peak_left_db", C.c_float),
-                ("peak_right_db", C.c_float)]
+                ("peak_right_db", C.c_float), ("squelch_active", C.c_int32)]
 
 
 def build(verbose=False):
@@ -112,7 +112,7 @@ def lib():
         L.sdrjfm_pilot_stats.argtypes = [vp, vp]
         for name in ("fm_mode", "fm_decoder", "sound_mode", "stereo_panorama", "sound_balance",
                      "deemphasis", "lf_cutoff", "bandwidth", "rds_mode", "local_oscillator",
-                     "squelch_mode", "auto_mono", "pss_mode", "dc_remove"):
+                     "squelch_mode", "squelch_value", "auto_mono", "pss_mode", "dc_remove"):
             getattr(L, f"sdrjfm_set_{name}").argtypes = [vp, i32]
         L.sdrjfm_set_volume_db.argtypes = [vp, f32]
         L.sdrjfm_set_attenuation.argtypes = [vp, f32, f32]
@@ -141,7 +141,7 @@ _HDR_FIELDS = [("magic", "u4"), ("version", "u4"), ("input_rate", "i4"), ("fm_ra
                ("off_rds_bp", "i8"), ("off_audio_lp", "i8"), ("off_input_taps", "i8"),
                ("off_comp_wide", "i8"), ("ncomp_wide", "i4"), ("reserved1", "i4"),
                ("rs_L", "i4"), ("rs_M", "i4"), ("rs_P", "i4"), ("rs_ntapsA", "i4"),
-               ("off_rsA", "i8"), ("off_rsB", "i8")]
+               ("off_rsA", "i8"), ("off_rsB", "i8"), ("off_squelch", "i8")]
 _HDR_DTYPE = np.dtype(_HDR_FIELDS)
 
 
@@ -189,6 +189,11 @@ class Tables:
             return None
         return (L, M, P, self._f(self.hdr["off_rsA"], self.hdr["rs_ntapsA"]),
                 self._f(self.hdr["off_rsB"], L * P).reshape(L, P))
+
+    @property
+    def squelch_iir(self):
+        """82 floats: high-pass gain, 10 x (A1 A2 B1 B2), low-pass gain, 10 x (A1 A2 B1 B2)."""
+        return self._f(self.hdr["off_squelch"], 82)
 
     @property
     def input_taps(self):
@@ -258,6 +263,7 @@ class FmProcessorB200:
     def setfmRdsSelector(self, m): self._ck(self.L.sdrjfm_set_rds_mode(self.h, m))
     def set_localOscillator(self, hz): self._ck(self.L.sdrjfm_set_local_oscillator(self.h, hz))
     def set_squelchMode(self, m): self._ck(self.L.sdrjfm_set_squelch_mode(self.h, m))
+    def set_squelchValue(self, n): self._ck(self.L.sdrjfm_set_squelch_value(self.h, n))
     def setAutoMonoMode(self, on): self._ck(self.L.sdrjfm_set_auto_mono(self.h, int(on)))
     def setPSSMode(self, on): self._ck(self.L.sdrjfm_set_pss_mode(self.h, int(on)))
     def setDCRemove(self, on): self._ck(self.L.sdrjfm_set_dc_remove(self.h, int(on)))
@@ -271,6 +277,7 @@ class FmProcessorB200:
                  pss_on=self.setPSSMode, dc_remove=self.setDCRemove,
                  input_filter_hz=self.setBandwidth, lf_cutoff_hz=self.setlfcutoff,
                  lo_hz=self.set_localOscillator, deemph_us=self.setDeemphasis,
+                 squelch_mode=self.set_squelchMode, squelch_value=self.set_squelchValue,
                  volume_db=self.setVolume, panorama=self.setStereoPanorama,
                  balance=self.setSoundBalance)
         if "lgain" in kw or "rgain" in kw:

@@ -121,6 +121,7 @@ struct Settings {
 	int32_t fm_mode, decoder, sound_sel, rds_mode;
 	int32_t auto_mono, pss_on, dc_remove, lo_hz;
 	int32_t input_filter_hz, lf_cutoff_hz, squelch_mode, deemph_us;
+	int32_t squelch_value, pad1 [3];
 	float   lgain, rgain, volume, panorama;
 	float   left_ch, right_ch, deemph_alpha, pad0;
 };

@@ -133,6 +133,7 @@ struct Lane {
 	dcplx   *d_tileB = nullptr; DiscrSnap *d_snap = nullptr; int32_t ntiles_cap = 0;   // K2 pre-pass
 	float2  *d_pss_ring = nullptr;          // [S][2048] PSS filter input ring (state)
 	int32_t *d_iter_stats = nullptr;        // pilot_kernel diagnostics: [S][4]
+	SquelchState *d_sq = nullptr;           // [S], allocated when the squelch is first switched on
 	bool    pilot_lut_smem = false;         // SDRJFM_PILOT_LUT_SMEM=1: sine table in shared memory, 1 CTA/SM
 	bool    sequential_pll = false;         // SDRJFM_SEQUENTIAL_PLL=1: lane-per-stream K3 (cross-check)
 	int64_t fm_total = 0;                   // fm-rate samples produced so far (per stream)
@@ -166,6 +167,7 @@ static void default_settings (Settings &s, int32_t fm_rate) {
 	s.volume = 0.5f;          // :127
 	s.panorama = 1.0f;        // :128
 	s.left_ch = s.right_ch = 1.0f;                      // :157-158
+	s.squelch_value = 0;      // squelchValue, fm-processor.cpp:194
 	s.deemph_us = 50;
 	{  // the constructor's own formula (:174) is always overwritten by setDeemphasis through
 	   // make_newProcessor (radio.cpp:940, default 50 us radio.cpp:2129); start from the latter
@@ -534,13 +536,15 @@ cudaError_t e;
 	    (e = cudaFuncSetAttribute (frontend_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                               kFtSmemBytes)) != cudaSuccess) return fail (e, "smem attr K1");
 	if ((e = poly_set_attr (shape)) != cudaSuccess) return fail (e, "smem attr K1g");
-	if ((e = cudaFuncSetAttribute (sequential_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                               (cfg -> fm_rate / 4 + 1) * (int)sizeof (float))) != cudaSuccess ||
-	    (e = cudaFuncSetAttribute (sequential_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                               (cfg -> fm_rate / 4 + 1) * (int)sizeof (float))) != cudaSuccess ||
-	    (e = cudaFuncSetAttribute (sequential_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                               (cfg -> fm_rate / 4 + 1) * (int)sizeof (float))) != cudaSuccess)
-	   return fail (e, "smem attr K3");
+	{  const int seqsm = (cfg -> fm_rate / 4 + 1) * (int)sizeof (float);
+	   const auto A = cudaFuncAttributeMaxDynamicSharedMemorySize;
+	   if ((e = cudaFuncSetAttribute (sequential_kernel<0, false>, A, seqsm)) != cudaSuccess ||
+	       (e = cudaFuncSetAttribute (sequential_kernel<1, false>, A, seqsm)) != cudaSuccess ||
+	       (e = cudaFuncSetAttribute (sequential_kernel<2, false>, A, seqsm)) != cudaSuccess ||
+	       (e = cudaFuncSetAttribute (sequential_kernel<0, true>, A, seqsm)) != cudaSuccess ||
+	       (e = cudaFuncSetAttribute (sequential_kernel<1, true>, A, seqsm)) != cudaSuccess ||
+	       (e = cudaFuncSetAttribute (sequential_kernel<2, true>, A, seqsm)) != cudaSuccess)
+	      return fail (e, "smem attr K3"); }
 	if ((e = cudaFuncSetAttribute (pilot_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                               (int)sizeof (PilotSmem))) != cudaSuccess) return fail (e, "smem attr pilot");
 //	the variant with the sine table staged in shared memory only fits with small windows
@@ -568,7 +572,7 @@ void *ptrs [] = { h -> d_tables, h -> d_sin_quarter, h -> d_in, h -> d_hist [0],
 	              h -> d_rds_dtaps, h -> d_rds_tws, h -> d_rds_hist [0], h -> d_rds_hist [1],
 	              h -> d_histw [0], h -> d_histw [1], h -> d_Uw, h -> d_Sw, h -> d_udel [0], h -> d_udel [1],
 	              h -> d_sdel [0], h -> d_sdel [1], h -> d_alp_hist [0], h -> d_alp_hist [1], h -> d_lrf, h -> d_lo_tab,
-	              h -> d_A, h -> d_SA, h -> d_bha [0], h -> d_bha [1], h -> d_bhs [0], h -> d_bhs [1] };
+	              h -> d_A, h -> d_SA, h -> d_bha [0], h -> d_bha [1], h -> d_bhs [0], h -> d_bhs [1], h -> d_sq };
 	for (void *p : ptrs) if (p) cudaFree (p);
 	if (h -> stream_rds) { cudaStreamSynchronize (h -> stream_rds); cudaStreamDestroy (h -> stream_rds); }
 	if (h -> ev_k3) cudaEventDestroy (h -> ev_k3);
@@ -855,18 +859,31 @@ SeqParams sp;
 	sp.n_streams = S;
 const int seq_blocks = (S + kSeqLanes - 1) / kSeqLanes;
 const size_t seq_smem = (h -> lut.quarter + 1) * sizeof (float);
-	if (st.decoder == 2)
-	   sequential_kernel<1><<<seq_blocks, kSeqLanes, seq_smem, h -> stream>>> (
-	         h -> d_res, h -> d_zabs, h -> d_iqn, h -> cap_fm, M, sp, h -> lut, T + th.off_atan,
-	         h -> d_state, h -> d_demod, h -> d_phase, h -> d_locked);
-	else if (st.decoder == 1)
-	   sequential_kernel<2><<<seq_blocks, kSeqLanes, seq_smem, h -> stream>>> (
-	         h -> d_res, h -> d_zabs, h -> d_iqn, h -> cap_fm, M, sp, h -> lut, T + th.off_atan,
-	         h -> d_state, h -> d_demod, h -> d_phase, h -> d_locked);
-	else if (h -> sequential_pll)
-	   sequential_kernel<0><<<seq_blocks, kSeqLanes, seq_smem, h -> stream>>> (
-	         h -> d_res, h -> d_zabs, h -> d_iqn, h -> cap_fm, M, sp, h -> lut, T + th.off_atan,
-	         h -> d_state, h -> d_demod, h -> d_phase, h -> d_locked);
+//	the squelch (20th-order IIRs per sample), the PLL and the AM decoder are per-sample float
+//	recurrences: lane per stream.  Everything else: the parallel-in-time pilot kernel.
+SquelchParams qp;
+	memset (&qp, 0, sizeof qp);
+	if (st.squelch_mode != 0) {
+	   qp.mode = st.squelch_mode;
+	   qp.hold = h -> cfg.fm_rate / 20;                              // holdPeriod, fm-processor.cpp:87
+	   qp.thr_level = std::pow (10.0f, (st.squelch_value - 80) / 30.0f);   // setSquelchLevel, squelchClass.cpp:34-38
+	   qp.thr_noise = 1.0f - st.squelch_value / 100.0f;
+	   qp.weight = (float)(h -> cfg.fm_rate / 100);
+	   const float *sq = h -> tables.payload () + th.off_squelch;
+	   memcpy (qp.hp, sq, sizeof qp.hp);
+	   memcpy (qp.lp, sq + 1 + 4 * kSqQuads, sizeof qp.lp);
+	}
+const int dec = st.decoder == 2 ? 1 : st.decoder == 1 ? 2 : 0;
+#define SEQ_LAUNCH(D, Q) sequential_kernel<D, Q><<<seq_blocks, kSeqLanes, seq_smem, h -> stream>>> ( \
+	         h -> d_res, h -> d_zabs, h -> d_iqn, h -> cap_fm, M, sp, h -> lut, T + th.off_atan, \
+	         h -> d_state, h -> d_demod, h -> d_phase, h -> d_locked, qp, h -> d_sq)
+	if (st.squelch_mode != 0) {
+	   if (dec == 1) SEQ_LAUNCH (1, true); else if (dec == 2) SEQ_LAUNCH (2, true); else SEQ_LAUNCH (0, true);
+	}
+	else if (dec == 1) SEQ_LAUNCH (1, false);
+	else if (dec == 2) SEQ_LAUNCH (2, false);
+	else if (h -> sequential_pll) SEQ_LAUNCH (0, false);
+#undef SEQ_LAUNCH
 	else {
 	   PilotParams pp;
 	   pp.K_FM = sp.K_FM; pp.omega = sp.omega; pp.gain = sp.gain;
@@ -1040,6 +1057,13 @@ std::vector<StreamState> st (S);
 	   m.pilot_lock_strength = h -> set.fm_mode != 2 ? x.pilot_lock : 0.f;
 	   m.pss_state = (h -> set.pss_on && locked) ? (x.pss_minimized ? 2 : 1) : 0;
 	   m.peak_left_db = x.peak_l_db; m.peak_right_db = x.peak_r_db;
+	   m.squelch_active = 0;
+	}
+	if (h -> d_sq) {                                                   // getSquelchState (:217-219)
+	   std::vector<SquelchState> sq (S);
+	   CK (cudaMemcpyAsync (sq.data (), h -> d_sq, S * sizeof (SquelchState), cudaMemcpyDeviceToHost, h -> stream));
+	   CK (cudaStreamSynchronize (h -> stream));
+	   for (int s = 0; s < S; s ++) meta [s].squelch_active = sq [s].suppress;
 	}
 	return SDRJFM_OK;
 }
@@ -1174,9 +1198,18 @@ static int lane_set_local_oscillator (Lane *h, int32_t hz) {
 	return upload_tables (h);        // taps with / without the DC folding, H (lo)
 }
 static int lane_set_squelch_mode (Lane *h, int32_t m) {
-	if (!h) return SDRJFM_ERR_ARG;
-	if (m != 0) { h -> err = "squelch is out of scope (SURVEY.md §2 row 11)"; return SDRJFM_ERR_UNSUPPORTED; }
-	h -> set.squelch_mode = 0; return SDRJFM_OK;
+	if (!h || m < 0 || m > 2) return SDRJFM_ERR_ARG;
+//	set_squelchMode (:882-884): ESqMode OFF / NSQ / LSQ.  The squelch object lives as long as the
+//	processor: its filters and counters keep their state while the mode is off.
+	if (m != 0 && !h -> d_sq) {
+	   CK (cudaSetDevice (h -> cfg.device));
+	   CK (dalloc (&h -> d_sq, (size_t)h -> cfg.n_streams));
+	}
+	h -> set.squelch_mode = m; return SDRJFM_OK;
+}
+static int lane_set_squelch_value (Lane *h, int32_t n) {
+	if (!h || n < 0 || n > 100) return SDRJFM_ERR_ARG;
+	h -> set.squelch_value = n; return SDRJFM_OK;                       // set_squelchValue (:213-215)
 }
 static int lane_set_auto_mono (Lane *h, int32_t on) {
 	if (!h) return SDRJFM_ERR_ARG;

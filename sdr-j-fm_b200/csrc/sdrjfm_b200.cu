@@ -360,6 +360,7 @@ FWD1 (set_bandwidth, int32_t)
 FWD1 (set_rds_mode, int32_t)
 FWD1 (set_local_oscillator, int32_t)
 FWD1 (set_squelch_mode, int32_t)
+FWD1 (set_squelch_value, int32_t)
 FWD1 (set_auto_mono, int32_t)
 FWD1 (set_pss_mode, int32_t)
 FWD1 (set_dc_remove, int32_t)

@@ -121,6 +121,68 @@ struct SeqParams {
 
 constexpr int kSeqLanes = 32;
 
+// ---- squelch (src/various/squelchClass.cpp; in the chain at fm-processor.cpp:499-510) -----------
+// Noise squelch: the demodulated sample goes through a 20th-order Chebyshev high-pass and low-pass
+// (10 biquads each, Basic_IIR::Pass (float), includes/various/iir-filters.h:90-104), the magnitudes
+// are averaged (one-pole, weight fs / 100) and every holdPeriod = fs / 20 samples the two averages
+// decide; level squelch: the carrier level decides.  A suppressed sample is multiplied by 0.
+// These are per-sample float recurrences with poles next to the unit circle: they are restated
+// operation by operation in the lane-per-stream kernel (no re-association).
+constexpr int kSqQuads = 10;
+struct SquelchParams {
+	int32_t mode;                       // 0 OFF, 1 NSQ, 2 LSQ (fm-processor.h:87)
+	int32_t hold;                       // holdPeriod
+	float   thr_noise, thr_level;       // setSquelchLevel, squelchClass.cpp:34-38
+	float   weight;                     // sampleRate / 100
+	float   hp [1 + 4 * kSqQuads];      // gain, then (A1 A2 B1 B2) per biquad
+	float   lp [1 + 4 * kSqQuads];
+};
+struct SquelchState {                  // squelch members (squelchClass.h:41-52) + the biquad memories
+	float   hp_m1 [kSqQuads], hp_m2 [kSqQuads], lp_m1 [kSqQuads], lp_m2 [kSqQuads];
+	float   avg_high, avg_low;
+	int32_t count, suppress;
+};
+
+__device__ __forceinline__ float iir_pass (const float *coef, float *m1, float *m2, float v) {
+float o = fmul (v, coef [0]);
+#pragma unroll
+	for (int i = 0; i < kSqQuads; i ++) {
+	   const float A1 = coef [1 + 4 * i], A2 = coef [2 + 4 * i], B1 = coef [3 + 4 * i], B2 = coef [4 + 4 * i];
+	   const float w = fsub (fsub (o, fmul (m1 [i], B1)), fmul (m2 [i], B2));
+	   o = fadd (fadd (w, fmul (m1 [i], A1)), fmul (m2 [i], A2));
+	   m2 [i] = m1 [i];
+	   m1 [i] = w;
+	}
+	return o;
+}
+__device__ __forceinline__ float decaying_average (float old, float input, float weight) {      // :40-45
+	if (weight <= 1) return input;
+	return (float)((double)input * (1.0 / (double)weight) + (double)old * (1.0 - (1.0 / (double)weight)));
+}
+__device__ __forceinline__ float squelch_step (const SquelchParams &Q, SquelchState &s, float sample, float carrier) {
+const float hystN = 0.001f;             // SQUELCH_HYSTERESIS_NSQ; _LSQ = 0; LEVELREDUCTIONFACTOR = 0
+	if (Q.mode == 1) {
+	   const float v1 = fabsf (iir_pass (Q.hp, s.hp_m1, s.hp_m2, sample));
+	   const float v2 = fabsf (iir_pass (Q.lp, s.lp_m1, s.lp_m2, sample));
+	   s.avg_high = decaying_average (s.avg_high, v1, Q.weight);
+	   s.avg_low  = decaying_average (s.avg_low, v2, Q.weight);
+	   if (++ s.count >= Q.hold) {
+	      s.count = 0;
+	      if (Q.thr_noise < hystN) s.suppress = 1;
+	      else if (s.avg_high < fsub (fmul (s.avg_low, Q.thr_noise), hystN)) s.suppress = 0;
+	      else if (s.avg_high >= fadd (fmul (s.avg_low, Q.thr_noise), hystN)) s.suppress = 1;
+	   }
+	}
+	else {
+	   if (++ s.count >= Q.hold) {
+	      s.count = 0;
+	      if (carrier < fsub (Q.thr_level, 0.0f)) s.suppress = 1;
+	      else if (carrier >= fadd (Q.thr_level, 0.0f)) s.suppress = 0;
+	   }
+	}
+	return s.suppress ? fmul (sample, 0.0f) : sample;
+}
+
 struct SeqCarry {      // loop-carried registers of one stream
 	float fm_afc, am, phase, oldv, plock, nco, incr;
 	int   locked, stable;
@@ -129,10 +191,11 @@ struct SeqCarry {      // loop-carried registers of one stream
 // DEC: 0 = discriminator output computed by K2 (Mixed, complex/real baseband delay, difference),
 //      1 = PLL decoder (pllC on the normalised sample), 2 = AM decoder (pllC on the raw sample for
 //      the AFC read-out, audio from the envelope: fm_Demodulator::decodeAM, fm-demodulator.cpp:215-241)
-template <int DEC>
+template <int DEC, bool SQ>
 __device__ __forceinline__ void seq_step (const SeqParams &P, const SinLut &L, const float *q,
                                           const float *atanPPY, SeqCarry &c, float res, float zAbs,
-                                          float2 nqv, float &demod_o, float &phase_o, uint8_t &lock_o) {
+                                          float2 nqv, const SquelchParams &Q, SquelchState &qs,
+                                          float &demod_o, float &phase_o, uint8_t &lock_o) {
 const float carrierAlpha = 0.0010f, fmDcAlpha = 0.0001f;          // fm-demodulator.cpp:115-117
 const float oneMinusCarrier = fsub (1.0f, carrierAlpha);
 const float oneMinusDc = fsub (1.0f, fmDcAlpha);
@@ -160,6 +223,7 @@ float demod = fdiv (fmul (fmul (20.0f, fsub (res, c.fm_afc)), 1.0f), P.K_FM);
 	   demod = fdiv (fsub (zAbs, c.am), c.am < gainLimit ? gainLimit : c.am);
 	   demod = demod > 1.0f ? 1.0f : (demod < -1.0f ? -1.0f : demod);
 	}
+	if (SQ) demod = squelch_step (Q, qs, demod, c.am);               // fm-processor.cpp:499-510
 //	pilotRecovery::getPilotPhase (5 * demod), pilot-recover.cpp:54-83
 const float pilot = fmul (5.0f, demod);
 const float osc = lut_getSin (L, q, c.phase);
@@ -179,14 +243,15 @@ const float quad = fdiv (fsub (osc, c.oldv), P.omega);
 
 // res_raw, zabs, iqn : K2 outputs.  demod / pilot_phase / locked : fm-rate outputs.
 // One lane per stream; the quarter-wave sine table lives in shared memory.
-template <int DEC>
+template <int DEC, bool SQ>
 __global__ void __launch_bounds__ (kSeqLanes)
 sequential_kernel (const float *__restrict__ res_raw, const float *__restrict__ zabs,
                    const float2 *__restrict__ iqn, int64_t pitch, int32_t M,
                    const SeqParams P, const SinLut L, const float *__restrict__ atanPPY,
                    StreamState *__restrict__ state,
                    float *__restrict__ demod_out, float *__restrict__ phase_out,
-                   uint8_t *__restrict__ locked_out) {
+                   uint8_t *__restrict__ locked_out,
+                   const SquelchParams Q, SquelchState *__restrict__ sqstate) {
 extern __shared__ float sq [];
 	for (int i = threadIdx.x; i <= L.quarter; i += blockDim.x) sq [i] = L.q [i];
 	__syncthreads ();
@@ -205,6 +270,8 @@ SeqCarry c;
 	c.phase = st.pilot_phase; c.oldv = st.pilot_old; c.plock = st.pilot_lock;
 	c.locked = st.pilot_locked; c.stable = st.pilot_stable_cnt;
 	c.nco = st.pll_nco_phase; c.incr = st.pll_phase_incr;
+SquelchState qs;
+	if (SQ) qs = sqstate [stream];
 
 int32_t m = 0;
 	for (; m + 4 <= M; m += 4) {
@@ -219,22 +286,23 @@ int32_t m = 0;
 	   float d4 [4], p4 [4]; uint8_t l4 [4];
 #pragma unroll
 	   for (int k = 0; k < 4; k ++)
-	      seq_step<DEC> (P, L, sq, atanPPY, c, rv [k], zv [k],
-	                     DEC != 0 ? n4 [k] : make_float2 (0.f, 0.f), d4 [k], p4 [k], l4 [k]);
+	      seq_step<DEC, SQ> (P, L, sq, atanPPY, c, rv [k], zv [k],
+	                         DEC != 0 ? n4 [k] : make_float2 (0.f, 0.f), Q, qs, d4 [k], p4 [k], l4 [k]);
 	   *reinterpret_cast<float4 *>(dm + m) = make_float4 (d4 [0], d4 [1], d4 [2], d4 [3]);
 	   *reinterpret_cast<float4 *>(ph + m) = make_float4 (p4 [0], p4 [1], p4 [2], p4 [3]);
 	   *reinterpret_cast<uchar4 *>(lk + m) = make_uchar4 (l4 [0], l4 [1], l4 [2], l4 [3]);
 	}
 	for (; m < M; m ++) {
 	   float d, p; uint8_t l;
-	   seq_step<DEC> (P, L, sq, atanPPY, c, rr [m], za [m],
-	                  DEC != 0 ? nq [m] : make_float2 (0.f, 0.f), d, p, l);
+	   seq_step<DEC, SQ> (P, L, sq, atanPPY, c, rr [m], za [m],
+	                      DEC != 0 ? nq [m] : make_float2 (0.f, 0.f), Q, qs, d, p, l);
 	   dm [m] = d; ph [m] = p; lk [m] = l;
 	}
 	st.fm_afc = c.fm_afc; st.am_carr_ampl = c.am;
 	st.pilot_phase = c.phase; st.pilot_old = c.oldv; st.pilot_lock = c.plock;
 	st.pilot_locked = c.locked; st.pilot_stable_cnt = c.stable;
 	st.pll_nco_phase = c.nco; st.pll_phase_incr = c.incr;
+	if (SQ) sqstate [stream] = qs;
 }
 
 }	// namespace sdrjfm

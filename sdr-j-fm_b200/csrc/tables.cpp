@@ -160,6 +160,88 @@ const double fc = 0.5 * (double)fm_rate / ((double)input_rate / DA * L);
 	return true;
 }
 
+// ---- squelch IIR design ----------------------------------------------------------------------
+// Restates, with the reference's float / double promotions (DSPFLOAT = float; `using namespace std`
+// picks the float overloads of sqrt / log / sinh / cosh / sin / cos for float arguments), the design
+// path the two squelch filters take through src/various/iir-filters.cpp:
+//   newChebyshev (:173-229, even order)  ->  low-pass (:469-500) / high-pass (:510-548) un-normalisation
+//   ->  Bilineair (:80-117).  order 20 => 10 biquads; apass = -1 dB.
+namespace {
+struct Quad { float A0, A1, A2, B0, B1, B2; };
+
+float asinh_ref (float x) { return logf (x + sqrtf (x * x + 1)); }           // sinhm1, :35-38
+
+float chebyshev_even (Quad *q, int n, int order, int apass) {
+const float Eps = sqrt (pow (10.0, -0.1 * apass) - 1);
+const float D = asinh_ref (1.0 / Eps) / order;
+const float sinhD = sinhf (D), coshD = coshf (D);
+	for (int i = 0; i < n; i ++) {
+	   const float Phim = (M_PI * (2 * i + 1) / (2 * order));
+	   const float sigma = - sinhD * sinf (Phim);
+	   const float omega =   coshD * cosf (Phim);
+	   q [i].A0 = 0; q [i].A1 = 0; q [i].A2 = (sigma * sigma + omega * omega);
+	   q [i].B0 = 1; q [i].B1 = -2 * sigma; q [i].B2 = (sigma * sigma + omega * omega);
+	}
+	return pow (10.0, 0.05 * apass);
+}
+
+float warp_d_to_a (int fd, int fs) { return 2.0 * fs * tan ((2 * M_PI * fd) / (2 * fs)); }   // :120-122
+
+float bilinear (Quad *q, int fs, int n) {
+const float f2 = 2 * fs, f4 = f2 * f2;
+float gain = 1.0;
+	for (int i = 0; i < n; i ++) {
+	   Quad &c = q [i];
+	   const float N0 = c.A0 * f4 + c.A1 * f2 + c.A2;
+	   const float N1 = 2 * (c.A2 - c.A0 * f4);
+	   const float N2 = c.A0 * f4 - c.A1 * f2 + c.A2;
+	   const float D0 = c.B0 * f4 + c.B1 * f2 + c.B2;
+	   const float D1 = 2 * (c.B2 - c.B0 * f4);
+	   const float D2 = c.B0 * f4 - c.B1 * f2 + c.B2;
+	   c.A0 = 1.0; c.A1 = N1 / N0; c.A2 = N2 / N0;
+	   c.B0 = 1.0; c.B1 = D1 / D0; c.B2 = D2 / D0;
+	   gain *= (N0 / D0);
+	}
+	return gain;
+}
+}	// namespace
+
+void design_squelch_iir (int32_t fm_rate, float *out) {
+const int order = 20, n = kSquelchQuads, apass = -1;
+const int key = 70000;                                   // keyFrequency, fm-processor.cpp:87
+Quad q [kSquelchQuads];
+int k = 0;
+	{  // HighPassIIR (20, key - 100, fs, S_CHEBYSHEV)
+	   int fpass = key - 100;
+	   if (2 * fpass >= fm_rate) fpass = fm_rate / 4;
+	   const float omega = warp_d_to_a (fpass, fm_rate);
+	   float gain = chebyshev_even (q, n, order, apass);
+	   for (int i = 0; i < n; i ++) {
+	      const float A0 = q [i].A0, A1 = q [i].A1, A2 = q [i].A2, B0 = q [i].B0, B1 = q [i].B1, B2 = q [i].B2;
+	      gain *= A2 / B2;
+	      q [i].A0 = 1.0; q [i].B0 = 1.0;
+	      q [i].A1 = (A1 / A2) * omega; q [i].B1 = (B1 / B2) * omega;
+	      q [i].A2 = (A0 / A2) * omega * omega; q [i].B2 = (B0 / B2) * omega * omega;
+	   }
+	   gain *= bilinear (q, fm_rate, n);
+	   out [k ++] = gain;
+	   for (int i = 0; i < n; i ++) { out [k ++] = q [i].A1; out [k ++] = q [i].A2; out [k ++] = q [i].B1; out [k ++] = q [i].B2; }
+	}
+	{  // LowPassIIR (20, key, fs, S_CHEBYSHEV)
+	   int fpass = key;
+	   if (2 * fpass >= fm_rate) fpass = fm_rate / 4;
+	   const float omega = warp_d_to_a (fpass, fm_rate);
+	   float gain = chebyshev_even (q, n, order, apass);
+	   for (int i = 0; i < n; i ++) {
+	      q [i].A1 = q [i].A1 * omega; q [i].B1 = q [i].B1 * omega;
+	      q [i].A2 = q [i].A2 * omega * omega; q [i].B2 = q [i].B2 * omega * omega;
+	   }
+	   gain *= bilinear (q, fm_rate, n);
+	   out [k ++] = gain;
+	   for (int i = 0; i < n; i ++) { out [k ++] = q [i].A1; out [k ++] = q [i].A2; out [k ++] = q [i].B1; out [k ++] = q [i].B2; }
+	}
+}
+
 namespace {
 struct Packer {
 	std::vector<float> f;
@@ -319,6 +401,11 @@ Packer pk;
 	      h.off_rsA = pk.put (hA);
 	      h.off_rsB = pk.put (hB);
 	   }
+	}
+	{
+	   float sq [kSquelchFloats];
+	   design_squelch_iir (fm_rate, sq);
+	   h.off_squelch = pk.put (sq, kSquelchFloats);
 	}
 	while (pk.f.size () % 4) pk.f.push_back (0.0f);
 	h.payload_floats = (int64_t)pk.f.size ();

@@ -62,6 +62,7 @@ struct TableHeader {
 	int32_t  rs_L, rs_M, rs_P, rs_ntapsA;   // stage B: up L, down M, P taps per phase; stage A taps (49)
 	int64_t  off_rsA;                        // rs_ntapsA real taps, unit DC gain
 	int64_t  off_rsB;                        // [rs_L][rs_P] real taps, every phase unit DC gain
+	int64_t  off_squelch;                    // kSquelchFloats floats, see design_squelch_iir
 };
 
 struct TableBlob {
@@ -84,6 +85,13 @@ std::vector<cf32>  fft_twiddles (int n);
 // L / M with L <= 16 and P <= 128
 bool design_resampler (int32_t input_rate, int32_t fm_rate, int &L, int &M, int &P,
                        std::vector<float> &hA, std::vector<float> &hB);
+
+// squelch filters (squelchClass.cpp:12-21): HighPassIIR (20, 70000 - 100, fs, S_CHEBYSHEV) and
+// LowPassIIR (20, 70000, fs, S_CHEBYSHEV), src/various/iir-filters.cpp.  out = 82 floats:
+// high-pass gain, 10 x (A1 A2 B1 B2), low-pass gain, 10 x (A1 A2 B1 B2).
+constexpr int kSquelchQuads = 10;
+constexpr int kSquelchFloats = 2 * (1 + 4 * kSquelchQuads);
+void design_squelch_iir (int32_t fm_rate, float *out);
 
 TableBlob build_tables (int32_t input_rate, int32_t fm_rate, int32_t input_filter_hz,
                         int32_t audio_lp_hz);

@@ -92,3 +92,13 @@ def test_tables_at_device_rates_match_reference_constructors(pkg, chainlib, ref_
     d = pkg.front_end_decimation(fs)
     assert d == int(T.hdr["decim1"]) * int(T.hdr["decim2"]) == {2400000: 12, 6000000: 30, 10000000: 48}[fs]
     assert int(T.hdr["ncomp"]) == 25 + 6 * (d // 6)
+
+
+def test_squelch_filter_design_matches_reference(pkg, chainlib, ref_available):
+    """the two 20th-order Chebyshev IIRs of the squelch (iir-filters.cpp via squelchClass.cpp:12-21):
+    host-side restatement of the design, bit-identical coefficients and gains."""
+    if not ref_available:
+        pytest.skip("oracle/_ref not available")
+    ref = chainlib.Chain("ref").dump("squelch_iir").view(np.float32)[:82]
+    mine = pkg.design_tables().squelch_iir
+    assert _same(np.ascontiguousarray(ref), np.ascontiguousarray(mine))

@@ -388,3 +388,47 @@ def test_many_streams_over_lanes_match_reference(pkg, signals, checker):
         assert rms(audio[s]) > 1e-3
     # streams are independent: distinct tones give distinct outputs
     assert rms(audio[0] - audio[1]) > 1e-3
+
+
+def _squelch_signal(signals, n):
+    """noise only for the first 40 %, then the stereo station, then a weak (20 dB down) tail."""
+    rng = np.random.default_rng(4242)
+    x = signals.stereo_pilot(n).astype(np.complex64)
+    k1, k2 = int(0.4 * n), int(0.8 * n)
+    noise = 0.02 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    x[:k1] = 0
+    x[k2:] *= 0.02
+    return (x + noise).astype(np.complex64)
+
+
+@pytest.mark.parametrize("mode,value", [(1, 50), (2, 60), (1, 80)])
+def test_squelch_matches_reference(pkg, signals, chainlib, ref_available, monkeypatch, mode, value):
+    """squelch (squelchClass.cpp; fm-processor.cpp:499-510): NSQ = two 20th-order Chebyshev IIRs on the
+    demodulated signal, averaged magnitudes compared every 9600 samples; LSQ = carrier level against a
+    threshold.  The checker is the reference's own class (QObject stubbed); the port has no squelch."""
+    if not ref_available:
+        pytest.skip("oracle/_ref not available")
+    n = N1
+    x = _squelch_signal(signals, n)
+    cfg = dict(fm_mode=0, volume_db=0.0, squelch_mode=mode, squelch_value=value)
+    c = chainlib.Chain("ref", **cfg)
+    ref = c.process(x)
+    got = run_gpu(pkg, x, chunks=[16384 * 7 + 5, N1 // 3, n], **cfg)
+    open_frac = float(np.mean(ref["demod"] != 0))
+    print("mode", mode, "value", value, "open fraction", open_frac,
+          "demod", rms(got["demod"][0] - ref["demod"]), "audio192", rms(got["audio192"][0] - ref["audio192"]))
+    assert 0.15 < open_frac < 0.85                       # the squelch both closed and opened
+    assert np.array_equal(got["demod"][0] == 0, ref["demod"] == 0)      # same decisions at the same samples
+    assert rms(got["demod"][0] - ref["demod"]) < 1e-5
+    assert rms(got["audio192"][0] - ref["audio192"]) < 1e-5
+    assert got["meta"][0]["squelch_active"] == c.meta()["squelch_active"]
+    if mode == 1:
+        # bit-exactness of the IIR restatement: the reference's squelch fed with the GPU's own
+        # (un-squelched) discriminator output must reproduce the GPU's squelched stream exactly
+        # (the lane-per-stream kernel, which is the one the squelch runs in: its AFC one-pole is the
+        # float recurrence, the pilot kernel's is a double-precision scan)
+        monkeypatch.setenv("SDRJFM_SEQUENTIAL_PLL", "1")
+        raw = run_gpu(pkg, x, chunks=[16384 * 7 + 5, N1 // 3, n], fm_mode=0, volume_db=0.0)["demod"][0]
+        monkeypatch.delenv("SDRJFM_SEQUENTIAL_PLL")
+        ref2 = chainlib.Chain("ref", **cfg).process_demod(raw, taps=("demod",))
+        assert np.array_equal(got["demod"][0].view(np.uint32), ref2["demod"].view(np.uint32))

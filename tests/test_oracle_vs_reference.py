@@ -54,6 +54,8 @@ def test_port_tables_bit_exact(chainlib, ref_available):
     cfg = dict(input_filter_hz=165000, lf_cutoff_hz=15000)
     a, b = chainlib.Chain("ref", **cfg), chainlib.Chain("orc", **cfg)
     for w in chainlib.DUMP:
+        if w == "squelch_iir":          # ref_ only: the port has no squelch (chain_api.h)
+            continue
         da, db = a.dump(w), b.dump(w)
         assert da is not None and db is not None, w
         assert _same(da, db), w
