@@ -120,10 +120,17 @@ enum sdrjfm_iq_format {
     SDRJFM_IQ_CF32 = 0,   /* interleaved float32: what getSamples delivers                          */
     SDRJFM_IQ_U8   = 1,   /* rtlsdr: (b - 127) / 128        devices/rtlsdr-handler/rtlsdr-handler.cpp:286-293 */
     SDRJFM_IQ_S8   = 2,   /* hackrf: b / 128                devices/hackrf-handler/hackrf-handler.cpp:355-368 */
-    SDRJFM_IQ_S16  = 3    /* v / denominator: sdrplay 2048|8192 (sdrplay-handler.cpp:266-270,481-488),
+    SDRJFM_IQ_S16  = 3,   /* v / denominator: sdrplay 2048|8192 (sdrplay-handler.cpp:266-270,481-488),
                              sdrplay v3 2048|4096 (sdrplay-handler-v3.cpp:254-263,293), pluto 2048
-                             (pluto-handler.cpp:574-583), lime 2048, airspy 2048                     */
+                             (pluto-handler.cpp:574-583), lime 2048                                  */
+    SDRJFM_IQ_AIRSPY_S16 = 4  /* airspy: int16 / 2048 at the device's NATIVE rate (sdrjfm_set_native_rate),
+                             converted to 2 304 000 samples/s by the handler's per-millisecond linear
+                             interpolation (devices/airspy/airspy-handler.cpp:117-128, 283-309), fused
+                             into the front-end kernel's read.  n_in / in_pitch count native samples.  */
 };
+/* native rate of the airspy (a multiple of 1000 Hz; the handler picks the one closest to 2.0 MS/s,
+ * airspy-handler.cpp:108-115).  The handle's input_rate must be 2304000.                          */
+int  sdrjfm_set_native_rate (sdrjfm_handle *h, int32_t hz);
 /* sdrjfm_process / sdrjfm_process_device for samples in a device format; in_pitch in IQ samples.
  * denominator: the int16 divisor (power of two); ignored for the 8-bit formats.               */
 int  sdrjfm_process_raw (sdrjfm_handle *h, const void *iq, int32_t format, int32_t denominator,

@@ -28,8 +28,8 @@ _TAP_DTYPE = dict(fm_z=np.complex64, demod=np.float32, pilot_phase=np.float32,
 
 
 # device sample formats (enum sdrjfm_iq_format): dtype of one I or Q component
-IQ_FORMAT = dict(cf32=0, u8=1, s8=2, s16=3)
-_IQ_DTYPE = {0: np.float32, 1: np.uint8, 2: np.int8, 3: np.int16}
+IQ_FORMAT = dict(cf32=0, u8=1, s8=2, s16=3, airspy=4)
+_IQ_DTYPE = {0: np.float32, 1: np.uint8, 2: np.int8, 3: np.int16, 4: np.int16}
 
 
 def front_end_decimation(input_rate, fm_rate=192000):
@@ -112,7 +112,7 @@ def lib():
         L.sdrjfm_pilot_stats.argtypes = [vp, vp]
         for name in ("fm_mode", "fm_decoder", "sound_mode", "stereo_panorama", "sound_balance",
                      "deemphasis", "lf_cutoff", "bandwidth", "rds_mode", "local_oscillator",
-                     "squelch_mode", "squelch_value", "auto_mono", "pss_mode", "dc_remove"):
+                     "squelch_mode", "squelch_value", "native_rate", "auto_mono", "pss_mode", "dc_remove"):
             getattr(L, f"sdrjfm_set_{name}").argtypes = [vp, i32]
         L.sdrjfm_set_volume_db.argtypes = [vp, f32]
         L.sdrjfm_set_attenuation.argtypes = [vp, f32, f32]
@@ -264,6 +264,7 @@ class FmProcessorB200:
     def set_localOscillator(self, hz): self._ck(self.L.sdrjfm_set_local_oscillator(self.h, hz))
     def set_squelchMode(self, m): self._ck(self.L.sdrjfm_set_squelch_mode(self.h, m))
     def set_squelchValue(self, n): self._ck(self.L.sdrjfm_set_squelch_value(self.h, n))
+    def set_nativeRate(self, hz): self._ck(self.L.sdrjfm_set_native_rate(self.h, hz))
     def setAutoMonoMode(self, on): self._ck(self.L.sdrjfm_set_auto_mono(self.h, int(on)))
     def setPSSMode(self, on): self._ck(self.L.sdrjfm_set_pss_mode(self.h, int(on)))
     def setDCRemove(self, on): self._ck(self.L.sdrjfm_set_dc_remove(self.h, int(on)))

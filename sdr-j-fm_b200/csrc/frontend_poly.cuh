@@ -33,19 +33,38 @@ namespace sdrjfm {
 constexpr int kPolyMaxTaps = 352;                   // max D * NG over the instantiated shapes
 __constant__ float c_poly [kPolyMaxTaps];
 
-enum { kFmtCF32 = 0, kFmtU8 = 1, kFmtS8 = 2, kFmtS16 = 3 };
+// kFmtAirspy: s16 IQ at the airspy's native rate, brought to 2.304 MS/s by the handler's own
+// per-millisecond linear interpolation (airspy-handler.cpp:117-128, 283-309): block b = native samples
+// b B .. (b + 1) B (B = native rate / 1000), output j of the block =
+// x[b B + mapInt[j] + 1] * mapFrac[j] + x[b B + mapInt[j]] * (1 - mapFrac[j]).  Sample index n of the
+// kernel is the OUTPUT index; the tables are the reference's (built on the host with its formulas).
+enum { kFmtCF32 = 0, kFmtU8 = 1, kFmtS8 = 2, kFmtS16 = 3, kFmtAirspy = 4 };
+constexpr int kAirspyOut = 2304;                    // output samples per millisecond block
 
 struct RawFmt {
 	int32_t fmt;               // kFmt*
 	float   scale;             // 1 / denominator (u8, s8: 1/128)
+	int32_t blk;               // kFmtAirspy: native samples per block
+	const int16_t *map_int;    // kFmtAirspy: mapTable_int [2304]
+	const float   *map_frac;   // kFmtAirspy: mapTable_float [2304]
 };
 
 __host__ __device__ constexpr int fmt_bytes (int fmt) {
-	return fmt == kFmtCF32 ? 8 : fmt == kFmtS16 ? 4 : 2;
+	return fmt == kFmtCF32 ? 8 : (fmt == kFmtS16 || fmt == kFmtAirspy) ? 4 : 2;
 }
 
 template <int FMT>
-__device__ __forceinline__ float2 load_iq (const void *base, int64_t n, float scale) {
+__device__ __forceinline__ float2 load_iq (const void *base, int64_t n, const RawFmt &rf) {
+const float scale = rf.scale;
+	if (FMT == kFmtAirspy) {
+	   const int b = (int)n / kAirspyOut, j = (int)n - b * kAirspyOut;
+	   const short2 *p = reinterpret_cast<const short2 *>(base) + ((int64_t)b * rf.blk + rf.map_int [j]);
+	   const short2 s0 = __ldg (p), s1 = __ldg (p + 1);
+	   const float r = rf.map_frac [j], r1 = fsub (1.0f, r);
+	   const float2 x0 = make_float2 ((float)s0.x * scale, (float)s0.y * scale);
+	   const float2 x1 = make_float2 ((float)s1.x * scale, (float)s1.y * scale);
+	   return make_float2 (fadd (fmul (x1.x, r), fmul (x0.x, r1)), fadd (fmul (x1.y, r), fmul (x0.y, r1)));
+	}
 	if (FMT == kFmtU8) {
 	   const uchar2 v = __ldcs (reinterpret_cast<const uchar2 *>(base) + n);
 	   return make_float2 ((float)((int)v.x - 127) * scale, (float)((int)v.y - 127) * scale);
@@ -61,12 +80,13 @@ __device__ __forceinline__ float2 load_iq (const void *base, int64_t n, float sc
 	return __ldcs (reinterpret_cast<const float2 *>(base) + n);
 }
 
-__device__ __forceinline__ float2 load_iq_rt (const void *base, int64_t n, RawFmt rf) {
+__device__ __forceinline__ float2 load_iq_rt (const void *base, int64_t n, const RawFmt &rf) {
 	switch (rf.fmt) {
-	   case kFmtU8:  return load_iq<kFmtU8> (base, n, rf.scale);
-	   case kFmtS8:  return load_iq<kFmtS8> (base, n, rf.scale);
-	   case kFmtS16: return load_iq<kFmtS16> (base, n, rf.scale);
-	   default:      return load_iq<kFmtCF32> (base, n, rf.scale);
+	   case kFmtU8:  return load_iq<kFmtU8> (base, n, rf);
+	   case kFmtS8:  return load_iq<kFmtS8> (base, n, rf);
+	   case kFmtS16: return load_iq<kFmtS16> (base, n, rf);
+	   case kFmtAirspy: return load_iq<kFmtAirspy> (base, n, rf);
+	   default:      return load_iq<kFmtCF32> (base, n, rf);
 	}
 }
 
@@ -94,12 +114,12 @@ struct Poly {
 template <class P, int FMT>
 __device__ __forceinline__ void poly_stage (float2 *sm, float2 *sRaw, const void *xs, int64_t in0, int64_t N,
                                             const float2 *hist_s, bool first_tile, const LoParams &lop,
-                                            bool lo, float scale, int tid) {
+                                            bool lo, const RawFmt &rf, int tid) {
 //	halo: sample in0 - HaloIn + i sits at row i % Rows, column i / Rows
 	for (int i = tid; i < P::HaloIn; i += kFeThreads) {
 	   float2 v;
 	   if (first_tile) v = hist_s [i];
-	   else            v = load_iq<FMT> (xs, in0 - P::HaloIn + i, scale);
+	   else            v = load_iq<FMT> (xs, in0 - P::HaloIn + i, rf);
 	   if (lo) v = lo_apply (lop, v, lo_index (lop, in0 - P::HaloIn + i));
 	   sm [(i % P::Rows) * P::Pitch + i / P::Rows] = v;
 	}
@@ -111,7 +131,7 @@ int32_t loIdx = lo ? lo_index (lop, in0 + tid) : 0;
 	   for (int k = 0; k < P::Batch; k ++) {
 	      const int j = (b * P::Batch + k) * kFeThreads + tid;
 	      const int64_t n = in0 + j;
-	      v [k] = (n < N) ? load_iq<FMT> (xs, n, scale) : make_float2 (0.f, 0.f);
+	      v [k] = (n < N) ? load_iq<FMT> (xs, n, rf) : make_float2 (0.f, 0.f);
 	   }
 	   if (lo) {
 #pragma unroll
@@ -156,10 +176,11 @@ const void *xs = reinterpret_cast<const char *>(x) + (int64_t)stream * in_pitch 
 const float2 *hs = hist + (int64_t)stream * hist_len + (hist_len - P::HaloIn);
 const bool first = blockIdx.x == 0;
 	switch (rf.fmt) {
-	   case kFmtU8:  poly_stage<P, kFmtU8>  (sm, sRaw, xs, in0, N, hs, first, lop, lo, rf.scale, tid); break;
-	   case kFmtS8:  poly_stage<P, kFmtS8>  (sm, sRaw, xs, in0, N, hs, first, lop, lo, rf.scale, tid); break;
-	   case kFmtS16: poly_stage<P, kFmtS16> (sm, sRaw, xs, in0, N, hs, first, lop, lo, rf.scale, tid); break;
-	   default:      poly_stage<P, kFmtCF32>(sm, sRaw, xs, in0, N, hs, first, lop, lo, rf.scale, tid); break;
+	   case kFmtU8:  poly_stage<P, kFmtU8>  (sm, sRaw, xs, in0, N, hs, first, lop, lo, rf, tid); break;
+	   case kFmtS8:  poly_stage<P, kFmtS8>  (sm, sRaw, xs, in0, N, hs, first, lop, lo, rf, tid); break;
+	   case kFmtS16: poly_stage<P, kFmtS16> (sm, sRaw, xs, in0, N, hs, first, lop, lo, rf, tid); break;
+	   case kFmtAirspy: poly_stage<P, kFmtAirspy> (sm, sRaw, xs, in0, N, hs, first, lop, lo, rf, tid); break;
+	   default:      poly_stage<P, kFmtCF32>(sm, sRaw, xs, in0, N, hs, first, lop, lo, rf, tid); break;
 	}
 	__syncthreads ();
 

@@ -47,6 +47,7 @@ static int lane_destroy (Lane *h);
 static int lane_restart_pss_analyzer (Lane *h);
 static int lane_get_meta (Lane *h, sdrjfm_meta *meta);
 static cudaError_t poly_set_attr (int shape);
+static RawFmt make_rawfmt (const Lane *h, int32_t fmt, float scale);
 
 
 // front-end shapes: decimation, outputs per thread, tap groups narrow / with inputFilter
@@ -134,6 +135,10 @@ struct Lane {
 	float2  *d_pss_ring = nullptr;          // [S][2048] PSS filter input ring (state)
 	int32_t *d_iter_stats = nullptr;        // pilot_kernel diagnostics: [S][4]
 	SquelchState *d_sq = nullptr;           // [S], allocated when the squelch is first switched on
+	// airspy native-rate input (kFmtAirspy): per-millisecond linear interpolation tables of the handler
+	int32_t  air_blk = 0;                   // native samples per millisecond block (native rate / 1000)
+	int16_t *d_air_int = nullptr; float *d_air_frac = nullptr;
+	short2  *d_air_pend = nullptr; int air_pend = 0;      // [S][air_blk + 1] native samples carried to the next call
 	bool    pilot_lut_smem = false;         // SDRJFM_PILOT_LUT_SMEM=1: sine table in shared memory, 1 CTA/SM
 	bool    sequential_pll = false;         // SDRJFM_SEQUENTIAL_PLL=1: lane-per-stream K3 (cross-check)
 	int64_t fm_total = 0;                   // fm-rate samples produced so far (per stream)
@@ -572,7 +577,8 @@ void *ptrs [] = { h -> d_tables, h -> d_sin_quarter, h -> d_in, h -> d_hist [0],
 	              h -> d_rds_dtaps, h -> d_rds_tws, h -> d_rds_hist [0], h -> d_rds_hist [1],
 	              h -> d_histw [0], h -> d_histw [1], h -> d_Uw, h -> d_Sw, h -> d_udel [0], h -> d_udel [1],
 	              h -> d_sdel [0], h -> d_sdel [1], h -> d_alp_hist [0], h -> d_alp_hist [1], h -> d_lrf, h -> d_lo_tab,
-	              h -> d_A, h -> d_SA, h -> d_bha [0], h -> d_bha [1], h -> d_bhs [0], h -> d_bhs [1], h -> d_sq };
+	              h -> d_A, h -> d_SA, h -> d_bha [0], h -> d_bha [1], h -> d_bhs [0], h -> d_bhs [1], h -> d_sq,
+	              h -> d_air_int, h -> d_air_frac, h -> d_air_pend };
 	for (void *p : ptrs) if (p) cudaFree (p);
 	if (h -> stream_rds) { cudaStreamSynchronize (h -> stream_rds); cudaStreamDestroy (h -> stream_rds); }
 	if (h -> ev_k3) cudaEventDestroy (h -> ev_k3);
@@ -738,7 +744,8 @@ static int lane_run_frontend_only (Lane *h, const void *d_iq, int32_t fmt, float
 	if (!h || !d_iq || n_in < h -> decim || in_pitch < n_in) return SDRJFM_ERR_ARG;
 	if (n_in > h -> cfg.max_samples_per_call) { h -> err = "n_in exceeds max_samples_per_call"; return SDRJFM_ERR_CAPACITY; }
 	CK (cudaSetDevice (h -> cfg.device));
-RawFmt rf; rf.fmt = fmt; rf.scale = scale;
+	if (fmt == kFmtAirspy) { h -> err = "front-end-only timing takes the rate-converted formats"; return SDRJFM_ERR_ARG; }
+const RawFmt rf = make_rawfmt (h, fmt, scale);
 	return launch_frontend (h, d_iq, rf, in_pitch, (int32_t)(n_in / h -> decim));
 }
 
@@ -1021,17 +1028,60 @@ const int newpend = (int)(total - *n_proc);
 	return SDRJFM_OK;
 }
 
+static RawFmt make_rawfmt (const Lane *h, int32_t fmt, float scale) {
+RawFmt rf;
+	memset (&rf, 0, sizeof rf);
+	rf.fmt = fmt; rf.scale = scale;
+	if (fmt == kFmtAirspy) { rf.blk = h -> air_blk; rf.map_int = h -> d_air_int; rf.map_frac = h -> d_air_frac; }
+	return rf;
+}
+
+// airspy: n_in NATIVE samples arrive; a block of B native samples (+ the first one of the next block)
+// gives 2304 samples at 2.304 MS/s (airspy-handler.cpp:283-309).  Stages (carried | new) native
+// samples and returns how many OUTPUT samples this call produces (a multiple of 2304, hence of 12).
+static int stage_input_airspy (Lane *h, const void *iq, int64_t n_in, int64_t in_pitch,
+                               const void **src, int64_t *pitch, int64_t *n_proc) {
+const int S = h -> cfg.n_streams;
+const int64_t B = h -> air_blk;
+	if (B <= 0) { h -> err = "set the native rate first (sdrjfm_set_native_rate)"; return SDRJFM_ERR_ARG; }
+	if (h -> pend) { h -> err = "sample format changed while samples were pending"; return SDRJFM_ERR_ARG; }
+const int64_t total = h -> air_pend + n_in;
+const int64_t blocks = total >= 1 ? (total - 1) / B : 0;
+	*n_proc = blocks * kAirspyOut;
+const size_t bps = sizeof (short2);
+const size_t rowb = (size_t)h -> cap_in * sizeof (float2);             // staging rows are cap_in * 8 bytes
+	if ((size_t)total * bps > rowb || *n_proc > h -> cfg.max_samples_per_call) {
+	   h -> err = "airspy call too large for max_samples_per_call"; return SDRJFM_ERR_CAPACITY;
+	}
+char *din = (char *)h -> d_in; char *dp = (char *)h -> d_air_pend;
+const size_t prow = (size_t)(B + 1) * bps;
+	if (h -> air_pend)
+	   CK (cudaMemcpy2DAsync (din, rowb, dp, prow, h -> air_pend * bps, S, cudaMemcpyDeviceToDevice, h -> stream));
+	if (n_in)
+	   CK (cudaMemcpy2DAsync (din + h -> air_pend * bps, rowb, iq, in_pitch * bps, n_in * bps, S,
+	                          cudaMemcpyDeviceToDevice, h -> stream));
+const int64_t keep = total - blocks * B;                               // 1 .. B once a sample has arrived
+	if (keep)
+	   CK (cudaMemcpy2DAsync (dp, prow, din + blocks * B * bps, rowb, keep * bps, S,
+	                          cudaMemcpyDeviceToDevice, h -> stream));
+	h -> air_pend = (int)keep;
+	*src = h -> d_in; *pitch = (int64_t)(rowb / bps);
+	return SDRJFM_OK;
+}
+
 static int lane_process_device (Lane *h, const void *d_iq, int32_t fmt, float scale, int64_t n_in, int64_t in_pitch,
                            float *d_audio, int64_t audio_pitch, int64_t *n_audio,
                            float *d_rds24, int64_t rds_pitch, int64_t *n_rds) {
 	if (!h || n_in < 0 || (n_in > 0 && (!d_iq || in_pitch < n_in))) return SDRJFM_ERR_ARG;
-	if (fmt < kFmtCF32 || fmt > kFmtS16) return SDRJFM_ERR_ARG;
+	if (fmt < kFmtCF32 || fmt > kFmtAirspy) return SDRJFM_ERR_ARG;
 	if (n_in > h -> cfg.max_samples_per_call) { h -> err = "n_in exceeds max_samples_per_call"; return SDRJFM_ERR_CAPACITY; }
 	CK (cudaSetDevice (h -> cfg.device));
 const void *src; int64_t pitch, n_proc;
-int rc = stage_input (h, d_iq, fmt, n_in, in_pitch, cudaMemcpyDeviceToDevice, &src, &pitch, &n_proc);
+int rc = fmt == kFmtAirspy ? stage_input_airspy (h, d_iq, n_in, in_pitch, &src, &pitch, &n_proc)
+                           : stage_input (h, d_iq, fmt, n_in, in_pitch, cudaMemcpyDeviceToDevice, &src, &pitch, &n_proc);
 	if (rc != SDRJFM_OK) return rc;
-RawFmt rf; rf.fmt = fmt; rf.scale = scale;
+	if (fmt != kFmtAirspy && h -> air_pend) { h -> err = "sample format changed while samples were pending"; return SDRJFM_ERR_ARG; }
+const RawFmt rf = make_rawfmt (h, fmt, scale);
 	return run_chain (h, src, rf, pitch, n_proc, (float2 *)d_audio, audio_pitch, n_audio,
 	                  (float2 *)d_rds24, rds_pitch, n_rds);
 }
@@ -1210,6 +1260,31 @@ static int lane_set_squelch_mode (Lane *h, int32_t m) {
 static int lane_set_squelch_value (Lane *h, int32_t n) {
 	if (!h || n < 0 || n > 100) return SDRJFM_ERR_ARG;
 	h -> set.squelch_value = n; return SDRJFM_OK;                       // set_squelchValue (:213-215)
+}
+// airspy: the handler picks the device rate closest to 2.0 MS/s and converts every millisecond of
+// it to 2304 samples by linear interpolation (airspy-handler.cpp:108-128); tables as built there
+static int lane_set_native_rate (Lane *h, int32_t hz) {
+	if (!h || hz < 1000 * kAirspyOut / 2 || hz > 20000000 || hz % 1000) return SDRJFM_ERR_ARG;
+	if (h -> cfg.input_rate != 2304000 || h -> resample) { h -> err = "the airspy conversion delivers 2 304 000 samples/s"; return SDRJFM_ERR_UNSUPPORTED; }
+	CK (cudaSetDevice (h -> cfg.device));
+	CK (cudaStreamSynchronize (h -> stream));
+const int32_t B = hz / 1000;
+	if ((int64_t)B + kAirspyOut > h -> cfg.max_samples_per_call) { h -> err = "max_samples_per_call is smaller than one airspy block"; return SDRJFM_ERR_CAPACITY; }
+std::vector<int16_t> mi (kAirspyOut); std::vector<float> mf (kAirspyOut);
+	for (int i = 0; i < kAirspyOut; i ++) {
+	   float inVal = float (hz / 1000);
+	   mi [i] = int (floor (i * (inVal / 2304.0)));
+	   mf [i] = i * (inVal / 2304.0) - mi [i];
+	}
+	for (void *p : { (void *)h -> d_air_int, (void *)h -> d_air_frac, (void *)h -> d_air_pend }) if (p) cudaFree (p);
+	h -> d_air_int = nullptr; h -> d_air_frac = nullptr; h -> d_air_pend = nullptr;
+	CK (cudaMalloc ((void **)&h -> d_air_int, kAirspyOut * sizeof (int16_t)));
+	CK (cudaMalloc ((void **)&h -> d_air_frac, kAirspyOut * sizeof (float)));
+	CK (dalloc (&h -> d_air_pend, (size_t)h -> cfg.n_streams * (B + 1)));
+	CK (cudaMemcpy (h -> d_air_int, mi.data (), kAirspyOut * sizeof (int16_t), cudaMemcpyHostToDevice));
+	CK (cudaMemcpy (h -> d_air_frac, mf.data (), kAirspyOut * sizeof (float), cudaMemcpyHostToDevice));
+	h -> air_blk = B; h -> air_pend = 0;
+	return SDRJFM_OK;
 }
 static int lane_set_auto_mono (Lane *h, int32_t on) {
 	if (!h) return SDRJFM_ERR_ARG;

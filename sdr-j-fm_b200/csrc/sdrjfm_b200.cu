@@ -160,7 +160,7 @@ static int raw_scale (sdrjfm_handle *h, int32_t format, int32_t denominator, flo
 	switch (format) {
 	   case SDRJFM_IQ_CF32: *scale = 1.0f; return SDRJFM_OK;
 	   case SDRJFM_IQ_U8: case SDRJFM_IQ_S8: *scale = 1.0f / 128.0f; return SDRJFM_OK;
-	   case SDRJFM_IQ_S16:
+	   case SDRJFM_IQ_S16: case SDRJFM_IQ_AIRSPY_S16:
 	      if (denominator <= 0 || (denominator & (denominator - 1)) != 0) {
 	         h -> err = "int16 denominator must be a power of two (2048, 4096, 8192 in the reference's handlers)";
 	         return SDRJFM_ERR_ARG;
@@ -361,6 +361,7 @@ FWD1 (set_rds_mode, int32_t)
 FWD1 (set_local_oscillator, int32_t)
 FWD1 (set_squelch_mode, int32_t)
 FWD1 (set_squelch_value, int32_t)
+FWD1 (set_native_rate, int32_t)
 FWD1 (set_auto_mono, int32_t)
 FWD1 (set_pss_mode, int32_t)
 FWD1 (set_dc_remove, int32_t)

@@ -238,3 +238,61 @@ def test_polyphase_resampler_mode_matches_float64_model(pkg, signals, chainlib, 
     k0, k1 = int(17000 * len(d) / 192000), int(21000 * len(d) / 192000)
     f = (k0 + np.argmax(spec[k0:k1])) * 192000.0 / len(d)
     assert abs(f - 19000.0) < 3.0
+
+
+# ---- airspy: native-rate int16 with the handler's per-millisecond linear interpolation ----------
+def airspy_handler_model(raw, native_rate):
+    """restatement of airspyHandler::data_available + the map tables of its constructor
+    (devices/airspy/airspy-handler.cpp:117-128, 283-309) in float32: raw int16 [n, 2] at the native
+    rate -> complex64 at 2 304 000 samples/s.  (The handler itself needs libairspy and Qt: this
+    model is the checker for the conversion; everything behind it is checked against the reference.)"""
+    B = native_rate // 1000
+    x = raw.astype(np.float32) / np.float32(2048)
+    j = np.arange(2304)
+    pos = j * (float(np.float32(B)) / 2304.0)
+    mi = np.floor(pos).astype(np.int64)
+    mf = (pos - mi).astype(np.float32)
+    blocks = (len(raw) - 1) // B
+    out = np.empty((blocks * 2304, 2), np.float32)
+    one_minus = (np.float32(1) - mf)
+    for b in range(blocks):
+        x0, x1 = x[b * B + mi], x[b * B + mi + 1]
+        out[b * 2304:(b + 1) * 2304] = x1 * mf[:, None] + x0 * one_minus[:, None]
+    return (out[:, 0] + 1j * out[:, 1]).astype(np.complex64)
+
+
+@pytest.mark.parametrize("native,chunks", [(2500000, None), (3000000, [16384, 5, 2999, 3001, 250001, 10 ** 7]),
+                                           (6000000, [65536] * 30 + [10 ** 7])])
+def test_airspy_native_rate_conversion(pkg, signals, checker, monkeypatch, native, chunks):
+    n = native // 2 + 17                                   # 0.5 s of native samples, ragged
+    x = signals.dc_offset(signals.stereo_pilot(n, fs=native, amp=0.6))
+    raw = np.clip(np.round(np.stack([x.real, x.imag], -1).astype(np.float64) * 2048), -32768, 32767).astype(np.int16)
+    xf = airspy_handler_model(raw, native)
+    assert len(xf) == ((n - 1) // (native // 1000)) * 2304
+    cfg = dict(fm_mode=0, volume_db=0.0)
+    p = pkg.FmProcessorB200(n_streams=1, input_rate=2304000, max_samples_per_call=max(chunks) if chunks else n + 8192)
+    p.configure(**cfg)
+    p.set_nativeRate(native)
+    taps = {k: [] for k in TAPS}
+    pos = 0
+    for c in (chunks or [n]):
+        if pos >= n:
+            break
+        p.process_raw(raw[pos:pos + c], "airspy", 2048)
+        for k in taps:
+            taps[k].append(p.read_tap(k, 0))
+        pos += c
+    p.close()
+    a = {k: np.concatenate(v) for k, v in taps.items()}
+    # the same floats through the same (generic) front-end kernel: bit-identical
+    monkeypatch.setenv("SDRJFM_GENERIC_FE", "1")
+    b = run_gpu(pkg, xf, 2304000, **cfg)
+    monkeypatch.delenv("SDRJFM_GENERIC_FE")
+    assert len(a["demod"]) == len(b["demod"]) == len(xf) // 12
+    assert np.array_equal(a["fm_z"].view(np.uint32), b["fm_z"].view(np.uint32))
+    # (behind the front end the one-pole scans depend on how the stream was cut into calls: rounding only)
+    assert rms(a["demod"] - b["demod"]) < 1e-6 and rms(a["audio192"] - b["audio192"]) < 1e-6
+    ref = checker(**cfg).process(xf)
+    print(native, "audio192 vs reference on the handler's floats", rms(a["audio192"] - ref["audio192"]))
+    assert rms(a["audio192"] - ref["audio192"]) < 1e-5 and rms(a["demod"] - ref["demod"]) < 1e-5
+    assert np.array_equal(a["locked"], ref["locked"])
