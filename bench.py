@@ -228,6 +228,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=3.0, help="cpu baseline: signal seconds per thread")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--rds-symbols", action="store_true",
+                    help="also run the optional GPU RDS symbol stage (Costas + rdsDecoder_1 -> bits) in every step")
     ap.add_argument("--front-end-sweep", action="store_true",
                     help="also time the front-end kernel alone for every device rate / sample format "
                          "(BASELINE config 4 and SURVEY.md §8(f) rank 1); adds `front_end_sweep` to the line")
@@ -279,6 +281,9 @@ def main():
     S = args.streams
     proc = pkg.FmProcessorB200(n_streams=S, max_samples_per_call=n, device=local, keep_taps=False)
     proc.configure(**settings)
+    if args.rds_symbols:
+        proc.setRdsSymbolStage(True)
+        config["rds_symbol_stage"] = "on (Costas loop + rdsDecoder_1, one lane per stream)"
     # shared tap/LUT blob: rank 0 designs, everyone imports what rank 0 broadcast (NCCL)
     if world > 1:
         sh = importlib.import_module("sdrjfm_b200.sharding")

@@ -176,6 +176,13 @@ int  sdrjfm_set_bandwidth (sdrjfm_handle *h, int32_t hz);          /* setBandwid
 int  sdrjfm_set_attenuation (sdrjfm_handle *h, float l, float r);  /* setAttenuation */
 int  sdrjfm_set_rds_mode (sdrjfm_handle *h, int32_t mode);         /* setfmRdsSelector: 0 off, 1..3 */
 int  sdrjfm_set_local_oscillator (sdrjfm_handle *h, int32_t hz);   /* set_localOscillator */
+/* RDS symbol stage on the GPU (optional, off by default): what rdsDecoder::doDecode does with every
+ * 24 kHz sample in mode RDS_1 before processBit — the Costas loop (includes/various/costas.h, ctor args
+ * src/rds/rds-decoder.cpp:40-41) and rdsDecoder_1::doDecode (src/rds/rds-decoder-1.cpp:126-143).  The bits
+ * of the last process call are read per stream and go to rdsDecoder::processBit on the host (block
+ * synchronisation and group decoding stay there).                                                   */
+int  sdrjfm_set_rds_symbol_stage (sdrjfm_handle *h, int32_t on);
+int64_t sdrjfm_read_rds_bits (sdrjfm_handle *h, int32_t stream, uint8_t *bits, int64_t cap);
 int  sdrjfm_set_squelch_mode (sdrjfm_handle *h, int32_t mode);     /* set_squelchMode: 0 OFF, 1 NSQ (noise), 2 LSQ (level) */
 int  sdrjfm_set_squelch_value (sdrjfm_handle *h, int32_t value);   /* set_squelchValue: 0..100 */
 int  sdrjfm_set_auto_mono (sdrjfm_handle *h, int32_t on);          /* setAutoMonoMode */

@@ -87,6 +87,16 @@ typedef struct chain_meta {   /* SMetaData, fm-processor.h:91-101, as of the las
 CHAIN_DECL(ref)
 CHAIN_DECL(orc)
 
+/* RDS symbol stage at 24 kHz, mode RDS_1 (src/rds/rds-decoder.cpp:69-82): Costas loop
+ * (includes/various/costas.h) + rdsDecoder_1::doDecode (src/rds/rds-decoder-1.cpp:126-143) —
+ * the reference's own classes (ref_ only).  Feeds n complex samples, writes the decoded bits
+ * (0/1, one byte each) and returns their number.  dump: 0 = match kernel (43 floats),
+ * 1 = rdsFilter kernel real parts (21 floats), 2 = sharpFilter: gain, 8 x (A1 A2 B1 B2) (33 floats). */
+void   *ref_rds1_create (int32_t rate);
+void    ref_rds1_destroy (void *h);
+int64_t ref_rds1_process (void *h, const float *rds24, int64_t n, uint8_t *bits, int64_t cap);
+int32_t ref_rds1_dump (void *h, int which, float *out, int32_t cap);
+
 /* `which` for *_dump_taps (complex entries unless noted) */
 enum {
     DUMP_FMBAND1 = 0,      /* 25 complex                      */

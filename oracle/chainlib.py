@@ -154,3 +154,34 @@ class Chain:
         a = np.zeros(cap, np.complex64)
         n = self._dump(self.h, DUMP[which], a.ctypes.data, cap)
         return None if n < 0 else a[:n].copy()
+
+
+class Rds1:
+    """RDS symbol stage, mode RDS_1: the reference's Costas loop + rdsDecoder_1 (ref_ only)."""
+
+    def __init__(self, rate=24000):
+        self.lib = C.CDLL(_PATHS["ref"])
+        self.lib.ref_rds1_create.restype = C.c_void_p
+        self.lib.ref_rds1_create.argtypes = [C.c_int32]
+        self.lib.ref_rds1_destroy.argtypes = [C.c_void_p]
+        self.lib.ref_rds1_process.restype = C.c_int64
+        self.lib.ref_rds1_process.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+        self.lib.ref_rds1_dump.restype = C.c_int32
+        self.lib.ref_rds1_dump.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int32]
+        self.h = self.lib.ref_rds1_create(rate)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.ref_rds1_destroy(self.h)
+            self.h = None
+
+    def process(self, rds24):
+        x = np.ascontiguousarray(rds24, dtype=np.complex64)
+        bits = np.zeros(len(x) // 8 + 16, np.uint8)
+        n = self.lib.ref_rds1_process(self.h, x.ctypes.data, len(x), bits.ctypes.data, len(bits))
+        return bits[:n].copy()
+
+    def dump(self, which):
+        a = np.zeros(64, np.float32)
+        n = self.lib.ref_rds1_dump(self.h, which, a.ctypes.data, 64)
+        return a[:n].copy()

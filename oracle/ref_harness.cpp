@@ -36,6 +36,10 @@
 #include "stereo-separation.h"
 #include "fm-demodulator.h"
 #include "squelchClass.h"
+#include "costas.h"
+#define private public       /* the dump below reads rdsDecoder_1's tables; nothing else is touched */
+#include "rds-decoder-1.h"
+#undef private
 #undef private
 #undef protected
 
@@ -401,5 +405,57 @@ int32_t n = 0;
 	if (n > cap) n = cap;
 	memcpy (out, src, (size_t)n * 2 * sizeof (float));
 	return n;
+}
+
+//	---- RDS symbol stage, mode RDS_1 (rds-decoder.cpp:36-41, 69-82) -------------------------------
+struct RefRds1 {
+	Costas		my_costas;
+	rdsDecoder_1	decoder;
+	RefRds1 (int32_t rate): my_costas (rate, 1.0f / 16.0f, 0.02f / 16.0f, 10.0f), decoder (nullptr, rate) {}
+};
+void	*ref_rds1_create (int32_t rate) { return new RefRds1 (rate); }
+void	ref_rds1_destroy (void *h) { delete (RefRds1 *)h; }
+int64_t	ref_rds1_process (void *h, const float *rds24, int64_t n, uint8_t *bits, int64_t cap) {
+RefRds1 *c = (RefRds1 *)h;
+int64_t nb = 0;
+	for (int64_t i = 0; i < n; i ++) {
+	   DSPCOMPLEX v (rds24 [2 * i], rds24 [2 * i + 1]);
+	   v = c -> my_costas. process_sample (v);
+	   uint8_t theBit;
+	   if (c -> decoder. doDecode (real (v), &theBit)) {
+	      if (nb < cap) bits [nb] = theBit;
+	      nb ++;
+	   }
+	}
+	return nb;
+}
+int32_t	ref_rds1_dump (void *h, int which, float *out, int32_t cap) {
+RefRds1 *c = (RefRds1 *)h;
+	switch (which) {
+	   case 0: {
+	      const int n = c -> decoder. rdsBufferSize;
+	      if (cap < n) return -1;
+	      for (int i = 0; i < n; i ++) out [i] = c -> decoder. rdsKernel [i];
+	      return n;
+	   }
+	   case 1: {
+	      const int n = c -> decoder. rdsFilter. filterSize;
+	      if (cap < n) return -1;
+	      for (int i = 0; i < n; i ++) out [i] = real (c -> decoder. rdsFilter. filterKernel [i]);
+	      return n;
+	   }
+	   case 2: {
+	      Basic_IIR &f = c -> decoder. sharpFilter;
+	      if (cap < 1 + 4 * f. numofQuads) return -1;
+	      int k = 0;
+	      out [k ++] = f. gain;
+	      for (int i = 0; i < f. numofQuads; i ++) {
+	         out [k ++] = f. Quads [i]. A1; out [k ++] = f. Quads [i]. A2;
+	         out [k ++] = f. Quads [i]. B1; out [k ++] = f. Quads [i]. B2;
+	      }
+	      return k;
+	   }
+	}
+	return -1;
 }
 }

@@ -112,8 +112,11 @@ def lib():
         L.sdrjfm_pilot_stats.argtypes = [vp, vp]
         for name in ("fm_mode", "fm_decoder", "sound_mode", "stereo_panorama", "sound_balance",
                      "deemphasis", "lf_cutoff", "bandwidth", "rds_mode", "local_oscillator",
-                     "squelch_mode", "squelch_value", "native_rate", "auto_mono", "pss_mode", "dc_remove"):
+                     "squelch_mode", "squelch_value", "native_rate", "rds_symbol_stage", "auto_mono", "pss_mode",
+                     "dc_remove"):
             getattr(L, f"sdrjfm_set_{name}").argtypes = [vp, i32]
+        L.sdrjfm_read_rds_bits.restype = i64
+        L.sdrjfm_read_rds_bits.argtypes = [vp, i32, vp, i64]
         L.sdrjfm_set_volume_db.argtypes = [vp, f32]
         L.sdrjfm_set_attenuation.argtypes = [vp, f32, f32]
         L.sdrjfm_trigger_frequency_change.argtypes = [vp]
@@ -141,7 +144,7 @@ _HDR_FIELDS = [("magic", "u4"), ("version", "u4"), ("input_rate", "i4"), ("fm_ra
                ("off_rds_bp", "i8"), ("off_audio_lp", "i8"), ("off_input_taps", "i8"),
                ("off_comp_wide", "i8"), ("ncomp_wide", "i4"), ("reserved1", "i4"),
                ("rs_L", "i4"), ("rs_M", "i4"), ("rs_P", "i4"), ("rs_ntapsA", "i4"),
-               ("off_rsA", "i8"), ("off_rsB", "i8"), ("off_squelch", "i8")]
+               ("off_rsA", "i8"), ("off_rsB", "i8"), ("off_squelch", "i8"), ("off_rds_sym", "i8")]
 _HDR_DTYPE = np.dtype(_HDR_FIELDS)
 
 
@@ -194,6 +197,12 @@ class Tables:
     def squelch_iir(self):
         """82 floats: high-pass gain, 10 x (A1 A2 B1 B2), low-pass gain, 10 x (A1 A2 B1 B2)."""
         return self._f(self.hdr["off_squelch"], 82)
+
+    @property
+    def rds_symbol(self):
+        """(match kernel [43], rdsFilter taps [21], sharpFilter gain + 8 x (A1 A2 B1 B2) [33])."""
+        f = self._f(self.hdr["off_rds_sym"], 97)
+        return f[:43], f[43:64], f[64:97]
 
     @property
     def input_taps(self):
@@ -265,6 +274,15 @@ class FmProcessorB200:
     def set_squelchMode(self, m): self._ck(self.L.sdrjfm_set_squelch_mode(self.h, m))
     def set_squelchValue(self, n): self._ck(self.L.sdrjfm_set_squelch_value(self.h, n))
     def set_nativeRate(self, hz): self._ck(self.L.sdrjfm_set_native_rate(self.h, hz))
+    def setRdsSymbolStage(self, on): self._ck(self.L.sdrjfm_set_rds_symbol_stage(self.h, int(on)))
+
+    def read_rds_bits(self, stream=0):
+        """bits (uint8 0/1) the GPU symbol stage decoded for `stream` in the last process call."""
+        a = np.zeros(self.cfg.max_samples_per_call // (8 * self.decim * 16) + 64, np.uint8)
+        n = self.L.sdrjfm_read_rds_bits(self.h, stream, a.ctypes.data, a.size)
+        if n < 0:
+            raise SdrjfmError(n, self.L.sdrjfm_last_error(self.h).decode())
+        return a[:n].copy()
     def setAutoMonoMode(self, on): self._ck(self.L.sdrjfm_set_auto_mono(self.h, int(on)))
     def setPSSMode(self, on): self._ck(self.L.sdrjfm_set_pss_mode(self.h, int(on)))
     def setDCRemove(self, on): self._ck(self.L.sdrjfm_set_dc_remove(self.h, int(on)))

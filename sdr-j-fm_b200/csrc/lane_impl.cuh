@@ -131,6 +131,10 @@ struct Lane {
 	float2  *d_rds_R = nullptr, *d_rds_tw = nullptr, *d_rds_tws = nullptr, *d_rds_dtaps = nullptr;
 	float2  *d_rds_hist [2] = { nullptr, nullptr }; int rds_hist_sel = 0;
 	int64_t  rds_total = 0, rds_last_block = -1;
+	// RDS symbol stage (mode RDS_1), optional: Costas loop + rdsDecoder_1 -> bits
+	bool     rds_symbols = false;
+	RdsSymState *d_rsy_state = nullptr; uint8_t *d_rsy_bits = nullptr; int32_t *d_rsy_nbits = nullptr;
+	int32_t  cap_bits = 0;
 	dcplx   *d_tileB = nullptr; DiscrSnap *d_snap = nullptr; int32_t ntiles_cap = 0;   // K2 pre-pass
 	float2  *d_pss_ring = nullptr;          // [S][2048] PSS filter input ring (state)
 	int32_t *d_iter_stats = nullptr;        // pilot_kernel diagnostics: [S][4]
@@ -578,7 +582,7 @@ void *ptrs [] = { h -> d_tables, h -> d_sin_quarter, h -> d_in, h -> d_hist [0],
 	              h -> d_histw [0], h -> d_histw [1], h -> d_Uw, h -> d_Sw, h -> d_udel [0], h -> d_udel [1],
 	              h -> d_sdel [0], h -> d_sdel [1], h -> d_alp_hist [0], h -> d_alp_hist [1], h -> d_lrf, h -> d_lo_tab,
 	              h -> d_A, h -> d_SA, h -> d_bha [0], h -> d_bha [1], h -> d_bhs [0], h -> d_bhs [1], h -> d_sq,
-	              h -> d_air_int, h -> d_air_frac, h -> d_air_pend };
+	              h -> d_air_int, h -> d_air_frac, h -> d_air_pend, h -> d_rsy_state, h -> d_rsy_bits, h -> d_rsy_nbits };
 	for (void *p : ptrs) if (p) cudaFree (p);
 	if (h -> stream_rds) { cudaStreamSynchronize (h -> stream_rds); cudaStreamDestroy (h -> stream_rds); }
 	if (h -> ev_k3) cudaEventDestroy (h -> ev_k3);
@@ -956,6 +960,19 @@ const int dec = st.decoder == 2 ? 1 : st.decoder == 1 ? 2 : 0;
 	   h -> rds_total += M;
 	   h -> last_nrds = nout;
 	   if (n_rds) *n_rds = nout;
+	   if (h -> rds_symbols && nout > 0) {
+//	      symbol stage, mode RDS_1 (rds-decoder.cpp:69-82): Costas (rate, 1/16, 0.02/16, 10 Hz) + decoder 1
+	      RdsSymParams sp2;
+	      sp2.alpha = 1.0f / 16.0f; sp2.beta = 0.02f / 16.0f;
+	      sp2.freq_limit = 2 * M_PI * 10.0f / 24000.0f;
+	      const float *tab = h -> tables.payload () + th.off_rds_sym;
+	      memcpy (sp2.match, tab, sizeof sp2.match);
+	      memcpy (sp2.lp, tab + kRsyMatch, sizeof sp2.lp);
+	      memcpy (sp2.bp, tab + kRsyMatch + kRsyLp, sizeof sp2.bp);
+	      rds_symbol_kernel<<<(S + kRsyLanes - 1) / kRsyLanes, kRsyLanes, 0, rs>>> (
+	            rout, rpitch, nout, S, sp2, h -> d_rsy_state, h -> d_rsy_bits, h -> cap_bits, h -> d_rsy_nbits);
+	      h -> launches ++;
+	   }
 	   CK (cudaEventRecord (h -> ev_rds, rs));
 	}
 //	K6 ------------------------------------------------------------------------------------
@@ -1226,6 +1243,42 @@ static int lane_set_rds_mode (Lane *h, int32_t m) {
 	   if (rc != SDRJFM_OK) return rc;
 	}
 	h -> set.rds_mode = m; return SDRJFM_OK;
+}
+// the symbol stage of rdsDecoder::doDecode for mode RDS_1 on the GPU (optional).
+// Switching it on starts the Costas loop and the decoder's filters from their constructor state.
+static int lane_set_rds_symbol_stage (Lane *h, int32_t on) {
+	if (!h) return SDRJFM_ERR_ARG;
+	CK (cudaSetDevice (h -> cfg.device));
+const size_t S = h -> cfg.n_streams;
+	if (on && !h -> d_rsy_state) {
+	   h -> cap_bits = (int32_t)(h -> cap_rds / 16 + 16);          // ~20.2 samples per bit
+	   CK (dalloc (&h -> d_rsy_state, S));
+	   CK (dalloc (&h -> d_rsy_bits, S * h -> cap_bits));
+	   CK (dalloc (&h -> d_rsy_nbits, S));
+	}
+	else if (on && !h -> rds_symbols) {
+	   CK (cudaStreamSynchronize (h -> stream));
+	   CK (cudaMemset (h -> d_rsy_state, 0, S * sizeof (RdsSymState)));
+	   CK (cudaMemset (h -> d_rsy_nbits, 0, S * sizeof (int32_t)));
+	}
+	h -> rds_symbols = on != 0;
+	return SDRJFM_OK;
+}
+// bits decoded for `stream` by the LAST process call; returns their number
+static int64_t lane_read_rds_bits (Lane *h, int32_t stream, uint8_t *out, int64_t cap) {
+	if (!h || !out || stream < 0 || stream >= h -> cfg.n_streams) return SDRJFM_ERR_ARG;
+	if (!h -> rds_symbols || !h -> d_rsy_nbits || h -> last_nrds == 0) return 0;
+	CK (cudaSetDevice (h -> cfg.device));
+int32_t n = 0;
+	CK (cudaMemcpyAsync (&n, h -> d_rsy_nbits + stream, sizeof n, cudaMemcpyDeviceToHost, h -> stream));
+	CK (cudaStreamSynchronize (h -> stream));
+	if (n > h -> cap_bits) n = h -> cap_bits;
+	if (n > cap) n = (int32_t)cap;
+	if (n > 0) {
+	   CK (cudaMemcpyAsync (out, h -> d_rsy_bits + (size_t)stream * h -> cap_bits, n, cudaMemcpyDeviceToHost, h -> stream));
+	   CK (cudaStreamSynchronize (h -> stream));
+	}
+	return n;
 }
 static int lane_set_local_oscillator (Lane *h, int32_t hz) {
 	if (!h) return SDRJFM_ERR_ARG;

@@ -21,6 +21,7 @@
 // rds_decim_kernel the 24 kHz output, restating DecimatingFIR::Pass tap by tap.
 #pragma once
 #include "common.cuh"
+#include "sequential.cuh"
 
 namespace sdrjfm {
 
@@ -274,6 +275,101 @@ float2 acc = make_float2 (0.f, 0.f);
 	   acc.x = fadd (acc.x, t.x); acc.y = fadd (acc.y, t.y);
 	}
 	out [(int64_t)stream * out_pitch + o] = acc;
+}
+
+// ---- RDS symbol stage at 24 kHz, mode RDS_1 ---------------------------
+//   Costas loop            includes/various/costas.h:21-33 (ctor args rds-decoder.cpp:40-41)
+//   rdsDecoder_1::doDecode src/rds/rds-decoder-1.cpp:126-143: LowPassFIR (21), matched filter (43 taps),
+//                          BandPassIIR (8 biquads) on the squared signal, bit at every top of that sine
+// Everything here is a per-sample float recurrence (loop filter, ring-buffer FIRs summed in the
+// reference's order, IIR): one lane per stream walks the call's 24 kHz samples.  The bits go to the
+// host, where block synchronisation and group decoding stay (rds-blocksynchronizer.cpp, rds-groupdecoder.cpp).
+constexpr int kRsyLp = 21, kRsyMatch = 43, kRsyQuads = 8, kRsyLanes = 32;
+struct RdsSymState {               // Costas + rdsDecoder_1 members
+	float   freq, phase;
+	float   lp_buf [kRsyLp], mt_buf [kRsyMatch];
+	int32_t lp_ip, mt_ip;
+	float   m1 [kRsyQuads], m2 [kRsyQuads];
+	float   last_sync_slope, last_sync, last_data;
+	int32_t prev_bit;
+};
+struct RdsSymParams {
+	float alpha, beta, freq_limit;  // 1/16, 0.02/16, 2 pi 10 / rate
+	float match [kRsyMatch], lp [kRsyLp], bp [1 + 4 * kRsyQuads];
+};
+
+__global__ void __launch_bounds__ (kRsyLanes)
+rds_symbol_kernel (const float2 *__restrict__ rds24, int64_t pitch, int32_t n, int32_t n_streams,
+                   const RdsSymParams P, RdsSymState *__restrict__ state,
+                   uint8_t *__restrict__ bits, int32_t cap_bits, int32_t *__restrict__ nbits) {
+__shared__ float sLp [kRsyLp][kRsyLanes], sMt [kRsyMatch][kRsyLanes];
+const int lane = threadIdx.x;
+const int stream = blockIdx.x * kRsyLanes + lane;
+	if (stream >= n_streams) return;
+RdsSymState st = state [stream];
+#pragma unroll
+	for (int i = 0; i < kRsyLp; i ++) sLp [i][lane] = st.lp_buf [i];
+#pragma unroll
+	for (int i = 0; i < kRsyMatch; i ++) sMt [i][lane] = st.mt_buf [i];
+int lp_ip = st.lp_ip, mt_ip = st.mt_ip;
+float m1 [kRsyQuads], m2 [kRsyQuads];
+#pragma unroll
+	for (int i = 0; i < kRsyQuads; i ++) { m1 [i] = st.m1 [i]; m2 [i] = st.m2 [i]; }
+const float2 *x = rds24 + (int64_t)stream * pitch;
+uint8_t *out = bits + (int64_t)stream * cap_bits;
+int nb = 0;
+	for (int32_t t = 0; t < n; t ++) {
+//	   Costas: r = z * exp (-i phase); the loop runs on re * im
+	   float sn, cs;
+	   sincosf (-st.phase, &sn, &cs);
+	   const float2 r = cmul_rn (x [t], make_float2 (cs, sn));
+	   const float err = fmul (r.x, r.y);
+	   st.freq = fadd (st.freq, fmul (P.beta, err));
+	   if (fabsf (st.freq) > P.freq_limit) st.freq = 0.f;
+	   st.phase = fadd (st.phase, fadd (st.freq, fmul (P.alpha, err)));
+	   st.phase = pi_constrain (st.phase);
+//	   rdsFilter.Pass (float): newest first, fir-filters.h:95-108
+	   sLp [lp_ip][lane] = r.x;
+	   float v = 0.f;
+	   { int idx = lp_ip;
+#pragma unroll
+	     for (int i = 0; i < kRsyLp; i ++) {
+	        v = fadd (v, fmul (sLp [idx][lane], P.lp [i]));
+	        idx = idx == 0 ? kRsyLp - 1 : idx - 1;
+	     } }
+	   lp_ip = lp_ip + 1 == kRsyLp ? 0 : lp_ip + 1;
+//	   Match, rds-decoder-1.cpp:108-122
+	   sMt [mt_ip][lane] = v;
+	   float w = 0.f;
+	   { int idx = mt_ip;
+#pragma unroll
+	     for (int i = 0; i < kRsyMatch; i ++) {
+	        w = fadd (w, fmul (sMt [idx][lane], P.match [i]));
+	        idx = idx == 0 ? kRsyMatch - 1 : idx - 1;
+	     } }
+	   mt_ip = mt_ip + 1 == kRsyMatch ? 0 : mt_ip + 1;
+//	   sharpFilter on the squared signal; a bit at every top of the resulting sine, :130-142
+	   const float mag = iir_pass<kRsyQuads> (P.bp, m1, m2, fmul (w, w));
+	   const float slope = fsub (mag, st.last_sync);
+	   st.last_sync = mag;
+	   if (slope < 0.f && st.last_sync_slope >= 0.f) {
+	      const int b = st.last_data >= 0.f ? 1 : 0;
+	      if (nb < cap_bits) out [nb] = (uint8_t)(b ^ st.prev_bit);
+	      nb ++;
+	      st.prev_bit = b;
+	   }
+	   st.last_data = w;
+	   st.last_sync_slope = slope;
+	}
+#pragma unroll
+	for (int i = 0; i < kRsyLp; i ++) st.lp_buf [i] = sLp [i][lane];
+#pragma unroll
+	for (int i = 0; i < kRsyMatch; i ++) st.mt_buf [i] = sMt [i][lane];
+	st.lp_ip = lp_ip; st.mt_ip = mt_ip;
+#pragma unroll
+	for (int i = 0; i < kRsyQuads; i ++) { st.m1 [i] = m1 [i]; st.m2 [i] = m2 [i]; }
+	state [stream] = st;
+	nbits [stream] = nb;
 }
 
 }	// namespace sdrjfm

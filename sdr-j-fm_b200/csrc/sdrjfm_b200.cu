@@ -362,6 +362,16 @@ FWD1 (set_local_oscillator, int32_t)
 FWD1 (set_squelch_mode, int32_t)
 FWD1 (set_squelch_value, int32_t)
 FWD1 (set_native_rate, int32_t)
+FWD1 (set_rds_symbol_stage, int32_t)
+int64_t sdrjfm_read_rds_bits (sdrjfm_handle *h, int32_t stream, uint8_t *out, int64_t cap) {
+	if (!h || !out) return SDRJFM_ERR_ARG;
+const int i = lane_of (h, stream);
+	if (i < 0) return SDRJFM_ERR_ARG;
+	HK (cudaStreamSynchronize (h -> stream));
+const int64_t n = lane_read_rds_bits (h -> lanes [i], stream - h -> first [i], out, cap);
+	if (n < 0) h -> err = h -> lanes [i] -> err;
+	return n;
+}
 FWD1 (set_auto_mono, int32_t)
 FWD1 (set_pss_mode, int32_t)
 FWD1 (set_dc_remove, int32_t)

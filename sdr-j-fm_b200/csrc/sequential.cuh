@@ -143,10 +143,11 @@ struct SquelchState {                  // squelch members (squelchClass.h:41-52)
 	int32_t count, suppress;
 };
 
+template <int NQ>
 __device__ __forceinline__ float iir_pass (const float *coef, float *m1, float *m2, float v) {
 float o = fmul (v, coef [0]);
 #pragma unroll
-	for (int i = 0; i < kSqQuads; i ++) {
+	for (int i = 0; i < NQ; i ++) {
 	   const float A1 = coef [1 + 4 * i], A2 = coef [2 + 4 * i], B1 = coef [3 + 4 * i], B2 = coef [4 + 4 * i];
 	   const float w = fsub (fsub (o, fmul (m1 [i], B1)), fmul (m2 [i], B2));
 	   o = fadd (fadd (w, fmul (m1 [i], A1)), fmul (m2 [i], A2));
@@ -162,8 +163,8 @@ __device__ __forceinline__ float decaying_average (float old, float input, float
 __device__ __forceinline__ float squelch_step (const SquelchParams &Q, SquelchState &s, float sample, float carrier) {
 const float hystN = 0.001f;             // SQUELCH_HYSTERESIS_NSQ; _LSQ = 0; LEVELREDUCTIONFACTOR = 0
 	if (Q.mode == 1) {
-	   const float v1 = fabsf (iir_pass (Q.hp, s.hp_m1, s.hp_m2, sample));
-	   const float v2 = fabsf (iir_pass (Q.lp, s.lp_m1, s.lp_m2, sample));
+	   const float v1 = fabsf (iir_pass<kSqQuads> (Q.hp, s.hp_m1, s.hp_m2, sample));
+	   const float v2 = fabsf (iir_pass<kSqQuads> (Q.lp, s.lp_m1, s.lp_m2, sample));
 	   s.avg_high = decaying_average (s.avg_high, v1, Q.weight);
 	   s.avg_low  = decaying_average (s.avg_low, v2, Q.weight);
 	   if (++ s.count >= Q.hold) {

@@ -242,6 +242,88 @@ int k = 0;
 	}
 }
 
+// ---- RDS symbol stage tables (rds-decoder-1.cpp:45-112) ------------------------------------------
+namespace {
+float butterworth_even (Quad *q, int n, int order, int apass) {          // newButterworth, iir-filters.cpp:124-171
+const float Eps = sqrt (pow (10.0, -0.1 * apass) - 1);
+const float R = 1.0 / pow (Eps, 1.0 / order);
+	for (int i = 0; i < n; i ++) {
+	   const float Phim = (M_PI * (2 * i + order + 1) / (2 * order));
+	   const float sigma = R * cosf (Phim);
+	   const float omega = R * sinf (Phim);
+	   q [i].A0 = 0; q [i].A1 = 0; q [i].A2 = (sigma * sigma + omega * omega);
+	   q [i].B0 = 1; q [i].B1 = -2 * sigma; q [i].B2 = (sigma * sigma + omega * omega);
+	}
+	return 1.0;
+}
+// roots of A s^2 + B s + C with complex<float> coefficients (cQuadratic, iir-filters.cpp:305-311)
+void quad_roots (cf32 A, cf32 B, cf32 C, cf32 &D, cf32 &E) {
+const cf32 AC = A * C;
+const cf32 t = std::sqrt (B * B - cf32 (AC.real () * 4.0, AC.imag () * 4.0));
+const cf32 A2 (A.real () * 2.0, A.imag () * 2.0);
+	D = (-B + t) / A2;
+	E = (-B - t) / A2;
+}
+}	// namespace
+
+void design_rds_symbol_tables (int32_t rate, float *out) {
+int k = 0;
+//	matched filter, rds-decoder-1.cpp:56-99
+	{
+	   const double bitclk = 1187.5;
+	   const float syncSamples = rate / (float)bitclk;
+	   const int length = ((int)ceil (syncSamples) & ~01) + 1;            // 21
+	   std::vector<float> kern (2 * length + 1, 0.f);
+	   for (int i = 1; i <= length; i ++) {
+	      const float x = ((float)i) / rate * bitclk;
+	      const float v = 0.75 * cos (4 * M_PI * x) * ((1.0 / (1.0 / x - 64.01 * x)) - ((1.0 / (9.0 / x - 64.01 * x))));
+	      const float w = - 0.75 * cos (4 * M_PI * x) * ((1.0 / (1.0 / x - 64.01 * x)) - ((1.0 / (9.0 / x - 64.01 * x))));
+	      kern [length + i] = v;
+	      kern [length - i] = w;
+	   }
+	   for (int i = 0; i < kRdsMatchTaps; i ++) out [k ++] = i < (int)kern.size () ? kern [i] : 0.f;
+	}
+//	rdsFilter = LowPassFIR (21, RDS_WIDTH = 4800, rate)
+	{
+	   std::vector<cf32> lp = design_lowpass (kRdsLpTaps, 2 * 2400, rate);
+	   for (int i = 0; i < kRdsLpTaps; i ++) out [k ++] = lp [i].real ();
+	}
+//	sharpFilter = BandPassIIR (7, bitclk - 6, bitclk + 6, rate, S_BUTTERWORTH), iir-filters.cpp:555-596, 315-382
+	{
+	   const int order = (7 + 1) & 0176;                                  // 8
+	   const int nq = order;                                              // Basic_IIR ((order + 1) & MAXORDER)
+	   int flow = (int)(1187.5 - 6), fhigh = (int)(1187.5 + 6);
+	   if (flow >= rate / 2) flow = (int)(0.2 * rate);
+	   if (fhigh >= rate / 2) fhigh = (int)(0.3 * rate);
+	   const float omegaL = warp_d_to_a (flow, rate), omegaH = warp_d_to_a (fhigh, rate);
+	   const float Wo = sqrtf (omegaL * omegaH);
+	   const float BW = omegaH - omegaL;
+	   Quad temp [kRdsBpQuads], Q [kRdsBpQuads];
+	   float gain = butterworth_even (temp, nq / 2, order, -1);
+	   for (int i = 0; i < nq / 2; i ++) {                                // unnormalizeBP
+	      cf32 A, B, C, D, E;
+	      if (temp [i].A0 == 0.0) {
+	         Q [2 * i].A0 = 0.0; Q [2 * i].A1 = sqrtf (temp [i].A2) * BW; Q [2 * i].A2 = 0.0;
+	         Q [2 * i + 1].A0 = 0.0; Q [2 * i + 1].A1 = sqrtf (temp [i].A2) * BW; Q [2 * i + 1].A2 = 0.0;
+	      }
+	      else {
+	         quad_roots (cf32 (temp [i].A0, 0.0), cf32 (temp [i].A1, 0.0), cf32 (temp [i].A2, 0.0), D, E);
+	         quad_roots (cf32 (1.0, 0.0), cf32 (-D.real () * BW, -D.imag () * BW), cf32 (Wo * Wo, 0.0), D, E);
+	         Q [2 * i].A0 = 1.0; Q [2 * i].A1 = -2.0 * D.real (); Q [2 * i].A2 = (D * std::conj (D)).real ();
+	         Q [2 * i + 1].A0 = 1.0; Q [2 * i + 1].A1 = -2.0 * E.real (); Q [2 * i + 1].A2 = (E * std::conj (E)).real ();
+	      }
+	      quad_roots (cf32 (temp [i].B0, 0.0), cf32 (temp [i].B1, 0.0), cf32 (temp [i].B2, 0.0), D, E);
+	      quad_roots (cf32 (1.0, 0.0), cf32 ((-D).real () * BW, (-D).imag () * BW), cf32 (Wo * Wo, 0), D, E);
+	      Q [2 * i].B0 = 1.0; Q [2 * i].B1 = -2.0 * D.real (); Q [2 * i].B2 = (D * std::conj (D)).real ();
+	      Q [2 * i + 1].B0 = 1.0; Q [2 * i + 1].B1 = -2.0 * E.real (); Q [2 * i + 1].B2 = (E * std::conj (E)).real ();
+	   }
+	   gain *= 1.0f;                                                       // unnormalizeBP returns 1.0
+	   gain *= bilinear (Q, rate, nq);
+	   out [k ++] = gain;
+	   for (int i = 0; i < nq; i ++) { out [k ++] = Q [i].A1; out [k ++] = Q [i].A2; out [k ++] = Q [i].B1; out [k ++] = Q [i].B2; }
+	}
+}
+
 namespace {
 struct Packer {
 	std::vector<float> f;
@@ -406,6 +488,9 @@ Packer pk;
 	   float sq [kSquelchFloats];
 	   design_squelch_iir (fm_rate, sq);
 	   h.off_squelch = pk.put (sq, kSquelchFloats);
+	   float rs [kRdsSymFloats];
+	   design_rds_symbol_tables (24000, rs);                              // RDS_RATE, fm-constants.h
+	   h.off_rds_sym = pk.put (rs, kRdsSymFloats);
 	}
 	while (pk.f.size () % 4) pk.f.push_back (0.0f);
 	h.payload_floats = (int64_t)pk.f.size ();

@@ -63,6 +63,7 @@ struct TableHeader {
 	int64_t  off_rsA;                        // rs_ntapsA real taps, unit DC gain
 	int64_t  off_rsB;                        // [rs_L][rs_P] real taps, every phase unit DC gain
 	int64_t  off_squelch;                    // kSquelchFloats floats, see design_squelch_iir
+	int64_t  off_rds_sym;                    // kRdsSymFloats floats, see design_rds_symbol_tables
 };
 
 struct TableBlob {
@@ -92,6 +93,13 @@ bool design_resampler (int32_t input_rate, int32_t fm_rate, int &L, int &M, int 
 constexpr int kSquelchQuads = 10;
 constexpr int kSquelchFloats = 2 * (1 + 4 * kSquelchQuads);
 void design_squelch_iir (int32_t fm_rate, float *out);
+
+// RDS symbol stage at 24 kHz, mode RDS_1 (src/rds/rds-decoder-1.cpp:45-112): out =
+// match kernel [43], rdsFilter real taps [21] (LowPassFIR (21, RDS_WIDTH, rate)), sharpFilter
+// = BandPassIIR (7, 1187.5 - 6, 1187.5 + 6, rate, S_BUTTERWORTH): gain, 8 x (A1 A2 B1 B2)  -> 97 floats
+constexpr int kRdsMatchTaps = 43, kRdsLpTaps = 21, kRdsBpQuads = 8;
+constexpr int kRdsSymFloats = kRdsMatchTaps + kRdsLpTaps + 1 + 4 * kRdsBpQuads;
+void design_rds_symbol_tables (int32_t rate, float *out);
 
 TableBlob build_tables (int32_t input_rate, int32_t fm_rate, int32_t input_filter_hz,
                         int32_t audio_lp_hz);

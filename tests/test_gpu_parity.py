@@ -432,3 +432,37 @@ def test_squelch_matches_reference(pkg, signals, chainlib, ref_available, monkey
         monkeypatch.delenv("SDRJFM_SEQUENTIAL_PLL")
         ref2 = chainlib.Chain("ref", **cfg).process_demod(raw, taps=("demod",))
         assert np.array_equal(got["demod"][0].view(np.uint32), ref2["demod"].view(np.uint32))
+
+
+@pytest.mark.parametrize("chunks", [None, [N1 // 3 + 12, 16384, 5, N1, N1 * 4]])
+def test_rds_symbol_stage_matches_reference(pkg, signals, chainlib, ref_available, chunks):
+    """the 24 kHz symbol stage of mode RDS_1 — Costas loop + rdsDecoder_1
+    (matched filter, 8-biquad band-pass on the squared signal, slope detector) — one lane per stream.
+    Checker: the reference's own classes fed with the GPU's 24 kHz baseband; the differentially
+    decoded bit stream must be the reference's, and it must be the transmitted one."""
+    if not ref_available:
+        pytest.skip("oracle/_ref not available")
+    n = N1 * 3
+    s = 9
+    x = signals.batch_stream(s, n)
+    p = pkg.FmProcessorB200(n_streams=1, max_samples_per_call=max(chunks) if chunks else n)
+    p.configure(fm_mode=0, rds_on=1, volume_db=-6.0)
+    p.setRdsSymbolStage(True)
+    rds, bits = [], []
+    pos = 0
+    for c in (chunks or [n]):
+        if pos >= n:
+            break
+        _, r = p.process(x[pos:pos + c])
+        rds.append(r[0]); bits.append(p.read_rds_bits(0))
+        pos += c
+    p.close()
+    rds, bits = np.concatenate(rds), np.concatenate(bits)
+    ref = chainlib.Rds1().process(rds)
+    print("bits", len(bits), "reference", len(ref), "mismatches", int(np.sum(bits[:min(len(bits), len(ref))] != ref[:min(len(bits), len(ref))])))
+    assert len(bits) == len(ref) and np.array_equal(bits, ref)
+    # and they are the transmitted bits (rng (2000 + s), differential encoding): search the alignment
+    tx = np.random.default_rng(2000 + s).integers(0, 2, size=4096).astype(np.uint8)
+    tail = bits[-600:]
+    best = max(int(np.sum(tail == np.roll(np.tile(tx, 2), -k)[:600])) for k in range(4096))
+    assert best >= 590, best
