@@ -134,6 +134,8 @@ struct Lane {
 	// RDS symbol stage (mode RDS_1), optional: Costas loop + rdsDecoder_1 -> bits
 	bool     rds_symbols = false;
 	RdsSymState *d_rsy_state = nullptr; uint8_t *d_rsy_bits = nullptr; int32_t *d_rsy_nbits = nullptr;
+	float   *d_rsy_c = nullptr, *d_rsy_v = nullptr, *d_rsy_w = nullptr;    // [S][cap_rds] Costas / low-pass / matched-filter outputs
+	float2  *d_rsy_in = nullptr;            // [S][cap_rds] private copy of the 24 kHz baseband of the call
 	int32_t  cap_bits = 0;
 	dcplx   *d_tileB = nullptr; DiscrSnap *d_snap = nullptr; int32_t ntiles_cap = 0;   // K2 pre-pass
 	float2  *d_pss_ring = nullptr;          // [S][2048] PSS filter input ring (state)
@@ -582,7 +584,8 @@ void *ptrs [] = { h -> d_tables, h -> d_sin_quarter, h -> d_in, h -> d_hist [0],
 	              h -> d_histw [0], h -> d_histw [1], h -> d_Uw, h -> d_Sw, h -> d_udel [0], h -> d_udel [1],
 	              h -> d_sdel [0], h -> d_sdel [1], h -> d_alp_hist [0], h -> d_alp_hist [1], h -> d_lrf, h -> d_lo_tab,
 	              h -> d_A, h -> d_SA, h -> d_bha [0], h -> d_bha [1], h -> d_bhs [0], h -> d_bhs [1], h -> d_sq,
-	              h -> d_air_int, h -> d_air_frac, h -> d_air_pend, h -> d_rsy_state, h -> d_rsy_bits, h -> d_rsy_nbits };
+	              h -> d_air_int, h -> d_air_frac, h -> d_air_pend, h -> d_rsy_state, h -> d_rsy_bits, h -> d_rsy_nbits,
+	              h -> d_rsy_c, h -> d_rsy_v, h -> d_rsy_w, h -> d_rsy_in };
 	for (void *p : ptrs) if (p) cudaFree (p);
 	if (h -> stream_rds) { cudaStreamSynchronize (h -> stream_rds); cudaStreamDestroy (h -> stream_rds); }
 	if (h -> ev_k3) cudaEventDestroy (h -> ev_k3);
@@ -606,6 +609,7 @@ static int lane_pilot_stats (Lane *h, int32_t *out /* [n_streams][4] */) {
 static int lane_sync (Lane *h) {
 	if (!h) return SDRJFM_ERR_ARG;
 	CK (cudaStreamSynchronize (h -> stream));
+	CK (cudaStreamSynchronize (h -> stream_rds));
 	return SDRJFM_OK;
 }
 
@@ -954,7 +958,11 @@ const int dec = st.decoder == 2 ? 1 : st.decoder == 1 ? 2 : 0;
 	   const int64_t rpitch = d_rds_out ? rds_pitch : h -> cap_rds;
 	   dim3 g ((unsigned)((std::max (nout, 1) + 127) / 128), (unsigned)S);
 	   rds_decim_kernel<<<g, 128, 0, rs>>> (h -> d_rdsc, h -> cap_fm, M, n0, h -> d_rds_dtaps,
-	         h -> d_rds_hist [h -> rds_hist_sel], h -> d_rds_hist [h -> rds_hist_sel ^ 1], rout, rpitch, nout);
+	         h -> d_rds_hist [h -> rds_hist_sel], h -> d_rds_hist [h -> rds_hist_sel ^ 1], rout, rpitch, nout,
+	         h -> rds_symbols ? h -> d_rsy_in : nullptr, h -> cap_rds);
+//	   join point of the 24 kHz baseband; the symbol stage below keeps running on the side stream,
+//	   beside the NEXT call's front end and pilot stage (its bits are waited for where they are read)
+	   CK (cudaEventRecord (h -> ev_rds, rs));
 	   h -> launches ++;
 	   h -> rds_hist_sel ^= 1;
 	   h -> rds_total += M;
@@ -969,11 +977,18 @@ const int dec = st.decoder == 2 ? 1 : st.decoder == 1 ? 2 : 0;
 	      memcpy (sp2.match, tab, sizeof sp2.match);
 	      memcpy (sp2.lp, tab + kRsyMatch, sizeof sp2.lp);
 	      memcpy (sp2.bp, tab + kRsyMatch + kRsyLp, sizeof sp2.bp);
-	      rds_symbol_kernel<<<(S + kRsyLanes - 1) / kRsyLanes, kRsyLanes, 0, rs>>> (
-	            rout, rpitch, nout, S, sp2, h -> d_rsy_state, h -> d_rsy_bits, h -> cap_bits, h -> d_rsy_nbits);
-	      h -> launches ++;
+	      const int64_t bp = h -> cap_rds;
+	      rds_costas_kernel<<<(S + kRsyLanes - 1) / kRsyLanes, kRsyLanes, 0, rs>>> (
+	            h -> d_rsy_in, bp, nout, S, sp2, h -> d_rsy_state, h -> d_rsy_c, bp);
+	      const dim3 gf ((unsigned)((nout + 127) / 128), (unsigned)S);
+	      rds_fir_kernel<kRsyLp, false><<<gf, 128, 0, rs>>> (h -> d_rsy_c, h -> d_rsy_v, bp, nout, sp2, h -> d_rsy_state);
+	      rds_fir_kernel<kRsyMatch, true><<<gf, 128, 0, rs>>> (h -> d_rsy_v, h -> d_rsy_w, bp, nout, sp2, h -> d_rsy_state);
+	      const int spb = kRsyLanes / kRsyQuads;                               // streams per block
+	      rds_bits_kernel<<<(S + spb - 1) / spb, kRsyLanes, 0, rs>>> (
+	            h -> d_rsy_w, bp, nout, S, sp2, h -> d_rsy_state, h -> d_rsy_bits, h -> cap_bits, h -> d_rsy_nbits);
+	      rds_sym_roll_kernel<<<S, 64, 0, rs>>> (h -> d_rsy_c, h -> d_rsy_v, bp, nout, h -> d_rsy_state);
+	      h -> launches += 5;
 	   }
-	   CK (cudaEventRecord (h -> ev_rds, rs));
 	}
 //	K6 ------------------------------------------------------------------------------------
 const float2 *lr_in = h -> d_lr;
@@ -1255,9 +1270,13 @@ const size_t S = h -> cfg.n_streams;
 	   CK (dalloc (&h -> d_rsy_state, S));
 	   CK (dalloc (&h -> d_rsy_bits, S * h -> cap_bits));
 	   CK (dalloc (&h -> d_rsy_nbits, S));
+	   CK (dalloc (&h -> d_rsy_c, S * h -> cap_rds)); CK (dalloc (&h -> d_rsy_v, S * h -> cap_rds));
+	   CK (dalloc (&h -> d_rsy_w, S * h -> cap_rds));
+	   CK (dalloc (&h -> d_rsy_in, S * h -> cap_rds));
 	}
 	else if (on && !h -> rds_symbols) {
 	   CK (cudaStreamSynchronize (h -> stream));
+	   CK (cudaStreamSynchronize (h -> stream_rds));
 	   CK (cudaMemset (h -> d_rsy_state, 0, S * sizeof (RdsSymState)));
 	   CK (cudaMemset (h -> d_rsy_nbits, 0, S * sizeof (int32_t)));
 	}
@@ -1270,6 +1289,7 @@ static int64_t lane_read_rds_bits (Lane *h, int32_t stream, uint8_t *out, int64_
 	if (!h -> rds_symbols || !h -> d_rsy_nbits || h -> last_nrds == 0) return 0;
 	CK (cudaSetDevice (h -> cfg.device));
 int32_t n = 0;
+	CK (cudaStreamSynchronize (h -> stream_rds));                        // the symbol stage runs past the call's join
 	CK (cudaMemcpyAsync (&n, h -> d_rsy_nbits + stream, sizeof n, cudaMemcpyDeviceToHost, h -> stream));
 	CK (cudaStreamSynchronize (h -> stream));
 	if (n > h -> cap_bits) n = h -> cap_bits;

@@ -252,7 +252,8 @@ const float2 osc = make_float2 (cosf (th), -sinf (th));
 __global__ void rds_decim_kernel (const float2 *__restrict__ rdsc, int64_t pitch, int32_t M,
                                   int64_t c0, const float2 *__restrict__ taps,
                                   const float2 *__restrict__ hist, float2 *__restrict__ new_hist,
-                                  float2 *__restrict__ out, int64_t out_pitch, int32_t nout) {
+                                  float2 *__restrict__ out, int64_t out_pitch, int32_t nout,
+                                  float2 *__restrict__ out2, int64_t out2_pitch) {     // out2: private copy for the symbol stage
 const int stream = blockIdx.y;
 const int o = blockIdx.x * blockDim.x + threadIdx.x;
 const float2 *x = rdsc + (int64_t)stream * pitch;
@@ -275,20 +276,26 @@ float2 acc = make_float2 (0.f, 0.f);
 	   acc.x = fadd (acc.x, t.x); acc.y = fadd (acc.y, t.y);
 	}
 	out [(int64_t)stream * out_pitch + o] = acc;
+	if (out2) out2 [(int64_t)stream * out2_pitch + o] = acc;
 }
 
 // ---- RDS symbol stage at 24 kHz, mode RDS_1 ---------------------------
 //   Costas loop            includes/various/costas.h:21-33 (ctor args rds-decoder.cpp:40-41)
 //   rdsDecoder_1::doDecode src/rds/rds-decoder-1.cpp:126-143: LowPassFIR (21), matched filter (43 taps),
 //                          BandPassIIR (8 biquads) on the squared signal, bit at every top of that sine
-// Everything here is a per-sample float recurrence (loop filter, ring-buffer FIRs summed in the
-// reference's order, IIR): one lane per stream walks the call's 24 kHz samples.  The bits go to the
-// host, where block synchronisation and group decoding stay (rds-blocksynchronizer.cpp, rds-groupdecoder.cpp).
+// Only the Costas loop (a non-linear feedback loop) and the IIR are recurrences:
+//   rds_costas_kernel   one lane per stream walks the call's samples (the loop filter)
+//   rds_fir_kernel      the two ring-buffer FIRs, one thread per output, summed in the reference's order
+//   rds_bits_kernel     the 8 biquads as a systolic pipeline over 8 lanes (lane q runs biquad q on the
+//                       sample lane q-1 finished one step earlier: every sample still sees the
+//                       reference's operations in the reference's order), slope detector on the last lane
+// The bits go to the host, where block synchronisation and group decoding stay
+// (rds-blocksynchronizer.cpp, rds-groupdecoder.cpp).
 constexpr int kRsyLp = 21, kRsyMatch = 43, kRsyQuads = 8, kRsyLanes = 32;
 struct RdsSymState {               // Costas + rdsDecoder_1 members
 	float   freq, phase;
-	float   lp_buf [kRsyLp], mt_buf [kRsyMatch];
-	int32_t lp_ip, mt_ip;
+	float   hist_c [kRsyLp - 1];    // the last 20 Costas outputs (oldest first) = rdsFilter's buffer
+	float   hist_v [kRsyMatch - 1]; // the last 42 low-pass outputs = rdsBuffer
 	float   m1 [kRsyQuads], m2 [kRsyQuads];
 	float   last_sync_slope, last_sync, last_data;
 	int32_t prev_bit;
@@ -299,77 +306,137 @@ struct RdsSymParams {
 };
 
 __global__ void __launch_bounds__ (kRsyLanes)
-rds_symbol_kernel (const float2 *__restrict__ rds24, int64_t pitch, int32_t n, int32_t n_streams,
-                   const RdsSymParams P, RdsSymState *__restrict__ state,
-                   uint8_t *__restrict__ bits, int32_t cap_bits, int32_t *__restrict__ nbits) {
-__shared__ float sLp [kRsyLp][kRsyLanes], sMt [kRsyMatch][kRsyLanes];
-const int lane = threadIdx.x;
-const int stream = blockIdx.x * kRsyLanes + lane;
+rds_costas_kernel (const float2 *__restrict__ rds24, int64_t pitch, int32_t n, int32_t n_streams,
+                   const RdsSymParams P, RdsSymState *__restrict__ state, float *__restrict__ cbuf, int64_t cpitch) {
+const int stream = blockIdx.x * kRsyLanes + threadIdx.x;
 	if (stream >= n_streams) return;
-RdsSymState st = state [stream];
-#pragma unroll
-	for (int i = 0; i < kRsyLp; i ++) sLp [i][lane] = st.lp_buf [i];
-#pragma unroll
-	for (int i = 0; i < kRsyMatch; i ++) sMt [i][lane] = st.mt_buf [i];
-int lp_ip = st.lp_ip, mt_ip = st.mt_ip;
-float m1 [kRsyQuads], m2 [kRsyQuads];
-#pragma unroll
-	for (int i = 0; i < kRsyQuads; i ++) { m1 [i] = st.m1 [i]; m2 [i] = st.m2 [i]; }
+float freq = state [stream].freq, phase = state [stream].phase;
 const float2 *x = rds24 + (int64_t)stream * pitch;
-uint8_t *out = bits + (int64_t)stream * cap_bits;
-int nb = 0;
-	for (int32_t t = 0; t < n; t ++) {
-//	   Costas: r = z * exp (-i phase); the loop runs on re * im
-	   float sn, cs;
-	   sincosf (-st.phase, &sn, &cs);
-	   const float2 r = cmul_rn (x [t], make_float2 (cs, sn));
-	   const float err = fmul (r.x, r.y);
-	   st.freq = fadd (st.freq, fmul (P.beta, err));
-	   if (fabsf (st.freq) > P.freq_limit) st.freq = 0.f;
-	   st.phase = fadd (st.phase, fadd (st.freq, fmul (P.alpha, err)));
-	   st.phase = pi_constrain (st.phase);
-//	   rdsFilter.Pass (float): newest first, fir-filters.h:95-108
-	   sLp [lp_ip][lane] = r.x;
-	   float v = 0.f;
-	   { int idx = lp_ip;
+float *c = cbuf + (int64_t)stream * cpitch;
+//	the samples are fetched one chunk ahead, so the loop never waits on global memory
+constexpr int CH = 8;
+float2 cur [CH], nxt [CH];
 #pragma unroll
-	     for (int i = 0; i < kRsyLp; i ++) {
-	        v = fadd (v, fmul (sLp [idx][lane], P.lp [i]));
-	        idx = idx == 0 ? kRsyLp - 1 : idx - 1;
-	     } }
-	   lp_ip = lp_ip + 1 == kRsyLp ? 0 : lp_ip + 1;
-//	   Match, rds-decoder-1.cpp:108-122
-	   sMt [mt_ip][lane] = v;
-	   float w = 0.f;
-	   { int idx = mt_ip;
+	for (int k = 0; k < CH; k ++) cur [k] = k < n ? x [k] : make_float2 (0.f, 0.f);
+	for (int32_t t0 = 0; t0 < n; t0 += CH) {
 #pragma unroll
-	     for (int i = 0; i < kRsyMatch; i ++) {
-	        w = fadd (w, fmul (sMt [idx][lane], P.match [i]));
-	        idx = idx == 0 ? kRsyMatch - 1 : idx - 1;
-	     } }
-	   mt_ip = mt_ip + 1 == kRsyMatch ? 0 : mt_ip + 1;
-//	   sharpFilter on the squared signal; a bit at every top of the resulting sine, :130-142
-	   const float mag = iir_pass<kRsyQuads> (P.bp, m1, m2, fmul (w, w));
-	   const float slope = fsub (mag, st.last_sync);
-	   st.last_sync = mag;
-	   if (slope < 0.f && st.last_sync_slope >= 0.f) {
-	      const int b = st.last_data >= 0.f ? 1 : 0;
-	      if (nb < cap_bits) out [nb] = (uint8_t)(b ^ st.prev_bit);
-	      nb ++;
-	      st.prev_bit = b;
+	   for (int k = 0; k < CH; k ++) nxt [k] = t0 + CH + k < n ? x [t0 + CH + k] : make_float2 (0.f, 0.f);
+#pragma unroll
+	   for (int k = 0; k < CH; k ++) {
+	      if (t0 + k < n) {
+//	         r = z * exp (-i phase); the loop runs on re * im  (costas.h:21-33)
+	         float sn, cs;
+	         sincosf (-phase, &sn, &cs);
+	         const float2 r = cmul_rn (cur [k], make_float2 (cs, sn));
+	         const float err = fmul (r.x, r.y);
+	         freq = fadd (freq, fmul (P.beta, err));
+	         if (fabsf (freq) > P.freq_limit) freq = 0.f;
+	         phase = pi_constrain (fadd (phase, fadd (freq, fmul (P.alpha, err))));
+	         c [t0 + k] = r.x;
+	      }
 	   }
-	   st.last_data = w;
-	   st.last_sync_slope = slope;
+#pragma unroll
+	   for (int k = 0; k < CH; k ++) cur [k] = nxt [k];
 	}
+	state [stream].freq = freq; state [stream].phase = phase;
+}
+
+// out[t] = sum_{i<NT} in[t - i] * taps[i], i ascending (Basic_FIR::Pass (float), fir-filters.h:95-108 and
+// rdsDecoder_1::Match, rds-decoder-1.cpp:108-122); in[t] for t < 0 comes from the carried history
+template <int NT, bool MATCH>
+__global__ void rds_fir_kernel (const float *__restrict__ in, float *__restrict__ out, int64_t pitch, int32_t n,
+                                const RdsSymParams P, const RdsSymState *__restrict__ state) {
+const int stream = blockIdx.y;
+const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n) return;
+const float *x = in + (int64_t)stream * pitch;
+const float *hist = MATCH ? state [stream].hist_v : state [stream].hist_c;     // NT - 1 entries, oldest first
+float acc = 0.f;
 #pragma unroll
-	for (int i = 0; i < kRsyLp; i ++) st.lp_buf [i] = sLp [i][lane];
+	for (int i = 0; i < NT; i ++) {
+	   const int k = t - i;
+	   const float v = k >= 0 ? x [k] : hist [NT - 1 + k];
+	   acc = fadd (acc, fmul (v, MATCH ? P.match [i] : P.lp [i]));
+	}
+	out [(int64_t)stream * pitch + t] = acc;
+}
+
+// 8 lanes per stream; w = matched-filter output of this call
+__global__ void __launch_bounds__ (kRsyLanes)
+rds_bits_kernel (const float *__restrict__ wbuf, int64_t pitch, int32_t n, int32_t n_streams,
+                 const RdsSymParams P, RdsSymState *__restrict__ state,
+                 uint8_t *__restrict__ bits, int32_t cap_bits, int32_t *__restrict__ nbits) {
+const int q = threadIdx.x & (kRsyQuads - 1);
+const int stream = blockIdx.x * (kRsyLanes / kRsyQuads) + (threadIdx.x >> 3);
+const bool live = stream < n_streams;
+const int sidx = live ? stream : 0;
+RdsSymState &st = state [sidx];
+const float A1 = P.bp [1 + 4 * q], A2 = P.bp [2 + 4 * q], B1 = P.bp [3 + 4 * q], B2 = P.bp [4 + 4 * q];
+float m1 = st.m1 [q], m2 = st.m2 [q];
+float lastSlope = st.last_sync_slope, lastSync = st.last_sync, lastData = st.last_data;
+int prev = st.prev_bit, nb = 0;
+const float *w = wbuf + (int64_t)sidx * pitch;
+uint8_t *out = bits + (int64_t)sidx * cap_bits;
+float o = 0.f;
+//	every lane fetches the matched-filter output of ITS sample (t = s - q) one chunk ahead
+constexpr int CH = 8;
+const int32_t steps = n + kRsyQuads - 1;
+float cur [CH], nxt [CH];
 #pragma unroll
-	for (int i = 0; i < kRsyMatch; i ++) st.mt_buf [i] = sMt [i][lane];
-	st.lp_ip = lp_ip; st.mt_ip = mt_ip;
+	for (int k = 0; k < CH; k ++) { const int32_t t = k - q; cur [k] = (t >= 0 && t < n) ? w [t] : 0.f; }
+	for (int32_t s0 = 0; s0 < steps; s0 += CH) {
 #pragma unroll
-	for (int i = 0; i < kRsyQuads; i ++) { st.m1 [i] = m1 [i]; st.m2 [i] = m2 [i]; }
-	state [stream] = st;
-	nbits [stream] = nb;
+	   for (int k = 0; k < CH; k ++) { const int32_t t = s0 + CH + k - q; nxt [k] = (t >= 0 && t < n) ? w [t] : 0.f; }
+#pragma unroll
+	   for (int k = 0; k < CH; k ++) {
+	      const int32_t s = s0 + k;
+	      const float fromPrev = __shfl_up_sync (0xffffffffu, o, 1, kRsyQuads);    // what lane q-1 produced last step
+	      const int32_t t = s - q;                                                 // the sample this lane works on now
+	      const bool act = t >= 0 && t < n;
+	      const float wt = cur [k];
+	      const float in = q == 0 ? fmul (fmul (wt, wt), P.bp [0]) : fromPrev;     // o = v * gain, iir-filters.h:93
+	      if (act) {
+	         const float ww = fsub (fsub (in, fmul (m1, B1)), fmul (m2, B2));
+	         o = fadd (fadd (ww, fmul (m1, A1)), fmul (m2, A2));
+	         m2 = m1; m1 = ww;
+	      }
+	      if (q == kRsyQuads - 1 && act && live) {
+//	         rdsMag = o: a bit at every top of the sine, rds-decoder-1.cpp:130-142
+	         const float slope = fsub (o, lastSync);
+	         lastSync = o;
+	         if (slope < 0.f && lastSlope >= 0.f) {
+	            const int b = lastData >= 0.f ? 1 : 0;
+	            if (nb < cap_bits) out [nb] = (uint8_t)(b ^ prev);
+	            nb ++;
+	            prev = b;
+	         }
+	         lastData = wt;
+	         lastSlope = slope;
+	      }
+	   }
+#pragma unroll
+	   for (int k = 0; k < CH; k ++) cur [k] = nxt [k];
+	}
+	if (live) {
+	   st.m1 [q] = m1; st.m2 [q] = m2;
+	   if (q == kRsyQuads - 1) {
+	      st.last_sync_slope = lastSlope; st.last_sync = lastSync; st.last_data = lastData; st.prev_bit = prev;
+	      nbits [stream] = nb;
+	   }
+	}
+}
+
+// carry the FIR histories to the next call: the last 20 Costas outputs and the last 42 low-pass outputs
+__global__ void rds_sym_roll_kernel (const float *__restrict__ cbuf, const float *__restrict__ vbuf, int64_t pitch,
+                                     int32_t n, RdsSymState *__restrict__ state) {
+const int stream = blockIdx.x, i = threadIdx.x;
+RdsSymState &st = state [stream];
+float a = 0.f, b = 0.f;
+	if (i < kRsyLp - 1) { const int k = n - (kRsyLp - 1) + i; a = k >= 0 ? cbuf [(int64_t)stream * pitch + k] : st.hist_c [kRsyLp - 1 + k]; }
+	if (i < kRsyMatch - 1) { const int k = n - (kRsyMatch - 1) + i; b = k >= 0 ? vbuf [(int64_t)stream * pitch + k] : st.hist_v [kRsyMatch - 1 + k]; }
+	__syncthreads ();
+	if (i < kRsyLp - 1) st.hist_c [i] = a;
+	if (i < kRsyMatch - 1) st.hist_v [i] = b;
 }
 
 }	// namespace sdrjfm

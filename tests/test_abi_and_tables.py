@@ -102,3 +102,14 @@ def test_squelch_filter_design_matches_reference(pkg, chainlib, ref_available):
     ref = chainlib.Chain("ref").dump("squelch_iir").view(np.float32)[:82]
     mine = pkg.design_tables().squelch_iir
     assert _same(np.ascontiguousarray(ref), np.ascontiguousarray(mine))
+
+
+def test_rds_symbol_stage_tables_match_reference(pkg, chainlib, ref_available):
+    """matched filter, low-pass and the 8-biquad band-pass of rdsDecoder_1 (rds-decoder-1.cpp:45-112,
+    iir-filters.cpp:315-382,555-596): host-side restatement, bit-identical to the reference's objects."""
+    if not ref_available:
+        pytest.skip("oracle/_ref not available")
+    r = chainlib.Rds1()
+    match, lp, bp = pkg.design_tables().rds_symbol
+    for mine, which in ((match, 0), (lp, 1), (bp, 2)):
+        assert _same(r.dump(which), np.ascontiguousarray(mine))
