@@ -181,6 +181,12 @@ int  sdrjfm_set_local_oscillator (sdrjfm_handle *h, int32_t hz);   /* set_localO
  * src/rds/rds-decoder.cpp:40-41) and rdsDecoder_1::doDecode (src/rds/rds-decoder-1.cpp:126-143).  The bits
  * of the last process call are read per stream and go to rdsDecoder::processBit on the host (block
  * synchronisation and group decoding stay there).                                                   */
+/* startScanning / stopScanning (src/fm/fm-processor.cpp:361-367, 478-495): while scanning, process
+ * calls produce no audio and no RDS; per completed block of 1024 fm-rate samples the level around the
+ * carrier and at the band edge are returned as (get_db (signal, 256), get_db (noise, 256)) pairs
+ * (:886-904); the reference's test is  signal - noise > thresHold  (a constructor argument).        */
+int  sdrjfm_set_scanning (sdrjfm_handle *h, int32_t on);
+int64_t sdrjfm_read_scan (sdrjfm_handle *h, int32_t stream, float *db_pairs, int64_t cap_pairs);
 int  sdrjfm_set_rds_symbol_stage (sdrjfm_handle *h, int32_t on);
 int64_t sdrjfm_read_rds_bits (sdrjfm_handle *h, int32_t stream, uint8_t *bits, int64_t cap);
 int  sdrjfm_set_squelch_mode (sdrjfm_handle *h, int32_t mode);     /* set_squelchMode: 0 OFF, 1 NSQ (noise), 2 LSQ (level) */

@@ -92,6 +92,10 @@ CHAIN_DECL(orc)
  * the reference's own classes (ref_ only).  Feeds n complex samples, writes the decoded bits
  * (0/1, one byte each) and returns their number.  dump: 0 = match kernel (43 floats),
  * 1 = rdsFilter kernel real parts (21 floats), 2 = sharpFilter: gain, 8 x (A1 A2 B1 B2) (33 floats). */
+/* station scan (src/fm/fm-processor.cpp:478-495, 886-904): per block of 1024 fm-rate complex samples,
+ * the reference's own Fft_transform followed by a restatement of getSignal / getNoise / get_db
+ * (private members of the Qt class fmProcessor).  out: nblocks pairs (signal dB, noise dB).          */
+int64_t ref_scan_blocks (const float *fm_z, int64_t n, float *out);
 void   *ref_rds1_create (int32_t rate);
 void    ref_rds1_destroy (void *h);
 int64_t ref_rds1_process (void *h, const float *rds24, int64_t n, uint8_t *bits, int64_t cap);

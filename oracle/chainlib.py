@@ -185,3 +185,14 @@ class Rds1:
         a = np.zeros(64, np.float32)
         n = self.lib.ref_rds1_dump(self.h, which, a.ctypes.data, 64)
         return a[:n].copy()
+
+
+def ref_scan_blocks(fm_z):
+    """(signal dB, noise dB) per 1024-sample block, computed with the reference's FFT (ref_ only)."""
+    lib = C.CDLL(_PATHS["ref"])
+    lib.ref_scan_blocks.restype = C.c_int64
+    lib.ref_scan_blocks.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+    z = np.ascontiguousarray(fm_z, dtype=np.complex64)
+    out = np.zeros((len(z) // 1024 + 1, 2), np.float32)
+    n = lib.ref_scan_blocks(z.ctypes.data, len(z), out.ctypes.data)
+    return out[:n].copy()

@@ -36,6 +36,7 @@
 #include "stereo-separation.h"
 #include "fm-demodulator.h"
 #include "squelchClass.h"
+#include "fft-complex.h"
 #include "costas.h"
 #define private public       /* the dump below reads rdsDecoder_1's tables; nothing else is touched */
 #include "rds-decoder-1.h"
@@ -457,5 +458,27 @@ RefRds1 *c = (RefRds1 *)h;
 	   }
 	}
 	return -1;
+}
+
+//	---- station scan, fm-processor.cpp:478-495 with getSignal / getNoise (:886-904) restated ----------
+int64_t	ref_scan_blocks (const float *fm_z, int64_t n, float *out) {
+std::complex<float> scanBuffer [1024];
+int64_t nb = 0;
+	for (int64_t b = 0; (b + 1) * 1024 <= n; b ++) {
+	   for (int i = 0; i < 1024; i ++)
+	      scanBuffer [i] = std::complex<float> (fm_z [2 * (b * 1024 + i)], fm_z [2 * (b * 1024 + i) + 1]);
+	   Fft_transform (scanBuffer, 1024, false);
+	   float signal = 0, Noise = 0;
+	   for (int i = 5; i < 25; i ++) signal += abs (scanBuffer [i]);
+	   for (int i = 5; i < 25; i ++) signal += abs (scanBuffer [1024 - 1 - i]);
+	   signal = signal / 40;
+	   for (int i = 5; i < 25; i ++) Noise += abs (scanBuffer [1024 / 2 - 1 - i]);
+	   for (int i = 5; i < 25; i ++) Noise += abs (scanBuffer [1024 / 2 + 1 + i]);
+	   Noise = Noise / 40;
+	   out [2 * nb] = get_db (signal, 256);
+	   out [2 * nb + 1] = get_db (Noise, 256);
+	   nb ++;
+	}
+	return nb;
 }
 }

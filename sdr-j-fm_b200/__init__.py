@@ -112,9 +112,11 @@ def lib():
         L.sdrjfm_pilot_stats.argtypes = [vp, vp]
         for name in ("fm_mode", "fm_decoder", "sound_mode", "stereo_panorama", "sound_balance",
                      "deemphasis", "lf_cutoff", "bandwidth", "rds_mode", "local_oscillator",
-                     "squelch_mode", "squelch_value", "native_rate", "rds_symbol_stage", "auto_mono", "pss_mode",
+                     "squelch_mode", "squelch_value", "native_rate", "rds_symbol_stage", "scanning", "auto_mono", "pss_mode",
                      "dc_remove"):
             getattr(L, f"sdrjfm_set_{name}").argtypes = [vp, i32]
+        L.sdrjfm_read_scan.restype = i64
+        L.sdrjfm_read_scan.argtypes = [vp, i32, vp, i64]
         L.sdrjfm_read_rds_bits.restype = i64
         L.sdrjfm_read_rds_bits.argtypes = [vp, i32, vp, i64]
         L.sdrjfm_set_volume_db.argtypes = [vp, f32]
@@ -274,6 +276,17 @@ class FmProcessorB200:
     def set_squelchMode(self, m): self._ck(self.L.sdrjfm_set_squelch_mode(self.h, m))
     def set_squelchValue(self, n): self._ck(self.L.sdrjfm_set_squelch_value(self.h, n))
     def set_nativeRate(self, hz): self._ck(self.L.sdrjfm_set_native_rate(self.h, hz))
+    def startScanning(self): self._ck(self.L.sdrjfm_set_scanning(self.h, 1))
+    def stopScanning(self): self._ck(self.L.sdrjfm_set_scanning(self.h, 0))
+
+    def read_scan(self, stream=0):
+        """[(signal dB, noise dB)] per 1024-sample block completed by the last process call while scanning."""
+        a = np.zeros((self.cfg.max_samples_per_call // (self.decim * 1024) + 4, 2), np.float32)
+        n = self.L.sdrjfm_read_scan(self.h, stream, a.ctypes.data, a.shape[0])
+        if n < 0:
+            raise SdrjfmError(n, self.L.sdrjfm_last_error(self.h).decode())
+        return a[:n].copy()
+
     def setRdsSymbolStage(self, on): self._ck(self.L.sdrjfm_set_rds_symbol_stage(self.h, int(on)))
 
     def read_rds_bits(self, stream=0):

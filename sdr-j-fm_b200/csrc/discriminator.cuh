@@ -25,6 +25,7 @@ struct DiscrParams {
 	double alpha, beta;         // alpha = (float)1/inputRate; beta = (1 - alpha)^decim
 	float  lgain, rgain;
 	int32_t dc_remove, decoder;
+	int32_t scan_only;          // station scan: the demodulator is not called, its state must not move
 	// local oscillator on: gains and rotation were applied per input sample by K1; the DC value
 	// the reference subtracted BEFORE the rotation comes back out as clamp (r) * gains *
 	// Table[LOPhase at decim (m + lo_moff) + decim - 1] * H,  H = sum_t C[t] exp (+2 pi i lo t / inputRate)
@@ -337,7 +338,7 @@ double pw [6];
 	      }
 	      p2 = p1;
 	      p1 = make_float2 (I, Q);
-	      if (j0 + j == M - 1) {
+	      if (j0 + j == M - 1 && !P.scan_only) {
 	         st.Imin1 = p1.x; st.Qmin1 = p1.y; st.Imin2 = p2.x; st.Qmin2 = p2.y;
 	      }
 	      if (j0 + j < M) {

@@ -33,6 +33,7 @@
 #include "pilot.cuh"
 #include "stereo.cuh"
 #include "rds.cuh"
+#include "scan.cuh"
 #include "audio_out.cuh"
 
 // One LANE = the complete launch sequence and state for a group of IQ streams on its own CUDA
@@ -141,6 +142,10 @@ struct Lane {
 	float2  *d_pss_ring = nullptr;          // [S][2048] PSS filter input ring (state)
 	int32_t *d_iter_stats = nullptr;        // pilot_kernel diagnostics: [S][4]
 	SquelchState *d_sq = nullptr;           // [S], allocated when the squelch is first switched on
+	// station scan (startScanning / stopScanning): 1024-sample blocks of fm-rate samples -> (signal, noise) dB
+	bool     scanning = false;
+	float2  *d_scan_carry [2] = { nullptr, nullptr }; int scan_sel = 0, scan_carry = 0;
+	float2  *d_scan_db = nullptr; int32_t cap_scan = 0, last_nscan = 0;
 	// airspy native-rate input (kFmtAirspy): per-millisecond linear interpolation tables of the handler
 	int32_t  air_blk = 0;                   // native samples per millisecond block (native rate / 1000)
 	int16_t *d_air_int = nullptr; float *d_air_frac = nullptr;
@@ -585,7 +590,8 @@ void *ptrs [] = { h -> d_tables, h -> d_sin_quarter, h -> d_in, h -> d_hist [0],
 	              h -> d_sdel [0], h -> d_sdel [1], h -> d_alp_hist [0], h -> d_alp_hist [1], h -> d_lrf, h -> d_lo_tab,
 	              h -> d_A, h -> d_SA, h -> d_bha [0], h -> d_bha [1], h -> d_bhs [0], h -> d_bhs [1], h -> d_sq,
 	              h -> d_air_int, h -> d_air_frac, h -> d_air_pend, h -> d_rsy_state, h -> d_rsy_bits, h -> d_rsy_nbits,
-	              h -> d_rsy_c, h -> d_rsy_v, h -> d_rsy_w, h -> d_rsy_in };
+	              h -> d_rsy_c, h -> d_rsy_v, h -> d_rsy_w, h -> d_rsy_in,
+	              h -> d_scan_carry [0], h -> d_scan_carry [1], h -> d_scan_db };
 	for (void *p : ptrs) if (p) cudaFree (p);
 	if (h -> stream_rds) { cudaStreamSynchronize (h -> stream_rds); cudaStreamDestroy (h -> stream_rds); }
 	if (h -> ev_k3) cudaEventDestroy (h -> ev_k3);
@@ -844,6 +850,7 @@ DiscrParams dp;
 	}
 	dp.lgain = st.lgain; dp.rgain = st.rgain;
 	dp.dc_remove = st.dc_remove; dp.decoder = st.decoder;
+	dp.scan_only = h -> scanning;
 const int32_t ntiles = (M + kDiBlock - 1) / kDiBlock;
 	{
 	   dim3 g ((unsigned)ntiles, (unsigned)S);
@@ -853,8 +860,23 @@ const int32_t ntiles = (M + kDiBlock - 1) / kDiBlock;
 	   discriminator_kernel<<<gd, kDiThreads, 0, h -> stream>>> (
 	         h -> d_U, h -> d_S, h -> cap_fm, M, dp, T + th.off_atan, T + th.off_arcsine,
 	         h -> d_state, h -> d_tileB, ntiles, h -> d_snap, h -> d_res, h -> d_zabs,
-	         (st.decoder == 2 || st.decoder == 1) ? h -> d_iqn : nullptr, h -> cfg.keep_taps ? h -> d_fmz : nullptr);
+	         (st.decoder == 2 || st.decoder == 1) ? h -> d_iqn : nullptr,
+	         (h -> cfg.keep_taps || h -> scanning) ? h -> d_fmz : nullptr);
 	   h -> launches += 2;
+	}
+	if (h -> scanning) {
+//	   fm-processor.cpp:478-495: while scanning nothing behind the decimators runs ("continue")
+	   const int32_t nblk = (h -> scan_carry + M) / kScanN;
+	   h -> last_nscan = std::min (nblk, h -> cap_scan);
+	   if (h -> last_nscan > 0)
+	      scan_kernel<<<dim3 ((unsigned)h -> last_nscan, (unsigned)S), kScanThreads, 0, h -> stream>>> (
+	            h -> d_fmz, h -> cap_fm, h -> d_scan_carry [h -> scan_sel], h -> scan_carry, h -> d_scan_db, h -> cap_scan);
+	   scan_carry_kernel<<<S, 256, 0, h -> stream>>> (h -> d_fmz, h -> cap_fm, M, h -> d_scan_carry [h -> scan_sel],
+	                                                  h -> scan_carry, h -> d_scan_carry [h -> scan_sel ^ 1]);
+	   h -> scan_sel ^= 1; h -> scan_carry = (h -> scan_carry + M) % kScanN;
+	   h -> launches += 2;
+	   CK (cudaGetLastError ());
+	   return SDRJFM_OK;
 	}
 //	K3 ------------------------------------------------------------------------------------
 SeqParams sp;
@@ -1298,6 +1320,32 @@ int32_t n = 0;
 	   CK (cudaMemcpyAsync (out, h -> d_rsy_bits + (size_t)stream * h -> cap_bits, n, cudaMemcpyDeviceToHost, h -> stream));
 	   CK (cudaStreamSynchronize (h -> stream));
 	}
+	return n;
+}
+// startScanning / stopScanning (fm-processor.cpp:361-367).  scanPointer is a local of run (): it
+// restarts at 0 whenever the run loop does; here it restarts with every startScanning.
+static int lane_set_scanning (Lane *h, int32_t on) {
+	if (!h) return SDRJFM_ERR_ARG;
+	CK (cudaSetDevice (h -> cfg.device));
+	if (on && !h -> d_scan_db) {
+	   const size_t S = h -> cfg.n_streams;
+	   h -> cap_scan = (int32_t)(h -> cap_fm / kScanN + 2);
+	   CK (dalloc (&h -> d_scan_carry [0], S * kScanN)); CK (dalloc (&h -> d_scan_carry [1], S * kScanN));
+	   CK (dalloc (&h -> d_scan_db, S * h -> cap_scan));
+	}
+	if (on && !h -> scanning) h -> scan_carry = 0;
+	h -> scanning = on != 0; h -> last_nscan = 0;
+	return SDRJFM_OK;
+}
+// (signal dB, noise dB) pairs of the 1024-sample blocks completed by the LAST process call
+static int64_t lane_read_scan (Lane *h, int32_t stream, float *out, int64_t cap_pairs) {
+	if (!h || !out || stream < 0 || stream >= h -> cfg.n_streams) return SDRJFM_ERR_ARG;
+int64_t n = h -> scanning ? h -> last_nscan : 0;
+	if (n > cap_pairs) n = cap_pairs;
+	if (n <= 0) return 0;
+	CK (cudaSetDevice (h -> cfg.device));
+	CK (cudaMemcpyAsync (out, h -> d_scan_db + (size_t)stream * h -> cap_scan, n * sizeof (float2), cudaMemcpyDeviceToHost, h -> stream));
+	CK (cudaStreamSynchronize (h -> stream));
 	return n;
 }
 static int lane_set_local_oscillator (Lane *h, int32_t hz) {

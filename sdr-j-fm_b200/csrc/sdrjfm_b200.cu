@@ -363,6 +363,16 @@ FWD1 (set_squelch_mode, int32_t)
 FWD1 (set_squelch_value, int32_t)
 FWD1 (set_native_rate, int32_t)
 FWD1 (set_rds_symbol_stage, int32_t)
+FWD1 (set_scanning, int32_t)
+int64_t sdrjfm_read_scan (sdrjfm_handle *h, int32_t stream, float *out, int64_t cap_pairs) {
+	if (!h || !out) return SDRJFM_ERR_ARG;
+const int i = lane_of (h, stream);
+	if (i < 0) return SDRJFM_ERR_ARG;
+	HK (cudaStreamSynchronize (h -> stream));
+const int64_t n = lane_read_scan (h -> lanes [i], stream - h -> first [i], out, cap_pairs);
+	if (n < 0) h -> err = h -> lanes [i] -> err;
+	return n;
+}
 int64_t sdrjfm_read_rds_bits (sdrjfm_handle *h, int32_t stream, uint8_t *out, int64_t cap) {
 	if (!h || !out) return SDRJFM_ERR_ARG;
 const int i = lane_of (h, stream);

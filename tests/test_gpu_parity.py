@@ -466,3 +466,39 @@ def test_rds_symbol_stage_matches_reference(pkg, signals, chainlib, ref_availabl
     tail = bits[-600:]
     best = max(int(np.sum(tail == np.roll(np.tile(tx, 2), -k)[:600])) for k in range(4096))
     assert best >= 590, best
+
+
+def test_station_scan_matches_reference(pkg, signals, chainlib, ref_available):
+    """startScanning (fm-processor.cpp:478-495): no demodulation, per 1024 fm-rate samples an FFT and
+    the carrier-level / band-edge-level pair; blocks run across call boundaries; a station is found
+    where the reference finds one.  After stopScanning the chain demodulates again."""
+    if not ref_available:
+        pytest.skip("oracle/_ref not available")
+    n = N1 // 2
+    rng = np.random.default_rng(77)
+    station = signals.stereo_pilot(n)
+    empty = (0.02 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))).astype(np.complex64)
+    for name, x in (("station", station), ("empty", empty)):
+        ref = chainlib.Chain("ref", dc_remove=1).process(x, taps=("fm_z",))
+        want = chainlib.ref_scan_blocks(ref["fm_z"])
+        p = pkg.FmProcessorB200(n_streams=1, max_samples_per_call=n)
+        p.startScanning()
+        got = []
+        pos = 0
+        for c in (16384 * 3 + 7, 12 * 1000, n):
+            a, r = p.process(x[pos:pos + c])
+            assert a.shape[1] == 0 and r.shape[1] == 0                  # nothing is demodulated while scanning
+            got.append(p.read_scan(0))
+            pos += c
+        got = np.concatenate(got)
+        p.stopScanning()
+        a, _ = p.process(x[:12 * 4000])
+        p.close()
+        assert a.shape[1] == 1000
+        assert got.shape == want.shape == ((n // 12) // 1024, 2)
+        d_got, d_want = got[:, 0] - got[:, 1], want[:, 0] - want[:, 1]
+        print(name, "max |dB error|", float(np.max(np.abs(got - want))), "signal - noise", float(d_want.mean()))
+        assert np.max(np.abs(got - want)) < 1e-3
+        th = 20                                                         # a typical thresHold
+        assert np.array_equal(d_got > th, d_want > th)
+        assert (d_want.mean() > th) == (name == "station")
