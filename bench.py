@@ -437,6 +437,33 @@ def main():
                        "h2d_bytes_per_step": S * n * 2,
                        "d2h_bytes_per_step": S * (na.value + nr.value) * 8, "steps": e2e_steps}}
 
+    # the GUI's real-time cadence: ONE stream, 16384-sample pulls (7.1 ms of signal,
+    # fm-processor.cpp:374) through the host-buffer call, as the Qt adapter makes them
+    gui = None
+    if not args.no_e2e and rank == 0:
+        sig = importlib.import_module("sdrjfm_b200.signals")
+        g = pkg.FmProcessorB200(n_streams=1, max_samples_per_call=16384, device=local, keep_taps=False)
+        g.configure(**settings)
+        xs = sig.batch_stream(0, 16384 * 64)
+        ga = np.zeros((1, 16384 // 48 + 2), np.complex64)
+        gr = np.zeros((1, 16384 // 96 + 2), np.complex64)
+        import ctypes as C2
+        a1, r1 = C2.c_int64(0), C2.c_int64(0)
+        lat = []
+        for i in range(64 * 4):
+            blk = xs[(i % 64) * 16384:(i % 64 + 1) * 16384]
+            t0 = time.perf_counter()
+            rc = g.L.sdrjfm_process(g.h, blk.ctypes.data, 16384, 16384, ga.ctypes.data, ga.shape[1], C2.byref(a1),
+                                    gr.ctypes.data, gr.shape[1], C2.byref(r1), None)
+            lat.append(time.perf_counter() - t0)
+            assert rc == 0
+        lat = np.array(lat[32:]) * 1e3
+        gui = {"call": "sdrjfm_process, 1 stream x 16384 IQ samples (7.11 ms of signal) from pageable host memory, "
+                       "audio + RDS baseband back", "calls": int(len(lat)), "ms_per_call_median": float(np.median(lat)),
+               "ms_per_call_p99": float(np.percentile(lat, 99)), "ms_per_call_max": float(lat.max()),
+               "x_realtime": float(16384 / 2304000 * 1e3 / np.median(lat))}
+        g.close()
+
     sweep = None
     if args.front_end_sweep and rank == 0:
         sweep = front_end_sweep(pkg, torch, dev, local, S, peak)
@@ -452,7 +479,7 @@ def main():
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "x_realtime_2p304MSps": value / 2.304, "roofline": roofline,
-                "cpu_baseline": cpu, "e2e": e2e, "device_format_u8": raw, "front_end_sweep": sweep,
+                "cpu_baseline": cpu, "e2e": e2e, "device_format_u8": raw, "front_end_sweep": sweep, "gui_cadence": gui,
                 "gpu_launches": int(launches),
                 "clocks": clk.summary()}
         emit(line)
