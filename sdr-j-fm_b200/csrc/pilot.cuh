@@ -290,6 +290,13 @@ int    itTotal = 0, itMax = 0, nFallback = 0;
 	         S.resid [c] = rs;
 	      }
 	      const int nbad = __syncthreads_count (bad);
+#ifdef SDRJFM_PILOT_TRACE      // per-pass convergence of a few windows of stream 0 (profiles/r1_summary.md)
+	      if (blockIdx.x == 0 && tid == 0 && base >= kPiWin * 30 && base < kPiWin * 34) {
+	         double mr = 0; int first = -1;
+	         for (int c = 0; c < nseg; c ++) { if (S.resid [c] != 0.0 && first < 0) first = c; mr = fmax (mr, fabs (S.resid [c])); }
+	         printf ("win %d it %d nseg %d nbad %d first %d maxresid %.3e\n", base / kPiWin, it, nseg, nbad, first, mr);
+	      }
+#endif
 	      if (nbad == 0) { converged = true; break; }
 //	   Newton correction of the anchors: delta[c+1] = resid[c] + der[c] delta[c], delta[0] = 0,
 //	   as a block-wide scan of affine maps (thread t owns segments per*t .. per*t + per - 1)
