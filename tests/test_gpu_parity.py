@@ -502,3 +502,38 @@ def test_station_scan_matches_reference(pkg, signals, chainlib, ref_available):
         th = 20                                                         # a typical thresHold
         assert np.array_equal(d_got > th, d_want > th)
         assert (d_want.mean() > th) == (name == "station")
+
+
+def test_edge_cases_empty_tiny_and_capacity(pkg, signals, checker):
+    """empty and one-sample calls, calls shorter than one fm-rate sample, NULL outputs, the capacity
+    error — and the stream they leave behind still equals the reference's."""
+    import ctypes as C
+    n = 12 * 3000 + 5
+    x = signals.mono_tone(n, seed=9)
+    cfg = dict(fm_mode=2, volume_db=0.0)
+    p = pkg.FmProcessorB200(n_streams=1, max_samples_per_call=20000)
+    p.configure(**cfg)
+    demod = []
+    a, r = p.process(x[:0])                                   # empty call
+    assert a.shape == (1, 0) and r.shape == (1, 0) and len(p.read_tap("demod")) == 0
+    pos = 0
+    for c in [1] * 25 + [11, 13, 0, 20000, 7, 20000]:
+        a, _ = p.process(x[pos:pos + c])
+        demod.append(p.read_tap("demod"))
+        pos += c
+    assert pos >= n
+    # NULL audio / rds / meta pointers are allowed
+    na = C.c_int64(-1)
+    blk = np.ascontiguousarray(x[:1200])
+    assert p.L.sdrjfm_process(p.h, blk.ctypes.data, 1200, 1200, None, 0, C.byref(na), None, 0, None, None) == 0
+    assert na.value == 25
+    # more than max_samples_per_call: refused, nothing consumed
+    big = np.zeros(20001, np.complex64)
+    rc = p.L.sdrjfm_process(p.h, big.ctypes.data, 20001, 20001, None, 0, None, None, 0, None, None)
+    assert rc == pkg.ERR_CAPACITY and b"max_samples_per_call" in p.L.sdrjfm_last_error(p.h)
+    assert p.L.sdrjfm_process(p.h, None, 5, 5, None, 0, None, None, 0, None, None) == pkg.ERR_ARG
+    p.close()
+    demod = np.concatenate(demod)
+    ref = checker(**cfg).process(x)
+    assert len(demod) == ref["n_fm"] == n // 12
+    assert rms(demod - ref["demod"]) < 1e-5
