@@ -16,6 +16,7 @@ struct sdrjfm_handle {
 	cudaStream_t stream = nullptr;          // the stream callers time / order against
 	bool own_stream = false;
 	cudaStream_t copy_stream = nullptr;     // H2D of the next time slice while the current one computes
+	cudaStream_t out_stream = nullptr;      // D2H of a finished slice's outputs while the next ones compute
 	cudaEvent_t  ev_fork = nullptr, ev_h2d [2] = { nullptr, nullptr }, ev_done [2] = { nullptr, nullptr };
 	std::vector<cudaEvent_t> ev_join;
 	int64_t cap_in = 0, cap_audio = 0, cap_rds = 0;
@@ -136,6 +137,7 @@ int sdrjfm_destroy (sdrjfm_handle *h) {
 	for (cudaEvent_t ev : { h -> ev_fork, h -> ev_h2d [0], h -> ev_h2d [1], h -> ev_done [0], h -> ev_done [1] })
 	   if (ev) cudaEventDestroy (ev);
 	if (h -> copy_stream) cudaStreamDestroy (h -> copy_stream);
+	if (h -> out_stream) cudaStreamDestroy (h -> out_stream);
 	if (h -> own_stream && h -> stream) cudaStreamDestroy (h -> stream);
 	delete h;
 	return SDRJFM_OK;
@@ -238,12 +240,13 @@ int64_t na = 0, nr = 0;
 //	Large offline calls (no tap read-back wanted): the call is cut into time slices and the
 //	host->device copy of slice c+1 runs on a second stream while slice c computes.  The chain is
 //	stateful, so this is exactly the sequence of smaller calls the GUI cadence would make.
-const int64_t kSlices = 8;
+const int64_t kSlices = 16;
 const int64_t unit = 256 * (int64_t)h -> lanes [0] -> decim;
 const int64_t slice = ((n_in / kSlices) / unit) * unit;          // multiple of the decimation
 	if (!h -> cfg.keep_taps && slice >= (1 << 16)) {
 	   if (!h -> copy_stream) {
 	      HK (cudaStreamCreateWithFlags (&h -> copy_stream, cudaStreamNonBlocking));
+	      HK (cudaStreamCreateWithFlags (&h -> out_stream, cudaStreamNonBlocking));
 	      for (int i = 0; i < 2; i ++) {
 	         HK (cudaEventCreateWithFlags (&h -> ev_h2d [i], cudaEventDisableTiming));
 	         HK (cudaEventCreateWithFlags (&h -> ev_done [i], cudaEventDisableTiming));
@@ -266,8 +269,27 @@ const int64_t slice = ((n_in / kSlices) / unit) * unit;          // multiple of 
 	                        (float *)(h -> d_rds24 + nr), h -> cap_rds, &r1);
 	      if (rc != SDRJFM_OK) return rc;
 	      HK (cudaEventRecord (h -> ev_done [b], h -> stream));
+//	      this slice's outputs go back on a third stream (PCIe is full duplex) while the next slices run
+	      if ((audio && a1 > 0) || (rds24 && r1 > 0)) {
+	         if ((audio && audio_pitch < na + a1) || (rds24 && rds_pitch < nr + r1)) return SDRJFM_ERR_ARG;
+	         HK (cudaStreamWaitEvent (h -> out_stream, h -> ev_done [b], 0));
+	         if (audio && a1 > 0)
+	            HK (cudaMemcpy2DAsync ((float2 *)audio + na, audio_pitch * sizeof (float2), h -> d_audio + na,
+	                                   h -> cap_audio * sizeof (float2), a1 * sizeof (float2), S,
+	                                   cudaMemcpyDeviceToHost, h -> out_stream));
+	         if (rds24 && r1 > 0)
+	            HK (cudaMemcpy2DAsync ((float2 *)rds24 + nr, rds_pitch * sizeof (float2), h -> d_rds24 + nr,
+	                                   h -> cap_rds * sizeof (float2), r1 * sizeof (float2), S,
+	                                   cudaMemcpyDeviceToHost, h -> out_stream));
+	      }
 	      na += a1; nr += r1; pos += len; c ++;
 	   }
+	   HK (cudaStreamSynchronize (h -> out_stream));
+	   HK (cudaStreamSynchronize (h -> stream));
+	   if (n_audio) *n_audio = na;
+	   if (n_rds) *n_rds = nr;
+	   if (meta) return sdrjfm_get_meta (h, meta);
+	   return SDRJFM_OK;
 	}
 	else {
 	   if (n_in)
