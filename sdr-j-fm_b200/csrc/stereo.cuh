@@ -148,11 +148,17 @@ float2 *ring = ring_g + (int64_t)stream * kPssRing;
 //	whole call so that the block loop never waits on global memory for them
 	if (tid == 0) sNTrans = 0;
 	__syncthreads ();
-	for (int32_t m = tid + 1; m < M; m += kStThreads)
-	   if ((lk [m] != 0) != (lk [m - 1] != 0)) {
-	      const int slot = atomicAdd (&sNTrans, 1);
-	      if (slot < kStMaxTrans) sTrans [slot] = m;
-	   }
+	for (int32_t m0 = 1 + tid * 8; m0 < M; m0 += kStThreads * 8) {       // 8 flags per step: the loads overlap
+	   uint8_t f [9];
+#pragma unroll
+	   for (int k = 0; k < 9; k ++) f [k] = (m0 - 1 + k < M) ? lk [m0 - 1 + k] : 0;
+#pragma unroll
+	   for (int k = 1; k < 9; k ++)
+	      if (m0 - 1 + k < M && (f [k] != 0) != (f [k - 1] != 0)) {
+	         const int slot = atomicAdd (&sNTrans, 1);
+	         if (slot < kStMaxTrans) sTrans [slot] = m0 - 1 + k;
+	      }
+	}
 	__syncthreads ();
 const int nTrans = sNTrans;                       // > kStMaxTrans: fall back to scanning per block
 bool curLock = M > 0 ? lk [0] != 0 : false;
@@ -179,6 +185,16 @@ bool curLock = M > 0 ? lk [0] != 0 : false;
 	   if (p + len < M) curLock = lk [p + len] != 0;    // (consumed one block later: latency hidden)
 	   const int m0 = tid * kStPer;
 	   const int pos = sPos;
+//	   this thread's demod / pilot-phase samples: requested now, used in step 3 (behind the FIR)
+	   float dv [kStPer], pv [kStPer];
+	   if (cat != 0) {
+#pragma unroll
+	      for (int k = 0; k < kStPer; k ++) {
+	         const bool ok = m0 + k < len;
+	         dv [k] = ok ? dm [p + m0 + k] : 0.f;
+	         pv [k] = ok ? ph [p + m0 + k] : 0.f;
+	      }
+	   }
 
 	   if (cat == 0) {
 //	   mono / not locked with autoMono: audioOut = (demod, 0), :728-730
@@ -341,15 +357,24 @@ bool curLock = M > 0 ? lk [0] != 0 : false;
 	      __syncthreads ();
 	   }
 
-//	   3. phi38, new filter inputs, L-R, matrix
+//	   3. phi38, new filter inputs, L-R, matrix.  All table look-ups of the thread are issued before
+//	      the first one is used.
+	   float phv [kStPer]; float2 csv [kStPer];
+#pragma unroll
+	   for (int k = 0; k < kStPer; k ++) {
+	      phv [k] = 0.f; csv [k] = make_float2 (0.f, 0.f);
+	      if (m0 + k < len) {
+	         phv [k] = phase_for_lr (pv [k], sDel [m0 + k]);
+	         csv [k] = sincos [sincos_index (phv [k])];
+	      }
+	   }
 #pragma unroll
 	   for (int k = 0; k < kStPer; k ++) {
 	      const int m = m0 + k;
 	      if (m < len) {
-	         const float d = dm [p + m];
-	         const float phLR = phase_for_lr (ph [p + m], sDel [m]);
-	         const int32_t idx = sincos_index (phLR);
-	         const float2 cs = sincos [idx];
+	         const float d = dv [k];
+	         const float phLR = phv [k];
+	         const float2 cs = csv [k];
 	         if (pss) sRing [(pos + m) & (kPssRing - 1)] = make_float2 (fmul (cs.x, d), fmul (cs.y, d));   // :66-67
 	         float osc = cs.x;
 	         if (P.sound_sel == 6) {               // S_LEFTminusRIGHT_Test: getSin, :721-723
