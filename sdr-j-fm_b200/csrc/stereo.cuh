@@ -227,7 +227,7 @@ bool curLock = M > 0 ? lk [0] != 0 : false;
 #pragma unroll
 	         for (int k = 0; k < kStPer; k ++) v [k] = sRing [(base + k) & (kPssRing - 1)];
 	         int nxt = base - 1;                                          // ring slot of element -j-1
-#pragma unroll 1
+#pragma unroll
 	         for (int j0 = 0; j0 + kStPer <= kPssTaps; j0 += kStPer) {
 #pragma unroll
 	            for (int u = 0; u < kStPer; u ++) {
