@@ -240,7 +240,8 @@ int64_t na = 0, nr = 0;
 //	Large offline calls (no tap read-back wanted): the call is cut into time slices and the
 //	host->device copy of slice c+1 runs on a second stream while slice c computes.  The chain is
 //	stateful, so this is exactly the sequence of smaller calls the GUI cadence would make.
-const int64_t kSlices = 16;
+int64_t kSlices = 16;
+	{ const char *env = getenv ("SDRJFM_SLICES"); if (env && atoi (env) > 0) kSlices = atoi (env); }
 const int64_t unit = 256 * (int64_t)h -> lanes [0] -> decim;
 const int64_t slice = ((n_in / kSlices) / unit) * unit;          // multiple of the decimation
 	if (!h -> cfg.keep_taps && slice >= (1 << 16)) {
