@@ -31,7 +31,7 @@ constexpr int kRdsTaps    = 768;                // PILOTFILTER_SIZE, fm-constant
 constexpr int kRdsBlock   = kRdsN - kRdsTaps;   // 32000 = NumofSamples
 constexpr int kRdsDelay   = 2 * kRdsBlock;      // RDS_SAMPLE_DELAY
 constexpr int kRdsRing    = 131072;             // per-stream history of demod / pilot phase
-constexpr int kRdsThreads = 1024;
+constexpr int kRdsThreads = 512;       // 512 x 64 registers + 128 KB: the SM keeps room for a CTA of another kernel
 constexpr int kRdsFftSmem = kRdsNh * (int)sizeof (float2);      // 131072 B
 constexpr int kRdsDecTaps = 11;
 constexpr int kRdsDecim   = 8;
@@ -51,18 +51,20 @@ constexpr int kRdsBpt = kRdsNh / 2 / kRdsThreads;       // butterflies per threa
 // Two radix-2 stages are merged into one pass over shared memory (a radix-4 butterfly written as the
 // two radix-2 layers it consists of, outputs left where the radix-2 stages would have put them, so the
 // overall permutation is still plain bit reversal): 7 passes and barriers instead of 14.
-constexpr int kRdsQpt = kRdsNh / 4 / kRdsThreads;       // quads per thread per pass (4)
+constexpr int kRdsQpt = 4;                              // quads per thread and batch
+constexpr int kRdsQbatches = kRdsNh / 4 / kRdsThreads / kRdsQpt;   // batches per pass (disjoint elements: no barrier between them)
 static_assert ((kRdsNh & (kRdsNh - 1)) == 0 && (31 - __builtin_clz (kRdsNh)) % 2 == 0, "an even number of radix-2 stages");
 
 // forward: decimation in frequency, natural order in -> bit-reversed order out
 __device__ void fft_dif (float2 *a, const float2 *__restrict__ tws) {
 	for (int h = kRdsNh / 2; h >= 2; h >>= 2) {           // stages `half = h` and `half = h / 2`
 	   const int hh = h >> 1;
+	   for (int bt = 0; bt < kRdsQbatches; bt ++) {
 	   float2 x0 [kRdsQpt], x1 [kRdsQpt], x2 [kRdsQpt], x3 [kRdsQpt], w [kRdsQpt], w2 [kRdsQpt];
 	   int idx [kRdsQpt];
 #pragma unroll
 	   for (int q = 0; q < kRdsQpt; q ++) {
-	      const int b = threadIdx.x + q * kRdsThreads;
+	      const int b = threadIdx.x + (bt * kRdsQpt + q) * kRdsThreads;
 	      const int pos = b & (hh - 1);
 	      idx [q] = ((b - pos) << 2) + pos;
 	      x0 [q] = a [idx [q]]; x1 [q] = a [idx [q] + hh]; x2 [q] = a [idx [q] + h]; x3 [q] = a [idx [q] + h + hh];
@@ -81,17 +83,19 @@ __device__ void fft_dif (float2 *a, const float2 *__restrict__ tws) {
 	      a [idx [q] + h]      = make_float2 (C.x + D.x, C.y + D.y);
 	      a [idx [q] + h + hh] = cmulf (make_float2 (C.x - D.x, C.y - D.y), w2 [q]);
 	   }
+	   }
 	   __syncthreads ();
 	}
 }
 // inverse: decimation in time with conjugate twiddles, bit-reversed order in -> natural order out
 __device__ void ifft_dit (float2 *a, const float2 *__restrict__ tws) {
 	for (int h = 1; h <= kRdsNh / 4; h <<= 2) {           // stages `half = h` and `half = 2 h`
+	   for (int bt = 0; bt < kRdsQbatches; bt ++) {
 	   float2 x0 [kRdsQpt], x1 [kRdsQpt], x2 [kRdsQpt], x3 [kRdsQpt], w [kRdsQpt], w2 [kRdsQpt];
 	   int idx [kRdsQpt];
 #pragma unroll
 	   for (int q = 0; q < kRdsQpt; q ++) {
-	      const int b = threadIdx.x + q * kRdsThreads;
+	      const int b = threadIdx.x + (bt * kRdsQpt + q) * kRdsThreads;
 	      const int pos = b & (h - 1);
 	      idx [q] = ((b - pos) << 2) + pos;
 	      x0 [q] = a [idx [q]]; x1 [q] = a [idx [q] + h]; x2 [q] = a [idx [q] + 2 * h]; x3 [q] = a [idx [q] + 3 * h];
@@ -109,6 +113,7 @@ __device__ void ifft_dit (float2 *a, const float2 *__restrict__ tws) {
 	      a [idx [q] + h]     = make_float2 (y1.x + tp.x, y1.y + tp.y);
 	      a [idx [q] + 2 * h] = make_float2 (y0.x - t.x, y0.y - t.y);
 	      a [idx [q] + 3 * h] = make_float2 (y1.x - tp.x, y1.y - tp.y);
+	   }
 	   }
 	   __syncthreads ();
 	}
@@ -163,7 +168,7 @@ __device__ void spectrum_pass (float2 *a, const float2 *__restrict__ tw, const f
 // bpb   : [S][2][32000] band-pass block (slot k & 1);  hib : [S][2][32768] its Hilbert transform
 // R     : kRdsNh + 1 complex, spectrum of 3 r[j] scaled by 1/Nh;  tw: exp (-2 pi i k / N), k < Nh (spectrum
 //         pass);  tws: per-stage twiddles of the Nh-point transforms
-__global__ void __launch_bounds__ (kRdsThreads, 1)
+__global__ void __launch_bounds__ (kRdsThreads, 2)      // <= 64 registers (shared memory allows one CTA per SM)
 rds_block_kernel (const float *__restrict__ dring, int64_t blk,
                   const float2 *__restrict__ tw, const float2 *__restrict__ tws, const float2 *__restrict__ R,
                   float *__restrict__ bpb, float *__restrict__ hib) {
@@ -186,22 +191,28 @@ const int64_t base = (blk - 1) * (int64_t)kRdsBlock - (kRdsTaps - 1);   // rds i
 	spectrum_pass<false> (fa, tw, R);
 	ifft_dit (fa, tws);
 //	valid outputs c[767 + i], i < 32000 -> bp block; re-pack zero-padded for the Hilbert pass
-float2 z [kRdsNh / kRdsThreads];
+//	(in two halves of the index range to keep the register count at 64: a half reads entries
+//	383 + m, 384 + m and, after a barrier, writes entries m of ITS range only; the second half's
+//	sources lie above everything the first half wrote)
+constexpr int kZ = kRdsNh / kRdsThreads / 2;
+	for (int part = 0; part < 2; part ++) {
+	   float2 z [kZ];
 #pragma unroll
-	for (int q = 0; q < kRdsNh / kRdsThreads; q ++) {
-	   const int m = tid + q * kRdsThreads;              // z[m] = (bp[2m], bp[2m+1])
-	   float2 v = make_float2 (0.f, 0.f);
-	   if (2 * m < kRdsBlock) v = make_float2 (fa [(kRdsTaps - 2) / 2 + m].y, fa [kRdsTaps / 2 + m].x);
-	   z [q] = v;
-	}
-	__syncthreads ();
+	   for (int q = 0; q < kZ; q ++) {
+	      const int m = tid + (part * kZ + q) * kRdsThreads;              // z[m] = (bp[2m], bp[2m+1])
+	      float2 v = make_float2 (0.f, 0.f);
+	      if (2 * m < kRdsBlock) v = make_float2 (fa [(kRdsTaps - 2) / 2 + m].y, fa [kRdsTaps / 2 + m].x);
+	      z [q] = v;
+	   }
+	   __syncthreads ();
 #pragma unroll
-	for (int q = 0; q < kRdsNh / kRdsThreads; q ++) {
-	   const int m = tid + q * kRdsThreads;
-	   fa [m] = z [q];
-	   if (2 * m < kRdsBlock) reinterpret_cast<float2 *>(bpo) [m] = z [q];
+	   for (int q = 0; q < kZ; q ++) {
+	      const int m = tid + (part * kZ + q) * kRdsThreads;
+	      fa [m] = z [q];
+	      if (2 * m < kRdsBlock) reinterpret_cast<float2 *>(bpo) [m] = z [q];
+	   }
+	   __syncthreads ();
 	}
-	__syncthreads ();
 	fft_dif (fa, tws);
 	spectrum_pass<true> (fa, tw, R);
 	ifft_dit (fa, tws);
