@@ -159,6 +159,22 @@ def cpu_reference_rate(settings, seconds_per_thread, threads=None):
             "seconds": dt}
 
 
+def bind_to_gpu_numa_node(index):
+    """one process per GPU: run (and first-touch the pinned host buffers) on the CPUs NVML names as
+    closest to this GPU, so that the host->device copies of the ranks do not share one memory controller"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def emit(line):
     """the ONE JSON line goes to the real stdout; everything else a library prints to fd 1 during the
     run (e.g. NCCL's version banner) has been routed to stderr by main()."""
@@ -269,6 +285,7 @@ def main():
         emit(line)
         return
 
+    bind_to_gpu_numa_node(local)
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():

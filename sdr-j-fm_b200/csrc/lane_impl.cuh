@@ -1,13 +1,18 @@
 // Launch sequencing of the B200 FM path for one lane of streams (included by sdrjfm_b200.cu).
 //
-// Per process call and per batch of streams the sequence mirrors the order of
+// Per process call and per lane of streams the sequence mirrors the order of
 // fmProcessor::run's per-sample loop (src/fm/fm-processor.cpp:461-648):
-//   K1 frontend_fir_kernel     DC sums + 37-tap /12 polyphase FIR      (:423-446,:462-475)
-//   K2 discriminator_kernel    DC subtract, gains, normalise, atan     (:497 -> fm-demodulator.cpp:111-195)
-//   K3 sequential_kernel       AFC/level one-poles, pilot PLL, lock    (fm-demodulator.cpp:197-198, pilot-recover.cpp)
-//   K4 stereo / mono matrix    PSS + 38 kHz demod + L/R selector       (:689-730,:517-549)
-//   K5 RDS branch              band-pass, Hilbert, x3 pilot mix, /8    (:733-758,:551-553)
-//   K6 de-emphasis, gain, 192->48 kHz, fade-in                        (:594-595,:630-642)
+//   K1t / K1 / K1g  front end: DC block sums + polyphase FIR to the fm rate   (:423-446,:462-475)
+//                   (K1t: TMA-fed, 2.304 MS/s complex float; K1g: any decimation / sample format;
+//                    resampler mode: K1g /5 + resample_b_kernel)
+//   K2  dc_tile + discriminator_kernel   DC subtract, gains, normalise, atan   (:497 -> fm-demodulator.cpp:111-195)
+//   Ksc scan_kernel (only while scanning: nothing behind it runs)              (:478-495)
+//   K3  pilot_kernel (parallel in time) | sequential_kernel (PLL / AM decoder, squelch)
+//                                         AFC, pilot PLL, lock                  (fm-demodulator.cpp:197-241, pilot-recover.cpp, squelchClass.cpp)
+//   K4  stereo_kernel                    PSS + 38 kHz demod + L/R selector     (:689-730,:517-549)
+//   K5  rds_* on the lane's side stream  band-pass, Hilbert, x3 pilot mix, /8  (:733-758,:551-553)
+//       (+ optional symbol stage: Costas, rdsDecoder_1 -> bits, running past the call's join)
+//   K6  audio_kernel                     [audio low-pass] de-emphasis, gain, 192->48 kHz, fade-in   (:589-595,:630-642)
 // There is NO CPU fallback: without a CUDA device sdrjfm_create fails with
 // SDRJFM_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
