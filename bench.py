@@ -241,7 +241,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=256, help="IQ streams per GPU")
     ap.add_argument("--seconds", type=float, default=0.5, help="signal seconds per stream per step")
-    ap.add_argument("--cpu-seconds", type=float, default=3.0, help="cpu baseline: signal seconds per thread")
+    ap.add_argument("--cpu-seconds", type=float, default=8.0, help="cpu baseline: signal seconds per thread")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--rds-symbols", action="store_true",
