@@ -82,7 +82,9 @@ enum sdrjfm_tap {
     SDRJFM_TAP_LR = 5,         /* complex: (left,right) after the selector (:527-549)    */
     SDRJFM_TAP_AUDIO192 = 6,   /* complex: after de-emphasis and gain (:594-595,:630)    */
     SDRJFM_TAP_RDS_CPLX = 7,   /* complex: rdsDataCplx (:754)                            */
-    SDRJFM_TAP_RDS24 = 8       /* complex @24 kHz: rdsSample (:553)                      */
+    SDRJFM_TAP_RDS24 = 8,      /* complex @24 kHz: rdsSample (:553)                      */
+    SDRJFM_TAP_FE_U = 9,       /* complex: raw output of the front-end FIR (before DC subtraction and the constant gain) */
+    SDRJFM_TAP_FE_S = 10       /* complex: block sums of the input samples behind each fm-rate sample (DC remover)      */
 };
 
 /* --- life cycle: replaces `new fmProcessor (...)` / `delete` (radio.cpp:908-949, 629-644) */

@@ -21,10 +21,11 @@ HEADER = os.path.join(os.path.dirname(PKG_DIR), "include", "sdrjfm_b200.h")
 OK, ERR_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_CAPACITY, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 
 TAP = dict(fm_z=0, demod=1, pilot_phase=2, locked=3, pss_delay=4, lr=5, audio192=6,
-           rds_cplx=7, rds24=8)
+           rds_cplx=7, rds24=8, fe_u=9, fe_s=10)
 _TAP_DTYPE = dict(fm_z=np.complex64, demod=np.float32, pilot_phase=np.float32,
                   locked=np.uint8, pss_delay=np.float32, lr=np.complex64,
-                  audio192=np.complex64, rds_cplx=np.complex64, rds24=np.complex64)
+                  audio192=np.complex64, rds_cplx=np.complex64, rds24=np.complex64,
+                  fe_u=np.complex64, fe_s=np.complex64)
 
 
 # device sample formats (enum sdrjfm_iq_format): dtype of one I or Q component

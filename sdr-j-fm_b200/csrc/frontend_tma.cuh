@@ -128,6 +128,12 @@ int it = 0;
 //	   box row tid + 1 = its own 48 samples
 	   ft_row<11, 13, -kFtRowSamples> (stage, tid * 3, acc, dcs);
 	   ft_row<0, 24, 0> (stage, (tid + 1) * 3, acc, dcs);
+//	   The next TMA write into this stage is an async-proxy access; this thread's shared loads are
+//	   generic-proxy accesses that may still be in flight when it reaches the barrier (their consumers
+//	   can be scheduled behind it).  The proxy fence orders them before anything the async proxy does
+//	   afterwards — without it a busy shared-memory pipe (another kernel on the SM) lets the refill
+//	   overtake the tail of a thread's row.
+	   asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");
 	   __syncthreads ();                                    // every thread has read the stage
 
 	   if (tid == 0) {

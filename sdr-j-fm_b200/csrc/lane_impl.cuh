@@ -1190,6 +1190,8 @@ const void *src = nullptr; size_t esz = 0; int64_t n = h -> last_nfm; int64_t pi
 	   case SDRJFM_TAP_AUDIO192:    src = h -> d_a192;   esz = 8; break;
 	   case SDRJFM_TAP_RDS_CPLX:    src = h -> d_rdsc;   esz = 8; break;
 	   case SDRJFM_TAP_RDS24:       src = h -> d_rds24;  esz = 8; n = h -> last_nrds; pitch = h -> cap_rds; break;
+	   case SDRJFM_TAP_FE_U:        src = h -> d_U;      esz = 8; break;
+	   case SDRJFM_TAP_FE_S:        src = h -> d_S;      esz = 8; break;
 	   default: return SDRJFM_ERR_ARG;
 	}
 	if (n > cap) n = cap;

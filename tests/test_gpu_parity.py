@@ -537,3 +537,44 @@ def test_edge_cases_empty_tiny_and_capacity(pkg, signals, checker):
     ref = checker(**cfg).process(x)
     assert len(demod) == ref["n_fm"] == n // 12
     assert rms(demod - ref["demod"]) < 1e-5
+
+
+def test_config5_full_size_properties(pkg, signals, checker):
+    """BASELINE config 5 at full size: 256 streams x 4 s of 2.304 MS/s IQ (18.9 GB) with RDS, fed in 1 s
+    calls.  Eight distinct config-5 signals are dealt over the 256 streams in a shuffled order:
+    (i) output counts, (ii) copies of the same signal give BIT-identical audio and RDS whatever lane and
+    position they run in, (iii) every distinct signal matches the reference."""
+    S, secs, K = 256, 4, 8
+    n1 = N1
+    base = [signals.batch_stream(40 + k, n1 * secs) for k in range(K)]
+    order = np.random.default_rng(5).permutation(S) % K
+    cfg = dict(fm_mode=0, rds_on=1, volume_db=-6.0)
+    p = pkg.FmProcessorB200(n_streams=S, max_samples_per_call=n1, keep_taps=False)
+    p.configure(**cfg)
+    audio, rds = [], []
+    for c in range(secs):
+        x = np.stack([base[k][c * n1:(c + 1) * n1] for k in order])
+        a, r = p.process(x)
+        audio.append(a); rds.append(r)
+        del x
+    p.close()
+    audio, rds = np.concatenate(audio, axis=1), np.concatenate(rds, axis=1)
+    assert audio.shape == (S, n1 * secs // 48) and rds.shape == (S, n1 * secs // 96)
+    for k in range(K):
+        idx = np.nonzero(order == k)[0]
+        assert len(idx) >= 2
+        for i in idx[1:]:
+            assert np.array_equal(audio[i].view(np.uint64), audio[idx[0]].view(np.uint64)), (k, i)
+            assert np.array_equal(rds[i].view(np.uint64), rds[idx[0]].view(np.uint64)), (k, i)
+        ref = checker(**cfg).process(base[k], taps=("audio192", "rds24"))
+        assert rms(rds[idx[0]] - ref["rds24"]) < 1e-5, k
+        # 48 kHz audio = our documented decimator applied to the reference's 192 kHz audio (fade-in over the first 0.5 s)
+        fc, nt = 20000.0 / 192000.0, 129
+        t = np.arange(nt) - nt // 2
+        h = np.where(t == 0, 2 * fc, np.sin(2 * np.pi * fc * t) / (np.pi * np.where(t == 0, 1, t)))
+        h = h * (0.42 - 0.5 * np.cos(2 * np.pi * np.arange(nt) / (nt - 1)) + 0.08 * np.cos(4 * np.pi * np.arange(nt) / (nt - 1)))
+        h = (h / h.sum()).astype(np.float32).astype(np.float64)
+        y = np.convolve(ref["audio192"].astype(np.complex128), h)[3::4][:audio.shape[1]]
+        q = np.arange(audio.shape[1])
+        y = y * np.where(q < 24000, q / 24000.0, 1.0)
+        assert rms(audio[idx[0]] - y) < 1e-5, k
