@@ -55,6 +55,35 @@ __device__ __forceinline__ float2 lo_apply (const LoParams &L, float2 v, int32_t
 	return cmul_rn (make_float2 (fmul (v.x, L.lgain), fmul (v.y, L.rgain)), L.tab [idx]);
 }
 
+// Block sums of the RAW samples when the oscillator is on (the RF DC estimate follows the samples
+// before gain and rotation), WITHOUT atomics: lanes hold consecutive samples j, a block of D
+// consecutive samples is cut only at multiples of 32, i.e. into at most kRawSlots warp segments.
+// Each segment is summed by a shuffle scan in a fixed order and stored in ITS slot; the slots are
+// added in a fixed order at the end, so the result never depends on timing.
+constexpr int kRawSlots = 3;                        // D <= 64
+__device__ __forceinline__ void raw_block_sum (float2 *sPart /* [blocks][kRawSlots] */, int j, float2 v, int D) {
+const int lane = threadIdx.x & 31;
+const int blk = j / D;
+float2 s = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+	   const float ox = __shfl_up_sync (0xffffffffu, s.x, d), oy = __shfl_up_sync (0xffffffffu, s.y, d);
+	   const int ob = __shfl_up_sync (0xffffffffu, blk, d);
+	   if (lane >= d && ob == blk) { s.x += ox; s.y += oy; }
+	}
+const int nb = __shfl_down_sync (0xffffffffu, blk, 1);
+	if (lane == 31 || nb != blk) {
+	   const int jfirst = max (blk * D, j - lane);      // block start or warp start
+	   sPart [blk * kRawSlots + ((jfirst >> 5) - ((blk * D) >> 5))] = s;
+	}
+}
+__device__ __forceinline__ float2 raw_block_total (const float2 *sPart, int blk) {
+float2 t = sPart [blk * kRawSlots];
+#pragma unroll
+	for (int q = 1; q < kRawSlots; q ++) { t.x += sPart [blk * kRawSlots + q].x; t.y += sPart [blk * kRawSlots + q].y; }
+	return t;
+}
+
 // x      : [n_streams][in_pitch] complex, this call's samples (N = 12 * M per stream)
 // hist   : [n_streams][hist_len] complex, the raw samples preceding x[.][0] (the last 36 are used)
 // U, S   : [n_streams][out_pitch] complex
@@ -65,8 +94,8 @@ frontend_fir_kernel (const float2 *__restrict__ x, int64_t in_pitch,
                      float2 *__restrict__ U, float2 *__restrict__ S,
                      int64_t out_pitch, int32_t M, const LoParams lop, int32_t tile0) {
 extern __shared__ float2 sm [];
-__shared__ float2 sRaw [LO ? kFeTileOut : 1];
-	if (LO) { for (int i = threadIdx.x; i < kFeTileOut; i += kFeThreads) sRaw [i] = make_float2 (0.f, 0.f); __syncthreads (); }
+__shared__ float2 sRaw [LO ? kFeTileOut * kRawSlots : 1];
+	if (LO) { for (int i = threadIdx.x; i < kFeTileOut * kRawSlots; i += kFeThreads) sRaw [i] = make_float2 (0.f, 0.f); __syncthreads (); }
 const int tid    = threadIdx.x;
 const int stream = blockIdx.y;
 const int tile = blockIdx.x + tile0;                     // tile0: the tiles before it were done by K1t
@@ -96,7 +125,7 @@ int32_t loIdx = LO ? lo_index (lop, in0 + tid) : 0;
 	      v [k] = (n < N) ? __ldcs (xs + n) : make_float2 (0.f, 0.f);
 	      if (LO) {
 	         // the RF DC estimate follows the RAW samples: block sums before gain and rotation
-	         atomicAdd (&sRaw [j / kDecim].x, v [k].x); atomicAdd (&sRaw [j / kDecim].y, v [k].y);
+	         raw_block_sum (sRaw, j, v [k], kDecim);
 	         v [k] = lo_apply (lop, v [k], loIdx);
 	         loIdx -= lop.step128; if (loIdx < 0) loIdx += lop.rate;
 	      }
@@ -152,7 +181,7 @@ float2 *Us = U + (int64_t)stream * out_pitch;
 float2 *Ss = S + (int64_t)stream * out_pitch;
 	if (LO) {
 #pragma unroll
-	   for (int k = 0; k < kFeGpt; k ++) dcs [k] = sRaw [tid * kFeGpt + k];
+	   for (int k = 0; k < kFeGpt; k ++) dcs [k] = raw_block_total (sRaw, tid * kFeGpt + k);
 	}
 	if (m0 + kFeGpt <= M && (out_pitch & 1) == 0) {
 	   float4 *u4 = reinterpret_cast<float4 *>(Us + m0);
@@ -209,8 +238,8 @@ frontend_wide_kernel (const float2 *__restrict__ x, int64_t in_pitch,
                       float2 *__restrict__ U, float2 *__restrict__ S,
                       int64_t out_pitch, int32_t M, const LoParams lop) {
 extern __shared__ float2 sm [];
-__shared__ float2 sRaw [LO ? kFeTileOut : 1];
-	if (LO) { for (int i = threadIdx.x; i < kFeTileOut; i += kFeThreads) sRaw [i] = make_float2 (0.f, 0.f); __syncthreads (); }
+__shared__ float2 sRaw [LO ? kFeTileOut * kRawSlots : 1];
+	if (LO) { for (int i = threadIdx.x; i < kFeTileOut * kRawSlots; i += kFeThreads) sRaw [i] = make_float2 (0.f, 0.f); __syncthreads (); }
 const int tid    = threadIdx.x;
 const int stream = blockIdx.y;
 const int64_t out0 = (int64_t)blockIdx.x * kFeTileOut;
@@ -238,7 +267,7 @@ int32_t loIdx = LO ? lo_index (lop, in0 + tid) : 0;
 	      v [k] = (n < N) ? __ldcs (xs + n) : make_float2 (0.f, 0.f);
 	      if (LO) {
 	         // the RF DC estimate follows the RAW samples: block sums before gain and rotation
-	         atomicAdd (&sRaw [j / kDecim].x, v [k].x); atomicAdd (&sRaw [j / kDecim].y, v [k].y);
+	         raw_block_sum (sRaw, j, v [k], kDecim);
 	         v [k] = lo_apply (lop, v [k], loIdx);
 	         loIdx -= lop.step128; if (loIdx < 0) loIdx += lop.rate;
 	      }
@@ -286,7 +315,7 @@ float2 *Us = U + (int64_t)stream * out_pitch;
 float2 *Ss = S + (int64_t)stream * out_pitch;
 #pragma unroll
 	for (int k = 0; k < kFeGpt; k ++)
-	   if (m0 + k < M) { Us [m0 + k] = acc [k]; Ss [m0 + k] = LO ? sRaw [tid * kFeGpt + k] : dcs [k]; }
+	   if (m0 + k < M) { Us [m0 + k] = acc [k]; Ss [m0 + k] = LO ? raw_block_total (sRaw, tid * kFeGpt + k) : dcs [k]; }
 }
 
 // fm-rate delay line: out[m] = (hist | in)[m], new_hist = the last D entries of (hist | in)

@@ -105,8 +105,8 @@ struct Poly {
 	static constexpr int HaloIn  = Halo * Rows;                    // raw samples before the tile
 	static constexpr int SmemBytes = Rows * Pitch * (int)sizeof (float2);
 	static constexpr int Batch   = poly_batch (Rows);
-	static constexpr int MinCtas = (200 * 1024) / (SmemBytes + TileOut * 8 + 1024) > 4 ? 4
-	                             : (200 * 1024) / (SmemBytes + TileOut * 8 + 1024);
+	static constexpr int MinCtas = (200 * 1024) / (SmemBytes + TileOut * 24 + 1024) > 4 ? 4
+	                             : (200 * 1024) / (SmemBytes + TileOut * 24 + 1024);
 	static_assert (D * NG <= kPolyMaxTaps, "tap table too small");
 	static_assert (Rows % Batch == 0, "batching");
 };
@@ -138,7 +138,7 @@ int32_t loIdx = lo ? lo_index (lop, in0 + tid) : 0;
 	      for (int k = 0; k < P::Batch; k ++) {
 	         const int j = (b * P::Batch + k) * kFeThreads + tid;
 	         // the RF DC estimate follows the RAW samples: block sums before gain and rotation
-	         atomicAdd (&sRaw [j / P::D].x, v [k].x); atomicAdd (&sRaw [j / P::D].y, v [k].y);
+	         raw_block_sum (sRaw, j, v [k], P::D);
 	         v [k] = lo_apply (lop, v [k], loIdx);
 	         loIdx -= lop.step128; if (loIdx < 0) loIdx += lop.rate;
 	      }
@@ -164,11 +164,11 @@ frontend_poly_kernel (const void *__restrict__ x, int64_t in_pitch, RawFmt rf,
                       int64_t out_pitch, int32_t M, const LoParams lop) {
 typedef Poly<D, GPT, NG> P;
 extern __shared__ float2 sm [];
-__shared__ float2 sRaw [P::TileOut];
+__shared__ float2 sRaw [P::TileOut * kRawSlots];
 const int tid    = threadIdx.x;
 const int stream = blockIdx.y;
 const bool lo    = lop.tab != nullptr;
-	if (lo) { for (int i = tid; i < P::TileOut; i += kFeThreads) sRaw [i] = make_float2 (0.f, 0.f); __syncthreads (); }
+	if (lo) { for (int i = tid; i < P::TileOut * kRawSlots; i += kFeThreads) sRaw [i] = make_float2 (0.f, 0.f); __syncthreads (); }
 const int64_t out0 = (int64_t)blockIdx.x * P::TileOut;
 const int64_t in0  = out0 * D;
 const int64_t N    = (int64_t)M * D;
@@ -219,7 +219,7 @@ float2 *Us = U + (int64_t)stream * out_pitch;
 float2 *Ss = S + (int64_t)stream * out_pitch;
 	if (lo) {
 #pragma unroll
-	   for (int k = 0; k < GPT; k ++) dcs [k] = sRaw [tid * GPT + k];
+	   for (int k = 0; k < GPT; k ++) dcs [k] = raw_block_total (sRaw, tid * GPT + k);
 	}
 	if (GPT % 2 == 0 && m0 + GPT <= M && (out_pitch & 1) == 0) {
 #pragma unroll

@@ -296,3 +296,46 @@ def test_airspy_native_rate_conversion(pkg, signals, checker, monkeypatch, nativ
     print(native, "audio192 vs reference on the handler's floats", rms(a["audio192"] - ref["audio192"]))
     assert rms(a["audio192"] - ref["audio192"]) < 1e-5 and rms(a["demod"] - ref["demod"]) < 1e-5
     assert np.array_equal(a["locked"], ref["locked"])
+
+
+@pytest.mark.parametrize("name,rate,mode,cfg,raw", [
+    ("input_filter", 2304000, 0, dict(fm_mode=0, rds_on=1, input_filter_hz=165000), None),
+    ("local_oscillator", 2304000, 0, dict(fm_mode=0, rds_on=1, lo_hz=30000), None),
+    ("rate_6M", 6000000, 0, dict(fm_mode=0, rds_on=1), None),
+    ("resampler_2p4M", 2400000, 1, dict(fm_mode=0, rds_on=1), None),
+    ("u8", 2304000, 0, dict(fm_mode=0, rds_on=1), ("u8", 128)),
+    ("squelch_audio_lp", 2304000, 0, dict(fm_mode=0, rds_on=1, squelch_mode=1, squelch_value=50, lf_cutoff_hz=15000), None),
+])
+def test_copies_of_a_stream_are_bit_identical_across_lanes(pkg, signals, name, rate, mode, cfg, raw):
+    """determinism under concurrency: 130 streams (4 lanes, RDS side streams) carrying two distinct
+    signals in a shuffled order, two calls; every copy of a signal must give bit-identical audio and
+    RDS output wherever it runs (a race between a lane's kernels and the others' shows up here, not
+    in a tolerance test)."""
+    S = 130
+    D = (rate // 192000) if mode == 1 else pkg.front_end_decimation(rate)
+    n = D * 48000 + 5 * D
+    fs = rate if mode == 1 else 192000 * D
+    base = [signals.batch_stream(60 + k, 2 * n, fs=fs) for k in range(2)]
+    order = np.random.default_rng(11).permutation(S) % 2
+    p = pkg.FmProcessorB200(n_streams=S, input_rate=rate, max_samples_per_call=n, keep_taps=False, front_end_mode=mode)
+    p.configure(volume_db=-6.0, **cfg)
+    p.setRdsSymbolStage(True)
+    outs = []
+    for c in range(2):
+        x = np.stack([base[k][c * n:(c + 1) * n] for k in order])
+        if raw:
+            q, _, den = _quantise(x, raw[0])
+            a, r = p.process_raw(q, raw[0], den)
+        else:
+            a, r = p.process(x)
+        bits = [p.read_rds_bits(s) for s in range(S)]
+        outs.append((a, r, bits))
+    p.close()
+    for a, r, bits in outs:
+        for k in range(2):
+            idx = np.nonzero(order == k)[0]
+            for i in idx[1:]:
+                assert np.array_equal(a[i].view(np.uint64), a[idx[0]].view(np.uint64)), (name, k, i)
+                assert np.array_equal(r[i].view(np.uint64), r[idx[0]].view(np.uint64)), (name, k, i)
+                assert np.array_equal(bits[i], bits[idx[0]]), (name, k, i)
+        assert not np.array_equal(a[np.nonzero(order == 0)[0][0]], a[np.nonzero(order == 1)[0][0]])
