@@ -105,8 +105,8 @@ struct Poly {
 	static constexpr int HaloIn  = Halo * Rows;                    // raw samples before the tile
 	static constexpr int SmemBytes = Rows * Pitch * (int)sizeof (float2);
 	static constexpr int Batch   = poly_batch (Rows);
-	static constexpr int MinCtas = (200 * 1024) / (SmemBytes + TileOut * 24 + 1024) > 4 ? 4
-	                             : (200 * 1024) / (SmemBytes + TileOut * 24 + 1024);
+	static constexpr int RawBytes = TileOut * kRawSlots * (int)sizeof (float2);   // oscillator on: raw block-sum slots behind the tile
+	static constexpr int MinCtas = (200 * 1024) / (SmemBytes + 1024) > 4 ? 4 : (200 * 1024) / (SmemBytes + 1024);
 	static_assert (D * NG <= kPolyMaxTaps, "tap table too small");
 	static_assert (Rows % Batch == 0, "batching");
 };
@@ -161,20 +161,20 @@ __global__ void __launch_bounds__ (kFeThreads, Poly<D, GPT, NG>::MinCtas)
 frontend_poly_kernel (const void *__restrict__ x, int64_t in_pitch, RawFmt rf,
                       const float2 *__restrict__ hist, int hist_len,
                       float2 *__restrict__ U, float2 *__restrict__ S,
-                      int64_t out_pitch, int32_t M, const LoParams lop) {
+                      int64_t out_pitch, int32_t M, const LoParams lop, int32_t tile0) {
 typedef Poly<D, GPT, NG> P;
 extern __shared__ float2 sm [];
-__shared__ float2 sRaw [P::TileOut * kRawSlots];
+float2 *sRaw = sm + P::Rows * P::Pitch;              // present only when the oscillator is on (launch adds RawBytes)
 const int tid    = threadIdx.x;
 const int stream = blockIdx.y;
 const bool lo    = lop.tab != nullptr;
 	if (lo) { for (int i = tid; i < P::TileOut * kRawSlots; i += kFeThreads) sRaw [i] = make_float2 (0.f, 0.f); __syncthreads (); }
-const int64_t out0 = (int64_t)blockIdx.x * P::TileOut;
+const int64_t out0 = (int64_t)(blockIdx.x + tile0) * P::TileOut;      // tile0: the tiles before it were done by K1t
 const int64_t in0  = out0 * D;
 const int64_t N    = (int64_t)M * D;
 const void *xs = reinterpret_cast<const char *>(x) + (int64_t)stream * in_pitch * fmt_bytes (rf.fmt);
 const float2 *hs = hist + (int64_t)stream * hist_len + (hist_len - P::HaloIn);
-const bool first = blockIdx.x == 0;
+const bool first = blockIdx.x + tile0 == 0;
 	switch (rf.fmt) {
 	   case kFmtU8:  poly_stage<P, kFmtU8>  (sm, sRaw, xs, in0, N, hs, first, lop, lo, rf, tid); break;
 	   case kFmtS8:  poly_stage<P, kFmtS8>  (sm, sRaw, xs, in0, N, hs, first, lop, lo, rf, tid); break;

@@ -21,6 +21,7 @@
 #include <cuda.h>
 #include "common.cuh"
 #include "frontend_fir.cuh"
+#include "frontend_poly.cuh"
 
 namespace sdrjfm {
 
@@ -52,37 +53,47 @@ __device__ __forceinline__ void tma_load_4d (uint32_t dst, const CUtensorMap *ma
 	                 "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
-// one sample at row-local position j (own row: 0..47, previous row: -26..-1) into the four outputs;
+// The kernel is instantiated for the shapes whose row (D * GPT samples) is 48 samples = 384 bytes:
+// (D, GPT, NT) = (12, 4, 37) — 2.304 / 2.4 MS/s — and (48, 1, 73) — 10 MS/s.
+// tap i of the composite: c_comp for D = 12, the K1g layout c_poly[p][g] (NG = 2) for D = 48
+template <int D>
+__device__ __forceinline__ float ft_tap (const int i) {
+	return D == kDecim ? c_comp [i] : c_poly [(D - 1 - i % D) * 2 + i / D];
+}
+
+// one sample at row-local position j (own row: 0..47, previous row: -26..-1) into the GPT outputs;
 // j is a compile-time constant at every call site (fully unrolled loops), so the tap test and the
 // constant-bank index fold away
-__device__ __forceinline__ void ft_accum (const int j, float2 v, float2 (&acc) [kFeGpt], float2 (&dcs) [kFeGpt]) {
+template <int D, int GPT, int NT>
+__device__ __forceinline__ void ft_accum (const int j, float2 v, float2 (&acc) [GPT], float2 (&dcs) [GPT]) {
 #pragma unroll
-	for (int k = 0; k < kFeGpt; k ++) {
-	   const int i = kDecim * k + kDecim - 1 - j;            // tap index
-	   if (i >= 0 && i <= 36) acc [k] = ffma2 (c_comp [i], v, acc [k]);
+	for (int k = 0; k < GPT; k ++) {
+	   const int i = D * k + D - 1 - j;                      // tap index
+	   if (i >= 0 && i < NT) acc [k] = ffma2 (ft_tap<D> (i), v, acc [k]);
 	}
-	if (j >= 0) { dcs [j / kDecim].x += v.x; dcs [j / kDecim].y += v.y; }
+	if (j >= 0) { dcs [j / D].x += v.x; dcs [j / D].y += v.y; }
 }
 
 // chunks LC0 .. LC0 + N - 1 of the row whose first 128-byte line is line0; chunk lc holds the
 // row-local samples 2 lc and 2 lc + 1 (+ JOFF: -48 for the previous row).  Physical address of chunk
 // q of line L under the 128-byte swizzle: L * 128 + ((q ^ (L & 7)) << 4).
-template <int LC0, int N, int JOFF>
+template <int D, int GPT, int NT, int LC0, int N, int JOFF>
 __device__ __forceinline__ void ft_row (const unsigned char *stage, int line0,
-                                        float2 (&acc) [kFeGpt], float2 (&dcs) [kFeGpt]) {
+                                        float2 (&acc) [GPT], float2 (&dcs) [GPT]) {
 #pragma unroll
 	for (int n = 0; n < N; n ++) {
 	   const int lc = LC0 + n, c = lc >> 3, q = lc & 7;
 	   const int L = line0 + c;
 	   const float4 v = *reinterpret_cast<const float4 *>(stage + L * 128 + ((q ^ (L & 7)) << 4));
-	   ft_accum (2 * lc + JOFF, make_float2 (v.x, v.y), acc, dcs);
-	   ft_accum (2 * lc + 1 + JOFF, make_float2 (v.z, v.w), acc, dcs);
+	   ft_accum<D, GPT, NT> (2 * lc + JOFF, make_float2 (v.x, v.y), acc, dcs);
+	   ft_accum<D, GPT, NT> (2 * lc + 1 + JOFF, make_float2 (v.z, v.w), acc, dcs);
 	}
 }
 
 // map  : 4-D tensor map over this call's samples, dims (innermost first) [32 floats][3][rows][streams]
 // hist : [n_streams][hist_len] the raw samples preceding x[.][0] (the last 36 are used)
-// U, S : [n_streams][out_pitch]; tiles_per_stream whole tiles (512 outputs each) are produced
+// U, S : [n_streams][out_pitch]; tiles_per_stream whole tiles (128 GPT outputs each) are produced
+template <int D, int GPT, int NT>
 __global__ void __launch_bounds__ (kFeThreads, 2)
 frontend_tma_kernel (const __grid_constant__ CUtensorMap map,
                      const float2 *__restrict__ hist, int hist_len,
@@ -121,13 +132,14 @@ int it = 0;
 	   while (!mbar_try_wait (&sFull [s], parity)) { }
 	   const unsigned char *stage = ring + s * kFtStageStride;
 
-	   float2 acc [kFeGpt], dcs [kFeGpt];
+	   static_assert (D * GPT == kFtRowSamples && NT - D <= 26, "row of 48 samples, history within the previous row's last 26");
+	   float2 acc [GPT], dcs [GPT];
 #pragma unroll
-	   for (int k = 0; k < kFeGpt; k ++) { acc [k] = make_float2 (0.f, 0.f); dcs [k] = make_float2 (0.f, 0.f); }
+	   for (int k = 0; k < GPT; k ++) { acc [k] = make_float2 (0.f, 0.f); dcs [k] = make_float2 (0.f, 0.f); }
 //	   box row tid = the row before this thread's outputs (samples -25..-1 matter: chunks 11..23),
 //	   box row tid + 1 = its own 48 samples
-	   ft_row<11, 13, -kFtRowSamples> (stage, tid * 3, acc, dcs);
-	   ft_row<0, 24, 0> (stage, (tid + 1) * 3, acc, dcs);
+	   ft_row<D, GPT, NT, 11, 13, -kFtRowSamples> (stage, tid * 3, acc, dcs);
+	   ft_row<D, GPT, NT, 0, 24, 0> (stage, (tid + 1) * 3, acc, dcs);
 //	   The next TMA write into this stage is an async-proxy access; this thread's shared loads are
 //	   generic-proxy accesses that may still be in flight when it reaches the barrier (their consumers
 //	   can be scheduled behind it).  The proxy fence orders them before anything the async proxy does
@@ -146,18 +158,25 @@ int it = 0;
 	      if (tile == 0) {
 //	         the row before the first tile of the call was zero-filled: add the carried history
 	         const float2 *hs = hist + (int64_t)stream * hist_len + hist_len;       // hs[j], j = -36..-1
-	         for (int k = 0; k < 3; k ++)
-	            for (int i = kDecim * k + kDecim; i <= 36; i ++)
-	               acc [k] = ffma2 (c_comp [i], hs [kDecim * k + kDecim - 1 - i], acc [k]);
+#pragma unroll
+	         for (int k = 0; k < GPT; k ++)
+	            for (int i = D * k + D; i < NT; i ++)
+	               acc [k] = ffma2 (ft_tap<D> (i), hs [D * k + D - 1 - i], acc [k]);
 	      }
 	   }
-	   const int64_t m0 = (int64_t)tile * kFeTileOut + (int64_t)tid * kFeGpt;
-	   float4 *u4 = reinterpret_cast<float4 *>(U + (int64_t)stream * out_pitch + m0);
-	   float4 *s4 = reinterpret_cast<float4 *>(S + (int64_t)stream * out_pitch + m0);
-	   u4 [0] = make_float4 (acc [0].x, acc [0].y, acc [1].x, acc [1].y);
-	   u4 [1] = make_float4 (acc [2].x, acc [2].y, acc [3].x, acc [3].y);
-	   s4 [0] = make_float4 (dcs [0].x, dcs [0].y, dcs [1].x, dcs [1].y);
-	   s4 [1] = make_float4 (dcs [2].x, dcs [2].y, dcs [3].x, dcs [3].y);
+	   const int64_t m0 = ((int64_t)tile * kFeThreads + tid) * GPT;
+	   float2 *up = U + (int64_t)stream * out_pitch + m0, *sp = S + (int64_t)stream * out_pitch + m0;
+	   if (GPT == 4) {
+	      float4 *u4 = reinterpret_cast<float4 *>(up), *s4 = reinterpret_cast<float4 *>(sp);
+	      u4 [0] = make_float4 (acc [0].x, acc [0].y, acc [GPT > 1 ? 1 : 0].x, acc [GPT > 1 ? 1 : 0].y);
+	      u4 [1] = make_float4 (acc [GPT > 2 ? 2 : 0].x, acc [GPT > 2 ? 2 : 0].y, acc [GPT > 3 ? 3 : 0].x, acc [GPT > 3 ? 3 : 0].y);
+	      s4 [0] = make_float4 (dcs [0].x, dcs [0].y, dcs [GPT > 1 ? 1 : 0].x, dcs [GPT > 1 ? 1 : 0].y);
+	      s4 [1] = make_float4 (dcs [GPT > 2 ? 2 : 0].x, dcs [GPT > 2 ? 2 : 0].y, dcs [GPT > 3 ? 3 : 0].x, dcs [GPT > 3 ? 3 : 0].y);
+	   }
+	   else {
+#pragma unroll
+	      for (int k = 0; k < GPT; k ++) { up [k] = acc [k]; sp [k] = dcs [k]; }
+	   }
 	}
 }
 

@@ -554,7 +554,9 @@ cudaError_t e;
 	                               kFeSmemBytes)) != cudaSuccess ||
 	    (e = cudaFuncSetAttribute (frontend_fir_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                               kFeSmemBytes)) != cudaSuccess ||
-	    (e = cudaFuncSetAttribute (frontend_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    (e = cudaFuncSetAttribute (frontend_tma_kernel<kDecim, kFeGpt, 37>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                               kFtSmemBytes)) != cudaSuccess ||
+	    (e = cudaFuncSetAttribute (frontend_tma_kernel<48, 1, 73>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                               kFtSmemBytes)) != cudaSuccess) return fail (e, "smem attr K1");
 	if ((e = poly_set_attr (shape)) != cudaSuccess) return fail (e, "smem attr K1g");
 	{  const int seqsm = (cfg -> fm_rate / 4 + 1) * (int)sizeof (float);
@@ -642,7 +644,7 @@ static TmaEncodeFn fn = [] () -> TmaEncodeFn {
 // ---- K1g dispatch over the instantiated shapes ---------------------------------------------
 template <int D, int GPT, int NG> static cudaError_t poly_attr_one () {
 	return cudaFuncSetAttribute (frontend_poly_kernel<D, GPT, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                             Poly<D, GPT, NG>::SmemBytes);
+	                             Poly<D, GPT, NG>::SmemBytes + Poly<D, GPT, NG>::RawBytes);
 }
 static cudaError_t poly_set_attr (int shape) {
 cudaError_t e;
@@ -656,11 +658,35 @@ cudaError_t e;
 }
 template <int D, int GPT, int NG>
 static void poly_launch (Lane *h, const void *src, int64_t pitch, RawFmt rf, const float2 *hist, int hist_len,
-                         float2 *U, float2 *Sb, int32_t M, const LoParams &lp) {
+                         float2 *U, float2 *Sb, int32_t M, const LoParams &lp, int32_t tile0 = 0) {
 typedef Poly<D, GPT, NG> P;
-dim3 grid ((unsigned)((M + P::TileOut - 1) / P::TileOut), (unsigned)h -> cfg.n_streams);
-	frontend_poly_kernel<D, GPT, NG><<<grid, kFeThreads, P::SmemBytes, h -> stream>>> (
-	      src, pitch, rf, hist, hist_len, U, Sb, h -> resample ? h -> cap_a : h -> cap_fm, M, lp);
+dim3 grid ((unsigned)((M + P::TileOut - 1) / P::TileOut - tile0), (unsigned)h -> cfg.n_streams);
+	frontend_poly_kernel<D, GPT, NG><<<grid, kFeThreads, P::SmemBytes + (lp.tab ? P::RawBytes : 0), h -> stream>>> (
+	      src, pitch, rf, hist, hist_len, U, Sb, h -> resample ? h -> cap_a : h -> cap_fm, M, lp, tile0);
+}
+
+// K1t over the whole tiles of a call (complex float, aligned rows, oscillator and inputFilter off);
+// returns the number of tiles per stream it produced (0: not applicable), the caller runs the rest
+template <int D, int GPT, int NT>
+static int32_t tma_launch (Lane *h, const float2 *x, int64_t pitch, int32_t M, const float2 *hist, int hlen,
+                           float2 *U, float2 *Sb) {
+const int S = h -> cfg.n_streams;
+const int32_t tileOut = kFeThreads * GPT;
+	if (!h -> use_tma || M < tileOut || ((uintptr_t)x & 15) != 0 || (pitch & 1) != 0 || !tma_encoder ()) return 0;
+const int32_t tiles = M / tileOut;
+CUtensorMap map;
+const cuuint64_t gdim [4] = { 32, 3, (cuuint64_t)tiles * kFtRows, (cuuint64_t)S };
+const cuuint64_t gstr [3] = { 128, 384, (cuuint64_t)pitch * sizeof (float2) };
+const cuuint32_t box [4] = { 32, 3, kFtBoxRows, 1 };
+const cuuint32_t estr [4] = { 1, 1, 1, 1 };
+	if (tma_encoder () (&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)x, gdim, gstr, box, estr,
+	                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+	                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return 0;
+const int64_t total = (int64_t)tiles * S;
+const unsigned g = (unsigned)std::min<int64_t> (total, (int64_t)h -> tma_ctas);
+	frontend_tma_kernel<D, GPT, NT><<<g, kFeThreads, kFtSmemBytes, h -> stream>>> (map, hist, hlen, U, Sb, h -> cap_fm, tiles, S);
+	h -> launches ++;
+	return tiles;
 }
 
 static int launch_frontend (Lane *h, const void *src, RawFmt rf, int64_t pitch, int32_t M) {
@@ -695,32 +721,23 @@ float2 *U = wide ? h -> d_Uw : h -> d_U, *Sb = wide ? h -> d_Sw : h -> d_S;
 	            x, pitch, hist, hlen, U, Sb, h -> cap_fm, M, lp, 0);
 	   else {
 //	      whole 512-output tiles through TMA (K1t), the ragged last tile through the plain kernel
-	      int32_t tiles = 0;
-	      CUtensorMap map;
-	      if (h -> use_tma && M >= kFeTileOut && ((uintptr_t)x & 15) == 0 && (pitch & 1) == 0 && tma_encoder ()) {
-	         tiles = M / kFeTileOut;
-	         const cuuint64_t gdim [4] = { 32, 3, (cuuint64_t)tiles * kFtRows, (cuuint64_t)S };
-	         const cuuint64_t gstr [3] = { 128, 384, (cuuint64_t)pitch * sizeof (float2) };
-	         const cuuint32_t box [4] = { 32, 3, kFtBoxRows, 1 };
-	         const cuuint32_t estr [4] = { 1, 1, 1, 1 };
-	         const CUresult r = tma_encoder () (&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)x, gdim, gstr, box, estr,
-	               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-	               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-	         if (r != CUDA_SUCCESS) tiles = 0;
-	      }
+	      const int32_t tiles = tma_launch<kDecim, kFeGpt, 37> (h, x, pitch, M, hist, hlen, U, Sb);
 	      if (tiles > 0) {
-	         const int64_t total = (int64_t)tiles * S;
-	         const unsigned g = (unsigned)std::min<int64_t> (total, (int64_t)h -> tma_ctas);
-	         frontend_tma_kernel<<<g, kFeThreads, kFtSmemBytes, h -> stream>>> (map, hist, hlen, U, Sb, h -> cap_fm, tiles, S);
-	         if (M % kFeTileOut) {
+	         if (M % kFeTileOut)
 	            frontend_fir_kernel<false><<<dim3 (1, S), kFeThreads, kFeSmemBytes, h -> stream>>> (
 	                  x, pitch, hist, hlen, U, Sb, h -> cap_fm, M, lp, tiles);
-	            h -> launches ++;
-	         }
+	         else h -> launches --;                          // (counted once below)
 	      }
 	      else frontend_fir_kernel<false><<<grid, kFeThreads, kFeSmemBytes, h -> stream>>> (
 	            x, pitch, hist, hlen, U, Sb, h -> cap_fm, M, lp, 0);
 	   }
+	}
+	else if (h -> shape == 2 && !wide && !lo && rf.fmt == kFmtCF32 && !h -> force_generic) {
+//	   10 MS/s complex float: the same TMA kernel with one output per row (48 = D samples, 73 taps)
+	   const int32_t tiles = tma_launch<48, 1, 73> (h, (const float2 *)src, pitch, M, hist, hlen, U, Sb);
+	   if (tiles == 0) poly_launch<48, 1, 2> (h, src, pitch, rf, hist, hlen, U, Sb, M, lp);
+	   else if (M % kFeThreads) poly_launch<48, 1, 2> (h, src, pitch, rf, hist, hlen, U, Sb, M, lp, tiles);
+	   else h -> launches --;
 	}
 	else switch (h -> shape * 2 + (wide ? 1 : 0)) {
 	   case 0: poly_launch<12, 4, 4>  (h, src, pitch, rf, hist, hlen, U, Sb, M, lp); break;

@@ -140,7 +140,7 @@ def test_device_sample_formats_equal_handler_conversion(pkg, signals, checker, f
     a = run_gpu(pkg, raw, fs, chunks=chunks, raw=(fmt.split("/")[0], den), **cfg)
     b = run_gpu(pkg, xf, fs, chunks=chunks, **cfg)
     for k in ("fm_z", "demod", "audio192"):
-        if D == 12:
+        if D in (12, 48):
             # float path = K1t (TMA), raw path = K1g: same taps, different summation order; behind the
             # discriminator a last-bit difference can flip an atan-table index (7.9e-5 per flip)
             assert rms(a[k] - b[k]) < (1e-6 if k == "fm_z" else 5e-6), k
