@@ -189,6 +189,23 @@ int  sdrjfm_set_local_oscillator (sdrjfm_handle *h, int32_t hz);   /* set_localO
  * (:886-904); the reference's test is  signal - noise > thresHold  (a constructor argument).        */
 int  sdrjfm_set_scanning (sdrjfm_handle *h, int32_t on);
 int64_t sdrjfm_read_scan (sdrjfm_handle *h, int32_t stream, float *db_pairs, int64_t cap_pairs);
+/* setlfPlotType (src/fm/fm-processor.cpp:244-266; enum ELfPlot, includes/fm/fm-processor.h:84-86): selects the
+ * stream the processor pushes into spectrumBuffer_lf / lfBuffer for the LF scope (:565-627, :651-658).
+ * -1 (default) = no scope stream, nothing extra is kept.  sdrjfm_read_lf_plot returns, for one stream, the
+ * complex samples the LAST process call pushed (interleaved re, im; real-valued types as (x, 0)): one per
+ * fm-rate sample, or one per 24 kHz sample for RDS_INPUT / RDS_DEMOD while the RDS branch is on.
+ * *sample_rate / *show_full = spectrumSampleRate / showFullSpectrum of the selected type.  The adapter cuts
+ * the stream into spectrumSize blocks for ls_scope::processLFSpectrum.  RDS_DEMOD needs the
+ * RDS symbol stage.  While a scope stream is selected, host calls are not cut into pipelined time slices.  */
+enum sdrjfm_lf_plot {
+    SDRJFM_LFPLOT_NONE = -1, SDRJFM_LFPLOT_OFF = 0, SDRJFM_LFPLOT_IF_FILTERED = 1, SDRJFM_LFPLOT_DEMODULATOR = 2,
+    SDRJFM_LFPLOT_AF_SUM = 3, SDRJFM_LFPLOT_AF_DIFF = 4, SDRJFM_LFPLOT_AF_MONO_FILTERED = 5,
+    SDRJFM_LFPLOT_AF_LEFT_FILTERED = 6, SDRJFM_LFPLOT_AF_RIGHT_FILTERED = 7, SDRJFM_LFPLOT_RDS_INPUT = 8,
+    SDRJFM_LFPLOT_RDS_DEMOD = 9
+};
+int  sdrjfm_set_lf_plot_type (sdrjfm_handle *h, int32_t type);
+int64_t sdrjfm_read_lf_plot (sdrjfm_handle *h, int32_t stream, float *out_complex, int64_t cap,
+                             int32_t *sample_rate, int32_t *show_full);
 int  sdrjfm_set_rds_symbol_stage (sdrjfm_handle *h, int32_t on);
 int64_t sdrjfm_read_rds_bits (sdrjfm_handle *h, int32_t stream, uint8_t *bits, int64_t cap);
 int  sdrjfm_set_squelch_mode (sdrjfm_handle *h, int32_t mode);     /* set_squelchMode: 0 OFF, 1 NSQ (noise), 2 LSQ (level) */

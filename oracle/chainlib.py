@@ -187,6 +187,17 @@ class Rds1:
         return a[:n].copy()
 
 
+def ref_rds1_mag(rds24, rate=24000):
+    """magCplx = 4 x Costas output per 24 kHz sample (mode RDS_1, fresh loop; ref_ only)."""
+    lib = C.CDLL(_PATHS["ref"])
+    lib.ref_rds1_mag.restype = None
+    lib.ref_rds1_mag.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
+    x = np.ascontiguousarray(rds24, dtype=np.complex64)
+    out = np.zeros(len(x), np.complex64)
+    lib.ref_rds1_mag(rate, x.ctypes.data, len(x), out.ctypes.data)
+    return out
+
+
 def ref_scan_blocks(fm_z):
     """(signal dB, noise dB) per 1024-sample block, computed with the reference's FFT (ref_ only)."""
     lib = C.CDLL(_PATHS["ref"])

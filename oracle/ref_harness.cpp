@@ -430,6 +430,17 @@ int64_t nb = 0;
 	}
 	return nb;
 }
+//	magCplx of rdsDecoder::doDecode in mode RDS_1 (rds-decoder.cpp:75-77): 4 x the Costas output of every
+//	24 kHz sample, from a fresh loop — what the LF scope shows as RDS_DEMOD (fm-processor.cpp:571-573)
+void	ref_rds1_mag (int32_t rate, const float *rds24, int64_t n, float *out) {
+Costas my_costas (rate, 1.0f / 16.0f, 0.02f / 16.0f, 10.0f);
+	for (int64_t i = 0; i < n; i ++) {
+	   DSPCOMPLEX v (rds24 [2 * i], rds24 [2 * i + 1]);
+	   v = my_costas. process_sample (v);
+	   const DSPCOMPLEX m = v * 4.0f;
+	   out [2 * i] = real (m); out [2 * i + 1] = imag (m);
+	}
+}
 int32_t	ref_rds1_dump (void *h, int which, float *out, int32_t cap) {
 RefRds1 *c = (RefRds1 *)h;
 	switch (which) {

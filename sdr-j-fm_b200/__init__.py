@@ -30,6 +30,9 @@ _TAP_DTYPE = dict(fm_z=np.complex64, demod=np.float32, pilot_phase=np.float32,
 
 # device sample formats (enum sdrjfm_iq_format): dtype of one I or Q component
 IQ_FORMAT = dict(cf32=0, u8=1, s8=2, s16=3, airspy=4)
+# enum class ELfPlot, includes/fm/fm-processor.h:84-86
+LF_PLOT = dict(OFF=0, IF_FILTERED=1, DEMODULATOR=2, AF_SUM=3, AF_DIFF=4, AF_MONO_FILTERED=5,
+               AF_LEFT_FILTERED=6, AF_RIGHT_FILTERED=7, RDS_INPUT=8, RDS_DEMOD=9)
 _IQ_DTYPE = {0: np.float32, 1: np.uint8, 2: np.int8, 3: np.int16, 4: np.int16}
 
 
@@ -116,6 +119,10 @@ def lib():
                      "squelch_mode", "squelch_value", "native_rate", "rds_symbol_stage", "scanning", "auto_mono", "pss_mode",
                      "dc_remove"):
             getattr(L, f"sdrjfm_set_{name}").argtypes = [vp, i32]
+        L.sdrjfm_set_lf_plot_type.restype = i32
+        L.sdrjfm_set_lf_plot_type.argtypes = [vp, i32]
+        L.sdrjfm_read_lf_plot.restype = i64
+        L.sdrjfm_read_lf_plot.argtypes = [vp, i32, vp, i64, vp, vp]
         L.sdrjfm_read_scan.restype = i64
         L.sdrjfm_read_scan.argtypes = [vp, i32, vp, i64]
         L.sdrjfm_read_rds_bits.restype = i64
@@ -287,6 +294,20 @@ class FmProcessorB200:
         if n < 0:
             raise SdrjfmError(n, self.L.sdrjfm_last_error(self.h).decode())
         return a[:n].copy()
+
+    def setlfPlotType(self, m):
+        """fmProcessor::setlfPlotType (ELfPlot name or number; None / -1: no scope stream)."""
+        t = -1 if m is None else (LF_PLOT[m] if isinstance(m, str) else int(m))
+        self._ck(self.L.sdrjfm_set_lf_plot_type(self.h, t))
+
+    def read_lf_plot(self, stream=0):
+        """(complex64 samples pushed into spectrumBuffer_lf by the last call, spectrumSampleRate, showFullSpectrum)."""
+        a = np.zeros(self.cfg.max_samples_per_call // self.decim + 8, np.complex64)
+        rate = C.c_int32(0); full = C.c_int32(0)
+        n = self.L.sdrjfm_read_lf_plot(self.h, stream, a.ctypes.data, a.size, C.byref(rate), C.byref(full))
+        if n < 0:
+            raise SdrjfmError(n, self.L.sdrjfm_last_error(self.h).decode())
+        return a[:n].copy(), rate.value, bool(full.value)
 
     def setRdsSymbolStage(self, on): self._ck(self.L.sdrjfm_set_rds_symbol_stage(self.h, int(on)))
 

@@ -44,16 +44,18 @@ struct AudioParams {
 	int32_t fade_cnt, fade_max;
 	int32_t write_tap;         // keep the 192 kHz stream (SDRJFM_TAP_AUDIO192)
 	int32_t sel;               // which de-emphasis state buffer holds the carried state
+	int32_t plot;              // 0, or ELfPlot AF_MONO / AF_LEFT / AF_RIGHT _FILTERED (5 / 6 / 7): scope stream wanted
 };
 
 // lr    : [S][pitch] fm-rate (left, right) of this call
 // hist  : [S][128] de-emphasised, gain-corrected samples preceding this call; new_hist: same, rolled
 // a192  : [S][pitch] tap (optional);  out: [S][out_pitch] working-rate stereo
+// plot  : [S][pitch] the de-emphasised audio BEFORE the gain, as the LF scope sees it (fm-processor.cpp:614-622)
 __global__ void __launch_bounds__ (kAuThreads)
 audio_kernel (const float2 *__restrict__ lr, int64_t pitch, AudioParams P,
               const float2 *__restrict__ hist, float2 *__restrict__ new_hist,
               StreamState *__restrict__ state, float2 *__restrict__ a192,
-              float2 *__restrict__ out, int64_t out_pitch) {
+              float2 *__restrict__ out, int64_t out_pitch, float *__restrict__ plot) {
 // phase-major staging: sample with global index g sits at [(g - G0) & 3][(g - G0) >> 2]
 __shared__ float2 sA [4][kAuSpan / 4 + 2];
 __shared__ float  sWl [kAuThreads / 32], sWr [kAuThreads / 32], sWa [kAuThreads / 32];
@@ -113,6 +115,8 @@ float2 *tap = a192 ? a192 + (int64_t)stream * pitch : nullptr;
 	      yr = fadd (fmul (fsub (x [j].y, yr), P.alpha), yr);
 	      v = make_float2 (fmul (P.gl, yl), fmul (P.gr, yr));       // :304-305
 	      if (tap && n >= t0 && P.write_tap) tap [n] = v;
+	      if (P.plot && n >= t0)
+	         plot [(int64_t)stream * pitch + n] = P.plot == 5 ? fadd (yl, yr) : P.plot == 6 ? yl : yr;
 	      if (n == P.M - 1) { state [stream].deemph [P.sel ^ 1][0] = yl; state [stream].deemph [P.sel ^ 1][1] = yr; }
 	   }
 	   else if (n < 0 && n >= -kRsHist) v = hist [(int64_t)stream * kRsHist + kRsHist + n];

@@ -147,6 +147,11 @@ struct Lane {
 	float2  *d_pss_ring = nullptr;          // [S][2048] PSS filter input ring (state)
 	int32_t *d_iter_stats = nullptr;        // pilot_kernel diagnostics: [S][4]
 	SquelchState *d_sq = nullptr;           // [S], allocated when the squelch is first switched on
+	// LF scope stream (setlfPlotType): -1 = no stream wanted, else ELfPlot; d_plot holds the float streams
+	// the chain does not keep otherwise (diffLR, pre-gain audio) for the last call
+	int32_t  lf_plot = -1;
+	float   *d_plot = nullptr;
+	const float2 *last_rds_ptr = nullptr; int64_t last_rds_pitch = 0;
 	// station scan (startScanning / stopScanning): 1024-sample blocks of fm-rate samples -> (signal, noise) dB
 	bool     scanning = false;
 	float2  *d_scan_carry [2] = { nullptr, nullptr }; int scan_sel = 0, scan_carry = 0;
@@ -883,7 +888,7 @@ const int32_t ntiles = (M + kDiBlock - 1) / kDiBlock;
 	         h -> d_U, h -> d_S, h -> cap_fm, M, dp, T + th.off_atan, T + th.off_arcsine,
 	         h -> d_state, h -> d_tileB, ntiles, h -> d_snap, h -> d_res, h -> d_zabs,
 	         (st.decoder == 2 || st.decoder == 1) ? h -> d_iqn : nullptr,
-	         (h -> cfg.keep_taps || h -> scanning) ? h -> d_fmz : nullptr);
+	         (h -> cfg.keep_taps || h -> scanning || h -> lf_plot == 1) ? h -> d_fmz : nullptr);
 	   h -> launches += 2;
 	}
 	if (h -> scanning) {
@@ -970,7 +975,7 @@ const int dec = st.decoder == 2 ? 1 : st.decoder == 1 ? 2 : 0;
 	   stereo_kernel<<<S, kStThreads, 0, h -> stream>>> (
 	         h -> d_demod, h -> d_phase, h -> d_locked, h -> cap_fm, M, q,
 	         reinterpret_cast<const float2 *>(T + th.off_sincos), h -> d_state, h -> d_pss_ring,
-	         h -> d_lr, h -> d_pssd);
+	         h -> d_lr, h -> d_pssd, h -> lf_plot == 4 ? h -> d_plot : nullptr);
 	   h -> launches ++;
 	}
 //	K5 ------------------------------------------------------------------------------------
@@ -1011,6 +1016,7 @@ const int dec = st.decoder == 2 ? 1 : st.decoder == 1 ? 2 : 0;
 	   h -> rds_hist_sel ^= 1;
 	   h -> rds_total += M;
 	   h -> last_nrds = nout;
+	   h -> last_rds_ptr = rout; h -> last_rds_pitch = rpitch;
 	   if (n_rds) *n_rds = nout;
 	   if (h -> rds_symbols && nout > 0) {
 //	      symbol stage, mode RDS_1 (rds-decoder.cpp:69-82): Costas (rate, 1/16, 0.02/16, 10 Hz) + decoder 1
@@ -1023,7 +1029,8 @@ const int dec = st.decoder == 2 ? 1 : st.decoder == 1 ? 2 : 0;
 	      memcpy (sp2.bp, tab + kRsyMatch + kRsyLp, sizeof sp2.bp);
 	      const int64_t bp = h -> cap_rds;
 	      rds_costas_kernel<<<(S + kRsyLanes - 1) / kRsyLanes, kRsyLanes, 0, rs>>> (
-	            h -> d_rsy_in, bp, nout, S, sp2, h -> d_rsy_state, h -> d_rsy_c, bp);
+	            h -> d_rsy_in, bp, nout, S, sp2, h -> d_rsy_state, h -> d_rsy_c, bp,
+	            h -> lf_plot == 9 ? h -> d_plot : nullptr, h -> cap_fm);
 	      const dim3 gf ((unsigned)((nout + 127) / 128), (unsigned)S);
 	      rds_fir_kernel<kRsyLp, false><<<gf, 128, 0, rs>>> (h -> d_rsy_c, h -> d_rsy_v, bp, nout, sp2, h -> d_rsy_state);
 	      rds_fir_kernel<kRsyMatch, true><<<gf, 128, 0, rs>>> (h -> d_rsy_v, h -> d_rsy_w, bp, nout, sp2, h -> d_rsy_state);
@@ -1058,10 +1065,11 @@ const int64_t apitch = d_audio_out ? audio_pitch : h -> cap_audio;
 	   ap.fade_cnt = h -> fade_cnt; ap.fade_max = h -> fade_max;
 	   ap.write_tap = h -> cfg.keep_taps;
 	   ap.sel = h -> ahist_sel;
+	   ap.plot = (h -> lf_plot >= 5 && h -> lf_plot <= 7) ? h -> lf_plot : 0;
 	   dim3 g ((unsigned)((M + kAuTile - 1) / kAuTile), (unsigned)S);
 	   audio_kernel<<<g, kAuThreads, 0, h -> stream>>> (
 	         lr_in, h -> cap_fm, ap, h -> d_ahist [h -> ahist_sel], h -> d_ahist [h -> ahist_sel ^ 1],
-	         h -> d_state, h -> d_a192, aout, apitch);
+	         h -> d_state, h -> d_a192, aout, apitch, h -> d_plot);
 	   h -> launches ++;
 	   h -> ahist_sel ^= 1;
 	   h -> fade_cnt = h -> fade_cnt > nq ? h -> fade_cnt - nq : 0;
@@ -1344,6 +1352,60 @@ int32_t n = 0;
 	   CK (cudaMemcpyAsync (out, h -> d_rsy_bits + (size_t)stream * h -> cap_bits, n, cudaMemcpyDeviceToHost, h -> stream));
 	   CK (cudaStreamSynchronize (h -> stream));
 	}
+	return n;
+}
+// setlfPlotType (fm-processor.cpp:244-266).  type -1: no scope stream (nothing extra is written)
+static int lane_set_lf_plot_type (Lane *h, int32_t type) {
+	if (!h || type < -1 || type > 9) return SDRJFM_ERR_ARG;
+	CK (cudaSetDevice (h -> cfg.device));
+	if (((type >= 4 && type <= 7) || type == 9) && !h -> d_plot) CK (dalloc (&h -> d_plot, (size_t)h -> cfg.n_streams * h -> cap_fm));
+	h -> lf_plot = type;
+	return SDRJFM_OK;
+}
+// What the LAST process call pushed into spectrumBuffer_lf for one stream (fm-processor.cpp:565-627):
+// complex samples, at the fm rate for every type except RDS_INPUT / RDS_DEMOD with the RDS branch on
+// (24 kHz).  The float streams become (x, 0) exactly as push_back (float) builds them.
+static int64_t lane_read_lf_plot (Lane *h, int32_t stream, float *out, int64_t cap) {
+	if (!h || !out || stream < 0 || stream >= h -> cfg.n_streams) return SDRJFM_ERR_ARG;
+	if (h -> lf_plot < 0) { h -> err = "no LF scope stream selected (sdrjfm_set_lf_plot_type)"; return SDRJFM_ERR_ARG; }
+	if (h -> scanning) return 0;                                          // :478-495: "continue" before the demodulator
+const int type = h -> lf_plot;
+const bool rds_rate = type >= 8 && h -> set.rds_mode != 0;
+int64_t n = rds_rate ? h -> last_nrds : h -> last_nfm;
+	if (n > cap) n = cap;
+	if (n <= 0) return 0;
+	CK (cudaSetDevice (h -> cfg.device));
+const void *src = nullptr; size_t esz = 4; int64_t pitch = h -> cap_fm; float mul = 1.f;
+	switch (type) {
+	   case 0: memset (out, 0, (size_t)n * 8); return n;                  // OFF: zeros
+	   case 1: src = h -> d_fmz; esz = 8; break;                          // IF_FILTERED: v
+	   case 2: case 3: src = h -> d_demod; break;                         // DEMODULATOR, AF_SUM (sumLR = demod, :724-729)
+	   case 4: case 5: case 6: case 7: src = h -> d_plot; break;          // AF_DIFF, AF_*_FILTERED
+	   case 8:                                                            // RDS_INPUT: 20 rdsSample
+	      if (!rds_rate) { memset (out, 0, (size_t)n * 8); return n; }    // RDS off: zeros at the fm rate (:579-586)
+	      src = h -> last_rds_ptr; esz = 8; pitch = h -> last_rds_pitch; mul = 20.f; break;
+	   case 9:                                                            // RDS_DEMOD: magCplx = 4 * Costas output (rds-decoder.cpp:76-77)
+	      if (!rds_rate) { memset (out, 0, (size_t)n * 8); return n; }
+	      if (!h -> rds_symbols) { h -> err = "the RDS_DEMOD scope stream needs the RDS symbol stage (sdrjfm_set_rds_symbol_stage)"; return SDRJFM_ERR_UNSUPPORTED; }
+	      CK (cudaStreamSynchronize (h -> stream_rds));                   // the symbol stage runs past the call's join
+	      {  // real parts from the symbol stage's own buffer, imaginary parts from d_plot
+	         std::vector<float> im ((size_t)n);
+	         CK (cudaMemcpyAsync (out + n, h -> d_rsy_c + (size_t)stream * h -> cap_rds, (size_t)n * 4, cudaMemcpyDeviceToHost, h -> stream));
+	         CK (cudaMemcpyAsync (im.data (), h -> d_plot + (size_t)stream * h -> cap_fm, (size_t)n * 4, cudaMemcpyDeviceToHost, h -> stream));
+	         CK (cudaStreamSynchronize (h -> stream));
+	         for (int64_t i = 0; i < n; i ++) { const float re = out [n + i]; out [2 * i] = re * 4.0f; out [2 * i + 1] = im [i] * 4.0f; }
+	         return n;
+	      }
+	}
+	if (!src) return 0;
+float *dst = esz == 8 ? out : out + n;                                    // floats land in the upper half, then spread
+	CK (cudaMemcpyAsync (dst, (const char *)src + (size_t)stream * pitch * esz, (size_t)n * esz,
+	                     cudaMemcpyDeviceToHost, h -> stream));
+	CK (cudaStreamSynchronize (h -> stream));
+	if (esz == 4)
+	   for (int64_t i = 0; i < n; i ++) { const float v = dst [i]; out [2 * i] = v; out [2 * i + 1] = 0.f; }
+	else if (mul != 1.f)
+	   for (int64_t i = 0; i < 2 * n; i ++) out [i] *= mul;
 	return n;
 }
 // startScanning / stopScanning (fm-processor.cpp:361-367).  scanPointer is a local of run (): it

@@ -318,12 +318,14 @@ struct RdsSymParams {
 
 __global__ void __launch_bounds__ (kRsyLanes)
 rds_costas_kernel (const float2 *__restrict__ rds24, int64_t pitch, int32_t n, int32_t n_streams,
-                   const RdsSymParams P, RdsSymState *__restrict__ state, float *__restrict__ cbuf, int64_t cpitch) {
+                   const RdsSymParams P, RdsSymState *__restrict__ state, float *__restrict__ cbuf, int64_t cpitch,
+                   float *__restrict__ qbuf, int64_t qpitch) {          // qbuf (optional): the imaginary parts, for the RDS_DEMOD scope stream
 const int stream = blockIdx.x * kRsyLanes + threadIdx.x;
 	if (stream >= n_streams) return;
 float freq = state [stream].freq, phase = state [stream].phase;
 const float2 *x = rds24 + (int64_t)stream * pitch;
 float *c = cbuf + (int64_t)stream * cpitch;
+float *qi = qbuf ? qbuf + (int64_t)stream * qpitch : nullptr;
 //	the samples are fetched one chunk ahead, so the loop never waits on global memory
 constexpr int CH = 8;
 float2 cur [CH], nxt [CH];
@@ -344,6 +346,7 @@ float2 cur [CH], nxt [CH];
 	         if (fabsf (freq) > P.freq_limit) freq = 0.f;
 	         phase = pi_constrain (fadd (phase, fadd (freq, fmul (P.alpha, err))));
 	         c [t0 + k] = r.x;
+	         if (qi) qi [t0 + k] = r.y;
 	      }
 	   }
 #pragma unroll

@@ -244,7 +244,7 @@ int64_t kSlices = 16;
 	{ const char *env = getenv ("SDRJFM_SLICES"); if (env && atoi (env) > 0) kSlices = atoi (env); }
 const int64_t unit = 256 * (int64_t)h -> lanes [0] -> decim;
 const int64_t slice = ((n_in / kSlices) / unit) * unit;          // multiple of the decimation
-	if (!h -> cfg.keep_taps && slice >= (1 << 16)) {
+	if (!h -> cfg.keep_taps && h -> lanes [0] -> lf_plot < 0 && slice >= (1 << 16)) {
 	   if (!h -> copy_stream) {
 	      HK (cudaStreamCreateWithFlags (&h -> copy_stream, cudaStreamNonBlocking));
 	      HK (cudaStreamCreateWithFlags (&h -> out_stream, cudaStreamNonBlocking));
@@ -387,6 +387,22 @@ FWD1 (set_squelch_value, int32_t)
 FWD1 (set_native_rate, int32_t)
 FWD1 (set_rds_symbol_stage, int32_t)
 FWD1 (set_scanning, int32_t)
+FWD1 (set_lf_plot_type, int32_t)
+int64_t sdrjfm_read_lf_plot (sdrjfm_handle *h, int32_t stream, float *out, int64_t cap,
+                             int32_t *sample_rate, int32_t *show_full) {
+	if (!h || !out) return SDRJFM_ERR_ARG;
+const int i = lane_of (h, stream);
+	if (i < 0) return SDRJFM_ERR_ARG;
+	HK (cudaStreamSynchronize (h -> stream));
+Lane *l = h -> lanes [i];
+const int64_t n = lane_read_lf_plot (l, stream - h -> first [i], out, cap);
+	if (n < 0) { h -> err = l -> err; return n; }
+//	spectrumSampleRate / showFullSpectrum as setlfPlotType leaves them (fm-processor.cpp:247-263; RDS_RATE = 24000)
+const int t = l -> lf_plot;
+	if (sample_rate) *sample_rate = t == 8 ? 24000 : t == 9 ? 24000 / 16 : h -> cfg.fm_rate;
+	if (show_full) *show_full = (t == 1 || t == 8 || t == 9) ? 1 : 0;
+	return n;
+}
 int64_t sdrjfm_read_scan (sdrjfm_handle *h, int32_t stream, float *out, int64_t cap_pairs) {
 	if (!h || !out) return SDRJFM_ERR_ARG;
 const int i = lane_of (h, stream);

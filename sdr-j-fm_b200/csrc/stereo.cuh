@@ -113,12 +113,13 @@ __device__ __forceinline__ void pss_step (PssState &s, float err, const StereoPa
 
 // demod, phase, locked : K3 outputs.  sincos: the reference SinCos table (cos, sin) x fmRate.
 // ring : [S][2048] past PSS filter inputs (state).  lr: [S][pitch] out.  pssd: tap (optional)
+// diff_out : [S][pitch] diffLR of every sample (optional: the AF_DIFF scope stream, fm-processor.cpp:611-613)
 __global__ void __launch_bounds__ (kStThreads)
 stereo_kernel (const float *__restrict__ demod, const float *__restrict__ phase,
                const uint8_t *__restrict__ locked, int64_t pitch, int32_t M,
                const StereoParams P, const float2 *__restrict__ sincos,
                StreamState *__restrict__ state, float2 *__restrict__ ring_g,
-               float2 *__restrict__ lr, float *__restrict__ pssd) {
+               float2 *__restrict__ lr, float *__restrict__ pssd, float *__restrict__ diff_out) {
 __shared__ float2 sRing [kPssRing];
 __shared__ float  sErr [kStBlock];              // raw re*im per sample of the block
 __shared__ float  sDel [kStBlock + 1];          // pilotDelayPSS BEFORE sample m (entry 0 = carry)
@@ -133,6 +134,7 @@ const float *dm = demod + (int64_t)stream * pitch;
 const float *ph = phase + (int64_t)stream * pitch;
 const uint8_t *lk = locked + (int64_t)stream * pitch;
 float2 *out = lr + (int64_t)stream * pitch;
+float *dtap = diff_out ? diff_out + (int64_t)stream * pitch : nullptr;
 float *tapd = pssd ? pssd + (int64_t)stream * pitch : nullptr;
 float2 *ring = ring_g + (int64_t)stream * kPssRing;
 
@@ -200,6 +202,7 @@ bool curLock = M > 0 ? lk [0] != 0 : false;
 //	   mono / not locked with autoMono: audioOut = (demod, 0), :728-730
 	      for (int m = tid; m < len; m += kStThreads) {
 	         out [p + m] = lr_matrix (dm [p + m], 0.f, P);
+	         if (dtap) dtap [p + m] = 0.f;
 	         if (tapd && P.write_pss_tap) tapd [p + m] = lock0 ? sS.delay : 0.f;
 	      }
 	      __syncthreads ();
@@ -385,6 +388,7 @@ bool curLock = M > 0 ? lk [0] != 0 : false;
 	         // doubling is exact, so this is the single float rounding of osc * d, doubled
 	         const float diff = fmul (2.0f, fmul (osc, d));
 	         out [p + m] = lr_matrix (d, diff, P);
+	         if (dtap) dtap [p + m] = diff;
 	         if (tapd && P.write_pss_tap) {
 	            // pilotDelayPSS after the sample = the value entering the next one
 	            float after;

@@ -504,6 +504,83 @@ def test_station_scan_matches_reference(pkg, signals, chainlib, ref_available):
         assert (d_want.mean() > th) == (name == "station")
 
 
+def test_lf_scope_stream_matches_reference(pkg, signals, chainlib, checker, ref_available):
+    """setlfPlotType (fm-processor.cpp:244-266): for every ELfPlot type the samples the processor pushes
+    into spectrumBuffer_lf (:565-627), read per call without the debug taps and over ragged calls.
+    Expected streams come from the checker's taps: sumLR = demod; diffLR = the selector output in mode
+    S_LEFTminusRIGHT; the pre-gain audio = the 192 kHz audio of a run at 0 dB; RDS_INPUT = 20 rdsSample;
+    RDS_DEMOD = 4 x the reference's Costas loop fed with the 24 kHz baseband."""
+    n = N1 + 16384 * 20 + 1234                   # pilot lock (0.5 s) and the RDS block latency (64000 fm samples) are inside
+    x = signals.batch_stream(3, n)
+    cfg = dict(fm_mode=0, rds_on=1, volume_db=-6.0)
+    ref = checker(**cfg).process(x)
+    ref_diff = checker(**dict(cfg, sound_sel=5)).process(x, taps=("lr",))["lr"].real
+    ref_0db = checker(**dict(cfg, volume_db=0.0)).process(x, taps=("audio192",))["audio192"]
+    want = {
+        "OFF": np.zeros(ref["n_fm"], np.complex64),
+        "IF_FILTERED": ref["fm_z"],
+        "DEMODULATOR": ref["demod"].astype(np.complex64),
+        "AF_SUM": ref["demod"].astype(np.complex64),
+        "AF_DIFF": ref_diff.astype(np.complex64),
+        "AF_MONO_FILTERED": (ref_0db.real + ref_0db.imag).astype(np.complex64),
+        "AF_LEFT_FILTERED": ref_0db.real.astype(np.complex64),
+        "AF_RIGHT_FILTERED": ref_0db.imag.astype(np.complex64),
+        "RDS_INPUT": (np.float32(20.0) * ref["rds24"]).astype(np.complex64),
+    }
+    rates = dict(IF_FILTERED=(192000, True), RDS_INPUT=(24000, True), RDS_DEMOD=(1500, True))
+    chunks = [16384 * 70, 16384, 5, 16384 * 20 + 77, n]
+    for name in list(want) + ["RDS_DEMOD"]:
+        p = pkg.FmProcessorB200(n_streams=2, max_samples_per_call=n, keep_taps=False)
+        p.configure(**cfg)
+        if name == "RDS_DEMOD":
+            p.setRdsSymbolStage(True)
+        p.setlfPlotType(name)
+        got, rds, pos = [], [], 0
+        for c in chunks:
+            if pos >= n:
+                break
+            _, r = p.process(np.stack([x[pos:pos + c]] * 2))
+            v, rate, full = p.read_lf_plot(1)
+            assert (rate, full) == rates.get(name, (192000, False))
+            got.append(v); rds.append(r[1])
+            pos += c
+        p.close()
+        got = np.concatenate(got)
+        if name == "RDS_DEMOD":
+            if not ref_available:
+                continue
+            w = chainlib.ref_rds1_mag(np.concatenate(rds))              # the reference's loop on the GPU's baseband
+        else:
+            w = want[name]
+        assert got.shape == w.shape, (name, got.shape, w.shape)
+        assert name == "OFF" or rms(w [len(w) // 2:]) > 1e-3, name      # a live signal, not zeros against zeros
+        scale = max(rms(w), 1e-3)
+        # fm_z as in the chain tests (relative); RDS_INPUT = 20 x the 24 kHz baseband, itself held to 1e-5
+        tol = 2e-6 if name == "IF_FILTERED" else 20e-5 if name == "RDS_INPUT" else 1e-5
+        e = rms(got - w) / (scale if name in ("IF_FILTERED", "RDS_DEMOD") else 1.0)
+        print(name, "rms error", e, "signal rms", rms(w))
+        assert e < tol, (name, e)
+        if name == "RDS_INPUT":
+            assert np.array_equal(got, np.float32(20.0) * np.concatenate(rds))
+        if name not in ("IF_FILTERED", "RDS_INPUT", "RDS_DEMOD"):
+            assert not got.imag.any()                                    # push_back (float) -> (x, 0)
+    # RDS off: RDS_INPUT pushes zeros at the fm rate (:579-586); no stream selected: reading is an error
+    p = pkg.FmProcessorB200(n_streams=1, max_samples_per_call=n, keep_taps=False)
+    p.configure(fm_mode=0, rds_on=0)
+    with pytest.raises(pkg.SdrjfmError):
+        p.read_lf_plot(0)
+    p.setlfPlotType("RDS_INPUT")
+    p.process(x[:12 * 5000])
+    v, rate, full = p.read_lf_plot(0)
+    assert v.shape == (5000,) and not v.any() and rate == 24000
+    p.setlfPlotType("RDS_DEMOD")
+    p.setfmRdsSelector(1)
+    p.process(x[:12 * 5000])
+    with pytest.raises(pkg.SdrjfmError):                                 # needs the symbol stage
+        p.read_lf_plot(0)
+    p.close()
+
+
 def test_edge_cases_empty_tiny_and_capacity(pkg, signals, checker):
     """empty and one-sample calls, calls shorter than one fm-rate sample, NULL outputs, the capacity
     error — and the stream they leave behind still equals the reference's."""
