@@ -206,6 +206,18 @@ enum sdrjfm_lf_plot {
 int  sdrjfm_set_lf_plot_type (sdrjfm_handle *h, int32_t type);
 int64_t sdrjfm_read_lf_plot (sdrjfm_handle *h, int32_t stream, float *out_complex, int64_t cap,
                              int32_t *sample_rate, int32_t *show_full);
+/* The LF scope's display spectrum on the GPU (optional): what
+ * ls_scope::processLFSpectrum (src/scopes-qwt6/ls-scope.cpp:76-92, window :50-52, mapSpectrum :130-176,
+ * add_to_average :178-193) computes from every spectrumSize block of the selected scope stream, for every
+ * stream of the batch; blocks run across call boundaries.  sdrjfm_set_lf_spectrum (spectrumSize, displaySize,
+ * averageCount as radio.cpp:238-249 passes them; spectrum_size 0 = off); sdrjfm_set_lf_plot_zoom =
+ * setlfPlotZoomFactor (fm-processor.cpp:268-271); sdrjfm_read_lf_spectrum copies displayBuffer
+ * (display_size doubles) of one stream and reports how many blocks the last call completed.  The first
+ * block after a (re)start only primes the average (lfBuffer_newFlag), as in the reference.            */
+int  sdrjfm_set_lf_spectrum (sdrjfm_handle *h, int32_t spectrum_size, int32_t display_size, int32_t average_count);
+int  sdrjfm_set_lf_plot_zoom (sdrjfm_handle *h, int32_t zoom);
+int64_t sdrjfm_read_lf_spectrum (sdrjfm_handle *h, int32_t stream, double *display, int64_t cap,
+                                 int32_t *blocks_in_last_call);
 int  sdrjfm_set_rds_symbol_stage (sdrjfm_handle *h, int32_t on);
 int64_t sdrjfm_read_rds_bits (sdrjfm_handle *h, int32_t stream, uint8_t *bits, int64_t cap);
 int  sdrjfm_set_squelch_mode (sdrjfm_handle *h, int32_t mode);     /* set_squelchMode: 0 OFF, 1 NSQ (noise), 2 LSQ (level) */

@@ -198,6 +198,20 @@ def ref_rds1_mag(rds24, rate=24000):
     return out
 
 
+def ref_lf_spectrum(v, spectrum_size=2048, display_size=512, average_count=5, zoom=1, show_full=False):
+    """ls_scope's displayBuffer after every block of spectrum_size samples of the LF scope stream v
+    (restated around the reference's Fft_transform; ref_ only). Returns float64 [blocks, display_size]."""
+    lib = C.CDLL(_PATHS["ref"])
+    lib.ref_lf_spectrum.restype = C.c_int64
+    lib.ref_lf_spectrum.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                    C.c_int32, C.c_void_p]
+    x = np.ascontiguousarray(v, dtype=np.complex64)
+    out = np.zeros((len(x) // spectrum_size + 1, display_size), np.float64)
+    n = lib.ref_lf_spectrum(x.ctypes.data, len(x), spectrum_size, display_size, average_count, zoom,
+                            int(show_full), out.ctypes.data)
+    return out[:n].copy()
+
+
 def ref_scan_blocks(fm_z):
     """(signal dB, noise dB) per 1024-sample block, computed with the reference's FFT (ref_ only)."""
     lib = C.CDLL(_PATHS["ref"])

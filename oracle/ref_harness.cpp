@@ -492,4 +492,66 @@ int64_t nb = 0;
 	}
 	return nb;
 }
+
+//	---- LF scope display spectrum: ls_scope (src/scopes-qwt6/ls-scope.cpp), restated ------------------
+//	ls-scope.cpp is a Qwt widget class and cannot be compiled here; the arithmetic of its constructor's
+//	window (:50-52), processLFSpectrum (:76-92), mapSpectrum (:130-176) and add_to_average (:178-193) is
+//	restated below around the reference's own Fft_transform.  v: the LF scope stream (complex); one
+//	displayBuffer (display doubles) is written per completed block of spectrumSize samples after the
+//	first (the first block has refresh = true: it only primes the average, :91-92).  Returns the blocks.
+int64_t	ref_lf_spectrum (const float *v, int64_t n, int32_t spectrumSize, int32_t displaySize,
+	                 int32_t averageCount, int32_t zoomFactor, int32_t showFull, double *display_out) {
+std::vector<float> Window (spectrumSize);
+std::vector<std::complex<float>> ftBuffer (spectrumSize);
+std::vector<double> averageBuffer (displaySize, 0.0), displayBuffer (displaySize, 0.0), Y (displaySize);
+	for (int i = 0; i < spectrumSize; i ++)
+	   Window [i] = 0.43 - 0.5 * cos ((2.0 * M_PI * i) / spectrumSize)
+	                     + 0.08 * cos ((4.0 * M_PI * i) / (spectrumSize - 1));
+int64_t nb = 0;
+bool refresh = true;
+	for (int64_t b = 0; (b + 1) * spectrumSize <= n; b ++) {
+	   for (int i = 0; i < spectrumSize; i ++) {
+	      std::complex<float> tmp (v [2 * (b * spectrumSize + i)], v [2 * (b * spectrumSize + i) + 1]);
+	      if (std::isinf (abs (tmp)) || std::isnan (abs (tmp)))
+	         ftBuffer [i] = std::complex<float> (0, 0);
+	      else
+	         ftBuffer [i] = std::complex<float> (real (tmp) * Window [i], imag (tmp) * Window [i]);   // cmul
+	   }
+	   Fft_transform (ftBuffer. data (), spectrumSize, false);
+	   int16_t factor = spectrumSize / displaySize;
+	   factor /= 2;
+	   int32_t zoom = zoomFactor;
+	   if (factor / zoom >= 1) factor /= zoom;
+	   else { zoom = factor; factor = 1; }
+	   if (showFull) {
+	      for (int32_t i = 0; i < displaySize / 2; i ++) {
+	         double f = 0;
+	         for (int32_t j = 0; j < factor; j ++) f += abs (ftBuffer [i * factor + j]);
+	         Y [displaySize / 2 + i] = f / factor;
+	         f = 0;
+	         for (int32_t j = 0; j < factor; j ++) f += abs (ftBuffer [spectrumSize - 1 - (i * factor + j)]);
+	         Y [displaySize / 2 - 1 - i] = f / factor;
+	      }
+	   }
+	   else {
+	      for (int32_t i = 0; i < displaySize; i ++) {
+	         double f = 0;
+	         for (int32_t j = 0; j < factor; j ++) f += abs (ftBuffer [i * factor + j]);
+	         Y [i] = f / factor;
+	      }
+	   }
+	   const double alpha = 1.0 / averageCount, beta = (averageCount - 1.0) / averageCount;
+	   if (refresh) {
+	      for (int32_t i = 0; i < displaySize; i ++) averageBuffer [i] = Y [i];
+	      refresh = false;
+	   }
+	   else {
+	      for (int32_t i = 0; i < displaySize; i ++) averageBuffer [i] = alpha * Y [i] + beta * averageBuffer [i];
+	      for (int32_t i = 0; i < displaySize; i ++) displayBuffer [i] = averageBuffer [i];
+	   }
+	   memcpy (display_out + nb * displaySize, displayBuffer. data (), displaySize * sizeof (double));
+	   nb ++;
+	}
+	return nb;
+}
 }

@@ -123,6 +123,12 @@ def lib():
         L.sdrjfm_set_lf_plot_type.argtypes = [vp, i32]
         L.sdrjfm_read_lf_plot.restype = i64
         L.sdrjfm_read_lf_plot.argtypes = [vp, i32, vp, i64, vp, vp]
+        L.sdrjfm_set_lf_spectrum.restype = i32
+        L.sdrjfm_set_lf_spectrum.argtypes = [vp, i32, i32, i32]
+        L.sdrjfm_set_lf_plot_zoom.restype = i32
+        L.sdrjfm_set_lf_plot_zoom.argtypes = [vp, i32]
+        L.sdrjfm_read_lf_spectrum.restype = i64
+        L.sdrjfm_read_lf_spectrum.argtypes = [vp, i32, vp, i64, vp]
         L.sdrjfm_read_scan.restype = i64
         L.sdrjfm_read_scan.argtypes = [vp, i32, vp, i64]
         L.sdrjfm_read_rds_bits.restype = i64
@@ -308,6 +314,22 @@ class FmProcessorB200:
         if n < 0:
             raise SdrjfmError(n, self.L.sdrjfm_last_error(self.h).decode())
         return a[:n].copy(), rate.value, bool(full.value)
+
+    def setlfPlotZoomFactor(self, zoom): self._ck(self.L.sdrjfm_set_lf_plot_zoom(self.h, int(zoom)))
+
+    def set_lf_spectrum(self, spectrum_size=2048, display_size=512, average_count=5):
+        """ls_scope (spectrumSize, displaySize, averageCount) on the GPU; spectrum_size 0 switches it off."""
+        self._ck(self.L.sdrjfm_set_lf_spectrum(self.h, spectrum_size, display_size, average_count))
+        self._display = display_size
+
+    def read_lf_spectrum(self, stream=0):
+        """(displayBuffer float64 [display_size], blocks completed by the last call)."""
+        a = np.zeros(self._display, np.float64)
+        nb = C.c_int32(0)
+        n = self.L.sdrjfm_read_lf_spectrum(self.h, stream, a.ctypes.data, a.size, C.byref(nb))
+        if n < 0:
+            raise SdrjfmError(n, self.L.sdrjfm_last_error(self.h).decode())
+        return a[:n].copy(), nb.value
 
     def setRdsSymbolStage(self, on): self._ck(self.L.sdrjfm_set_rds_symbol_stage(self.h, int(on)))
 

@@ -39,6 +39,7 @@
 #include "stereo.cuh"
 #include "rds.cuh"
 #include "scan.cuh"
+#include "spectrum.cuh"
 #include "audio_out.cuh"
 
 // One LANE = the complete launch sequence and state for a group of IQ streams on its own CUDA
@@ -152,6 +153,15 @@ struct Lane {
 	int32_t  lf_plot = -1;
 	float   *d_plot = nullptr;
 	const float2 *last_rds_ptr = nullptr; int64_t last_rds_pitch = 0;
+	// LF scope display spectrum (ls_scope::processLFSpectrum on the selected stream); spec_N = 0: off
+	int32_t  spec_N = 0, spec_logN = 0, spec_display = 0, spec_avg_count = 1, spec_zoom = 1;
+	bool     spec_refresh = true;           // lfBuffer_newFlag
+	float2  *d_spec_in = nullptr;           // [S][cap_fm] the stream of the call as complex samples
+	float2  *d_spec_carry [2] = { nullptr, nullptr }; int spec_sel = 0, spec_carry = 0;
+	float   *d_spec_win = nullptr;
+	double  *d_spec_Y = nullptr, *d_spec_avg = nullptr, *d_spec_disp = nullptr;
+	int32_t  cap_specblk = 0, last_nspec = 0;
+	cudaEvent_t ev_sym = nullptr;           // Costas output of the call ready (RDS_DEMOD spectrum)
 	// station scan (startScanning / stopScanning): 1024-sample blocks of fm-rate samples -> (signal, noise) dB
 	bool     scanning = false;
 	float2  *d_scan_carry [2] = { nullptr, nullptr }; int scan_sel = 0, scan_carry = 0;
@@ -603,11 +613,14 @@ void *ptrs [] = { h -> d_tables, h -> d_sin_quarter, h -> d_in, h -> d_hist [0],
 	              h -> d_A, h -> d_SA, h -> d_bha [0], h -> d_bha [1], h -> d_bhs [0], h -> d_bhs [1], h -> d_sq,
 	              h -> d_air_int, h -> d_air_frac, h -> d_air_pend, h -> d_rsy_state, h -> d_rsy_bits, h -> d_rsy_nbits,
 	              h -> d_rsy_c, h -> d_rsy_v, h -> d_rsy_w, h -> d_rsy_in,
-	              h -> d_scan_carry [0], h -> d_scan_carry [1], h -> d_scan_db };
+	              h -> d_scan_carry [0], h -> d_scan_carry [1], h -> d_scan_db, h -> d_plot,
+	              h -> d_spec_in, h -> d_spec_carry [0], h -> d_spec_carry [1], h -> d_spec_win,
+	              h -> d_spec_Y, h -> d_spec_avg, h -> d_spec_disp };
 	for (void *p : ptrs) if (p) cudaFree (p);
 	if (h -> stream_rds) { cudaStreamSynchronize (h -> stream_rds); cudaStreamDestroy (h -> stream_rds); }
 	if (h -> ev_k3) cudaEventDestroy (h -> ev_k3);
 	if (h -> ev_rds) cudaEventDestroy (h -> ev_rds);
+	if (h -> ev_sym) cudaEventDestroy (h -> ev_sym);
 	if (h -> stream) cudaStreamDestroy (h -> stream);
 	delete h;
 	return SDRJFM_OK;
@@ -790,6 +803,57 @@ const RawFmt rf = make_rawfmt (h, fmt, scale);
 	return launch_frontend (h, d_iq, rf, in_pitch, (int32_t)(n_in / h -> decim));
 }
 
+// LF scope display spectrum of the call (spectrum.cuh): the selected ELfPlot stream as complex samples,
+// cut into spectrumSize blocks across call boundaries, transformed, mapped and averaged
+static int run_lf_spectrum (Lane *h, int32_t M) {
+const int S = h -> cfg.n_streams;
+const int type = h -> lf_plot;
+const bool rds_rate = type >= 8 && h -> set.rds_mode != 0;
+const int32_t n = rds_rate ? (int32_t)h -> last_nrds : M;
+	h -> last_nspec = 0;
+	if (n <= 0) return SDRJFM_OK;
+LfGather G = {};
+	G.type = type; G.n = n; G.mul = 1.f;
+	switch (type) {
+	   case 1: G.c_src = h -> d_fmz; G.c_pitch = h -> cap_fm; break;
+	   case 2: case 3: G.f_src = h -> d_demod; G.f_pitch = h -> cap_fm; break;
+	   case 4: case 5: case 6: case 7: G.f_src = h -> d_plot; G.f_pitch = h -> cap_fm; break;
+	   case 8: if (rds_rate) { G.c_src = h -> last_rds_ptr; G.c_pitch = h -> last_rds_pitch; G.mul = 20.f; } break;
+	   case 9:
+	      if (rds_rate) {
+	         if (!h -> rds_symbols) { h -> err = "the RDS_DEMOD scope stream needs the RDS symbol stage (sdrjfm_set_rds_symbol_stage)"; return SDRJFM_ERR_UNSUPPORTED; }
+	         CK (cudaStreamWaitEvent (h -> stream, h -> ev_sym, 0));
+	         G.f_src = h -> d_rsy_c; G.f_pitch = h -> cap_rds; G.i_src = h -> d_plot; G.i_pitch = h -> cap_fm; G.mul = 4.f;
+	      }
+	      break;
+	   default: break;                                                     // OFF: zeros
+	}
+	lf_gather_kernel<<<dim3 ((unsigned)((n + 255) / 256), (unsigned)S), 256, 0, h -> stream>>> (G, h -> d_spec_in, h -> cap_fm);
+const int N = h -> spec_N;
+const int32_t nblk = std::min ((h -> spec_carry + n) / N, h -> cap_specblk);
+	if (nblk > 0) {
+	   LfSpecParams P;
+	   P.N = N; P.logN = h -> spec_logN; P.display = h -> spec_display; P.n_carry = h -> spec_carry;
+	   int factor = (N / h -> spec_display) / 2;                           // mapSpectrum, ls-scope.cpp:134-145
+	   factor = factor / h -> spec_zoom >= 1 ? factor / h -> spec_zoom : 1;
+	   P.factor = factor;
+	   P.full = (type == 1 || type == 8 || type == 9) ? 1 : 0;             // showFullSpectrum, fm-processor.cpp:247-263
+	   lf_spectrum_kernel<<<dim3 ((unsigned)nblk, (unsigned)S), kSpecThreads, (size_t)N * sizeof (float2), h -> stream>>> (
+	         h -> d_spec_in, h -> cap_fm, h -> d_spec_carry [h -> spec_sel], h -> d_spec_win, P, h -> d_spec_Y, h -> cap_specblk);
+	   lf_average_kernel<<<dim3 ((unsigned)((h -> spec_display + 127) / 128), (unsigned)S), 128, 0, h -> stream>>> (
+	         h -> d_spec_Y, h -> cap_specblk, nblk, h -> spec_display, h -> spec_avg_count, h -> spec_refresh ? 1 : 0,
+	         h -> d_spec_avg, h -> d_spec_disp);
+	   h -> spec_refresh = false;
+	   h -> launches += 2;
+	}
+	lf_carry_kernel<<<S, 256, 0, h -> stream>>> (h -> d_spec_in, h -> cap_fm, n, N, h -> d_spec_carry [h -> spec_sel],
+	                                             h -> spec_carry, h -> d_spec_carry [h -> spec_sel ^ 1]);
+	h -> spec_sel ^= 1; h -> spec_carry = (h -> spec_carry + n) % N;
+	h -> last_nspec = nblk;
+	h -> launches += 2;
+	return SDRJFM_OK;
+}
+
 // the launch sequence behind both process entry points; `src` is a device pointer holding
 // (pending | new) samples contiguously per stream with row pitch `pitch`
 static int run_chain (Lane *h, const void *src, RawFmt rf, int64_t pitch, int64_t n_proc,
@@ -803,7 +867,7 @@ const int32_t M1 = (int32_t)(n_proc / h -> decim);      // front-end (stage A) o
 int32_t M = M1;
 	if (h -> resample)      // fm samples that exist once stage-A sample a_total + M1 - 1 does (resample.cuh)
 	   M = (int32_t)(((h -> a_total + M1) * h -> rsL + h -> rsM - 1) / h -> rsM - h -> fm_total);
-	h -> last_nfm = M; h -> last_naudio = 0; h -> last_nrds = 0;
+	h -> last_nfm = M; h -> last_naudio = 0; h -> last_nrds = 0; h -> last_nspec = 0;
 	if (n_audio) *n_audio = 0;
 	if (n_rds) *n_rds = 0;
 	if (M1 == 0) return SDRJFM_OK;
@@ -1031,6 +1095,7 @@ const int dec = st.decoder == 2 ? 1 : st.decoder == 1 ? 2 : 0;
 	      rds_costas_kernel<<<(S + kRsyLanes - 1) / kRsyLanes, kRsyLanes, 0, rs>>> (
 	            h -> d_rsy_in, bp, nout, S, sp2, h -> d_rsy_state, h -> d_rsy_c, bp,
 	            h -> lf_plot == 9 ? h -> d_plot : nullptr, h -> cap_fm);
+	      if (h -> lf_plot == 9 && h -> spec_N) CK (cudaEventRecord (h -> ev_sym, rs));
 	      const dim3 gf ((unsigned)((nout + 127) / 128), (unsigned)S);
 	      rds_fir_kernel<kRsyLp, false><<<gf, 128, 0, rs>>> (h -> d_rsy_c, h -> d_rsy_v, bp, nout, sp2, h -> d_rsy_state);
 	      rds_fir_kernel<kRsyMatch, true><<<gf, 128, 0, rs>>> (h -> d_rsy_v, h -> d_rsy_w, bp, nout, sp2, h -> d_rsy_state);
@@ -1078,6 +1143,10 @@ const int64_t apitch = d_audio_out ? audio_pitch : h -> cap_audio;
 	h -> last_naudio = nq;
 	if (n_audio) *n_audio = nq;
 	if (st.rds_mode != 0) CK (cudaStreamWaitEvent (h -> stream, h -> ev_rds, 0));     // join
+	if (h -> spec_N && h -> lf_plot >= 0) {
+	   const int rc = run_lf_spectrum (h, M);
+	   if (rc != SDRJFM_OK) return rc;
+	}
 	CK (cudaGetLastError ());
 	return SDRJFM_OK;
 }
@@ -1311,6 +1380,7 @@ static int lane_set_rds_mode (Lane *h, int32_t m) {
 	   int rc = rds_setup (h);
 	   if (rc != SDRJFM_OK) return rc;
 	}
+	if (h -> lf_plot >= 8) h -> spec_refresh = true;                      // setfmRdsSelector: new_lfSpectrum (:843-846)
 	h -> set.rds_mode = m; return SDRJFM_OK;
 }
 // the symbol stage of rdsDecoder::doDecode for mode RDS_1 on the GPU (optional).
@@ -1360,7 +1430,59 @@ static int lane_set_lf_plot_type (Lane *h, int32_t type) {
 	CK (cudaSetDevice (h -> cfg.device));
 	if (((type >= 4 && type <= 7) || type == 9) && !h -> d_plot) CK (dalloc (&h -> d_plot, (size_t)h -> cfg.n_streams * h -> cap_fm));
 	h -> lf_plot = type;
+	h -> spec_refresh = true;                                             // lfBuffer_newFlag (:265)
 	return SDRJFM_OK;
+}
+// setlfPlotZoomFactor (fm-processor.cpp:268-271)
+static int lane_set_lf_plot_zoom (Lane *h, int32_t zoom) {
+	if (!h || zoom < 1) return SDRJFM_ERR_ARG;
+	h -> spec_zoom = zoom; h -> spec_refresh = true;
+	return SDRJFM_OK;
+}
+// The LF scope's display spectrum on the GPU: ls_scope (spectrumSize, displaySize, averageCount), radio.cpp:238-249,
+// 2009-2014.  spectrum_size 0 switches it off.
+static int lane_set_lf_spectrum (Lane *h, int32_t N, int32_t display, int32_t average_count) {
+	if (!h) return SDRJFM_ERR_ARG;
+	CK (cudaSetDevice (h -> cfg.device));
+	if (N == 0) { h -> spec_N = 0; return SDRJFM_OK; }
+	if (N < 64 || N > kSpecMaxN || (N & (N - 1)) || display < 2 || (display & (display - 1)) || N < 2 * display || average_count < 1) {
+	   h -> err = "LF spectrum: spectrum_size a power of two in 64..4096, display_size a power of two <= spectrum_size / 2, average_count >= 1";
+	   return SDRJFM_ERR_ARG;
+	}
+const size_t S = h -> cfg.n_streams;
+	CK (cudaStreamSynchronize (h -> stream));
+	for (void *p : { (void *)h -> d_spec_carry [0], (void *)h -> d_spec_carry [1], (void *)h -> d_spec_win,
+	                 (void *)h -> d_spec_Y, (void *)h -> d_spec_avg, (void *)h -> d_spec_disp }) if (p) cudaFree (p);
+	h -> d_spec_carry [0] = h -> d_spec_carry [1] = nullptr; h -> d_spec_win = nullptr;
+	h -> d_spec_Y = h -> d_spec_avg = h -> d_spec_disp = nullptr;
+	h -> spec_N = 0;
+	if (!h -> d_spec_in) CK (dalloc (&h -> d_spec_in, S * h -> cap_fm));
+	if (!h -> ev_sym) CK (cudaEventCreateWithFlags (&h -> ev_sym, cudaEventDisableTiming));
+	h -> cap_specblk = (int32_t)(h -> cap_fm / N + 2);
+	CK (dalloc (&h -> d_spec_carry [0], S * N)); CK (dalloc (&h -> d_spec_carry [1], S * N));
+	CK (dalloc (&h -> d_spec_win, (size_t)N));
+	CK (dalloc (&h -> d_spec_Y, S * h -> cap_specblk * display));
+	CK (dalloc (&h -> d_spec_avg, S * display)); CK (dalloc (&h -> d_spec_disp, S * display));
+std::vector<float> win ((size_t)N);
+	for (int i = 0; i < N; i ++)                                          // ls-scope.cpp:50-52, evaluated in double
+	   win [i] = 0.43 - 0.5 * cos ((2.0 * M_PI * i) / N) + 0.08 * cos ((4.0 * M_PI * i) / (N - 1));
+	CK (cudaMemcpy (h -> d_spec_win, win.data (), (size_t)N * sizeof (float), cudaMemcpyHostToDevice));
+	h -> spec_logN = 0; while ((1 << h -> spec_logN) < N) h -> spec_logN ++;
+	h -> spec_N = N; h -> spec_display = display; h -> spec_avg_count = average_count;
+	h -> spec_sel = 0; h -> spec_carry = 0; h -> spec_refresh = true; h -> last_nspec = 0;
+	return SDRJFM_OK;
+}
+// displayBuffer of one stream (display_size doubles) as the last process call left it
+static int64_t lane_read_lf_spectrum (Lane *h, int32_t stream, double *out, int64_t cap, int32_t *blocks) {
+	if (!h || !out || stream < 0 || stream >= h -> cfg.n_streams) return SDRJFM_ERR_ARG;
+	if (!h -> spec_N) { h -> err = "the LF spectrum is off (sdrjfm_set_lf_spectrum)"; return SDRJFM_ERR_ARG; }
+	if (cap < h -> spec_display) return SDRJFM_ERR_CAPACITY;
+	CK (cudaSetDevice (h -> cfg.device));
+	CK (cudaMemcpyAsync (out, h -> d_spec_disp + (size_t)stream * h -> spec_display, h -> spec_display * sizeof (double),
+	                     cudaMemcpyDeviceToHost, h -> stream));
+	CK (cudaStreamSynchronize (h -> stream));
+	if (blocks) *blocks = h -> last_nspec;
+	return h -> spec_display;
 }
 // What the LAST process call pushed into spectrumBuffer_lf for one stream (fm-processor.cpp:565-627):
 // complex samples, at the fm rate for every type except RDS_INPUT / RDS_DEMOD with the RDS branch on
@@ -1513,6 +1635,7 @@ static int lane_set_dc_remove (Lane *h, int32_t on) {
 static int lane_trigger_frequency_change (Lane *h) {
 	if (!h) return SDRJFM_ERR_ARG;
 	h -> fade_cnt = h -> fade_max;                                        // :848
+	h -> spec_refresh = true;                                             // new_lfSpectrum (:853)
 	return lane_restart_pss_analyzer (h);
 }
 static int lane_restart_pss_analyzer (Lane *h) {

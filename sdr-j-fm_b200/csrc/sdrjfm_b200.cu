@@ -388,6 +388,19 @@ FWD1 (set_native_rate, int32_t)
 FWD1 (set_rds_symbol_stage, int32_t)
 FWD1 (set_scanning, int32_t)
 FWD1 (set_lf_plot_type, int32_t)
+FWD1 (set_lf_plot_zoom, int32_t)
+int sdrjfm_set_lf_spectrum (sdrjfm_handle *h, int32_t spectrum_size, int32_t display_size, int32_t average_count) {
+	return for_lanes (h, [&](Lane *l) { return lane_set_lf_spectrum (l, spectrum_size, display_size, average_count); });
+}
+int64_t sdrjfm_read_lf_spectrum (sdrjfm_handle *h, int32_t stream, double *display, int64_t cap, int32_t *blocks) {
+	if (!h || !display) return SDRJFM_ERR_ARG;
+const int i = lane_of (h, stream);
+	if (i < 0) return SDRJFM_ERR_ARG;
+	HK (cudaStreamSynchronize (h -> stream));
+const int64_t n = lane_read_lf_spectrum (h -> lanes [i], stream - h -> first [i], display, cap, blocks);
+	if (n < 0) h -> err = h -> lanes [i] -> err;
+	return n;
+}
 int64_t sdrjfm_read_lf_plot (sdrjfm_handle *h, int32_t stream, float *out, int64_t cap,
                              int32_t *sample_rate, int32_t *show_full) {
 	if (!h || !out) return SDRJFM_ERR_ARG;

@@ -581,6 +581,58 @@ def test_lf_scope_stream_matches_reference(pkg, signals, chainlib, checker, ref_
     p.close()
 
 
+@pytest.mark.parametrize("kind,N,display,avg,zoom", [
+    ("DEMODULATOR", 2048, 512, 5, 1),        # the reference's defaults (radio.cpp:238-249), one-sided
+    ("IF_FILTERED", 2048, 512, 5, 1),        # two-sided
+    ("RDS_INPUT", 1024, 256, 3, 2),          # 24 kHz stream, zoomed
+    ("AF_LEFT_FILTERED", 4096, 1024, 1, 4),  # largest size; zoom beyond the bin factor is clamped
+])
+def test_lf_display_spectrum_matches_reference(pkg, signals, chainlib, ref_available, kind, N, display, avg, zoom):
+    """ls_scope::processLFSpectrum on the GPU (SURVEY.md §8(f) rank 4): window, FFT, mapSpectrum, running
+    average, blocks cut across ragged calls, two streams.  Checker: the same arithmetic restated around
+    the reference's own Fft_transform (oracle/ref_harness.cpp), fed with the scope stream the GPU kept."""
+    if not ref_available:
+        pytest.skip("oracle/_ref not available")
+    n = N1 + 16384 * 11 + 321
+    x = np.stack([signals.batch_stream(5, n), signals.batch_stream(6, n)])
+    p = pkg.FmProcessorB200(n_streams=2, max_samples_per_call=n, keep_taps=False)
+    p.configure(fm_mode=0, rds_on=1, volume_db=-6.0)
+    p.setlfPlotType(kind)
+    p.set_lf_spectrum(N, display, avg)
+    p.setlfPlotZoomFactor(zoom)
+    full = kind in ("IF_FILTERED", "RDS_INPUT")
+    streams = [[], []]
+    shots = []                                   # (stream, cumulative samples, display, blocks of the call)
+    pos = 0
+    for c in [16384 * 50, 16384, 7, 16384 * 33 + 5, 12 * 100, n]:
+        if pos >= n:
+            break
+        p.process(x[:, pos:pos + c])
+        for s in range(2):
+            streams[s].append(p.read_lf_plot(s)[0])
+            d, nb = p.read_lf_spectrum(s)
+            shots.append((s, sum(len(v) for v in streams[s]), d, nb))
+        pos += c
+    p.close()
+    worst = 0.0
+    for s in range(2):
+        v = np.concatenate(streams[s])
+        want = chainlib.ref_lf_spectrum(v, N, display, avg, zoom, full)
+        assert len(want) == len(v) // N and len(want) > 10
+        done = 0
+        for (ss, cum, d, nb) in shots:
+            if ss != s:
+                continue
+            assert nb == cum // N - done                                  # blocks per call: the index contract
+            done = cum // N
+            w = want[done - 1] if done else np.zeros(display)
+            e = float(np.max(np.abs(d - w))) / max(float(np.max(w)), 1e-6)
+            worst = max(worst, e)
+        assert done == len(want) and float(np.max(want[-1])) > 1e-3
+    print(kind, "max display error / peak", worst)
+    assert worst < 5e-6
+
+
 def test_edge_cases_empty_tiny_and_capacity(pkg, signals, checker):
     """empty and one-sample calls, calls shorter than one fm-rate sample, NULL outputs, the capacity
     error — and the stream they leave behind still equals the reference's."""
