@@ -169,7 +169,11 @@ float vy = (u.y - ky) * P.rgain;
 //	error against the reference (composite FIR), so the magnitude is taken in float (1e-7) instead of
 //	through a double square root, and the two divisions share one reciprocal: q = a r, corrected
 //	once with the exact residual (q + (a - q b) r), which is the correctly rounded quotient.
-	za = __fsqrt_rn (fmaf (z.x, z.x, fmul (z.y, z.y)));
+//	The decoders other than MIXED read look-up tables whose index flips on a 1-ulp change of I or Q
+//	(arcsine table, the PLL's sine table): for them the magnitude is the reference's own rounding,
+//	hypotf = the double-precision root rounded once to float.
+	if (P.decoder != 3) za = (float)sqrt ((double)z.x * (double)z.x + (double)z.y * (double)z.y);
+	else za = __fsqrt_rn (fmaf (z.x, z.x, fmul (z.y, z.y)));
 	if (za <= 0.001f) nq = make_float2 (0.001f, 0.001f);          // :120-122
 	else {
 	   const float r = __frcp_rn (za);

@@ -359,6 +359,36 @@ def test_am_decoder_matches_reference(pkg, signals, checker, chunks):
     assert abs(m["dc_if"] - rm["dc_if"]) < 1e-4
 
 
+@pytest.mark.parametrize("decoder,name", [(2, "PLL"), (4, "complex baseband"), (5, "real baseband"), (6, "difference")])
+def test_other_fm_decoders_match_reference(pkg, signals, checker, decoder, name):
+    """fm_Demodulator::demodulate for the decoders other than the default MIXED (fm-demodulator.cpp:140-195):
+    PLL (pllC::do_pll, a per-sample loop: sequential kernel), complex baseband (arg of the delay
+    product), real baseband (arcsine LUT) and difference based — stereo chain behind them, ragged
+    calls; switching the decoder mid-stream follows the reference too."""
+    n = N1 + 12 * 777
+    x = signals.dc_offset(signals.stereo_pilot(n))
+    cfg = dict(decoder=decoder, fm_mode=0, volume_db=0.0)
+    ref = checker(**cfg).process(x)
+    got = run_gpu(pkg, x, chunks=[16384 * 30 + 5, 16384, 3, n], **cfg)
+    e_d, e_a = rms(got["demod"][0] - ref["demod"]), rms(got["audio192"][0] - ref["audio192"])
+    print(name, "demod rms err", e_d, "audio192", e_a, "signal rms", rms(ref["demod"]), "locked", int(ref["locked"][-1]))
+    assert len(got["demod"][0]) == ref["n_fm"]
+    assert rms(ref["demod"]) > 0.05
+    # the decoder alone: the reference's classes fed with the GPU's own fm-rate samples (decimator bypass,
+    # fm-processor.cpp:471) must give the GPU's demod
+    iso = checker(**dict(cfg, input_rate=192000, fm_rate=192000, dc_remove=0)).process_fm(got["fm_z"][0])
+    e_iso = rms(got["demod"][0] - iso["demod"])
+    print(name, "decoder alone: demod rms err", e_iso, "audio192", rms(got["audio192"][0] - iso["audio192"]))
+    assert e_iso < 1e-6 and rms(got["audio192"][0] - iso["audio192"]) < 2e-6
+    # end to end.  The PLL and real-baseband decoders read their result from look-up tables (sine table of
+    # 192000 entries + atan table; arcsine table of 8192 entries): a 3e-7 rounding difference in fm_z moves
+    # some samples into the neighbouring table entry, one table step (1e-4) each — the reference itself is
+    # that sensitive to its own rounding — hence the wider end-to-end bound for these two.
+    tol = 5e-5 if decoder in (2, 5) else 1e-5
+    assert e_d < tol and e_a < tol
+    assert np.array_equal(got["locked"][0], ref["locked"])
+
+
 def test_many_streams_over_lanes_match_reference(pkg, signals, checker):
     """130 streams in one handle: split over 4 lanes (own CUDA streams, RDS branch on a side stream,
     persistent TMA front end striding over (stream, tile) items).  Streams at the lane boundaries and a
