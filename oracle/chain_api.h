@@ -96,6 +96,8 @@ CHAIN_DECL(orc)
  * the reference's own Fft_transform followed by a restatement of getSignal / getNoise / get_db
  * (private members of the Qt class fmProcessor).  out: nblocks pairs (signal dB, noise dB).          */
 int64_t ref_scan_blocks (const float *fm_z, int64_t n, float *out);
+/* run-time setters between process calls (ref_ only): see ref_harness.cpp */
+void    ref_update (void *h, const chain_cfg *cfg, int32_t actions);
 void   *ref_rds1_create (int32_t rate);
 void    ref_rds1_destroy (void *h);
 int64_t ref_rds1_process (void *h, const float *rds24, int64_t n, uint8_t *bits, int64_t cap);

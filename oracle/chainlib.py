@@ -107,6 +107,17 @@ class Chain:
             self._destroy(self.h)
             self.h = None
 
+    def update(self, actions=0, **cfg):
+        """run-time setters between process calls (ref_ only): new values for fm_mode, decoder, sound_sel,
+        panorama, balance, volume_db, deemph_us, auto_mono, pss_on, lgain, rgain, lo_hz, squelch_*;
+        actions: 1 restartPssAnalyzer, 2 triggerFrequencyChange, 4 setDCRemove (dc_remove=...)."""
+        assert self.prefix == "ref"
+        for k, v in cfg.items():
+            setattr(self.cfg, k, v)
+        self.lib.ref_update.restype = None
+        self.lib.ref_update.argtypes = [C.c_void_p, C.POINTER(ChainCfg), C.c_int32]
+        self.lib.ref_update(self.h, C.byref(self.cfg), actions)
+
     def process_demod(self, demod, taps=TAPS):
         """enter the chain AFTER the discriminator with given float32 demod values."""
         demod = np.ascontiguousarray(demod, dtype=np.float32)

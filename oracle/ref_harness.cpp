@@ -339,6 +339,34 @@ int64_t nfm = 0, nrds = 0;
 	return nfm;
 }
 
+//	The setters the GUI thread calls while run () is going (fm-processor.cpp:240-301, 855-933): the new
+//	chain_cfg carries fm_mode, decoder, sound_sel, panorama, balance, volume, de-emphasis, auto_mono, pss_on,
+//	IQ gains, LO, squelch; filters and rates are not touched.  actions: 1 = restartPssAnalyzer (:857-860),
+//	2 = triggerFrequencyChange (:849-855: the PSS restart is the part inside this chain),
+//	4 = setDCRemove (cfg -> dc_remove) (:924-927: also zeroes RfDC).
+void	ref_update (void *h, const chain_cfg *n, int32_t actions) {
+RefChain *c = (RefChain *)h;
+	if (n -> decoder != c -> cfg.decoder)
+	   c -> theDemodulator. setDecoder (QString (decoderName (n -> decoder)));
+	c -> cfg.decoder = n -> decoder;
+	c -> cfg.fm_mode = n -> fm_mode; c -> cfg.sound_sel = n -> sound_sel;
+	c -> cfg.auto_mono = n -> auto_mono; c -> cfg.pss_on = n -> pss_on;
+	c -> cfg.squelch_mode = n -> squelch_mode;
+	if (n -> squelch_value != c -> cfg.squelch_value) c -> mySquelch. setSquelchLevel (n -> squelch_value);
+	c -> cfg.squelch_value = n -> squelch_value;
+	c -> Lgain = n -> lgain; c -> Rgain = n -> rgain;
+	c -> loFrequency = n -> lo_hz;
+	{
+	   float Tau = 1000000.0 / n -> deemph_us;
+	   c -> deemphAlpha = 1.0 / (float (c -> fmRate) / Tau + 1.0);
+	}
+	c -> volumeFactor = std::pow (10.0f, n -> volume_db / 20.0f);
+	c -> panorama = (float)n -> panorama / 100.0f;
+	c -> leftChannel  = (n -> balance > 0 ? (100 - n -> balance) / 100.0 : 1.0f);
+	c -> rightChannel = (n -> balance < 0 ? (100 + n -> balance) / 100.0 : 1.0f);
+	if (actions & 3) { c -> pilotDelayPSS = 0; c -> pPSS. reset (); }
+	if (actions & 4) { c -> cfg.dc_remove = n -> dc_remove; c -> RfDC = DSPCOMPLEX (0, 0); }
+}
 void	ref_get_meta (void *h, chain_meta *m) {
 RefChain *c = (RefChain *)h;
 	m -> dc_rf_re = real (c -> RfDC);

@@ -389,6 +389,63 @@ def test_other_fm_decoders_match_reference(pkg, signals, checker, decoder, name)
     assert np.array_equal(got["locked"][0], ref["locked"])
 
 
+def test_setters_between_calls_match_reference(pkg, signals, chainlib, ref_available):
+    """The GUI thread calls the fmProcessor setters while run () is going (fm-processor.h:122-157); the
+    library applies them at the next process boundary.  A stream processed in six calls with the settings
+    changed in between — selector, panorama, balance, volume, de-emphasis, decoder, mono/stereo,
+    restartPssAnalyzer, setDCRemove off and on again (zeroes RfDC), triggerFrequencyChange, IQ gains —
+    against the reference's classes driven through the same sequence."""
+    if not ref_available:
+        pytest.skip("oracle/_ref not available")
+    c = N1 // 2 + 12 * 3
+    n = 6 * c
+    x = signals.dc_offset(signals.batch_stream(4, n))
+    cfg0 = dict(fm_mode=0, volume_db=-6.0)
+    plan = [                                        # (settings changed before the call, actions)
+        ({}, 0),
+        (dict(fm_mode=1, sound_sel=1, panorama=140, balance=-30), 0),
+        (dict(deemph_us=75, volume_db=0.0, decoder=4), 0),
+        ({}, 1),                                                        # restartPssAnalyzer
+        (dict(decoder=3, fm_mode=2, dc_remove=0), 4),                   # mono, setDCRemove (false)
+        (dict(fm_mode=0, dc_remove=1, lgain=0.9, rgain=1.1, sound_sel=0), 4 | 2),   # setDCRemove (true), triggerFrequencyChange
+    ]
+    ref = chainlib.Chain("ref", **cfg0)
+    p = pkg.FmProcessorB200(n_streams=1, max_samples_per_call=c)
+    p.configure(**cfg0)
+    keys = ("fm_z", "demod", "pss_delay", "lr", "audio192")
+    for i, (chg, act) in enumerate(plan):
+        if chg or act:
+            ref.update(actions=act, **chg)
+            g = dict(chg)
+            if act & 4:
+                p.setDCRemove(g.pop("dc_remove"))
+            p.configure(**g)
+            if act & 1:
+                p.restartPssAnalyzer()
+            if act & 2:
+                p.triggerFrequencyChange()
+        xi = x[i * c:(i + 1) * c]
+        r = ref.process(xi)
+        a48, _ = p.process(xi)
+        # setDCRemove / setAttenuation act on input samples BEFORE the decimating FIR; here the DC is folded
+        # into the taps and the IQ gains are applied behind the (real-tap) FIR, so the 3 fm-rate samples whose
+        # FIR window straddles the switch see the new setting for the whole window: a documented 16 us
+        # transient (DESIGN.md section 4), left out here together with its de-emphasis tail
+        lo = 4 if (act & 4 or "lgain" in chg) else 0
+        e = {k: rms(p.read_tap(k, 0)[lo + (300 if lo and k == "audio192" else 0):] -
+                    r[k][lo + (300 if lo and k == "audio192" else 0):]) for k in keys}
+        e["fm_z"] /= rms(r["fm_z"])
+        assert np.array_equal(p.read_tap("locked", 0), r["locked"]), i
+        print("call", i, chg, act, e)
+        assert e["fm_z"] < 2e-6 and e["demod"] < 1e-5 and e["audio192"] < 1e-5 and e["lr"] < 3e-5, (i, e)
+        assert e["pss_delay"] < 2e-5, (i, e)
+        if i == 3:                                                      # the PSS loop restarted from zero
+            assert abs(float(r["pss_delay"][0])) < 1e-4 and abs(float(p.read_tap("pss_delay", 0)[0])) < 1e-4
+        if i == 5:                                                      # fade-in restarted (:638-642, :848)
+            assert abs(a48[0, 0]) < 1e-4 and rms(a48[0, -2000:]) > 1e-2
+    p.close()
+
+
 def test_many_streams_over_lanes_match_reference(pkg, signals, checker):
     """130 streams in one handle: split over 4 lanes (own CUDA streams, RDS branch on a side stream,
     persistent TMA front end striding over (stream, tile) items).  Streams at the lane boundaries and a
