@@ -211,6 +211,24 @@ def test_stereo_chain_matches_reference(pkg, signals, checker, sig_name, cfg):
         assert np.max(np.abs(ref["pss_delay"][300000:])) > 1e-4       # the PSS loop did something
 
 
+@pytest.mark.parametrize("sound_sel,name", [(2, "S_LEFT"), (3, "S_RIGHT"), (4, "S_LEFTplusRIGHT"), (5, "S_LEFTminusRIGHT")])
+def test_sound_selectors_match_reference(pkg, signals, checker, sound_sel, name):
+    """the remaining entries of the Channels selector (fm-processor.cpp:527-549), 75 us de-emphasis,
+    balance to the right; the stereo test above covers S_STEREO, S_STEREO_SWAPPED and the _Test entry."""
+    n = N1 + N1 // 2
+    x = signals.stereo_pilot(n, left_hz=1000.0, right_hz=1700.0)
+    cfg = dict(fm_mode=1, panorama=60, sound_sel=sound_sel, balance=40, deemph_us=75, volume_db=-3.0)
+    ref = checker(**cfg).process(x)
+    got = run_gpu(pkg, x, chunks=[N1 // 2 + 12 * 5, 16384, n], **cfg)
+    e = _stereo_report(got, ref, 0)
+    print(name, e)
+    assert e["audio192"] < 1e-5 and e["lr"] < 3e-5 and e["demod"] < 1e-5
+    lr = got["lr"][0][-50000:]
+    if sound_sel != 5:
+        assert rms(lr) > 0.1
+    assert np.array_equal(lr.real, lr.imag) == (sound_sel in (2, 3, 4, 5))
+
+
 def test_stereo_separation_figure(pkg, signals, checker):
     """L-only 1 kHz tone: leakage into R after lock and PSS convergence, measured on the tone
     component of the 192 kHz output.  The figure must be the reference's own (22 dB with this
