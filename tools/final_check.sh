@@ -1,0 +1,7 @@
+set -x
+mkdir -p gpurun_out
+( time python -m pytest tests -x -q -m gpu ) > gpurun_out/final_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/final_tests.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/final_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/final_smoke.log
+python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err; echo "bench rc=$?" >> gpurun_out/final_bench.err
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"frontend|roll_history|dc_tile|discriminator|pilot_kernel|stereo_kernel|rds_|audio_kernel" --launch-skip 216 -c 144 --csv --log-file gpurun_out/r1_launches_final.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/final_ncu.log 2>&1
+tail -3 gpurun_out/final_tests.log; cat gpurun_out/final_smoke.log | tail -2; cut -c1-400 gpurun_out/final_bench.json
