@@ -23,6 +23,26 @@ def test_library_exports_every_declared_symbol(pkg):
     assert b"sm_100a" in L.sdrjfm_version()
 
 
+def test_host_mirror_binds_every_entry_point_and_reference_setter(pkg):
+    """the Python mirror of the reference interface reaches every C entry point, and carries the
+    fmProcessor setter names (includes/fm/fm-processor.h:122-157) the parity tests are written in."""
+    hdr = open(pkg.HEADER).read()
+    src = open(pkg.__file__).read()
+    names = sorted(set(re.findall(r"\b(sdrjfm_[a-z0-9_]+)\s*\(", hdr)))
+    unbound = [n for n in names if n not in src]
+    assert not unbound, unbound
+    for setter in ("setfmMode", "setFMdecoder", "setSoundMode", "setStereoPanorama", "setSoundBalance",
+                   "setDeemphasis", "setVolume", "setlfcutoff", "setBandwidth", "setAttenuation",
+                   "setfmRdsSelector", "set_localOscillator", "set_squelchMode", "set_squelchValue",
+                   "setAutoMonoMode", "setPSSMode", "setDCRemove", "triggerFrequencyChange",
+                   "restartPssAnalyzer", "startScanning", "stopScanning", "setlfPlotType",
+                   "setlfPlotZoomFactor"):
+        assert hasattr(pkg.FmProcessorB200, setter), setter
+    # enum values follow the reference's declarations
+    assert pkg.LF_PLOT["RDS_DEMOD"] == 9 and pkg.LF_PLOT["OFF"] == 0
+    assert pkg.IQ_FORMAT["cf32"] == 0
+
+
 def test_create_fails_loudly_without_device(pkg):
     import torch
     if torch.cuda.is_available():

@@ -79,3 +79,69 @@ def test_decimation_index_contract(chainlib):
     imp[12 * 5 + 11] = 1.0
     z = c.process(imp)["fm_z"]
     assert np.all(z[:5] == 0) and z[5] != 0
+
+
+def test_checker_runtime_setters_are_consistent(chainlib, ref_available, signals):
+    """ref_update (the run-time setters of the checker): an update that changes nothing leaves the stream
+    bit-identical to uninterrupted processing; settings given at construction and settings applied by an
+    update before the first sample are the same chain; setDCRemove zeroes RfDC."""
+    if not ref_available:
+        pytest.skip("oracle/_ref not built")
+    n = N1 // 3
+    x = signals.dc_offset(signals.stereo_pilot(n))
+    cfg = dict(fm_mode=1, panorama=140, sound_sel=1, balance=-30, deemph_us=75, volume_db=-3.0, decoder=4,
+               lgain=0.9, rgain=1.1)
+    whole = chainlib.Chain("ref", **cfg).process(x)
+    a = chainlib.Chain("ref", **cfg)
+    first = a.process(x[:n // 2 + 5])
+    a.update(actions=0)
+    second = a.process(x[n // 2 + 5:])
+    b = chainlib.Chain("ref")
+    b.update(actions=0, **cfg)
+    late = b.process(x)
+    for k in chainlib.Chain.TAPS:
+        assert _same(np.concatenate([first[k], second[k]]), whole[k]), k
+        assert _same(late[k], whole[k]), k
+    c = chainlib.Chain("ref")
+    c.process(x[:n // 2])
+    assert abs(c.meta()["dc_rf_re"]) > 1e-4
+    c.update(actions=4, dc_remove=1)
+    assert c.meta()["dc_rf_re"] == 0.0 and c.meta()["dc_rf_im"] == 0.0
+
+
+def test_checker_lf_spectrum_against_float64_model(chainlib, ref_available):
+    """ref_lf_spectrum (ls_scope's arithmetic restated around the reference's Fft_transform) against an
+    independent float64 numpy model of ls-scope.cpp:50-52, 76-92, 130-193."""
+    if not ref_available:
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(5)
+    for N, D, avg, zoom, full in ((2048, 512, 5, 1, False), (2048, 512, 5, 1, True), (1024, 256, 3, 2, True),
+                                  (4096, 1024, 1, 4, False)):
+        t = np.arange(N * 9 + 100)
+        v = (0.5 * np.exp(2j * np.pi * 0.11 * t) + 0.2 * np.cos(2 * np.pi * 0.031 * t)
+             + 0.01 * (rng.standard_normal(len(t)) + 1j * rng.standard_normal(len(t)))).astype(np.complex64)
+        got = chainlib.ref_lf_spectrum(v, N, D, avg, zoom, full)
+        i = np.arange(N)
+        win = (0.43 - 0.5 * np.cos(2 * np.pi * i / N) + 0.08 * np.cos(4 * np.pi * i / (N - 1))).astype(np.float32)
+        factor = (N // D) // 2
+        factor = factor // zoom if factor // zoom >= 1 else 1
+        avgbuf = np.zeros(D); disp = np.zeros(D); want = []
+        for b in range(len(v) // N):
+            f = np.abs(np.fft.fft(v[b * N:(b + 1) * N].astype(np.complex128) * win))
+            y = np.zeros(D)
+            if full:
+                for k in range(D // 2):
+                    y[D // 2 + k] = f[k * factor:(k + 1) * factor].mean()
+                    y[D // 2 - 1 - k] = f[N - 1 - np.arange(k * factor, (k + 1) * factor)].mean()
+            else:
+                y = f[:D * factor].reshape(D, factor).mean(axis=1)
+            if b == 0:
+                avgbuf = y.copy()
+            else:
+                avgbuf = y / avg + (avg - 1.0) / avg * avgbuf
+                disp = avgbuf.copy()
+            want.append(disp.copy())
+        want = np.array(want)
+        assert got.shape == want.shape == (9, D)
+        assert np.max(np.abs(got - want)) < 2e-6 * np.max(want)
+        assert np.max(want[-1]) > 1.0
