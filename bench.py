@@ -29,6 +29,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# 11 CUDA streams per handle (lanes + side streams): more hardware queues than the default 8; must be in
+# the environment before the CUDA context exists (torch creates it first in this process)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 from __graft_entry__ import load_package  # noqa: E402
 
 INPUT_RATE = 2304000

@@ -8,6 +8,13 @@
 // There is NO CPU fallback: without an sm_100 device sdrjfm_create fails with
 // SDRJFM_ERR_NO_DEVICE.
 #include "lane_impl.cuh"
+#include <cstdlib>
+
+// A handle with 4 lanes works on 11 CUDA streams (lane + RDS side stream each, the caller's stream, two
+// copy streams).  The driver maps streams onto 8 hardware queues by default, which makes independent
+// streams wait for each other; when this library is loaded before the process creates its CUDA context
+// (and the host did not choose a value itself) it asks for 32.  Measured: 4.36 -> 4.30 ms per bench step.
+namespace { struct QueueHint { QueueHint () { setenv ("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); } } g_queue_hint; }
 
 struct sdrjfm_handle {
 	sdrjfm_config cfg;
