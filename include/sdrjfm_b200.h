@@ -5,7 +5,16 @@
  * fmProcessor::run does between deviceHandler::getSamples and audioSink::putSample /
  * rdsDecoder::doDecode.  Plain pointers and sizes only; no C++/Qt/torch types; never
  * throws; every entry point returns an int status (0 = SDRJFM_OK) unless stated.
- * One calling thread per handle (the reference has exactly one: the fmProcessor QThread).
+ * One calling thread per handle (the reference has exactly one: the fmProcessor QThread); different
+ * handles may be driven from different threads (calls into one device are serialised inside the
+ * library: the tap sets live in per-device constant banks), and a process may hold handles on several
+ * devices (sdrjfm_config.device).
+ * A call that fails with an argument / capacity / unsupported status leaves the handle as it was; a call
+ * that fails after stream state has moved (a CUDA error in mid-flight) poisons the handle: every later
+ * call returns SDRJFM_ERR_CUDA until it is destroyed.
+ * Environment: when the library is loaded before the process creates its CUDA context it sets
+ * CUDA_DEVICE_MAX_CONNECTIONS=32 unless the host set a value itself (a handle works on up to 11
+ * streams); SDRJFM_NO_ENV_HINT=1 leaves the environment untouched.
  *
  * Every entry point names the reference interface it replaces (paths relative to the
  * reference tree).  INTEGRATION.md shows the reference-side binding.
@@ -49,10 +58,21 @@ typedef struct sdrjfm_config {
     int32_t device;                /* CUDA device ordinal                                */
     int64_t max_samples_per_call;  /* per stream; sizes the device buffers               */
     int32_t keep_taps;             /* 1: keep fm-rate intermediates for sdrjfm_read_tap  */
-    int32_t front_end_mode;        /* 0: the reference's integer decimation (12m+11 index contract);
+    int32_t front_end_mode;        /* 0: the reference's integer decimation (12m+11 index contract), evaluated as
+                                         ONE real polyphase FIR with the DC removal finished at the fm rate
+                                         (HBM-bound; fm-rate samples within 3e-7 of the reference's).  The
+                                         library moves a stream onto mode 2 by itself while the PLL or
+                                         real-baseband decoder is selected or the oscillator is non-zero
+                                         (their look-up-table indices flip on a 3e-7 difference);
                                       1: rational polyphase resampler to exactly fm_rate (new block,
                                          BASELINE config 4): /5 low-pass, then L/M = 5 fm_rate / input_rate
-                                         (2/5, 4/25, 12/125 at 2.4, 6, 10 MS/s); csrc/resample.cuh        */
+                                         (2/5, 4/25, 12/125 at 2.4, 6, 10 MS/s); csrc/resample.cuh;
+                                      2: the same arithmetic as 0 in the REFERENCE'S OPERATION ORDER: RF DC
+                                         one-pole per input sample in float32, IQ gain, oscillator, fmBand_1
+                                         and fmBand_2 tap by tap (fm-processor.cpp:423-446, 462-475;
+                                         fir-filters.cpp:397-424): fm-rate samples bit-identical to the
+                                         reference's.  Latency-bound (the DC recurrence); with inputFilter
+                                         on, mode 0 is used; csrc/frontend_exact.cuh                       */
 } sdrjfm_config;
 
 /* fmProcessor::SMetaData (includes/fm/fm-processor.h:91-101) per stream, plus the RF DC
@@ -171,7 +191,8 @@ int  sdrjfm_set_fm_decoder (sdrjfm_handle *h, int32_t decoder);    /* setFMdecod
 int  sdrjfm_set_sound_mode (sdrjfm_handle *h, int32_t selector);   /* setSoundMode: Channels enum */
 int  sdrjfm_set_stereo_panorama (sdrjfm_handle *h, int32_t pan);   /* setStereoPanorama 0..200 */
 int  sdrjfm_set_sound_balance (sdrjfm_handle *h, int32_t balance); /* setSoundBalance -100..100 */
-int  sdrjfm_set_deemphasis (sdrjfm_handle *h, int32_t usec);       /* setDeemphasis (>=1) */
+int  sdrjfm_set_deemphasis (sdrjfm_handle *h, int32_t usec);       /* setDeemphasis, 1 ("Off") .. 100 us (the GUI offers 1, 50, 75);
+                                                                       above: SDRJFM_ERR_UNSUPPORTED */
 int  sdrjfm_set_volume_db (sdrjfm_handle *h, float db);            /* setVolume */
 int  sdrjfm_set_lf_cutoff (sdrjfm_handle *h, int32_t hz);          /* setlfcutoff (<=0: off) */
 int  sdrjfm_set_bandwidth (sdrjfm_handle *h, int32_t hz);          /* setBandwidth ("Off" -> 0) */
@@ -196,7 +217,10 @@ int64_t sdrjfm_read_scan (sdrjfm_handle *h, int32_t stream, float *db_pairs, int
  * fm-rate sample, or one per 24 kHz sample for RDS_INPUT / RDS_DEMOD while the RDS branch is on.
  * *sample_rate / *show_full = spectrumSampleRate / showFullSpectrum of the selected type.  The adapter cuts
  * the stream into spectrumSize blocks for ls_scope::processLFSpectrum.  RDS_DEMOD needs the
- * RDS symbol stage.  While a scope stream is selected, host calls are not cut into pipelined time slices.  */
+ * RDS symbol stage.  Host calls (sdrjfm_process) of more than ~1 M samples are cut into pipelined time slices
+ * (H2D of slice c+1 under the compute of slice c) — except while a scope stream is selected, the RDS symbol
+ * stage is on or the station scan runs: the per-call side outputs (sdrjfm_read_lf_plot, _read_rds_bits,
+ * _read_scan) always describe the WHOLE last call.                                                          */
 enum sdrjfm_lf_plot {
     SDRJFM_LFPLOT_NONE = -1, SDRJFM_LFPLOT_OFF = 0, SDRJFM_LFPLOT_IF_FILTERED = 1, SDRJFM_LFPLOT_DEMODULATOR = 2,
     SDRJFM_LFPLOT_AF_SUM = 3, SDRJFM_LFPLOT_AF_DIFF = 4, SDRJFM_LFPLOT_AF_MONO_FILTERED = 5,

@@ -260,6 +260,7 @@ class FmProcessorB200:
         if not self.h:
             raise SdrjfmError(st.value, self.L.sdrjfm_last_error(None).decode())
         self.n_streams = n_streams
+        self._display = 0
         # input samples per fm-rate sample (a lower bound in the resampler mode: sizes the outputs)
         self.decim = (input_rate // fm_rate) if front_end_mode == 1 else front_end_decimation(input_rate, fm_rate)
 
@@ -324,6 +325,8 @@ class FmProcessorB200:
 
     def read_lf_spectrum(self, stream=0):
         """(displayBuffer float64 [display_size], blocks completed by the last call)."""
+        if not self._display:
+            raise SdrjfmError(ERR_ARG, "the LF spectrum is off: call set_lf_spectrum first")
         a = np.zeros(self._display, np.float64)
         nb = C.c_int32(0)
         n = self.L.sdrjfm_read_lf_spectrum(self.h, stream, a.ctypes.data, a.size, C.byref(nb))

@@ -26,6 +26,7 @@ struct DiscrParams {
 	float  lgain, rgain;
 	int32_t dc_remove, decoder;
 	int32_t scan_only;          // station scan: the demodulator is not called, its state must not move
+	int32_t exact;              // K1x ran (frontend_exact.cuh): U already is the reference's fm-rate sample, bit for bit
 	// local oscillator on: gains and rotation were applied per input sample by K1; the DC value
 	// the reference subtracted BEFORE the rotation comes back out as clamp (r) * gains *
 	// Table[LOPhase at decim (m + lo_moff) + decim - 1] * H,  H = sum_t C[t] exp (+2 pi i lo t / inputRate)
@@ -172,7 +173,7 @@ float vy = (u.y - ky) * P.rgain;
 //	The decoders other than MIXED read look-up tables whose index flips on a 1-ulp change of I or Q
 //	(arcsine table, the PLL's sine table): for them the magnitude is the reference's own rounding,
 //	hypotf = the double-precision root rounded once to float.
-	if (P.decoder != 3) za = (float)sqrt ((double)z.x * (double)z.x + (double)z.y * (double)z.y);
+	if (P.decoder != 3 || P.exact) za = (float)sqrt ((double)z.x * (double)z.x + (double)z.y * (double)z.y);
 	else za = __fsqrt_rn (fmaf (z.x, z.x, fmul (z.y, z.y)));
 	if (za <= 0.001f) nq = make_float2 (0.001f, 0.001f);          // :120-122
 	else {

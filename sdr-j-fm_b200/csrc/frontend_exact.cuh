@@ -1,0 +1,202 @@
+// K1x — the front end in the REFERENCE'S OWN OPERATION ORDER (front_end_mode 2, and chosen
+// automatically for the table-indexed decoders and for lo != 0).
+//
+// The composite front end (frontend_tma.cuh / frontend_fir.cuh) re-associates the two decimators
+// into one real 37-tap FIR and finishes the RF DC removal at the fm rate: fm-rate samples within
+// 3e-7 of the reference's.  That is far inside the audio tolerance, but the PLL and real-baseband
+// decoders read look-up tables whose index flips on such a difference.  These kernels instead
+// restate, operation by operation,
+//     RfDC = (x - RfDC) * rfDcAlpha + RfDC; x -= clamp (RfDC, +-0.01)      fm-processor.cpp:423-446
+//     v = (re * Lgain, im * Rgain) * Oscillator::nextValue (lo)            fm-processor.cpp:462-466
+//     fmBand_1.Pass: tmp += Buffer [newest - i] * filterKernel [i], i = 0 .. 24, every 6th sample
+//     fmBand_2.Pass: the same with D2 + 1 taps on every D2-th stage-1 output   fir-filters.cpp:397-424
+// with std::complex<float> products in the four-multiply form GCC emits without -ffast-math and no
+// FMA contraction, so the fm-rate samples are BIT-IDENTICAL to the
+// reference's (tests/test_gpu_parity.py::test_exact_front_end_is_bit_identical).
+//
+//   fx_dc_kernel      the RF DC one-pole is a float32 recurrence at the INPUT rate: every rounding
+//                     feeds the next step, so it is walked sample by sample, one lane per stream
+//                     (both components), loads prefetched a batch ahead.  ~14 cycles per sample:
+//                     this stage is latency-bound (7 ms per 0.5 s of signal for any number of
+//                     streams up to 32 x SMs), which is why the mode is opt-in / per decoder.
+//   frontend_exact_kernel   tile of 128 fm-rate outputs per CTA: the DC-free samples are staged in
+//                     shared memory (gain and oscillator applied on the way), thread t evaluates
+//                     the D2 stage-1 outputs behind fm sample t and the stage-2 sum in order.
+#pragma once
+#include "common.cuh"
+#include "frontend_fir.cuh"
+#include "frontend_poly.cuh"
+
+namespace sdrjfm {
+
+constexpr int kFxThreads = 128;                    // fm-rate outputs per CTA
+constexpr int kFxHist    = 32;                     // filter-input history kept per stream (>= 25)
+constexpr int kFxTaps1   = 25;                     // fmBand_1, fm-processor.cpp:68-71
+constexpr int kFxBatch   = 32;                     // samples per prefetch batch of the DC walker
+
+__constant__ float2 c_fx_taps [kFxTaps1 + 9 + 2];  // filterKernel of fmBand_1 [25], then of fmBand_2 [D2 + 1]
+
+// ---- RF DC removal, sample by sample ---------------------------------------------------------
+// x : [S][in_pitch] samples in format rf; xd : [S][out_pitch] float2 = x - clamp (RfDC) per component
+__global__ void __launch_bounds__ (32)
+fx_dc_kernel (const void *__restrict__ x, int64_t in_pitch, RawFmt rf, int64_t N, int32_t S,
+              float alpha, StreamState *__restrict__ state, float2 *__restrict__ xd, int64_t out_pitch,
+              int write_state) {
+const int stream = blockIdx.x * 32 + threadIdx.x;
+	if (stream >= S) return;
+StreamState &st = state [stream];
+const void *xs = reinterpret_cast<const char *>(x) + (int64_t)stream * in_pitch * fmt_bytes (rf.fmt);
+float2 *out = xd + (int64_t)stream * out_pitch;
+float rr = (float)st.dc_re, ri = (float)st.dc_im;    // RfDC: float32 in the reference; carried exactly in the double fields
+const float lim = 0.01f;                              // DCRlimit, :429
+float2 cur [kFxBatch], nxt [kFxBatch];
+	if (rf.fmt == kFmtCF32) {
+#pragma unroll
+	   for (int j = 0; j < kFxBatch; j ++) cur [j] = j < N ? __ldcs (reinterpret_cast<const float2 *>(xs) + j) : make_float2 (0.f, 0.f);
+	}
+	else {
+#pragma unroll
+	   for (int j = 0; j < kFxBatch; j ++) cur [j] = j < N ? load_iq_rt (xs, j, rf) : make_float2 (0.f, 0.f);
+	}
+	for (int64_t n0 = 0; n0 < N; n0 += kFxBatch) {
+	   const int64_t n1 = n0 + kFxBatch;
+	   if (rf.fmt == kFmtCF32) {
+#pragma unroll
+	      for (int j = 0; j < kFxBatch; j ++)
+	         nxt [j] = n1 + j < N ? __ldcs (reinterpret_cast<const float2 *>(xs) + n1 + j) : make_float2 (0.f, 0.f);
+	   }
+	   else {
+#pragma unroll
+	      for (int j = 0; j < kFxBatch; j ++) nxt [j] = n1 + j < N ? load_iq_rt (xs, n1 + j, rf) : make_float2 (0.f, 0.f);
+	   }
+#pragma unroll
+	   for (int j = 0; j < kFxBatch; j ++) {
+	      if (n0 + j < N) {
+	         const float2 v = cur [j];
+	         rr = fadd (fmul (fsub (v.x, rr), alpha), rr);                 // :425
+	         ri = fadd (fmul (fsub (v.y, ri), alpha), ri);
+	         const float cr = rr > lim ? lim : (rr < -lim ? -lim : rr);     // :430-443
+	         const float ci = ri > lim ? lim : (ri < -lim ? -lim : ri);
+	         __stcs (out + n0 + j, make_float2 (fsub (v.x, cr), fsub (v.y, ci)));   // :445
+	      }
+	   }
+#pragma unroll
+	   for (int j = 0; j < kFxBatch; j ++) cur [j] = nxt [j];
+	}
+	if (write_state) { st.dc_re = (double)rr; st.dc_im = (double)ri; }
+}
+
+// gain and oscillator of one filter-input sample (fm-processor.cpp:462-466); n = its index in the call
+__device__ __forceinline__ float2 fx_stage (const LoParams &L, float2 v, int64_t n) {
+	v = make_float2 (fmul (v.x, L.lgain), fmul (v.y, L.rgain));
+	if (L.tab) v = cmul_rn (v, L.tab [lo_index (L, n)]);     // lo == 0 multiplies by Table [0] = (1, 0): the identity
+	return v;
+}
+
+template <int D2_>
+struct Fx {
+	static constexpr int D2   = D2_;                       // stage-2 decimation (IRate / fmRate)
+	static constexpr int D    = 6 * D2;                    // input samples per fm-rate sample
+	static constexpr int NT2  = D2 + 1;                    // stage-2 taps, fm-processor.cpp:72-75
+	static constexpr int Span = D * kFxThreads + kFxTaps1; // staged inputs: D m0 - 25 .. D (m0 + 128) - 1
+	static constexpr int Slots = Span + Span / D + 2;      // one pad slot per D samples: odd thread stride
+	static constexpr int SmemBytes = Slots * (int)sizeof (float2);
+};
+
+// src   : filter-input samples of this call BEFORE gain / oscillator: xd (float2, fmt cf32) when the
+//         DC remover is on, else the raw samples in their device format
+// xhist : [S][kFxHist] the last filter inputs AFTER gain / oscillator of the previous call
+// Z     : [S][out_pitch] fm-rate samples (the reference's v after fmBand_2, :474)
+template <int D2>
+__global__ void __launch_bounds__ (kFxThreads)
+frontend_exact_kernel (const void *__restrict__ src, int64_t in_pitch, RawFmt rf,
+                       const float2 *__restrict__ xhist, const LoParams lop,
+                       float2 *__restrict__ Z, int64_t out_pitch, int32_t M) {
+typedef Fx<D2> P;
+constexpr int D = P::D;
+extern __shared__ float2 sm [];
+__shared__ float2 sY [kFxThreads + 1];
+const int tid = threadIdx.x;
+const int stream = blockIdx.y;
+const int64_t m0 = (int64_t)blockIdx.x * kFxThreads;
+const int64_t O = D * m0 - kFxTaps1;                   // call-relative index of staged element 0
+const int64_t N = (int64_t)M * D;
+const void *xs = reinterpret_cast<const char *>(src) + (int64_t)stream * in_pitch * fmt_bytes (rf.fmt);
+const float2 *hs = xhist + (int64_t)stream * kFxHist;
+	for (int e = tid; e < P::Span; e += kFxThreads) {
+	   const int64_t n = O + e;
+	   float2 v = make_float2 (0.f, 0.f);
+	   if (n < 0) v = hs [kFxHist + n];
+	   else if (n < N) v = fx_stage (lop, rf.fmt == kFmtCF32 ? __ldcs (reinterpret_cast<const float2 *>(xs) + n)
+	                                                          : load_iq_rt (xs, n, rf), n);
+	   sm [e + e / D] = v;
+	}
+	__syncthreads ();
+
+//	stage 1: the D2 outputs k = D2 (m0 + t) + j; output k reads inputs 6 k + 5 - i = D (m0 + t) + 6 j + 5 - i,
+//	i.e. staged element D t + q with q = 6 j + 30 - i
+const float2 *mine = sm + (D + 1) * tid;
+float2 y1 [D2];
+#pragma unroll
+	for (int j = 0; j < D2; j ++) {
+	   float2 acc = make_float2 (0.f, 0.f);
+#pragma unroll
+	   for (int i = 0; i < kFxTaps1; i ++) {
+	      const int q = 6 * j + 30 - i;
+	      const float2 p = cmul_rn (mine [q + q / D], c_fx_taps [i]);
+	      acc.x = fadd (acc.x, p.x); acc.y = fadd (acc.y, p.y);
+	   }
+	   y1 [j] = acc;
+	}
+	sY [tid + 1] = y1 [D2 - 1];
+	if (tid == 0) {             // stage-1 output D2 m0 - 1 (the newest one of the fm sample before the tile)
+	   float2 acc = make_float2 (0.f, 0.f);
+#pragma unroll
+	   for (int i = 0; i < kFxTaps1; i ++) {
+	      const int q = 24 - i;
+	      const float2 p = cmul_rn (sm [q + q / D], c_fx_taps [i]);
+	      acc.x = fadd (acc.x, p.x); acc.y = fadd (acc.y, p.y);
+	   }
+	   sY [0] = acc;
+	}
+	__syncthreads ();
+//	stage 2: tmp += y1 [D2 m + D2 - 1 - i] * K2 [i], i = 0 .. D2
+float2 z = make_float2 (0.f, 0.f);
+#pragma unroll
+	for (int i = 0; i < P::NT2; i ++) {
+	   const float2 a = i < D2 ? y1 [D2 - 1 - i] : sY [tid];
+	   const float2 p = cmul_rn (a, c_fx_taps [kFxTaps1 + i]);
+	   z.x = fadd (z.x, p.x); z.y = fadd (z.y, p.y);
+	}
+	if (m0 + tid < M) Z [(int64_t)stream * out_pitch + m0 + tid] = z;
+}
+
+// history for the next call: the last kFxHist filter inputs AFTER gain / oscillator
+__global__ void fx_roll_hist_kernel (const void *__restrict__ src, int64_t in_pitch, RawFmt rf, const LoParams lop,
+                                     const float2 *__restrict__ old_hist, float2 *__restrict__ new_hist, int64_t n_proc) {
+const int stream = blockIdx.x, i = threadIdx.x;
+	if (i >= kFxHist) return;
+const int64_t pos = n_proc - kFxHist + i;
+const void *xs = reinterpret_cast<const char *>(src) + (int64_t)stream * in_pitch * fmt_bytes (rf.fmt);
+	new_hist [(int64_t)stream * kFxHist + i] =
+	      pos >= 0 ? fx_stage (lop, load_iq_rt (xs, pos, rf), pos) : old_hist [(int64_t)stream * kFxHist + kFxHist + pos];
+}
+
+// entering the mode in mid-stream (decoder or oscillator changed between calls): the filter-input history
+// is rebuilt from the raw-sample history the composite front end keeps, with the DC estimate as it stands
+// (the reference subtracted the estimate of each sample's own time: a difference of < 1e-8 on 25 samples)
+__global__ void fx_seed_hist_kernel (const float2 *__restrict__ raw_hist, int hist_len, const LoParams lop,
+                                     const StreamState *__restrict__ state, int dc_remove, float2 *__restrict__ new_hist) {
+const int stream = blockIdx.x, i = threadIdx.x;
+	if (i >= kFxHist) return;
+float2 v = raw_hist [(int64_t)stream * hist_len + hist_len - kFxHist + i];
+	if (dc_remove) {
+	   const float lim = 0.01f;
+	   const float rr = (float)state [stream].dc_re, ri = (float)state [stream].dc_im;
+	   v.x = fsub (v.x, rr > lim ? lim : (rr < -lim ? -lim : rr));
+	   v.y = fsub (v.y, ri > lim ? lim : (ri < -lim ? -lim : ri));
+	}
+	new_hist [(int64_t)stream * kFxHist + i] = fx_stage (lop, v, (int64_t)i - kFxHist);
+}
+
+}	// namespace sdrjfm

@@ -32,6 +32,7 @@
 #include "frontend_fir.cuh"
 #include "frontend_poly.cuh"
 #include "frontend_tma.cuh"
+#include "frontend_exact.cuh"
 #include "resample.cuh"
 #include "discriminator.cuh"
 #include "sequential.cuh"
@@ -76,9 +77,13 @@ struct ConstImage {
 	float  poly [kPolyMaxTaps];
 	float2 pss [kPssTaps + 1];
 	float  alp [kAlpTaps];
+	float2 fx [kFxTaps1 + 9 + 2];
 	uint64_t sig;
 };
-static uint64_t g_const_sig = 0;          // signature of the image the device holds now
+// signature of the image each DEVICE holds now (the constant banks are per device and context:
+// a second handle on another device of the same process needs its own upload)
+constexpr int kMaxDevices = 64;
+static uint64_t g_const_sig [kMaxDevices] = { 0 };
 
 struct Lane {
 	sdrjfm_config cfg;
@@ -106,6 +111,12 @@ struct Lane {
 	float2 *d_hist [2] = { nullptr, nullptr }; int hist_sel = 0;
 	float2 *d_pend = nullptr; int pend = 0; // leftover raw samples (< decim per stream), in format pend_fmt
 	int     pend_fmt = 0;
+	// reference-order front end (frontend_exact.cuh; allocated when first used)
+	bool    auto_exact = true;              // SDRJFM_NO_AUTO_EXACT=1: only front_end_mode 2 selects it
+	float2 *d_xd = nullptr;                 // [S][cap_in] samples behind the per-sample DC remover
+	float2 *d_xhist [2] = { nullptr, nullptr }; int xhist_sel = 0;
+	bool    fx_hist_valid = false;          // d_xhist continues the stream (false after a composite call)
+	int64_t in_total = 0;                   // input samples consumed so far (per stream)
 	// rational polyphase resampler (front_end_mode 1): stage-A output and the stage-B state
 	bool    resample = false;
 	int     rsL = 0, rsM = 0, rsP = 0, rsHB = 0;
@@ -215,6 +226,7 @@ static void default_settings (Settings &s, int32_t fm_rate) {
 // copies the lane's constant image to the device (all launches of the process are drained first:
 // kernels of another configuration may still be reading the banks)
 static int consts_upload (Lane *h) {
+	CK (cudaSetDevice (h -> cfg.device));
 	CK (cudaDeviceSynchronize ());
 	CK (cudaMemcpyToSymbol (c_comp, h -> ci.comp, sizeof h -> ci.comp));
 	CK (cudaMemcpyToSymbol (c_rs_taps, h -> ci.rs_taps, sizeof h -> ci.rs_taps));
@@ -222,7 +234,8 @@ static int consts_upload (Lane *h) {
 	CK (cudaMemcpyToSymbol (c_poly, h -> ci.poly, sizeof h -> ci.poly));
 	CK (cudaMemcpyToSymbol (c_pss_taps, h -> ci.pss, sizeof h -> ci.pss));
 	CK (cudaMemcpyToSymbol (c_alp_taps, h -> ci.alp, sizeof h -> ci.alp));
-	g_const_sig = h -> ci.sig;
+	CK (cudaMemcpyToSymbol (c_fx_taps, h -> ci.fx, sizeof h -> ci.fx));
+	g_const_sig [h -> cfg.device] = h -> ci.sig;
 	return SDRJFM_OK;
 }
 // new contents: recompute the signature (FNV-1a over the image) and upload
@@ -231,12 +244,12 @@ uint64_t x = 1469598103934665603ull;
 const unsigned char *p = reinterpret_cast<const unsigned char *>(&h -> ci);
 	for (size_t i = 0; i < offsetof (ConstImage, sig); i ++) { x ^= p [i]; x *= 1099511628211ull; }
 	h -> ci.sig = x ? x : 1;
-	if (h -> ci.sig == g_const_sig) return SDRJFM_OK;
+	if (h -> ci.sig == g_const_sig [h -> cfg.device]) return SDRJFM_OK;
 	return consts_upload (h);
 }
 // before launching: the device must hold this lane's image
 static inline int consts_ensure (Lane *h) {
-	return h -> ci.sig == g_const_sig ? SDRJFM_OK : consts_upload (h);
+	return h -> ci.sig == g_const_sig [h -> cfg.device] ? SDRJFM_OK : consts_upload (h);
 }
 
 // uploads constant-memory taps and derives the launch parameters that depend on the tables
@@ -268,6 +281,13 @@ const int32_t lo_hz = h -> set.lo_hz;
 	   h -> lo_Hre = (float)H.real (); h -> lo_Him = (float)H.imag ();
 	}
 	memcpy (h -> ci.comp, comp, sizeof h -> ci.comp);
+	{  // K1x: the two filterKernels exactly as DecimatingFIR builds them (complex, fir-filters.cpp:327-347)
+	   memset (h -> ci.fx, 0, sizeof h -> ci.fx);
+	   if (th.ntaps1 == kFxTaps1 && th.ntaps2 <= 9) {
+	      memcpy (h -> ci.fx, h -> tables.payload () + th.off_fmband1, kFxTaps1 * sizeof (float2));
+	      memcpy (h -> ci.fx + kFxTaps1, h -> tables.payload () + th.off_fmband2, th.ntaps2 * sizeof (float2));
+	   }
+	}
 
 //	audio decimator taps (our own design, audio_out.cuh): Blackman-windowed sinc, fc = 20 kHz
 	{
@@ -471,7 +491,7 @@ int rsL = 0, rsM = 0, rsP = 0;
 	      decim = kRsStageADecim; shape = kShapeResample;
 	   }
 	}
-	else if (cfg -> front_end_mode != 0) { g_create_error = "front_end_mode must be 0 or 1"; return nullptr; }
+	else if (cfg -> front_end_mode != 0 && cfg -> front_end_mode != 2) { g_create_error = "front_end_mode must be 0, 1 or 2"; return nullptr; }
 	else if (cfg -> fm_rate == 192000 && cfg -> input_rate >= 12 * cfg -> fm_rate) {
 	   const int32_t irate = cfg -> input_rate / 6;
 	   decim = (cfg -> input_rate / irate) * (irate / cfg -> fm_rate);
@@ -485,7 +505,8 @@ int rsL = 0, rsM = 0, rsP = 0;
 	   *status = SDRJFM_ERR_UNSUPPORTED; return nullptr;
 	}
 int ndev = 0;
-	if (cudaGetDeviceCount (&ndev) != cudaSuccess || ndev <= cfg -> device) {
+	if (cfg -> device < 0 || cfg -> device >= kMaxDevices ||
+	    cudaGetDeviceCount (&ndev) != cudaSuccess || ndev <= cfg -> device) {
 	   g_create_error = "no CUDA device: this library has no CPU fallback";
 	   *status = SDRJFM_ERR_NO_DEVICE; return nullptr;
 	}
@@ -508,7 +529,8 @@ Lane *h = new Lane ();
 	   h -> hist_len_w = std::max (((fs.ngw - 1 + fs.gpt - 1) / fs.gpt) * rows, fs.ngw * fs.D);
 	   const char *env = getenv ("SDRJFM_GENERIC_FE"); h -> force_generic = env && env [0] == '1';
 	   env = getenv ("SDRJFM_NO_TMA"); h -> use_tma = !(env && env [0] == '1');
-	   env = getenv ("SDRJFM_TMA_CTAS"); h -> tma_ctas = env && atoi (env) > 0 ? atoi (env) : 0; }
+	   env = getenv ("SDRJFM_TMA_CTAS"); h -> tma_ctas = env && atoi (env) > 0 ? atoi (env) : 0;
+	   env = getenv ("SDRJFM_NO_AUTO_EXACT"); h -> auto_exact = !(env && env [0] == '1'); }
 	if (h -> cfg.working_rate <= 0) h -> cfg.working_rate = 48000;
 	if (h -> cfg.audio_rate <= 0) h -> cfg.audio_rate = h -> cfg.working_rate;
 	h -> n_sm = prop.multiProcessorCount;
@@ -574,6 +596,10 @@ cudaError_t e;
 	    (e = cudaFuncSetAttribute (frontend_tma_kernel<48, 1, 73>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                               kFtSmemBytes)) != cudaSuccess) return fail (e, "smem attr K1");
 	if ((e = poly_set_attr (shape)) != cudaSuccess) return fail (e, "smem attr K1g");
+	if ((e = cudaFuncSetAttribute (frontend_exact_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fx<2>::SmemBytes)) != cudaSuccess ||
+	    (e = cudaFuncSetAttribute (frontend_exact_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fx<5>::SmemBytes)) != cudaSuccess ||
+	    (e = cudaFuncSetAttribute (frontend_exact_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fx<8>::SmemBytes)) != cudaSuccess)
+	   return fail (e, "smem attr K1x");
 	{  const int seqsm = (cfg -> fm_rate / 4 + 1) * (int)sizeof (float);
 	   const auto A = cudaFuncAttributeMaxDynamicSharedMemorySize;
 	   if ((e = cudaFuncSetAttribute (sequential_kernel<0, false>, A, seqsm)) != cudaSuccess ||
@@ -615,7 +641,7 @@ void *ptrs [] = { h -> d_tables, h -> d_sin_quarter, h -> d_in, h -> d_hist [0],
 	              h -> d_rsy_c, h -> d_rsy_v, h -> d_rsy_w, h -> d_rsy_in,
 	              h -> d_scan_carry [0], h -> d_scan_carry [1], h -> d_scan_db, h -> d_plot,
 	              h -> d_spec_in, h -> d_spec_carry [0], h -> d_spec_carry [1], h -> d_spec_win,
-	              h -> d_spec_Y, h -> d_spec_avg, h -> d_spec_disp };
+	              h -> d_spec_Y, h -> d_spec_avg, h -> d_spec_disp, h -> d_xd, h -> d_xhist [0], h -> d_xhist [1] };
 	for (void *p : ptrs) if (p) cudaFree (p);
 	if (h -> stream_rds) { cudaStreamSynchronize (h -> stream_rds); cudaStreamDestroy (h -> stream_rds); }
 	if (h -> ev_k3) cudaEventDestroy (h -> ev_k3);
@@ -771,6 +797,59 @@ float2 *U = wide ? h -> d_Uw : h -> d_U, *Sb = wide ? h -> d_Sw : h -> d_S;
 	return SDRJFM_OK;
 }
 
+// the reference-order front end is in force for this call?
+static bool exact_wanted (const Lane *h) {
+	if (h -> resample || h -> set.input_filter_hz > 0 || h -> shape > 2) return false;   // inputFilter: an FFT filter sits between the oscillator and fmBand_1
+	if (h -> cfg.front_end_mode == 2) return true;
+	return h -> auto_exact && (h -> set.decoder == 2 || h -> set.decoder == 5 || h -> set.lo_hz != 0);
+}
+
+// K1x: per-sample DC removal, then the two decimators in the reference's operation order -> d_U = fm-rate samples
+static int launch_frontend_exact (Lane *h, const void *src, RawFmt rf, int64_t pitch, int32_t M, int64_t n_proc, bool dry) {
+const int S = h -> cfg.n_streams;
+	{ const int rc = consts_ensure (h); if (rc != SDRJFM_OK) return rc; }
+	if (!h -> d_xd) {
+	   CK (dalloc (&h -> d_xd, (size_t)S * h -> cap_in));
+	   CK (dalloc (&h -> d_xhist [0], (size_t)S * kFxHist)); CK (dalloc (&h -> d_xhist [1], (size_t)S * kFxHist));
+	}
+LoParams lp;
+	memset (&lp, 0, sizeof lp);
+	lp.lgain = h -> set.lgain; lp.rgain = h -> set.rgain;
+	lp.rate = h -> cfg.input_rate; lp.phase = h -> lo_phase;
+	if (h -> set.lo_hz != 0) { lp.tab = h -> d_lo_tab; lp.lo = h -> set.lo_hz; }
+	if (!h -> fx_hist_valid && !dry) {
+	   if (h -> in_total > 0) {
+	      fx_seed_hist_kernel<<<S, kFxHist, 0, h -> stream>>> (h -> d_hist [h -> hist_sel], h -> hist_len, lp, h -> d_state,
+	                                                         h -> set.dc_remove, h -> d_xhist [h -> xhist_sel]);
+	      h -> launches ++;
+	   }
+	   else CK (cudaMemsetAsync (h -> d_xhist [h -> xhist_sel], 0, (size_t)S * kFxHist * sizeof (float2), h -> stream));
+	   h -> fx_hist_valid = true;
+	}
+const void *fsrc = src; RawFmt frf = rf; int64_t fpitch = pitch;
+	if (h -> set.dc_remove) {
+	   fx_dc_kernel<<<(S + 31) / 32, 32, 0, h -> stream>>> (src, pitch, rf, n_proc, S, 1.0f / (float)h -> cfg.input_rate,
+	                                                      h -> d_state, h -> d_xd, h -> cap_in, dry ? 0 : 1);
+	   h -> launches ++;
+	   fsrc = h -> d_xd; fpitch = h -> cap_in;
+	   memset (&frf, 0, sizeof frf); frf.fmt = kFmtCF32; frf.scale = 1.f;
+	}
+const dim3 grid ((unsigned)((M + kFxThreads - 1) / kFxThreads), (unsigned)S);
+const float2 *xh = h -> d_xhist [h -> xhist_sel];
+	switch (h -> decim / 6) {
+	   case 2:  frontend_exact_kernel<2><<<grid, kFxThreads, Fx<2>::SmemBytes, h -> stream>>> (fsrc, fpitch, frf, xh, lp, h -> d_U, h -> cap_fm, M); break;
+	   case 5:  frontend_exact_kernel<5><<<grid, kFxThreads, Fx<5>::SmemBytes, h -> stream>>> (fsrc, fpitch, frf, xh, lp, h -> d_U, h -> cap_fm, M); break;
+	   default: frontend_exact_kernel<8><<<grid, kFxThreads, Fx<8>::SmemBytes, h -> stream>>> (fsrc, fpitch, frf, xh, lp, h -> d_U, h -> cap_fm, M); break;
+	}
+	h -> launches ++;
+	if (!dry) {
+	   fx_roll_hist_kernel<<<S, kFxHist, 0, h -> stream>>> (fsrc, fpitch, frf, lp, xh, h -> d_xhist [h -> xhist_sel ^ 1], n_proc);
+	   h -> xhist_sel ^= 1; h -> launches ++;
+	}
+	CK (cudaGetLastError ());
+	return SDRJFM_OK;
+}
+
 // buffers of the wide (input filter ON) front end; cleared start
 static int wide_setup (Lane *h) {
 const int64_t S = h -> cfg.n_streams;
@@ -800,6 +879,7 @@ static int lane_run_frontend_only (Lane *h, const void *d_iq, int32_t fmt, float
 	CK (cudaSetDevice (h -> cfg.device));
 	if (fmt == kFmtAirspy) { h -> err = "front-end-only timing takes the rate-converted formats"; return SDRJFM_ERR_ARG; }
 const RawFmt rf = make_rawfmt (h, fmt, scale);
+	if (exact_wanted (h)) return launch_frontend_exact (h, d_iq, rf, in_pitch, (int32_t)(n_in / h -> decim), (n_in / h -> decim) * h -> decim, true);
 	return launch_frontend (h, d_iq, rf, in_pitch, (int32_t)(n_in / h -> decim));
 }
 
@@ -874,7 +954,11 @@ int32_t M = M1;
 int rc;
 //	K1 ------------------------------------------------------------------------------------
 const bool wide = st.input_filter_hz > 0;
-	if ((rc = launch_frontend (h, src, rf, pitch, M1)) != SDRJFM_OK) return rc;
+const bool exact = exact_wanted (h);
+	if (exact) rc = launch_frontend_exact (h, src, rf, pitch, M1, n_proc, false);
+	else { rc = launch_frontend (h, src, rf, pitch, M1); h -> fx_hist_valid = false; }
+	if (rc != SDRJFM_OK) return rc;
+	h -> in_total += n_proc;
 	if (wide) {
 	   roll_history_raw_kernel<<<dim3 ((h -> hist_len_w + 159) / 160, S), 160, 0, h -> stream>>> (
 	         src, pitch, rf, h -> d_histw [h -> histw_sel], h -> d_histw [h -> histw_sel ^ 1], n_proc, h -> hist_len_w);
@@ -926,7 +1010,7 @@ DiscrParams dp;
 	dp.decim = h -> decim;
 	dp.lo_phase = h -> lo_phase; dp.Hre = h -> lo_Hre; dp.Him = h -> lo_Him;
 	if (st.lo_hz != 0) {
-	   dp.lo_tab = h -> d_lo_tab;
+	   if (!exact) dp.lo_tab = h -> d_lo_tab;
 	   int64_t np = (h -> lo_phase - (int64_t)st.lo_hz * n_proc) % h -> cfg.input_rate;
 	   h -> lo_phase = np < 0 ? np + h -> cfg.input_rate : np;       // LOPhase after this call's samples
 	}
@@ -942,6 +1026,11 @@ DiscrParams dp;
 	dp.lgain = st.lgain; dp.rgain = st.rgain;
 	dp.dc_remove = st.dc_remove; dp.decoder = st.decoder;
 	dp.scan_only = h -> scanning;
+	dp.exact = exact;
+	if (exact) {      // K1x delivered the reference's fm-rate samples: K2 only normalises and discriminates
+	   dp.dc_remove = 0; dp.sumC = dp.sumCm = 0.f; dp.gb0 = dp.gb1 = dp.gb2 = 0.f;
+	   dp.lgain = dp.rgain = 1.f; dp.Gre = 1.f; dp.Gim = 0.f;
+	}
 const int32_t ntiles = (M + kDiBlock - 1) / kDiBlock;
 	{
 	   dim3 g ((unsigned)ntiles, (unsigned)S);
@@ -1229,11 +1318,12 @@ static int lane_process_device (Lane *h, const void *d_iq, int32_t fmt, float sc
 	if (fmt < kFmtCF32 || fmt > kFmtAirspy) return SDRJFM_ERR_ARG;
 	if (n_in > h -> cfg.max_samples_per_call) { h -> err = "n_in exceeds max_samples_per_call"; return SDRJFM_ERR_CAPACITY; }
 	CK (cudaSetDevice (h -> cfg.device));
+//	every argument / format check comes BEFORE anything is staged or any state moves
+	if (fmt != kFmtAirspy && h -> air_pend) { h -> err = "sample format changed while samples were pending"; return SDRJFM_ERR_ARG; }
 const void *src; int64_t pitch, n_proc;
 int rc = fmt == kFmtAirspy ? stage_input_airspy (h, d_iq, n_in, in_pitch, &src, &pitch, &n_proc)
                            : stage_input (h, d_iq, fmt, n_in, in_pitch, cudaMemcpyDeviceToDevice, &src, &pitch, &n_proc);
 	if (rc != SDRJFM_OK) return rc;
-	if (fmt != kFmtAirspy && h -> air_pend) { h -> err = "sample format changed while samples were pending"; return SDRJFM_ERR_ARG; }
 const RawFmt rf = make_rawfmt (h, fmt, scale);
 	return run_chain (h, src, rf, pitch, n_proc, (float2 *)d_audio, audio_pitch, n_audio,
 	                  (float2 *)d_rds24, rds_pitch, n_rds);
@@ -1321,6 +1411,9 @@ static int lane_set_sound_balance (Lane *h, int32_t balance) {
 }
 static int lane_set_deemphasis (Lane *h, int32_t v) {
 	if (!h || v < 1) return SDRJFM_ERR_ARG;
+//	K6 restarts the one-pole kAuWarm = 384 samples ahead of every tile from a zero state: the state
+//	error left is (1 - alpha)^384, below 1e-8 only up to 100 us (the GUI offers 1 ("Off"), 50 and 75)
+	if (v > 100) { h -> err = "de-emphasis time constants above 100 us are not supported (tile warm-up of the one-pole)"; return SDRJFM_ERR_UNSUPPORTED; }
 float Tau = 1000000.0 / v;                                                // :295-296
 	h -> set.deemph_us = v;
 	h -> set.deemph_alpha = 1.0 / (float (h -> cfg.fm_rate) / Tau + 1.0);
@@ -1659,10 +1752,31 @@ static int lane_tables_export (const Lane *h, void *out, int64_t cap) {
 static int lane_tables_import (Lane *h, const void *blob, int64_t nbytes) {
 	if (!h || !blob || nbytes < (int64_t)sizeof (TableHeader)) return SDRJFM_ERR_ARG;
 const TableHeader *th = (const TableHeader *)blob;
-	if (th -> magic != 0x54464A53u ||
+	if (th -> magic != 0x54464A53u || th -> payload_floats < 0 ||
 	    nbytes != (int64_t)(sizeof (TableHeader) + th -> payload_floats * sizeof (float)) ||
 	    th -> input_rate != h -> cfg.input_rate || th -> fm_rate != h -> cfg.fm_rate)
 	   return SDRJFM_ERR_ARG;
+//	the blob comes from another rank: nothing in it is trusted.  It must describe THIS handle's
+//	configuration (the kernels are chosen from the handle's settings) and every table must lie
+//	inside the payload.
+const TableBlob &mine = h -> tables;
+const TableHeader &my = mine.hdr ();
+	if (th -> version != my.version || th -> ncomp != my.ncomp || th -> ncomp > 96 || th -> ncomp < 1 ||
+	    th -> ntaps1 != my.ntaps1 || th -> ntaps2 != my.ntaps2 || th -> decim1 != my.decim1 || th -> decim2 != my.decim2 ||
+	    th -> ncomp_wide != my.ncomp_wide || th -> payload_floats != my.payload_floats ||
+	    th -> input_filter_hz != h -> set.input_filter_hz ||
+	    th -> rs_L != my.rs_L || th -> rs_M != my.rs_M || th -> rs_P != my.rs_P || th -> rs_ntapsA != my.rs_ntapsA) {
+	   h -> err = "table blob does not match this handle's rates / filter settings"; return SDRJFM_ERR_ARG;
+	}
+	{  // same designer, same configuration: the layout must be the one this handle computed itself
+	   const int64_t *a = &th -> off_fmband1, *b = &my.off_fmband1;
+	   const int noff = (int)((&th -> off_comp_wide - &th -> off_fmband1) + 1);
+	   for (int i = 0; i < noff; i ++) if (a [i] != b [i] || a [i] < 0 || a [i] > th -> payload_floats) {
+	      h -> err = "table blob layout differs from this build's"; return SDRJFM_ERR_ARG;
+	   }
+	   if (th -> off_rsA != my.off_rsA || th -> off_rsB != my.off_rsB || th -> off_squelch != my.off_squelch ||
+	       th -> off_rds_sym != my.off_rds_sym) { h -> err = "table blob layout differs from this build's"; return SDRJFM_ERR_ARG; }
+	}
 	CK (cudaSetDevice (h -> cfg.device));
 	CK (cudaStreamSynchronize (h -> stream));
 	h -> tables.bytes.assign ((const unsigned char *)blob, (const unsigned char *)blob + nbytes);

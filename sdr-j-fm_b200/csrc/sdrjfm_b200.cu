@@ -9,12 +9,23 @@
 // SDRJFM_ERR_NO_DEVICE.
 #include "lane_impl.cuh"
 #include <cstdlib>
+#include <mutex>
 
 // A handle with 4 lanes works on 11 CUDA streams (lane + RDS side stream each, the caller's stream, two
 // copy streams).  The driver maps streams onto 8 hardware queues by default, which makes independent
 // streams wait for each other; when this library is loaded before the process creates its CUDA context
 // (and the host did not choose a value itself) it asks for 32.  Measured: 4.36 -> 4.30 ms per bench step.
-namespace { struct QueueHint { QueueHint () { setenv ("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); } } g_queue_hint; }
+// This writes one variable of the host process's environment at load time and never overrides a value
+// the host set; SDRJFM_NO_ENV_HINT=1 switches it off (documented in include/sdrjfm_b200.h).
+namespace { struct QueueHint { QueueHint () {
+	const char *off = getenv ("SDRJFM_NO_ENV_HINT");
+	if (!(off && off [0] == '1')) setenv ("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); } } g_queue_hint; }
+
+// The tap sets live in __constant__ banks shared by every handle on a device (lane_impl.cuh), and a
+// call's launches must see the image that was ensured at its start: calls into handles on the SAME
+// device are serialised on the host side (enqueueing only; the GPU work of different handles still
+// overlaps).  Recursive: the host entry points call the device ones.
+static std::recursive_mutex g_dev_mutex [kMaxDevices];
 
 struct sdrjfm_handle {
 	sdrjfm_config cfg;
@@ -29,8 +40,11 @@ struct sdrjfm_handle {
 	int64_t cap_in = 0, cap_audio = 0, cap_rds = 0;
 	float2 *d_in [2] = { nullptr, nullptr }; // host-call staging [S][cap_in] (second one on first pipelined call)
 	float2 *d_audio = nullptr, *d_rds24 = nullptr;
+	bool poisoned = false;                  // a call failed after state had moved: streams are desynchronised
 	std::string err;
 };
+#define LOCK_DEV(h) std::lock_guard<std::recursive_mutex> lock_ (g_dev_mutex [(h) -> cfg.device])
+#define CHECK_POISON(h) do { if ((h) -> poisoned) { (h) -> err = "handle poisoned: an earlier call failed after stream state had moved; destroy and re-create it"; return SDRJFM_ERR_CUDA; } } while (0)
 
 #define HK(call)                                                                          \
 	do { cudaError_t e_ = (call); if (e_ != cudaSuccess) {                                \
@@ -47,9 +61,16 @@ static int lane_of (const sdrjfm_handle *h, int32_t stream) {
 // applies one lane-level call to every lane, stopping at (and reporting) the first failure
 template <typename F> static int for_lanes (sdrjfm_handle *h, F f) {
 	if (!h) return SDRJFM_ERR_ARG;
-	for (Lane *l : h -> lanes) {
+	LOCK_DEV (h);
+	CHECK_POISON (h);
+	for (size_t i = 0; i < h -> lanes.size (); i ++) {
+	   Lane *l = h -> lanes [i];
 	   const int rc = f (l);
-	   if (rc != SDRJFM_OK) { h -> err = l -> err; return rc; }
+	   if (rc != SDRJFM_OK) {
+	      h -> err = l -> err;
+	      if (i > 0) h -> poisoned = true;    // earlier lanes already took the setting: the lanes disagree now
+	      return rc;
+	   }
 	}
 	return SDRJFM_OK;
 }
@@ -65,7 +86,16 @@ const size_t nl = h -> lanes.size ();
 	   Lane *l = h -> lanes [i];
 	   if (nl > 1) HK (cudaStreamWaitEvent (l -> stream, h -> ev_fork, 0));
 	   const int rc = f (l, h -> first [i]);
-	   if (rc != SDRJFM_OK) { h -> err = l -> err; return rc; }
+	   if (rc != SDRJFM_OK) {
+	      h -> err = l -> err;
+//	      argument errors are detected by every lane before it touches anything; any other failure, or
+//	      one after an earlier lane ran, leaves the lanes' streams out of step
+	      if (i > 0 || (rc != SDRJFM_ERR_ARG && rc != SDRJFM_ERR_CAPACITY && rc != SDRJFM_ERR_UNSUPPORTED)) {
+	         cudaDeviceSynchronize ();
+	         h -> poisoned = true;
+	      }
+	      return rc;
+	   }
 	   if (nl > 1) {
 	      HK (cudaEventRecord (h -> ev_join [i], l -> stream));
 	      HK (cudaStreamWaitEvent (h -> stream, h -> ev_join [i], 0));
@@ -91,6 +121,8 @@ int dummy; if (!status) status = &dummy;
 //	lanes: groups of >= 32 streams, at most 4 (SDRJFM_LANES overrides)
 int nl = std::min (4, std::max (1, cfg -> n_streams / 32));
 	{ const char *env = getenv ("SDRJFM_LANES"); if (env && atoi (env) > 0) nl = std::min (atoi (env), cfg -> n_streams); }
+	if (cfg -> device < 0 || cfg -> device >= kMaxDevices) { g_create_error = "bad device ordinal"; return nullptr; }
+std::lock_guard<std::recursive_mutex> lock_ (g_dev_mutex [cfg -> device]);
 sdrjfm_handle *h = new sdrjfm_handle ();
 	h -> cfg = *cfg;
 	for (int i = 0; i < nl; i ++) {
@@ -136,6 +168,7 @@ const size_t S = cfg -> n_streams;
 
 int sdrjfm_destroy (sdrjfm_handle *h) {
 	if (!h) return SDRJFM_ERR_ARG;
+	LOCK_DEV (h);
 	cudaSetDevice (h -> cfg.device);
 	if (h -> stream) cudaStreamSynchronize (h -> stream);
 	for (Lane *l : h -> lanes) lane_destroy (l);
@@ -160,6 +193,7 @@ int64_t n = 0;
 
 int sdrjfm_sync (sdrjfm_handle *h) {
 	if (!h) return SDRJFM_ERR_ARG;
+	LOCK_DEV (h);
 	HK (cudaStreamSynchronize (h -> stream));
 	return for_lanes (h, [](Lane *l) { return lane_sync (l); });
 }
@@ -184,6 +218,8 @@ static int process_dev (sdrjfm_handle *h, const void *d_iq, int32_t fmt, float s
                         float *d_rds24, int64_t rds_pitch, int64_t *n_rds) {
 	if (!h || n_in < 0 || (n_in > 0 && (!d_iq || in_pitch < n_in))) return SDRJFM_ERR_ARG;
 	if (n_in > h -> cfg.max_samples_per_call) { h -> err = "n_in exceeds max_samples_per_call"; return SDRJFM_ERR_CAPACITY; }
+	LOCK_DEV (h);
+	CHECK_POISON (h);
 	HK (cudaSetDevice (h -> cfg.device));
 int64_t na = 0, nr = 0;
 const int64_t bps = fmt_bytes (fmt);
@@ -226,6 +262,8 @@ int sdrjfm_run_frontend_only_raw (sdrjfm_handle *h, const void *d_iq, int32_t fo
 float scale;
 int rc = raw_scale (h, format, denominator, &scale);
 	if (rc != SDRJFM_OK) return rc;
+	LOCK_DEV (h);
+	CHECK_POISON (h);
 	HK (cudaSetDevice (h -> cfg.device));
 const int64_t bps = fmt_bytes (format);
 	return fork_join (h, [&](Lane *l, int32_t s0) {
@@ -238,6 +276,8 @@ static int process_host (sdrjfm_handle *h, const void *iq, int32_t fmt, float sc
                          float *rds24, int64_t rds_pitch, int64_t *n_rds, sdrjfm_meta *meta) {
 	if (!h || n_in < 0 || (n_in > 0 && (!iq || in_pitch < n_in))) return SDRJFM_ERR_ARG;
 	if (n_in > h -> cfg.max_samples_per_call) { h -> err = "n_in exceeds max_samples_per_call"; return SDRJFM_ERR_CAPACITY; }
+	LOCK_DEV (h);
+	CHECK_POISON (h);
 	HK (cudaSetDevice (h -> cfg.device));
 const int S = h -> cfg.n_streams;
 const size_t bps = (size_t)fmt_bytes (fmt);
@@ -251,7 +291,16 @@ int64_t kSlices = 16;
 	{ const char *env = getenv ("SDRJFM_SLICES"); if (env && atoi (env) > 0) kSlices = atoi (env); }
 const int64_t unit = 256 * (int64_t)h -> lanes [0] -> decim;
 const int64_t slice = ((n_in / kSlices) / unit) * unit;          // multiple of the decimation
-	if (!h -> cfg.keep_taps && h -> lanes [0] -> lf_plot < 0 && slice >= (1 << 16)) {
+//	The per-call side outputs (RDS bits, scan blocks, scope stream) describe ONE chain call: they would
+//	be overwritten slice by slice, so calls that produce them are not cut.
+const Lane *l0 = h -> lanes [0];
+	if (!h -> cfg.keep_taps && l0 -> lf_plot < 0 && !l0 -> rds_symbols && !l0 -> scanning && slice >= (1 << 16)) {
+//	   output capacities are checked before the first slice moves any state: a call of n_in samples
+//	   yields at most n_in / decim / 4 + 1 audio and n_in / decim / 8 + 1 RDS samples per stream
+	   const int64_t max_fm = (n_in + l0 -> pend) / l0 -> decim + 1;
+	   if ((audio && audio_pitch < max_fm / kRsDecim + 1) || (rds24 && l0 -> set.rds_mode != 0 && rds_pitch < max_fm / 8 + 1)) {
+	      h -> err = "audio_pitch / rds_pitch too small for this call"; return SDRJFM_ERR_ARG;
+	   }
 	   if (!h -> copy_stream) {
 	      HK (cudaStreamCreateWithFlags (&h -> copy_stream, cudaStreamNonBlocking));
 	      HK (cudaStreamCreateWithFlags (&h -> out_stream, cudaStreamNonBlocking));
@@ -275,11 +324,13 @@ const int64_t slice = ((n_in / kSlices) / unit) * unit;          // multiple of 
 	      rc = process_dev (h, h -> d_in [b], fmt, scale, len, h -> cap_in,
 	                        (float *)(h -> d_audio + na), h -> cap_audio, &a1,
 	                        (float *)(h -> d_rds24 + nr), h -> cap_rds, &r1);
-	      if (rc != SDRJFM_OK) return rc;
+	      if (rc != SDRJFM_OK) {
+	         if (c > 0) { cudaDeviceSynchronize (); h -> poisoned = true; }     // earlier slices already advanced the streams
+	         return rc;
+	      }
 	      HK (cudaEventRecord (h -> ev_done [b], h -> stream));
 //	      this slice's outputs go back on a third stream (PCIe is full duplex) while the next slices run
 	      if ((audio && a1 > 0) || (rds24 && r1 > 0)) {
-	         if ((audio && audio_pitch < na + a1) || (rds24 && rds_pitch < nr + r1)) return SDRJFM_ERR_ARG;
 	         HK (cudaStreamWaitEvent (h -> out_stream, h -> ev_done [b], 0));
 	         if (audio && a1 > 0)
 	            HK (cudaMemcpy2DAsync ((float2 *)audio + na, audio_pitch * sizeof (float2), h -> d_audio + na,
@@ -347,6 +398,7 @@ int rc = raw_scale (h, format, denominator, &scale);
 
 int sdrjfm_get_meta (sdrjfm_handle *h, sdrjfm_meta *meta) {
 	if (!h || !meta) return SDRJFM_ERR_ARG;
+	LOCK_DEV (h);
 	HK (cudaStreamSynchronize (h -> stream));
 	for (size_t i = 0; i < h -> lanes.size (); i ++) {
 	   const int rc = lane_get_meta (h -> lanes [i], meta + h -> first [i]);
@@ -357,6 +409,7 @@ int sdrjfm_get_meta (sdrjfm_handle *h, sdrjfm_meta *meta) {
 
 int sdrjfm_pilot_stats (sdrjfm_handle *h, int32_t *out) {
 	if (!h || !out) return SDRJFM_ERR_ARG;
+	LOCK_DEV (h);
 	HK (cudaStreamSynchronize (h -> stream));
 	for (size_t i = 0; i < h -> lanes.size (); i ++) {
 	   const int rc = lane_pilot_stats (h -> lanes [i], out + 4 * h -> first [i]);
@@ -367,6 +420,7 @@ int sdrjfm_pilot_stats (sdrjfm_handle *h, int32_t *out) {
 
 int64_t sdrjfm_read_tap (sdrjfm_handle *h, int which, int32_t stream, void *out, int64_t cap) {
 	if (!h || !out) return SDRJFM_ERR_ARG;
+	LOCK_DEV (h);
 const int i = lane_of (h, stream);
 	if (i < 0) return SDRJFM_ERR_ARG;
 	HK (cudaStreamSynchronize (h -> stream));
@@ -401,6 +455,7 @@ int sdrjfm_set_lf_spectrum (sdrjfm_handle *h, int32_t spectrum_size, int32_t dis
 }
 int64_t sdrjfm_read_lf_spectrum (sdrjfm_handle *h, int32_t stream, double *display, int64_t cap, int32_t *blocks) {
 	if (!h || !display) return SDRJFM_ERR_ARG;
+	LOCK_DEV (h);
 const int i = lane_of (h, stream);
 	if (i < 0) return SDRJFM_ERR_ARG;
 	HK (cudaStreamSynchronize (h -> stream));
@@ -411,6 +466,7 @@ const int64_t n = lane_read_lf_spectrum (h -> lanes [i], stream - h -> first [i]
 int64_t sdrjfm_read_lf_plot (sdrjfm_handle *h, int32_t stream, float *out, int64_t cap,
                              int32_t *sample_rate, int32_t *show_full) {
 	if (!h || !out) return SDRJFM_ERR_ARG;
+	LOCK_DEV (h);
 const int i = lane_of (h, stream);
 	if (i < 0) return SDRJFM_ERR_ARG;
 	HK (cudaStreamSynchronize (h -> stream));
@@ -425,6 +481,7 @@ const int t = l -> lf_plot;
 }
 int64_t sdrjfm_read_scan (sdrjfm_handle *h, int32_t stream, float *out, int64_t cap_pairs) {
 	if (!h || !out) return SDRJFM_ERR_ARG;
+	LOCK_DEV (h);
 const int i = lane_of (h, stream);
 	if (i < 0) return SDRJFM_ERR_ARG;
 	HK (cudaStreamSynchronize (h -> stream));
@@ -434,6 +491,7 @@ const int64_t n = lane_read_scan (h -> lanes [i], stream - h -> first [i], out, 
 }
 int64_t sdrjfm_read_rds_bits (sdrjfm_handle *h, int32_t stream, uint8_t *out, int64_t cap) {
 	if (!h || !out) return SDRJFM_ERR_ARG;
+	LOCK_DEV (h);
 const int i = lane_of (h, stream);
 	if (i < 0) return SDRJFM_ERR_ARG;
 	HK (cudaStreamSynchronize (h -> stream));
@@ -463,6 +521,7 @@ int sdrjfm_tables_export (const sdrjfm_handle *h, void *out, int64_t cap) {
 	return h ? lane_tables_export (h -> lanes [0], out, cap) : SDRJFM_ERR_ARG;
 }
 int sdrjfm_tables_import (sdrjfm_handle *h, const void *blob, int64_t nbytes) {
+//	validated by every lane BEFORE anything is replaced (lane_tables_import), so a bad blob leaves the handle as it was
 	return for_lanes (h, [&](Lane *l) { return lane_tables_import (l, blob, nbytes); });
 }
 
