@@ -53,7 +53,10 @@ typedef struct sdrjfm_config {
                                       stage 1 /6, stage 2 /(inputRate/6/fmRate) = /12, /30, /48  */
     int32_t fm_rate;               /* fmRate, 192000 (radio.cpp:68)                      */
     int32_t working_rate;          /* workingRate, 48000 (radio.cpp:233)                 */
-    int32_t audio_rate;            /* audioRate, 48000 (main.cpp:42)                     */
+    int32_t audio_rate;            /* audioRate, 48000 (main.cpp:42); 192000 with -m (main.cpp:57-65), or the ini
+                                      file's value (radio.cpp:250-252).  When it differs from working_rate the
+                                      second converter runs (theConverter, fm-processor.cpp:89-91, 825-838) and
+                                      the audio output of the process calls is at audio_rate               */
     int32_t n_streams;             /* independent IQ streams handled by this handle (>=1)*/
     int32_t device;                /* CUDA device ordinal                                */
     int64_t max_samples_per_call;  /* per stream; sizes the device buffers               */
@@ -87,8 +90,9 @@ typedef struct sdrjfm_meta {
     int32_t pss_state;             /* EPssState 0 OFF, 1 ANALYZING, 2 ESTABLISHED (:676) */
     float   pilot_lock_strength;   /* PilotPllLockStrength (:666)                        */
     int32_t pilot_locked;          /* PilotPllLocked                                     */
-    float   peak_left_db, peak_right_db; /* reserved (0): evaluatePeakLevel (:772-798) and insertTestTone work on
-                                            the 48 kHz PCM the caller already holds; see INTEGRATION.md      */
+    float   peak_left_db, peak_right_db; /* the newest showPeakLevel read-out (evaluatePeakLevel, :772-798: peak of
+                                            |left|, |right| per 961 PCM samples in dB, behind the display delay
+                                            line); -40 before the first.  All read-outs: sdrjfm_read_peak_levels */
     int32_t squelch_active;        /* getSquelchState (:217-219)                          */
 } sdrjfm_meta;
 
@@ -247,6 +251,16 @@ int64_t sdrjfm_read_rds_bits (sdrjfm_handle *h, int32_t stream, uint8_t *bits, i
 int  sdrjfm_set_squelch_mode (sdrjfm_handle *h, int32_t mode);     /* set_squelchMode: 0 OFF, 1 NSQ (noise), 2 LSQ (level) */
 int  sdrjfm_set_squelch_value (sdrjfm_handle *h, int32_t value);   /* set_squelchValue: 0..100 */
 int  sdrjfm_set_auto_mono (sdrjfm_handle *h, int32_t on);          /* setAutoMonoMode */
+/* setTestTone (fm-processor.cpp:931-933; insertTestTone :800-823): while on, every working-rate PCM sample is
+ * scaled by (1 - 0.9) and a 25 ms burst of a 1 kHz tone at level 0.9 is added every 2 s + 1 sample, behind the
+ * fade-in and in front of the peak meter, exactly as the reference's state machine does.                   */
+int  sdrjfm_set_test_tone (sdrjfm_handle *h, int32_t on);
+/* setDispDelay (:935-937): steps of the peak meter's display delay line (0 .. 512); restarts the line.    */
+int  sdrjfm_set_disp_delay (sdrjfm_handle *h, int32_t steps);
+/* the (left dB, right dB) pairs the reference would have emitted through showPeakLevel during the LAST process
+ * call (one per 961 working-rate samples, counted from the start of the processor), oldest first; returns
+ * their number.  At most 1024 - delay read-outs of a call are kept.                                        */
+int64_t sdrjfm_read_peak_levels (sdrjfm_handle *h, int32_t stream, float *db_pairs, int64_t cap_pairs);
 int  sdrjfm_set_pss_mode (sdrjfm_handle *h, int32_t on);           /* setPSSMode */
 int  sdrjfm_set_dc_remove (sdrjfm_handle *h, int32_t on);          /* setDCRemove (also zeroes RfDC) */
 int  sdrjfm_trigger_frequency_change (sdrjfm_handle *h);           /* triggerFrequencyChange */

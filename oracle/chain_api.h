@@ -103,6 +103,13 @@ void    ref_rds1_destroy (void *h);
 int64_t ref_rds1_process (void *h, const float *rds24, int64_t n, uint8_t *bits, int64_t cap);
 int32_t ref_rds1_dump (void *h, int which, float *out, int32_t cap);
 
+/* working-rate post-processing (ref_ only): insertTestTone + evaluatePeakLevel with the display delay line
+ * (src/fm/fm-processor.cpp:772-823), restated in ref_harness.cpp.  See there.                               */
+void   *ref_post_create (int32_t working_rate);
+void    ref_post_destroy (void *h);
+void    ref_post_set (void *h, int32_t tone_on, int32_t delay_steps);
+int64_t ref_post_process (void *h, const float *pcm, int64_t n, float *pcm_out, float *peaks, int64_t cap_pairs);
+
 /* `which` for *_dump_taps (complex entries unless noted) */
 enum {
     DUMP_FMBAND1 = 0,      /* 25 complex                      */

@@ -232,3 +232,34 @@ def ref_scan_blocks(fm_z):
     out = np.zeros((len(z) // 1024 + 1, 2), np.float32)
     n = lib.ref_scan_blocks(z.ctypes.data, len(z), out.ctypes.data)
     return out[:n].copy()
+
+
+class RefPost:
+    """insertTestTone + evaluatePeakLevel (fm-processor.cpp:772-823) as restated in ref_harness.cpp (ref_ only)."""
+
+    def __init__(self, working_rate=48000):
+        self.lib = C.CDLL(_PATHS["ref"])
+        self.lib.ref_post_create.restype = C.c_void_p
+        self.lib.ref_post_create.argtypes = [C.c_int32]
+        self.lib.ref_post_destroy.argtypes = [C.c_void_p]
+        self.lib.ref_post_set.restype = None
+        self.lib.ref_post_set.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+        self.lib.ref_post_process.restype = C.c_int64
+        self.lib.ref_post_process.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64]
+        self.h = self.lib.ref_post_create(working_rate)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.ref_post_destroy(self.h)
+            self.h = None
+
+    def set(self, tone_on, delay_steps=-1):
+        self.lib.ref_post_set(self.h, int(tone_on), int(delay_steps))
+
+    def process(self, pcm):
+        """pcm complex64 [n] -> (pcm behind the test tone, [(left dB, right dB)] showPeakLevel read-outs)."""
+        x = np.ascontiguousarray(pcm, dtype=np.complex64)
+        out = np.zeros_like(x)
+        peaks = np.zeros((len(x) // 900 + 4, 2), np.float32)
+        n = self.lib.ref_post_process(self.h, x.ctypes.data, len(x), out.ctypes.data, peaks.ctypes.data, len(peaks))
+        return out, peaks[:n].copy()

@@ -583,3 +583,100 @@ bool refresh = true;
 	return nb;
 }
 }
+
+// ---- working-rate post-processing: insertTestTone, evaluatePeakLevel ---------------------------
+// Members of the Qt class fmProcessor (src/fm/fm-processor.cpp:772-823; state in includes/fm/fm-processor.h:
+// 54-75 DelayLine, 233-251), restated statement by statement around DSPCOMPLEX and PI_Constrain from the
+// reference's own fm-constants.h.  Fed with working-rate PCM (the GPU's, behind its fade-in): the 192 -> 48 kHz
+// step in front of it is libsamplerate in the reference (parity unpinned), so this is where the comparison starts.
+namespace {
+struct RefPost {
+	int32_t workingRate;
+	struct TestTone {                              // fm-processor.h:241-249
+	   bool     Enabled = false;
+	   float    TimePeriod = 2.0f;
+	   float    SignalDuration = 0.025f;
+	   uint32_t TimePeriodCounter = 0;
+	   uint32_t NoSamplRemain = 0;
+	   float    CurPhase = 0.0f;
+	   float    PhaseIncr = 0.0f;
+	} testTone;
+	int32_t  peakLevelCurSampleCnt = 0, peakLevelSampleMax;
+	DSPFLOAT absPeakLeft = 0, absPeakRight = 0;    // fm-processor.cpp:125-126
+	uint32_t DataPtrIdx = 0;                       // DelayLine<DSPCOMPLEX> delayLine {(-40, -40)}
+	std::vector<DSPCOMPLEX> DelayBuffer;
+	DSPCOMPLEX mDefault = DSPCOMPLEX (-40.0f, -40.0f);
+	explicit RefPost (int32_t wr) : workingRate (wr), peakLevelSampleMax (wr / 50) { set_delay_steps (0); }   // :142
+	void set_delay_steps (uint32_t iSteps) { DataPtrIdx = 0; DelayBuffer. assign (iSteps + 1, mDefault); }
+	// (the reference's resize (n, default) keeps old entries when growing; a fresh line is what
+	//  setDispDelay yields on a processor whose line was never longer)
+	const DSPCOMPLEX &get_set_value (const DSPCOMPLEX &iVal) {
+	   DelayBuffer [DataPtrIdx] = iVal;
+	   DataPtrIdx = (DataPtrIdx + 1) % DelayBuffer. size ();
+	   return DelayBuffer [DataPtrIdx];
+	}
+	void insertTestTone (DSPCOMPLEX &ioS) {        // :800-823
+	   float toneFreqHz = 1000.0f;
+	   float level = 0.9f;
+	   if (!testTone. Enabled)
+	      return;
+	   ioS *= (1.0f - level);
+	   if (testTone. NoSamplRemain > 0) {
+	      testTone. NoSamplRemain --;
+	      testTone. CurPhase += testTone. PhaseIncr;
+	      testTone. CurPhase = PI_Constrain (testTone. CurPhase);
+	      const float smpl = sin (testTone. CurPhase);
+	      ioS += level * DSPCOMPLEX (smpl, smpl);
+	   }
+	   else
+	   if (++testTone. TimePeriodCounter > workingRate * testTone. TimePeriod) {
+	      testTone. TimePeriodCounter = 0;
+	      testTone. NoSamplRemain = workingRate * testTone. SignalDuration;
+	      testTone. CurPhase = 0.0f;
+	      testTone. PhaseIncr = 2 * M_PI / workingRate * toneFreqHz;
+	   }
+	}
+	bool evaluatePeakLevel (const DSPCOMPLEX s, float *l, float *r) {     // :772-798; true: showPeakLevel emitted
+	   const float absLeft  = std::abs (real (s));
+	   const float absRight = std::abs (imag (s));
+	   if (absLeft  > absPeakLeft)  absPeakLeft  = absLeft;
+	   if (absRight > absPeakRight) absPeakRight = absRight;
+	   peakLevelCurSampleCnt ++;
+	   if (peakLevelCurSampleCnt > peakLevelSampleMax) {
+	      peakLevelCurSampleCnt = 0;
+	      float leftDb  = (absPeakLeft  > 0.0f ? 20.0f * std::log10 (absPeakLeft)  : -40.0f);
+	      float rightDb = (absPeakRight > 0.0f ? 20.0f * std::log10 (absPeakRight) : -40.0f);
+	      DSPCOMPLEX delayed = get_set_value (DSPCOMPLEX (leftDb, rightDb));
+	      *l = real (delayed); *r = imag (delayed);
+	      absPeakLeft = 0.0f; absPeakRight = 0.0f;
+	      return true;
+	   }
+	   return false;
+	}
+};
+}
+
+extern "C" {
+void	*ref_post_create (int32_t working_rate) { return new RefPost (working_rate); }
+void	ref_post_destroy (void *h) { delete (RefPost *)h; }
+// tone_on: setTestTone; delay_steps >= 0: setDispDelay, < 0: leave the line as it is
+void	ref_post_set (void *h, int32_t tone_on, int32_t delay_steps) {
+RefPost *p = (RefPost *)h;
+	p -> testTone. Enabled = tone_on != 0;
+	if (delay_steps >= 0) p -> set_delay_steps ((uint32_t)delay_steps);
+}
+// pcm: n working-rate (left, right) samples behind the fade-in -> pcm_out: what goes to sendSampletoOutput;
+// peaks: the (left dB, right dB) pairs showPeakLevel is emitted with; returns their number
+int64_t	ref_post_process (void *h, const float *pcm, int64_t n, float *pcm_out, float *peaks, int64_t cap_pairs) {
+RefPost *p = (RefPost *)h;
+int64_t ne = 0;
+	for (int64_t i = 0; i < n; i ++) {
+	   DSPCOMPLEX s (pcm [2 * i], pcm [2 * i + 1]);
+	   p -> insertTestTone (s);
+	   float l, r;
+	   if (p -> evaluatePeakLevel (s, &l, &r) && ne < cap_pairs) { peaks [2 * ne] = l; peaks [2 * ne + 1] = r; ne ++; }
+	   pcm_out [2 * i] = real (s); pcm_out [2 * i + 1] = imag (s);
+	}
+	return ne;
+}
+}

@@ -117,7 +117,7 @@ def lib():
         for name in ("fm_mode", "fm_decoder", "sound_mode", "stereo_panorama", "sound_balance",
                      "deemphasis", "lf_cutoff", "bandwidth", "rds_mode", "local_oscillator",
                      "squelch_mode", "squelch_value", "native_rate", "rds_symbol_stage", "scanning", "auto_mono", "pss_mode",
-                     "dc_remove"):
+                     "dc_remove", "test_tone", "disp_delay"):
             getattr(L, f"sdrjfm_set_{name}").argtypes = [vp, i32]
         L.sdrjfm_set_lf_plot_type.restype = i32
         L.sdrjfm_set_lf_plot_type.argtypes = [vp, i32]
@@ -133,6 +133,8 @@ def lib():
         L.sdrjfm_read_scan.argtypes = [vp, i32, vp, i64]
         L.sdrjfm_read_rds_bits.restype = i64
         L.sdrjfm_read_rds_bits.argtypes = [vp, i32, vp, i64]
+        L.sdrjfm_read_peak_levels.restype = i64
+        L.sdrjfm_read_peak_levels.argtypes = [vp, i32, vp, i64]
         L.sdrjfm_set_volume_db.argtypes = [vp, f32]
         L.sdrjfm_set_attenuation.argtypes = [vp, f32, f32]
         L.sdrjfm_trigger_frequency_change.argtypes = [vp]
@@ -261,6 +263,7 @@ class FmProcessorB200:
             raise SdrjfmError(st.value, self.L.sdrjfm_last_error(None).decode())
         self.n_streams = n_streams
         self._display = 0
+        self.audio_ratio = audio_rate / working_rate
         # input samples per fm-rate sample (a lower bound in the resampler mode: sizes the outputs)
         self.decim = (input_rate // fm_rate) if front_end_mode == 1 else front_end_decimation(input_rate, fm_rate)
 
@@ -343,6 +346,17 @@ class FmProcessorB200:
         if n < 0:
             raise SdrjfmError(n, self.L.sdrjfm_last_error(self.h).decode())
         return a[:n].copy()
+    def setTestTone(self, on): self._ck(self.L.sdrjfm_set_test_tone(self.h, int(on)))
+    def setDispDelay(self, steps): self._ck(self.L.sdrjfm_set_disp_delay(self.h, int(steps)))
+
+    def read_peak_levels(self, stream=0):
+        """[(left dB, right dB)] per showPeakLevel read-out of the last process call (one per 961 PCM samples)."""
+        a = np.zeros((1024, 2), np.float32)
+        n = self.L.sdrjfm_read_peak_levels(self.h, stream, a.ctypes.data, a.shape[0])
+        if n < 0:
+            raise SdrjfmError(n, self.L.sdrjfm_last_error(self.h).decode())
+        return a[:n].copy()
+
     def setAutoMonoMode(self, on): self._ck(self.L.sdrjfm_set_auto_mono(self.h, int(on)))
     def setPSSMode(self, on): self._ck(self.L.sdrjfm_set_pss_mode(self.h, int(on)))
     def setDCRemove(self, on): self._ck(self.L.sdrjfm_set_dc_remove(self.h, int(on)))
@@ -373,7 +387,7 @@ class FmProcessorB200:
             iq = iq[None, :]
         assert iq.shape[0] == self.n_streams
         n = iq.shape[1]
-        audio = np.zeros((self.n_streams, n // (4 * self.decim) + 2), np.complex64)
+        audio = np.zeros((self.n_streams, int((n // (4 * self.decim) + 2) * self.audio_ratio) + 2), np.complex64)
         rds = np.zeros((self.n_streams, n // (8 * self.decim) + 2), np.complex64)
         na, nr = C.c_int64(0), C.c_int64(0)
         meta = (Meta * self.n_streams)() if want_meta else None

@@ -18,7 +18,10 @@
 //     y[q] = sum_{i<129} h[i] a[4 q + 3 - i],   h = Blackman-windowed sinc, fc = 20 kHz
 // validated against a float64 model of the same taps.
 #pragma once
+#include <vector>
+#include <cmath>
 #include "common.cuh"
+#include "audio_post.cuh"
 
 namespace sdrjfm {
 
@@ -45,6 +48,7 @@ struct AudioParams {
 	int32_t write_tap;         // keep the 192 kHz stream (SDRJFM_TAP_AUDIO192)
 	int32_t sel;               // which de-emphasis state buffer holds the carried state
 	int32_t plot;              // 0, or ELfPlot AF_MONO / AF_LEFT / AF_RIGHT _FILTERED (5 / 6 / 7): scope stream wanted
+	ToneParams tone;           // insertTestTone (fm-processor.cpp:800-823), behind the fade-in
 };
 
 // lr    : [S][pitch] fm-rate (left, right) of this call
@@ -55,7 +59,8 @@ __global__ void __launch_bounds__ (kAuThreads)
 audio_kernel (const float2 *__restrict__ lr, int64_t pitch, AudioParams P,
               const float2 *__restrict__ hist, float2 *__restrict__ new_hist,
               StreamState *__restrict__ state, float2 *__restrict__ a192,
-              float2 *__restrict__ out, int64_t out_pitch, float *__restrict__ plot) {
+              float2 *__restrict__ out, int64_t out_pitch, float *__restrict__ plot,
+              const float *__restrict__ tone_tab) {
 // phase-major staging: sample with global index g sits at [(g - G0) & 3][(g - G0) >> 2]
 __shared__ float2 sA [4][kAuSpan / 4 + 2];
 __shared__ float  sWl [kAuThreads / 32], sWr [kAuThreads / 32], sWa [kAuThreads / 32];
@@ -162,6 +167,7 @@ float2 *tap = a192 ? a192 + (int64_t)stream * pitch : nullptr;
 	      const float f = fdiv (fsub ((float)P.fade_max, (float)cnt), (float)P.fade_max);
 	      acc.x = fmul (acc.x, f); acc.y = fmul (acc.y, f);
 	   }
+	   if (P.tone.on) acc = tone_apply (P.tone, tone_tab, acc, q - P.q0);   // :644
 	   out [(int64_t)stream * out_pitch + (q - P.q0)] = acc;
 	}
 }

@@ -109,10 +109,10 @@ struct StreamState {
 	int32_t rds_inp, rds_phase_idx, rds_decim_cnt;
 	// audio: samples still to fade in (suppressAudioSampleCnt), peak meter
 	int32_t fade_cnt;
-	float   peak_l, peak_r;
-	int32_t peak_cnt;
-	float   peak_l_db, peak_r_db;
-	int32_t pad [1];
+	// evaluatePeakLevel (fm-processor.cpp:772-798): running |left|, |right| maxima of the open 961-sample block,
+	// double-buffered (the CTA closing a call's last block writes what the next call's first block reads)
+	float   peak_carry [2][2];
+	int32_t pad [2];
 };
 
 // Settings snapshot taken at a process boundary (fm-processor.cpp:397-413 does the same

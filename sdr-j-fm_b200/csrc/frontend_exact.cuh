@@ -199,4 +199,34 @@ float2 v = raw_hist [(int64_t)stream * hist_len + hist_len - kFxHist + i];
 	new_hist [(int64_t)stream * kFxHist + i] = fx_stage (lop, v, (int64_t)i - kFxHist);
 }
 
+// the filter-input history of a composite front end changes meaning when the per-sample DC remover is
+// switched in or out in front of it (raw samples <-> DC-free samples): shift it by the clamped estimate
+__global__ void hist_shift_dc_kernel (float2 *__restrict__ hist, int hist_len, const StreamState *__restrict__ state, float sign) {
+const int stream = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= hist_len) return;
+const float lim = 0.01f;
+const float rr = (float)state [stream].dc_re, ri = (float)state [stream].dc_im;
+float2 &v = hist [(int64_t)stream * hist_len + i];
+	v.x = fadd (v.x, fmul (sign, rr > lim ? lim : (rr < -lim ? -lim : rr)));
+	v.y = fadd (v.y, fmul (sign, ri > lim ? lim : (ri < -lim ? -lim : ri)));
+}
+
+// inputFilter on: the fm-rate stage sees the block sums behind an fm-rate delay line of `len` entries, so
+// StreamState::dc is the estimate of `len` fm samples ago.  RfDC as of NOW (metadata, DcValRf) = that state
+// pushed through the sums still waiting in the line (oldest first).
+__global__ void __launch_bounds__ (256)
+dc_advance_kernel (const float2 *__restrict__ sdel, int len, double alpha, double beta,
+                   const StreamState *__restrict__ state, double2 *__restrict__ out) {
+__shared__ double sA [8], sB [8];
+const int stream = blockIdx.x, tid = threadIdx.x;
+const float2 *s = sdel + (int64_t)stream * len;
+const int per = (len + 255) / 256, i0 = tid * per, i1 = min (i0 + per, len);
+double A = 1.0, Br = 0.0, Bi = 0.0;
+	for (int i = i0; i < i1; i ++) { Br = Br * beta + alpha * (double)s [i].x; Bi = Bi * beta + alpha * (double)s [i].y; A *= beta; }
+double tr, ti;
+	block_affine_start (A, Br, state [stream].dc_re, sA, sB, &tr);
+	block_affine_start (A, Bi, state [stream].dc_im, sA, sB, &ti);
+	if (tid == 0) out [stream] = make_double2 (tr, ti);
+}
+
 }	// namespace sdrjfm

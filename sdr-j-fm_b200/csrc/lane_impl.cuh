@@ -116,6 +116,8 @@ struct Lane {
 	float2 *d_xd = nullptr;                 // [S][cap_in] samples behind the per-sample DC remover
 	float2 *d_xhist [2] = { nullptr, nullptr }; int xhist_sel = 0;
 	bool    fx_hist_valid = false;          // d_xhist continues the stream (false after a composite call)
+	bool    hybrid_last = false;            // the last call ran the per-sample DC remover in front of the wide composite
+	double2 *d_dcnow = nullptr;             // [S] RfDC advanced through the fm-rate delay line (metadata, inputFilter on)
 	int64_t in_total = 0;                   // input samples consumed so far (per stream)
 	// rational polyphase resampler (front_end_mode 1): stage-A output and the stage-B state
 	bool    resample = false;
@@ -185,6 +187,16 @@ struct Lane {
 	bool    sequential_pll = false;         // SDRJFM_SEQUENTIAL_PLL=1: lane-per-stream K3 (cross-check)
 	int64_t fm_total = 0;                   // fm-rate samples produced so far (per stream)
 	int32_t fade_cnt = 0, fade_max = 0;     // suppressAudioSampleCnt(Max), fm-processor.cpp:130-131
+	// test tone (setTestTone / insertTestTone), peak meter (evaluatePeakLevel, setDispDelay), second converter
+	bool     tone_on = false; int32_t tone_arm = 0, tone_burst = 0; int64_t tone_pos = 0;
+	float   *d_tone_tab = nullptr;
+	int32_t  peak_block = 961, peak_sel = 0, peak_delay = 0;
+	int64_t  peak_e_set = 0, peak_e0 = 0, peak_e1 = 0;   // emission index at the last setDispDelay; emissions of the last call
+	float2  *d_peak_ring = nullptr;
+	int32_t  cvL = 1, cvM = 1;              // audio_rate / working_rate = cvL / cvM
+	int64_t  cap_out = 0;                   // per-stream capacity of the audio output at audio_rate
+	int64_t  cv_in_total = 0;               // working-rate samples fed to the converter so far
+	float   *d_cv_taps = nullptr; float2 *d_cv_hist [2] = { nullptr, nullptr }; int cv_sel = 0;
 	int64_t last_nfm = 0, last_naudio = 0, last_nrds = 0;
 	int64_t launches = 0;
 	ConstImage ci;
@@ -547,6 +559,20 @@ const int64_t S = cfg -> n_streams;
 	}
 	h -> cap_audio = ((h -> cap_fm / kRsDecim + 1 + 15) / 16) * 16;
 	h -> cap_rds   = ((h -> cap_fm / 8 + 1 + 15) / 16) * 16;
+	h -> cap_out   = h -> cap_audio;
+std::vector<float> cv_taps;
+	if (h -> cfg.working_rate * kRsDecim != cfg -> fm_rate) {
+	   g_create_error = "working_rate must be fm_rate / 4 (48000)"; *status = SDRJFM_ERR_UNSUPPORTED; delete h; return nullptr;
+	}
+	if (h -> cfg.audio_rate != h -> cfg.working_rate) {
+//	   theConverter (workingRate, audioRate, workingRate / 20), fm-processor.cpp:89-91, 831-836
+	   if (!convert_design (h -> cfg.working_rate, h -> cfg.audio_rate, h -> cvL, h -> cvM, cv_taps)) {
+	      g_create_error = "unsupported audio_rate (audio_rate / working_rate must reduce to L / M with L <= 640)";
+	      *status = SDRJFM_ERR_UNSUPPORTED; delete h; return nullptr;
+	   }
+	   h -> cap_out = ((h -> cap_audio * h -> cvL / h -> cvM + 2 + 15) / 16) * 16;
+	}
+	h -> peak_block = h -> cfg.working_rate / 50 + 1;          // peakLevelSampleMax = workingRate / 50, test `> max` (:142, :782)
 auto fail = [&](cudaError_t e, const char *what) -> Lane * {
 	   g_create_error = std::string (what) + ": " + cudaGetErrorString (e);
 	   *status = SDRJFM_ERR_CUDA; lane_destroy (h); return nullptr;
@@ -574,6 +600,19 @@ cudaError_t e;
 	AL (d_rdsc, S * h -> cap_fm); AL (d_rds24, S * h -> cap_rds);
 	AL (d_ahist [0], S * kRsHist); AL (d_ahist [1], S * kRsHist);
 	AL (d_audio, S * h -> cap_audio);
+	AL (d_peak_ring, S * kPeakRing);
+	if (!cv_taps.empty ()) {
+	   AL (d_cv_taps, cv_taps.size ());
+	   AL (d_cv_hist [0], S * kCvTapsPerPhase); AL (d_cv_hist [1], S * kCvTapsPerPhase);
+	   if ((e = cudaMemcpy (h -> d_cv_taps, cv_taps.data (), cv_taps.size () * sizeof (float), cudaMemcpyHostToDevice)) != cudaSuccess)
+	      return fail (e, "converter taps upload");
+	}
+	{  std::vector<float> tt;
+	   tone_design (h -> cfg.working_rate, h -> tone_arm, tt);
+	   h -> tone_burst = (int32_t)tt.size ();
+	   AL (d_tone_tab, tt.size () + 1);
+	   if ((e = cudaMemcpy (h -> d_tone_tab, tt.data (), tt.size () * sizeof (float), cudaMemcpyHostToDevice)) != cudaSuccess)
+	      return fail (e, "tone table upload"); }
 	AL (d_state, S);
 	AL (d_iter_stats, S * 4);
 	h -> ntiles_cap = (int32_t)((h -> cap_fm + kDiBlock - 1) / kDiBlock);
@@ -641,7 +680,8 @@ void *ptrs [] = { h -> d_tables, h -> d_sin_quarter, h -> d_in, h -> d_hist [0],
 	              h -> d_rsy_c, h -> d_rsy_v, h -> d_rsy_w, h -> d_rsy_in,
 	              h -> d_scan_carry [0], h -> d_scan_carry [1], h -> d_scan_db, h -> d_plot,
 	              h -> d_spec_in, h -> d_spec_carry [0], h -> d_spec_carry [1], h -> d_spec_win,
-	              h -> d_spec_Y, h -> d_spec_avg, h -> d_spec_disp, h -> d_xd, h -> d_xhist [0], h -> d_xhist [1] };
+	              h -> d_spec_Y, h -> d_spec_avg, h -> d_spec_disp, h -> d_xd, h -> d_xhist [0], h -> d_xhist [1], h -> d_dcnow,
+	              h -> d_tone_tab, h -> d_peak_ring, h -> d_cv_taps, h -> d_cv_hist [0], h -> d_cv_hist [1] };
 	for (void *p : ptrs) if (p) cudaFree (p);
 	if (h -> stream_rds) { cudaStreamSynchronize (h -> stream_rds); cudaStreamDestroy (h -> stream_rds); }
 	if (h -> ev_k3) cudaEventDestroy (h -> ev_k3);
@@ -804,6 +844,14 @@ static bool exact_wanted (const Lane *h) {
 	return h -> auto_exact && (h -> set.decoder == 2 || h -> set.decoder == 5 || h -> set.lo_hz != 0);
 }
 
+// inputFilter on (the composite has to stand in for the reference's FFT filter) but the decoder or the oscillator
+// asks for the reference's own DC arithmetic: the per-sample DC remover of K1x runs in front of the wide composite
+static bool hybrid_wanted (const Lane *h) {
+	if (h -> resample || h -> set.input_filter_hz <= 0 || h -> shape > 2 || !h -> set.dc_remove) return false;
+	if (h -> cfg.front_end_mode == 2) return true;
+	return h -> auto_exact && (h -> set.decoder == 2 || h -> set.decoder == 5 || h -> set.lo_hz != 0);
+}
+
 // K1x: per-sample DC removal, then the two decimators in the reference's operation order -> d_U = fm-rate samples
 static int launch_frontend_exact (Lane *h, const void *src, RawFmt rf, int64_t pitch, int32_t M, int64_t n_proc, bool dry) {
 const int S = h -> cfg.n_streams;
@@ -955,6 +1003,25 @@ int rc;
 //	K1 ------------------------------------------------------------------------------------
 const bool wide = st.input_filter_hz > 0;
 const bool exact = exact_wanted (h);
+const bool hybrid = !exact && hybrid_wanted (h);
+	if (wide && hybrid != h -> hybrid_last && h -> in_total > 0) {
+//	   the wide history holds raw samples after a plain call, DC-free ones after a hybrid call
+	   hist_shift_dc_kernel<<<dim3 ((h -> hist_len_w + 127) / 128, S), 128, 0, h -> stream>>> (
+	         h -> d_histw [h -> histw_sel], h -> hist_len_w, h -> d_state, hybrid ? -1.0f : 1.0f);
+	   h -> launches ++;
+	}
+	h -> hybrid_last = wide && hybrid;
+	if (hybrid) {
+	   if (!h -> d_xd) {
+	      CK (dalloc (&h -> d_xd, (size_t)S * h -> cap_in));
+	      CK (dalloc (&h -> d_xhist [0], (size_t)S * kFxHist)); CK (dalloc (&h -> d_xhist [1], (size_t)S * kFxHist));
+	   }
+	   fx_dc_kernel<<<(S + 31) / 32, 32, 0, h -> stream>>> (src, pitch, rf, n_proc, S, 1.0f / (float)h -> cfg.input_rate,
+	                                                      h -> d_state, h -> d_xd, h -> cap_in, 1);
+	   h -> launches ++;
+	   src = h -> d_xd; pitch = h -> cap_in;
+	   memset (&rf, 0, sizeof rf); rf.fmt = kFmtCF32; rf.scale = 1.f;
+	}
 	if (exact) rc = launch_frontend_exact (h, src, rf, pitch, M1, n_proc, false);
 	else { rc = launch_frontend (h, src, rf, pitch, M1); h -> fx_hist_valid = false; }
 	if (rc != SDRJFM_OK) return rc;
@@ -1027,6 +1094,7 @@ DiscrParams dp;
 	dp.dc_remove = st.dc_remove; dp.decoder = st.decoder;
 	dp.scan_only = h -> scanning;
 	dp.exact = exact;
+	if (hybrid) dp.dc_remove = 0;      // the DC went out sample by sample in front of the composite
 	if (exact) {      // K1x delivered the reference's fm-rate samples: K2 only normalises and discriminates
 	   dp.dc_remove = 0; dp.sumC = dp.sumCm = 0.f; dp.gb0 = dp.gb1 = dp.gb2 = 0.f;
 	   dp.lgain = dp.rgain = 1.f; dp.Gre = 1.f; dp.Gim = 0.f;
@@ -1209,8 +1277,10 @@ const float2 *lr_in = h -> d_lr;
 const int64_t q0 = h -> fm_total / kRsDecim;
 const int64_t q1 = (h -> fm_total + M) / kRsDecim;
 const int32_t nq = (int32_t)(q1 - q0);
-float2 *aout = d_audio_out ? d_audio_out : h -> d_audio;
-const int64_t apitch = d_audio_out ? audio_pitch : h -> cap_audio;
+const bool convert = h -> cfg.audio_rate != h -> cfg.working_rate;
+//	working-rate PCM: straight into the caller's buffer unless the second converter follows
+float2 *aout = (d_audio_out && !convert) ? d_audio_out : h -> d_audio;
+const int64_t apitch = (d_audio_out && !convert) ? audio_pitch : h -> cap_audio;
 	{
 	   AudioParams ap;
 	   ap.alpha = st.deemph_alpha;
@@ -1220,17 +1290,49 @@ const int64_t apitch = d_audio_out ? audio_pitch : h -> cap_audio;
 	   ap.write_tap = h -> cfg.keep_taps;
 	   ap.sel = h -> ahist_sel;
 	   ap.plot = (h -> lf_plot >= 5 && h -> lf_plot <= 7) ? h -> lf_plot : 0;
+	   ap.tone.on = h -> tone_on; ap.tone.arm = h -> tone_arm; ap.tone.burst = h -> tone_burst; ap.tone.pos = h -> tone_pos;
 	   dim3 g ((unsigned)((M + kAuTile - 1) / kAuTile), (unsigned)S);
 	   audio_kernel<<<g, kAuThreads, 0, h -> stream>>> (
 	         lr_in, h -> cap_fm, ap, h -> d_ahist [h -> ahist_sel], h -> d_ahist [h -> ahist_sel ^ 1],
-	         h -> d_state, h -> d_a192, aout, apitch, h -> d_plot);
+	         h -> d_state, h -> d_a192, aout, apitch, h -> d_plot, h -> d_tone_tab);
 	   h -> launches ++;
 	   h -> ahist_sel ^= 1;
 	   h -> fade_cnt = h -> fade_cnt > nq ? h -> fade_cnt - nq : 0;
+	   if (h -> tone_on) h -> tone_pos = (h -> tone_pos + nq) % (h -> tone_arm + h -> tone_burst);
+	}
+//	evaluatePeakLevel (:772-798): one read-out per 961 PCM samples, counted from the start of the processor
+	h -> peak_e0 = q0 / h -> peak_block; h -> peak_e1 = q1 / h -> peak_block;
+	if (nq > 0) {
+	   const unsigned nb = (unsigned)((q1 - 1) / h -> peak_block - q0 / h -> peak_block + 1);
+	   peak_kernel<<<dim3 (nb, (unsigned)S), 32, 0, h -> stream>>> (aout, apitch, q0, nq, h -> peak_block, h -> d_state,
+	                                                             h -> peak_sel, h -> d_peak_ring);
+	   h -> peak_sel ^= 1; h -> launches ++;
+	}
+int64_t n_out = nq;
+	if (convert) {
+//	   sendSampletoOutput (:825-838): the second converter, working rate -> audio rate
+	   ConvertParams cp;
+	   cp.L = h -> cvL; cp.M = h -> cvM; cp.P = kCvTapsPerPhase;
+	   cp.t0 = h -> cv_in_total; cp.nt = nq;
+	   const int64_t t1 = cp.t0 + nq;
+	   cp.k0 = (cp.t0 * cp.L + cp.M - 1) / cp.M;                        // outputs that existed before this call: ceil (T L / M)
+	   cp.nk = (int32_t)((t1 * cp.L + cp.M - 1) / cp.M - cp.k0);
+	   float2 *cout = d_audio_out ? d_audio_out : h -> d_audio + 0;     // (no caller buffer: results stay internal)
+	   const int64_t cpitch = d_audio_out ? audio_pitch : h -> cap_out;
+	   if (d_audio_out && cp.nk > 0) {
+	      audio_convert_kernel<<<dim3 ((unsigned)((cp.nk + 255) / 256), (unsigned)S), 256, 0, h -> stream>>> (
+	            aout, apitch, h -> d_cv_hist [h -> cv_sel], h -> d_cv_taps, cp, cout, cpitch);
+	      h -> launches ++;
+	   }
+	   convert_roll_kernel<<<S, kCvTapsPerPhase, 0, h -> stream>>> (aout, apitch, nq, kCvTapsPerPhase, h -> d_cv_hist [h -> cv_sel],
+	                                                                h -> d_cv_hist [h -> cv_sel ^ 1]);
+	   h -> cv_sel ^= 1; h -> launches ++;
+	   h -> cv_in_total = t1;
+	   n_out = cp.nk;
 	}
 	h -> fm_total += M;
-	h -> last_naudio = nq;
-	if (n_audio) *n_audio = nq;
+	h -> last_naudio = n_out;
+	if (n_audio) *n_audio = n_out;
 	if (st.rds_mode != 0) CK (cudaStreamWaitEvent (h -> stream, h -> ev_rds, 0));     // join
 	if (h -> spec_N && h -> lf_plot >= 0) {
 	   const int rc = run_lf_spectrum (h, M);
@@ -1334,11 +1436,28 @@ static int lane_get_meta (Lane *h, sdrjfm_meta *meta) {
 const int S = h -> cfg.n_streams;
 std::vector<StreamState> st (S);
 	CK (cudaMemcpyAsync (st.data (), h -> d_state, S * sizeof (StreamState), cudaMemcpyDeviceToHost, h -> stream));
+//	inputFilter on: the fm-rate DC estimate runs behind the 5440-sample delay line; RfDC as of the last input sample
+const bool adv = h -> set.input_filter_hz > 0 && h -> set.dc_remove && !h -> hybrid_last && h -> d_sdel [0] && h -> in_total > 0;
+std::vector<double2> dcnow (adv ? S : 0);
+	if (adv) {
+	   CK (cudaSetDevice (h -> cfg.device));
+	   if (!h -> d_dcnow) CK (dalloc (&h -> d_dcnow, (size_t)S));
+	   const double alpha = (double)(1.0f / h -> cfg.input_rate);
+	   dc_advance_kernel<<<S, 256, 0, h -> stream>>> (h -> d_sdel [h -> del_sel], h -> fw_delay, alpha,
+	                                                 pow (1.0 - alpha, (double)h -> decim), h -> d_state, h -> d_dcnow);
+	   CK (cudaMemcpyAsync (dcnow.data (), h -> d_dcnow, S * sizeof (double2), cudaMemcpyDeviceToHost, h -> stream));
+	}
+//	showPeakLevel: the newest read-out of the peak meter behind the display delay line (-40 dB before the first)
+std::vector<float2> peaks (S, make_float2 (-40.0f, -40.0f));
+	{  const int64_t E = (h -> fm_total / kRsDecim) / h -> peak_block - 1 - h -> peak_delay;
+	   if (E >= h -> peak_e_set && E >= 0)
+	      CK (cudaMemcpy2DAsync (peaks.data (), sizeof (float2), h -> d_peak_ring + (E & (kPeakRing - 1)), kPeakRing * sizeof (float2),
+	                             sizeof (float2), S, cudaMemcpyDeviceToHost, h -> stream)); }
 	CK (cudaStreamSynchronize (h -> stream));
 	for (int s = 0; s < S; s ++) {
 	   sdrjfm_meta &m = meta [s];
 	   const StreamState &x = st [s];
-	   m.dc_rf_re = (float)x.dc_re; m.dc_rf_im = (float)x.dc_im;
+	   m.dc_rf_re = (float)(adv ? dcnow [s].x : x.dc_re); m.dc_rf_im = (float)(adv ? dcnow [s].y : x.dc_im);
 	   m.dc_rf_db = h -> set.dc_remove ?
 	         20 * log10f (hypotf (m.dc_rf_re, m.dc_rf_im) + 1.0f / 32768) : -99.99f;
 	   m.dc_if = x.fm_afc;
@@ -1349,7 +1468,7 @@ std::vector<StreamState> st (S);
 	   m.pilot_locked = locked;
 	   m.pilot_lock_strength = h -> set.fm_mode != 2 ? x.pilot_lock : 0.f;
 	   m.pss_state = (h -> set.pss_on && locked) ? (x.pss_minimized ? 2 : 1) : 0;
-	   m.peak_left_db = x.peak_l_db; m.peak_right_db = x.peak_r_db;
+	   m.peak_left_db = peaks [s].x; m.peak_right_db = peaks [s].y;
 	   m.squelch_active = 0;
 	}
 	if (h -> d_sq) {                                                   // getSquelchState (:217-219)
@@ -1707,6 +1826,38 @@ std::vector<int16_t> mi (kAirspyOut); std::vector<float> mf (kAirspyOut);
 	CK (cudaMemcpy (h -> d_air_frac, mf.data (), kAirspyOut * sizeof (float), cudaMemcpyHostToDevice));
 	h -> air_blk = B; h -> air_pend = 0;
 	return SDRJFM_OK;
+}
+// setTestTone (fm-processor.cpp:931-933): the burst state machine keeps its position while switched off
+static int lane_set_test_tone (Lane *h, int32_t on) {
+	if (!h) return SDRJFM_ERR_ARG;
+	h -> tone_on = on != 0; return SDRJFM_OK;
+}
+// setDispDelay (:935-937): delayLine.set_delay_steps (n) restarts the line filled with (-40, -40)
+static int lane_set_disp_delay (Lane *h, int32_t steps) {
+	if (!h || steps < 0 || steps > kPeakRing / 2) return SDRJFM_ERR_ARG;
+	h -> peak_delay = steps;
+	h -> peak_e_set = (h -> fm_total / kRsDecim) / h -> peak_block;
+	return SDRJFM_OK;
+}
+// the (left dB, right dB) pairs showPeakLevel was emitted with during the LAST process call, oldest first
+static int64_t lane_read_peak_levels (Lane *h, int32_t stream, float *out, int64_t cap_pairs) {
+	if (!h || !out || stream < 0 || stream >= h -> cfg.n_streams) return SDRJFM_ERR_ARG;
+int64_t e0 = h -> peak_e0, e1 = h -> peak_e1;
+	if (e1 - e0 > kPeakRing - h -> peak_delay) e0 = e1 - (kPeakRing - h -> peak_delay);     // older raw read-outs left the ring
+int64_t n = e1 - e0;
+	if (n > cap_pairs) { e0 = e1 - cap_pairs; n = cap_pairs; }
+	if (n <= 0) return 0;
+	CK (cudaSetDevice (h -> cfg.device));
+std::vector<float2> ring (kPeakRing);
+	CK (cudaMemcpyAsync (ring.data (), h -> d_peak_ring + (size_t)stream * kPeakRing, kPeakRing * sizeof (float2),
+	                     cudaMemcpyDeviceToHost, h -> stream));
+	CK (cudaStreamSynchronize (h -> stream));
+	for (int64_t E = e0; E < e1; E ++) {
+	   const int64_t idx = E - h -> peak_delay;
+	   const float2 v = (idx >= h -> peak_e_set && idx >= 0) ? ring [idx & (kPeakRing - 1)] : make_float2 (-40.0f, -40.0f);
+	   out [2 * (E - e0)] = v.x; out [2 * (E - e0) + 1] = v.y;
+	}
+	return n;
 }
 static int lane_set_auto_mono (Lane *h, int32_t on) {
 	if (!h) return SDRJFM_ERR_ARG;

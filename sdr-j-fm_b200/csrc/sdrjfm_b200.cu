@@ -141,7 +141,7 @@ sdrjfm_handle *h = new sdrjfm_handle ();
 	if (!getenv ("SDRJFM_TMA_CTAS"))
 	   for (Lane *l : h -> lanes) l -> tma_ctas = std::max (1, (l -> n_sm + nl - 1) / nl);
 	h -> cfg = h -> lanes [0] -> cfg; h -> cfg.n_streams = cfg -> n_streams;
-	h -> cap_in = h -> lanes [0] -> cap_in; h -> cap_audio = h -> lanes [0] -> cap_audio;
+	h -> cap_in = h -> lanes [0] -> cap_in; h -> cap_audio = h -> lanes [0] -> cap_out;     // at audio_rate
 	h -> cap_rds = h -> lanes [0] -> cap_rds;
 auto fail = [&](cudaError_t e, const char *what) -> sdrjfm_handle * {
 	   g_create_error = std::string (what) + ": " + cudaGetErrorString (e);
@@ -298,7 +298,7 @@ const Lane *l0 = h -> lanes [0];
 //	   output capacities are checked before the first slice moves any state: a call of n_in samples
 //	   yields at most n_in / decim / 4 + 1 audio and n_in / decim / 8 + 1 RDS samples per stream
 	   const int64_t max_fm = (n_in + l0 -> pend) / l0 -> decim + 1;
-	   if ((audio && audio_pitch < max_fm / kRsDecim + 1) || (rds24 && l0 -> set.rds_mode != 0 && rds_pitch < max_fm / 8 + 1)) {
+	   if ((audio && audio_pitch < (max_fm / kRsDecim + 1) * l0 -> cvL / l0 -> cvM + 1) || (rds24 && l0 -> set.rds_mode != 0 && rds_pitch < max_fm / 8 + 1)) {
 	      h -> err = "audio_pitch / rds_pitch too small for this call"; return SDRJFM_ERR_ARG;
 	   }
 	   if (!h -> copy_stream) {
@@ -311,6 +311,7 @@ const Lane *l0 = h -> lanes [0];
 	      HK (cudaMalloc ((void **)&h -> d_in [1], (size_t)S * h -> cap_in * sizeof (float2)));
 	   }
 	   int64_t pos = 0; int c = 0;
+	   std::vector<int64_t> peak_e0;               // the peak read-outs of the whole call, not of its last slice
 	   while (pos < n_in) {
 	      const int64_t rest = n_in - pos;
 	      const int64_t len = rest < 2 * slice ? rest : slice;     // the last slice takes the ragged tail
@@ -328,6 +329,7 @@ const Lane *l0 = h -> lanes [0];
 	         if (c > 0) { cudaDeviceSynchronize (); h -> poisoned = true; }     // earlier slices already advanced the streams
 	         return rc;
 	      }
+	      if (c == 0) for (Lane *l : h -> lanes) peak_e0.push_back (l -> peak_e0);
 	      HK (cudaEventRecord (h -> ev_done [b], h -> stream));
 //	      this slice's outputs go back on a third stream (PCIe is full duplex) while the next slices run
 	      if ((audio && a1 > 0) || (rds24 && r1 > 0)) {
@@ -345,6 +347,7 @@ const Lane *l0 = h -> lanes [0];
 	   }
 	   HK (cudaStreamSynchronize (h -> out_stream));
 	   HK (cudaStreamSynchronize (h -> stream));
+	   for (size_t i = 0; i < peak_e0.size (); i ++) h -> lanes [i] -> peak_e0 = peak_e0 [i];
 	   if (n_audio) *n_audio = na;
 	   if (n_rds) *n_rds = nr;
 	   if (meta) return sdrjfm_get_meta (h, meta);
@@ -496,6 +499,18 @@ const int i = lane_of (h, stream);
 	if (i < 0) return SDRJFM_ERR_ARG;
 	HK (cudaStreamSynchronize (h -> stream));
 const int64_t n = lane_read_rds_bits (h -> lanes [i], stream - h -> first [i], out, cap);
+	if (n < 0) h -> err = h -> lanes [i] -> err;
+	return n;
+}
+FWD1 (set_test_tone, int32_t)
+FWD1 (set_disp_delay, int32_t)
+int64_t sdrjfm_read_peak_levels (sdrjfm_handle *h, int32_t stream, float *out, int64_t cap_pairs) {
+	if (!h || !out) return SDRJFM_ERR_ARG;
+	LOCK_DEV (h);
+const int i = lane_of (h, stream);
+	if (i < 0) return SDRJFM_ERR_ARG;
+	HK (cudaStreamSynchronize (h -> stream));
+const int64_t n = lane_read_peak_levels (h -> lanes [i], stream - h -> first [i], out, cap_pairs);
 	if (n < 0) h -> err = h -> lanes [i] -> err;
 	return n;
 }
