@@ -338,7 +338,7 @@ def _compare_meta(m, rm, cfg):
     assert m["squelch_active"] == rm["squelch_active"]
 
 
-@pytest.mark.parametrize("name", ["config1_mono", "config2_stereo_pss", "config3_input_filter"])
+@pytest.mark.parametrize("name", ["config1_mono", "config2_stereo_pss", "config2_stereo_pss_exact", "config3_input_filter"])
 def test_baseline_configs_at_their_stated_length(pkg, signals, checker, name):
     """BASELINE.json configs 1-3 as written: 10 s of 2.304 MS/s IQ (23 040 000 samples), in 1 s calls, against
     the reference's classes fed with the same calls.  Per call: audio192 and demod within 1e-5 RMS, the lock
@@ -346,8 +346,12 @@ def test_baseline_configs_at_their_stated_length(pkg, signals, checker, name):
     fm-processor.cpp:662-681): pilot lock and strength, PssState including the ANALYZING -> ESTABLISHED
     transition (stereo-separation.cpp:86-100: |mean_error| < 1e-3 for 3 s, which switches the x10 error
     gain off), PssPhaseShift, PssPhaseChange, DcValRf, DcValIf.  Config 2 also carries the L/R separation
-    figure of every second: it must be the reference's own."""
+    figure of every second: it must be the reference's own; it is run on both front ends (the reference-order
+    one, front_end_mode 2, keeps every tap two orders closer)."""
     secs = 10
+    exact = name.endswith("_exact")
+    if exact:
+        name = name[:-6]
     if name == "config1_mono":
         x = signals.dc_offset(signals.mono_tone(N1 * secs))
         cfg = dict(fm_mode=2, volume_db=0.0)
@@ -358,7 +362,7 @@ def test_baseline_configs_at_their_stated_length(pkg, signals, checker, name):
         x = signals.adjacent_interferer(N1 * secs)
         cfg = dict(fm_mode=0, input_filter_hz=165000, volume_db=0.0)
     ref = checker(**cfg)
-    p = pkg.FmProcessorB200(n_streams=1, max_samples_per_call=N1)
+    p = pkg.FmProcessorB200(n_streams=1, max_samples_per_call=N1, front_end_mode=2 if exact else 0)
     p.configure(**cfg)
     states = []
     for k in range(secs):
@@ -368,15 +372,20 @@ def test_baseline_configs_at_their_stated_length(pkg, signals, checker, name):
         a, d = p.read_tap("audio192"), p.read_tap("demod")
         assert audio.shape[1] == N1 // 48 and len(d) == r["n_fm"] == N1 // 12
         e_a, e_d = rms(a - r["audio192"]), rms(d - r["demod"])
-        e_p = float(np.max(np.abs(p.read_tap("pss_delay") - r["pss_delay"])))
+        dp = p.read_tap("pss_delay") - r["pss_delay"]
+        e_p, e_pmax = rms(dp), float(np.max(np.abs(dp)))
         rm = ref.meta()
-        line = f"{name} second {k + 1}: audio192 {e_a:.2e} demod {e_d:.2e} pss_delay max {e_p:.2e} pss_state {meta[0]['pss_state']}"
+        line = (f"{name}{' (front_end_mode 2)' if exact else ''} second {k + 1}: audio192 {e_a:.2e} demod {e_d:.2e} "
+                f"pss_delay rms {e_p:.2e} max {e_pmax:.2e} pss_state {meta[0]['pss_state']}")
         if name == "config2_stereo_pss":
             sg, sr = _tone_separation_db(a), _tone_separation_db(r["audio192"])
             line += f" separation gpu {sg:.3f} dB reference {sr:.3f} dB"
             assert abs(sg - sr) < 0.02
         print(line)
-        assert e_a < 1e-5 and e_d < 1e-5 and e_p < 2e-5
+        if exact:
+            assert e_a < 1e-6 and e_d < 1e-7 and e_pmax < 2e-6
+        else:
+            assert e_a < 1e-5 and e_d < 1e-5 and e_p < 2e-5
         assert np.array_equal(p.read_tap("locked"), r["locked"])
         _compare_meta(meta[0], rm, cfg)
         states.append(meta[0]["pss_state"])
