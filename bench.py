@@ -14,7 +14,12 @@ collective; the only collective is the one-time broadcast of the tap/LUT blob).
   roofline  the decimating front-end kernel timed alone: 8.667 algorithmic bytes per input
             sample (8 B float2 read + 8/12 B fm-rate float2 write)
   cpu_baseline  the reference's own DSP classes (oracle/_ref) — or the port when _ref is
-            absent — on the host cores, bounded sample (rank 0, N=1 only)
+            absent — on the host cores, bounded sample (rank 0, N=1 only): all cores, one stream
+            per thread, plus the single-core figure
+  strong_scaling  BASELINE config 5 as written: `--streams` streams IN TOTAL sharded over the N
+            ranks (sharding.stream_range), same bytes per step as the N=1 line
+  streams_sweep   (N=1) the chain at 32 .. 1024 streams per GPU at constant bytes per step
+  per_rank_ms     ms per step of every rank (value uses the max)
 """
 import argparse
 import importlib
@@ -57,6 +62,60 @@ def peak_hbm():
         except Exception:
             pass
     return FALLBACK_HBM_GBS, "fallback"
+
+
+def kernel_sass_hash(kernel="frontend_tma_kernelILi12ELi4ELi37"):
+    """sha256 of the SASS of one kernel of the loaded library (addresses and encodings stripped): the committed
+    ncu traffic figure is only reported while the kernel it was captured from is the kernel that runs."""
+    import hashlib
+    import re
+    so = os.path.join(ROOT, "sdr-j-fm_b200", "libsdrjfm_b200.so")
+    try:
+        out = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, timeout=120).stdout
+    except Exception:
+        return None
+    keep, on = [], False
+    for ln in out.splitlines():
+        if "Function :" in ln:
+            on = kernel in ln
+            continue
+        if on:
+            m = re.match(r"\s*/\*[0-9a-f]+\*/\s+(.*?);", ln)
+            if m:
+                keep.append(m.group(1).strip())
+    if not keep:
+        return None
+    return hashlib.sha256("\n".join(keep).encode()).hexdigest()[:16]
+
+
+def audio48_parity():
+    """the reference's 192 -> 48 kHz step is libsamplerate (newconverter.cpp:37,55-80): pinned only where the
+    library exists (tests/test_gpu_parity.py::test_audio48_against_libsamplerate_if_present)"""
+    import ctypes.util
+    name = ctypes.util.find_library("samplerate")
+    return f"libsamplerate present ({name}): see the GPU test log" if name else "unpinned (libsamplerate absent)"
+
+
+def host_topology(index):
+    """NUMA placement of this rank: the CPUs NVML names for the GPU, the node they sit on, nodes of the box"""
+    info = {}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = sorted(64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1)
+        info["gpu_cpu_affinity"] = f"{cpus[0]}-{cpus[-1]}" if cpus else None
+    except Exception:
+        pass
+    try:
+        nodes = sorted(d for d in os.listdir("/sys/devices/system/node") if d.startswith("node"))
+        info["numa_nodes"] = len(nodes)
+        info["numa_cpulists"] = {d: open(f"/sys/devices/system/node/{d}/cpulist").read().strip() for d in nodes}
+    except Exception:
+        pass
+    info["process_cpus"] = len(os.sched_getaffinity(0))
+    return info
 
 
 class ClockSampler:
@@ -133,7 +192,7 @@ def gen_batch_gpu(torch, dev, n_streams, n, stream0=0, group=16):
 
 def cpu_reference_rate(settings, seconds_per_thread, threads=None):
     """times the reference DSP classes (oracle/_ref; the port if absent) on host cores:
-    one stream per thread, each `seconds_per_thread` of config-2/5 signal. Returns dict."""
+    one stream per thread, each `seconds_per_thread` (>= 10 s) of config-2/5 signal. Returns dict."""
     from oracle import chainlib
     chainlib.build(("oracle", "ref"))
     kind, prefix = ("reference", "ref") if chainlib.available("ref") else ("port", "orc")
@@ -157,9 +216,19 @@ def cpu_reference_rate(settings, seconds_per_thread, threads=None):
     dt = time.perf_counter() - t0
     total = cores * reps * len(block)
     return {"value": total / dt / 1e6, "unit": "MS/s", "cores": cores, "kind": kind,
-            "sample": f"{cores} streams x {reps} s of 2.304 MS/s stereo+pilot IQ, one stream per "
-                      f"thread, chain up to 192 kHz de-emphasised audio (libsamplerate absent)",
+            "sample": f"{cores} streams x {reps} s of 2.304 MS/s stereo+pilot+RDS IQ, one stream per "
+                      f"thread, the reference's classes up to the 192 kHz de-emphasised audio and the 24 kHz RDS "
+                      f"baseband; EXCLUDES the 192->48 kHz libsamplerate step (library absent), which the GPU arm includes",
             "seconds": dt}
+
+
+def cpu_reference_both(settings, seconds_per_thread):
+    """all host cores (the headline CPU figure) and ONE core"""
+    allc = cpu_reference_rate(settings, seconds_per_thread)
+    one = cpu_reference_rate(settings, seconds_per_thread, threads=1)
+    allc["single_core"] = {"value": one["value"], "unit": "MS/s", "cores": 1,
+                           "x_realtime_2p304MSps": one["value"] / 2.304}
+    return allc
 
 
 def bind_to_gpu_numa_node(index):
@@ -244,7 +313,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=256, help="IQ streams per GPU")
     ap.add_argument("--seconds", type=float, default=0.5, help="signal seconds per stream per step")
-    ap.add_argument("--cpu-seconds", type=float, default=8.0, help="cpu baseline: signal seconds per thread")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="cpu baseline: signal seconds per thread")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the streams-per-GPU sweep (N=1) / strong-scaling leg (N>1)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--rds-symbols", action="store_true",
@@ -271,18 +341,24 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
+        # one untimed warm-up pass (page-in, table design), then K timed steps of the bounded sample
+        # (each step = cores x cpu_seconds of signal, all host threads), then the single-core figure
+        cpu_reference_rate(settings, 1.0)
         r = cpu_reference_rate(settings, args.cpu_seconds)
-        # K timed steps of the bounded sample (each step = cores x cpu_seconds of signal)
         vals = [r["value"]]
         for _ in range(max(0, min(args.steps, 3) - 1)):
             vals.append(cpu_reference_rate(settings, args.cpu_seconds)["value"])
         v = float(np.mean(vals))
+        one = cpu_reference_rate(settings, args.cpu_seconds, threads=1)
         line = {"impl": "reference", "metric": "IQ MS/s through full FM demod chain", "value": v,
-                "unit": "MS/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": 0,
+                "unit": "MS/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": 1,
                 "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": v, "unit": "MS/s", "cores": r["cores"], "kind": r["kind"],
-                                 "sample": r["sample"]},
+                                 "sample": r["sample"],
+                                 "single_core": {"value": one["value"], "unit": "MS/s", "cores": 1,
+                                                 "x_realtime_2p304MSps": one["value"] / 2.304}},
+                "audio48_parity": audio48_parity(),
                 "e2e": {"value": v, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         emit(line)
@@ -335,10 +411,13 @@ def main():
             e1.record(st)
         barrier()
         ms = e0.elapsed_time(e1)
+        timed.per_rank = [ms]
         if world > 1:
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            allt = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            timed.per_rank = [float(v.item()) for v in allt]
+            ms = max(timed.per_rank)
         return ms
 
     for _ in range(args.warmup):
@@ -350,6 +429,7 @@ def main():
     clk = ClockSampler(local)
     clk.__enter__()
     ms = timed(step_device, args.steps)
+    per_rank_ms = [v / args.steps for v in timed.per_rank]
     launches = proc.launch_count - l0
     value = world * S * n * args.steps / (ms * 1e-3) / 1e6
 
@@ -374,15 +454,23 @@ def main():
     proc1.close()
     peak, peak_kind = peak_hbm()
     achieved = ALGO_BYTES_PER_SAMPLE * S * n / (fe_ms * 1e-3) / 1e9
-    traffic = None      # dram bytes per launch from the committed ncu --set full capture of this workload
+    # dram bytes per launch: from the committed ncu --set full capture of this workload — only while the kernel
+    # that capture profiled is the kernel in the loaded library (SASS hash), else null
+    traffic, traffic_note = None, "no capture of this kernel build / workload committed"
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_frontend_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_frontend_traffic.json")))
         if tr["streams"] == S and tr["samples_per_stream"] == n and tr["kernel"] == "frontend_tma_kernel":
-            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            have = kernel_sass_hash() if rank == 0 else None
+            if have is not None and have == tr.get("sass_sha16"):
+                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+                traffic_note = f"ncu capture {tr.get('capture', '')}, kernel SASS sha {have}"
+            else:
+                traffic_note = f"committed capture is of another kernel build (sha {tr.get('sass_sha16')} vs loaded {have})"
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "frontend_tma_kernel", "achieved": achieved, "peak": peak,
                 "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": traffic_note,
                 "kernel_ms": fe_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SAMPLE * S * n,
                 "launches_timed": fe_launches,
                 "note": "one cp.async.bulk.tensor-fed launch over all streams (+ one small launch for the "
@@ -412,13 +500,21 @@ def main():
             step_host()          # synchronous: returns after the D2H copies completed
         barrier()
         dt = time.perf_counter() - t0
+        dts = [dt]
         if world > 1:
             t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+            allt = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            dts = [float(v.item()) for v in allt]
+            dt = max(dts)
         e2e = {"value": world * S * n * e2e_steps / dt / 1e6, "unit": "MS/s",
                "h2d_bytes_per_step": S * n * 8,
-               "d2h_bytes_per_step": S * (na.value + nr.value) * 8, "steps": e2e_steps}
+               "d2h_bytes_per_step": S * (na.value + nr.value) * 8, "steps": e2e_steps,
+               "h2d_GBps_per_rank": [S * n * 8 * e2e_steps / d / 1e9 for d in dts],
+               "host": host_topology(local),
+               "note": "cf32 (8 B/sample) is bound by the host->device copy: one PCIe Gen5 x16 link per GPU, and all "
+                       "links of the box draw on the host memory of the NUMA node(s) listed; device_format_u8 is the "
+                       "same stream at 2 B/sample"}
 
     # the same streams as an rtlsdr would deliver them (u8 I/Q, 2 bytes per sample): the handler's
     # (b - 127) / 128 conversion is fused into the front-end kernel, PCIe carries a quarter of the bytes
@@ -447,15 +543,78 @@ def main():
             step_host_u8()
         barrier()
         dt8 = time.perf_counter() - t0
+        dts8 = [dt8]
         if world > 1:
             t = torch.tensor([dt8], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt8 = float(t.item())
+            allt = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            dts8 = [float(v.item()) for v in allt]
+            dt8 = max(dts8)
         raw = {"format": "u8 I/Q as delivered by rtlsdr (2 B/sample), converted in the front-end kernel",
                "value": world * S * n * args.steps / (ms8 * 1e-3) / 1e6,
                "e2e": {"value": world * S * n * e2e_steps / dt8 / 1e6, "unit": "MS/s",
                        "h2d_bytes_per_step": S * n * 2,
-                       "d2h_bytes_per_step": S * (na.value + nr.value) * 8, "steps": e2e_steps}}
+                       "d2h_bytes_per_step": S * (na.value + nr.value) * 8, "steps": e2e_steps,
+                       "h2d_GBps_per_rank": [S * n * 2 * e2e_steps / d / 1e9 for d in dts8]}}
+
+    def chain_rate(streams, samples, stream0, steps, front_end_mode=0):
+        """device-resident rate of a fresh handle with `streams` streams x `samples` IQ samples per step"""
+        q = pkg.FmProcessorB200(n_streams=streams, max_samples_per_call=samples, device=local, keep_taps=False,
+                                front_end_mode=front_end_mode)
+        q.configure(**settings)
+        xq = gen_batch_gpu(torch, dev, streams, samples, stream0=stream0)
+        da = torch.empty((streams, samples // 48 + 16), dtype=torch.complex64, device=dev)
+        dr = torch.empty((streams, samples // 96 + 16), dtype=torch.complex64, device=dev)
+        stq = torch.cuda.ExternalStream(q.cuda_stream, device=dev)
+
+        def f():
+            q.process_device(xq.data_ptr(), samples, xq.stride(0), da.data_ptr(), da.stride(0), dr.data_ptr(), dr.stride(0))
+        for _ in range(3):
+            f()
+        q.sync()
+        msq = timed(f, steps, stq)
+        per = [v / steps for v in timed.per_rank]
+        q.close()
+        del xq, da, dr
+        return msq / steps, per
+
+    # BASELINE config 5 as written: `--streams` streams IN TOTAL, sharded over the ranks (strong scaling).  Every
+    # rank runs its contiguous share (sharding.stream_range) of the same 256 x n batch the N=1 line processes.
+    strong = None
+    if not args.no_sweep:
+        sh = importlib.import_module("sdrjfm_b200.sharding")
+        if world == 1:
+            strong = {"streams_total": S, "streams_per_gpu": [S], "ms_per_step": ms / args.steps,
+                      "value": value, "per_rank_ms": per_rank_ms, "note": "N=1: the weak-scaling line itself"}
+        else:
+            lo, hi = sh.stream_range(S, world, rank)
+            ms_s, per = chain_rate(hi - lo, n, lo, max(5, args.steps // 2))
+            strong = {"streams_total": S, "streams_per_gpu": [sh.stream_range(S, world, r)[1] - sh.stream_range(S, world, r)[0]
+                                                               for r in range(world)],
+                      "samples_per_stream": n, "ms_per_step": ms_s, "value": S * n / (ms_s * 1e-3) / 1e6, "unit": "MS/s",
+                      "per_rank_ms": per, "scaling": "strong"}
+
+    # the chain against the number of streams on ONE GPU, at constant bytes per step (streams x seconds fixed):
+    # the per-stream recurrences (pilot PLL, PSS) bound the rate when few streams share the SMs
+    sweep_streams = None
+    if not args.no_sweep and world == 1:
+        sweep_streams = []
+        for s_ in (32, 64, 128, 256, 512, 1024):
+            if s_ == S:
+                sweep_streams.append({"streams": s_, "samples_per_stream": n, "ms_per_step": ms / args.steps, "GS_per_s": value / 1e3})
+                continue
+            n_ = (S * n // s_) // (12 * 512) * (12 * 512)
+            ms_, _ = chain_rate(s_, n_, 0, 5)
+            sweep_streams.append({"streams": s_, "samples_per_stream": n_, "ms_per_step": ms_,
+                                  "GS_per_s": s_ * n_ / (ms_ * 1e-3) / 1e9})
+
+    # the reference-order front end (front_end_mode 2: fm-rate samples bit-identical to the reference's)
+    exact_fe = None
+    if not args.no_sweep and world == 1:
+        ms_x, _ = chain_rate(S, n, 0, 3, front_end_mode=2)
+        exact_fe = {"front_end_mode": 2, "ms_per_step": ms_x, "value": S * n / (ms_x * 1e-3) / 1e6, "unit": "MS/s",
+                    "note": "whole chain with the per-sample float32 DC recurrence and the tap-by-tap decimators "
+                            "(frontend_exact.cuh); latency-bound by the DC walker"}
 
     # the GUI's real-time cadence (SURVEY.md §8(b)): ONE stream, 16384-sample pulls (7.1 ms of signal,
     # fm-processor.cpp:374) through the host-buffer call, as the Qt adapter makes them
@@ -490,7 +649,7 @@ def main():
     clk.__exit__()
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_reference_rate(settings, args.cpu_seconds)
+        cpu = cpu_reference_both(settings, args.cpu_seconds)
         cpu.pop("seconds", None)
 
     if rank == 0:
@@ -498,7 +657,11 @@ def main():
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "x_realtime_2p304MSps": value / 2.304, "roofline": roofline,
+                "x_realtime_2p304MSps": value / 2.304, "per_rank_ms": per_rank_ms,
+                "x_realtime_note": "aggregate over all streams of the batch; ONE stream runs at x_realtime of gui_cadence "
+                                   "(the per-stream recurrences are sequential in time)",
+                "strong_scaling": strong, "streams_sweep": sweep_streams, "front_end_exact": exact_fe,
+                "audio48_parity": audio48_parity(), "roofline": roofline,
                 "cpu_baseline": cpu, "e2e": e2e, "device_format_u8": raw, "front_end_sweep": sweep, "gui_cadence": gui,
                 "gpu_launches": int(launches),
                 "clocks": clk.summary()}
