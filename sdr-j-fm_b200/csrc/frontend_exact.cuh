@@ -86,6 +86,111 @@ float2 cur [kFxBatch], nxt [kFxBatch];
 	if (write_state) { st.dc_re = (double)rr; st.dc_im = (double)ri; }
 }
 
+// ---- RF DC removal, EXACT and parallel in time -------------------------------------------------
+// The recurrence r[n] = fl (fl (fl (x[n] - r[n-1]) alpha) + r[n-1]) is sequential, but it can be SOLVED
+// in parallel like the pilot PLL (pilot.cuh): cut a window of 3072 samples into 256 segments of 12, give
+// every segment a start value s[t], let 256 threads walk their segments with the exact float32 arithmetic,
+// and compare: where e[t-1] (the end of segment t-1) equals s[t] bit for bit for every t, the window IS the
+// sequential trajectory (s[0] is the exact carried state, every link an exact reference step).  Otherwise
+// the starts are corrected by the prefix sum of the mismatches — on a float grid the segment map is a pure
+// translation except where a rounding or a binade changes, so one correction leaves at most a few 1-ulp
+// mismatches — and the walk repeats.  The exact prefix grows by at least one segment per pass, so 257 passes
+// always suffice; measured: 3-4 passes per window in steady state, a few tens in the first windows of a
+// stream where the estimate climbs through the binades (prototype against the sequential loop: bit-identical
+// on six signal classes).  One CTA per stream, both components per thread.
+constexpr int kFdThreads = 256;
+constexpr int kFdSeg     = 12;
+constexpr int kFdWin     = kFdThreads * kFdSeg;     // 3072 input samples per window
+constexpr int kFdMaxPass = kFdThreads + 1;
+
+__global__ void __launch_bounds__ (kFdThreads, 2)
+fx_dc_par_kernel (const void *__restrict__ x, int64_t in_pitch, RawFmt rf, int64_t N, float alpha,
+                  StreamState *__restrict__ state, float2 *__restrict__ xd, int64_t out_pitch, int write_state,
+                  int32_t *__restrict__ pass_stats) {
+__shared__ float2 sx [kFdWin + kFdWin / kFdSeg];     // slot (n) = n + n / 12: thread t's samples at 13 t + j
+__shared__ float2 sE [kFdThreads];
+__shared__ double sWx [kFdThreads / 32], sWy [kFdThreads / 32];
+const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+const int stream = blockIdx.x;
+StreamState &st = state [stream];
+const void *xs = reinterpret_cast<const char *>(x) + (int64_t)stream * in_pitch * fmt_bytes (rf.fmt);
+float2 *out = xd + (int64_t)stream * out_pitch;
+float2 carry = make_float2 ((float)st.dc_re, (float)st.dc_im);      // RfDC: exact float32 values in the double fields
+const float lim = 0.01f;                                             // DCRlimit, fm-processor.cpp:429
+int passes = 0, worst = 0;
+
+float2 nxt [kFdSeg];
+#pragma unroll
+	for (int k = 0; k < kFdSeg; k ++) {
+	   const int64_t n = (int64_t)k * kFdThreads + tid;
+	   nxt [k] = n < N ? load_iq_rt (xs, n, rf) : make_float2 (0.f, 0.f);
+	}
+	for (int64_t w0 = 0; w0 < N; w0 += kFdWin) {
+	   const int valid = (int)min ((int64_t)kFdWin, N - w0);
+//	   stage this window (coalesced loads were issued one window ahead), request the next one
+#pragma unroll
+	   for (int k = 0; k < kFdSeg; k ++) {
+	      const int n = k * kFdThreads + tid;
+	      sx [n + n / kFdSeg] = nxt [k];
+	   }
+#pragma unroll
+	   for (int k = 0; k < kFdSeg; k ++) {
+	      const int64_t n = w0 + kFdWin + (int64_t)k * kFdThreads + tid;
+	      nxt [k] = n < N ? load_iq_rt (xs, n, rf) : make_float2 (0.f, 0.f);
+	   }
+	   __syncthreads ();
+	   float2 v [kFdSeg], o [kFdSeg];
+#pragma unroll
+	   for (int j = 0; j < kFdSeg; j ++) v [j] = sx [(kFdSeg + 1) * tid + j];
+	   const int cnt = max (0, min (kFdSeg, valid - kFdSeg * tid));
+	   float2 s = carry;
+	   int pass = 0;
+	   for (; pass < kFdMaxPass; pass ++) {
+	      float rr = s.x, ri = s.y;
+#pragma unroll
+	      for (int j = 0; j < kFdSeg; j ++) {
+	         if (j < cnt) {
+	            rr = fadd (fmul (fsub (v [j].x, rr), alpha), rr);            // :425
+	            ri = fadd (fmul (fsub (v [j].y, ri), alpha), ri);
+	            const float cr = rr > lim ? lim : (rr < -lim ? -lim : rr);    // :430-443
+	            const float ci = ri > lim ? lim : (ri < -lim ? -lim : ri);
+	            o [j] = make_float2 (fsub (v [j].x, cr), fsub (v [j].y, ci));  // :445
+	         }
+	      }
+	      sE [tid] = make_float2 (rr, ri);
+	      __syncthreads ();
+	      const float2 prev = tid ? sE [tid - 1] : s;
+	      double dx = (double)prev.x - (double)s.x, dy = (double)prev.y - (double)s.y;      // mismatch at this segment's start
+	      const int bad = (dx != 0.0) || (dy != 0.0);
+#pragma unroll
+	      for (int k = 1; k < 32; k <<= 1) {                                  // inclusive prefix sums over the warp
+	         const double ux = __shfl_up_sync (0xffffffffu, dx, k), uy = __shfl_up_sync (0xffffffffu, dy, k);
+	         if (lane >= k) { dx += ux; dy += uy; }
+	      }
+	      if (lane == 31) { sWx [warp] = dx; sWy [warp] = dy; }
+	      if (!__syncthreads_or (bad)) break;
+	      for (int q = 0; q < warp; q ++) { dx += sWx [q]; dy += sWy [q]; }
+	      s = make_float2 ((float)((double)s.x + dx), (float)((double)s.y + dy));
+	   }
+	   carry = sE [kFdThreads - 1];
+	   passes += pass + 1; worst = max (worst, pass + 1);
+//	   results back through shared memory for coalesced stores
+#pragma unroll
+	   for (int j = 0; j < kFdSeg; j ++) if (j < cnt) sx [(kFdSeg + 1) * tid + j] = o [j];
+	   __syncthreads ();
+#pragma unroll
+	   for (int k = 0; k < kFdSeg; k ++) {
+	      const int n = k * kFdThreads + tid;
+	      if (n < valid) __stcs (out + w0 + n, sx [n + n / kFdSeg]);
+	   }
+	   __syncthreads ();
+	}
+	if (tid == 0) {
+	   if (write_state) { st.dc_re = (double)carry.x; st.dc_im = (double)carry.y; }
+	   if (pass_stats) { pass_stats [2 * stream] = passes; pass_stats [2 * stream + 1] = worst; }
+	}
+}
+
 // gain and oscillator of one filter-input sample (fm-processor.cpp:462-466); n = its index in the call
 __device__ __forceinline__ float2 fx_stage (const LoParams &L, float2 v, int64_t n) {
 	v = make_float2 (fmul (v.x, L.lgain), fmul (v.y, L.rgain));

@@ -116,6 +116,7 @@ struct Lane {
 	float2 *d_xd = nullptr;                 // [S][cap_in] samples behind the per-sample DC remover
 	float2 *d_xhist [2] = { nullptr, nullptr }; int xhist_sel = 0;
 	bool    fx_hist_valid = false;          // d_xhist continues the stream (false after a composite call)
+	bool    seq_dc = false;                 // SDRJFM_SEQ_DC=1: the lane-per-stream DC walker instead of the parallel solver (cross-check)
 	bool    hybrid_last = false;            // the last call ran the per-sample DC remover in front of the wide composite
 	double2 *d_dcnow = nullptr;             // [S] RfDC advanced through the fm-rate delay line (metadata, inputFilter on)
 	int64_t in_total = 0;                   // input samples consumed so far (per stream)
@@ -542,7 +543,8 @@ Lane *h = new Lane ();
 	   const char *env = getenv ("SDRJFM_GENERIC_FE"); h -> force_generic = env && env [0] == '1';
 	   env = getenv ("SDRJFM_NO_TMA"); h -> use_tma = !(env && env [0] == '1');
 	   env = getenv ("SDRJFM_TMA_CTAS"); h -> tma_ctas = env && atoi (env) > 0 ? atoi (env) : 0;
-	   env = getenv ("SDRJFM_NO_AUTO_EXACT"); h -> auto_exact = !(env && env [0] == '1'); }
+	   env = getenv ("SDRJFM_NO_AUTO_EXACT"); h -> auto_exact = !(env && env [0] == '1');
+	   env = getenv ("SDRJFM_SEQ_DC"); h -> seq_dc = env && env [0] == '1'; }
 	if (h -> cfg.working_rate <= 0) h -> cfg.working_rate = 48000;
 	if (h -> cfg.audio_rate <= 0) h -> cfg.audio_rate = h -> cfg.working_rate;
 	h -> n_sm = prop.multiProcessorCount;
@@ -852,6 +854,18 @@ static bool hybrid_wanted (const Lane *h) {
 	return h -> auto_exact && (h -> set.decoder == 2 || h -> set.decoder == 5 || h -> set.lo_hz != 0);
 }
 
+// the per-sample RF DC remover: exact parallel-in-time solver (or the sequential walker as a cross-check)
+static void launch_dc_exact (Lane *h, const void *src, int64_t pitch, RawFmt rf, int64_t n_proc, int write_state) {
+const int S = h -> cfg.n_streams;
+const float alpha = 1.0f / (float)h -> cfg.input_rate;                    // rfDcAlpha, fm-processor.cpp:379
+	if (h -> seq_dc)
+	   fx_dc_kernel<<<(S + 31) / 32, 32, 0, h -> stream>>> (src, pitch, rf, n_proc, S, alpha, h -> d_state, h -> d_xd, h -> cap_in, write_state);
+	else
+	   fx_dc_par_kernel<<<S, kFdThreads, 0, h -> stream>>> (src, pitch, rf, n_proc, alpha, h -> d_state, h -> d_xd, h -> cap_in,
+	                                                       write_state, getenv ("SDRJFM_DC_STATS") ? h -> d_iter_stats : nullptr);
+	h -> launches ++;
+}
+
 // K1x: per-sample DC removal, then the two decimators in the reference's operation order -> d_U = fm-rate samples
 static int launch_frontend_exact (Lane *h, const void *src, RawFmt rf, int64_t pitch, int32_t M, int64_t n_proc, bool dry) {
 const int S = h -> cfg.n_streams;
@@ -876,9 +890,7 @@ LoParams lp;
 	}
 const void *fsrc = src; RawFmt frf = rf; int64_t fpitch = pitch;
 	if (h -> set.dc_remove) {
-	   fx_dc_kernel<<<(S + 31) / 32, 32, 0, h -> stream>>> (src, pitch, rf, n_proc, S, 1.0f / (float)h -> cfg.input_rate,
-	                                                      h -> d_state, h -> d_xd, h -> cap_in, dry ? 0 : 1);
-	   h -> launches ++;
+	   launch_dc_exact (h, src, pitch, rf, n_proc, dry ? 0 : 1);
 	   fsrc = h -> d_xd; fpitch = h -> cap_in;
 	   memset (&frf, 0, sizeof frf); frf.fmt = kFmtCF32; frf.scale = 1.f;
 	}
@@ -1016,9 +1028,7 @@ const bool hybrid = !exact && hybrid_wanted (h);
 	      CK (dalloc (&h -> d_xd, (size_t)S * h -> cap_in));
 	      CK (dalloc (&h -> d_xhist [0], (size_t)S * kFxHist)); CK (dalloc (&h -> d_xhist [1], (size_t)S * kFxHist));
 	   }
-	   fx_dc_kernel<<<(S + 31) / 32, 32, 0, h -> stream>>> (src, pitch, rf, n_proc, S, 1.0f / (float)h -> cfg.input_rate,
-	                                                      h -> d_state, h -> d_xd, h -> cap_in, 1);
-	   h -> launches ++;
+	   launch_dc_exact (h, src, pitch, rf, n_proc, 1);
 	   src = h -> d_xd; pitch = h -> cap_in;
 	   memset (&rf, 0, sizeof rf); rf.fmt = kFmtCF32; rf.scale = 1.f;
 	}
