@@ -103,6 +103,7 @@ constexpr int kFdSeg     = 12;
 constexpr int kFdWin     = kFdThreads * kFdSeg;     // 3072 input samples per window
 constexpr int kFdMaxPass = kFdThreads + 1;
 
+template <bool CF32>
 __global__ void __launch_bounds__ (kFdThreads, 2)
 fx_dc_par_kernel (const void *__restrict__ x, int64_t in_pitch, RawFmt rf, int64_t N, float alpha,
                   StreamState *__restrict__ state, float2 *__restrict__ xd, int64_t out_pitch, int write_state,
@@ -123,7 +124,7 @@ float2 nxt [kFdSeg];
 #pragma unroll
 	for (int k = 0; k < kFdSeg; k ++) {
 	   const int64_t n = (int64_t)k * kFdThreads + tid;
-	   nxt [k] = n < N ? load_iq_rt (xs, n, rf) : make_float2 (0.f, 0.f);
+	   nxt [k] = n < N ? (CF32 ? __ldcs (reinterpret_cast<const float2 *>(xs) + n) : load_iq_rt (xs, n, rf)) : make_float2 (0.f, 0.f);
 	}
 	for (int64_t w0 = 0; w0 < N; w0 += kFdWin) {
 	   const int valid = (int)min ((int64_t)kFdWin, N - w0);
@@ -136,10 +137,10 @@ float2 nxt [kFdSeg];
 #pragma unroll
 	   for (int k = 0; k < kFdSeg; k ++) {
 	      const int64_t n = w0 + kFdWin + (int64_t)k * kFdThreads + tid;
-	      nxt [k] = n < N ? load_iq_rt (xs, n, rf) : make_float2 (0.f, 0.f);
+	      nxt [k] = n < N ? (CF32 ? __ldcs (reinterpret_cast<const float2 *>(xs) + n) : load_iq_rt (xs, n, rf)) : make_float2 (0.f, 0.f);
 	   }
 	   __syncthreads ();
-	   float2 v [kFdSeg], o [kFdSeg];
+	   float2 v [kFdSeg];
 #pragma unroll
 	   for (int j = 0; j < kFdSeg; j ++) v [j] = sx [(kFdSeg + 1) * tid + j];
 	   const int cnt = max (0, min (kFdSeg, valid - kFdSeg * tid));
@@ -152,9 +153,6 @@ float2 nxt [kFdSeg];
 	         if (j < cnt) {
 	            rr = fadd (fmul (fsub (v [j].x, rr), alpha), rr);            // :425
 	            ri = fadd (fmul (fsub (v [j].y, ri), alpha), ri);
-	            const float cr = rr > lim ? lim : (rr < -lim ? -lim : rr);    // :430-443
-	            const float ci = ri > lim ? lim : (ri < -lim ? -lim : ri);
-	            o [j] = make_float2 (fsub (v [j].x, cr), fsub (v [j].y, ci));  // :445
 	         }
 	      }
 	      sE [tid] = make_float2 (rr, ri);
@@ -174,9 +172,21 @@ float2 nxt [kFdSeg];
 	   }
 	   carry = sE [kFdThreads - 1];
 	   passes += pass + 1; worst = max (worst, pass + 1);
-//	   results back through shared memory for coalesced stores
+//	   the starts are exact now: one more walk subtracts the clamped estimate; results go back through shared
+//	   memory for coalesced stores
+	   {
+	      float rr = s.x, ri = s.y;
 #pragma unroll
-	   for (int j = 0; j < kFdSeg; j ++) if (j < cnt) sx [(kFdSeg + 1) * tid + j] = o [j];
+	      for (int j = 0; j < kFdSeg; j ++) {
+	         if (j < cnt) {
+	            rr = fadd (fmul (fsub (v [j].x, rr), alpha), rr);
+	            ri = fadd (fmul (fsub (v [j].y, ri), alpha), ri);
+	            const float cr = rr > lim ? lim : (rr < -lim ? -lim : rr);    // :430-443
+	            const float ci = ri > lim ? lim : (ri < -lim ? -lim : ri);
+	            sx [(kFdSeg + 1) * tid + j] = make_float2 (fsub (v [j].x, cr), fsub (v [j].y, ci));  // :445
+	         }
+	      }
+	   }
 	   __syncthreads ();
 #pragma unroll
 	   for (int k = 0; k < kFdSeg; k ++) {
@@ -212,7 +222,7 @@ struct Fx {
 //         DC remover is on, else the raw samples in their device format
 // xhist : [S][kFxHist] the last filter inputs AFTER gain / oscillator of the previous call
 // Z     : [S][out_pitch] fm-rate samples (the reference's v after fmBand_2, :474)
-template <int D2>
+template <int D2, bool PLAIN>       // PLAIN: complex-float source (the DC solver's output), oscillator off
 __global__ void __launch_bounds__ (kFxThreads)
 frontend_exact_kernel (const void *__restrict__ src, int64_t in_pitch, RawFmt rf,
                        const float2 *__restrict__ xhist, const LoParams lop,
@@ -232,8 +242,14 @@ const float2 *hs = xhist + (int64_t)stream * kFxHist;
 	   const int64_t n = O + e;
 	   float2 v = make_float2 (0.f, 0.f);
 	   if (n < 0) v = hs [kFxHist + n];
-	   else if (n < N) v = fx_stage (lop, rf.fmt == kFmtCF32 ? __ldcs (reinterpret_cast<const float2 *>(xs) + n)
-	                                                          : load_iq_rt (xs, n, rf), n);
+	   else if (n < N) {
+	      if (PLAIN) {
+	         v = __ldcs (reinterpret_cast<const float2 *>(xs) + n);
+	         v = make_float2 (fmul (v.x, lop.lgain), fmul (v.y, lop.rgain));
+	      }
+	      else v = fx_stage (lop, rf.fmt == kFmtCF32 ? __ldcs (reinterpret_cast<const float2 *>(xs) + n)
+	                                                 : load_iq_rt (xs, n, rf), n);
+	   }
 	   sm [e + e / D] = v;
 	}
 	__syncthreads ();

@@ -32,6 +32,7 @@
 #include "frontend_fir.cuh"
 #include "frontend_poly.cuh"
 #include "frontend_tma.cuh"
+#include "frontend_tmab.cuh"
 #include "frontend_exact.cuh"
 #include "resample.cuh"
 #include "discriminator.cuh"
@@ -92,7 +93,9 @@ struct Lane {
 	float        *d_tables = nullptr;
 	cudaStream_t  stream = nullptr;
 	cudaStream_t  stream_rds = nullptr;     // the RDS branch runs beside the stereo decoder (both only read K3's outputs)
-	cudaEvent_t   ev_k3 = nullptr, ev_rds = nullptr;
+	cudaEvent_t   ev_k3 = nullptr, ev_rds = nullptr, ev_k2 = nullptr;
+	cudaStream_t  stream_k3 = nullptr;      // the pilot stage of time slice j + 1 beside K4 / K5 / K6 of slice j
+	int32_t       slice_fm = 0;             // fm-rate samples per time slice (0: calls are not sliced; SDRJFM_FM_SLICE)
 	int           n_sm = 0;
 	bool          smem_lut_ok = false;
 	SinLut        lut;
@@ -544,7 +547,10 @@ Lane *h = new Lane ();
 	   env = getenv ("SDRJFM_NO_TMA"); h -> use_tma = !(env && env [0] == '1');
 	   env = getenv ("SDRJFM_TMA_CTAS"); h -> tma_ctas = env && atoi (env) > 0 ? atoi (env) : 0;
 	   env = getenv ("SDRJFM_NO_AUTO_EXACT"); h -> auto_exact = !(env && env [0] == '1');
-	   env = getenv ("SDRJFM_SEQ_DC"); h -> seq_dc = env && env [0] == '1'; }
+	   env = getenv ("SDRJFM_SEQ_DC"); h -> seq_dc = env && env [0] == '1';
+//	   time slices of 12 pilot windows = 49152 fm samples (0.256 s): 32 PSS blocks, 24 audio tiles
+	   env = getenv ("SDRJFM_FM_SLICE"); h -> slice_fm = env ? atoi (env) : 12 * kPiWin;
+	   if (h -> slice_fm % 4096) h -> slice_fm = 0; }
 	if (h -> cfg.working_rate <= 0) h -> cfg.working_rate = 48000;
 	if (h -> cfg.audio_rate <= 0) h -> cfg.audio_rate = h -> cfg.working_rate;
 	h -> n_sm = prop.multiProcessorCount;
@@ -583,6 +589,8 @@ cudaError_t e;
 #define AL(p, n) if ((e = dalloc (&h -> p, (size_t)(n))) != cudaSuccess) return fail (e, "cudaMalloc " #p)
 	if ((e = cudaStreamCreateWithFlags (&h -> stream, cudaStreamNonBlocking)) != cudaSuccess ||
 	    (e = cudaStreamCreateWithFlags (&h -> stream_rds, cudaStreamNonBlocking)) != cudaSuccess ||
+	    (e = cudaStreamCreateWithFlags (&h -> stream_k3, cudaStreamNonBlocking)) != cudaSuccess ||
+	    (e = cudaEventCreateWithFlags (&h -> ev_k2, cudaEventDisableTiming)) != cudaSuccess ||
 	    (e = cudaEventCreateWithFlags (&h -> ev_k3, cudaEventDisableTiming)) != cudaSuccess ||
 	    (e = cudaEventCreateWithFlags (&h -> ev_rds, cudaEventDisableTiming)) != cudaSuccess)
 	   return fail (e, "cudaStreamCreate");
@@ -637,9 +645,12 @@ cudaError_t e;
 	    (e = cudaFuncSetAttribute (frontend_tma_kernel<48, 1, 73>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                               kFtSmemBytes)) != cudaSuccess) return fail (e, "smem attr K1");
 	if ((e = poly_set_attr (shape)) != cudaSuccess) return fail (e, "smem attr K1g");
-	if ((e = cudaFuncSetAttribute (frontend_exact_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fx<2>::SmemBytes)) != cudaSuccess ||
-	    (e = cudaFuncSetAttribute (frontend_exact_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fx<5>::SmemBytes)) != cudaSuccess ||
-	    (e = cudaFuncSetAttribute (frontend_exact_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fx<8>::SmemBytes)) != cudaSuccess)
+	if ((e = cudaFuncSetAttribute (frontend_exact_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fx<2>::SmemBytes)) != cudaSuccess ||
+	    (e = cudaFuncSetAttribute (frontend_exact_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fx<5>::SmemBytes)) != cudaSuccess ||
+	    (e = cudaFuncSetAttribute (frontend_exact_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fx<8>::SmemBytes)) != cudaSuccess ||
+	    (e = cudaFuncSetAttribute (frontend_exact_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fx<2>::SmemBytes)) != cudaSuccess ||
+	    (e = cudaFuncSetAttribute (frontend_exact_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fx<5>::SmemBytes)) != cudaSuccess ||
+	    (e = cudaFuncSetAttribute (frontend_exact_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fx<8>::SmemBytes)) != cudaSuccess)
 	   return fail (e, "smem attr K1x");
 	{  const int seqsm = (cfg -> fm_rate / 4 + 1) * (int)sizeof (float);
 	   const auto A = cudaFuncAttributeMaxDynamicSharedMemorySize;
@@ -686,6 +697,8 @@ void *ptrs [] = { h -> d_tables, h -> d_sin_quarter, h -> d_in, h -> d_hist [0],
 	              h -> d_tone_tab, h -> d_peak_ring, h -> d_cv_taps, h -> d_cv_hist [0], h -> d_cv_hist [1] };
 	for (void *p : ptrs) if (p) cudaFree (p);
 	if (h -> stream_rds) { cudaStreamSynchronize (h -> stream_rds); cudaStreamDestroy (h -> stream_rds); }
+	if (h -> stream_k3) { cudaStreamSynchronize (h -> stream_k3); cudaStreamDestroy (h -> stream_k3); }
+	if (h -> ev_k2) cudaEventDestroy (h -> ev_k2);
 	if (h -> ev_k3) cudaEventDestroy (h -> ev_k3);
 	if (h -> ev_rds) cudaEventDestroy (h -> ev_rds);
 	if (h -> ev_sym) cudaEventDestroy (h -> ev_sym);
@@ -709,6 +722,7 @@ static int lane_sync (Lane *h) {
 	if (!h) return SDRJFM_ERR_ARG;
 	CK (cudaStreamSynchronize (h -> stream));
 	CK (cudaStreamSynchronize (h -> stream_rds));
+	CK (cudaStreamSynchronize (h -> stream_k3));
 	return SDRJFM_OK;
 }
 
@@ -775,6 +789,57 @@ const unsigned g = (unsigned)std::min<int64_t> (total, (int64_t)h -> tma_ctas);
 	return tiles;
 }
 
+// K1tb over the whole tiles of a call: device sample formats (and complex float at 6 MS/s) through a plain
+// 3-D tensor map of 32-bit words; returns the tiles per stream it produced (0: not applicable)
+template <int D, int GPT, int NT, int FMT>
+static int32_t tmab_launch (Lane *h, const void *x, int64_t pitch, RawFmt rf, int32_t M, const float2 *hist, int hlen,
+                            float2 *U, float2 *Sb) {
+typedef Fb<D, GPT, NT, FMT> F;
+const int S = h -> cfg.n_streams;
+const int32_t tileOut = kFeThreads * GPT;
+	if (!h -> use_tma || M < tileOut || ((uintptr_t)x & 15) != 0 || ((pitch * F::Bps) & 15) != 0 || !tma_encoder ()) return 0;
+FbConv cv = { 0u, 0.f };
+	if (FMT == kFmtU8) { cv.magic = 0x47800000u; cv.offset = 65536.0f + 127.0f / 128.0f; }
+	else if (FMT == kFmtS8) { cv.magic = 0x47800000u; cv.offset = 65536.0f + 1.0f; }
+	else if (FMT == kFmtS16) {
+	   int k = 0; while (k < 16 && ldexpf (1.0f, -k) != rf.scale) k ++;
+	   if (k < 8 || k >= 16) return 0;                              // denominators 256 .. 32768: the integer fits the mantissa field
+	   cv.magic = (uint32_t)(150 - k) << 23; cv.offset = ldexpf (1.0f, 23 - k) + ldexpf (1.0f, 15 - k);
+	}
+const int32_t tiles = M / tileOut;
+static bool attr_done = false;
+	if (!attr_done) {
+	   if (cudaFuncSetAttribute (frontend_tmab_kernel<D, GPT, NT, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SmemBytes) != cudaSuccess) return 0;
+	   attr_done = true;
+	}
+CUtensorMap map;
+const cuuint64_t gdim [3] = { (cuuint64_t)F::RowBytes / 4, (cuuint64_t)tiles * kFtRows, (cuuint64_t)S };
+const cuuint64_t gstr [2] = { (cuuint64_t)F::RowBytes, (cuuint64_t)pitch * F::Bps };
+const cuuint32_t box [3] = { (cuuint32_t)F::RowBytes / 4, (cuuint32_t)F::BoxRows, 1 };
+const cuuint32_t estr [3] = { 1, 1, 1 };
+	if (tma_encoder () (&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)x, gdim, gstr, box, estr,
+	                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+	                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return 0;
+const int64_t total = (int64_t)tiles * S;
+const int per_sm = F::SmemBytes * 2 <= 200 * 1024 ? 2 : 1;           // small stages: two persistent CTAs per SM
+const unsigned g = (unsigned)std::min<int64_t> (total, (int64_t)h -> tma_ctas * per_sm);
+	frontend_tmab_kernel<D, GPT, NT, FMT><<<g, kFeThreads, F::SmemBytes, h -> stream>>> (map, cv, hist, hlen, U, Sb,
+	      h -> resample ? h -> cap_a : h -> cap_fm, tiles, S);
+	h -> launches ++;
+	return tiles;
+}
+// the three byte formats of one front-end shape
+template <int D, int GPT, int NT>
+static int32_t tmab_launch_fmt (Lane *h, const void *x, int64_t pitch, RawFmt rf, int32_t M, const float2 *hist, int hlen,
+                                float2 *U, float2 *Sb) {
+	switch (rf.fmt) {
+	   case kFmtU8:  return tmab_launch<D, GPT, NT, kFmtU8>  (h, x, pitch, rf, M, hist, hlen, U, Sb);
+	   case kFmtS8:  return tmab_launch<D, GPT, NT, kFmtS8>  (h, x, pitch, rf, M, hist, hlen, U, Sb);
+	   case kFmtS16: return tmab_launch<D, GPT, NT, kFmtS16> (h, x, pitch, rf, M, hist, hlen, U, Sb);
+	   default:      return 0;
+	}
+}
+
 static int launch_frontend (Lane *h, const void *src, RawFmt rf, int64_t pitch, int32_t M) {
 const int S = h -> cfg.n_streams;
 	{ const int rc = consts_ensure (h); if (rc != SDRJFM_OK) return rc; }
@@ -825,6 +890,39 @@ float2 *U = wide ? h -> d_Uw : h -> d_U, *Sb = wide ? h -> d_Sw : h -> d_S;
 	   else if (M % kFeThreads) poly_launch<48, 1, 2> (h, src, pitch, rf, hist, hlen, U, Sb, M, lp, tiles);
 	   else h -> launches --;
 	}
+	else if (!wide && !lo && !h -> force_generic && rf.fmt != kFmtAirspy &&
+	         (rf.fmt != kFmtCF32 || h -> shape == 1 || h -> shape == kShapeResample)) {
+//	   device sample formats (and complex float at 6 MS/s) through TMA: K1tb over the whole tiles, K1g for the ragged rest
+	   int32_t tiles = 0;
+	   if (h -> shape == 0) {
+	      tiles = tmab_launch_fmt<12, 4, 37> (h, src, pitch, rf, M, hist, hlen, U, Sb);
+	      if (tiles == 0) poly_launch<12, 4, 4> (h, src, pitch, rf, hist, hlen, U, Sb, M, lp);
+	      else if (M % (kFeThreads * 4)) poly_launch<12, 4, 4> (h, src, pitch, rf, hist, hlen, U, Sb, M, lp, tiles);
+	      else h -> launches --;
+	   }
+	   else if (h -> shape == 1) {
+//	      rows of 60 samples: 480 / 240 bytes; the 8-bit formats (120-byte rows) stay on K1g
+	      tiles = rf.fmt == kFmtCF32 ? tmab_launch<30, 2, 55, kFmtCF32> (h, src, pitch, rf, M, hist, hlen, U, Sb)
+	            : rf.fmt == kFmtS16  ? tmab_launch<30, 2, 55, kFmtS16> (h, src, pitch, rf, M, hist, hlen, U, Sb) : 0;
+	      if (tiles == 0) poly_launch<30, 2, 2> (h, src, pitch, rf, hist, hlen, U, Sb, M, lp);
+	      else if (M % (kFeThreads * 2)) poly_launch<30, 2, 2> (h, src, pitch, rf, hist, hlen, U, Sb, M, lp, tiles);
+	      else h -> launches --;
+	   }
+	   else if (h -> shape == kShapeResample) {
+//	      stage A of the rational resampler: 49 taps / 5, rows of 40 samples, two rows of history
+	      tiles = rf.fmt == kFmtCF32 ? tmab_launch<kRsStageADecim, 8, kRsStageATaps, kFmtCF32> (h, src, pitch, rf, M, hist, hlen, U, Sb)
+	                                 : tmab_launch_fmt<kRsStageADecim, 8, kRsStageATaps> (h, src, pitch, rf, M, hist, hlen, U, Sb);
+	      if (tiles == 0) poly_launch<kRsStageADecim, 8, 10> (h, src, pitch, rf, hist, hlen, U, Sb, M, lp);
+	      else if (M % (kFeThreads * 8)) poly_launch<kRsStageADecim, 8, 10> (h, src, pitch, rf, hist, hlen, U, Sb, M, lp, tiles);
+	      else h -> launches --;
+	   }
+	   else {
+	      tiles = tmab_launch_fmt<48, 1, 73> (h, src, pitch, rf, M, hist, hlen, U, Sb);
+	      if (tiles == 0) poly_launch<48, 1, 2> (h, src, pitch, rf, hist, hlen, U, Sb, M, lp);
+	      else if (M % kFeThreads) poly_launch<48, 1, 2> (h, src, pitch, rf, hist, hlen, U, Sb, M, lp, tiles);
+	      else h -> launches --;
+	   }
+	}
 	else switch (h -> shape * 2 + (wide ? 1 : 0)) {
 	   case 0: poly_launch<12, 4, 4>  (h, src, pitch, rf, hist, hlen, U, Sb, M, lp); break;
 	   case 1: poly_launch<12, 4, 25> (h, src, pitch, rf, hist, hlen, U, Sb, M, lp); break;
@@ -860,9 +958,12 @@ const int S = h -> cfg.n_streams;
 const float alpha = 1.0f / (float)h -> cfg.input_rate;                    // rfDcAlpha, fm-processor.cpp:379
 	if (h -> seq_dc)
 	   fx_dc_kernel<<<(S + 31) / 32, 32, 0, h -> stream>>> (src, pitch, rf, n_proc, S, alpha, h -> d_state, h -> d_xd, h -> cap_in, write_state);
+	else if (rf.fmt == kFmtCF32)
+	   fx_dc_par_kernel<true><<<S, kFdThreads, 0, h -> stream>>> (src, pitch, rf, n_proc, alpha, h -> d_state, h -> d_xd, h -> cap_in,
+	                                                             write_state, getenv ("SDRJFM_DC_STATS") ? h -> d_iter_stats : nullptr);
 	else
-	   fx_dc_par_kernel<<<S, kFdThreads, 0, h -> stream>>> (src, pitch, rf, n_proc, alpha, h -> d_state, h -> d_xd, h -> cap_in,
-	                                                       write_state, getenv ("SDRJFM_DC_STATS") ? h -> d_iter_stats : nullptr);
+	   fx_dc_par_kernel<false><<<S, kFdThreads, 0, h -> stream>>> (src, pitch, rf, n_proc, alpha, h -> d_state, h -> d_xd, h -> cap_in,
+	                                                              write_state, getenv ("SDRJFM_DC_STATS") ? h -> d_iter_stats : nullptr);
 	h -> launches ++;
 }
 
@@ -896,11 +997,15 @@ const void *fsrc = src; RawFmt frf = rf; int64_t fpitch = pitch;
 	}
 const dim3 grid ((unsigned)((M + kFxThreads - 1) / kFxThreads), (unsigned)S);
 const float2 *xh = h -> d_xhist [h -> xhist_sel];
+const bool plain = frf.fmt == kFmtCF32 && lp.tab == nullptr;
+#define FX_LAUNCH(D2) do { if (plain) frontend_exact_kernel<D2, true><<<grid, kFxThreads, Fx<D2>::SmemBytes, h -> stream>>> (fsrc, fpitch, frf, xh, lp, h -> d_U, h -> cap_fm, M); \
+	                      else frontend_exact_kernel<D2, false><<<grid, kFxThreads, Fx<D2>::SmemBytes, h -> stream>>> (fsrc, fpitch, frf, xh, lp, h -> d_U, h -> cap_fm, M); } while (0)
 	switch (h -> decim / 6) {
-	   case 2:  frontend_exact_kernel<2><<<grid, kFxThreads, Fx<2>::SmemBytes, h -> stream>>> (fsrc, fpitch, frf, xh, lp, h -> d_U, h -> cap_fm, M); break;
-	   case 5:  frontend_exact_kernel<5><<<grid, kFxThreads, Fx<5>::SmemBytes, h -> stream>>> (fsrc, fpitch, frf, xh, lp, h -> d_U, h -> cap_fm, M); break;
-	   default: frontend_exact_kernel<8><<<grid, kFxThreads, Fx<8>::SmemBytes, h -> stream>>> (fsrc, fpitch, frf, xh, lp, h -> d_U, h -> cap_fm, M); break;
+	   case 2:  FX_LAUNCH (2); break;
+	   case 5:  FX_LAUNCH (5); break;
+	   default: FX_LAUNCH (8); break;
 	}
+#undef FX_LAUNCH
 	h -> launches ++;
 	if (!dry) {
 	   fx_roll_hist_kernel<<<S, kFxHist, 0, h -> stream>>> (fsrc, fpitch, frf, lp, xh, h -> d_xhist [h -> xhist_sel ^ 1], n_proc);
@@ -1136,7 +1241,23 @@ const int32_t ntiles = (M + kDiBlock - 1) / kDiBlock;
 	   CK (cudaGetLastError ());
 	   return SDRJFM_OK;
 	}
-//	K3 ------------------------------------------------------------------------------------
+//	K3 .. K6 run per TIME SLICE of the call: the per-stream recurrences (pilot solver, PSS loop) walk a stream in
+//	order, so inside one call K3 of slice j + 1 (on its own CUDA stream) runs beside K4 / K5 / K6 of slice j — the
+//	critical path of a call becomes max (K3, K4) instead of their sum.  A slice is a whole number of pilot windows,
+//	PSS blocks and audio tiles; stream state is carried exactly as it is between calls, so slicing is invisible in
+//	the results.  The per-call side outputs (scope stream, symbol stage) keep the whole call in one piece.
+const int32_t Mcall = M;
+const bool may_slice = h -> slice_fm > 0 && !h -> rds_symbols && h -> lf_plot < 0 && h -> spec_N == 0 && Mcall >= 2 * h -> slice_fm;
+const int32_t nsl = may_slice ? (Mcall + h -> slice_fm - 1) / h -> slice_fm : 1;
+	if (nsl > 1) {
+	   CK (cudaEventRecord (h -> ev_k2, h -> stream));
+	   CK (cudaStreamWaitEvent (h -> stream_k3, h -> ev_k2, 0));
+	}
+cudaStream_t ks = nsl > 1 ? h -> stream_k3 : h -> stream;
+int64_t na_tot = 0, nr_tot = 0, nq_tot = 0;
+	for (int32_t sl = 0; sl < nsl; sl ++) {
+const int64_t o = may_slice ? (int64_t)sl * h -> slice_fm : 0;
+const int32_t M = may_slice ? (int32_t)std::min<int64_t> (h -> slice_fm, Mcall - o) : Mcall;
 SeqParams sp;
 	sp.K_FM = consts [4];
 	sp.omega = (float)(((float)19000 / h -> cfg.fm_rate) * (2 * M_PI));   // OMEGA_PILOT, :34
@@ -1169,9 +1290,9 @@ SquelchParams qp;
 	   memcpy (qp.lp, sq + 1 + 4 * kSqQuads, sizeof qp.lp);
 	}
 const int dec = st.decoder == 2 ? 1 : st.decoder == 1 ? 2 : 0;
-#define SEQ_LAUNCH(D, Q) sequential_kernel<D, Q><<<seq_blocks, kSeqLanes, seq_smem, h -> stream>>> ( \
-	         h -> d_res, h -> d_zabs, h -> d_iqn, h -> cap_fm, M, sp, h -> lut, T + th.off_atan, \
-	         h -> d_state, h -> d_demod, h -> d_phase, h -> d_locked, qp, h -> d_sq)
+#define SEQ_LAUNCH(D, Q) sequential_kernel<D, Q><<<seq_blocks, kSeqLanes, seq_smem, ks>>> ( \
+	         (h -> d_res + o), (h -> d_zabs + o), (h -> d_iqn + o), h -> cap_fm, M, sp, h -> lut, T + th.off_atan, \
+	         h -> d_state, (h -> d_demod + o), (h -> d_phase + o), (h -> d_locked + o), qp, h -> d_sq)
 	if (st.squelch_mode != 0) {
 	   if (dec == 1) SEQ_LAUNCH (1, true); else if (dec == 2) SEQ_LAUNCH (2, true); else SEQ_LAUNCH (0, true);
 	}
@@ -1184,16 +1305,17 @@ const int dec = st.decoder == 2 ? 1 : st.decoder == 1 ? 2 : 0;
 	   pp.K_FM = sp.K_FM; pp.omega = sp.omega; pp.gain = sp.gain;
 	   pp.lock_half_rate = sp.lock_half_rate; pp.n_streams = S;
 	   if (h -> pilot_lut_smem)
-	      pilot_kernel<true><<<S, kPiThreads, kPiSmemBytes, h -> stream>>> (
-	            h -> d_res, h -> d_zabs, h -> cap_fm, M, pp, h -> lut, h -> d_state,
-	            h -> d_demod, h -> d_phase, h -> d_locked, h -> d_iter_stats);
+	      pilot_kernel<true><<<S, kPiThreads, kPiSmemBytes, ks>>> (
+	            (h -> d_res + o), (h -> d_zabs + o), h -> cap_fm, M, pp, h -> lut, h -> d_state,
+	            (h -> d_demod + o), (h -> d_phase + o), (h -> d_locked + o), h -> d_iter_stats, sl > 0 ? 1 : 0);
 	   else
-	      pilot_kernel<false><<<S, kPiThreads, sizeof (PilotSmem), h -> stream>>> (
-	            h -> d_res, h -> d_zabs, h -> cap_fm, M, pp, h -> lut, h -> d_state,
-	            h -> d_demod, h -> d_phase, h -> d_locked, h -> d_iter_stats);
+	      pilot_kernel<false><<<S, kPiThreads, sizeof (PilotSmem), ks>>> (
+	            (h -> d_res + o), (h -> d_zabs + o), h -> cap_fm, M, pp, h -> lut, h -> d_state,
+	            (h -> d_demod + o), (h -> d_phase + o), (h -> d_locked + o), h -> d_iter_stats, sl > 0 ? 1 : 0);
 	}
 	h -> launches ++;
-	if (st.rds_mode != 0) CK (cudaEventRecord (h -> ev_k3, h -> stream));
+	if (st.rds_mode != 0 || nsl > 1) CK (cudaEventRecord (h -> ev_k3, ks));
+	if (nsl > 1) CK (cudaStreamWaitEvent (h -> stream, h -> ev_k3, 0));
 //	K4 ------------------------------------------------------------------------------------
 	{
 	   StereoParams q;
@@ -1204,9 +1326,9 @@ const int dec = st.decoder == 2 ? 1 : st.decoder == 1 ? 2 : 0;
 	   q.rate3 = 3 * h -> cfg.fm_rate;
 	   q.write_pss_tap = h -> cfg.keep_taps;
 	   stereo_kernel<<<S, kStThreads, 0, h -> stream>>> (
-	         h -> d_demod, h -> d_phase, h -> d_locked, h -> cap_fm, M, q,
+	         (h -> d_demod + o), (h -> d_phase + o), (h -> d_locked + o), h -> cap_fm, M, q,
 	         reinterpret_cast<const float2 *>(T + th.off_sincos), h -> d_state, h -> d_pss_ring,
-	         h -> d_lr, h -> d_pssd, h -> lf_plot == 4 ? h -> d_plot : nullptr);
+	         (h -> d_lr + o), (h -> d_pssd + o), h -> lf_plot == 4 ? h -> d_plot + o : nullptr);
 	   h -> launches ++;
 	}
 //	K5 ------------------------------------------------------------------------------------
@@ -1219,7 +1341,7 @@ const int dec = st.decoder == 2 ? 1 : st.decoder == 1 ? 2 : 0;
 	      const int64_t K = (n0 + m) / kRdsBlock;
 	      const int32_t mEnd = (int32_t)std::min<int64_t> (M, (K + 1) * kRdsBlock - n0);
 	      dim3 g ((unsigned)((mEnd - m + 255) / 256), (unsigned)S);
-	      rds_append_kernel<<<g, 256, 0, rs>>> (h -> d_demod, h -> d_phase, h -> cap_fm, m, mEnd, n0,
+	      rds_append_kernel<<<g, 256, 0, rs>>> ((h -> d_demod + o), (h -> d_phase + o), h -> cap_fm, m, mEnd, n0,
 	                                                    h -> d_rds_dring, h -> d_rds_pring);
 	      h -> launches ++;
 	      if (K >= 1 && h -> rds_last_block < K - 1) {
@@ -1229,15 +1351,15 @@ const int dec = st.decoder == 2 ? 1 : st.decoder == 1 ? 2 : 0;
 	         h -> rds_last_block = K - 1;
 	      }
 	      rds_mix_kernel<<<g, 256, 0, rs>>> (h -> d_rds_pring, h -> d_rds_bp, h -> d_rds_hi,
-	                                                 h -> cap_fm, m, mEnd, n0, h -> d_rdsc);
+	                                                 h -> cap_fm, m, mEnd, n0, (h -> d_rdsc + o));
 	      h -> launches ++;
 	      m = mEnd;
 	   }
 	   const int32_t nout = (int32_t)((n0 + M) / kRdsDecim - n0 / kRdsDecim);
-	   float2 *rout = d_rds_out ? d_rds_out : h -> d_rds24;
+	   float2 *rout = (d_rds_out ? d_rds_out : h -> d_rds24) + nr_tot;
 	   const int64_t rpitch = d_rds_out ? rds_pitch : h -> cap_rds;
 	   dim3 g ((unsigned)((std::max (nout, 1) + 127) / 128), (unsigned)S);
-	   rds_decim_kernel<<<g, 128, 0, rs>>> (h -> d_rdsc, h -> cap_fm, M, n0, h -> d_rds_dtaps,
+	   rds_decim_kernel<<<g, 128, 0, rs>>> ((h -> d_rdsc + o), h -> cap_fm, M, n0, h -> d_rds_dtaps,
 	         h -> d_rds_hist [h -> rds_hist_sel], h -> d_rds_hist [h -> rds_hist_sel ^ 1], rout, rpitch, nout,
 	         h -> rds_symbols ? h -> d_rsy_in : nullptr, h -> cap_rds);
 //	   join point of the 24 kHz baseband; the symbol stage below keeps running on the side stream,
@@ -1246,9 +1368,10 @@ const int dec = st.decoder == 2 ? 1 : st.decoder == 1 ? 2 : 0;
 	   h -> launches ++;
 	   h -> rds_hist_sel ^= 1;
 	   h -> rds_total += M;
-	   h -> last_nrds = nout;
-	   h -> last_rds_ptr = rout; h -> last_rds_pitch = rpitch;
-	   if (n_rds) *n_rds = nout;
+	   nr_tot += nout;
+	   h -> last_nrds = nr_tot;
+	   h -> last_rds_ptr = rout - (nr_tot - nout); h -> last_rds_pitch = rpitch;
+	   if (n_rds) *n_rds = nr_tot;
 	   if (h -> rds_symbols && nout > 0) {
 //	      symbol stage, mode RDS_1 (rds-decoder.cpp:69-82): Costas (rate, 1/16, 0.02/16, 10 Hz) + decoder 1
 	      RdsSymParams sp2;
@@ -1274,22 +1397,22 @@ const int dec = st.decoder == 2 ? 1 : st.decoder == 1 ? 2 : 0;
 	   }
 	}
 //	K6 ------------------------------------------------------------------------------------
-const float2 *lr_in = h -> d_lr;
+const float2 *lr_in = (h -> d_lr + o);
 	if (st.lf_cutoff_hz > 0) {
 	   dim3 g ((unsigned)((M + kAlpTile - 1) / kAlpTile), (unsigned)S);
-	   audio_lp_kernel<<<g, kAlpThreads, 0, h -> stream>>> (h -> d_lr, h -> cap_fm, M,
-	                                                        h -> d_alp_hist [h -> alp_sel], h -> d_lrf);
+	   audio_lp_kernel<<<g, kAlpThreads, 0, h -> stream>>> ((h -> d_lr + o), h -> cap_fm, M,
+	                                                        h -> d_alp_hist [h -> alp_sel], (h -> d_lrf + o));
 	   roll_history_kernel<<<dim3 (kAlpHist / 256, S), 256, 0, h -> stream>>> (
-	         h -> d_lr, h -> cap_fm, h -> d_alp_hist [h -> alp_sel], h -> d_alp_hist [h -> alp_sel ^ 1], M, kAlpHist);
+	         (h -> d_lr + o), h -> cap_fm, h -> d_alp_hist [h -> alp_sel], h -> d_alp_hist [h -> alp_sel ^ 1], M, kAlpHist);
 	   h -> alp_sel ^= 1; h -> launches += 2;
-	   lr_in = h -> d_lrf;
+	   lr_in = (h -> d_lrf + o);
 	}
 const int64_t q0 = h -> fm_total / kRsDecim;
 const int64_t q1 = (h -> fm_total + M) / kRsDecim;
 const int32_t nq = (int32_t)(q1 - q0);
 const bool convert = h -> cfg.audio_rate != h -> cfg.working_rate;
 //	working-rate PCM: straight into the caller's buffer unless the second converter follows
-float2 *aout = (d_audio_out && !convert) ? d_audio_out : h -> d_audio;
+float2 *aout = ((d_audio_out && !convert) ? d_audio_out : h -> d_audio) + nq_tot;
 const int64_t apitch = (d_audio_out && !convert) ? audio_pitch : h -> cap_audio;
 	{
 	   AudioParams ap;
@@ -1304,14 +1427,15 @@ const int64_t apitch = (d_audio_out && !convert) ? audio_pitch : h -> cap_audio;
 	   dim3 g ((unsigned)((M + kAuTile - 1) / kAuTile), (unsigned)S);
 	   audio_kernel<<<g, kAuThreads, 0, h -> stream>>> (
 	         lr_in, h -> cap_fm, ap, h -> d_ahist [h -> ahist_sel], h -> d_ahist [h -> ahist_sel ^ 1],
-	         h -> d_state, h -> d_a192, aout, apitch, h -> d_plot, h -> d_tone_tab);
+	         h -> d_state, (h -> d_a192 + o), aout, apitch, h -> d_plot ? h -> d_plot + o : nullptr, h -> d_tone_tab);
 	   h -> launches ++;
 	   h -> ahist_sel ^= 1;
 	   h -> fade_cnt = h -> fade_cnt > nq ? h -> fade_cnt - nq : 0;
 	   if (h -> tone_on) h -> tone_pos = (h -> tone_pos + nq) % (h -> tone_arm + h -> tone_burst);
 	}
 //	evaluatePeakLevel (:772-798): one read-out per 961 PCM samples, counted from the start of the processor
-	h -> peak_e0 = q0 / h -> peak_block; h -> peak_e1 = q1 / h -> peak_block;
+	if (sl == 0) h -> peak_e0 = q0 / h -> peak_block;
+	h -> peak_e1 = q1 / h -> peak_block;
 	if (nq > 0) {
 	   const unsigned nb = (unsigned)((q1 - 1) / h -> peak_block - q0 / h -> peak_block + 1);
 	   peak_kernel<<<dim3 (nb, (unsigned)S), 32, 0, h -> stream>>> (aout, apitch, q0, nq, h -> peak_block, h -> d_state,
@@ -1327,7 +1451,7 @@ int64_t n_out = nq;
 	   const int64_t t1 = cp.t0 + nq;
 	   cp.k0 = (cp.t0 * cp.L + cp.M - 1) / cp.M;                        // outputs that existed before this call: ceil (T L / M)
 	   cp.nk = (int32_t)((t1 * cp.L + cp.M - 1) / cp.M - cp.k0);
-	   float2 *cout = d_audio_out ? d_audio_out : h -> d_audio + 0;     // (no caller buffer: results stay internal)
+	   float2 *cout = d_audio_out ? d_audio_out + na_tot : nullptr;     // (no caller buffer: nothing to write)
 	   const int64_t cpitch = d_audio_out ? audio_pitch : h -> cap_out;
 	   if (d_audio_out && cp.nk > 0) {
 	      audio_convert_kernel<<<dim3 ((unsigned)((cp.nk + 255) / 256), (unsigned)S), 256, 0, h -> stream>>> (
@@ -1341,11 +1465,13 @@ int64_t n_out = nq;
 	   n_out = cp.nk;
 	}
 	h -> fm_total += M;
-	h -> last_naudio = n_out;
-	if (n_audio) *n_audio = n_out;
+	na_tot += n_out; nq_tot += nq;
+	}        // time slices
+	h -> last_naudio = na_tot;
+	if (n_audio) *n_audio = na_tot;
 	if (st.rds_mode != 0) CK (cudaStreamWaitEvent (h -> stream, h -> ev_rds, 0));     // join
 	if (h -> spec_N && h -> lf_plot >= 0) {
-	   const int rc = run_lf_spectrum (h, M);
+	   const int rc = run_lf_spectrum (h, Mcall);
 	   if (rc != SDRJFM_OK) return rc;
 	}
 	CK (cudaGetLastError ());

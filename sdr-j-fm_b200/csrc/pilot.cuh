@@ -148,7 +148,7 @@ pilot_kernel (const float *__restrict__ res_raw, const float *__restrict__ zabs,
               int64_t pitch, int32_t M, const PilotParams P, const SinLut L,
               StreamState *__restrict__ state,
               float *__restrict__ demod_out, float *__restrict__ phase_out,
-              uint8_t *__restrict__ locked_out, int32_t *__restrict__ iter_stats) {
+              uint8_t *__restrict__ locked_out, int32_t *__restrict__ iter_stats, int accumulate) {
 extern __shared__ __align__ (16) unsigned char smem_raw [];
 // LUT_SMEM: the quarter-wave sine table is staged in shared memory (one CTA per SM).  Otherwise it is
 // read through L1 (192 KB, read-only path), which leaves room for two CTAs per SM.
@@ -433,11 +433,12 @@ int    itTotal = 0, itMax = 0, nFallback = 0;
 	   st.pilot_phase = phi0; st.pilot_old = oscPrev;
 	   st.pilot_locked = runCarry > P.lock_half_rate;
 	   st.pilot_stable_cnt = min (runCarry, P.lock_half_rate + 1);
-	   if (iter_stats) {
-	      iter_stats [stream * 4 + 0] = itTotal;
-	      iter_stats [stream * 4 + 1] = itMax;
-	      iter_stats [stream * 4 + 2] = nFallback;
-	      iter_stats [stream * 4 + 3] = (M + kPiWin - 1) / kPiWin;
+	   if (iter_stats) {          // accumulate: a later time slice of the same call
+	      int32_t *q = iter_stats + stream * 4;
+	      q [0] = (accumulate ? q [0] : 0) + itTotal;
+	      q [1] = max (accumulate ? q [1] : 0, itMax);
+	      q [2] = (accumulate ? q [2] : 0) + nFallback;
+	      q [3] = (accumulate ? q [3] : 0) + (M + kPiWin - 1) / kPiWin;
 	   }
 	}
 }
