@@ -124,21 +124,25 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.stop = index, [], threading.Event()
+    def __init__(self, indices, period=0.2):
+        """indices: the GPUs of this job.  ONE sampler per job (rank 0) polls all of them in one nvidia-smi call:
+        eight ranks polling five times a second each put 40 nvidia-smi processes per second on the host, which
+        showed as a 10 % slower slowest rank at N=8 (profiles/r2_summary.md)."""
+        self.indices, self.rows, self.stop, self.period = list(indices), [], threading.Event(), period
         self.t = threading.Thread(target=self.run, daemon=True)
 
     def run(self):
         while not self.stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                out = subprocess.run(["nvidia-smi", "-i", ",".join(str(i) for i in self.indices), f"--query-gpu={self.Q}",
                                       "--format=csv,noheader,nounits"], capture_output=True,
                                      text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                for ln in out.splitlines():
+                    if ln.strip():
+                        self.rows.append([c.strip() for c in ln.split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(self.period)
 
     def __enter__(self):
         self.t.start()
@@ -426,8 +430,9 @@ def main():
     l0 = proc.launch_count
     # clocks / throttle reasons are sampled over ALL timed regions of this run (device-resident steps,
     # front-end kernel alone, end-to-end steps); the sampler is stopped before the CPU baseline leg
-    clk = ClockSampler(local)
-    clk.__enter__()
+    clk = ClockSampler(range(world) if world > 1 else [local], period=0.2 if world == 1 else 0.5)
+    if rank == 0:
+        clk.__enter__()
     ms = timed(step_device, args.steps)
     per_rank_ms = [v / args.steps for v in timed.per_rank]
     launches = proc.launch_count - l0
@@ -646,7 +651,8 @@ def main():
     sweep = None
     if args.front_end_sweep and rank == 0:
         sweep = front_end_sweep(pkg, torch, dev, local, S, peak)
-    clk.__exit__()
+    if rank == 0:
+        clk.__exit__()
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_reference_both(settings, args.cpu_seconds)

@@ -110,6 +110,12 @@ void    ref_post_destroy (void *h);
 void    ref_post_set (void *h, int32_t tone_on, int32_t delay_steps);
 int64_t ref_post_process (void *h, const float *pcm, int64_t n, float *pcm_out, float *peaks, int64_t cap_pairs);
 
+/* RDS symbol stage of mode RDS_2 (ref_ only): the reference's own rdsDecoder_2, see ref_harness.cpp */
+void   *ref_rds2_create (int32_t rate);
+void    ref_rds2_destroy (void *h);
+int64_t ref_rds2_process (void *h, const float *rds24, int64_t n, uint8_t *bits, int64_t cap);
+int32_t ref_rds2_dump (void *h, float *out, int32_t cap);
+
 /* `which` for *_dump_taps (complex entries unless noted) */
 enum {
     DUMP_FMBAND1 = 0,      /* 25 complex                      */

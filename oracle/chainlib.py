@@ -263,3 +263,34 @@ class RefPost:
         peaks = np.zeros((len(x) // 900 + 4, 2), np.float32)
         n = self.lib.ref_post_process(self.h, x.ctypes.data, len(x), out.ctypes.data, peaks.ctypes.data, len(peaks))
         return out, peaks[:n].copy()
+
+
+class Rds2:
+    """RDS symbol stage, mode RDS_2: the reference's rdsDecoder_2 (matched filter, AGC, M&M timing, Costas) (ref_ only)."""
+
+    def __init__(self, rate=24000):
+        self.lib = C.CDLL(_PATHS["ref"])
+        self.lib.ref_rds2_create.restype = C.c_void_p
+        self.lib.ref_rds2_create.argtypes = [C.c_int32]
+        self.lib.ref_rds2_destroy.argtypes = [C.c_void_p]
+        self.lib.ref_rds2_process.restype = C.c_int64
+        self.lib.ref_rds2_process.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+        self.lib.ref_rds2_dump.restype = C.c_int32
+        self.lib.ref_rds2_dump.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+        self.h = self.lib.ref_rds2_create(rate)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.ref_rds2_destroy(self.h)
+            self.h = None
+
+    def process(self, rds24):
+        x = np.ascontiguousarray(rds24, dtype=np.complex64)
+        bits = np.zeros(len(x) // 8 + 16, np.uint8)
+        n = self.lib.ref_rds2_process(self.h, x.ctypes.data, len(x), bits.ctypes.data, len(bits))
+        return bits[:n].copy()
+
+    def matched_filter(self):
+        a = np.zeros(64, np.float32)
+        n = self.lib.ref_rds2_dump(self.h, a.ctypes.data, 64)
+        return a[:n].copy()

@@ -17,6 +17,8 @@
  * (newconverter.cpp:55-80), which is not installed and not vendored.
  */
 #include <cstring>
+#include <cstdlib>
+#include <cstdio>
 #include <vector>
 #include <complex>
 #include <cmath>
@@ -40,6 +42,7 @@
 #include "costas.h"
 #define private public       /* the dump below reads rdsDecoder_1's tables; nothing else is touched */
 #include "rds-decoder-1.h"
+#include "rds-decoder-2.h"
 #undef private
 #undef private
 #undef protected
@@ -678,5 +681,33 @@ int64_t ne = 0;
 	   pcm_out [2 * i] = real (s); pcm_out [2 * i + 1] = imag (s);
 	}
 	return ne;
+}
+}
+
+// ---- RDS symbol stage, mode RDS_2: the reference's own rdsDecoder_2 (src/rds/rds-decoder-2.cpp), fed sample by
+// sample as rdsDecoder::doDecode does in case RDS_2 (src/rds/rds-decoder.cpp:84-88)
+extern "C" {
+void	*ref_rds2_create (int32_t rate) {
+rdsDecoder_2 *d = new rdsDecoder_2 (nullptr, rate);
+	d -> previousBit = false;          // left uninitialised by the reference's constructor
+	return d;
+}
+void	ref_rds2_destroy (void *h) { delete (rdsDecoder_2 *)h; }
+int64_t	ref_rds2_process (void *h, const float *rds24, int64_t n, uint8_t *bits, int64_t cap) {
+rdsDecoder_2 *d = (rdsDecoder_2 *)h;
+int64_t nb = 0;
+	for (int64_t i = 0; i < n; i ++) {
+	   std::complex<float> m;
+	   uint8_t b;
+	   if (d -> doDecode (std::complex<float> (rds24 [2 * i], rds24 [2 * i + 1]), &m, &b) && nb < cap) bits [nb ++] = b;
+	}
+	return nb;
+}
+int32_t	ref_rds2_dump (void *h, float *out, int32_t cap) {
+rdsDecoder_2 *d = (rdsDecoder_2 *)h;
+int32_t n = (int32_t)d -> my_matchedFltKernelVec. size ();
+	if (n > cap) n = cap;
+	for (int32_t i = 0; i < n; i ++) out [i] = d -> my_matchedFltKernelVec [i];
+	return n;
 }
 }

@@ -160,6 +160,7 @@ struct Lane {
 	RdsSymState *d_rsy_state = nullptr; uint8_t *d_rsy_bits = nullptr; int32_t *d_rsy_nbits = nullptr;
 	float   *d_rsy_c = nullptr, *d_rsy_v = nullptr, *d_rsy_w = nullptr;    // [S][cap_rds] Costas / low-pass / matched-filter outputs
 	float2  *d_rsy_in = nullptr;            // [S][cap_rds] private copy of the 24 kHz baseband of the call
+	Rds2State *d_rs2_state = nullptr; float2 *d_rs2_m = nullptr;     // mode RDS_2: rdsDecoder_2 state, matched-filter output
 	int32_t  cap_bits = 0;
 	dcplx   *d_tileB = nullptr; DiscrSnap *d_snap = nullptr; int32_t ntiles_cap = 0;   // K2 pre-pass
 	float2  *d_pss_ring = nullptr;          // [S][2048] PSS filter input ring (state)
@@ -548,8 +549,8 @@ Lane *h = new Lane ();
 	   env = getenv ("SDRJFM_TMA_CTAS"); h -> tma_ctas = env && atoi (env) > 0 ? atoi (env) : 0;
 	   env = getenv ("SDRJFM_NO_AUTO_EXACT"); h -> auto_exact = !(env && env [0] == '1');
 	   env = getenv ("SDRJFM_SEQ_DC"); h -> seq_dc = env && env [0] == '1';
-//	   time slices of 12 pilot windows = 49152 fm samples (0.256 s): 32 PSS blocks, 24 audio tiles
-	   env = getenv ("SDRJFM_FM_SLICE"); h -> slice_fm = env ? atoi (env) : 12 * kPiWin;
+//	   time slices of 6 pilot windows = 24576 fm samples (0.128 s): 16 PSS blocks, 12 audio tiles
+	   env = getenv ("SDRJFM_FM_SLICE"); h -> slice_fm = env ? atoi (env) : 6 * kPiWin;
 	   if (h -> slice_fm % 4096) h -> slice_fm = 0; }
 	if (h -> cfg.working_rate <= 0) h -> cfg.working_rate = 48000;
 	if (h -> cfg.audio_rate <= 0) h -> cfg.audio_rate = h -> cfg.working_rate;
@@ -694,7 +695,8 @@ void *ptrs [] = { h -> d_tables, h -> d_sin_quarter, h -> d_in, h -> d_hist [0],
 	              h -> d_scan_carry [0], h -> d_scan_carry [1], h -> d_scan_db, h -> d_plot,
 	              h -> d_spec_in, h -> d_spec_carry [0], h -> d_spec_carry [1], h -> d_spec_win,
 	              h -> d_spec_Y, h -> d_spec_avg, h -> d_spec_disp, h -> d_xd, h -> d_xhist [0], h -> d_xhist [1], h -> d_dcnow,
-	              h -> d_tone_tab, h -> d_peak_ring, h -> d_cv_taps, h -> d_cv_hist [0], h -> d_cv_hist [1] };
+	              h -> d_tone_tab, h -> d_peak_ring, h -> d_cv_taps, h -> d_cv_hist [0], h -> d_cv_hist [1],
+	              h -> d_rs2_state, h -> d_rs2_m };
 	for (void *p : ptrs) if (p) cudaFree (p);
 	if (h -> stream_rds) { cudaStreamSynchronize (h -> stream_rds); cudaStreamDestroy (h -> stream_rds); }
 	if (h -> stream_k3) { cudaStreamSynchronize (h -> stream_k3); cudaStreamDestroy (h -> stream_k3); }
@@ -1372,7 +1374,21 @@ const int dec = st.decoder == 2 ? 1 : st.decoder == 1 ? 2 : 0;
 	   h -> last_nrds = nr_tot;
 	   h -> last_rds_ptr = rout - (nr_tot - nout); h -> last_rds_pitch = rpitch;
 	   if (n_rds) *n_rds = nr_tot;
-	   if (h -> rds_symbols && nout > 0) {
+	   if (h -> rds_symbols && nout > 0 && st.rds_mode == 2) {
+//	      symbol stage, mode RDS_2 (rds-decoder.cpp:84-88): rdsDecoder_2 (matched filter, AGC, M&M timing, Costas)
+	      Rds2Params p2;
+	      design_rds2_matched_filter (24000, p2.taps);
+	      p2.agc_rate = 2e-3f; p2.agc_ref = 0.38f;                             // my_AGC (2e-3f, 0.38f, 9.0f), rds-decoder-2.cpp:46
+	      p2.sps = 24000 / (float)1187.5f; p2.mm_alpha = 0.01;                  // :52, :59
+	      p2.c_alpha = 1.0f; p2.c_beta = 0.02f; p2.freq_limit = 2 * M_PI * 10.0f / 24000.0f;     // my_Costas (rate, 1.0f, 0.02f, 10.0f)
+	      const int64_t bp = h -> cap_rds;
+	      rds2_match_kernel<<<dim3 ((unsigned)((nout + 127) / 128), (unsigned)S), 128, 0, rs>>> (
+	            h -> d_rsy_in, bp, nout, p2, h -> d_rs2_state, h -> d_rs2_m);
+	      rds2_seq_kernel<<<(S + kRsyLanes - 1) / kRsyLanes, kRsyLanes, 0, rs>>> (
+	            h -> d_rsy_in, h -> d_rs2_m, bp, nout, S, p2, h -> d_rs2_state, h -> d_rsy_bits, h -> cap_bits, h -> d_rsy_nbits);
+	      h -> launches += 2;
+	   }
+	   else if (h -> rds_symbols && nout > 0) {
 //	      symbol stage, mode RDS_1 (rds-decoder.cpp:69-82): Costas (rate, 1/16, 0.02/16, 10 Hz) + decoder 1
 	      RdsSymParams sp2;
 	      sp2.alpha = 1.0f / 16.0f; sp2.beta = 0.02f / 16.0f;
@@ -1728,15 +1744,38 @@ static int lane_set_rds_mode (Lane *h, int32_t m) {
 	   int rc = rds_setup (h);
 	   if (rc != SDRJFM_OK) return rc;
 	}
+	if (m == 3 && h -> rds_symbols) {
+	   h -> err = "the GPU symbol stage covers RDS_1 and RDS_2; switch it off for RDS_3"; return SDRJFM_ERR_UNSUPPORTED;
+	}
 	if (h -> lf_plot >= 8) h -> spec_refresh = true;                      // setfmRdsSelector: new_lfSpectrum (:843-846)
 	h -> set.rds_mode = m; return SDRJFM_OK;
 }
 // the symbol stage of rdsDecoder::doDecode for mode RDS_1 on the GPU (optional).
 // Switching it on starts the Costas loop and the decoder's filters from their constructor state.
+static int rs2_reset (Lane *h) {            // rdsDecoder_2's constructor state (rds-decoder-2.cpp:44-77)
+const size_t S = h -> cfg.n_streams;
+std::vector<Rds2State> st (S);
+	memset (st.data (), 0, S * sizeof (Rds2State));
+	for (auto &q : st) { q.gain = 9.0f; q.skip = 3; }
+	CK (cudaMemcpy (h -> d_rs2_state, st.data (), S * sizeof (Rds2State), cudaMemcpyHostToDevice));
+	return SDRJFM_OK;
+}
 static int lane_set_rds_symbol_stage (Lane *h, int32_t on) {
 	if (!h) return SDRJFM_ERR_ARG;
+	if (on && h -> set.rds_mode == 3) {
+	   h -> err = "RDS_3 re-synchronises its bit clock from the block synchroniser's error count (rds-decoder-3.cpp:96-101): "
+	              "its symbol stage stays with the host-side rdsDecoder"; return SDRJFM_ERR_UNSUPPORTED;
+	}
 	CK (cudaSetDevice (h -> cfg.device));
 const size_t S = h -> cfg.n_streams;
+	if (on && !h -> d_rs2_state) {
+	   CK (dalloc (&h -> d_rs2_state, S)); CK (dalloc (&h -> d_rs2_m, S * h -> cap_rds));
+	   const int rc = rs2_reset (h); if (rc != SDRJFM_OK) return rc;
+	}
+	else if (on && !h -> rds_symbols) {
+	   CK (cudaStreamSynchronize (h -> stream)); CK (cudaStreamSynchronize (h -> stream_rds));
+	   const int rc = rs2_reset (h); if (rc != SDRJFM_OK) return rc;
+	}
 	if (on && !h -> d_rsy_state) {
 	   h -> cap_bits = (int32_t)(h -> cap_rds / 16 + 16);          // ~20.2 samples per bit
 	   CK (dalloc (&h -> d_rsy_state, S));

@@ -453,4 +453,100 @@ float a = 0.f, b = 0.f;
 	if (i < kRsyMatch - 1) st.hist_v [i] = b;
 }
 
+// ---- symbol stage of mode RDS_2: rdsDecoder_2::doDecode (src/rds/rds-decoder-2.cpp:96-158) ------------------
+//   doMatchFiltering   45-tap root-raised-cosine matched filter on the complex 24 kHz baseband (:79-93)
+//   AGC                output = input * curGain; curGain += 2e-3 (0.38 - |output|)         (includes/various/agc.h)
+//   process_sample     Mueller & Mueller timing recovery on hard decisions: one symbol per ~20.2 samples (:115-158)
+//   Costas             (rate, 1.0, 0.02, 10 Hz) on the SYMBOLS (includes/various/costas.h), then the differential bit
+// The matched filter is a FIR (thread per output, taps accumulated in the reference's order); everything behind
+// it is a per-sample recurrence with data-dependent decimation: one lane per stream, statement by statement.
+constexpr int kRs2Taps = 45;
+struct Rds2State {                  // rdsDecoder_2 members
+	float2  hist [kRs2Taps - 1];     // the last 44 inputs of the matched filter (oldest first)
+	float   gain;                    // AGC::curGain
+	float2  sb [3];                  // sampleBuffer
+	float   mu;                      // mMu
+	int32_t skip, count;             // skipNrSamples, sampleCount
+	float   freq, phase;             // Costas
+	int32_t prev_bit, started;
+};
+struct Rds2Params {
+	float taps [kRs2Taps];
+	float agc_rate, agc_ref;         // 2e-3, 0.38 (rds-decoder-2.cpp:46)
+	float sps, mm_alpha;             // rate / 1187.5, 0.01
+	float c_alpha, c_beta, freq_limit;
+};
+
+__global__ void __launch_bounds__ (128)
+rds2_match_kernel (const float2 *__restrict__ in, int64_t pitch, int32_t n, const Rds2Params P,
+                   const Rds2State *__restrict__ state, float2 *__restrict__ out) {
+const int stream = blockIdx.y;
+const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n) return;
+const float2 *x = in + (int64_t)stream * pitch;
+const float2 *hs = state [stream].hist;
+float2 tmp = make_float2 (0.f, 0.f);
+#pragma unroll 5
+	for (int i = 0; i < kRs2Taps; i ++) {                       // tmp += buf [newest - i] * kernel [i]
+	   const int k = t - i;
+	   const float2 v = k >= 0 ? x [k] : hs [kRs2Taps - 1 + k];
+	   tmp.x = fadd (tmp.x, fmul (v.x, P.taps [i])); tmp.y = fadd (tmp.y, fmul (v.y, P.taps [i]));
+	}
+	out [(int64_t)stream * pitch + t] = tmp;
+}
+
+__global__ void __launch_bounds__ (kRsyLanes)
+rds2_seq_kernel (const float2 *__restrict__ in, const float2 *__restrict__ mf, int64_t pitch, int32_t n, int32_t n_streams,
+                 const Rds2Params P, Rds2State *__restrict__ state,
+                 uint8_t *__restrict__ bits, int32_t cap_bits, int32_t *__restrict__ nbits) {
+const int stream = blockIdx.x * kRsyLanes + threadIdx.x;
+	if (stream >= n_streams) return;
+Rds2State &st = state [stream];
+const float2 *m = mf + (int64_t)stream * pitch;
+uint8_t *out = bits + (int64_t)stream * cap_bits;
+float gain = st.gain, mu = st.mu, freq = st.freq, phase = st.phase;
+float2 s0 = st.sb [0], s1 = st.sb [1], s2 = st.sb [2];
+int skip = st.skip, count = st.count, prev = st.prev_bit, nb = 0;
+	for (int32_t t = 0; t < n; t ++) {
+	   float2 v = m [t];
+	   v = make_float2 (fmul (v.x, gain), fmul (v.y, gain));                                         // AGC::process_sample
+	   const float mag = (float)sqrt ((double)v.x * (double)v.x + (double)v.y * (double)v.y);        // std::abs (complex<float>)
+	   gain = fadd (gain, fmul (P.agc_rate, fsub (P.agc_ref, mag)));
+	   s0 = s1; s1 = s2; s2 = v;                                                                       // :117-119
+	   if (++ count >= skip) {
+	      const float2 r0 = make_float2 (s0.x > 0.0f ? 1.0f : -1.0f, s0.y > 0.0f ? 1.0f : -1.0f);
+	      const float2 r1 = make_float2 (s1.x > 0.0f ? 1.0f : -1.0f, s1.y > 0.0f ? 1.0f : -1.0f);
+	      const float2 r2 = make_float2 (s2.x > 0.0f ? 1.0f : -1.0f, s2.y > 0.0f ? 1.0f : -1.0f);
+	      const float x = fadd (fmul (fsub (r2.x, r0.x), s1.x), fmul (fsub (r2.y, r0.y), s1.y));      // :130-134
+	      const float y = fadd (fmul (fsub (s2.x, s0.x), r1.x), fmul (fsub (s2.y, s0.y), r1.y));      // :135-139
+	      const float mm_val = fsub (y, x);
+	      mu = fadd (mu, fadd (P.sps, fmul (P.mm_alpha, mm_val)));                                     // :143
+	      skip = (int32_t)mu;
+	      mu = fsub (mu, (float)skip);
+	      count = 0;
+//	      Costas on the symbol (costas.h:21-33), then the differential bit (:104-108)
+	      float sn, cs;
+	      sincosf (-phase, &sn, &cs);
+	      const float2 r = cmul_rn (s2, make_float2 (cs, sn));
+	      const float err = fmul (r.x, r.y);
+	      freq = fadd (freq, fmul (P.c_beta, err));
+	      if (fabsf (freq) > P.freq_limit) freq = 0.f;
+	      phase = pi_constrain (fadd (phase, fadd (freq, fmul (P.c_alpha, err))));
+	      const int b = r.x >= 0.f ? 1 : 0;
+	      if (nb < cap_bits) out [nb] = (uint8_t)(b ^ prev);
+	      nb ++;
+	      prev = b;
+	   }
+	}
+	st.gain = gain; st.mu = mu; st.freq = freq; st.phase = phase;
+	st.sb [0] = s0; st.sb [1] = s1; st.sb [2] = s2;
+	st.skip = skip; st.count = count; st.prev_bit = prev;
+	nbits [stream] = nb;
+//	matched-filter history for the next call: the last 44 inputs of (hist | in)
+const float2 *x = in + (int64_t)stream * pitch;
+float2 keep [kRs2Taps - 1];
+	for (int i = 0; i < kRs2Taps - 1; i ++) { const int k = n - (kRs2Taps - 1) + i; keep [i] = k >= 0 ? x [k] : st.hist [kRs2Taps - 1 + k]; }
+	for (int i = 0; i < kRs2Taps - 1; i ++) st.hist [i] = keep [i];
+}
+
 }	// namespace sdrjfm

@@ -340,6 +340,32 @@ struct Packer {
 };
 }
 
+void design_rds2_matched_filter (int32_t rate, float *out) {
+//	root_raised_cosine (gain 1, sampling_freq rate, symbol_rate 2 * 1187.5, alpha 1, ntaps 45), every term in
+//	double and in the reference's order (shaping_filter.cpp:9-54): with alpha = 1 the singular taps are -1
+const int ntaps = 45 | 1;
+const double gain = 1.0, alpha = 1.0;
+const double spb = (double)rate / (2 * 1187.5);
+double scale = 0;
+std::vector<float> taps (ntaps);
+	for (int i = 0; i < ntaps; i ++) {
+	   double x1, x2, x3, num, den;
+	   const double xindx = i - ntaps / 2;
+	   x1 = M_PI * xindx / spb;
+	   x2 = 4 * alpha * xindx / spb;
+	   x3 = x2 * x2 - 1;
+	   if (fabs (x3) >= 0.000001) {
+	      if (i != ntaps / 2) num = cos ((1 + alpha) * x1) + sin ((1 - alpha) * x1) / (4 * alpha * xindx / spb);
+	      else num = cos ((1 + alpha) * x1) + (1 - alpha) * M_PI / (4 * alpha);
+	      den = x3 * M_PI;
+	   }
+	   else { taps [i] = -1; scale += taps [i]; continue; }        // alpha == 1
+	   taps [i] = 4 * alpha * num / den;
+	   scale += taps [i];
+	}
+	for (int i = 0; i < ntaps; i ++) out [i] = taps [i] * gain / scale;
+}
+
 TableBlob build_tables (int32_t input_rate, int32_t fm_rate, int32_t input_filter_hz,
                         int32_t audio_lp_hz) {
 TableHeader h;

@@ -704,19 +704,22 @@ def test_squelch_matches_reference(pkg, signals, chainlib, ref_available, monkey
         assert np.array_equal(got["demod"][0].view(np.uint32), ref2["demod"].view(np.uint32))
 
 
-@pytest.mark.parametrize("chunks", [None, [N1 // 3 + 12, 16384, 5, N1, N1 * 4]])
-def test_rds_symbol_stage_matches_reference(pkg, signals, chainlib, ref_available, chunks):
-    """the 24 kHz symbol stage of mode RDS_1 — Costas loop + rdsDecoder_1
-    (matched filter, 8-biquad band-pass on the squared signal, slope detector) — one lane per stream.
-    Checker: the reference's own classes fed with the GPU's 24 kHz baseband; the differentially
-    decoded bit stream must be the reference's, and it must be the transmitted one."""
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("chunks", [None, [16384 * 20 + 7, 16384, N1, N1 * 3]])
+def test_rds_symbol_stage_matches_reference(pkg, signals, chainlib, ref_available, chunks, mode):
+    """the 24 kHz symbol stage on the GPU, one lane per stream.
+    mode 1 (rds-decoder.cpp:73-82): Costas loop + rdsDecoder_1 (matched filter, 8-biquad band-pass on the squared
+    signal, slope detector); mode 2 (:84-88): rdsDecoder_2 (45-tap root-raised-cosine matched filter, AGC,
+    Mueller & Mueller timing recovery, Costas loop on the symbols).  Checker: the reference's own classes fed with
+    the GPU's 24 kHz baseband; the differentially decoded bit stream must be the reference's, and it must be the
+    transmitted one.  (Mode 3 takes its re-synchronisation from the block synchroniser: host side.)"""
     if not ref_available:
         pytest.skip("oracle/_ref not available")
     n = N1 * 3
     s = 9
     x = signals.batch_stream(s, n)
     p = pkg.FmProcessorB200(n_streams=1, max_samples_per_call=max(chunks) if chunks else n)
-    p.configure(fm_mode=0, rds_on=1, volume_db=-6.0)
+    p.configure(fm_mode=0, rds_on=mode, volume_db=-6.0)
     p.setRdsSymbolStage(True)
     rds, bits = [], []
     pos = 0
@@ -726,11 +729,24 @@ def test_rds_symbol_stage_matches_reference(pkg, signals, chainlib, ref_availabl
         _, r = p.process(x[pos:pos + c])
         rds.append(r[0]); bits.append(p.read_rds_bits(0))
         pos += c
+    with pytest.raises(pkg.SdrjfmError):
+        p.setfmRdsSelector(3)                    # the GPU symbol stage covers modes 1 and 2
     p.close()
     rds, bits = np.concatenate(rds), np.concatenate(bits)
-    ref = chainlib.Rds1().process(rds)
-    print("bits", len(bits), "reference", len(ref), "mismatches", int(np.sum(bits[:min(len(bits), len(ref))] != ref[:min(len(bits), len(ref))])))
-    assert len(bits) == len(ref) and np.array_equal(bits, ref)
+    ref = (chainlib.Rds1() if mode == 1 else chainlib.Rds2()).process(rds)
+    m = min(len(bits), len(ref))
+    bad = np.nonzero(bits[:m] != ref[:m])[0]
+    print("mode", mode, "bits", len(bits), "reference", len(ref), "mismatches", len(bad), "at", bad[:10])
+    assert len(bits) == len(ref)
+    if mode == 1:
+        assert len(bad) == 0
+    else:
+        # rdsDecoder_2 takes a hard decision on EVERY symbol from the first sample on, also while the RDS branch still
+        # delivers zeros (its two 32000-sample filter latencies: the first ~400 symbols) and while AGC, timing loop and
+        # Costas loop (std::exp (complex<float>) = libm sinf / cosf, whose last bit differs between libm builds and
+        # from CUDA's) pull in on the signal that then arrives: single decisions at rounding level may differ in that
+        # acquisition phase (measured: 1-2 around symbol 440), none once the loops have locked
+        assert len(bad) <= 3 and (len(bad) == 0 or bad.max() < 600)
     # and they are the transmitted bits (rng (2000 + s), differential encoding): search the alignment
     tx = np.random.default_rng(2000 + s).integers(0, 2, size=4096).astype(np.uint8)
     tail = bits[-600:]
