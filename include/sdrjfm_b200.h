@@ -274,6 +274,11 @@ int  sdrjfm_restart_pss_analyzer (sdrjfm_handle *h);               /* restartPss
  * out (if cap suffices) and returns its size in bytes, or a negative status.             */
 int64_t sdrjfm_design_tables (int32_t input_rate, int32_t fm_rate, int32_t input_filter_hz,
                               int32_t audio_lp_hz, void *out, int64_t cap);
+/* host-only designers of the small tables outside the blob (no device needed): which = 0: the RDS_2 matched filter
+ * (45 taps at rate a; rds-decoder-2.cpp:67-71); 1: the test-tone burst at working rate a (out [0] = samples of a
+ * cycle before the burst, then the burst; fm-processor.cpp:800-823); 2: the second converter a -> b (out [0] = L,
+ * out [1] = M, then 32 L taps).  Returns the number of floats written or a negative status.                */
+int64_t sdrjfm_design_aux (int32_t which, int32_t a, int32_t b, float *out, int64_t cap);
 int64_t sdrjfm_tables_nbytes (const sdrjfm_handle *h);
 int  sdrjfm_tables_export (const sdrjfm_handle *h, void *out, int64_t cap);
 int  sdrjfm_tables_import (sdrjfm_handle *h, const void *blob, int64_t nbytes);

@@ -141,6 +141,8 @@ def lib():
         L.sdrjfm_restart_pss_analyzer.argtypes = [vp]
         L.sdrjfm_design_tables.restype = i64
         L.sdrjfm_design_tables.argtypes = [i32, i32, i32, i32, vp, i64]
+        L.sdrjfm_design_aux.restype = i64
+        L.sdrjfm_design_aux.argtypes = [i32, i32, i32, vp, i64]
         L.sdrjfm_tables_nbytes.restype = i64
         L.sdrjfm_tables_nbytes.argtypes = [vp]
         L.sdrjfm_tables_export.argtypes = [vp, vp, i64]
@@ -236,6 +238,15 @@ def design_tables(input_rate=2304000, fm_rate=192000, input_filter_hz=0, audio_l
     buf = (C.c_uint8 * n)()
     L.sdrjfm_design_tables(input_rate, fm_rate, input_filter_hz, audio_lp_hz, buf, n)
     return Tables(buf)
+
+
+def design_aux(which, a, b=0, cap=70000):
+    """host-only designers outside the blob: 0 RDS_2 matched filter, 1 test-tone burst, 2 second converter."""
+    out = np.zeros(cap, np.float32)
+    n = lib().sdrjfm_design_aux(which, a, b, out.ctypes.data, cap)
+    if n < 0:
+        raise SdrjfmError(n, "design_aux")
+    return out[:n].copy()
 
 
 # ------------------------------------------------------------------------------------------

@@ -531,6 +531,29 @@ TableBlob b = build_tables (input_rate, fm_rate, input_filter_hz, audio_lp_hz);
 	if (out && cap >= (int64_t)b.bytes.size ()) memcpy (out, b.bytes.data (), b.bytes.size ());
 	return (int64_t)b.bytes.size ();
 }
+// host-only designers of the small tables that are not part of the blob (no device needed; used by the CPU tests)
+int64_t sdrjfm_design_aux (int32_t which, int32_t a, int32_t b, float *out, int64_t cap) {
+	if (!out) return SDRJFM_ERR_ARG;
+	if (which == 0) {                                     // RDS_2 matched filter at rate a
+	   if (cap < kRs2Taps) return SDRJFM_ERR_CAPACITY;
+	   design_rds2_matched_filter (a, out); return kRs2Taps;
+	}
+	if (which == 1) {                                     // test-tone burst at working rate a; out [0] = samples before the burst
+	   std::vector<float> t; int32_t arm = 0;
+	   tone_design (a, arm, t);
+	   if (cap < (int64_t)t.size () + 1) return SDRJFM_ERR_CAPACITY;
+	   out [0] = (float)arm; memcpy (out + 1, t.data (), t.size () * sizeof (float));
+	   return (int64_t)t.size () + 1;
+	}
+	if (which == 2) {                                     // second converter a -> b: out [0] = L, out [1] = M, then L * 32 taps
+	   std::vector<float> t; int L = 0, M = 0;
+	   if (!convert_design (a, b, L, M, t)) return SDRJFM_ERR_UNSUPPORTED;
+	   if (cap < (int64_t)t.size () + 2) return SDRJFM_ERR_CAPACITY;
+	   out [0] = (float)L; out [1] = (float)M; memcpy (out + 2, t.data (), t.size () * sizeof (float));
+	   return (int64_t)t.size () + 2;
+	}
+	return SDRJFM_ERR_ARG;
+}
 int64_t sdrjfm_tables_nbytes (const sdrjfm_handle *h) { return h ? lane_tables_nbytes (h -> lanes [0]) : SDRJFM_ERR_ARG; }
 int sdrjfm_tables_export (const sdrjfm_handle *h, void *out, int64_t cap) {
 	return h ? lane_tables_export (h -> lanes [0], out, cap) : SDRJFM_ERR_ARG;

@@ -133,3 +133,42 @@ def test_rds_symbol_stage_tables_match_reference(pkg, chainlib, ref_available):
     match, lp, bp = pkg.design_tables().rds_symbol
     for mine, which in ((match, 0), (lp, 1), (bp, 2)):
         assert _same(r.dump(which), np.ascontiguousarray(mine))
+
+
+def test_rds2_matched_filter_is_bit_identical(pkg, chainlib, ref_available):
+    """the 45-tap root-raised-cosine matched filter of rdsDecoder_2 (rds-decoder-2.cpp:67-71, shaping_filter.cpp:4-56)
+    restated on the host must be the reference's bit for bit."""
+    if not ref_available:
+        pytest.skip("oracle/_ref not available")
+    mine = pkg.design_aux(0, 24000)
+    ref = chainlib.Rds2(24000).matched_filter()
+    assert len(mine) == len(ref) == 45
+    assert np.array_equal(mine.view(np.uint32), ref.view(np.uint32))
+
+
+def test_test_tone_table_follows_the_reference_state_machine(pkg, chainlib, ref_available):
+    """insertTestTone (fm-processor.cpp:800-823) restated in the checker: fed with zeros, the burst it inserts must be
+    the table the library indexes by cycle position, and it must start where the table says."""
+    if not ref_available:
+        pytest.skip("oracle/_ref not available")
+    t = pkg.design_aux(1, 48000)
+    arm, burst = int(t[0]), t[1:]
+    assert arm == 96001 and len(burst) == 1200
+    r = chainlib.RefPost(48000)
+    r.set(1, 0)
+    out, _ = r.process(np.zeros(2 * (arm + len(burst)) + 10, np.complex64))
+    for cyc in (0, 1):
+        a = cyc * (arm + len(burst))
+        assert not out[a:a + arm].any()
+        seg = out[a + arm:a + arm + len(burst)]
+        assert np.array_equal(seg.real.view(np.uint32), (np.float32(0.9) * burst).view(np.uint32))
+        assert np.array_equal(seg.real, seg.imag)
+
+
+def test_second_converter_design(pkg):
+    """rational L / M, unit DC gain per polyphase branch, for the rates main.cpp / the ini file can ask for"""
+    for rate, L, M in ((192000, 4, 1), (44100, 147, 160), (96000, 2, 1), (32000, 2, 3)):
+        t = pkg.design_aux(2, 48000, rate)
+        assert (int(t[0]), int(t[1])) == (L, M)
+        h = t[2:].reshape(32, L).astype(np.float64)          # h [j * L + p]
+        assert np.allclose(h.sum(axis=0), 1.0, atol=1e-6)
