@@ -6,7 +6,4 @@ python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err; ech
 python bench.py --impl reference --steps 2 > gpurun_out/final_bench_ref.json 2>> gpurun_out/final_bench.err
 python bench.py --no-cpu --no-e2e --no-sweep --front-end-sweep --steps 5 > gpurun_out/final_sweep.json 2>> gpurun_out/final_bench.err
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"sdrjfm" --csv --log-file gpurun_out/r2_launches.csv python tools/prof_step.py --steps 2 --warmup 1 > gpurun_out/final_ncu.log 2>&1
-ncu --set full --import-source on --clock-control none -k regex:frontend_tma_kernel --launch-skip 2 -c 1 -o gpurun_out/r2_k1t python tools/prof_frontend.py > gpurun_out/final_ncu_k1t.log 2>&1
-ncu --set full --import-source on --clock-control none -k regex:frontend_tmab_kernel --launch-skip 2 -c 1 -o gpurun_out/r2_k1tb_u8 python tools/prof_frontend.py --format u8 > gpurun_out/final_ncu_k1tb.log 2>&1
-ncu --set full --import-source on --clock-control none -k regex:"pilot_kernel|stereo_kernel|rds_block_kernel|discriminator_kernel" --launch-skip 4 -c 4 -o gpurun_out/r2_chain python tools/prof_step.py --lanes 1 --streams 64 --steps 1 --warmup 1 > gpurun_out/final_ncu_chain.log 2>&1
 tail -3 gpurun_out/final_tests.log; cat gpurun_out/final_smoke.log | tail -2; cut -c1-400 gpurun_out/final_bench.json
