@@ -47,10 +47,12 @@ typedef struct sdrjfm_handle sdrjfm_handle;
 /* Constructor arguments of fmProcessor (src/fm/fm-processor.cpp:48-63) that matter to
  * the arithmetic, plus the batch shape.  Zero-initialise, then fill.                    */
 typedef struct sdrjfm_config {
-    int32_t input_rate;            /* inputRate, 2304000 (includes/fm-constants.h:35); also
-                                      2400000 / 6000000 / 10000000 with the reference's own
-                                      integer-decimation arithmetic (fm-processor.cpp:36,68-75):
-                                      stage 1 /6, stage 2 /(inputRate/6/fmRate) = /12, /30, /48  */
+    int32_t input_rate;            /* inputRate, 2304000 (includes/fm-constants.h:35); any rate from
+                                      1152000 to 12670000 with the reference's own integer-decimation
+                                      arithmetic (fm-processor.cpp:36,68-75): stage 1 /6, stage 2
+                                      /(inputRate/6/fmRate), i.e. /6 .. /60.  /12, /30, /48 (2.304 / 2.4,
+                                      6, 10 MS/s) have the tuned HBM-bound kernels; every other rate runs
+                                      the reference-order front end (front_end_mode 2 semantics)          */
     int32_t fm_rate;               /* fmRate, 192000 (radio.cpp:68)                      */
     int32_t working_rate;          /* workingRate, 48000 (radio.cpp:233)                 */
     int32_t audio_rate;            /* audioRate, 48000 (main.cpp:42); 192000 with -m (main.cpp:57-65), or the ini

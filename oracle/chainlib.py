@@ -127,7 +127,9 @@ class Chain:
         """iq: complex64[n]. Returns dict tap -> ndarray (fm-rate length, rds24 shorter)."""
         iq = np.ascontiguousarray(iq, dtype=np.complex64)
         n = iq.shape[0]
-        return self._run(self._process, iq, n, n // 12 + 2, taps)
+        irate = self.cfg.input_rate // 6                      # fm-processor.cpp:36,68-75
+        dec = max(1, (self.cfg.input_rate // irate) * (irate // self.cfg.fm_rate)) if self.cfg.input_rate > self.cfg.fm_rate else 1
+        return self._run(self._process, iq, n, n // min(dec, 12) + 2, taps)
 
     def process_fm(self, z, taps=TAPS):
         """for a chain created with input_rate == fm_rate (the reference's decimator bypass,

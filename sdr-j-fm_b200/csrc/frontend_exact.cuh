@@ -34,7 +34,8 @@ constexpr int kFxHist    = 32;                     // filter-input history kept 
 constexpr int kFxTaps1   = 25;                     // fmBand_1, fm-processor.cpp:68-71
 constexpr int kFxBatch   = 32;                     // samples per prefetch batch of the DC walker
 
-__constant__ float2 c_fx_taps [kFxTaps1 + 9 + 2];  // filterKernel of fmBand_1 [25], then of fmBand_2 [D2 + 1]
+constexpr int kFxMaxTaps2 = 11;                    // fmBand_2 has IRate / fmRate + 1 taps: rates up to 12.6 MS/s
+__constant__ float2 c_fx_taps [kFxTaps1 + kFxMaxTaps2];  // filterKernel of fmBand_1 [25], then of fmBand_2 [D2 + 1]
 
 // ---- RF DC removal, sample by sample ---------------------------------------------------------
 // x : [S][in_pitch] samples in format rf; xd : [S][out_pitch] float2 = x - clamp (RfDC) per component
@@ -290,6 +291,37 @@ float2 z = make_float2 (0.f, 0.f);
 	   z.x = fadd (z.x, p.x); z.y = fadd (z.y, p.y);
 	}
 	if (m0 + tid < M) Z [(int64_t)stream * out_pitch + m0 + tid] = z;
+}
+
+// ANY other rate the reference's constructor arithmetic accepts (fm-processor.cpp:36,68-75: stage 1 = 25 taps / 6,
+// stage 2 = D2 + 1 taps / D2 with D2 = (inputRate / 6) / fmRate = 1 .. 10; e.g. 2.048 MS/s -> / 6, 4 MS/s -> / 18,
+// 8 MS/s -> / 36): the same arithmetic with D2 at run time, one thread per fm-rate output reading its inputs
+// straight from global memory.  Not tuned — the three device rates have their own kernels — but exact.
+__global__ void __launch_bounds__ (kFxThreads)
+frontend_exact_generic_kernel (const void *__restrict__ src, int64_t in_pitch, RawFmt rf, int D2,
+                               const float2 *__restrict__ xhist, const LoParams lop,
+                               float2 *__restrict__ Z, int64_t out_pitch, int32_t M) {
+const int stream = blockIdx.y;
+const int64_t m = (int64_t)blockIdx.x * kFxThreads + threadIdx.x;
+	if (m >= M) return;
+const int D = 6 * D2;
+const void *xs = reinterpret_cast<const char *>(src) + (int64_t)stream * in_pitch * fmt_bytes (rf.fmt);
+const float2 *hs = xhist + (int64_t)stream * kFxHist;
+float2 z = make_float2 (0.f, 0.f);
+	for (int i2 = 0; i2 <= D2; i2 ++) {                 // stage 2, newest stage-1 output first
+	   const int64_t k6 = 6 * (D2 * m + D2 - 1 - i2) + 5;   // newest input of stage-1 output D2 m + D2 - 1 - i2
+	   float2 acc = make_float2 (0.f, 0.f);
+	   for (int i = 0; i < kFxTaps1; i ++) {
+	      const int64_t n = k6 - i;
+	      const float2 v = n < 0 ? hs [kFxHist + n] : fx_stage (lop, load_iq_rt (xs, n, rf), n);
+	      const float2 p = cmul_rn (v, c_fx_taps [i]);
+	      acc.x = fadd (acc.x, p.x); acc.y = fadd (acc.y, p.y);
+	   }
+	   const float2 p = cmul_rn (acc, c_fx_taps [kFxTaps1 + i2]);
+	   z.x = fadd (z.x, p.x); z.y = fadd (z.y, p.y);
+	}
+	(void)D;
+	Z [(int64_t)stream * out_pitch + m] = z;
 }
 
 // history for the next call: the last kFxHist filter inputs AFTER gain / oscillator

@@ -64,7 +64,13 @@ struct FeShape { int D, gpt, ng, ngw; };
 static const FeShape kFeShapes [] = { { 12, 4, 4, 25 }, { 30, 2, 2, 11 }, { 48, 1, 2, 7 },
                                       { kRsStageADecim, 8, 10, 0 } };     // last: stage A of the rational resampler
 constexpr int kShapeResample = 3;
+constexpr int kShapeGeneric = 4;          // any other decimation 6 * D2: reference-order front end only (frontend_exact.cuh)
 constexpr int kInputFilterDelay = kInputFftSize - kInputDegree;       // 65285 input samples
+
+static inline FeShape fe_shape (int shape, int decim) {
+	if (shape == kShapeGeneric) { const FeShape g = { decim, 1, 2, 0 }; return g; }
+	return kFeShapes [shape];
+}
 
 // Host image of everything this configuration keeps in __constant__ memory.  The constant banks
 // belong to the one loaded module, i.e. they are shared by every handle of the process: each lane
@@ -78,7 +84,7 @@ struct ConstImage {
 	float  poly [kPolyMaxTaps];
 	float2 pss [kPssTaps + 1];
 	float  alp [kAlpTaps];
-	float2 fx [kFxTaps1 + 9 + 2];
+	float2 fx [kFxTaps1 + kFxMaxTaps2];
 	uint64_t sig;
 };
 // signature of the image each DEVICE holds now (the constant banks are per device and context:
@@ -300,7 +306,7 @@ const int32_t lo_hz = h -> set.lo_hz;
 	memcpy (h -> ci.comp, comp, sizeof h -> ci.comp);
 	{  // K1x: the two filterKernels exactly as DecimatingFIR builds them (complex, fir-filters.cpp:327-347)
 	   memset (h -> ci.fx, 0, sizeof h -> ci.fx);
-	   if (th.ntaps1 == kFxTaps1 && th.ntaps2 <= 9) {
+	   if (th.ntaps1 == kFxTaps1 && th.ntaps2 <= kFxMaxTaps2) {
 	      memcpy (h -> ci.fx, h -> tables.payload () + th.off_fmband1, kFxTaps1 * sizeof (float2));
 	      memcpy (h -> ci.fx + kFxTaps1, h -> tables.payload () + th.off_fmband2, th.ntaps2 * sizeof (float2));
 	   }
@@ -325,7 +331,7 @@ const int32_t lo_hz = h -> set.lo_hz;
 
 //	K1g taps, narrow: c_poly[p][g] = C'[D g + D - 1 - p]
 const int D = h -> decim;
-const FeShape &fs = kFeShapes [h -> shape];
+const FeShape fs = fe_shape (h -> shape, h -> decim);
 float cpoly [kPolyMaxTaps];
 	memset (cpoly, 0, sizeof cpoly);
 	if (h -> resample) {      // stage A of the rational resampler: its own 49 taps, no DC folding
@@ -509,15 +515,17 @@ int rsL = 0, rsM = 0, rsP = 0;
 	   }
 	}
 	else if (cfg -> front_end_mode != 0 && cfg -> front_end_mode != 2) { g_create_error = "front_end_mode must be 0, 1 or 2"; return nullptr; }
-	else if (cfg -> fm_rate == 192000 && cfg -> input_rate >= 12 * cfg -> fm_rate) {
+	else if (cfg -> fm_rate == 192000 && cfg -> input_rate >= 6 * cfg -> fm_rate) {
 	   const int32_t irate = cfg -> input_rate / 6;
 	   decim = (cfg -> input_rate / irate) * (irate / cfg -> fm_rate);
 	   for (int i = 0; i < (int)(sizeof kFeShapes / sizeof kFeShapes [0]); i ++)
-	      if (kFeShapes [i].D == decim) shape = i;
+	      if (kFeShapes [i].D == decim && i != kShapeResample) shape = i;
+//	   every other rate whose constructor arithmetic is well defined (stage 2 = D2 + 1 taps / D2, D2 = 1 .. 10)
+	   if (shape < 0 && irate >= cfg -> fm_rate && cfg -> input_rate / irate == 6 && decim >= 6 && decim <= 60) shape = kShapeGeneric;
 	}
 	if (shape < 0) {
-	   g_create_error = "unsupported rates: fm_rate must be 192000 and input_rate must give a front-end "
-	                    "decimation of 12, 30 or 48 (2304000, 2400000, 6000000, 10000000, ...); the resampler "
+	   g_create_error = "unsupported rates: fm_rate must be 192000 and input_rate between 1152000 and 12670000 (front-end "
+	                    "decimation 6 .. 60; 12, 30 and 48 have tuned kernels); the resampler "
 	                    "mode needs 5 * 192000 / input_rate = L / M with L <= 16";
 	   *status = SDRJFM_ERR_UNSUPPORTED; return nullptr;
 	}
@@ -538,9 +546,9 @@ Lane *h = new Lane ();
 	h -> decim = decim; h -> shape = shape;
 	h -> resample = shape == kShapeResample;
 	h -> rsL = rsL; h -> rsM = rsM; h -> rsP = rsP; h -> rsHB = rsP - 1 + kRsHistPad;
-	h -> ngw = kFeShapes [shape].ngw;
+	h -> ngw = fe_shape (shape, decim).ngw;
 	h -> fw_delay = kInputFilterDelay / decim; h -> fw_shift = kInputFilterDelay % decim;
-	{  const FeShape &fs = kFeShapes [shape];
+	{  const FeShape fs = fe_shape (shape, decim);
 	   const int rows = fs.D * fs.gpt;
 	   h -> hist_len   = ((fs.ng - 1 + fs.gpt - 1) / fs.gpt) * rows;      // Poly<>::HaloIn
 	   h -> hist_len_w = std::max (((fs.ngw - 1 + fs.gpt - 1) / fs.gpt) * rows, fs.ngw * fs.D);
@@ -751,6 +759,7 @@ template <int D, int GPT, int NG> static cudaError_t poly_attr_one () {
 static cudaError_t poly_set_attr (int shape) {
 cudaError_t e;
 	switch (shape) {
+	   case kShapeGeneric: e = cudaSuccess; break;
 	   case 0:  e = poly_attr_one<12, 4, 4> (); if (e == cudaSuccess) e = poly_attr_one<12, 4, 25> (); break;
 	   case 1:  e = poly_attr_one<30, 2, 2> (); if (e == cudaSuccess) e = poly_attr_one<30, 2, 11> (); break;
 	   case 2:  e = poly_attr_one<48, 1, 2> (); if (e == cudaSuccess) e = poly_attr_one<48, 1, 7> (); break;
@@ -941,6 +950,7 @@ float2 *U = wide ? h -> d_Uw : h -> d_U, *Sb = wide ? h -> d_Sw : h -> d_S;
 
 // the reference-order front end is in force for this call?
 static bool exact_wanted (const Lane *h) {
+	if (h -> shape == kShapeGeneric) return true;       // rates without a composite kernel
 	if (h -> resample || h -> set.input_filter_hz > 0 || h -> shape > 2) return false;   // inputFilter: an FFT filter sits between the oscillator and fmBand_1
 	if (h -> cfg.front_end_mode == 2) return true;
 	return h -> auto_exact && (h -> set.decoder == 2 || h -> set.decoder == 5 || h -> set.lo_hz != 0);
@@ -1002,10 +1012,12 @@ const float2 *xh = h -> d_xhist [h -> xhist_sel];
 const bool plain = frf.fmt == kFmtCF32 && lp.tab == nullptr;
 #define FX_LAUNCH(D2) do { if (plain) frontend_exact_kernel<D2, true><<<grid, kFxThreads, Fx<D2>::SmemBytes, h -> stream>>> (fsrc, fpitch, frf, xh, lp, h -> d_U, h -> cap_fm, M); \
 	                      else frontend_exact_kernel<D2, false><<<grid, kFxThreads, Fx<D2>::SmemBytes, h -> stream>>> (fsrc, fpitch, frf, xh, lp, h -> d_U, h -> cap_fm, M); } while (0)
-	switch (h -> decim / 6) {
+	switch (h -> shape == kShapeGeneric ? 0 : h -> decim / 6) {
 	   case 2:  FX_LAUNCH (2); break;
 	   case 5:  FX_LAUNCH (5); break;
-	   default: FX_LAUNCH (8); break;
+	   case 8:  FX_LAUNCH (8); break;
+	   default: frontend_exact_generic_kernel<<<grid, kFxThreads, 0, h -> stream>>> (fsrc, fpitch, frf, h -> decim / 6, xh, lp,
+	                                                                             h -> d_U, h -> cap_fm, M); break;
 	}
 #undef FX_LAUNCH
 	h -> launches ++;
@@ -1723,6 +1735,7 @@ static int lane_set_bandwidth (Lane *h, int32_t hz) {
 	CK (cudaSetDevice (h -> cfg.device));
 	const int32_t v = hz > 0 ? hz : 0;
 	if (v > 0 && h -> resample) { h -> err = "inputFilter is not available in the resampler mode"; return SDRJFM_ERR_UNSUPPORTED; }
+	if (v > 0 && h -> shape == kShapeGeneric) { h -> err = "inputFilter is built for the decimations 12, 30 and 48 (2.304 / 2.4, 6, 10 MS/s)"; return SDRJFM_ERR_UNSUPPORTED; }
 	if (v == h -> set.input_filter_hz) return SDRJFM_OK;
 	h -> set.input_filter_hz = v;
 	int rc = rebuild_tables (h);

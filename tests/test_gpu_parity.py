@@ -1240,3 +1240,59 @@ def test_audio48_against_libsamplerate_if_present(pkg, signals):
         assert e < 0.05 * rms(ref[1000:m])
     except (OSError, AttributeError, RuntimeError) as ex:
         pytest.skip(f"audio48_parity: unpinned (libsamplerate probe failed: {ex})")
+
+
+def test_tables_import_rejects_foreign_blobs(pkg, signals):
+    """sdrjfm_tables_import takes a blob another rank broadcast: nothing in it is trusted.  A blob of other rates, of
+    another filter setting, a truncated one and one with a corrupted header are refused with SDRJFM_ERR_ARG and leave
+    the handle exactly as it was (same audio afterwards); the handle's own blob is accepted."""
+    n = N1 // 8
+    x = signals.stereo_pilot(n)
+    p = pkg.FmProcessorB200(n_streams=1, max_samples_per_call=n)
+    p.configure(fm_mode=0, volume_db=0.0)
+    good = p.tables_export()
+    a0, _ = p.process(x)
+    bad = [pkg.design_tables(input_filter_hz=165000).blob,           # another inputFilter setting than the handle's
+           pkg.design_tables(input_rate=6000000).blob,               # other rates
+           good[:len(good) - 64],                                    # truncated
+           good.copy(), good.copy()]
+    hdr = bad[3][:pkg._HDR_DTYPE.itemsize].view(pkg._HDR_DTYPE)
+    hdr["ncomp"] = 4000                                              # would overflow the composite buffer
+    hdr = bad[4][:pkg._HDR_DTYPE.itemsize].view(pkg._HDR_DTYPE)
+    hdr["off_atan"] = int(hdr["payload_floats"][0]) + 12345          # offset outside the payload
+    for i, b in enumerate(bad):
+        with pytest.raises(pkg.SdrjfmError) as e:
+            p.tables_import(b)
+        assert e.value.status == pkg.ERR_ARG, i
+    p.tables_import(good)
+    q = pkg.FmProcessorB200(n_streams=1, max_samples_per_call=n)
+    q.configure(fm_mode=0, volume_db=0.0)
+    b0, _ = q.process(x)
+    a1, _ = p.process(x)
+    b1, _ = q.process(x)
+    p.close(); q.close()
+    assert np.array_equal(a0, b0) and np.array_equal(a1, b1) and rms(a1) > 1e-3
+
+
+def test_unsupported_settings_fail_loudly_and_leave_the_handle_usable(pkg, signals):
+    """what the GPU path does not implement returns SDRJFM_ERR_UNSUPPORTED (never a silent CPU path), and an argument
+    error of a process call leaves the stream where it was."""
+    n = N1 // 8
+    x = signals.stereo_pilot(2 * n)
+    p = pkg.FmProcessorB200(n_streams=1, max_samples_per_call=n)
+    p.configure(fm_mode=0, volume_db=0.0)
+    for bad in (lambda: p.setDeemphasis(1000), lambda: pkg.FmProcessorB200(input_rate=1000000),
+                lambda: pkg.FmProcessorB200(working_rate=44100), lambda: pkg.FmProcessorB200(audio_rate=48001 * 7)):
+        with pytest.raises(pkg.SdrjfmError) as e:
+            bad()
+        assert e.value.status == pkg.ERR_UNSUPPORTED
+    a, _ = p.process(x[:n])
+    with pytest.raises(pkg.SdrjfmError) as e:
+        p.process(x)                                                  # more than max_samples_per_call
+    assert e.value.status == pkg.ERR_CAPACITY
+    b, _ = p.process(x[n:])
+    q = pkg.FmProcessorB200(n_streams=1, max_samples_per_call=n)
+    q.configure(fm_mode=0, volume_db=0.0)
+    a2, _ = q.process(x[:n]); b2, _ = q.process(x[n:])
+    p.close(); q.close()
+    assert np.array_equal(a, a2) and np.array_equal(b, b2)

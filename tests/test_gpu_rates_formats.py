@@ -339,3 +339,31 @@ def test_copies_of_a_stream_are_bit_identical_across_lanes(pkg, signals, name, r
                 assert np.array_equal(r[i].view(np.uint64), r[idx[0]].view(np.uint64)), (name, k, i)
                 assert np.array_equal(bits[i], bits[idx[0]]), (name, k, i)
         assert not np.array_equal(a[np.nonzero(order == 0)[0][0]], a[np.nonzero(order == 1)[0][0]])
+
+
+@pytest.mark.parametrize("fs,chunks", [
+    (2048000, None), (1920000, [16384, 5, 6 * 70001 + 3, 10 ** 7]), (3200000, None),
+    (4000000, [18 * 7 + 1, 16384 * 9, 10 ** 7]), (8000000, None), (12000000, [16384, 10 ** 8]),
+])
+def test_any_input_rate_of_the_reference_arithmetic(pkg, signals, checker, fs, chunks):
+    """The reference takes whatever rate the WAV file carries (devices/filereader/filehulp.cpp:62) through its
+    constructor arithmetic (fm-processor.cpp:36,68-75): stage 1 = 25 taps / 6, stage 2 = D2 + 1 taps / D2 with
+    D2 = (inputRate / 6) / 192000.  Rates without a tuned kernel (any D2 from 1 to 10 other than 2, 5, 8: e.g. the
+    colibri's 1.92 MS/s, rtlsdr's 2.048 MS/s, 4, 8, 12 MS/s) run the reference-order front end with D2 at run time:
+    fm-rate samples bit-identical to the reference's, exact output counts, audio within the north-star tolerance."""
+    D = pkg.front_end_decimation(fs)
+    n = D * 48000 + 7
+    x = signals.dc_offset(signals.stereo_pilot(n, fs=192000 * D, amp=0.6))
+    cfg = dict(fm_mode=0, volume_db=0.0)
+    ref = checker(input_rate=fs, **cfg).process(x)
+    got = run_gpu(pkg, x, fs, chunks=chunks, **cfg)
+    assert len(got["fm_z"]) == ref["n_fm"] == n // D
+    tuned = D in (12, 30, 48)
+    e = rms(got["fm_z"] - ref["fm_z"]) / rms(ref["fm_z"])
+    print(fs, "D", D, "fm_z rel", e, "demod", rms(got["demod"] - ref["demod"]), "audio192", rms(got["audio192"] - ref["audio192"]))
+    if tuned:
+        assert e < 2e-6
+    else:
+        assert np.array_equal(got["fm_z"].view(np.uint32), ref["fm_z"].view(np.uint32))
+    assert rms(got["demod"] - ref["demod"]) < 1e-5 and rms(got["audio192"] - ref["audio192"]) < 1e-5
+    assert np.array_equal(got["locked"], ref["locked"])
