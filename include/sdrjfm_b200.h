@@ -248,6 +248,16 @@ int  sdrjfm_set_lf_spectrum (sdrjfm_handle *h, int32_t spectrum_size, int32_t di
 int  sdrjfm_set_lf_plot_zoom (sdrjfm_handle *h, int32_t zoom);
 int64_t sdrjfm_read_lf_spectrum (sdrjfm_handle *h, int32_t stream, double *display, int64_t cap,
                                  int32_t *blocks_in_last_call);
+/* The HF scope's display spectrum on the GPU (optional): what hs_scope::addElement
+ * (src/scopes-qwt6/hs-scope.cpp:102-151, doAverage :175-203) computes from the RAW input the processor copies into
+ * hfBuffer (fm-processor.cpp:420): of every segment of inputRate / repeat_rate samples the first 4 display_size are
+ * windowed and transformed, mapped to display_size points and averaged with the weight 1 / (repeat_rate / 2).
+ * sdrjfm_set_hf_spectrum (displaySize, repeatRate as radio.cpp:232-249 passes them; display_size 0 = off);
+ * sdrjfm_read_hf_spectrum copies displayBuffer (display_size doubles, before the widget's dB scaling) of one stream
+ * and reports how many segments the last call completed.  Not available for the airspy native-rate format.      */
+int  sdrjfm_set_hf_spectrum (sdrjfm_handle *h, int32_t display_size, int32_t repeat_rate);
+int64_t sdrjfm_read_hf_spectrum (sdrjfm_handle *h, int32_t stream, double *display, int64_t cap,
+                                 int32_t *segments_in_last_call);
 int  sdrjfm_set_rds_symbol_stage (sdrjfm_handle *h, int32_t on);
 int64_t sdrjfm_read_rds_bits (sdrjfm_handle *h, int32_t stream, uint8_t *bits, int64_t cap);
 int  sdrjfm_set_squelch_mode (sdrjfm_handle *h, int32_t mode);     /* set_squelchMode: 0 OFF, 1 NSQ (noise), 2 LSQ (level) */

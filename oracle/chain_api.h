@@ -116,6 +116,10 @@ void    ref_rds2_destroy (void *h);
 int64_t ref_rds2_process (void *h, const float *rds24, int64_t n, uint8_t *bits, int64_t cap);
 int32_t ref_rds2_dump (void *h, float *out, int32_t cap);
 
+/* HF scope display spectrum (hs-scope.cpp:102-151, 175-203) restated around the reference's Fft_transform (ref_ only) */
+int64_t ref_hf_spectrum (const float *x, int64_t n, int32_t displaySize, int32_t sampleRate, int32_t freq,
+                         double *display_out, int64_t cap_blocks);
+
 /* `which` for *_dump_taps (complex entries unless noted) */
 enum {
     DUMP_FMBAND1 = 0,      /* 25 complex                      */

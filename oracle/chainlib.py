@@ -296,3 +296,16 @@ class Rds2:
         a = np.zeros(64, np.float32)
         n = self.lib.ref_rds2_dump(self.h, a.ctypes.data, 64)
         return a[:n].copy()
+
+
+def ref_hf_spectrum(x, display_size=1024, sample_rate=2304000, repeat_rate=10):
+    """hs_scope's displayBuffer after every completed segment of the raw IQ x (restated around the reference's
+    Fft_transform; ref_ only). Returns float64 [segments, display_size]."""
+    lib = C.CDLL(_PATHS["ref"])
+    lib.ref_hf_spectrum.restype = C.c_int64
+    lib.ref_hf_spectrum.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]
+    z = np.ascontiguousarray(x, dtype=np.complex64)
+    cap = len(z) // (sample_rate // repeat_rate) + 1
+    out = np.zeros((cap, display_size), np.float64)
+    n = lib.ref_hf_spectrum(z.ctypes.data, len(z), display_size, sample_rate, repeat_rate, out.ctypes.data, cap)
+    return out[:n].copy()

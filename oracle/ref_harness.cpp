@@ -711,3 +711,65 @@ int32_t n = (int32_t)d -> my_matchedFltKernelVec. size ();
 	return n;
 }
 }
+
+// ---- HF scope display spectrum: hs_scope::addElement + doAverage (src/scopes-qwt6/hs-scope.cpp:102-151, 175-203) ----
+// hs_scope is a Qwt widget class; its arithmetic is restated here around the reference's own Fft_transform.
+// x: raw IQ; one displayBuffer (displaySize doubles, before Scope::Display's dB scaling) per completed segment.
+extern "C" int64_t ref_hf_spectrum (const float *x, int64_t n, int32_t displaySize, int32_t sampleRate, int32_t freq,
+                                    double *display_out, int64_t cap_blocks) {
+const int32_t segmentSize = sampleRate / freq;                    // :41
+const int32_t spectrumSize = 4 * displaySize, spectrumFillpoint = spectrumSize;   // :45-46
+int32_t averageCount = 0;                                         // :44 (setAverager is commented out)
+std::vector<float> Window (spectrumFillpoint);
+std::vector<std::complex<float>> inputBuffer (spectrumFillpoint), ftBuffer (spectrumSize);
+std::vector<double> displayBuffer (displaySize, 0.0), averageBuffer (displaySize, 0.0);
+	for (int16_t i = 0; i < spectrumFillpoint; i ++)
+	   Window [i] = 0.43 - 0.5 * cos ((2.0 * M_PI * i) / spectrumFillpoint)
+	                     + 0.08 * cos ((4.0 * M_PI * i) / (spectrumFillpoint - 1));
+int32_t fillPointer = 0, sampleCounter = 0;
+int64_t nb = 0;
+	for (int64_t s = 0; s < n; s ++) {
+	   const std::complex<float> v (x [2 * s], x [2 * s + 1]);
+	   if (fillPointer < spectrumFillpoint)
+	      inputBuffer [fillPointer ++] = v;
+	   sampleCounter ++;
+	   if (sampleCounter < segmentSize)
+	      continue;
+	   fillPointer = 0;
+	   sampleCounter = 0;
+	   for (int i = 0; i < spectrumFillpoint; i ++) {
+	      std::complex<float> tmp = inputBuffer [i];
+	      if (std::isinf (abs (tmp)) || std::isnan (abs (tmp)))
+	         ftBuffer [i] = std::complex<float> (0, 0);
+	      else
+	         ftBuffer [i] = std::complex<float> (real (tmp) * Window [i], imag (tmp) * Window [i]);   // cmul
+	   }
+	   for (int i = spectrumFillpoint; i < spectrumSize; i ++)
+	      ftBuffer [i] = std::complex<float> (0, 0);
+	   Fft_transform (ftBuffer. data (), spectrumSize, false);
+	   int ratio = spectrumSize / displaySize;
+	   for (int i = 0; i < displaySize / 2; i ++) {
+	      float sum = 0;
+	      for (int j = 0; j < ratio; j ++)
+	         sum += abs (ftBuffer [i * ratio + j]);
+	      displayBuffer [displaySize / 2 + i] = sum / ratio;
+	      sum = 0;
+	      for (int j = 0; j < ratio; j ++)
+	         sum += abs (ftBuffer [spectrumSize / 2 + i * ratio + j]);
+	      displayBuffer [i] = sum / ratio;
+	   }
+	   if (averageCount > 0) { /* never: see above */ }
+	   else {
+	      for (int i = 0; i < displaySize; i ++) {
+	         if (displayBuffer [i] != displayBuffer [i])
+	            displayBuffer [i] = 0;
+	         averageBuffer [i] = ((double)(freq / 2 - 1)) / (freq / 2) * averageBuffer [i]
+	                             + 1.0f / (freq / 2) * displayBuffer [i];
+	         displayBuffer [i] = averageBuffer [i];
+	      }
+	   }
+	   if (nb < cap_blocks) memcpy (display_out + nb * displaySize, displayBuffer. data (), displaySize * sizeof (double));
+	   nb ++;
+	}
+	return nb;
+}

@@ -129,6 +129,10 @@ def lib():
         L.sdrjfm_set_lf_plot_zoom.argtypes = [vp, i32]
         L.sdrjfm_read_lf_spectrum.restype = i64
         L.sdrjfm_read_lf_spectrum.argtypes = [vp, i32, vp, i64, vp]
+        L.sdrjfm_set_hf_spectrum.restype = i32
+        L.sdrjfm_set_hf_spectrum.argtypes = [vp, i32, i32]
+        L.sdrjfm_read_hf_spectrum.restype = i64
+        L.sdrjfm_read_hf_spectrum.argtypes = [vp, i32, vp, i64, vp]
         L.sdrjfm_read_scan.restype = i64
         L.sdrjfm_read_scan.argtypes = [vp, i32, vp, i64]
         L.sdrjfm_read_rds_bits.restype = i64
@@ -344,6 +348,22 @@ class FmProcessorB200:
         a = np.zeros(self._display, np.float64)
         nb = C.c_int32(0)
         n = self.L.sdrjfm_read_lf_spectrum(self.h, stream, a.ctypes.data, a.size, C.byref(nb))
+        if n < 0:
+            raise SdrjfmError(n, self.L.sdrjfm_last_error(self.h).decode())
+        return a[:n].copy(), nb.value
+
+    def set_hf_spectrum(self, display_size=1024, repeat_rate=10):
+        """hs_scope (displaySize, ..., inputRate, repeatRate) on the GPU; display_size 0 switches it off."""
+        self._ck(self.L.sdrjfm_set_hf_spectrum(self.h, display_size, repeat_rate))
+        self._hf_display = display_size
+
+    def read_hf_spectrum(self, stream=0):
+        """(displayBuffer float64 [display_size], segments completed by the last call)."""
+        if not getattr(self, "_hf_display", 0):
+            raise SdrjfmError(ERR_ARG, "the HF spectrum is off: call set_hf_spectrum first")
+        a = np.zeros(self._hf_display, np.float64)
+        nb = C.c_int32(0)
+        n = self.L.sdrjfm_read_hf_spectrum(self.h, stream, a.ctypes.data, a.size, C.byref(nb))
         if n < 0:
             raise SdrjfmError(n, self.L.sdrjfm_last_error(self.h).decode())
         return a[:n].copy(), nb.value

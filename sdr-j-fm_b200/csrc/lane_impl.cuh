@@ -55,6 +55,7 @@ struct Lane;
 static int lane_destroy (Lane *h);
 static int lane_restart_pss_analyzer (Lane *h);
 static int lane_get_meta (Lane *h, sdrjfm_meta *meta);
+static int run_hf_spectrum (Lane *h, const void *d_iq, RawFmt rf, int64_t pitch, int64_t n_in);
 static cudaError_t poly_set_attr (int shape);
 static RawFmt make_rawfmt (const Lane *h, int32_t fmt, float scale);
 
@@ -186,6 +187,10 @@ struct Lane {
 	double  *d_spec_Y = nullptr, *d_spec_avg = nullptr, *d_spec_disp = nullptr;
 	int32_t  cap_specblk = 0, last_nspec = 0;
 	cudaEvent_t ev_sym = nullptr;           // Costas output of the call ready (RDS_DEMOD spectrum)
+	// HF scope display spectrum (hs_scope::addElement on the raw input); hf_N = 0: off
+	int32_t  hf_N = 0, hf_logN = 0, hf_display = 0, hf_seg = 0, hf_half_freq = 1, last_nhf = 0;
+	int64_t  hf_total = 0;                  // raw input samples seen since the HF spectrum was switched on
+	float2  *d_hf_blk = nullptr; float *d_hf_win = nullptr; double *d_hf_avg = nullptr, *d_hf_disp = nullptr;
 	// station scan (startScanning / stopScanning): 1024-sample blocks of fm-rate samples -> (signal, noise) dB
 	bool     scanning = false;
 	float2  *d_scan_carry [2] = { nullptr, nullptr }; int scan_sel = 0, scan_carry = 0;
@@ -704,7 +709,7 @@ void *ptrs [] = { h -> d_tables, h -> d_sin_quarter, h -> d_in, h -> d_hist [0],
 	              h -> d_spec_in, h -> d_spec_carry [0], h -> d_spec_carry [1], h -> d_spec_win,
 	              h -> d_spec_Y, h -> d_spec_avg, h -> d_spec_disp, h -> d_xd, h -> d_xhist [0], h -> d_xhist [1], h -> d_dcnow,
 	              h -> d_tone_tab, h -> d_peak_ring, h -> d_cv_taps, h -> d_cv_hist [0], h -> d_cv_hist [1],
-	              h -> d_rs2_state, h -> d_rs2_m };
+	              h -> d_rs2_state, h -> d_rs2_m, h -> d_hf_blk, h -> d_hf_win, h -> d_hf_avg, h -> d_hf_disp };
 	for (void *p : ptrs) if (p) cudaFree (p);
 	if (h -> stream_rds) { cudaStreamSynchronize (h -> stream_rds); cudaStreamDestroy (h -> stream_rds); }
 	if (h -> stream_k3) { cudaStreamSynchronize (h -> stream_k3); cudaStreamDestroy (h -> stream_k3); }
@@ -1110,6 +1115,32 @@ const int32_t nblk = std::min ((h -> spec_carry + n) / N, h -> cap_specblk);
 	h -> spec_sel ^= 1; h -> spec_carry = (h -> spec_carry + n) % N;
 	h -> last_nspec = nblk;
 	h -> launches += 2;
+	return SDRJFM_OK;
+}
+
+// HF scope display spectrum of the call's raw samples (spectrum.cuh): of every segment of hf_seg input samples the
+// first hf_N are gathered (across calls) and transformed when the segment is complete, as hs_scope::addElement does
+static int run_hf_spectrum (Lane *h, const void *d_iq, RawFmt rf, int64_t pitch, int64_t n_in) {
+const int S = h -> cfg.n_streams;
+const int64_t T0 = h -> hf_total, T1 = T0 + n_in;
+const int64_t seg = h -> hf_seg;
+int nb = 0;
+	for (int64_t k = T0 / seg; k * seg < T1; k ++) {
+	   const int64_t lo = std::max (T0, k * seg), hi = std::min (T1, k * seg + h -> hf_N);
+	   if (hi > lo) {
+	      hf_gather_kernel<<<dim3 ((unsigned)((hi - lo + 255) / 256), (unsigned)S), 256, 0, h -> stream>>> (
+	            d_iq, pitch, rf, lo - T0, (int32_t)(hi - lo), (int32_t)(lo - k * seg), h -> hf_N, h -> d_hf_blk);
+	      h -> launches ++;
+	   }
+	   if (T1 >= (k + 1) * seg) {                                           // sampleCounter reached segmentSize (:109-110)
+	      HfSpecParams P = { h -> hf_N, h -> hf_logN, h -> hf_display, h -> hf_half_freq };
+	      hf_spectrum_kernel<<<S, kSpecThreads, (size_t)h -> hf_N * sizeof (float2), h -> stream>>> (
+	            h -> d_hf_blk, h -> d_hf_win, P, h -> d_hf_avg, h -> d_hf_disp);
+	      h -> launches ++; nb ++;
+	   }
+	}
+	h -> hf_total = T1; h -> last_nhf = nb;
+	CK (cudaGetLastError ());
 	return SDRJFM_OK;
 }
 
@@ -1586,6 +1617,11 @@ static int lane_process_device (Lane *h, const void *d_iq, int32_t fmt, float sc
 	CK (cudaSetDevice (h -> cfg.device));
 //	every argument / format check comes BEFORE anything is staged or any state moves
 	if (fmt != kFmtAirspy && h -> air_pend) { h -> err = "sample format changed while samples were pending"; return SDRJFM_ERR_ARG; }
+	if (h -> hf_N && n_in > 0 && fmt != kFmtAirspy) {
+	   const int rc2 = run_hf_spectrum (h, d_iq, make_rawfmt (h, fmt, scale), in_pitch, n_in);
+	   if (rc2 != SDRJFM_OK) return rc2;
+	}
+	else h -> last_nhf = 0;
 const void *src; int64_t pitch, n_proc;
 int rc = fmt == kFmtAirspy ? stage_input_airspy (h, d_iq, n_in, in_pitch, &src, &pitch, &n_proc)
                            : stage_input (h, d_iq, fmt, n_in, in_pitch, cudaMemcpyDeviceToDevice, &src, &pitch, &n_proc);
@@ -1871,6 +1907,44 @@ std::vector<float> win ((size_t)N);
 	h -> spec_N = N; h -> spec_display = display; h -> spec_avg_count = average_count;
 	h -> spec_sel = 0; h -> spec_carry = 0; h -> spec_refresh = true; h -> last_nspec = 0;
 	return SDRJFM_OK;
+}
+// hs_scope (displaySize, rasterSize, SampleRate = inputRate, freq = repeatRate), radio.cpp:232-237; display_size 0: off
+static int lane_set_hf_spectrum (Lane *h, int32_t display, int32_t repeat_rate) {
+	if (!h) return SDRJFM_ERR_ARG;
+	CK (cudaSetDevice (h -> cfg.device));
+	CK (cudaStreamSynchronize (h -> stream));
+	for (void *p : { (void *)h -> d_hf_blk, (void *)h -> d_hf_win, (void *)h -> d_hf_avg, (void *)h -> d_hf_disp }) if (p) cudaFree (p);
+	h -> d_hf_blk = nullptr; h -> d_hf_win = nullptr; h -> d_hf_avg = h -> d_hf_disp = nullptr; h -> hf_N = 0;
+	if (display == 0) return SDRJFM_OK;
+	if (display < 16 || display > kSpecMaxN / 4 || (display & (display - 1)) || repeat_rate < 2 ||
+	    h -> cfg.input_rate / repeat_rate < 4 * display) {
+	   h -> err = "HF spectrum: display_size a power of two in 16..1024, repeat_rate >= 2, inputRate / repeat_rate >= 4 display_size";
+	   return SDRJFM_ERR_ARG;
+	}
+const size_t S = h -> cfg.n_streams;
+const int N = 4 * display;                                                  // spectrumSize = 4 * displaySize (:43)
+	CK (dalloc (&h -> d_hf_blk, S * N)); CK (dalloc (&h -> d_hf_win, (size_t)N));
+	CK (dalloc (&h -> d_hf_avg, S * display)); CK (dalloc (&h -> d_hf_disp, S * display));
+std::vector<float> win ((size_t)N);
+	for (int i = 0; i < N; i ++)                                                // hs-scope.cpp:66-68, evaluated in double
+	   win [i] = 0.43 - 0.5 * cos ((2.0 * M_PI * i) / N) + 0.08 * cos ((4.0 * M_PI * i) / (N - 1));
+	CK (cudaMemcpy (h -> d_hf_win, win.data (), (size_t)N * sizeof (float), cudaMemcpyHostToDevice));
+	h -> hf_logN = 0; while ((1 << h -> hf_logN) < N) h -> hf_logN ++;
+	h -> hf_display = display; h -> hf_seg = h -> cfg.input_rate / repeat_rate; h -> hf_half_freq = repeat_rate / 2;
+	h -> hf_total = 0; h -> last_nhf = 0;
+	h -> hf_N = N;
+	return SDRJFM_OK;
+}
+static int64_t lane_read_hf_spectrum (Lane *h, int32_t stream, double *out, int64_t cap, int32_t *blocks) {
+	if (!h || !out || stream < 0 || stream >= h -> cfg.n_streams) return SDRJFM_ERR_ARG;
+	if (!h -> hf_N) { h -> err = "the HF spectrum is off (sdrjfm_set_hf_spectrum)"; return SDRJFM_ERR_ARG; }
+	if (cap < h -> hf_display) return SDRJFM_ERR_CAPACITY;
+	CK (cudaSetDevice (h -> cfg.device));
+	CK (cudaMemcpyAsync (out, h -> d_hf_disp + (size_t)stream * h -> hf_display, h -> hf_display * sizeof (double),
+	                     cudaMemcpyDeviceToHost, h -> stream));
+	CK (cudaStreamSynchronize (h -> stream));
+	if (blocks) *blocks = h -> last_nhf;
+	return h -> hf_display;
 }
 // displayBuffer of one stream (display_size doubles) as the last process call left it
 static int64_t lane_read_lf_spectrum (Lane *h, int32_t stream, double *out, int64_t cap, int32_t *blocks) {

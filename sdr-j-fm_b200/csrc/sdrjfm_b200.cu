@@ -294,7 +294,7 @@ const int64_t slice = ((n_in / kSlices) / unit) * unit;          // multiple of 
 //	The per-call side outputs (RDS bits, scan blocks, scope stream) describe ONE chain call: they would
 //	be overwritten slice by slice, so calls that produce them are not cut.
 const Lane *l0 = h -> lanes [0];
-	if (!h -> cfg.keep_taps && l0 -> lf_plot < 0 && !l0 -> rds_symbols && !l0 -> scanning && slice >= (1 << 16)) {
+	if (!h -> cfg.keep_taps && l0 -> lf_plot < 0 && !l0 -> rds_symbols && !l0 -> scanning && l0 -> hf_N == 0 && slice >= (1 << 16)) {
 //	   output capacities are checked before the first slice moves any state: a call of n_in samples
 //	   yields at most n_in / decim / 4 + 1 audio and n_in / decim / 8 + 1 RDS samples per stream
 	   const int64_t max_fm = (n_in + l0 -> pend) / l0 -> decim + 1;
@@ -463,6 +463,19 @@ const int i = lane_of (h, stream);
 	if (i < 0) return SDRJFM_ERR_ARG;
 	HK (cudaStreamSynchronize (h -> stream));
 const int64_t n = lane_read_lf_spectrum (h -> lanes [i], stream - h -> first [i], display, cap, blocks);
+	if (n < 0) h -> err = h -> lanes [i] -> err;
+	return n;
+}
+int sdrjfm_set_hf_spectrum (sdrjfm_handle *h, int32_t display_size, int32_t repeat_rate) {
+	return for_lanes (h, [&](Lane *l) { return lane_set_hf_spectrum (l, display_size, repeat_rate); });
+}
+int64_t sdrjfm_read_hf_spectrum (sdrjfm_handle *h, int32_t stream, double *display, int64_t cap, int32_t *blocks) {
+	if (!h || !display) return SDRJFM_ERR_ARG;
+	LOCK_DEV (h);
+const int i = lane_of (h, stream);
+	if (i < 0) return SDRJFM_ERR_ARG;
+	HK (cudaStreamSynchronize (h -> stream));
+const int64_t n = lane_read_hf_spectrum (h -> lanes [i], stream - h -> first [i], display, cap, blocks);
 	if (n < 0) h -> err = h -> lanes [i] -> err;
 	return n;
 }

@@ -9,6 +9,7 @@
 //   lf_carry_kernel     the samples behind the last whole block wait for the next call
 #pragma once
 #include "common.cuh"
+#include "frontend_poly.cuh"
 
 namespace sdrjfm {
 
@@ -123,6 +124,68 @@ const int total = n_carry + n, keep = total % N;
 	for (int i = threadIdx.x; i < keep; i += blockDim.x) {
 	   const int64_t g = (int64_t)(total - keep + i) - n_carry;
 	   carry_new [(int64_t)stream * N + i] = g >= 0 ? z [(int64_t)stream * pitch + g] : carry [(int64_t)stream * N + n_carry + g];
+	}
+}
+
+// ---- HF scope display spectrum: hs_scope::addElement (src/scopes-qwt6/hs-scope.cpp:102-151, 175-203) -------------
+// The HF scope looks at the RAW input (hfBuffer, fm-processor.cpp:420): of every segment of segmentSize =
+// inputRate / repeatRate samples the first spectrumSize = 4 displaySize are windowed (:114-120) and transformed;
+// displayBuffer [display/2 + i] = mean of |F [4 i + j]|, displayBuffer [i] = mean of |F [N/2 + 4 i + j]| (:127-136),
+// then doAverage (:190-199: averageCount stays 0, so the running average has the weight 1 / (repeatRate / 2)).
+//   hf_gather_kernel    the part of the open segment's first N samples that this call delivers -> blk (converted)
+//   hf_spectrum_kernel  one CTA per stream: window, FFT in shared memory, map, average (in place)
+struct HfSpecParams { int32_t N, logN, display, half_freq; };
+
+__global__ void hf_gather_kernel (const void *__restrict__ src, int64_t pitch, RawFmt rf, int64_t first, int32_t count,
+                                  int32_t dst0, int32_t N, float2 *__restrict__ blk) {
+const int stream = blockIdx.y;
+const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count) return;
+const void *xs = reinterpret_cast<const char *>(src) + (int64_t)stream * pitch * fmt_bytes (rf.fmt);
+	blk [(int64_t)stream * N + dst0 + i] = load_iq_rt (xs, first + i, rf);
+}
+
+__global__ void __launch_bounds__ (kSpecThreads)
+hf_spectrum_kernel (const float2 *__restrict__ blk, const float *__restrict__ window, const HfSpecParams P,
+                    double *__restrict__ avg, double *__restrict__ disp) {
+extern __shared__ float2 sp_a [];
+const int tid = threadIdx.x, stream = blockIdx.x;
+const int N = P.N;
+const float2 *zs = blk + (int64_t)stream * N;
+	for (int i = tid; i < N; i += kSpecThreads) {
+	   float2 v = zs [i];
+	   const float m = (float)sqrt ((double)v.x * v.x + (double)v.y * v.y);
+	   if (isinf (m) || isnan (m)) v = make_float2 (0.f, 0.f);           // :115-118
+	   else { const float w = window [i]; v = make_float2 (fmul (v.x, w), fmul (v.y, w)); }
+	   sp_a [__brev ((unsigned)i) >> (32 - P.logN)] = v;
+	}
+	__syncthreads ();
+	for (int half = 1; half < N; half <<= 1) {
+	   for (int b = tid; b < N / 2; b += kSpecThreads) {
+	      const int pos = b & (half - 1);
+	      const int i0 = ((b - pos) << 1) + pos;
+	      float sn, cs2;
+	      sincospif (-(float)pos / (float)half, &sn, &cs2);
+	      const float2 u = sp_a [i0], v = sp_a [i0 + half];
+	      const float2 t = make_float2 (v.x * cs2 - v.y * sn, v.x * sn + v.y * cs2);
+	      sp_a [i0] = make_float2 (u.x + t.x, u.y + t.y);
+	      sp_a [i0 + half] = make_float2 (u.x - t.x, u.y - t.y);
+	   }
+	   __syncthreads ();
+	}
+const int ratio = N / P.display;
+const double beta = (double)(P.half_freq - 1) / P.half_freq;            // :194
+const float alpha = 1.0f / P.half_freq;                                 // :195
+	for (int o = tid; o < P.display; o += kSpecThreads) {
+	   const int hd = P.display / 2;
+	   const int base = o >= hd ? (o - hd) * ratio : N / 2 + o * ratio;
+	   float sum = 0.f;
+	   for (int j = 0; j < ratio; j ++) { const float2 v = sp_a [base + j]; sum = fadd (sum, (float)sqrt ((double)v.x * v.x + (double)v.y * v.y)); }
+	   double d = (double)fdiv (sum, (float)ratio);
+	   if (d != d) d = 0;                                                   // :191-192
+	   const double a = __dadd_rn (__dmul_rn (beta, avg [(int64_t)stream * P.display + o]), __dmul_rn ((double)alpha, d));
+	   avg [(int64_t)stream * P.display + o] = a;
+	   disp [(int64_t)stream * P.display + o] = a;
 	}
 }
 
