@@ -562,8 +562,9 @@ Lane *h = new Lane ();
 	   env = getenv ("SDRJFM_TMA_CTAS"); h -> tma_ctas = env && atoi (env) > 0 ? atoi (env) : 0;
 	   env = getenv ("SDRJFM_NO_AUTO_EXACT"); h -> auto_exact = !(env && env [0] == '1');
 	   env = getenv ("SDRJFM_SEQ_DC"); h -> seq_dc = env && env [0] == '1';
-//	   time slices of 6 pilot windows = 24576 fm samples (0.128 s): 16 PSS blocks, 12 audio tiles
-	   env = getenv ("SDRJFM_FM_SLICE"); h -> slice_fm = env ? atoi (env) : 6 * kPiWin;
+//	   time slices of 6 pilot windows = 24576 fm samples (0.128 s: 16 PSS blocks, 12 audio tiles); 3 windows when few
+//	   streams leave the SMs idle anyway (measured, 32 streams x 0.5 s: 1.60 / 1.48 / 1.61 ms at 2 / 3 / 6 windows)
+	   env = getenv ("SDRJFM_FM_SLICE"); h -> slice_fm = env ? atoi (env) : (cfg -> n_streams <= 64 ? 3 : 6) * kPiWin;
 	   if (h -> slice_fm % 4096) h -> slice_fm = 0; }
 	if (h -> cfg.working_rate <= 0) h -> cfg.working_rate = 48000;
 	if (h -> cfg.audio_rate <= 0) h -> cfg.audio_rate = h -> cfg.working_rate;

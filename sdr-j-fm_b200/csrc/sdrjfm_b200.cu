@@ -11,8 +11,8 @@
 #include <cstdlib>
 #include <mutex>
 
-// A handle with 4 lanes works on 11 CUDA streams (lane + RDS side stream each, the caller's stream, two
-// copy streams).  The driver maps streams onto 8 hardware queues by default, which makes independent
+// A handle works on up to 15 CUDA streams (per lane: its own, the RDS side stream, the pilot stream of the next
+// time slice; the caller's stream; two copy streams).  The driver maps streams onto 8 hardware queues by default, which makes independent
 // streams wait for each other; when this library is loaded before the process creates its CUDA context
 // (and the host did not choose a value itself) it asks for 32.  Measured: 4.36 -> 4.30 ms per bench step.
 // This writes one variable of the host process's environment at load time and never overrides a value
@@ -118,8 +118,10 @@ int dummy; if (!status) status = &dummy;
 	if (!cfg || cfg -> n_streams < 1 || cfg -> max_samples_per_call < 1) {
 	   g_create_error = "bad config"; return nullptr;
 	}
-//	lanes: groups of >= 32 streams, at most 4 (SDRJFM_LANES overrides)
-int nl = std::min (4, std::max (1, cfg -> n_streams / 32));
+//	lanes: with K3 of time slice j + 1 running beside K4-K6 of slice j inside every lane (lane_impl.cuh), two lanes
+//	are enough to keep a B200 busy from 128 streams on, and one below (measured, 256 streams x 0.5 s: 1 / 2 / 4 lanes
+//	4.28 / 4.28 / 4.38 ms; 32 streams: every extra lane only adds launches).  SDRJFM_LANES overrides.
+int nl = cfg -> n_streams >= 128 ? 2 : 1;
 	{ const char *env = getenv ("SDRJFM_LANES"); if (env && atoi (env) > 0) nl = std::min (atoi (env), cfg -> n_streams); }
 	if (cfg -> device < 0 || cfg -> device >= kMaxDevices) { g_create_error = "bad device ordinal"; return nullptr; }
 std::lock_guard<std::recursive_mutex> lock_ (g_dev_mutex [cfg -> device]);
