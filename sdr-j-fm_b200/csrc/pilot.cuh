@@ -37,26 +37,30 @@ namespace sdrjfm {
 // 512 threads x 8 samples: a 4096-sample window has about 410 segments, so most lanes walk one
 // segment per iteration; at 64 registers two CTAs share an SM (32 warps: the walk is a dependent
 // chain of ~9-cycle instructions, only thread-level parallelism hides it).
-constexpr int kPiThreads = 512;
+constexpr int kPiThreads = 512;                      // the throughput shape: 4096-sample windows, two CTAs per SM
+constexpr int kPiThreadsWide = 1024;                 // 8192-sample windows (SDRJFM_PILOT_WIDE=1): a pass covers twice the samples,
+                                                     // but needs about one pass more per window (up to 9 without a pilot) and
+                                                     // its 32-warp scans are slower: measured no faster for 32-128 streams, not used
 constexpr int kPiPer     = 8;                        // consecutive samples per thread
-constexpr int kPiWin     = kPiThreads * kPiPer;      // 4096 fm samples per window
-constexpr int kPiMaxSeg  = 896;                      // anchors per window (about 410 in practice)
+constexpr int kPiWin     = kPiThreads * kPiPer;      // 4096 fm samples per window (time slices are multiples of it)
 constexpr int kPiMaxIter = 24;
-constexpr int kPiWarps   = kPiThreads / 32;
 
-struct PilotSmem {
-	float   x [kPiWin];             // 5 * demod
-	float   est [kPiWin];           // phase BEFORE the step of sample n (the unknowns)
-	double  delta [kPiMaxSeg + 1];  // Newton correction per anchor
-	double  resid [kPiMaxSeg + 1];
-	float   G [kPiMaxSeg + 1];      // phase after the last step of segment c
-	float   der [kPiMaxSeg + 1];
-	int16_t anc [kPiMaxSeg + 2];    // first sample of segment c
-	double  warpA [kPiWarps], warpB [kPiWarps];
-	int     warpI [kPiWarps];
+template <int THREADS>
+struct PilotSmemT {
+	static constexpr int Win = THREADS * kPiPer, MaxSeg = Win * 7 / 32, Warps = THREADS / 32;    // ~0.1 anchors per sample in practice
+	float   x [Win];                // 5 * demod
+	float   est [Win];              // phase BEFORE the step of sample n (the unknowns)
+	double  delta [MaxSeg + 1];     // Newton correction per anchor
+	double  resid [MaxSeg + 1];
+	float   G [MaxSeg + 1];         // phase after the last step of segment c
+	float   der [MaxSeg + 1];
+	int16_t anc [MaxSeg + 2];       // first sample of segment c
+	double  warpA [Warps], warpB [Warps];
+	int     warpI [Warps];
 	int     nseg, overflow;
 	double  carry [4];
 };
+typedef PilotSmemT<kPiThreads> PilotSmem;
 constexpr size_t kPiLutBytes  = ((size_t)(kFmRate / 4 + 1) * sizeof (float) + 15) / 16 * 16;
 constexpr size_t kPiSmemBytes = kPiLutBytes + sizeof (PilotSmem);
 
@@ -142,8 +146,8 @@ float f = (float)v;
 	return f < 0.f ? 0.f : f;
 }
 
-template <bool LUT_SMEM>
-__global__ void __launch_bounds__ (kPiThreads, LUT_SMEM ? 1 : 2)
+template <bool LUT_SMEM, int THREADS = kPiThreads>
+__global__ void __launch_bounds__ (THREADS, (LUT_SMEM || THREADS > 512) ? 1 : 2)
 pilot_kernel (const float *__restrict__ res_raw, const float *__restrict__ zabs,
               int64_t pitch, int32_t M, const PilotParams P, const SinLut L,
               StreamState *__restrict__ state,
@@ -153,7 +157,8 @@ extern __shared__ __align__ (16) unsigned char smem_raw [];
 // LUT_SMEM: the quarter-wave sine table is staged in shared memory (one CTA per SM).  Otherwise it is
 // read through L1 (192 KB, read-only path), which leaves room for two CTAs per SM.
 const float *sq = LUT_SMEM ? reinterpret_cast<const float *>(smem_raw) : L.q;
-PilotSmem &S = *reinterpret_cast<PilotSmem *>(smem_raw + (LUT_SMEM ? kPiLutBytes : 0));
+constexpr int kPiThreads = THREADS, kPiWin = THREADS * kPiPer, kPiMaxSeg = PilotSmemT<THREADS>::MaxSeg, kPiWarps = THREADS / 32;
+PilotSmemT<THREADS> &S = *reinterpret_cast<PilotSmemT<THREADS> *>(smem_raw + (LUT_SMEM ? kPiLutBytes : 0));
 const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 const int stream = blockIdx.x;
 	if (LUT_SMEM) { float *w = reinterpret_cast<float *>(smem_raw); for (int i = tid; i <= kFmRate / 4; i += kPiThreads) w [i] = L.q [i]; }

@@ -5,5 +5,4 @@ python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/final_smoke.log 
 python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err; echo "bench rc=$?" >> gpurun_out/final_bench.err
 python bench.py --impl reference --steps 2 > gpurun_out/final_bench_ref.json 2>> gpurun_out/final_bench.err
 python bench.py --no-cpu --no-e2e --no-sweep --front-end-sweep --steps 5 > gpurun_out/final_sweep.json 2>> gpurun_out/final_bench.err
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"sdrjfm" --csv --log-file gpurun_out/r2_launches.csv python tools/prof_step.py --steps 2 --warmup 1 > gpurun_out/final_ncu.log 2>&1
 tail -3 gpurun_out/final_tests.log; cat gpurun_out/final_smoke.log | tail -2; cut -c1-400 gpurun_out/final_bench.json
