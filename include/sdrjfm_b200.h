@@ -205,11 +205,18 @@ int  sdrjfm_set_bandwidth (sdrjfm_handle *h, int32_t hz);          /* setBandwid
 int  sdrjfm_set_attenuation (sdrjfm_handle *h, float l, float r);  /* setAttenuation */
 int  sdrjfm_set_rds_mode (sdrjfm_handle *h, int32_t mode);         /* setfmRdsSelector: 0 off, 1..3 */
 int  sdrjfm_set_local_oscillator (sdrjfm_handle *h, int32_t hz);   /* set_localOscillator */
-/* RDS symbol stage on the GPU (optional, off by default): what rdsDecoder::doDecode does with every
- * 24 kHz sample in mode RDS_1 before processBit — the Costas loop (includes/various/costas.h, ctor args
- * src/rds/rds-decoder.cpp:40-41) and rdsDecoder_1::doDecode (src/rds/rds-decoder-1.cpp:126-143).  The bits
- * of the last process call are read per stream and go to rdsDecoder::processBit on the host (block
- * synchronisation and group decoding stay there).                                                   */
+/* RDS symbol stage on the GPU (optional, off by default): what rdsDecoder::doDecode (src/rds/rds-decoder.cpp:63-102)
+ * does with every 24 kHz sample before processBit, for the mode sdrjfm_set_rds_mode selects:
+ *   RDS_1  the Costas loop (includes/various/costas.h, ctor args rds-decoder.cpp:40-41) and rdsDecoder_1::doDecode
+ *          (src/rds/rds-decoder-1.cpp:126-143);
+ *   RDS_2  rdsDecoder_2::doDecode (src/rds/rds-decoder-2.cpp:96-158): matched filter, AGC, timing recovery, Costas;
+ *   RDS_3  the same Costas loop and rdsDecoder_3::doDecode (src/rds/rds-decoder-3.cpp:83-118).  That decoder reads the
+ *          block synchroniser's error count to re-synchronise its bit clock, so in this mode rdsBlockSynchronizer::pushBit
+ *          (src/rds/rds-blocksynchronizer.cpp) and rdsDecoder::processBit (rds-decoder.cpp:104-131) run on the device too.
+ * The bits of the last process call are read per stream (sdrjfm_read_rds_bits) and go to rdsDecoder::processBit on the
+ * host.  In mode RDS_3 sdrjfm_read_rds_groups returns the groups the device-side synchroniser completed in the last call
+ * (blocks A, B, C, D per group: what processBit hands to rdsGroupDecoder::decode) and, in status [4], synchronised /
+ * bit-clock re-synchronisations in that call / sync errors / crc errors; group decoding (GUI strings) stays on the host. */
 /* startScanning / stopScanning (src/fm/fm-processor.cpp:361-367, 478-495): while scanning, process
  * calls produce no audio and no RDS; per completed block of 1024 fm-rate samples the level around the
  * carrier and at the band edge are returned as (get_db (signal, 256), get_db (noise, 256)) pairs
@@ -260,6 +267,7 @@ int64_t sdrjfm_read_hf_spectrum (sdrjfm_handle *h, int32_t stream, double *displ
                                  int32_t *segments_in_last_call);
 int  sdrjfm_set_rds_symbol_stage (sdrjfm_handle *h, int32_t on);
 int64_t sdrjfm_read_rds_bits (sdrjfm_handle *h, int32_t stream, uint8_t *bits, int64_t cap);
+int64_t sdrjfm_read_rds_groups (sdrjfm_handle *h, int32_t stream, uint16_t *blocks, int64_t cap_groups, int32_t *status);
 int  sdrjfm_set_squelch_mode (sdrjfm_handle *h, int32_t mode);     /* set_squelchMode: 0 OFF, 1 NSQ (noise), 2 LSQ (level) */
 int  sdrjfm_set_squelch_value (sdrjfm_handle *h, int32_t value);   /* set_squelchValue: 0..100 */
 int  sdrjfm_set_auto_mono (sdrjfm_handle *h, int32_t on);          /* setAutoMonoMode */

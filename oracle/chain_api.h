@@ -115,6 +115,14 @@ void   *ref_rds2_create (int32_t rate);
 void    ref_rds2_destroy (void *h);
 int64_t ref_rds2_process (void *h, const float *rds24, int64_t n, uint8_t *bits, int64_t cap);
 int32_t ref_rds2_dump (void *h, float *out, int32_t cap);
+/* mode RDS_3 (rds-decoder.cpp:90-98, 104-131): Costas + the reference's rdsDecoder_3, rdsBlockSynchronizer and RDSGroup,
+ * sequenced as rdsDecoder::doDecode / processBit do.  groups: [cap_groups][4] blocks A..D of every completed group. */
+void   *ref_rds3_create (int32_t rate);
+void    ref_rds3_destroy (void *h);
+int64_t ref_rds3_process (void *h, const float *rds24, int64_t n, uint8_t *bits, int64_t cap,
+                          uint16_t *groups, int64_t cap_groups, int64_t *n_groups, int32_t *n_resync);
+/* the synchroniser alone, fed with bits (checks the test signal's checkwords): returns completed groups */
+int64_t ref_blocksync_groups (const uint8_t *bits, int64_t n, uint16_t *groups, int64_t cap_groups);
 
 /* HF scope display spectrum (hs-scope.cpp:102-151, 175-203) restated around the reference's Fft_transform (ref_ only) */
 int64_t ref_hf_spectrum (const float *x, int64_t n, int32_t displaySize, int32_t sampleRate, int32_t freq,

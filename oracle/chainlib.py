@@ -298,6 +298,46 @@ class Rds2:
         return a[:n].copy()
 
 
+class Rds3:
+    """RDS symbol stage, mode RDS_3: the reference's Costas loop, rdsDecoder_3, rdsBlockSynchronizer and RDSGroup (ref_ only)."""
+
+    def __init__(self, rate=24000):
+        self.lib = C.CDLL(_PATHS["ref"])
+        self.lib.ref_rds3_create.restype = C.c_void_p
+        self.lib.ref_rds3_create.argtypes = [C.c_int32]
+        self.lib.ref_rds3_destroy.argtypes = [C.c_void_p]
+        self.lib.ref_rds3_process.restype = C.c_int64
+        self.lib.ref_rds3_process.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                              C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        self.h = self.lib.ref_rds3_create(rate)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.ref_rds3_destroy(self.h)
+            self.h = None
+
+    def process(self, rds24):
+        """-> (bits, groups [n, 4], bit-clock re-synchronisations)"""
+        x = np.ascontiguousarray(rds24, dtype=np.complex64)
+        bits = np.zeros(len(x) // 8 + 16, np.uint8)
+        groups = np.zeros((len(x) // 2000 + 8, 4), np.uint16)
+        ng, nrs = C.c_int64(0), C.c_int32(0)
+        n = self.lib.ref_rds3_process(self.h, x.ctypes.data, len(x), bits.ctypes.data, len(bits),
+                                      groups.ctypes.data, groups.shape[0], C.byref(ng), C.byref(nrs))
+        return bits[:n].copy(), groups[:ng.value].copy(), nrs.value
+
+
+def ref_blocksync_groups(bits):
+    """the reference's rdsBlockSynchronizer fed with a bit stream (as rdsDecoder::processBit does) -> completed groups"""
+    lib = C.CDLL(_PATHS["ref"])
+    lib.ref_blocksync_groups.restype = C.c_int64
+    lib.ref_blocksync_groups.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+    b = np.ascontiguousarray(bits, dtype=np.uint8)
+    g = np.zeros((len(b) // 104 + 4, 4), np.uint16)
+    n = lib.ref_blocksync_groups(b.ctypes.data, len(b), g.ctypes.data, g.shape[0])
+    return g[:n].copy()
+
+
 def ref_hf_spectrum(x, display_size=1024, sample_rate=2304000, repeat_rate=10):
     """hs_scope's displayBuffer after every completed segment of the raw IQ x (restated around the reference's
     Fft_transform; ref_ only). Returns float64 [segments, display_size]."""

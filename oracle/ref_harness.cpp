@@ -43,6 +43,9 @@
 #define private public       /* the dump below reads rdsDecoder_1's tables; nothing else is touched */
 #include "rds-decoder-1.h"
 #include "rds-decoder-2.h"
+#include "rds-decoder-3.h"
+#include "rds-blocksynchronizer.h"
+#include "rds-group.h"
 #undef private
 #undef private
 #undef protected
@@ -709,6 +712,88 @@ int32_t n = (int32_t)d -> my_matchedFltKernelVec. size ();
 	if (n > cap) n = cap;
 	for (int32_t i = 0; i < n; i ++) out [i] = d -> my_matchedFltKernelVec [i];
 	return n;
+}
+}
+
+// ---- RDS symbol stage, mode RDS_3: Costas (the one shared with mode 1) + the reference's rdsDecoder_3, which reads the
+// block synchroniser's error count to re-synchronise its bit clock (src/rds/rds-decoder-3.cpp:96-101), so the
+// synchroniser and the group are the reference's own too; sequencing of rdsDecoder::doDecode case RDS_3 and
+// rdsDecoder::processBit (src/rds/rds-decoder.cpp:90-98, 104-131) without the group decoder (GUI strings).
+// The signal bodies moc would generate for rds-blocksynchronizer.h:
+void	rdsBlockSynchronizer::setRDSisSynchronized (bool) {}
+void	rdsBlockSynchronizer::setbitErrorRate (double) {}
+struct RefRds3 {
+	RDSGroup		group;
+	rdsBlockSynchronizer	sync;
+	Costas			my_costas;
+	rdsDecoder_3		decoder;
+	RefRds3 (int32_t rate): sync (nullptr), my_costas (rate, 1.0f / 16.0f, 0.02f / 16.0f, 10.0f),
+	                        decoder (nullptr, rate, &sync, &group, nullptr) {
+	   group. clear ();
+	   sync. setFecEnabled (true);
+	}
+//	returns true when a group was completed
+	bool processBit (bool bit) {
+	   switch (sync. pushBit (bit, &group)) {
+	      case rdsBlockSynchronizer::RDS_NO_SYNC:
+	      case rdsBlockSynchronizer::RDS_NO_CRC:
+	         sync. resync ();
+	         return false;
+	      case rdsBlockSynchronizer::RDS_COMPLETE_GROUP:
+	         return true;                 // (the caller copies the group, then clears it)
+	      default:
+	         return false;
+	   }
+	}
+};
+extern "C" {
+void	*ref_rds3_create (int32_t rate) { return new RefRds3 (rate); }
+void	ref_rds3_destroy (void *h) { delete (RefRds3 *)h; }
+int64_t	ref_rds3_process (void *h, const float *rds24, int64_t n, uint8_t *bits, int64_t cap,
+	                  uint16_t *groups, int64_t cap_groups, int64_t *n_groups, int32_t *n_resync) {
+RefRds3 *c = (RefRds3 *)h;
+int64_t nb = 0, ng = 0;
+int32_t nrs = 0;
+	for (int64_t i = 0; i < n; i ++) {
+	   DSPCOMPLEX v (rds24 [2 * i], rds24 [2 * i + 1]);
+	   v = c -> my_costas. process_sample (v);
+	   if (c -> decoder. Resync || c -> sync. getNumSyncErrors () > 3) nrs ++;        // the decoder re-synchronises on this sample
+	   uint8_t theBit;
+	   if (c -> decoder. doDecode (real (v), &theBit)) {
+	      if (nb < cap) bits [nb] = theBit;
+	      nb ++;
+	      if (c -> processBit (theBit)) {
+	         if (groups && ng < cap_groups)
+	            for (int b = 0; b < 4; b ++) groups [4 * ng + b] = c -> group. getBlock ((RDSGroup::RdsBlock)b);
+	         ng ++;
+	         c -> group. clear ();
+	      }
+	   }
+	}
+	if (n_groups) *n_groups = ng;
+	if (n_resync) *n_resync = nrs;
+	return nb;
+}
+int64_t	ref_blocksync_groups (const uint8_t *bits, int64_t n, uint16_t *groups, int64_t cap_groups) {
+RDSGroup group;
+rdsBlockSynchronizer sync (nullptr);
+int64_t ng = 0;
+	group. clear ();
+	sync. setFecEnabled (true);
+	for (int64_t i = 0; i < n; i ++) {
+	   switch (sync. pushBit (bits [i] != 0, &group)) {
+	      case rdsBlockSynchronizer::RDS_NO_SYNC:
+	      case rdsBlockSynchronizer::RDS_NO_CRC:
+	         sync. resync (); break;
+	      case rdsBlockSynchronizer::RDS_COMPLETE_GROUP:
+	         if (ng < cap_groups) for (int b = 0; b < 4; b ++) groups [4 * ng + b] = group. getBlock ((RDSGroup::RdsBlock)b);
+	         ng ++;
+	         group. clear ();
+	         break;
+	      default: break;
+	   }
+	}
+	return ng;
 }
 }
 

@@ -137,6 +137,8 @@ def lib():
         L.sdrjfm_read_scan.argtypes = [vp, i32, vp, i64]
         L.sdrjfm_read_rds_bits.restype = i64
         L.sdrjfm_read_rds_bits.argtypes = [vp, i32, vp, i64]
+        L.sdrjfm_read_rds_groups.restype = i64
+        L.sdrjfm_read_rds_groups.argtypes = [vp, i32, vp, i64, vp]
         L.sdrjfm_read_peak_levels.restype = i64
         L.sdrjfm_read_peak_levels.argtypes = [vp, i32, vp, i64]
         L.sdrjfm_set_volume_db.argtypes = [vp, f32]
@@ -377,6 +379,16 @@ class FmProcessorB200:
         if n < 0:
             raise SdrjfmError(n, self.L.sdrjfm_last_error(self.h).decode())
         return a[:n].copy()
+    def read_rds_groups(self, stream=0):
+        """mode RDS_3: (groups uint16 [n, 4] the device-side block synchroniser completed in the last call,
+        dict(synchronized, bitclk_resyncs, sync_errors, crc_errors))."""
+        a = np.zeros((self.cfg.max_samples_per_call // (8 * self.decim * 2000) + 8, 4), np.uint16)
+        st = (C.c_int32 * 4)()
+        n = self.L.sdrjfm_read_rds_groups(self.h, stream, a.ctypes.data, a.shape[0], st)
+        if n < 0:
+            raise SdrjfmError(n, self.L.sdrjfm_last_error(self.h).decode())
+        return a[:n].copy(), dict(synchronized=st[0], bitclk_resyncs=st[1], sync_errors=st[2], crc_errors=st[3])
+
     def setTestTone(self, on): self._ck(self.L.sdrjfm_set_test_tone(self.h, int(on)))
     def setDispDelay(self, steps): self._ck(self.L.sdrjfm_set_disp_delay(self.h, int(steps)))
 

@@ -46,6 +46,15 @@ __device__ __forceinline__ int atan_index (float num_scaled, float den) {
 	return (int)fadd (fdiv (num_scaled, den), 0.5f);
 }
 
+// The reference picks one of eight tables by quadrant and octant (Xtan2.cpp:74-97); every one of them is the first-
+// octant table PPY looked up at (int)(8192 * small / large + 0.5) and then negated and / or shifted by pi/2 or pi with
+// ONE float operation (Xtan2.cpp:30-37).  Division, rounding and the final add are sign-symmetric, so the eight
+// branches collapse into one division, one look-up and one add, chosen by three comparisons — the same floats,
+// without divergence:
+//     x > 0, y >= 0 :  x >= y :  t                |  else  H - t = -(t - H)
+//     x > 0, y <  0 :  x >= -y: -t                |  else  t - H
+//     x < 0, y >= 0 : -x >= y :  S - t = -(t - S) |  else  t + H
+//     x < 0, y <  0 :  x <= y :  t - S            |  else -H - t = -(t + H)
 __device__ __forceinline__ float lut_atan2 (const float *PPY, float y, float x) {
 const float S = (float)M_PI;
 const float H = fmul (S, 0.5f);
@@ -55,20 +64,14 @@ const float H = fmul (S, 0.5f);
 	   if (y == 0.f) return 0.f;
 	   return y > 0.f ? (float)(M_PI / 2) : (float)(-M_PI / 2);
 	}
-	if (x > 0.f) {
-	   if (y >= 0.f) {
-	      if (x >= y) return PPY [atan_index (fmul (8192.f, y), x)];
-	      return fsub (H, PPY [atan_index (fmul (8192.f, x), y)]);
-	   }
-	   if (x >= -y) return -PPY [atan_index (fmul (-8192.f, y), x)];
-	   return fsub (PPY [atan_index (fmul (-8192.f, x), y)], H);
-	}
-	if (y >= 0.f) {
-	   if (-x >= y) return fsub (S, PPY [atan_index (fmul (-8192.f, y), x)]);
-	   return fadd (PPY [atan_index (fmul (-8192.f, x), y)], H);
-	}
-	if (x <= y) return fsub (PPY [atan_index (fmul (8192.f, y), x)], S);
-	return fsub (-H, PPY [atan_index (fmul (8192.f, x), y)]);
+const bool xpos = x > 0.f, ypos = y >= 0.f;
+const float ax = fabsf (x), ay = fabsf (y);
+const bool swap = ay > ax;                               // the octant: every branch above keeps the ratio <= 1, ties unswapped
+const float t = PPY [atan_index (fmul (8192.f, swap ? ax : ay), swap ? ay : ax)];
+const float add = xpos ? (swap ? -H : 0.f) : (swap ? H : -S);
+const bool neg = xpos ? (ypos == swap) : (ypos != swap);
+const float r = add == 0.f ? t : fadd (t, add);
+	return neg ? -r : r;
 }
 
 struct dcplx { double re, im; };

@@ -168,6 +168,9 @@ struct Lane {
 	float   *d_rsy_c = nullptr, *d_rsy_v = nullptr, *d_rsy_w = nullptr;    // [S][cap_rds] Costas / low-pass / matched-filter outputs
 	float2  *d_rsy_in = nullptr;            // [S][cap_rds] private copy of the 24 kHz baseband of the call
 	Rds2State *d_rs2_state = nullptr; float2 *d_rs2_m = nullptr;     // mode RDS_2: rdsDecoder_2 state, matched-filter output
+	Rds3State *d_rs3_state = nullptr; float *d_rs3_sin = nullptr;     // mode RDS_3: rdsDecoder_3 + block synchroniser, SinCos (24000)
+	uint16_t *d_rs3_groups = nullptr; int32_t *d_rs3_ngroups = nullptr, *d_rs3_stat = nullptr;
+	int32_t  cap_groups = 0; float rs3_omega = 0.f; int8_t rs3_kmap [kRs3Sym] = { 0 };
 	int32_t  cap_bits = 0;
 	dcplx   *d_tileB = nullptr; DiscrSnap *d_snap = nullptr; int32_t ntiles_cap = 0;   // K2 pre-pass
 	float2  *d_pss_ring = nullptr;          // [S][2048] PSS filter input ring (state)
@@ -717,7 +720,7 @@ void *ptrs [] = { h -> d_tables, h -> d_sin_quarter, h -> d_in, h -> d_hist [0],
 	              h -> d_spec_in, h -> d_spec_carry [0], h -> d_spec_carry [1], h -> d_spec_win,
 	              h -> d_spec_Y, h -> d_spec_avg, h -> d_spec_disp, h -> d_xd, h -> d_xhist [0], h -> d_xhist [1], h -> d_dcnow,
 	              h -> d_tone_tab, h -> d_peak_ring, h -> d_cv_taps, h -> d_cv_hist [0], h -> d_cv_hist [1],
-	              h -> d_rs2_state, h -> d_rs2_m, h -> d_hf_blk, h -> d_hf_win, h -> d_hf_avg, h -> d_hf_disp };
+	              h -> d_rs2_state, h -> d_rs2_m, h -> d_rs3_state, h -> d_rs3_sin, h -> d_rs3_groups, h -> d_rs3_ngroups, h -> d_rs3_stat, h -> d_hf_blk, h -> d_hf_win, h -> d_hf_avg, h -> d_hf_disp };
 	for (void *p : ptrs) if (p) cudaFree (p);
 	if (h -> stream_rds) { cudaStreamSynchronize (h -> stream_rds); cudaStreamDestroy (h -> stream_rds); }
 	if (h -> stream_k3) { cudaStreamSynchronize (h -> stream_k3); cudaStreamDestroy (h -> stream_k3); }
@@ -915,7 +918,8 @@ float2 *U = wide ? h -> d_Uw : h -> d_U, *Sb = wide ? h -> d_Sw : h -> d_S;
 	   else h -> launches --;
 	}
 	else if (!wide && !lo && !h -> force_generic && rf.fmt != kFmtAirspy &&
-	         (rf.fmt != kFmtCF32 || h -> shape == 1 || h -> shape == kShapeResample)) {
+	         h -> shape != kShapeResample && (rf.fmt != kFmtCF32 || h -> shape == 1)) {
+//	   (stage A of the rational resampler stays on K1g: its 49 taps / 5 measured slower through TMA, 0.38 against 0.68)
 //	   device sample formats (and complex float at 6 MS/s) through TMA: K1tb over the whole tiles, K1g for the ragged rest
 	   int32_t tiles = 0;
 	   if (h -> shape == 0) {
@@ -930,14 +934,6 @@ float2 *U = wide ? h -> d_Uw : h -> d_U, *Sb = wide ? h -> d_Sw : h -> d_S;
 	            : rf.fmt == kFmtS16  ? tmab_launch<30, 2, 55, kFmtS16> (h, src, pitch, rf, M, hist, hlen, U, Sb) : 0;
 	      if (tiles == 0) poly_launch<30, 2, 2> (h, src, pitch, rf, hist, hlen, U, Sb, M, lp);
 	      else if (M % (kFeThreads * 2)) poly_launch<30, 2, 2> (h, src, pitch, rf, hist, hlen, U, Sb, M, lp, tiles);
-	      else h -> launches --;
-	   }
-	   else if (h -> shape == kShapeResample) {
-//	      stage A of the rational resampler: 49 taps / 5, rows of 40 samples, two rows of history
-	      tiles = rf.fmt == kFmtCF32 ? tmab_launch<kRsStageADecim, 8, kRsStageATaps, kFmtCF32> (h, src, pitch, rf, M, hist, hlen, U, Sb)
-	                                 : tmab_launch_fmt<kRsStageADecim, 8, kRsStageATaps> (h, src, pitch, rf, M, hist, hlen, U, Sb);
-	      if (tiles == 0) poly_launch<kRsStageADecim, 8, 10> (h, src, pitch, rf, hist, hlen, U, Sb, M, lp);
-	      else if (M % (kFeThreads * 8)) poly_launch<kRsStageADecim, 8, 10> (h, src, pitch, rf, hist, hlen, U, Sb, M, lp, tiles);
 	      else h -> launches --;
 	   }
 	   else {
@@ -1443,6 +1439,32 @@ const int dec = st.decoder == 2 ? 1 : st.decoder == 1 ? 2 : 0;
 	            h -> d_rsy_in, h -> d_rs2_m, bp, nout, S, p2, h -> d_rs2_state, h -> d_rsy_bits, h -> cap_bits, h -> d_rsy_nbits);
 	      h -> launches += 2;
 	   }
+	   else if (h -> rds_symbols && nout > 0 && st.rds_mode == 3) {
+//	      symbol stage, mode RDS_3 (rds-decoder.cpp:90-98): the Costas loop of mode 1, then rdsDecoder_3 with the block
+//	      synchroniser in its loop
+	      RdsSymParams sp2;
+	      sp2.alpha = 1.0f / 16.0f; sp2.beta = 0.02f / 16.0f;
+	      sp2.freq_limit = 2 * M_PI * 10.0f / 24000.0f;
+	      const float *tab = h -> tables.payload () + th.off_rds_sym;
+	      memcpy (sp2.match, tab, sizeof sp2.match);
+	      memcpy (sp2.lp, tab + kRsyMatch, sizeof sp2.lp);
+	      memcpy (sp2.bp, tab + kRsyMatch + kRsyLp, sizeof sp2.bp);
+	      Rds3Params p3;
+	      p3.sin_tab = h -> d_rs3_sin; p3.C = 24000 / (2 * M_PI); p3.rate = 24000; p3.omega = h -> rs3_omega;
+	      memcpy (p3.kmap, h -> rs3_kmap, sizeof p3.kmap);
+	      const int64_t bp = h -> cap_rds;
+	      rds_costas_kernel<<<(S + kRsyLanes - 1) / kRsyLanes, kRsyLanes, 0, rs>>> (
+	            h -> d_rsy_in, bp, nout, S, sp2, h -> d_rsy_state, h -> d_rsy_c, bp,
+	            h -> lf_plot == 9 ? h -> d_plot : nullptr, h -> cap_fm);
+	      if (h -> lf_plot == 9 && h -> spec_N) CK (cudaEventRecord (h -> ev_sym, rs));
+	      const dim3 gf ((unsigned)((nout + 127) / 128), (unsigned)S);
+	      rds_fir_kernel<kRsyLp, false><<<gf, 128, 0, rs>>> (h -> d_rsy_c, h -> d_rsy_v, bp, nout, sp2, h -> d_rsy_state);
+	      rds3_seq_kernel<<<(S + kRsyLanes - 1) / kRsyLanes, kRsyLanes, 0, rs>>> (
+	            h -> d_rsy_c, h -> d_rsy_v, bp, nout, S, p3, h -> d_rsy_state, h -> d_rs3_state,
+	            h -> d_rsy_bits, h -> cap_bits, h -> d_rsy_nbits, h -> d_rs3_groups, h -> cap_groups, h -> d_rs3_ngroups, h -> d_rs3_stat);
+	      rds_sym_roll_kernel<<<S, 64, 0, rs>>> (h -> d_rsy_c, h -> d_rsy_v, bp, nout, h -> d_rsy_state);
+	      h -> launches += 4;
+	   }
 	   else if (h -> rds_symbols && nout > 0) {
 //	      symbol stage, mode RDS_1 (rds-decoder.cpp:69-82): Costas (rate, 1/16, 0.02/16, 10 Hz) + decoder 1
 	      RdsSymParams sp2;
@@ -1805,9 +1827,6 @@ static int lane_set_rds_mode (Lane *h, int32_t m) {
 	   int rc = rds_setup (h);
 	   if (rc != SDRJFM_OK) return rc;
 	}
-	if (m == 3 && h -> rds_symbols) {
-	   h -> err = "the GPU symbol stage covers RDS_1 and RDS_2; switch it off for RDS_3"; return SDRJFM_ERR_UNSUPPORTED;
-	}
 	if (h -> lf_plot >= 8) h -> spec_refresh = true;                      // setfmRdsSelector: new_lfSpectrum (:843-846)
 	h -> set.rds_mode = m; return SDRJFM_OK;
 }
@@ -1821,14 +1840,35 @@ std::vector<Rds2State> st (S);
 	CK (cudaMemcpy (h -> d_rs2_state, st.data (), S * sizeof (Rds2State), cudaMemcpyHostToDevice));
 	return SDRJFM_OK;
 }
+static int rs3_reset (Lane *h) {
+const size_t S = h -> cfg.n_streams;
+std::vector<Rds3State> st (S);
+	memset (st.data (), 0, S * sizeof (Rds3State));
+	for (auto &q : st) q.resync = 1;
+	CK (cudaMemcpy (h -> d_rs3_state, st.data (), S * sizeof (Rds3State), cudaMemcpyHostToDevice));
+	CK (cudaMemset (h -> d_rs3_ngroups, 0, S * sizeof (int32_t)));
+	CK (cudaMemset (h -> d_rs3_stat, 0, S * 4 * sizeof (int32_t)));
+	return SDRJFM_OK;
+}
 static int lane_set_rds_symbol_stage (Lane *h, int32_t on) {
 	if (!h) return SDRJFM_ERR_ARG;
-	if (on && h -> set.rds_mode == 3) {
-	   h -> err = "RDS_3 re-synchronises its bit clock from the block synchroniser's error count (rds-decoder-3.cpp:96-101): "
-	              "its symbol stage stays with the host-side rdsDecoder"; return SDRJFM_ERR_UNSUPPORTED;
-	}
 	CK (cudaSetDevice (h -> cfg.device));
 const size_t S = h -> cfg.n_streams;
+	if (on && !h -> d_rs3_state) {
+//	   rdsDecoder_3's constructor state (rds-decoder-3.cpp:44-79): everything zero, Resync set; rdsBlockSynchronizer::reset
+	   std::vector<float> tab;
+	   design_rds3_clock (24000, tab, &h -> rs3_omega, h -> rs3_kmap);
+	   CK (dalloc (&h -> d_rs3_sin, tab.size ()));
+	   CK (cudaMemcpy (h -> d_rs3_sin, tab.data (), tab.size () * sizeof (float), cudaMemcpyHostToDevice));
+	   h -> cap_groups = (int32_t)(h -> cap_rds / 2000 + 4);               // a group is 104 bits = 2101 samples
+	   CK (dalloc (&h -> d_rs3_state, S)); CK (dalloc (&h -> d_rs3_groups, S * h -> cap_groups * 4));
+	   CK (dalloc (&h -> d_rs3_ngroups, S)); CK (dalloc (&h -> d_rs3_stat, S * 4));
+	   const int rc = rs3_reset (h); if (rc != SDRJFM_OK) return rc;
+	}
+	else if (on && !h -> rds_symbols) {
+	   CK (cudaStreamSynchronize (h -> stream)); CK (cudaStreamSynchronize (h -> stream_rds));
+	   const int rc = rs3_reset (h); if (rc != SDRJFM_OK) return rc;
+	}
 	if (on && !h -> d_rs2_state) {
 	   CK (dalloc (&h -> d_rs2_state, S)); CK (dalloc (&h -> d_rs2_m, S * h -> cap_rds));
 	   const int rc = rs2_reset (h); if (rc != SDRJFM_OK) return rc;
@@ -1868,6 +1908,27 @@ int32_t n = 0;
 	if (n > cap) n = (int32_t)cap;
 	if (n > 0) {
 	   CK (cudaMemcpyAsync (out, h -> d_rsy_bits + (size_t)stream * h -> cap_bits, n, cudaMemcpyDeviceToHost, h -> stream));
+	   CK (cudaStreamSynchronize (h -> stream));
+	}
+	return n;
+}
+// groups completed for `stream` by the LAST process call in mode RDS_3 (blocks A..D each), and the synchroniser's status:
+// status [0] synchronised, [1] bit-clock re-synchronisations in that call, [2] sync errors, [3] crc errors
+static int64_t lane_read_rds_groups (Lane *h, int32_t stream, uint16_t *out, int64_t cap, int32_t *status) {
+	if (!h || stream < 0 || stream >= h -> cfg.n_streams || (cap > 0 && !out)) return SDRJFM_ERR_ARG;
+	if (status) memset (status, 0, 4 * sizeof (int32_t));
+	if (!h -> rds_symbols || !h -> d_rs3_ngroups || h -> set.rds_mode != 3 || h -> last_nrds == 0) return 0;
+	CK (cudaSetDevice (h -> cfg.device));
+int32_t n = 0;
+	CK (cudaStreamSynchronize (h -> stream_rds));
+	CK (cudaMemcpyAsync (&n, h -> d_rs3_ngroups + stream, sizeof n, cudaMemcpyDeviceToHost, h -> stream));
+	if (status) CK (cudaMemcpyAsync (status, h -> d_rs3_stat + 4 * stream, 4 * sizeof (int32_t), cudaMemcpyDeviceToHost, h -> stream));
+	CK (cudaStreamSynchronize (h -> stream));
+	if (n > h -> cap_groups) n = h -> cap_groups;
+	if (n > cap) n = (int32_t)cap;
+	if (n > 0) {
+	   CK (cudaMemcpyAsync (out, h -> d_rs3_groups + (size_t)stream * h -> cap_groups * 4, (size_t)n * 4 * sizeof (uint16_t),
+	                        cudaMemcpyDeviceToHost, h -> stream));
 	   CK (cudaStreamSynchronize (h -> stream));
 	}
 	return n;

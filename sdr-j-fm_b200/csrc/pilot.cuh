@@ -121,6 +121,7 @@ const float p1 = fadd (phi, fmul (fmul (pilot, osc), gain));
 // The same step for the segment walk: phi is known to lie in [0, 2 pi] (it is a pi_constrain or
 // wrap_2pi result), only the next phase is wanted, and the derivative is accumulated to first
 // order (sum of x cos phi).  Bit-identical to pilot_step for such phi.
+template <bool DER>
 __device__ __forceinline__ float pilot_walk_step (const SinLut &L, const float *q, float phi, float pilot,
                                                   float gain, float omega, float &dsum) {
 constexpr int32_t Q = kFmRate / 4, H = 2 * Q;
@@ -133,7 +134,7 @@ int32_t k = neg ? i - H : i;
 float v = q [k];
 	v = neg ? -v : v;
 	if (i == H) v = L.sin_at_half;               // the zero crossing at pi: the table holds sin (pi) as computed, not -0
-	dsum = fmaf (pilot, __cosf (phi), dsum);
+	if (DER) dsum = fmaf (pilot, __cosf (phi), dsum);
 float p2 = fadd (fadd (phi, fmul (fmul (pilot, v), gain)), omega);
 	if (p2 >= kTwoPiF) p2 = (float)((double)p2 - 2 * M_PI);     // PI_Constrain: fmod (v, 2 pi), v < 4 pi
 	else if (p2 < 0.f) p2 = pi_constrain (p2);                  // cannot happen for |pilot| < 1000
@@ -215,11 +216,18 @@ int    itTotal = 0, itMax = 0, nFallback = 0;
 	   }
 	   double afc = lin_scan_start (bDc, S.carry [0], powDc, S.warpA);
 	   double am  = lin_scan_start (bCa, S.carry [1], powCa, S.warpB);
+//	   (the carrier level is only read at the end of a call: its per-sample replay is left to the owner of the
+//	   window's last sample)
+	   const bool ownsLast = n0 <= Tw - 1 && Tw - 1 < n0 + kPiPer;
+	   if (ownsLast) {
+#pragma unroll
+	      for (int j = 0; j < kPiPer; j ++)
+	         if (n0 + j < Tw) am = am * (double)oneMinusCarrier + (double)fmul (carrierAlpha, zb [j]);
+	   }
 #pragma unroll
 	   for (int j = 0; j < kPiPer; j ++) {
 	      if (n0 + j < Tw) {
 	         afc = afc * (double)oneMinusDc + (double)fmul (fmDcAlpha, r [j]);
-	         am  = am * (double)oneMinusCarrier + (double)fmul (carrierAlpha, zb [j]);
 	         const float demod = fdiv (fmul (fmul (20.0f, fsub (r [j], (float)afc)), 1.0f), P.K_FM);
 	         dm [base + n0 + j] = demod;
 	         S.x [n0 + j] = fmul (5.0f, demod);
@@ -237,8 +245,10 @@ int    itTotal = 0, itMax = 0, nFallback = 0;
 	   bool converged = false;
 	   for (; it < kPiMaxIter; it ++) {
 //	   anchors: sample 0, and the first sample of every run of est inside [4.6, 5.3).  They only
-//	   depend on the estimate to ~0.05 rad, so they are refreshed at iterations 0, 4, 8 and 16.
-	      if (it == 0 || it == 4 || it == 8 || it == 16) {
+//	   depend on the estimate to ~0.05 rad (the first guess is good to ~1e-3 in a locked window), so they are
+//	   only refreshed when a window has not converged after 6, 12 and 18 passes.
+	      const bool refresh = it == 0 || it == 6 || it == 12 || it == 18;
+	      if (refresh) {
 	         unsigned flags = 0;
 	         {
 	            bool prevIn = false;
@@ -275,18 +285,29 @@ int    itTotal = 0, itMax = 0, nFallback = 0;
 	      const int nseg = S.nseg;
 //	   advance every segment with the exact reference arithmetic; a segment is consistent when it
 //	   ends bit-exactly on the value the next segment starts from
+//	   (the derivative of a segment moves by ~1e-6 of itself once the estimate is within a few ulp: it is taken in
+//	   the first two passes and after an anchor refresh, and kept afterwards)
 	      int bad = 0;
+	      const bool wantDer = it < 2 || refresh;
 	      for (int c = tid; c < nseg; c += kPiThreads) {
 	         const int a0 = S.anc [c];
 	         const int a1 = (c + 1 < nseg) ? (int)S.anc [c + 1] : Tw;
 	         float p = S.est [a0];
 	         float dsum = 0.0f;
-	         for (int n = a0; n < a1; n ++) {
-	            if (n > a0) S.est [n] = p;
-	            p = pilot_walk_step (L, sq, p, S.x [n], P.gain, P.omega, dsum);
+	         if (wantDer) {
+	            for (int n = a0; n < a1; n ++) {
+	               if (n > a0) S.est [n] = p;
+	               p = pilot_walk_step<true> (L, sq, p, S.x [n], P.gain, P.omega, dsum);
+	            }
+	            S.der [c] = fmaf (P.gain, dsum, 1.0f);   // d(end)/d(start) to first order
+	         }
+	         else {
+	            for (int n = a0; n < a1; n ++) {
+	               if (n > a0) S.est [n] = p;
+	               p = pilot_walk_step<false> (L, sq, p, S.x [n], P.gain, P.omega, dsum);
+	            }
 	         }
 	         S.G [c] = p;
-	         S.der [c] = fmaf (P.gain, dsum, 1.0f);      // d(end)/d(start) to first order
 	         double rs = 0.0;
 	         if (c + 1 < nseg) {
 	            const float nextP = S.est [a1];          // only its owner's walk reads it; nobody writes it here

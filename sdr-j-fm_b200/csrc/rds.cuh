@@ -549,4 +549,174 @@ float2 keep [kRs2Taps - 1];
 	for (int i = 0; i < kRs2Taps - 1; i ++) st.hist [i] = keep [i];
 }
 
+// ---- symbol stage of mode RDS_3: Costas (shared with mode 1) + rdsDecoder_3 (src/rds/rds-decoder-3.cpp:83-118) ----
+//   rdsFilter.Pass          the 21-tap low-pass of mode 1, kept in a ring of 21 = ceil (24000 / 1187.5) values (:88-89)
+//   synchronizeOnBitClk     folds that ring over half a bit-clock period and puts the clock phase on its rising edge (:121-158);
+//                           it runs on the first sample and whenever the block synchroniser has counted more than 3
+//                           sync errors (:91-96) — which is why the synchroniser (src/rds/rds-blocksynchronizer.cpp) and
+//                           the group it fills (src/rds/rds-group.cpp) live on the device in this mode
+//   bit clock               sine of a phase advancing 2 pi 1187.5 / 24000 per sample (the reference's table SinCos (24000));
+//                           the Costas output is integrated against it and a bit is taken at every rising edge (:98-115)
+// Integer state machine and float recurrence alike: one lane per stream, statement by statement.
+constexpr int kRs3Sym = 21;                     // symbolCeiling; symbolFloor = 20
+constexpr int kRs3BlockBits = 26, kRs3CrcBits = 10;
+struct Rds3Sync {                  // rdsBlockSynchronizer members + RDSGroup::rdsBlocks
+	uint32_t bitstream;
+	int32_t  synced, block, bits_in_block;
+	uint16_t sync_errors, crc_errors, bits_processed, bit_errors;
+	uint16_t grp [4];
+};
+struct Rds3State {                 // rdsDecoder_3 members
+	float    integ, clk_phase, prev_clk;
+	int32_t  prev_bit, resync;
+	Rds3Sync sy;
+};
+struct Rds3Params {
+	const float *sin_tab;           // (float) sin (2 pi i / 24000), i < 24000 (SinCos::SinCos (Rate), sincos.cpp:35-44)
+	double   C;                     // Rate / (2 pi)
+	int32_t  rate;
+	float    omega;                 // omegaRDS
+	int8_t   kmap [kRs3Sym];        // correlationVector slot of ring element i (a constant of the clock, :133-147)
+};
+enum { kRs3Waiting = 0, kRs3Buffering, kRs3NoSync, kRs3NoCrc, kRs3Group };
+
+// SinCos::getSin (sincos.cpp:53-58, 76-80)
+__device__ __forceinline__ float rs3_sin (const Rds3Params &P, float phase) {
+const bool neg = phase < 0.f;
+const float a = neg ? -phase : phase;
+const int32_t i = ((int32_t)((double)a * P.C)) % P.rate;
+const float v = P.sin_tab [i];
+	return neg ? -v : v;
+}
+// remainder of (bits ^ offset) x^10 modulo the RDS generator polynomial, fed msb first as the reference's shift
+// register does (getSyndrome, rds-blocksynchronizer.cpp:109-125): zero for an error-free block
+__device__ __forceinline__ uint32_t rs3_syndrome (uint32_t bits, uint32_t offset) {
+const uint32_t block = bits ^ offset;
+uint32_t reg = 0;
+	for (int k = kRs3BlockBits - 1; k >= 0; k --) {
+	   const bool top = (reg >> (kRs3CrcBits - 1)) & 1u;
+	   reg <<= 1;
+	   if (top) reg ^= 0x5B9u;
+	   if ((block >> k) & 1u) reg ^= 0x31Bu;
+	}
+	return reg;
+}
+__device__ __forceinline__ uint32_t rs3_offset (int block, bool typeB) {
+	return block == 0 ? 0xFCu : block == 1 ? 0x198u : block == 2 ? (typeB ? 0x350u : 0x168u) : 0x1B4u;
+}
+// rdsBlockSynchronizer::pushBit (:215-335) with decodeBlock (:127-163) and doMeggit (:171-191) folded in
+__device__ __forceinline__ int rs3_push_bit (Rds3Sync &s, bool b) {
+const bool typeB = (s.grp [1] >> 11) & 1u;                          // RDSGroup::isTypeBGroup
+	s.bitstream = (s.bitstream << 1) | (b ? 1u : 0u);
+	if (s.synced) {
+	   s.bits_in_block = (s.bits_in_block + 1) & 0xffff;
+	   if (s.bits_in_block < kRs3BlockBits) return kRs3Buffering;
+	   s.bits_in_block = 0;
+	   const uint32_t syn = rs3_syndrome (s.bitstream, rs3_offset (s.block, typeB));
+	   s.bits_processed += 16;
+	   if (syn != 0) {
+//	      the single-burst correction runs on the bit stream; its verdict is not read back (:140-147)
+	      uint32_t y = syn, mask = 1u << (kRs3BlockBits - 1);
+	      for (int i = 0; i < 16; i ++) {
+	         if (y & 0x200u) {
+	            if ((y & 0x1fu) == 0) { s.bitstream ^= mask; s.bit_errors ++; }
+	            else y ^= 0x5B9u;
+	         }
+	         y <<= 1; mask >>= 1;
+	      }
+	      s.bit_errors += 16;
+	   }
+	   if (s.bits_processed >= 4000) { s.bit_errors = 0; s.bits_processed = 0; }
+	   if (syn != 0) { s.crc_errors ++; return kRs3NoCrc; }
+	   s.grp [s.block] = (uint16_t)(s.bitstream >> kRs3CrcBits);
+	   const int res = s.block == 3 ? kRs3Group : kRs3Buffering;
+	   s.block = (s.block + 1) & 3;
+	   return res;
+	}
+	if (s.block == 0) {                                               // shifting until a valid block A passes
+	   if (rs3_syndrome (s.bitstream & 0x3FFFFFFu, rs3_offset (0, typeB)) != 0) return kRs3Waiting;
+	   s.grp [0] = (uint16_t)(s.bitstream >> kRs3CrcBits);
+	   s.bits_in_block = 0;
+	   s.block = 1;
+	   return kRs3Buffering;
+	}
+	if (s.bits_in_block < kRs3BlockBits - 1) { s.bits_in_block ++; return kRs3Buffering; }
+	s.bits_in_block = 0;
+	if (rs3_syndrome (s.bitstream, rs3_offset (s.block, typeB)) != 0) { s.sync_errors ++; return kRs3NoSync; }
+	s.grp [s.block] = (uint16_t)(s.bitstream >> kRs3CrcBits);
+	if (s.block < 2) { s.block ++; return kRs3Buffering; }
+	s.synced = 1;                                                      // blocks A, B, C in a row: synchronised
+	const int res = s.block == 3 ? kRs3Group : kRs3Buffering;
+	s.block = (s.block + 1) & 3;
+	return res;
+}
+__device__ __forceinline__ void rs3_resync (Rds3Sync &s) { s.block = 0; s.synced = 0; s.bits_in_block = 0; }
+
+// cbuf: Costas outputs (real part) of this call; vbuf: their low-pass (rds_fir_kernel<kRsyLp>); hist_v: the low-pass outputs
+// before this call (RdsSymState::hist_v, newest last).  groups: [S][cap_groups][4]; stat: [S][4] = synchronised, bit-clock
+// re-synchronisations in this call, sync errors, crc errors
+__global__ void __launch_bounds__ (kRsyLanes)
+rds3_seq_kernel (const float *__restrict__ cbuf, const float *__restrict__ vbuf, int64_t pitch, int32_t n, int32_t n_streams,
+                 const Rds3Params P, const RdsSymState *__restrict__ sym, Rds3State *__restrict__ state,
+                 uint8_t *__restrict__ bits, int32_t cap_bits, int32_t *__restrict__ nbits,
+                 uint16_t *__restrict__ groups, int32_t cap_groups, int32_t *__restrict__ ngroups, int32_t *__restrict__ stat) {
+const int stream = blockIdx.x * kRsyLanes + threadIdx.x;
+	if (stream >= n_streams) return;
+Rds3State st = state [stream];
+const float *c = cbuf + (int64_t)stream * pitch;
+const float *v = vbuf + (int64_t)stream * pitch;
+const float *hv = sym [stream].hist_v;                                // kRsyMatch - 1 entries
+uint8_t *out = bits + (int64_t)stream * cap_bits;
+uint16_t *gout = groups + (int64_t)stream * cap_groups * 4;
+int nb = 0, ng = 0, nrs = 0;
+	for (int32_t t = 0; t < n; t ++) {
+	   if (st.resync || st.sy.sync_errors > 3) {
+//	      synchronizeOnBitClk on the last 21 low-pass outputs, oldest first
+	      float corr [kRs3Sym];
+#pragma unroll
+	      for (int i = 0; i < kRs3Sym; i ++) corr [i] = 0.f;
+	      for (int i = 0; i < kRs3Sym; i ++) {
+	         const int k = t - (kRs3Sym - 1) + i;
+	         const float x = k >= 0 ? v [k] : hv [kRsyMatch - 1 + k];
+	         corr [P.kmap [i]] = fadd (corr [P.kmap [i]], x);
+	      }
+	      int iMin = 0;
+	      while (iMin < kRs3Sym - 1) { const float q = corr [iMin ++]; if (!(q > 0.f)) break; }
+	      while (iMin < kRs3Sym - 1) { const float q = corr [iMin ++]; if (!(q < 0.f)) break; }
+	      float ph = (float)fmod ((double)fmul (-P.omega, (float)(iMin - 1)), 2 * M_PI);
+	      while (ph < 0.f) ph = (float)((double)ph + 2 * M_PI);
+	      st.clk_phase = ph;
+	      rs3_resync (st.sy);
+	      st.sy.sync_errors = 0;
+	      st.resync = 0;
+	      nrs ++;
+	   }
+	   const float clk = rs3_sin (P, st.clk_phase);
+	   st.integ = fadd (st.integ, fmul (clk, c [t]));
+	   if (st.prev_clk <= 0.f && clk > 0.f) {                          // rising edge: look at the integrator
+	      const int theBit = st.integ >= 0.f ? 1 : 0;
+	      const int d = theBit ^ st.prev_bit;
+	      st.integ = 0.f;
+	      st.prev_bit = theBit;
+	      if (nb < cap_bits) out [nb] = (uint8_t)d;
+	      nb ++;
+//	      rdsDecoder::processBit (rds-decoder.cpp:104-131)
+	      const int r = rs3_push_bit (st.sy, d != 0);
+	      if (r == kRs3NoSync || r == kRs3NoCrc) rs3_resync (st.sy);
+	      else if (r == kRs3Group) {
+	         if (ng < cap_groups) { for (int b = 0; b < 4; b ++) gout [4 * ng + b] = st.sy.grp [b]; }
+	         ng ++;
+	         for (int b = 0; b < 4; b ++) st.sy.grp [b] = 0;            // my_rdsGroup.clear ()
+	      }
+	   }
+	   st.prev_clk = clk;
+	   st.clk_phase = (float)fmod ((double)fadd (st.clk_phase, P.omega), 2 * M_PI);
+	}
+	state [stream] = st;
+	nbits [stream] = nb;
+	ngroups [stream] = ng;
+	stat [4 * stream] = st.sy.synced; stat [4 * stream + 1] = nrs;
+	stat [4 * stream + 2] = st.sy.sync_errors; stat [4 * stream + 3] = st.sy.crc_errors;
+}
+
 }	// namespace sdrjfm

@@ -517,6 +517,16 @@ const int64_t n = lane_read_rds_bits (h -> lanes [i], stream - h -> first [i], o
 	if (n < 0) h -> err = h -> lanes [i] -> err;
 	return n;
 }
+int64_t sdrjfm_read_rds_groups (sdrjfm_handle *h, int32_t stream, uint16_t *blocks, int64_t cap_groups, int32_t *status) {
+	if (!h || cap_groups < 0) return SDRJFM_ERR_ARG;
+	LOCK_DEV (h);
+const int i = lane_of (h, stream);
+	if (i < 0) return SDRJFM_ERR_ARG;
+	HK (cudaStreamSynchronize (h -> stream));
+const int64_t n = lane_read_rds_groups (h -> lanes [i], stream - h -> first [i], blocks, cap_groups, status);
+	if (n < 0) h -> err = h -> lanes [i] -> err;
+	return n;
+}
 FWD1 (set_test_tone, int32_t)
 FWD1 (set_disp_delay, int32_t)
 int64_t sdrjfm_read_peak_levels (sdrjfm_handle *h, int32_t stream, float *out, int64_t cap_pairs) {

@@ -366,6 +366,27 @@ std::vector<float> taps (ntaps);
 	for (int i = 0; i < ntaps; i ++) out [i] = taps [i] * gain / scale;
 }
 
+// rdsDecoder_3's bit clock (src/rds/rds-decoder-3.cpp:62, 121-147): the sine table of SinCos (rate) (sincos.cpp:35-44),
+// omegaRDS, and the slot of the correlation vector each of the 21 ring elements is added to — the index k of
+// synchronizeOnBitClk restarts whenever the half-rate clock changes sign, which only depends on the element's number
+void design_rds3_clock (int32_t rate, std::vector<float> &sin_tab, float *omega, int8_t *kmap /* [21] */) {
+	sin_tab.resize (rate);
+	for (int32_t i = 0; i < rate; i ++) sin_tab [i] = (float)sin (2 * M_PI * i / rate);
+const double C = rate / (2 * M_PI);
+const float w = (float)((2 * M_PI * 1187.5) / (float)rate);
+	*omega = w;
+const int ceiling = (int)ceil (rate / (float)1187.5);
+bool isHigh = false;
+int k = 0;
+	for (int i = 0; i < ceiling && i < 21; i ++) {
+	   const float phase = (float)fmod ((double)(i * (w / 2)), 2 * M_PI);
+	   const float sn = phase < 0 ? -sin_tab [((int32_t)((double)(-phase) * C)) % rate] : sin_tab [((int32_t)((double)phase * C)) % rate];
+	   if (sn > 0 && !isHigh) { isHigh = true; k = 0; }
+	   else if (sn < 0 && isHigh) { isHigh = false; k = 0; }
+	   kmap [i] = (int8_t)(k ++);
+	}
+}
+
 TableBlob build_tables (int32_t input_rate, int32_t fm_rate, int32_t input_filter_hz,
                         int32_t audio_lp_hz) {
 TableHeader h;

@@ -104,6 +104,7 @@ void design_rds_symbol_tables (int32_t rate, float *out);
 // RDS symbol stage of mode RDS_2: the 45-tap matched filter ShapingFilter ().root_raised_cosine (1.0, rate,
 // 2 * 1187.5, 1.0, 45) of rds-decoder-2.cpp:67-71 (src/various/shaping_filter.cpp:4-56)
 void design_rds2_matched_filter (int32_t rate, float *out /* [45] */);
+void design_rds3_clock (int32_t rate, std::vector<float> &sin_tab, float *omega, int8_t *kmap /* [21] */);
 
 TableBlob build_tables (int32_t input_rate, int32_t fm_rate, int32_t input_filter_hz,
                         int32_t audio_lp_hz);

@@ -73,10 +73,38 @@ def adjacent_interferer(n, fs=INPUT_RATE, seed=1236, amp=0.05, snr_db=40.0):
     return (want + adj + _awgn(rng, n, amp, snr_db)).astype(np.complex64)
 
 
-def batch_stream(s, n, fs=INPUT_RATE, amp=0.5, snr_db=40.0, with_rds=True):
-    """config 5, stream s: config-2 MPX with tone 400+10·s Hz, RDS bits from rng(2000+s)."""
+RDS_OFFSET_WORDS = dict(A=0x0FC, B=0x198, C=0x168, C2=0x350, D=0x1B4)      # IEC 62106 annex A
+
+
+def rds_checkword(data16, offset):
+    """10-bit checkword of one RDS block: remainder of data x^10 modulo g(x) = x^10 + x^8 + x^7 + x^5 + x^4 + x^3 + 1,
+    plus the block's offset word."""
+    reg = (int(data16) & 0xFFFF) << 10
+    for k in range(25, 9, -1):
+        if reg & (1 << k):
+            reg ^= 0x5B9 << (k - 10)
+    return (reg & 0x3FF) ^ offset
+
+
+def rds_group_bits(groups):
+    """groups: iterable of (A, B, C, D) 16-bit block contents -> the 104 bits per group, msb first, with checkwords
+    (block C takes offset C' in version-B groups, i.e. when bit 11 of block B is set)."""
+    out = []
+    for a, b, c, d in groups:
+        offs = (RDS_OFFSET_WORDS["A"], RDS_OFFSET_WORDS["B"],
+                RDS_OFFSET_WORDS["C2"] if (b >> 11) & 1 else RDS_OFFSET_WORDS["C"], RDS_OFFSET_WORDS["D"])
+        for w, o in zip((a, b, c, d), offs):
+            word = ((int(w) & 0xFFFF) << 10) | rds_checkword(w, o)
+            out.extend((word >> k) & 1 for k in range(25, -1, -1))
+    return np.array(out, dtype=np.uint8)
+
+
+def batch_stream(s, n, fs=INPUT_RATE, amp=0.5, snr_db=40.0, with_rds=True, rds_bits=None):
+    """config 5, stream s: config-2 MPX with tone 400+10·s Hz, RDS bits from rng(2000+s) (or `rds_bits`, repeated)."""
     rng = np.random.default_rng(2000 + s)
     bits = rng.integers(0, 2, size=4096) if with_rds else None
+    if rds_bits is not None:
+        bits = np.asarray(rds_bits)
     mpx = stereo_mpx(n, fs, left_hz=400.0 + 10.0 * s, right_hz=None, rds_bits=bits)
     x = fm_modulate(mpx, fs, amp=amp, phase0=0.1 * s)
     return (x + _awgn(rng, n, amp, snr_db)).astype(np.complex64)

@@ -57,7 +57,7 @@ def test_bad_arguments(pkg):
     L = pkg.lib()
     st = C.c_int(0)
     assert not L.sdrjfm_create(None, C.byref(st)) and st.value == pkg.ERR_ARG
-    cfg = pkg.Config(1920000, 192000, 48000, 48000, 1, 0, 1000, 0, 0)   # colibri's rate: stage 2 would decimate by 1
+    cfg = pkg.Config(1000000, 192000, 48000, 48000, 1, 0, 1000, 0, 0)   # below 6 x fmRate: the reference's stage 1 alone would undershoot the fm rate
     assert not L.sdrjfm_create(C.byref(cfg), C.byref(st)) and st.value == pkg.ERR_UNSUPPORTED
     assert L.sdrjfm_design_tables(100, 192000, 0, 0, None, 0) == pkg.ERR_ARG
 
@@ -172,3 +172,20 @@ def test_second_converter_design(pkg):
         assert (int(t[0]), int(t[1])) == (L, M)
         h = t[2:].reshape(32, L).astype(np.float64)          # h [j * L + p]
         assert np.allclose(h.sum(axis=0), 1.0, atol=1e-6)
+
+
+def test_rds_group_bits_pass_the_reference_synchroniser(signals, chainlib, ref_available):
+    """the test signal of the RDS_3 symbol stage carries checkwords the reference's own rdsBlockSynchronizer accepts
+    (IEC 62106 generator polynomial and offset words, version A and B groups): every group comes back, in order."""
+    if not ref_available:
+        pytest.skip("oracle/_ref not available")
+    rng = np.random.default_rng(8)
+    groups = [(0xABCD, ((i % 16) << 12) | ((i & 1) << 11) | (i & 0x1F), int(rng.integers(0, 65536)), int(rng.integers(0, 65536)))
+              for i in range(25)]
+    bits = np.concatenate([rng.integers(0, 2, 41).astype(np.uint8), signals.rds_group_bits(groups)])
+    got = chainlib.ref_blocksync_groups(bits)
+    assert [tuple(int(v) for v in g) for g in got] == groups
+    # one flipped payload bit: the synchroniser drops that group (the burst correction's verdict is not used) and re-locks
+    bad = bits.copy(); bad[41 + 104 * 10 + 30] ^= 1
+    got = chainlib.ref_blocksync_groups(bad)
+    assert 20 <= len(got) < 25 and all(tuple(int(v) for v in g) in groups for g in got)

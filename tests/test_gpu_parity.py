@@ -712,7 +712,7 @@ def test_rds_symbol_stage_matches_reference(pkg, signals, chainlib, ref_availabl
     signal, slope detector); mode 2 (:84-88): rdsDecoder_2 (45-tap root-raised-cosine matched filter, AGC,
     Mueller & Mueller timing recovery, Costas loop on the symbols).  Checker: the reference's own classes fed with
     the GPU's 24 kHz baseband; the differentially decoded bit stream must be the reference's, and it must be the
-    transmitted one.  (Mode 3 takes its re-synchronisation from the block synchroniser: host side.)"""
+    transmitted one.  (Mode 3: test_rds3_symbol_stage_and_block_synchroniser_match_reference.)"""
     if not ref_available:
         pytest.skip("oracle/_ref not available")
     n = N1 * 3
@@ -729,8 +729,6 @@ def test_rds_symbol_stage_matches_reference(pkg, signals, chainlib, ref_availabl
         _, r = p.process(x[pos:pos + c])
         rds.append(r[0]); bits.append(p.read_rds_bits(0))
         pos += c
-    with pytest.raises(pkg.SdrjfmError):
-        p.setfmRdsSelector(3)                    # the GPU symbol stage covers modes 1 and 2
     p.close()
     rds, bits = np.concatenate(rds), np.concatenate(bits)
     ref = (chainlib.Rds1() if mode == 1 else chainlib.Rds2()).process(rds)
@@ -752,6 +750,53 @@ def test_rds_symbol_stage_matches_reference(pkg, signals, chainlib, ref_availabl
     tail = bits[-600:]
     best = max(int(np.sum(tail == np.roll(np.tile(tx, 2), -k)[:600])) for k in range(4096))
     assert best >= 590, best
+
+
+@pytest.mark.parametrize("chunks", [None, [16384 * 30 + 5, 16384, N1, N1 + 7]])
+def test_rds3_symbol_stage_and_block_synchroniser_match_reference(pkg, signals, chainlib, ref_available, chunks):
+    """SURVEY.md §8(f) rank 2, mode RDS_3 (rds-decoder.cpp:90-98): the Costas loop + rdsDecoder_3, whose bit clock is
+    re-synchronised whenever the block synchroniser has counted more than three sync errors (rds-decoder-3.cpp:91-96) —
+    so rdsBlockSynchronizer::pushBit and rdsDecoder::processBit run on the device as well.  The signal carries valid
+    groups (checkwords, version A and B), then eight valid A blocks each followed by garbage (one sync error apiece,
+    which forces a re-synchronisation), then valid groups again.  Checker: the reference's own Costas, rdsDecoder_3,
+    rdsBlockSynchronizer and RDSGroup fed with the GPU's 24 kHz baseband: bits, completed groups and the number of
+    bit-clock re-synchronisations must be the reference's, and the groups must be the transmitted ones."""
+    if not ref_available:
+        pytest.skip("oracle/_ref not available")
+    n = N1 * 4
+    rng = np.random.default_rng(31)
+    mk = lambda i: (0x2468, ((i % 16) << 12) | ((i & 1) << 11) | (i * 37 & 0x7FF), int(rng.integers(0, 65536)), int(rng.integers(0, 65536)))
+    g1 = [mk(i) for i in range(12)]
+    g2 = [mk(100 + i) for i in range(40)]
+    junk = []
+    for k in range(8):
+        junk.append(signals.rds_group_bits([(0x1111 * (k + 1), 0, 0, 0)])[:26])
+        junk.append(rng.integers(0, 2, 26).astype(np.uint8))
+    bits_tx = np.concatenate([signals.rds_group_bits(g1)] + junk + [signals.rds_group_bits(g2)])
+    x = signals.batch_stream(3, n, rds_bits=bits_tx)
+    p = pkg.FmProcessorB200(n_streams=1, max_samples_per_call=max(chunks) if chunks else n)
+    p.configure(fm_mode=0, rds_on=3, volume_db=-6.0)
+    p.setRdsSymbolStage(True)
+    rds, bits, groups, resyncs = [], [], [], 0
+    pos, k = 0, 0
+    while pos < n:
+        c = (chunks[k % len(chunks)] if chunks else n)
+        _, r = p.process(x[pos:pos + c])
+        rds.append(r[0]); bits.append(p.read_rds_bits(0))
+        g, st = p.read_rds_groups(0)
+        groups.append(g); resyncs += st["bitclk_resyncs"]
+        pos += c; k += 1
+    p.close()
+    rds, bits, groups = np.concatenate(rds), np.concatenate(bits), np.concatenate(groups)
+    rbits, rgroups, rres = chainlib.Rds3().process(rds)
+    print("bits", len(bits), len(rbits), "groups", len(groups), len(rgroups), "bit-clock re-synchronisations", resyncs, rres,
+          "synchronised at the end", st["synchronized"])
+    assert len(bits) == len(rbits) and np.array_equal(bits, rbits)
+    assert groups.shape == rgroups.shape and np.array_equal(groups, rgroups)
+    assert resyncs == rres and resyncs >= 2          # the constructor's and at least one forced by the sync errors
+    sent = {tuple(g) for g in g1 + g2}
+    assert len(groups) >= 30 and all(tuple(int(v) for v in g) in sent for g in groups)
+    assert st["synchronized"] == 1
 
 
 def test_station_scan_matches_reference(pkg, signals, chainlib, ref_available):
