@@ -192,7 +192,7 @@ float vy = (u.y - ky) * P.rgain;
 // zabs: |z| ; fmz (optional): the fm-rate complex sample (tap after fmBand_2).
 // grid (tiles of kDiBlock samples, streams): every tile is independent given the snapshot and
 // the tile aggregates of the DC one-pole.
-__global__ void __launch_bounds__ (kDiThreads)
+__global__ void __launch_bounds__ (kDiThreads, 3)
 discriminator_kernel (const float2 *__restrict__ U, const float2 *__restrict__ Ssum,
                       int64_t pitch, int32_t M, DiscrParams P,
                       const float *__restrict__ atanPPY, const float *__restrict__ arcsine,

@@ -10,7 +10,8 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-pkg = importlib.import_module("sdr-j-fm_b200")
+from __graft_entry__ import load_package  # noqa: E402
+pkg = load_package()
 
 
 QUICK = os.environ.get('PROF_GUI_QUICK') == '1'
@@ -29,8 +30,8 @@ def med(f, n=300, skip=40):
 
 def main():
     N = 16384
-    rng = np.random.default_rng(1)
-    xs = (rng.standard_normal(N * 64) + 1j * rng.standard_normal(N * 64)).astype(np.complex64) * 0.3
+    sig = importlib.import_module("sdrjfm_b200.signals")
+    xs = sig.batch_stream(0, N * 64)
     g = pkg.FmProcessorB200(n_streams=1, max_samples_per_call=N, device=0, keep_taps=False)
     g.configure(fm_mode=0, decoder=3, rds_on=1, auto_mono=1, pss_on=1, dc_remove=1, deemph_us=50, volume_db=-6.0)
     ga = np.zeros((1, N // 48 + 2), np.complex64)
@@ -45,6 +46,7 @@ def main():
     l0 = g.launch_count
     out = {"host_pageable_ms": med(host)}
     out["launches_per_call"] = (g.launch_count - l0) / (30.0 if QUICK else 300.0)
+    out["pilot_stats_last_call(passes, worst, fallbacks, windows)"] = g.pilot_stats().reshape(-1)[:4].tolist()
     if QUICK:
         print(out)
         g.close()
