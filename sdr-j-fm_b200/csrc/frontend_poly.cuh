@@ -106,7 +106,7 @@ struct Poly {
 	static constexpr int SmemBytes = Rows * Pitch * (int)sizeof (float2);
 	static constexpr int Batch   = poly_batch (Rows);
 	static constexpr int RawBytes = TileOut * kRawSlots * (int)sizeof (float2);   // oscillator on: raw block-sum slots behind the tile
-	static constexpr int MinCtas = (200 * 1024) / (SmemBytes + 1024) > 4 ? 4 : (200 * 1024) / (SmemBytes + 1024);
+	static constexpr int MinCtas = (226 * 1024) / (SmemBytes + 1024) > 8 ? 8 : (226 * 1024) / (SmemBytes + 1024);
 	static_assert (D * NG <= kPolyMaxTaps, "tap table too small");
 	static_assert (Rows % Batch == 0, "batching");
 };

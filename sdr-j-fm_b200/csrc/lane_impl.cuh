@@ -63,7 +63,7 @@ static RawFmt make_rawfmt (const Lane *h, int32_t fmt, float scale);
 // front-end shapes: decimation, outputs per thread, tap groups narrow / with inputFilter
 struct FeShape { int D, gpt, ng, ngw; };
 static const FeShape kFeShapes [] = { { 12, 4, 4, 25 }, { 30, 2, 2, 11 }, { 48, 1, 2, 7 },
-                                      { kRsStageADecim, 8, 10, 0 } };     // last: stage A of the rational resampler
+                                      { kRsStageADecim, 4, 10, 0 } };     // last: stage A of the rational resampler
 constexpr int kShapeResample = 3;
 constexpr int kShapeGeneric = 4;          // any other decimation 6 * D2: reference-order front end only (frontend_exact.cuh)
 constexpr int kInputFilterDelay = kInputFftSize - kInputDegree;       // 65285 input samples
@@ -779,7 +779,7 @@ cudaError_t e;
 	   case 0:  e = poly_attr_one<12, 4, 4> (); if (e == cudaSuccess) e = poly_attr_one<12, 4, 25> (); break;
 	   case 1:  e = poly_attr_one<30, 2, 2> (); if (e == cudaSuccess) e = poly_attr_one<30, 2, 11> (); break;
 	   case 2:  e = poly_attr_one<48, 1, 2> (); if (e == cudaSuccess) e = poly_attr_one<48, 1, 7> (); break;
-	   default: e = poly_attr_one<kRsStageADecim, 8, 10> (); break;
+	   default: e = poly_attr_one<kRsStageADecim, 4, 10> (); break;
 	}
 	return e;
 }
@@ -950,7 +950,7 @@ float2 *U = wide ? h -> d_Uw : h -> d_U, *Sb = wide ? h -> d_Sw : h -> d_S;
 	   case 3: poly_launch<30, 2, 11> (h, src, pitch, rf, hist, hlen, U, Sb, M, lp); break;
 	   case 4: poly_launch<48, 1, 2>  (h, src, pitch, rf, hist, hlen, U, Sb, M, lp); break;
 	   case 5: poly_launch<48, 1, 7> (h, src, pitch, rf, hist, hlen, U, Sb, M, lp); break;
-	   default: poly_launch<kRsStageADecim, 8, 10> (h, src, pitch, rf, hist, hlen, U, Sb, M, lp); break;
+	   default: poly_launch<kRsStageADecim, 4, 10> (h, src, pitch, rf, hist, hlen, U, Sb, M, lp); break;
 	}
 	h -> launches ++;
 	CK (cudaGetLastError ());

@@ -799,6 +799,37 @@ def test_rds3_symbol_stage_and_block_synchroniser_match_reference(pkg, signals, 
     assert st["synchronized"] == 1
 
 
+def test_rds3_streams_of_a_batch_keep_their_own_synchroniser(pkg, signals, chainlib, ref_available):
+    """mode RDS_3 on a batch: every stream carries its own decoder and block-synchroniser state (one with valid groups,
+    one with random bits — no group may come out of it —, one with other groups); each equals the reference's classes
+    fed with that stream's baseband."""
+    if not ref_available:
+        pytest.skip("oracle/_ref not available")
+    n = N1 * 2
+    rng = np.random.default_rng(77)
+    mk = lambda i: (0x1357 + i, ((i % 16) << 12) | (i * 53 & 0x7FF), int(rng.integers(0, 65536)), int(rng.integers(0, 65536)))
+    ga, gc = [mk(i) for i in range(30)], [mk(200 + i) for i in range(30)]
+    tx = [signals.rds_group_bits(ga), rng.integers(0, 2, 3000).astype(np.uint8), signals.rds_group_bits(gc)]
+    x = np.stack([signals.batch_stream(s, n, rds_bits=tx[s]) for s in range(3)])
+    p = pkg.FmProcessorB200(n_streams=3, max_samples_per_call=N1)
+    p.configure(fm_mode=0, rds_on=3, volume_db=-6.0)
+    p.setRdsSymbolStage(True)
+    rds, bits, groups = [[] for _ in range(3)], [[] for _ in range(3)], [[] for _ in range(3)]
+    for pos in range(0, n, N1):
+        _, r = p.process(x[:, pos:pos + N1])
+        for s in range(3):
+            rds[s].append(r[s]); bits[s].append(p.read_rds_bits(s)); groups[s].append(p.read_rds_groups(s)[0])
+    p.close()
+    for s in range(3):
+        rb, rg, _ = chainlib.Rds3().process(np.concatenate(rds[s]))
+        b, g = np.concatenate(bits[s]), np.concatenate(groups[s])
+        print("stream", s, "bits", len(b), "groups", len(g), len(rg))
+        assert np.array_equal(b, rb) and g.shape == rg.shape and np.array_equal(g, rg)
+    assert len(np.concatenate(groups[0])) >= 10 and len(np.concatenate(groups[2])) >= 10
+    assert {tuple(int(v) for v in g) for g in np.concatenate(groups[0])} <= set(ga)
+    assert {tuple(int(v) for v in g) for g in np.concatenate(groups[2])} <= set(gc)
+
+
 def test_station_scan_matches_reference(pkg, signals, chainlib, ref_available):
     """startScanning (fm-processor.cpp:478-495): no demodulation, per 1024 fm-rate samples an FFT and
     the carrier-level / band-edge-level pair; blocks run across call boundaries; a station is found
