@@ -119,29 +119,55 @@ def host_topology(index):
 
 
 class ClockSampler:
-    """samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """samples SM clocks / throttle reasons during the timed region: through NVML in this process (what nvidia-smi
+    reads; no process is spawned while the GPUs are being timed), else with the recipe's looping nvidia-smi."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    # nvmlClocksEventReason bits (nvml.h): SwPowerCap 0x4, HwSlowdown 0x8, SwThermalSlowdown 0x20, HwThermalSlowdown 0x40
+    BITS = (0x8, 0x40, 0x20, 0x4)
 
-    def __init__(self, indices, period=0.2):
-        """indices: the GPUs of this job.  ONE sampler per job (rank 0) polls all of them in one nvidia-smi call:
-        eight ranks polling five times a second each put 40 nvidia-smi processes per second on the host, which
-        showed as a 10 % slower slowest rank at N=8 (profiles/r2_summary.md)."""
+    def __init__(self, indices, period=0.1):
+        """indices: the GPUs of this job.  ONE sampler per job (rank 0) reads all of them: eight ranks each starting
+        an nvidia-smi five times a second showed as a 10 % slower slowest rank at N=8, one rank doing so as 7 %
+        (every new nvidia-smi attaches to all eight GPUs while they are timed; profiles/r2_summary.md)."""
         self.indices, self.rows, self.stop, self.period = list(indices), [], threading.Event(), period
+        self.source, self.nvml, self.handles, self.proc = "nvidia-smi -lms", None, [], None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handles = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in self.indices]
+            self.nvml, self.source = pynvml, "nvml"
+        except Exception:
+            self.nvml = None
         self.t = threading.Thread(target=self.run, daemon=True)
 
     def run(self):
-        while not self.stop.is_set():
+        if self.nvml is None:
+            # the recipe's form: ONE nvidia-smi that stays attached and prints a row per GPU every period
             try:
-                out = subprocess.run(["nvidia-smi", "-i", ",".join(str(i) for i in self.indices), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True,
-                                     text=True, timeout=5).stdout.strip()
-                for ln in out.splitlines():
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", ",".join(str(i) for i in self.indices),
+                                              f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                              "-lms", str(int(self.period * 1000))], stdout=subprocess.PIPE, text=True)
+                for ln in self.proc.stdout:
                     if ln.strip():
                         self.rows.append([c.strip() for c in ln.split(",")])
+                    if self.stop.is_set():
+                        break
             except Exception:
                 pass
+            return
+        n = self.nvml
+        reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop.is_set():
+            for h in self.handles:
+                try:
+                    r = int(reasons(h))
+                    self.rows.append([str(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)),
+                                      str(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM))] +
+                                     ["Active" if r & b else "Not Active" for b in self.BITS])
+                except Exception:
+                    pass
             self.stop.wait(self.period)
 
     def __enter__(self):
@@ -150,6 +176,11 @@ class ClockSampler:
 
     def __exit__(self, *a):
         self.stop.set()
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
         self.t.join(timeout=6)
 
     def summary(self):
@@ -163,7 +194,7 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": int(np.median(sm)) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(self.rows)}
+                "samples": len(self.rows), "sm_mhz_min": min(sm) if sm else None, "source": self.source}
 
 
 def gen_batch_gpu(torch, dev, n_streams, n, stream0=0, group=16):
