@@ -127,12 +127,14 @@ class ClockSampler:
     # nvmlClocksEventReason bits (nvml.h): SwPowerCap 0x4, HwSlowdown 0x8, SwThermalSlowdown 0x20, HwThermalSlowdown 0x40
     BITS = (0x8, 0x40, 0x20, 0x4)
 
-    def __init__(self, indices, period=0.1):
+    def __init__(self, indices, period=None):
         """indices: the GPUs of this job.  ONE sampler per job (rank 0) reads all of them: eight ranks each starting
         an nvidia-smi five times a second showed as a 10 % slower slowest rank at N=8, one rank doing so as 7 %
         (every new nvidia-smi attaches to all eight GPUs while they are timed; profiles/r2_summary.md)."""
         self.indices, self.rows, self.stop, self.period = list(indices), [], threading.Event(), period
+        self.win = None
         self.source, self.nvml, self.handles, self.proc = "nvidia-smi -lms", None, [], None
+        self.per_gpu = {}
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -140,7 +142,18 @@ class ClockSampler:
             self.nvml, self.source = pynvml, "nvml"
         except Exception:
             self.nvml = None
+        if self.period is None:
+            self.period = 0.02 if self.nvml is not None else 0.2
         self.t = threading.Thread(target=self.run, daemon=True)
+
+    def window_begin(self):
+        """the device-resident timed steps (`value`): per-GPU figures are kept for this window alone as well"""
+        self.win = {gi: len(self.per_gpu.get(gi, {"sm": []})["sm"]) for gi in self.indices}
+
+    def window_end(self):
+        if self.win is not None:
+            # (a pass over eight GPUs takes NVML ~0.1 s under load: the samples next to the window count as well)
+            self.win = {gi: (max(a - 1, 0), len(self.per_gpu.get(gi, {"sm": []})["sm"]) + 1) for gi, a in self.win.items()}
 
     def run(self):
         if self.nvml is None:
@@ -160,12 +173,17 @@ class ClockSampler:
         n = self.nvml
         reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
         while not self.stop.is_set():
-            for h in self.handles:
+            for gi, h in zip(self.indices, self.handles):
                 try:
                     r = int(reasons(h))
-                    self.rows.append([str(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)),
-                                      str(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM))] +
+                    sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+                    self.rows.append([str(sm), str(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM))] +
                                      ["Active" if r & b else "Not Active" for b in self.BITS])
+                    g = self.per_gpu.setdefault(gi, {"sm": [], "mem": [], "w": [], "reasons": 0})
+                    g["sm"].append(sm)
+                    g["mem"].append(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_MEM))
+                    g["w"].append(n.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                    g["reasons"] |= r
                 except Exception:
                     pass
             self.stop.wait(self.period)
@@ -194,12 +212,29 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": int(np.median(sm)) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(self.rows), "sm_mhz_min": min(sm) if sm else None, "source": self.source}
+                "samples": len(self.rows), "sm_mhz_min": min(sm) if sm else None, "source": self.source,
+                # per GPU of the job: median / min SM clock, min memory clock, median / max board power, reason bits seen
+                "per_gpu": [{"gpu": gi, "sm_mhz": int(np.median(g["sm"])), "sm_mhz_min": int(min(g["sm"])),
+                             "mem_mhz_min": int(min(g["mem"])), "power_w": round(float(np.median(g["w"])), 1),
+                             "power_w_max": round(float(max(g["w"])), 1), "reason_bits": hex(g["reasons"])}
+                            for gi, g in sorted(self.per_gpu.items()) if g["sm"]],
+                # the same for the samples taken inside the device-resident timed steps only
+                "per_gpu_timed_steps": [{"gpu": gi, "samples": len(self.per_gpu[gi]["sm"][a:b]),
+                                         "sm_mhz_min": int(min(self.per_gpu[gi]["sm"][a:b])),
+                                         "mem_mhz_min": int(min(self.per_gpu[gi]["mem"][a:b])),
+                                         "power_w": round(float(np.median(self.per_gpu[gi]["w"][a:b])), 1),
+                                         "power_w_max": round(float(max(self.per_gpu[gi]["w"][a:b])), 1)}
+                                        for gi, (a, b) in sorted((self.win or {}).items())
+                                        if gi in self.per_gpu and self.per_gpu[gi]["sm"][a:b]]}
 
 
 def gen_batch_gpu(torch, dev, n_streams, n, stream0=0, group=16):
-    """config-5 style IQ on the GPU: stream s = stereo MPX, L tone 400+10 s Hz, 10 % pilot,
-    57 kHz BPSK-like RDS sub-carrier, 75 kHz deviation, amp 0.5, AWGN 40 dB (seeded)."""
+    """config-5 style IQ on the GPU: stream s = stereo MPX, L tone 400 + 10 (s mod 256) Hz, 10 % pilot,
+    57 kHz BPSK-like RDS sub-carrier, 75 kHz deviation, amp 0.5, AWGN 40 dB (seeded).
+    The tone wraps at BASELINE config 5's 256 streams: with the global stream index in it, rank 7 of an 8-GPU
+    weak-scaling run got audio tones of 18.3-20.9 kHz — on top of the 19 kHz pilot, where the pilot PLL solver needs
+    more passes — and set the job's `value` 7 % below the other ranks (profiles/r2_summary.md, "N = 8").  Phase, noise
+    and RDS bits stay per global stream."""
     out = torch.empty((n_streams, n), dtype=torch.complex64, device=dev)
     t = torch.arange(n, dtype=torch.float64, device=dev) / INPUT_RATE
     th = 2 * np.pi * 19000.0 * t
@@ -208,7 +243,7 @@ def gen_batch_gpu(torch, dev, n_streams, n, stream0=0, group=16):
     for s0 in range(0, n_streams, group):
         ss = torch.arange(s0, min(s0 + group, n_streams), device=dev, dtype=torch.float64)
         sid = ss + stream0
-        L = torch.sin(2 * np.pi * (400.0 + 10.0 * sid)[:, None] * t[None, :])
+        L = torch.sin(2 * np.pi * (400.0 + 10.0 * torch.remainder(sid, 256.0))[:, None] * t[None, :])
         g.manual_seed(2000 + int(sid[0].item()))
         bits = torch.randint(0, 2, (len(ss), 4096), device=dev, generator=g)
         d = torch.cumsum(bits, dim=1) & 1
@@ -461,10 +496,14 @@ def main():
     l0 = proc.launch_count
     # clocks / throttle reasons are sampled over ALL timed regions of this run (device-resident steps,
     # front-end kernel alone, end-to-end steps); the sampler is stopped before the CPU baseline leg
-    clk = ClockSampler(range(world) if world > 1 else [local], period=0.2 if world == 1 else 0.5)
+    clk = ClockSampler(range(world) if world > 1 else [local])
     if rank == 0:
         clk.__enter__()
+        time.sleep(0.05)                  # (a first sample of every GPU before the steps start)
+        clk.window_begin()
     ms = timed(step_device, args.steps)
+    if rank == 0:
+        clk.window_end()
     per_rank_ms = [v / args.steps for v in timed.per_rank]
     launches = proc.launch_count - l0
     value = world * S * n * args.steps / (ms * 1e-3) / 1e6

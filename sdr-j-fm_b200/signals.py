@@ -100,12 +100,13 @@ def rds_group_bits(groups):
 
 
 def batch_stream(s, n, fs=INPUT_RATE, amp=0.5, snr_db=40.0, with_rds=True, rds_bits=None):
-    """config 5, stream s: config-2 MPX with tone 400+10·s Hz, RDS bits from rng(2000+s) (or `rds_bits`, repeated)."""
+    """config 5, stream s: config-2 MPX with tone 400 + 10·(s mod 256) Hz (the 256 streams of the config; beyond them the
+    tones repeat instead of climbing into the pilot), RDS bits from rng(2000+s) (or `rds_bits`, repeated)."""
     rng = np.random.default_rng(2000 + s)
     bits = rng.integers(0, 2, size=4096) if with_rds else None
     if rds_bits is not None:
         bits = np.asarray(rds_bits)
-    mpx = stereo_mpx(n, fs, left_hz=400.0 + 10.0 * s, right_hz=None, rds_bits=bits)
+    mpx = stereo_mpx(n, fs, left_hz=400.0 + 10.0 * (s % 256), right_hz=None, rds_bits=bits)
     x = fm_modulate(mpx, fs, amp=amp, phase0=0.1 * s)
     return (x + _awgn(rng, n, amp, snr_db)).astype(np.complex64)
 
