@@ -143,7 +143,7 @@ class ClockSampler:
         except Exception:
             self.nvml = None
         if self.period is None:
-            self.period = 0.02 if self.nvml is not None else 0.2
+            self.period = 0.05 if self.nvml is not None else 0.2
         self.t = threading.Thread(target=self.run, daemon=True)
 
     def window_begin(self):
