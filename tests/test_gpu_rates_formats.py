@@ -29,10 +29,11 @@ def checker(chainlib, ref_available):
 TAPS = ("fm_z", "demod", "pilot_phase", "locked", "lr", "audio192")
 
 
-def run_gpu(pkg, x, input_rate, chunks=None, raw=None, **cfg):
+def run_gpu(pkg, x, input_rate, chunks=None, raw=None, front_end_mode=0, **cfg):
     """x: complex64 [n] (raw=None) or component array [n, 2] with raw=(fmt, denominator)."""
     n = x.shape[0]
-    p = pkg.FmProcessorB200(n_streams=1, input_rate=input_rate, max_samples_per_call=max(chunks) if chunks else n)
+    p = pkg.FmProcessorB200(n_streams=1, input_rate=input_rate, max_samples_per_call=max(chunks) if chunks else n,
+                            front_end_mode=front_end_mode)
     p.configure(**cfg)
     taps = {k: [] for k in TAPS}
     audio, rds = [], []
@@ -367,3 +368,24 @@ def test_any_input_rate_of_the_reference_arithmetic(pkg, signals, checker, fs, c
         assert np.array_equal(got["fm_z"].view(np.uint32), ref["fm_z"].view(np.uint32))
     assert rms(got["demod"] - ref["demod"]) < 1e-5 and rms(got["audio192"] - ref["audio192"]) < 1e-5
     assert np.array_equal(got["locked"], ref["locked"])
+
+
+@pytest.mark.parametrize("fmt,fs", [("u8", 2304000), ("s16/4096", 6000000), ("s8", 3200000)])
+def test_reference_order_front_end_reads_device_formats(pkg, signals, checker, fmt, fs):
+    """front_end_mode 2 (K1x: the reference's per-sample DC recurrence and tap-by-tap decimators) on the device's own
+    bytes: bit-identical to the same stream handed over as the handler's floats, and fm_z bit-identical to the
+    reference's classes fed with those floats (3.2 MS/s is a rate only this front end serves)."""
+    D = pkg.front_end_decimation(fs)
+    n = D * 60000 + 5
+    x = signals.dc_offset(signals.stereo_pilot(n, fs=192000 * D, amp=0.7))
+    raw, xf, den = _quantise(x, fmt)
+    cfg = dict(fm_mode=0, volume_db=0.0)
+    chunks = [16384, 7, n // 2, n]
+    a = run_gpu(pkg, raw, fs, chunks=chunks, raw=(fmt.split("/")[0], den), front_end_mode=2, **cfg)
+    b = run_gpu(pkg, xf, fs, chunks=chunks, front_end_mode=2, **cfg)
+    for k in ("fm_z", "demod", "audio192"):
+        assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), k
+    ref = checker(input_rate=fs, **cfg).process(xf)
+    m = min(len(a["fm_z"]), len(ref["fm_z"]))
+    assert m == len(ref["fm_z"]) and np.array_equal(a["fm_z"][:m].view(np.uint32), ref["fm_z"][:m].view(np.uint32))
+    assert rms(a["audio192"] - ref["audio192"]) < 1e-5
