@@ -306,6 +306,8 @@ def test_airspy_native_rate_conversion(pkg, signals, checker, monkeypatch, nativ
     ("resampler_2p4M", 2400000, 1, dict(fm_mode=0, rds_on=1), None),
     ("u8", 2304000, 0, dict(fm_mode=0, rds_on=1), ("u8", 128)),
     ("squelch_audio_lp", 2304000, 0, dict(fm_mode=0, rds_on=1, squelch_mode=1, squelch_value=50, lf_cutoff_hz=15000), None),
+    ("rds_mode_2", 2304000, 0, dict(fm_mode=0, rds_on=2), None),
+    ("rds_mode_3", 2304000, 0, dict(fm_mode=0, rds_on=3), None),
 ])
 def test_copies_of_a_stream_are_bit_identical_across_lanes(pkg, signals, name, rate, mode, cfg, raw):
     """determinism under concurrency: 130 streams (4 lanes, RDS side streams) carrying two distinct
