@@ -729,6 +729,10 @@ def test_rds_symbol_stage_matches_reference(pkg, signals, chainlib, ref_availabl
         _, r = p.process(x[pos:pos + c])
         rds.append(r[0]); bits.append(p.read_rds_bits(0))
         pos += c
+    g, gst = p.read_rds_groups(0)                # groups only come out of mode 3 (the device-side block synchroniser)
+    assert len(g) == 0 and gst["bitclk_resyncs"] == 0
+    with pytest.raises(pkg.SdrjfmError):
+        p.read_rds_groups(5)
     p.close()
     rds, bits = np.concatenate(rds), np.concatenate(bits)
     ref = (chainlib.Rds1() if mode == 1 else chainlib.Rds2()).process(rds)
