@@ -202,7 +202,6 @@ struct Lane {
 	int32_t  air_blk = 0;                   // native samples per millisecond block (native rate / 1000)
 	int16_t *d_air_int = nullptr; float *d_air_frac = nullptr;
 	short2  *d_air_pend = nullptr; int air_pend = 0;      // [S][air_blk + 1] native samples carried to the next call
-	bool    pilot_lut_smem = false;         // SDRJFM_PILOT_LUT_SMEM=1: sine table in shared memory, 1 CTA/SM
 	bool    pilot_wide = false;             // SDRJFM_PILOT_WIDE=1: 1024 threads, 8192-sample windows (experiment: no gain, see lane_create)
 	bool    sequential_pll = false;         // SDRJFM_SEQUENTIAL_PLL=1: lane-per-stream K3 (cross-check)
 	int64_t fm_total = 0;                   // fm-rate samples produced so far (per stream)
@@ -503,10 +502,6 @@ const TableHeader &th = h -> tables.hdr ();
 	return SDRJFM_OK;
 }
 
-static const char *lane_last_error (const Lane *h) {
-	return h ? h -> err.c_str () : g_create_error.c_str ();
-}
-
 static Lane *lane_create (const sdrjfm_config *cfg, int *status) {
 int dummy; if (!status) status = &dummy;
 	*status = SDRJFM_ERR_ARG;
@@ -688,11 +683,6 @@ cudaError_t e;
 //	  measured (32 / 64 / 128 streams x 0.5 s): 1.496 / 1.773 / 2.703 ms against 1.499 / 1.778 / 2.566 ms for the
 //	  512-thread shape — one pass more per window and slower 32-warp scans eat what the wider pass gains: off by default
 	  h -> pilot_wide = env && env [0] == '1'; }
-//	the variant with the sine table staged in shared memory only fits with small windows
-	{ const char *env = getenv ("SDRJFM_PILOT_LUT_SMEM");
-	  h -> pilot_lut_smem = env && env [0] == '1' && kPiSmemBytes <= 227 * 1024 &&
-	        cudaFuncSetAttribute (pilot_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                              (int)kPiSmemBytes) == cudaSuccess; }
 	{ const char *env = getenv ("SDRJFM_SEQUENTIAL_PLL"); h -> sequential_pll = env && env [0] == '1'; }
 int rc = rebuild_tables (h);
 	if (rc != SDRJFM_OK) { g_create_error = h -> err; *status = rc; lane_destroy (h); return nullptr; }
@@ -1353,11 +1343,7 @@ const int dec = st.decoder == 2 ? 1 : st.decoder == 1 ? 2 : 0;
 	   PilotParams pp;
 	   pp.K_FM = sp.K_FM; pp.omega = sp.omega; pp.gain = sp.gain;
 	   pp.lock_half_rate = sp.lock_half_rate; pp.n_streams = S;
-	   if (h -> pilot_lut_smem)
-	      pilot_kernel<true><<<S, kPiThreads, kPiSmemBytes, ks>>> (
-	            (h -> d_res + o), (h -> d_zabs + o), h -> cap_fm, M, pp, h -> lut, h -> d_state,
-	            (h -> d_demod + o), (h -> d_phase + o), (h -> d_locked + o), h -> d_iter_stats, sl > 0 ? 1 : 0);
-	   else if (h -> pilot_wide)
+	   if (h -> pilot_wide)
 	      pilot_kernel<false, kPiThreadsWide><<<S, kPiThreadsWide, sizeof (PilotSmemT<kPiThreadsWide>), ks>>> (
 	            (h -> d_res + o), (h -> d_zabs + o), h -> cap_fm, M, pp, h -> lut, h -> d_state,
 	            (h -> d_demod + o), (h -> d_phase + o), (h -> d_locked + o), h -> d_iter_stats, sl > 0 ? 1 : 0);

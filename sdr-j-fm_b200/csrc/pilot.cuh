@@ -155,8 +155,9 @@ pilot_kernel (const float *__restrict__ res_raw, const float *__restrict__ zabs,
               float *__restrict__ demod_out, float *__restrict__ phase_out,
               uint8_t *__restrict__ locked_out, int32_t *__restrict__ iter_stats, int accumulate) {
 extern __shared__ __align__ (16) unsigned char smem_raw [];
-// LUT_SMEM: the quarter-wave sine table is staged in shared memory (one CTA per SM).  Otherwise it is
-// read through L1 (192 KB, read-only path), which leaves room for two CTAs per SM.
+// LUT_SMEM: the quarter-wave sine table staged in shared memory (192 KB: only fits with windows of <= 2048 samples, a
+// shape no launch uses any more).  Otherwise it is read through L1, which leaves room for two CTAs per SM; folding the
+// table to a quarter of its footprint moved the step by < 1 % (profiles/r2_summary.md), so the look-up is not the limiter.
 const float *sq = LUT_SMEM ? reinterpret_cast<const float *>(smem_raw) : L.q;
 constexpr int kPiThreads = THREADS, kPiWin = THREADS * kPiPer, kPiMaxSeg = PilotSmemT<THREADS>::MaxSeg, kPiWarps = THREADS / 32;
 PilotSmemT<THREADS> &S = *reinterpret_cast<PilotSmemT<THREADS> *>(smem_raw + (LUT_SMEM ? kPiLutBytes : 0));
