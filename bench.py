@@ -118,6 +118,14 @@ def host_topology(index):
     return info
 
 
+def visible_to_physical(indices, env=None):
+    """CUDA device ordinals of this process -> what NVML / nvidia-smi call the same boards: the entries of
+    CUDA_VISIBLE_DEVICES (physical indices or GPU-... UUIDs) when it is set, the ordinals themselves otherwise."""
+    cvd = (os.environ if env is None else env).get("CUDA_VISIBLE_DEVICES", "")
+    toks = [t.strip() for t in cvd.split(",") if t.strip()]
+    return [toks[i] if i < len(toks) else str(i) for i in indices] if toks else [str(i) for i in indices]
+
+
 class ClockSampler:
     """samples SM clocks / throttle reasons during the timed region: through NVML in this process (what nvidia-smi
     reads; no process is spawned while the GPUs are being timed), else with the recipe's looping nvidia-smi."""
@@ -135,10 +143,13 @@ class ClockSampler:
         self.win = None
         self.source, self.nvml, self.handles, self.proc = "nvidia-smi -lms", None, [], None
         self.per_gpu = {}
+        # CUDA ordinals -> the board NVML / nvidia-smi must be asked about (CUDA_VISIBLE_DEVICES may renumber or name them)
+        self.ids = visible_to_physical(self.indices)
         try:
             import pynvml
             pynvml.nvmlInit()
-            self.handles = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in self.indices]
+            self.handles = [pynvml.nvmlDeviceGetHandleByIndex(int(t)) if t.isdigit() else pynvml.nvmlDeviceGetHandleByUUID(t)
+                            for t in self.ids]
             self.nvml, self.source = pynvml, "nvml"
         except Exception:
             self.nvml = None
@@ -159,7 +170,7 @@ class ClockSampler:
         if self.nvml is None:
             # the recipe's form: ONE nvidia-smi that stays attached and prints a row per GPU every period
             try:
-                self.proc = subprocess.Popen(["nvidia-smi", "-i", ",".join(str(i) for i in self.indices),
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", ",".join(self.ids),
                                               f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                               "-lms", str(int(self.period * 1000))], stdout=subprocess.PIPE, text=True)
                 for ln in self.proc.stdout:
@@ -214,7 +225,7 @@ class ClockSampler:
                 "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
                 "samples": len(self.rows), "sm_mhz_min": min(sm) if sm else None, "source": self.source,
                 # per GPU of the job: median / min SM clock, min memory clock, median / max board power, reason bits seen
-                "per_gpu": [{"gpu": gi, "sm_mhz": int(np.median(g["sm"])), "sm_mhz_min": int(min(g["sm"])),
+                "per_gpu": [{"gpu": gi, "board": dict(zip(self.indices, self.ids)).get(gi), "sm_mhz": int(np.median(g["sm"])), "sm_mhz_min": int(min(g["sm"])),
                              "mem_mhz_min": int(min(g["mem"])), "power_w": round(float(np.median(g["w"])), 1),
                              "power_w_max": round(float(max(g["w"])), 1), "reason_bits": hex(g["reasons"])}
                             for gi, g in sorted(self.per_gpu.items()) if g["sm"]],
